@@ -1,0 +1,329 @@
+"""Deterministic synthetic DIA runs + spectral libraries (SURVEY.md §8d data model).
+
+The arrays produced here have *exactly* the layouts of the reference's raw-file
+views, so the same buffers feed the CUDA engine, the C oracle and (in this
+container only) the reference's numba classes:
+
+* 3-D (Thermo-shape) runs follow ``AlphaRawJIT``'s 15 fields
+  (reference ``alphadia/search/jitclasses/alpharaw_jit.py:78-138``, built at
+  ``alphadia/raw_data/alpharaw_wrapper.py:86-156``).
+* Libraries follow ``precursors_flat_schema`` / ``fragments_flat_schema``
+  (reference ``alphadia/validation/schemas.py:11-48``).
+
+Nothing here touches the oracle or the reference.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import pandas as pd
+
+ISOTOPE_MASS_DIFF = 1.0033548350700006  # reference selection/utils.py:35
+
+
+@dataclass
+class RawFile3D:
+    """Host-side 3-D raw file; attribute names mirror the reference's ``AlphaRaw``
+    wrapper (``raw_data/alpharaw_wrapper.py:22-71``) so either object can be
+    handed to the engine."""
+
+    cycle: np.ndarray  # f64 [1, L, 1, 2]
+    rt_values: np.ndarray  # f32 [n_spec], seconds
+    peak_start_idx_list: np.ndarray  # i64 [n_spec]
+    peak_stop_idx_list: np.ndarray  # i64 [n_spec]
+    mz_values: np.ndarray  # f32 [n_peaks] ascending within a spectrum
+    intensity_values: np.ndarray  # f32 [n_peaks]
+    mobility_values: np.ndarray = field(
+        default_factory=lambda: np.array([1e-6, 0], dtype=np.float32)
+    )
+    zeroth_frame: int = 0
+    scan_max_index: int = 1
+    has_mobility: bool = False
+    has_ms1: bool = True
+
+    @property
+    def cycle_len(self) -> int:
+        return int(self.cycle.shape[1])
+
+    @property
+    def precursor_cycle_max_index(self) -> int:
+        return len(self.rt_values) // self.cycle_len
+
+    @property
+    def frame_max_index(self) -> int:
+        return len(self.rt_values) - 1
+
+    @property
+    def n_peaks(self) -> int:
+        return int(self.mz_values.shape[0])
+
+    # scalars only used for bookkeeping in the reference (alpharaw_wrapper.py:95-108)
+    @property
+    def max_mz_value(self) -> np.float32:
+        return np.float32(self.cycle[self.cycle > 0].max()) if (self.cycle > 0).any() else np.float32(0)
+
+    @property
+    def min_mz_value(self) -> np.float32:
+        return np.float32(self.cycle[self.cycle > 0].min()) if (self.cycle > 0).any() else np.float32(0)
+
+
+def _float_sort_key(spec_idx: np.ndarray, mz: np.ndarray) -> np.ndarray:
+    """(spectrum, m/z) -> uint64 key; positive f32 bit patterns are monotone."""
+    return (spec_idx.astype(np.uint64) << np.uint64(32)) | mz.view(np.uint32).astype(
+        np.uint64
+    )
+
+
+def make_library(
+    n_precursors: int,
+    rng: np.random.Generator,
+    *,
+    quad_lo: float,
+    quad_hi: float,
+    rt_lo: float,
+    rt_hi: float,
+    n_fragments: int = 12,
+    n_isotopes: int = 4,
+    with_strings: bool = True,
+) -> tuple[pd.DataFrame, pd.DataFrame]:
+    """Flat spectral library (precursor_df, fragment_df), SURVEY §8d."""
+    P, F = n_precursors, n_fragments
+    idx = np.arange(P, dtype=np.uint32)
+    charge = rng.integers(2, 4, size=P).astype(np.uint8)
+    mz = rng.uniform(quad_lo + 1.0, quad_hi - 3.0, size=P).astype(np.float32)
+    rt = rng.uniform(rt_lo, rt_hi, size=P).astype(np.float32)
+    iso = np.array([0.5, 0.3, 0.15, 0.05], dtype=np.float32)[:n_isotopes]
+
+    prec = {
+        "elution_group_idx": idx.copy(),
+        "precursor_idx": idx.copy(),
+        "channel": np.zeros(P, dtype=np.uint32),
+        "decoy": (idx % 2).astype(np.uint8),
+        "flat_frag_start_idx": (idx * F).astype(np.uint32),
+        "flat_frag_stop_idx": ((idx + 1) * F).astype(np.uint32),
+        "charge": charge,
+        "rt_library": rt,
+        "mobility_library": np.zeros(P, dtype=np.float32),
+        "mz_library": mz,
+    }
+    for i in range(n_isotopes):
+        prec[f"i_{i}"] = np.full(P, iso[i], dtype=np.float32)
+    precursor_df = pd.DataFrame(prec)
+    if with_strings:
+        aa = np.array(list("ACDEFGHIKLMNPQRSTVWY"))
+        letters = aa[rng.integers(0, 20, size=(P, 9))]
+        seqs = np.array(["".join(r) for r in letters], dtype=object) if P <= 200_000 else None
+        if seqs is None:
+            # cheap path for multi-million libraries: a handful of distinct strings
+            pool = np.array(["".join(r) for r in aa[rng.integers(0, 20, size=(4096, 9))]], dtype=object)
+            seqs = pool[rng.integers(0, 4096, size=P)]
+        precursor_df["sequence"] = pd.Series(seqs, dtype=object)
+        for col in ("proteins", "genes"):
+            precursor_df[col] = pd.Series(np.full(P, "P0", dtype=object), dtype=object)
+        for col in ("mods", "mod_sites"):
+            precursor_df[col] = pd.Series(np.full(P, "", dtype=object), dtype=object)
+
+    fmz = rng.uniform(200.0, 1800.0, size=P * F).astype(np.float32)
+    fint = rng.uniform(0.05, 1.0, size=P * F).astype(np.float32)
+    ftype = np.where(rng.integers(0, 2, size=P * F) == 0, 98, 121).astype(np.uint8)
+    fragment_df = pd.DataFrame(
+        {
+            "mz_library": fmz,
+            "intensity": fint,
+            "cardinality": np.ones(P * F, dtype=np.uint8),
+            "type": ftype,
+            "loss_type": np.zeros(P * F, dtype=np.uint8),
+            "charge": np.ones(P * F, dtype=np.uint8),
+            "number": rng.integers(1, 20, size=P * F).astype(np.uint8),
+            "position": rng.integers(1, 20, size=P * F).astype(np.uint8),
+        }
+    )
+    return precursor_df, fragment_df
+
+
+def make_run_3d(
+    precursor_df: pd.DataFrame,
+    fragment_df: pd.DataFrame,
+    rng: np.random.Generator,
+    *,
+    n_cycles: int,
+    n_windows: int,
+    quad_lo: float,
+    quad_hi: float,
+    cycle_seconds: float,
+    n_noise_ms2: int,
+    n_noise_ms1: int,
+    planted_fraction: float = 0.5,
+    max_planted: int | None = None,
+    elution_sigma: float = 3.0,
+    rt_jitter: float = 5.0,
+) -> tuple[RawFile3D, np.ndarray]:
+    """Thermo-shape run: every cycle = 1 MS1 + ``n_windows`` MS2 spectra.
+
+    Returns the raw file and the apex RT planted for each precursor (NaN = not planted).
+    """
+    L = n_windows + 1
+    n_spec = n_cycles * L
+    width = (quad_hi - quad_lo) / n_windows
+    cycle = np.zeros((1, L, 1, 2), dtype=np.float64)
+    cycle[0, 0, 0, :] = -1.0
+    cycle[0, 1:, 0, 0] = quad_lo + width * np.arange(n_windows)
+    cycle[0, 1:, 0, 1] = quad_lo + width * (np.arange(n_windows) + 1)
+
+    rt_values = (np.arange(n_spec, dtype=np.float64) * (cycle_seconds / L)).astype(np.float32)
+    is_ms1 = (np.arange(n_spec) % L) == 0
+    n_noise = np.where(is_ms1, n_noise_ms1, n_noise_ms2).astype(np.int64)
+
+    # ---- noise: per-spectrum sorted m/z -------------------------------------------------
+    total_noise = int(n_noise.sum())
+    spec_of_noise = np.repeat(np.arange(n_spec, dtype=np.int64), n_noise)
+    noise_mz = rng.uniform(150.0, 1900.0, size=total_noise).astype(np.float32)
+    noise_int = rng.exponential(200.0, size=total_noise).astype(np.float32) + np.float32(1.0)
+
+    # ---- planted signal -----------------------------------------------------------------
+    P = len(precursor_df)
+    decoy = precursor_df["decoy"].values
+    targets = np.flatnonzero(decoy == 0)
+    n_plant = int(len(targets) * planted_fraction)
+    if max_planted is not None:
+        n_plant = min(n_plant, max_planted)
+    planted = np.sort(rng.choice(targets, size=n_plant, replace=False)) if n_plant else np.zeros(0, np.int64)
+    apex = np.full(P, np.nan, dtype=np.float64)
+    apex[planted] = precursor_df["rt_library"].values[planted] + rng.normal(0, rt_jitter, size=n_plant)
+
+    sig_spec, sig_mz, sig_int = [], [], []
+    if n_plant:
+        pmz = precursor_df["mz_library"].values.astype(np.float64)[planted]
+        pch = precursor_df["charge"].values.astype(np.float64)[planted]
+        window = np.clip(((pmz - quad_lo) // width).astype(np.int64), 0, n_windows - 1)
+        apex_cycle = apex[planted] / cycle_seconds
+        half = int(np.ceil(3.0 * elution_sigma / cycle_seconds))
+        offs = np.arange(-half, half + 1)
+        cyc = np.rint(apex_cycle)[:, None].astype(np.int64) + offs[None, :]  # (n_plant, W)
+        ok = (cyc >= 0) & (cyc < n_cycles)
+        cyc_c = np.clip(cyc, 0, n_cycles - 1)
+
+        # MS2: fragments in the precursor's window
+        fs = precursor_df["flat_frag_start_idx"].values[planted].astype(np.int64)
+        fe = precursor_df["flat_frag_stop_idx"].values[planted].astype(np.int64)
+        nf = int((fe - fs).max())
+        fmz_all = fragment_df["mz_library"].values
+        fint_all = fragment_df["intensity"].values
+        for k in range(nf):
+            has = (fs + k) < fe
+            fi = np.minimum(fs + k, len(fmz_all) - 1)
+            spec = cyc_c * L + 1 + window[:, None]
+            t = rt_values[spec].astype(np.float64)
+            shape = np.exp(-0.5 * ((t - apex[planted][:, None]) / elution_sigma) ** 2)
+            inten = shape * fint_all[fi][:, None] * 1e5
+            jit = 1.0 + rng.normal(0, 2e-6, size=spec.shape)
+            mzv = fmz_all[fi].astype(np.float64)[:, None] * jit
+            m = ok & has[:, None] & (inten > 1.0)
+            sig_spec.append(spec[m])
+            sig_mz.append(mzv[m].astype(np.float32))
+            sig_int.append(inten[m].astype(np.float32))
+        # MS1: isotopes
+        iso_cols = [c for c in precursor_df.columns if c.startswith("i_")]
+        for i, col in enumerate(iso_cols):
+            ab = precursor_df[col].values.astype(np.float64)[planted]
+            spec = cyc_c * L
+            t = rt_values[spec].astype(np.float64)
+            shape = np.exp(-0.5 * ((t - apex[planted][:, None]) / elution_sigma) ** 2)
+            inten = shape * ab[:, None] * 1e6
+            jit = 1.0 + rng.normal(0, 2e-6, size=spec.shape)
+            mzv = (pmz + i * ISOTOPE_MASS_DIFF / pch)[:, None] * jit
+            m = ok & (inten > 1.0)
+            sig_spec.append(spec[m])
+            sig_mz.append(mzv[m].astype(np.float32))
+            sig_int.append(inten[m].astype(np.float32))
+
+    if sig_spec:
+        all_spec = np.concatenate([spec_of_noise] + sig_spec)
+        all_mz = np.concatenate([noise_mz] + sig_mz)
+        all_int = np.concatenate([noise_int] + sig_int)
+    else:
+        all_spec, all_mz, all_int = spec_of_noise, noise_mz, noise_int
+    del spec_of_noise, noise_mz, noise_int, sig_spec, sig_mz, sig_int
+
+    order = np.argsort(_float_sort_key(all_spec, all_mz), kind="stable")
+    mz_values = np.ascontiguousarray(all_mz[order])
+    intensity_values = np.ascontiguousarray(all_int[order])
+    counts = np.bincount(all_spec, minlength=n_spec).astype(np.int64)
+    del order, all_spec, all_mz, all_int
+    stop = np.cumsum(counts)
+    start = stop - counts
+
+    raw = RawFile3D(
+        cycle=cycle,
+        rt_values=rt_values,
+        peak_start_idx_list=start.astype(np.int64),
+        peak_stop_idx_list=stop.astype(np.int64),
+        mz_values=mz_values,
+        intensity_values=intensity_values,
+    )
+    return raw, apex
+
+
+# --------------------------------------------------------------------------------------
+# The named configurations of BASELINE.json / SURVEY.md §8d
+# --------------------------------------------------------------------------------------
+CONFIGS_3D = {
+    # config 1: plumbing (reference-runnable on CPU)
+    "config1": dict(
+        seed=1, n_precursors=1000, n_cycles=50, n_windows=9, quad_lo=400.0, quad_hi=1200.0,
+        cycle_seconds=1.5, n_noise_ms2=200, n_noise_ms1=200, rt_tolerance=30.0,
+        planted_fraction=0.5, max_planted=None,
+    ),
+    # a mid-size case for parity tests (a few thousand candidates, C_sel = 64..)
+    "parity_small": dict(
+        seed=11, n_precursors=600, n_cycles=160, n_windows=12, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=1.0, n_noise_ms2=400, n_noise_ms1=800, rt_tolerance=25.0,
+        planted_fraction=0.6, max_planted=None,
+    ),
+    # config 2: 50k precursors, Thermo shape (91 200 spectra, ~1.4e8 peaks)
+    "config2": dict(
+        seed=2, n_precursors=50_000, n_cycles=1200, n_windows=75, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=1.0, n_noise_ms2=1500, n_noise_ms1=4000, rt_tolerance=100.0,
+        planted_fraction=0.5, max_planted=None,
+    ),
+    # config 3: 2M precursors, same frames
+    "config3": dict(
+        seed=3, n_precursors=2_000_000, n_cycles=1200, n_windows=75, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=1.0, n_noise_ms2=1500, n_noise_ms1=4000, rt_tolerance=100.0,
+        planted_fraction=0.5, max_planted=60_000,
+    ),
+    # config 5 (per file): 500k precursors
+    "config5": dict(
+        seed=50, n_precursors=500_000, n_cycles=1200, n_windows=75, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=1.0, n_noise_ms2=1500, n_noise_ms1=4000, rt_tolerance=100.0,
+        planted_fraction=0.5, max_planted=60_000,
+    ),
+}
+
+
+def make_config_3d(name: str, *, seed: int | None = None, n_precursors: int | None = None,
+                   with_strings: bool = True, scale_noise: float = 1.0):
+    """Build (raw, precursor_df, fragment_df, params) for a named 3-D configuration."""
+    p = dict(CONFIGS_3D[name])
+    if seed is not None:
+        p["seed"] = seed
+    if n_precursors is not None:
+        p["n_precursors"] = n_precursors
+    rng = np.random.default_rng(p["seed"])
+    run_s = p["n_cycles"] * p["cycle_seconds"]
+    margin = min(60.0, run_s * 0.15)
+    precursor_df, fragment_df = make_library(
+        p["n_precursors"], rng, quad_lo=p["quad_lo"], quad_hi=p["quad_hi"],
+        rt_lo=margin, rt_hi=run_s - margin, with_strings=with_strings,
+    )
+    raw, apex = make_run_3d(
+        precursor_df, fragment_df, rng,
+        n_cycles=p["n_cycles"], n_windows=p["n_windows"], quad_lo=p["quad_lo"], quad_hi=p["quad_hi"],
+        cycle_seconds=p["cycle_seconds"],
+        n_noise_ms2=int(p["n_noise_ms2"] * scale_noise), n_noise_ms1=int(p["n_noise_ms1"] * scale_noise),
+        planted_fraction=p["planted_fraction"], max_planted=p["max_planted"],
+    )
+    p["apex_rt"] = apex
+    return raw, precursor_df, fragment_df, p

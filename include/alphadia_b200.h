@@ -1,0 +1,225 @@
+/*
+ * alphadia_b200 — C ABI of the B200-native precursor-candidate hot path.
+ *
+ * This is the drop-in boundary: the three numba entry points of the reference
+ * become three blocking C calls on device-resident objects.  Plain pointers and sizes only;
+ * the caller owns every host buffer (in and out); the library copies in, never keeps a host
+ * pointer after return, and never calls back into the host language.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo root):
+ *   adb_rawfile3d_create   <- DiaData.to_jitclass() -> AlphaRawJIT(...)        alphadia/raw_data/alpharaw_wrapper.py:138-156,
+ *                                                                               alphadia/search/jitclasses/alpharaw_jit.py:98-138
+ *   adb_library_create     <- PrecursorFlatContainer / FragmentContainer       alphadia/search/selection/config_df.py:184-223,
+ *                                                                               alphadia/search/jitclasses/fragment_container.py:12-45
+ *   adb_select_candidates  <- _select_candidates_pjit(range(n), ...)           alphadia/search/selection/selection.py:78-203,656-666
+ *   adb_score_candidates   <- _process_score_groups(range(n), ...)             alphadia/search/scoring/scoring.py:114-137,633-643
+ *                             (Candidate.process                               alphadia/search/scoring/containers/candidate.py:166-481)
+ *   adb_fragment_competition <- _compete_for_fragments(np.arange(n_win), ...)  alphadia/fragcomp/fragcomp.py:51-143,275-289
+ *
+ * Error convention: every call returns 0 on success, non-zero otherwise; adb_last_error() then
+ * holds a message (thread-local).  Per-item failures follow the reference: the output row is left
+ * untouched (score == 0 / valid == 0) and the call still returns 0.
+ *
+ * Threading: one host thread per handle.  Kernels run on a per-handle CUDA stream; calls block
+ * until results are in the caller's host buffers.
+ */
+#ifndef ALPHADIA_B200_H
+#define ALPHADIA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADB_NUM_FEATURES 46 /* alphadia/constants/settings.py:5 */
+#define ADB_MAX_FRAGMENTS 32 /* hard cap on top_k_fragments handled on the device */
+#define ADB_MAX_ISOTOPES 8
+
+typedef struct adb_rawfile adb_rawfile_t; /* opaque, device resident */
+typedef struct adb_library adb_library_t; /* opaque, device resident */
+
+/* ---- raw file, 3-D (RT x m/z), AlphaRawJIT field for field ------------------------------- */
+typedef struct {
+  const double* cycle;               /* f64 [1, cycle_len, 1, 2]  (quad lower, upper); MS1 row = (-1,-1) */
+  int64_t cycle_len;                 /* L = spectra per DIA cycle */
+  const float* rt_values;            /* f32 [n_spectra], seconds */
+  int64_t n_spectra;
+  const float* mobility_values;      /* f32 [n_mobility]; 3-D files: {1e-6, 0} */
+  int64_t n_mobility;
+  const int64_t* peak_start_idx;     /* i64 [n_spectra] */
+  const int64_t* peak_stop_idx;      /* i64 [n_spectra] */
+  const float* mz_values;            /* f32 [n_peaks], ascending inside a spectrum */
+  const float* intensity_values;     /* f32 [n_peaks] */
+  int64_t n_peaks;
+  int64_t zeroth_frame;              /* 0/1 */
+  int64_t precursor_cycle_max_index; /* n_spectra / cycle_len */
+  int64_t scan_max_index;            /* 1 for 3-D files */
+  int64_t frame_max_index;           /* n_spectra - 1 */
+} adb_rawfile3d_desc;
+
+/* ---- spectral library (flat), precursors sorted by precursor_idx -------------------------- */
+typedef struct {
+  int64_t n_precursors;
+  const uint32_t* precursor_idx;   /* [P] */
+  const uint32_t* frag_start_idx;  /* [P] */
+  const uint32_t* frag_stop_idx;   /* [P] */
+  const uint8_t* charge;           /* [P] */
+  const float* rt;                 /* [P] rt_column      */
+  const float* mobility;           /* [P] mobility_column */
+  const float* mz;                 /* [P] precursor_mz_column */
+  const float* isotopes;           /* [P, n_isotopes] row-major (i_0 .. i_k) */
+  int32_t n_isotopes;
+  int64_t n_fragments;
+  const float* frag_mz_library;    /* [NF] */
+  const float* frag_mz;            /* [NF] fragment_mz_column */
+  const float* frag_intensity;     /* [NF] */
+  const uint8_t* frag_type;        /* [NF] 98 = b, 121 = y */
+  const uint8_t* frag_loss_type;   /* [NF] */
+  const uint8_t* frag_charge;      /* [NF] */
+  const uint8_t* frag_number;      /* [NF] */
+  const uint8_t* frag_position;    /* [NF] */
+  const uint8_t* frag_cardinality; /* [NF] */
+} adb_library_desc;
+
+/* ---- selection: CandidateSelectionConfigJIT (alphadia/search/selection/config_df.py:14-124) */
+typedef struct {
+  double rt_tolerance;
+  double precursor_mz_tolerance;
+  double fragment_mz_tolerance;
+  double mobility_tolerance;
+  int64_t candidate_count;
+  int64_t top_k_precursors;
+  int64_t top_k_fragments; /* carried, unused by the reference kernel too */
+  int32_t exclude_shared_ions;
+  int64_t kernel_size;
+  double f_mobility;
+  double f_rt;
+  double center_fraction;
+  int64_t min_size_mobility;
+  int64_t min_size_rt;
+  int64_t max_size_mobility;
+  int64_t max_size_rt;
+  int32_t use_weighted_score;
+  int32_t join_close_candidates;
+  double join_close_candidates_scan_threshold;
+  double join_close_candidates_cycle_threshold;
+  double feature_std;    /* feature_std[0]    */
+  double feature_mean;   /* feature_mean[0]   */
+  double feature_weight; /* feature_weight[0] */
+} adb_selection_config;
+
+/* CandidateContainer (config_df.py:226-254): n_precursors * candidate_count rows, caller-zeroed or not:
+ * the library zero-fills them first, exactly like CandidateContainer.__init__. */
+typedef struct {
+  int64_t n_rows;
+  uint32_t* precursor_idx;
+  uint8_t* rank;
+  float* score;
+  uint32_t* scan_center;
+  uint32_t* scan_start;
+  uint32_t* scan_stop;
+  uint32_t* frame_center;
+  uint32_t* frame_start;
+  uint32_t* frame_stop;
+} adb_candidates_out;
+
+/* ---- scoring: CandidateScoringConfigJIT (alphadia/search/scoring/config.py:13-65) -------- */
+typedef struct {
+  int32_t collect_fragments;
+  int32_t exclude_shared_ions;
+  uint32_t top_k_fragments;
+  uint32_t top_k_isotopes;
+  uint32_t quant_window;
+  int32_t quant_all;
+  float precursor_mz_tolerance;
+  float fragment_mz_tolerance;
+  int32_t experimental_xic;
+  /* SimpleQuadrupoleJit state (alphadia/search/scoring/quadrupole.py:58-78) */
+  double quad_sigma[2];
+  double quad_delta_mu[2];
+} adb_scoring_config;
+
+/* One row per candidate, in output order (= sorted by score_group_idx, precursor_idx). */
+typedef struct {
+  int64_t n;
+  const int64_t* lib_row; /* row of the candidate's precursor in adb_library_desc arrays */
+  const uint8_t* rank;
+  const int64_t* scan_start;
+  const int64_t* scan_stop;
+  const int64_t* scan_center;
+  const int64_t* frame_start;
+  const int64_t* frame_stop;
+  const int64_t* frame_center;
+} adb_candidates_in;
+
+/* OutputPsmDF (alphadia/search/scoring/output.py:18-70).  Fragment tables are [n, top_k_fragments]. */
+typedef struct {
+  float* features;   /* [n, 46] */
+  uint8_t* valid;    /* [n] */
+  float* fragment_mz_library;
+  float* fragment_mz;
+  float* fragment_mz_observed;
+  float* fragment_height;
+  float* fragment_intensity;
+  float* fragment_mass_error;
+  float* fragment_correlation;
+  uint8_t* fragment_position;
+  uint8_t* fragment_number;
+  uint8_t* fragment_type;
+  uint8_t* fragment_charge;
+  uint8_t* fragment_loss_type;
+} adb_scores_out;
+
+/* ---- entry points ------------------------------------------------------------------------- */
+const char* adb_last_error(void);
+const char* adb_version(void);
+int adb_device_count(void);
+
+int adb_rawfile3d_create(const adb_rawfile3d_desc* desc, int device, adb_rawfile_t** out);
+void adb_rawfile_destroy(adb_rawfile_t* raw);
+int64_t adb_rawfile_device_bytes(const adb_rawfile_t* raw);
+
+int adb_library_create(const adb_library_desc* desc, int device, adb_library_t** out);
+void adb_library_destroy(adb_library_t* lib);
+
+/* kernel: GaussianKernel.get_dense_matrix() output, f32 [kernel_h, kernel_w] (selection/kernel.py:141-218) */
+int adb_select_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_selection_config* cfg,
+                          const float* kernel, int32_t kernel_h, int32_t kernel_w,
+                          adb_candidates_out* out);
+
+int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scoring_config* cfg,
+                         const adb_candidates_in* cand, adb_scores_out* out);
+
+/* rt / fragment_mz are f32 when is_f64 == 0, f64 otherwise (the reference computes in the array dtype).
+ * valid: u8 [n_psm], in/out (the reference starts from all-true). */
+int adb_fragment_competition(int device, int64_t n_windows, const int64_t* window_start,
+                             const int64_t* window_stop, int64_t n_psm, const void* rt,
+                             const int64_t* frag_start_idx, const int64_t* frag_stop_idx,
+                             int64_t n_frag, const void* fragment_mz, int32_t is_f64,
+                             double rt_tol_seconds, double mass_tol_ppm, uint8_t* valid);
+
+/* ---- resident / staged variants used by bench.py and the sharded driver -------------------
+ * Same kernels; inputs already in HBM, outputs stay in HBM.  Timing with CUDA events on the
+ * handle's stream.  (Not needed by a reference-side binding.) */
+typedef struct adb_session adb_session_t;
+int adb_session_create(adb_rawfile_t* raw, adb_library_t* lib, adb_session_t** out);
+void adb_session_destroy(adb_session_t* s);
+/* upload configs + kernel, allocate device outputs for n_precursors*candidate_count rows */
+int adb_session_prepare_selection(adb_session_t* s, const adb_selection_config* cfg, const float* kernel,
+                                  int32_t kernel_h, int32_t kernel_w);
+/* run selection on device; device-side compaction (score > 0) feeds scoring; returns #candidates */
+int adb_session_run_selection(adb_session_t* s, int64_t* n_candidates, float* elapsed_ms);
+int adb_session_prepare_scoring(adb_session_t* s, const adb_scoring_config* cfg);
+int adb_session_run_scoring(adb_session_t* s, float* elapsed_ms);
+/* copy the device-resident results to host buffers (n rows as returned by run_selection) */
+int adb_session_fetch_candidates(adb_session_t* s, adb_candidates_out* out, int64_t* lib_row);
+int adb_session_fetch_scores(adb_session_t* s, adb_scores_out* out);
+/* device pointer + byte size of the packed score table [n, 46] f32 (for the NCCL all-gather) */
+int adb_session_score_table(adb_session_t* s, void** dev_ptr, int64_t* n_rows);
+int64_t adb_session_kernel_launches(const adb_session_t* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALPHADIA_B200_H */

@@ -1,0 +1,156 @@
+"""Generate golden vectors by running the UNMODIFIED reference numba path (CPU, this container).
+
+    python tests/golden/generate_golden.py [config1 parity_small ...]
+
+Needs /root/reference (read-only) and numba; pays ~6 min of JIT once per process.  Writes
+``tests/golden/<name>.npz`` — inputs are NOT stored (they are regenerated from the seed by
+``alphadia_b200.synthetic``; a checksum of the inputs is stored so the tests can tell).
+
+Parameters mirror ``ClassicExtractionHandler`` (reference
+``alphadia/workflow/peptidecentric/extraction_handler.py:349-409,423-431,460-468``).
+"""
+
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from alphadia_b200.synthetic import make_config_3d  # noqa: E402
+from oracle import refshim  # noqa: E402
+
+SELECTION_BASE = {
+    "peak_len_rt": 10.0, "sigma_scale_rt": 0.5, "peak_len_mobility": 0.01, "sigma_scale_mobility": 1.0,
+    "top_k_precursors": 3, "kernel_size": 30, "f_mobility": 1.0, "f_rt": 0.99, "center_fraction": 0.5,
+    "min_size_mobility": 8, "min_size_rt": 3, "max_size_mobility": 20, "max_size_rt": 15,
+    "group_channels": False, "use_weighted_score": True, "join_close_candidates": False,
+    "join_close_candidates_scan_threshold": 0.6, "join_close_candidates_cycle_threshold": 0.6,
+    "top_k_fragments": 12, "exclude_shared_ions": True,
+}
+SCORING_BASE = {
+    "score_grouped": False, "top_k_isotopes": 3, "reference_channel": -1,
+    "precursor_mz_tolerance": 10, "fragment_mz_tolerance": 15, "exclude_shared_ions": True,
+    "quant_window": 3, "quant_all": True, "experimental_xic": True, "top_k_fragments": 12,
+}
+
+
+def input_checksum(raw, precursor_df, fragment_df) -> str:
+    h = hashlib.sha256()
+    for a in (raw.mz_values, raw.intensity_values, raw.peak_start_idx_list, raw.rt_values,
+              precursor_df["mz_library"].values, precursor_df["rt_library"].values,
+              fragment_df["mz_library"].values, fragment_df["intensity"].values):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def prepare_library(precursor_df, fragment_df):
+    precursor_df = precursor_df.copy()
+    fragment_df = fragment_df.copy()
+    return precursor_df, fragment_df
+
+
+def run(name: str, threads: int, variants: bool):
+    raw, precursor_df, fragment_df, p = make_config_3d(name)
+    chk = input_checksum(raw, precursor_df, fragment_df)
+    dia = refshim.RefDiaData(raw)
+
+    sel_mod = refshim.ref("alphadia.search.selection.selection")
+    cfg_mod = refshim.ref("alphadia.search.selection.config_df")
+    sc_mod = refshim.ref("alphadia.search.scoring.scoring")
+    sccfg_mod = refshim.ref("alphadia.search.scoring.config")
+    fc_mod = refshim.ref("alphadia.fragcomp.fragcomp")
+
+    out = {"input_checksum": np.array(chk)}
+
+    # ---------------- selection ----------------
+    sel_cfg = cfg_mod.CandidateSelectionConfig()
+    sel_cfg.update({**SELECTION_BASE, "rt_tolerance": float(p["rt_tolerance"]), "mobility_tolerance": 0.1,
+                    "candidate_count": 3, "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0})
+    sel = sel_mod.CandidateSelection(
+        dia, precursor_df.copy(), fragment_df.copy(), sel_cfg,
+        rt_column="rt_library", mobility_column="mobility_library",
+        precursor_mz_column="mz_library", fragment_mz_column="mz_library",
+        fwhm_rt=5.0, fwhm_mobility=0.01,
+    )
+    out["sel_kernel"] = np.asarray(sel.kernel)
+    t0 = time.perf_counter()
+    cand = sel(thread_count=threads)
+    t_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cand = sel(thread_count=threads)
+    t_sel = time.perf_counter() - t0
+    print(f"[{name}] selection: first {t_first:.1f}s warm {t_sel:.3f}s -> {len(cand)} candidates "
+          f"({len(precursor_df) / t_sel:.0f} precursors/s, {threads} threads)", flush=True)
+    for c in cand.columns:
+        out[f"cand_{c}"] = cand[c].values
+
+    # ---------------- scoring ------------------
+    def score(cfg_updates, tag):
+        sc_cfg = sccfg_mod.CandidateScoringConfig()
+        sc_cfg.update({**SCORING_BASE, "precursor_mz_tolerance": 5, "fragment_mz_tolerance": 10, **cfg_updates})
+        scorer = sc_mod.CandidateScoring(
+            dia_data=dia, precursors_flat=precursor_df.copy(), fragments_flat=fragment_df.copy(),
+            config=sc_cfg, rt_column="rt_library", mobility_column="mobility_library",
+            precursor_mz_column="mz_library", fragment_mz_column="mz_library",
+        )
+        t0 = time.perf_counter()
+        feat, frag = scorer(cand.copy(), thread_count=threads, include_decoy_fragment_features=True)
+        t1 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        feat, frag = scorer(cand.copy(), thread_count=threads, include_decoy_fragment_features=True)
+        t2 = time.perf_counter() - t0
+        print(f"[{name}] scoring{tag}: first {t1:.1f}s warm {t2:.3f}s -> {len(feat)} rows, {len(frag)} fragment rows "
+              f"({len(cand) / t2:.0f} candidates/s)", flush=True)
+        out[f"feat{tag}_columns"] = np.array(list(feat.columns))
+        fcols = sc_mod.DEFAULT_FEATURE_COLUMNS
+        out[f"feat{tag}_matrix"] = feat[fcols].values.astype(np.float32)
+        out[f"feat{tag}_precursor_idx"] = feat["precursor_idx"].values
+        out[f"feat{tag}_rank"] = feat["rank"].values
+        for c in ("delta_rt", "n_K", "n_R", "n_P", "score", "frame_start", "frame_stop", "decoy", "charge"):
+            if c in feat.columns:
+                out[f"feat{tag}_{c}"] = feat[c].values
+        for c in frag.columns:
+            out[f"frag{tag}_{c}"] = frag[c].values
+        return feat, frag
+
+    feat, frag = score({}, "")
+    if variants:
+        score({"quant_all": False, "experimental_xic": False}, "_legacy")
+        score({"top_k_fragments": 6, "top_k_isotopes": 4, "quant_window": 2}, "_k6")
+
+    # ---------------- fragment competition ------------------
+    psm = feat.copy()
+    # deterministic pseudo-classifier output: lower proba = better (fdr.py sorts ascending)
+    rng = np.random.default_rng(12345)
+    psm["proba"] = rng.uniform(0, 1, size=len(psm)).astype(np.float64)
+    fc = fc_mod.FragmentCompetition(rt_tol_seconds=3, mass_tol_ppm=15, thread_count=threads)
+    t0 = time.perf_counter()
+    kept = fc(psm.copy(), frag.copy(), raw.cycle)
+    t1 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    kept = fc(psm.copy(), frag.copy(), raw.cycle)
+    t2 = time.perf_counter() - t0
+    print(f"[{name}] fragcomp: first {t1:.1f}s warm {t2:.3f}s -> kept {len(kept)} of {len(psm)}", flush=True)
+    out["fc_proba"] = psm["proba"].values
+    out["fc_kept_precursor_idx"] = kept["precursor_idx"].values
+    out["fc_kept_rank"] = kept["rank"].values
+    out["fc_kept_candidate_idx"] = kept["_candidate_idx"].values
+
+    path = os.path.join(HERE, f"{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or ["config1", "parity_small"]
+    threads = int(os.environ.get("ADB_THREADS", os.cpu_count() or 1))
+    for i, n in enumerate(names):
+        run(n, threads, variants=(n == "parity_small"))

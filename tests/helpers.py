@@ -1,0 +1,99 @@
+"""Shared test helpers: named synthetic workloads, default configs, golden loading, comparisons."""
+
+from __future__ import annotations
+
+import functools
+import hashlib
+import os
+
+import numpy as np
+
+from alphadia_b200 import _abi
+from alphadia_b200.config import CandidateScoringConfig, CandidateSelectionConfig
+from alphadia_b200.kernel import GaussianKernel
+from alphadia_b200.library import assemble_library_arrays
+from alphadia_b200.synthetic import make_config_3d
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# ClassicExtractionHandler parameters (reference extraction_handler.py:349-409)
+SELECTION_BASE = {
+    "peak_len_rt": 10.0, "sigma_scale_rt": 0.5, "peak_len_mobility": 0.01, "sigma_scale_mobility": 1.0,
+    "top_k_precursors": 3, "kernel_size": 30, "f_mobility": 1.0, "f_rt": 0.99, "center_fraction": 0.5,
+    "min_size_mobility": 8, "min_size_rt": 3, "max_size_mobility": 20, "max_size_rt": 15,
+    "group_channels": False, "use_weighted_score": True, "join_close_candidates": False,
+    "join_close_candidates_scan_threshold": 0.6, "join_close_candidates_cycle_threshold": 0.6,
+    "top_k_fragments": 12, "exclude_shared_ions": True,
+}
+SCORING_BASE = {
+    "score_grouped": False, "top_k_isotopes": 3, "reference_channel": -1,
+    "precursor_mz_tolerance": 10, "fragment_mz_tolerance": 15, "exclude_shared_ions": True,
+    "quant_window": 3, "quant_all": True, "experimental_xic": True, "top_k_fragments": 12,
+}
+
+
+def selection_config(rt_tolerance: float, **kw) -> CandidateSelectionConfig:
+    c = CandidateSelectionConfig()
+    c.update({**SELECTION_BASE, "rt_tolerance": float(rt_tolerance), "mobility_tolerance": 0.1, "candidate_count": 3,
+              "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0, **kw})
+    return c
+
+
+def scoring_config(**kw) -> CandidateScoringConfig:
+    c = CandidateScoringConfig()
+    c.update({**SCORING_BASE, "precursor_mz_tolerance": 5, "fragment_mz_tolerance": 10, **kw})
+    return c
+
+
+@functools.lru_cache(maxsize=4)
+def workload(name: str):
+    raw, precursor_df, fragment_df, p = make_config_3d(name)
+    lib = assemble_library_arrays(precursor_df, fragment_df, "rt_library", "mobility_library", "mz_library", "mz_library")
+    return raw, precursor_df, fragment_df, lib, p
+
+
+def input_checksum(raw, precursor_df, fragment_df) -> str:
+    h = hashlib.sha256()
+    for a in (raw.mz_values, raw.intensity_values, raw.peak_start_idx_list, raw.rt_values,
+              precursor_df["mz_library"].values, precursor_df["rt_library"].values,
+              fragment_df["mz_library"].values, fragment_df["intensity"].values):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def load_golden(name: str):
+    path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+    if not os.path.exists(path):
+        return None
+    return np.load(path, allow_pickle=False)
+
+
+def default_kernel(raw, fwhm_rt=5.0, fwhm_mobility=0.01) -> np.ndarray:
+    g = GaussianKernel(raw, fwhm_rt=fwhm_rt, sigma_scale_rt=0.5, fwhm_mobility=fwhm_mobility, sigma_scale_mobility=1.0,
+                       kernel_width=30, kernel_height=min(30, raw.scan_max_index + 1))
+    return g.get_dense_matrix(verbose=False)
+
+
+def candidates_in_from_arrays(lib, cand: dict):
+    """Build adb_candidates_in from candidate arrays (precursor_idx, rank, scan_*, frame_*), in scoring order."""
+    order = np.lexsort((cand["rank"], cand["precursor_idx"]))  # == sort by (elution_group=precursor_idx, decoy, rank)
+    pidx = np.asarray(cand["precursor_idx"])[order]
+    lib_row = np.searchsorted(lib["precursor_idx"], pidx)
+    d, keep = _abi.make_candidates_in(
+        lib_row, np.asarray(cand["rank"])[order],
+        np.asarray(cand["scan_start"])[order], np.asarray(cand["scan_stop"])[order], np.asarray(cand["scan_center"])[order],
+        np.asarray(cand["frame_start"])[order], np.asarray(cand["frame_stop"])[order], np.asarray(cand["frame_center"])[order],
+    )
+    keep["precursor_idx"] = pidx
+    keep["order"] = order
+    return d, keep
+
+
+def rel_err(a, b, floor=1e-6):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    d = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
+    d = np.where(both_nan, 0.0, d)
+    d = np.where(np.isnan(d), np.inf, d)
+    return d
