@@ -1,0 +1,656 @@
+// alphadia_b200 — C ABI implementation: handles, H2D/D2H staging, launches (see include/alphadia_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "adb_common.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const std::string& msg) {
+  g_error = msg;
+  return 1;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                  std::to_string(__LINE__) + ")");                                            \
+  } while (0)
+
+struct DeviceBuffer {  // grow-only cached device allocation
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need) {
+    if (need <= bytes) return 0;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    size_t cap = need + need / 8 + 256;
+    cudaError_t e = cudaMalloc(&ptr, cap);
+    if (e != cudaSuccess) return fail(std::string("cudaMalloc(") + std::to_string(cap) + ") failed: " + cudaGetErrorString(e));
+    bytes = cap;
+    return 0;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return (T*)ptr; }
+};
+
+template <typename T>
+int upload(const T* host, int64_t n, T** dev, std::vector<void*>& allocs, int64_t& total, cudaStream_t stream) {
+  size_t bytes = sizeof(T) * (size_t)(n > 0 ? n : 1);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+  allocs.push_back(p);
+  total += (int64_t)bytes;
+  if (n > 0) {
+    e = cudaMemcpyAsync(p, host, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return fail(std::string("cudaMemcpy H2D failed: ") + cudaGetErrorString(e));
+  }
+  *dev = (T*)p;
+  return 0;
+}
+
+}  // namespace
+
+struct adb_library {
+  int device = 0;
+  DevLib dev{};
+  std::vector<void*> allocs;
+  int64_t bytes = 0;
+  int max_lib_fragments = 0;
+};
+
+struct adb_rawfile {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevRaw dev{};
+  std::vector<void*> allocs;
+  int64_t bytes = 0;
+  std::vector<float> rt_host;  // host copy of rt_values (to bound the cycle window on the host)
+  uint32_t* d_status = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;
+  int launches = 0;
+  int sm_count = 148;
+  // cached workspaces
+  DeviceBuffer kern, order_keys, order_vals, order_tmp, sel_ws;
+  DeviceBuffer cont;       // candidate container (9 columns)
+  DeviceBuffer cand_in;    // compacted candidates (8 columns)
+  DeviceBuffer flags, offs, scan_tmp, count;
+  DeviceBuffer scores;     // score outputs
+  DeviceBuffer score_ws;
+  DeviceBuffer staging;    // generic H2D staging
+  // resident state
+  int64_t cont_rows = 0, cont_count = 0;
+  DevCandidatesOut d_cont{};
+  int64_t n_cand = 0;
+  DevCandidatesIn d_cand{};
+  DevScoresOut d_scores{};
+  int64_t scores_n = 0;
+  int scores_k = 0;
+};
+
+namespace {
+
+int set_device(int device) {
+  CUDA_TRY(cudaSetDevice(device));
+  return 0;
+}
+
+int check_status(adb_rawfile* raw, const char* where) {
+  uint32_t st = 0;
+  CUDA_TRY(cudaMemcpyAsync(&st, raw->d_status, sizeof(st), cudaMemcpyDeviceToHost, raw->stream));
+  CUDA_TRY(cudaStreamSynchronize(raw->stream));
+  CUDA_TRY(cudaGetLastError());
+  if (st == 0) return 0;
+  std::string msg = std::string(where) + ": unsupported input on device:";
+  if (st & ADB_STATUS_TOO_MANY_OBS) msg += " a precursor overlaps more than " + std::to_string(ADB_MAX_OBS) + " quadrupole windows;";
+  if (st & ADB_STATUS_TOO_MANY_LIB_FRAGMENTS) msg += " a precursor has more than " + std::to_string(ADB_MAX_LIB_FRAGMENTS) + " library fragments;";
+  if (st & ADB_STATUS_SCRATCH_OVERFLOW) msg += " a candidate/precursor window exceeds the device scratch;";
+  CUDA_TRY(cudaMemsetAsync(raw->d_status, 0, sizeof(uint32_t), raw->stream));
+  return fail(msg);
+}
+
+// candidate container columns carved from one buffer
+DevCandidatesOut carve_container(void* base, int64_t n) {
+  DevCandidatesOut c{};
+  c.n_rows = n;
+  size_t N = (size_t)n;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+  c.precursor_idx = (uint32_t*)take(4 * N);
+  c.score = (float*)take(4 * N);
+  c.scan_center = (uint32_t*)take(4 * N);
+  c.scan_start = (uint32_t*)take(4 * N);
+  c.scan_stop = (uint32_t*)take(4 * N);
+  c.frame_center = (uint32_t*)take(4 * N);
+  c.frame_start = (uint32_t*)take(4 * N);
+  c.frame_stop = (uint32_t*)take(4 * N);
+  c.rank = (uint8_t*)take(N);
+  return c;
+}
+size_t container_bytes(int64_t n) { return 9 * (((size_t)n * 4 + 255) & ~(size_t)255) + 512; }
+
+struct CandInPtrs {
+  int64_t *lib_row, *scan_start, *scan_stop, *scan_center, *frame_start, *frame_stop, *frame_center;
+  uint8_t* rank;
+};
+CandInPtrs carve_cand_in(void* base, int64_t n) {
+  CandInPtrs c{};
+  size_t N = (size_t)n;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+  c.lib_row = (int64_t*)take(8 * N);
+  c.scan_start = (int64_t*)take(8 * N);
+  c.scan_stop = (int64_t*)take(8 * N);
+  c.scan_center = (int64_t*)take(8 * N);
+  c.frame_start = (int64_t*)take(8 * N);
+  c.frame_stop = (int64_t*)take(8 * N);
+  c.frame_center = (int64_t*)take(8 * N);
+  c.rank = (uint8_t*)take(N);
+  return c;
+}
+size_t cand_in_bytes(int64_t n) { return 8 * (((size_t)n * 8 + 255) & ~(size_t)255) + 512; }
+
+DevScoresOut carve_scores(void* base, int64_t n, int k) {
+  DevScoresOut s{};
+  size_t N = (size_t)n, K = (size_t)k;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+  s.features = (float*)take(4 * N * ADB_NUM_FEATURES);
+  s.fragment_mz_library = (float*)take(4 * N * K);
+  s.fragment_mz = (float*)take(4 * N * K);
+  s.fragment_mz_observed = (float*)take(4 * N * K);
+  s.fragment_height = (float*)take(4 * N * K);
+  s.fragment_intensity = (float*)take(4 * N * K);
+  s.fragment_mass_error = (float*)take(4 * N * K);
+  s.fragment_correlation = (float*)take(4 * N * K);
+  s.fragment_position = (uint8_t*)take(N * K);
+  s.fragment_number = (uint8_t*)take(N * K);
+  s.fragment_type = (uint8_t*)take(N * K);
+  s.fragment_charge = (uint8_t*)take(N * K);
+  s.fragment_loss_type = (uint8_t*)take(N * K);
+  s.valid = (uint8_t*)take(N);
+  return s;
+}
+size_t scores_bytes(int64_t n, int k) {
+  size_t N = (size_t)n, K = (size_t)k;
+  return 4 * N * ADB_NUM_FEATURES + 7 * 4 * N * K + 5 * N * K + N + 15 * 256;
+}
+
+__global__ void order_key_kernel(DevRaw raw, DevLib lib, uint64_t* keys, int32_t* vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= lib.n_precursors) return;
+  float mz = lib.mz[i];
+  uint32_t win = 0xFFFFu;
+  for (int64_t j = 0; j < raw.cycle_len; j++)
+    if ((double)mz <= raw.cycle[2 * j + 1] && (double)mz >= raw.cycle[2 * j]) { win = (uint32_t)j; break; }
+  float rt = lib.rt[i];
+  uint32_t rb = __float_as_uint(rt);
+  rb = (rb & 0x80000000u) ? ~rb : (rb | 0x80000000u);  // order-preserving float -> uint
+  keys[i] = ((uint64_t)win << 32) | rb;
+  vals[i] = (int32_t)i;
+}
+
+// upper bound of the selection cycle window: jitclasses/utils.py:62-70 over every possible precursor RT
+int64_t cycle_window_upper_bound(const adb_rawfile* raw, double rt_tol, int64_t kernel_size) {
+  const std::vector<float>& rt = raw->rt_host;
+  const int64_t n = (int64_t)rt.size(), L = raw->dev.cycle_len;
+  int64_t max_span = 0, j = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (j < i) j = i;
+    while (j < n && (double)rt[j] <= (double)rt[i] + 2.0 * rt_tol + 1e-3) j++;
+    max_span = std::max(max_span, j - i);
+  }
+  int64_t len = max_span / L + 2;
+  int64_t opt = std::max(len, kernel_size);
+  opt = 16 * ((opt + 15) / 16);
+  return std::min<int64_t>(opt, std::max<int64_t>(raw->dev.precursor_cycle_max_index, 1));
+}
+
+int run_selection(adb_rawfile* raw, adb_library* lib, const adb_selection_config* cfg, const float* kernel,
+                  int32_t kh, int32_t kw) {
+  if (raw->device != lib->device) return fail("raw file and library live on different devices");
+  if (kh != 2) return fail("3-D selection expects a kernel of height 2 (GaussianKernel with scan_max_index + 1 == 2)");
+  if (kw < 1 || kw > ADB_MAX_KERNEL_W) return fail("kernel width must be in [1, " + std::to_string(ADB_MAX_KERNEL_W) + "]");
+  if (cfg->candidate_count < 1 || cfg->candidate_count > 16) return fail("candidate_count must be in [1, 16]");
+  if (cfg->top_k_precursors < 1) return fail("top_k_precursors must be >= 1");
+  if (set_device(raw->device)) return 1;
+  cudaStream_t st = raw->stream;
+  const int64_t P = lib->dev.n_precursors;
+  const int64_t rows = P * cfg->candidate_count;
+
+  CUDA_TRY(cudaEventRecord(raw->ev[0], st));
+  // kernel -> doubles on the device
+  std::vector<double> kd((size_t)kh * kw);
+  for (size_t t = 0; t < kd.size(); t++) kd[t] = (double)kernel[t];
+  if (raw->kern.reserve(sizeof(double) * kd.size())) return 1;
+  CUDA_TRY(cudaMemcpyAsync(raw->kern.ptr, kd.data(), sizeof(double) * kd.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // kd goes out of scope below only after this point
+  if (raw->cont.reserve(container_bytes(rows))) return 1;
+  raw->d_cont = carve_container(raw->cont.ptr, rows);
+  raw->cont_rows = rows;
+  raw->cont_count = cfg->candidate_count;
+  CUDA_TRY(cudaEventRecord(raw->ev[1], st));
+  // CandidateContainer.__init__ zero-fills (config_df.py:241-254)
+  CUDA_TRY(cudaMemsetAsync(raw->cont.ptr, 0, container_bytes(rows), st));
+
+  // processing order: (quad window of the precursor, library RT) so that concurrently resident CTAs read
+  // the same spectra (L2 reuse); results do not depend on it (disjoint output rows)
+  int32_t* d_order = nullptr;
+  if (P > 1) {
+    if (raw->order_keys.reserve(sizeof(uint64_t) * 2 * (size_t)P)) return 1;
+    if (raw->order_vals.reserve(sizeof(int32_t) * 2 * (size_t)P)) return 1;
+    uint64_t* k_in = raw->order_keys.as<uint64_t>();
+    uint64_t* k_out = k_in + P;
+    int32_t* v_in = raw->order_vals.as<int32_t>();
+    int32_t* v_out = v_in + P;
+    order_key_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(raw->dev, lib->dev, k_in, v_in);
+    raw->launches++;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)P, 0, 64, st);
+    if (raw->order_tmp.reserve(tmp)) return 1;
+    cub::DeviceRadixSort::SortPairs(raw->order_tmp.ptr, tmp, k_in, k_out, v_in, v_out, (int)P, 0, 64, st);
+    raw->launches += 4;
+    d_order = v_out;
+  }
+
+  // geometry
+  const int64_t c_upper = cycle_window_upper_bound(raw, cfg->rt_tolerance, cfg->kernel_size);
+  const int nI = (int)std::min<int64_t>(std::min<int64_t>(lib->dev.n_isotopes, cfg->top_k_precursors), ADB_MAX_ISOTOPES);
+  const int max_layers = std::min(lib->max_lib_fragments, (int)ADB_MAX_LIB_FRAGMENTS) + nI;
+  int c_cap = (int)c_upper;
+  const size_t smem_limit = 200 * 1024;
+  float* d_ws = nullptr;
+  int64_t ws_floats = 0;
+  if (adb_select_smem_bytes(c_cap, max_layers) > smem_limit) {
+    // shrink the shared-memory layout; windows that do not fit use the HBM workspace
+    c_cap = (int)((smem_limit - sizeof(double) * 2 * ADB_MAX_KERNEL_W) / (sizeof(float) * max_layers + 2 * sizeof(double)));
+    c_cap = std::max(16, (c_cap / 16) * 16);
+    ws_floats = (int64_t)max_layers * c_upper + 6 * c_upper + 16;
+    ws_floats = (ws_floats + 3) & ~(int64_t)3;
+  }
+  int grid = adb_select_resident_ctas(raw->device, c_cap, max_layers);
+  if (ws_floats > 0) {
+    if (raw->sel_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)grid)) return 1;
+    d_ws = raw->sel_ws.as<float>();
+  }
+  adb_launch_select_ex(raw->dev, lib->dev, *cfg, raw->kern.as<double>(), kh, kw, raw->d_cont, 0, P, d_order, raw->d_status,
+                       c_cap, max_layers, d_ws, ws_floats, grid, st, &raw->launches);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int run_compaction(adb_rawfile* raw) {
+  cudaStream_t st = raw->stream;
+  const int64_t rows = raw->cont_rows;
+  if (raw->flags.reserve(sizeof(int) * (size_t)std::max<int64_t>(rows, 1))) return 1;
+  if (raw->offs.reserve(sizeof(int) * (size_t)std::max<int64_t>(rows, 1))) return 1;
+  size_t tmp = adb_compact_temp_bytes(rows);
+  if (raw->scan_tmp.reserve(tmp + 16)) return 1;
+  if (raw->count.reserve(sizeof(int64_t))) return 1;
+  if (raw->cand_in.reserve(cand_in_bytes(rows))) return 1;
+  CandInPtrs c = carve_cand_in(raw->cand_in.ptr, rows);
+  CUDA_TRY(cudaMemsetAsync(raw->count.ptr, 0, sizeof(int64_t), st));
+  adb_launch_compact_ex(raw->d_cont, raw->cont_count, raw->flags.as<int>(), raw->offs.as<int>(), raw->scan_tmp.ptr, tmp,
+                        c.lib_row, c.rank, c.scan_start, c.scan_stop, c.scan_center, c.frame_start, c.frame_stop,
+                        c.frame_center, raw->count.as<int64_t>(), st, &raw->launches);
+  CUDA_TRY(cudaGetLastError());
+  int64_t n = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n, raw->count.ptr, sizeof(n), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  raw->n_cand = n;
+  raw->d_cand = DevCandidatesIn{n, c.lib_row, c.rank, c.scan_start, c.scan_stop, c.scan_center, c.frame_start, c.frame_stop, c.frame_center};
+  return 0;
+}
+
+int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cfg, int64_t c_max_hint) {
+  if (raw->device != lib->device) return fail("raw file and library live on different devices");
+  if (cfg->top_k_fragments < 1 || cfg->top_k_fragments > ADB_MAX_FRAGMENTS)
+    return fail("top_k_fragments must be in [1, " + std::to_string(ADB_MAX_FRAGMENTS) + "]");
+  if (cfg->top_k_isotopes < 1) return fail("top_k_isotopes must be >= 1");
+  cudaStream_t st = raw->stream;
+  const int64_t n = raw->d_cand.n;
+  const int K = (int)cfg->top_k_fragments;
+  if (raw->scores.reserve(scores_bytes(std::max<int64_t>(n, 1), K))) return 1;
+  raw->d_scores = carve_scores(raw->scores.ptr, std::max<int64_t>(n, 1), K);
+  raw->scores_n = n;
+  raw->scores_k = K;
+  // OutputPsmDF.__init__ zero-fills (scoring/output.py:42-70)
+  CUDA_TRY(cudaMemsetAsync(raw->scores.ptr, 0, scores_bytes(std::max<int64_t>(n, 1), K), st));
+  int warps = adb_score_resident_warps(raw->device);
+  // HBM fallback scratch for candidates whose cube exceeds the shared-memory budget
+  int64_t c_max = std::max<int64_t>(c_max_hint, 32);
+  int64_t ws_floats = (adb_score_workspace_floats(K, c_max) + 3) & ~(int64_t)3;
+  if (raw->score_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)warps)) return 1;
+  adb_launch_score(raw->dev, lib->dev, *cfg, raw->d_cand, raw->d_scores, raw->score_ws.as<float>(), ws_floats, warps,
+                   raw->d_status, st, &raw->launches);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+void finish_timing(adb_rawfile* raw) {
+  cudaEventSynchronize(raw->ev[3]);
+  cudaEventElapsedTime(&raw->h2d_ms, raw->ev[0], raw->ev[1]);
+  cudaEventElapsedTime(&raw->kernel_ms, raw->ev[1], raw->ev[2]);
+  cudaEventElapsedTime(&raw->d2h_ms, raw->ev[2], raw->ev[3]);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* adb_last_error(void) { return g_error.c_str(); }
+const char* adb_version(void) { return "alphadia_b200 0.1 (sm_100a)"; }
+
+int adb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t** out) {
+  if (!d || !out) return fail("null argument");
+  if (d->cycle_len < 1 || d->n_spectra < 1) return fail("empty raw file");
+  if (d->n_mobility < 1) return fail("mobility_values must not be empty");
+  if (set_device(device)) return 1;
+  adb_rawfile* r = new adb_rawfile();
+  r->device = device;
+  CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&r->ev[i]));
+  cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, device);
+  DevRaw& v = r->dev;
+  double* cyc; float *rt, *mob, *mz, *it; int64_t *ps, *pe;
+  if (upload(d->cycle, d->cycle_len * 2, &cyc, r->allocs, r->bytes, r->stream) ||
+      upload(d->rt_values, d->n_spectra, &rt, r->allocs, r->bytes, r->stream) ||
+      upload(d->mobility_values, d->n_mobility, &mob, r->allocs, r->bytes, r->stream) ||
+      upload(d->peak_start_idx, d->n_spectra, &ps, r->allocs, r->bytes, r->stream) ||
+      upload(d->peak_stop_idx, d->n_spectra, &pe, r->allocs, r->bytes, r->stream) ||
+      upload(d->mz_values, d->n_peaks, &mz, r->allocs, r->bytes, r->stream) ||
+      upload(d->intensity_values, d->n_peaks, &it, r->allocs, r->bytes, r->stream)) {
+    adb_rawfile_destroy(r);
+    return 1;
+  }
+  v.cycle = cyc; v.cycle_len = d->cycle_len; v.rt_values = rt; v.n_spectra = d->n_spectra;
+  v.mobility_values = mob; v.n_mobility = d->n_mobility; v.peak_start = ps; v.peak_stop = pe;
+  v.mz = mz; v.intensity = it; v.n_peaks = d->n_peaks; v.zeroth_frame = d->zeroth_frame;
+  v.precursor_cycle_max_index = d->precursor_cycle_max_index; v.scan_max_index = d->scan_max_index;
+  v.frame_max_index = d->frame_max_index;
+  // MS1 positions: windows overlapping the query [-1, -1] (alpharaw_jit.py:46-48)
+  v.n_ms1_pos = 0;
+  for (int64_t j = 0; j < d->cycle_len; j++)
+    if ((-1.0 <= d->cycle[2 * j + 1]) && (-1.0 >= d->cycle[2 * j])) {
+      if (v.n_ms1_pos >= ADB_MAX_MS1_POS) { adb_rawfile_destroy(r); return fail("more than 8 MS1 spectra per cycle"); }
+      v.ms1_pos[v.n_ms1_pos++] = (int32_t)j;
+    }
+  r->rt_host.assign(d->rt_values, d->rt_values + d->n_spectra);
+  void* st = nullptr;
+  if (cudaMalloc(&st, sizeof(uint32_t)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc status failed"); }
+  r->d_status = (uint32_t*)st;
+  cudaMemsetAsync(r->d_status, 0, sizeof(uint32_t), r->stream);
+  cudaError_t e = cudaStreamSynchronize(r->stream);
+  if (e != cudaSuccess) { adb_rawfile_destroy(r); return fail(std::string("raw file upload failed: ") + cudaGetErrorString(e)); }
+  *out = r;
+  return 0;
+}
+
+void adb_rawfile_destroy(adb_rawfile_t* r) {
+  if (!r) return;
+  cudaSetDevice(r->device);
+  if (r->stream) cudaStreamSynchronize(r->stream);
+  for (void* p : r->allocs) cudaFree(p);
+  if (r->d_status) cudaFree(r->d_status);
+  DeviceBuffer* bufs[] = {&r->kern, &r->order_keys, &r->order_vals, &r->order_tmp, &r->sel_ws, &r->cont, &r->cand_in,
+                          &r->flags, &r->offs, &r->scan_tmp, &r->count, &r->scores, &r->score_ws, &r->staging};
+  for (DeviceBuffer* b : bufs) b->release();
+  for (int i = 0; i < 4; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
+  if (r->stream) cudaStreamDestroy(r->stream);
+  delete r;
+}
+
+int64_t adb_rawfile_device_bytes(const adb_rawfile_t* r) { return r ? r->bytes : 0; }
+void* adb_rawfile_stream(const adb_rawfile_t* r) { return r ? (void*)r->stream : nullptr; }
+
+int adb_library_create(const adb_library_desc* d, int device, adb_library_t** out) {
+  if (!d || !out) return fail("null argument");
+  if (d->n_isotopes < 1) return fail("library needs at least one isotope column");
+  if (set_device(device)) return 1;
+  adb_library* l = new adb_library();
+  l->device = device;
+  cudaStream_t st = nullptr;  // default stream, synchronous
+  DevLib& v = l->dev;
+  const int64_t P = d->n_precursors, NF = d->n_fragments;
+  uint32_t *a, *b, *c; uint8_t* ch; float *rt, *mob, *mz, *iso, *fl, *fm, *fi; uint8_t *t, *lt, *fc, *fn, *fp, *fcard;
+  if (upload(d->precursor_idx, P, &a, l->allocs, l->bytes, st) || upload(d->frag_start_idx, P, &b, l->allocs, l->bytes, st) ||
+      upload(d->frag_stop_idx, P, &c, l->allocs, l->bytes, st) || upload(d->charge, P, &ch, l->allocs, l->bytes, st) ||
+      upload(d->rt, P, &rt, l->allocs, l->bytes, st) || upload(d->mobility, P, &mob, l->allocs, l->bytes, st) ||
+      upload(d->mz, P, &mz, l->allocs, l->bytes, st) || upload(d->isotopes, P * d->n_isotopes, &iso, l->allocs, l->bytes, st) ||
+      upload(d->frag_mz_library, NF, &fl, l->allocs, l->bytes, st) || upload(d->frag_mz, NF, &fm, l->allocs, l->bytes, st) ||
+      upload(d->frag_intensity, NF, &fi, l->allocs, l->bytes, st) || upload(d->frag_type, NF, &t, l->allocs, l->bytes, st) ||
+      upload(d->frag_loss_type, NF, &lt, l->allocs, l->bytes, st) || upload(d->frag_charge, NF, &fc, l->allocs, l->bytes, st) ||
+      upload(d->frag_number, NF, &fn, l->allocs, l->bytes, st) || upload(d->frag_position, NF, &fp, l->allocs, l->bytes, st) ||
+      upload(d->frag_cardinality, NF, &fcard, l->allocs, l->bytes, st)) {
+    adb_library_destroy(l);
+    return 1;
+  }
+  v.n_precursors = P; v.precursor_idx = a; v.frag_start_idx = b; v.frag_stop_idx = c; v.charge = ch; v.rt = rt;
+  v.mobility = mob; v.mz = mz; v.isotopes = iso; v.n_isotopes = d->n_isotopes; v.n_fragments = NF;
+  v.frag_mz_library = fl; v.frag_mz = fm; v.frag_intensity = fi; v.frag_type = t; v.frag_loss_type = lt;
+  v.frag_charge = fc; v.frag_number = fn; v.frag_position = fp; v.frag_cardinality = fcard;
+  int mx = 0;
+  for (int64_t i = 0; i < P; i++) {
+    int64_t s = d->frag_start_idx[i], e = d->frag_stop_idx[i];
+    if (e > NF || s > e) { adb_library_destroy(l); return fail("fragment index range of precursor row " + std::to_string(i) + " is outside the fragment table"); }
+    mx = std::max<int>(mx, (int)(e - s));
+  }
+  l->max_lib_fragments = mx;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { adb_library_destroy(l); return fail(std::string("library upload failed: ") + cudaGetErrorString(e)); }
+  *out = l;
+  return 0;
+}
+
+void adb_library_destroy(adb_library_t* l) {
+  if (!l) return;
+  cudaSetDevice(l->device);
+  for (void* p : l->allocs) cudaFree(p);
+  delete l;
+}
+
+int adb_fetch_candidates(adb_rawfile_t* raw, adb_candidates_out* out) {
+  if (!raw || !out) return fail("null argument");
+  if (out->n_rows != raw->cont_rows) return fail("candidate container size mismatch");
+  if (set_device(raw->device)) return 1;
+  cudaStream_t st = raw->stream;
+  const size_t N = (size_t)raw->cont_rows;
+  const DevCandidatesOut& c = raw->d_cont;
+  CUDA_TRY(cudaMemcpyAsync(out->precursor_idx, c.precursor_idx, 4 * N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out->rank, c.rank, N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out->score, c.score, 4 * N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out->scan_center, c.scan_center, 4 * N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out->scan_start, c.scan_start, 4 * N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out->scan_stop, c.scan_stop, 4 * N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out->frame_center, c.frame_center, 4 * N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out->frame_start, c.frame_start, 4 * N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out->frame_stop, c.frame_stop, 4 * N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int adb_fetch_scores(adb_rawfile_t* raw, adb_scores_out* out, int64_t* lib_row, uint8_t* rank) {
+  if (!raw || !out) return fail("null argument");
+  if (set_device(raw->device)) return 1;
+  cudaStream_t st = raw->stream;
+  const size_t N = (size_t)raw->scores_n, K = (size_t)raw->scores_k;
+  const DevScoresOut& s = raw->d_scores;
+  if (N > 0) {
+    CUDA_TRY(cudaMemcpyAsync(out->features, s.features, 4 * N * ADB_NUM_FEATURES, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->valid, s.valid, N, cudaMemcpyDeviceToHost, st));
+    float* hf[] = {out->fragment_mz_library, out->fragment_mz, out->fragment_mz_observed, out->fragment_height,
+                   out->fragment_intensity, out->fragment_mass_error, out->fragment_correlation};
+    float* df[] = {s.fragment_mz_library, s.fragment_mz, s.fragment_mz_observed, s.fragment_height,
+                   s.fragment_intensity, s.fragment_mass_error, s.fragment_correlation};
+    for (int i = 0; i < 7; i++) CUDA_TRY(cudaMemcpyAsync(hf[i], df[i], 4 * N * K, cudaMemcpyDeviceToHost, st));
+    uint8_t* hu[] = {out->fragment_position, out->fragment_number, out->fragment_type, out->fragment_charge, out->fragment_loss_type};
+    uint8_t* du[] = {s.fragment_position, s.fragment_number, s.fragment_type, s.fragment_charge, s.fragment_loss_type};
+    for (int i = 0; i < 5; i++) CUDA_TRY(cudaMemcpyAsync(hu[i], du[i], N * K, cudaMemcpyDeviceToHost, st));
+    if (lib_row) CUDA_TRY(cudaMemcpyAsync(lib_row, raw->d_cand.lib_row, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (rank) CUDA_TRY(cudaMemcpyAsync(rank, raw->d_cand.rank, N, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int adb_select_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_selection_config* cfg, const float* kernel,
+                          int32_t kh, int32_t kw, adb_candidates_out* out) {
+  if (!raw || !lib || !cfg || !kernel || !out) return fail("null argument");
+  if (out->n_rows != lib->dev.n_precursors * cfg->candidate_count) return fail("candidate container must have n_precursors * candidate_count rows");
+  if (run_selection(raw, lib, cfg, kernel, kh, kw)) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[2], raw->stream));
+  if (check_status(raw, "adb_select_candidates")) return 1;
+  if (adb_fetch_candidates(raw, out)) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[3], raw->stream));
+  finish_timing(raw);
+  return 0;
+}
+
+int adb_select_candidates_resident(adb_rawfile_t* raw, adb_library_t* lib, const adb_selection_config* cfg,
+                                   const float* kernel, int32_t kh, int32_t kw, int64_t* n_candidates) {
+  if (!raw || !lib || !cfg || !kernel) return fail("null argument");
+  if (run_selection(raw, lib, cfg, kernel, kh, kw)) return 1;
+  if (run_compaction(raw)) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[2], raw->stream));
+  if (check_status(raw, "adb_select_candidates_resident")) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[3], raw->stream));
+  finish_timing(raw);
+  if (n_candidates) *n_candidates = raw->n_cand;
+  return 0;
+}
+
+int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scoring_config* cfg,
+                         const adb_candidates_in* cand, adb_scores_out* out) {
+  if (!raw || !lib || !cfg || !cand || !out) return fail("null argument");
+  if (set_device(raw->device)) return 1;
+  cudaStream_t st = raw->stream;
+  const int64_t n = cand->n;
+  CUDA_TRY(cudaEventRecord(raw->ev[0], st));
+  // H2D of the candidate table
+  if (raw->cand_in.reserve(cand_in_bytes(std::max<int64_t>(n, 1)))) return 1;
+  CandInPtrs c = carve_cand_in(raw->cand_in.ptr, std::max<int64_t>(n, 1));
+  int64_t c_max = 0;
+  if (n > 0) {
+    const size_t N = (size_t)n;
+    const int64_t P = lib->dev.n_precursors, L = raw->dev.cycle_len;
+    for (int64_t i = 0; i < n; i++) {
+      if (cand->lib_row[i] < 0 || cand->lib_row[i] >= P) return fail("candidate " + std::to_string(i) + " refers to a precursor outside the library");
+      if (cand->frame_start[i] >= 0 && cand->frame_stop[i] >= 0)
+        c_max = std::max<int64_t>(c_max, cand->frame_stop[i] / L - cand->frame_start[i] / L);
+    }
+    CUDA_TRY(cudaMemcpyAsync(c.lib_row, cand->lib_row, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.rank, cand->rank, N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.scan_start, cand->scan_start, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.scan_stop, cand->scan_stop, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.scan_center, cand->scan_center, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.frame_start, cand->frame_start, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.frame_stop, cand->frame_stop, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.frame_center, cand->frame_center, 8 * N, cudaMemcpyHostToDevice, st));
+  }
+  raw->d_cand = DevCandidatesIn{n, c.lib_row, c.rank, c.scan_start, c.scan_stop, c.scan_center, c.frame_start, c.frame_stop, c.frame_center};
+  raw->n_cand = n;
+  CUDA_TRY(cudaEventRecord(raw->ev[1], st));
+  if (c_max > 4096) return fail("a candidate spans more than 4096 cycles");
+  if (run_scoring(raw, lib, cfg, c_max)) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[2], st));
+  if (check_status(raw, "adb_score_candidates")) return 1;
+  if (adb_fetch_scores(raw, out, nullptr, nullptr)) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[3], st));
+  finish_timing(raw);
+  return 0;
+}
+
+int adb_score_candidates_resident(adb_rawfile_t* raw, adb_library_t* lib, const adb_scoring_config* cfg) {
+  if (!raw || !lib || !cfg) return fail("null argument");
+  if (set_device(raw->device)) return 1;
+  cudaStream_t st = raw->stream;
+  CUDA_TRY(cudaEventRecord(raw->ev[0], st));
+  CUDA_TRY(cudaEventRecord(raw->ev[1], st));
+  if (run_scoring(raw, lib, cfg, 64)) return 1;  // selection emits at most 2 * max_size_rt - 1 cycles
+  CUDA_TRY(cudaEventRecord(raw->ev[2], st));
+  if (check_status(raw, "adb_score_candidates_resident")) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[3], st));
+  finish_timing(raw);
+  return 0;
+}
+
+int adb_resident_score_table(adb_rawfile_t* raw, void** features, void** valid, void** lib_row, void** rank, int64_t* n_rows) {
+  if (!raw) return fail("null argument");
+  if (features) *features = raw->d_scores.features;
+  if (valid) *valid = raw->d_scores.valid;
+  if (lib_row) *lib_row = (void*)raw->d_cand.lib_row;
+  if (rank) *rank = (void*)raw->d_cand.rank;
+  if (n_rows) *n_rows = raw->scores_n;
+  return 0;
+}
+
+int adb_last_timing(const adb_rawfile_t* raw, float* h2d_ms, float* kernel_ms, float* d2h_ms) {
+  if (!raw) return fail("null argument");
+  if (h2d_ms) *h2d_ms = raw->h2d_ms;
+  if (kernel_ms) *kernel_ms = raw->kernel_ms;
+  if (d2h_ms) *d2h_ms = raw->d2h_ms;
+  return 0;
+}
+
+int64_t adb_kernel_launches(const adb_rawfile_t* raw) { return raw ? raw->launches : 0; }
+
+int adb_fragment_competition(int device, int64_t n_windows, const int64_t* window_start, const int64_t* window_stop,
+                             int64_t n_psm, const void* rt, const int64_t* frag_start_idx, const int64_t* frag_stop_idx,
+                             int64_t n_frag, const void* fragment_mz, int32_t is_f64, double rt_tol_seconds,
+                             double mass_tol_ppm, uint8_t* valid) {
+  if (n_windows < 0 || n_psm < 0 || n_frag < 0) return fail("negative size");
+  if (n_windows == 0 || n_psm == 0) return 0;
+  if (!window_start || !window_stop || !rt || !frag_start_idx || !frag_stop_idx || !valid) return fail("null argument");
+  if (n_frag > 0 && !fragment_mz) return fail("null argument");
+  for (int64_t w = 0; w < n_windows; w++)
+    if (window_start[w] < 0 || window_stop[w] > n_psm || window_start[w] > window_stop[w]) return fail("window range outside the PSM table");
+  for (int64_t i = 0; i < n_psm; i++)
+    if (frag_start_idx[i] < 0 || frag_stop_idx[i] > n_frag || frag_start_idx[i] > frag_stop_idx[i]) return fail("fragment range outside the fragment table");
+  if (set_device(device)) return 1;
+  const size_t es_rt = (is_f64 & 1) ? 8 : 4, es = (is_f64 & 2) ? 8 : 4;
+  DeviceBuffer b_ws, b_we, b_rt, b_fs, b_fe, b_mz, b_valid;
+  auto cleanup = [&]() { b_ws.release(); b_we.release(); b_rt.release(); b_fs.release(); b_fe.release(); b_mz.release(); b_valid.release(); };
+  if (b_ws.reserve(8 * (size_t)n_windows) || b_we.reserve(8 * (size_t)n_windows) || b_rt.reserve(es_rt * (size_t)n_psm) ||
+      b_fs.reserve(8 * (size_t)n_psm) || b_fe.reserve(8 * (size_t)n_psm) || b_mz.reserve(es * (size_t)std::max<int64_t>(n_frag, 1)) ||
+      b_valid.reserve((size_t)n_psm)) { cleanup(); return 1; }
+  cudaError_t e = cudaSuccess;
+  auto cp = [&](void* d, const void* h, size_t bytes) { if (e == cudaSuccess && bytes) e = cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice); };
+  cp(b_ws.ptr, window_start, 8 * (size_t)n_windows); cp(b_we.ptr, window_stop, 8 * (size_t)n_windows);
+  cp(b_rt.ptr, rt, es_rt * (size_t)n_psm); cp(b_fs.ptr, frag_start_idx, 8 * (size_t)n_psm); cp(b_fe.ptr, frag_stop_idx, 8 * (size_t)n_psm);
+  cp(b_mz.ptr, fragment_mz, es * (size_t)n_frag); cp(b_valid.ptr, valid, (size_t)n_psm);
+  if (e != cudaSuccess) { cleanup(); return fail(std::string("fragcomp H2D failed: ") + cudaGetErrorString(e)); }
+  int launches = 0;
+  adb_launch_fragcomp(n_windows, b_ws.as<int64_t>(), b_we.as<int64_t>(), b_rt.ptr, b_fs.as<int64_t>(), b_fe.as<int64_t>(),
+                      b_mz.ptr, is_f64, rt_tol_seconds, mass_tol_ppm, b_valid.as<uint8_t>(), nullptr, &launches);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(valid, b_valid.ptr, (size_t)n_psm, cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail(std::string("fragcomp kernel failed: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,369 @@
+"""``CandidateScoring`` — drop-in for alphadia/search/scoring/scoring.py:140-661 on the B200 engine.
+
+Same keyword-only constructor, same ``__call__(candidates_df, thread_count, debug,
+include_decoy_fragment_features) -> (features_df, fragments_df)``, same static helpers
+(``merge_candidate_data``, ``merge_precursor_data``) and the same output tables: the 46
+``DEFAULT_FEATURE_COLUMNS`` in order + ids + candidate/precursor columns + ``delta_rt, n_K, n_R, n_P``
+(scoring.py:394-467) and the flattened fragment table (scoring.py:520-580).
+
+The per-candidate numba loop (scoring.py:114-137 -> Candidate.process, candidate.py:166-481) is one CUDA
+launch behind ``adb_score_candidates``.  The per-candidate jitclass construction of the reference
+(``ScoreGroupContainer.build_from_df``, score_group.py:145-229) is replaced by direct SoA marshalling;
+its checks (duplicate precursor in a score group, missing reference channel) are kept.
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import pandas as pd
+
+from alphadia_b200 import _abi, _lib
+from alphadia_b200.config import CandidateScoringConfig
+from alphadia_b200.library import assemble_library_arrays
+from alphadia_b200.raw_data import adapt_dia_data
+from alphadia_b200.validation import (
+    candidates_schema,
+    features_schema,
+    fragment_features_schema,
+    fragments_flat_schema,
+    get_isotope_columns,
+    precursors_flat_schema,
+)
+
+logger = logging.getLogger()
+
+DEFAULT_FEATURE_COLUMNS = [
+    "base_width_mobility", "base_width_rt", "rt_observed", "mobility_observed",
+    "mono_ms1_intensity", "top_ms1_intensity", "sum_ms1_intensity", "weighted_ms1_intensity",
+    "weighted_mass_deviation", "weighted_mass_error", "mz_observed",
+    "mono_ms1_height", "top_ms1_height", "sum_ms1_height", "weighted_ms1_height",
+    "isotope_intensity_correlation", "isotope_height_correlation", "n_observations",
+    "intensity_correlation", "height_correlation", "intensity_fraction", "height_fraction",
+    "intensity_fraction_weighted", "height_fraction_weighted", "mean_observation_score",
+    "sum_b_ion_intensity", "sum_y_ion_intensity", "diff_b_y_ion_intensity", "f_masked",
+    "fragment_scan_correlation", "template_scan_correlation", "fragment_frame_correlation",
+    "top3_frame_correlation", "template_frame_correlation", "top3_b_ion_correlation", "n_b_ions",
+    "top3_y_ion_correlation", "n_y_ions", "cycle_fwhm", "mobility_fwhm", "delta_frame_peak",
+    "top_3_ms2_mass_error", "mean_ms2_mass_error", "n_overlapping", "mean_overlapping_intensity",
+    "mean_overlapping_mass_error",
+]
+
+DEFAULT_CANDIDATE_COLUMNS = [
+    "elution_group_idx", "scan_center", "scan_start", "scan_stop", "frame_center", "frame_start", "frame_stop",
+]
+
+DEFAULT_PRECURSOR_COLUMNS = [
+    "rt_library", "mobility_library", "mz_library", "charge", "decoy", "channel",
+    "flat_frag_start_idx", "flat_frag_stop_idx", "proteins", "genes", "sequence", "mods", "mod_sites",
+]
+
+FRAGMENT_COLUMNS = [
+    "precursor_idx", "rank", "mz_library", "mz", "mz_observed", "height", "intensity", "mass_error",
+    "correlation", "position", "number", "type", "charge", "loss_type",
+]
+
+
+def _get_isotope_column_names(colnames):
+    return [f"i_{i}" for i in get_isotope_columns(colnames)]
+
+
+def merge_missing_columns(left_df, right_df, right_columns, on=None, how="left"):
+    """alphadia/search/scoring/utils.py:203-266 (missing columns keep the order of ``right_columns``)."""
+    if isinstance(on, str):
+        on = [on]
+    if isinstance(right_columns, str):
+        right_columns = [right_columns]
+    seen = set()
+    missing_from_left = [c for c in right_columns if c not in left_df.columns and not (c in seen or seen.add(c))]
+    missing_from_right = [c for c in missing_from_left if c not in right_df.columns]
+    if len(missing_from_left) == 0:
+        return left_df
+    if missing_from_right:
+        raise ValueError(f"Columns {missing_from_right} must be present in right_df")
+    if on is None:
+        raise ValueError("Parameter on must be specified")
+    if not all(col in left_df.columns for col in on):
+        raise ValueError(f"Columns {on} must be present in left_df")
+    if not all(col in right_df.columns for col in on):
+        raise ValueError(f"Columns {on} must be present in right_df")
+    if how not in ["left", "right", "inner", "outer"]:
+        raise ValueError("Parameter how must be one of left, right, inner, outer")
+    return left_df.merge(right_df[on + missing_from_left], on=on, how=how)
+
+
+def calculate_score_groups(input_df: pd.DataFrame, group_channels: bool = False) -> pd.DataFrame:
+    """alphadia/search/scoring/utils.py:269-410."""
+    if "rank" in input_df.columns:
+        input_df = input_df.sort_values(by=["elution_group_idx", "decoy", "rank", "precursor_idx"])
+        rank_values = input_df["rank"].values
+    else:
+        input_df = input_df.sort_values(by=["elution_group_idx", "decoy", "precursor_idx"])
+        rank_values = np.zeros(len(input_df), dtype=np.uint32)
+    if group_channels:
+        eg = input_df["elution_group_idx"].values
+        decoy = input_df["decoy"].values
+        n = len(eg)
+        if n == 0:
+            groups = np.zeros(0, dtype=np.uint32)
+        else:
+            change = np.zeros(n, dtype=bool)
+            change[1:] = (eg[1:] != eg[:-1]) | (decoy[1:] != decoy[:-1]) | (rank_values[1:] != rank_values[:-1])
+            groups = np.cumsum(change).astype(np.uint32)
+        input_df["score_group_idx"] = groups
+    else:
+        input_df["score_group_idx"] = np.arange(len(input_df), dtype=np.uint32)
+    return input_df.sort_values(by=["score_group_idx", "precursor_idx"]).reset_index(drop=True)
+
+
+class SimpleQuadrupoleJit:
+    """State of alphadia/search/scoring/quadrupole.py:46-78 (uncalibrated: sigma 0.2, delta_mu 0)."""
+
+    def __init__(self, cycle):
+        self.cycle = cycle
+        self.sigma = np.array([0.2, 0.2])
+        self.delta_mu = np.array([0.0, 0.0])
+
+
+class SimpleQuadrupole:
+    """alphadia/search/scoring/quadrupole.py:130-151 without the (feature-unused) calibrated cycle scan."""
+
+    def __init__(self, cycle):
+        self.cycle = cycle
+        self.jit = SimpleQuadrupoleJit(cycle)
+
+
+class CandidateScoring:
+    """Calculate features for each precursor candidate used in scoring."""
+
+    def __init__(
+        self,
+        *,
+        dia_data,
+        precursors_flat: pd.DataFrame,
+        fragments_flat: pd.DataFrame,
+        rt_column: str,
+        mobility_column: str,
+        precursor_mz_column: str,
+        fragment_mz_column: str,
+        config: CandidateScoringConfig | None = None,
+        quadrupole_calibration=None,
+    ):
+        self._dia_data = dia_data
+        self._raw = adapt_dia_data(dia_data)
+
+        precursors_flat_schema.validate(precursors_flat, warn_on_critical_values=True)
+        self.precursors_flat_df = precursors_flat
+
+        fragments_flat_schema.validate(fragments_flat, warn_on_critical_values=True)
+        self.fragments_flat = fragments_flat
+
+        if quadrupole_calibration is None:
+            self.quadrupole_calibration = SimpleQuadrupole(self._raw.cycle)
+        else:
+            self.quadrupole_calibration = quadrupole_calibration
+
+        self.config = CandidateScoringConfig() if config is None else config
+
+        self.rt_column = rt_column
+        self.mobility_column = mobility_column
+        self.precursor_mz_column = precursor_mz_column
+        self.fragment_mz_column = fragment_mz_column
+
+    # ---- properties mirroring the reference ---------------------------------------------------
+    @property
+    def dia_data(self):
+        return self._dia_data
+
+    @property
+    def precursors_flat_df(self) -> pd.DataFrame:
+        return self._precursors_flat_df
+
+    @precursors_flat_df.setter
+    def precursors_flat_df(self, precursors_flat_df) -> None:
+        precursors_flat_schema.validate(precursors_flat_df, warn_on_critical_values=True)
+        self._precursors_flat_df = precursors_flat_df.sort_values(by="precursor_idx")
+
+    @property
+    def fragments_flat_df(self) -> pd.DataFrame:
+        return self._fragments_flat
+
+    @fragments_flat_df.setter
+    def fragments_flat_df(self, fragments_flat: pd.DataFrame) -> None:
+        fragments_flat_schema.validate(fragments_flat, warn_on_critical_values=True)
+        self._fragments_flat = fragments_flat
+
+    @property
+    def quadrupole_calibration(self):
+        return self._quadrupole_calibration
+
+    @quadrupole_calibration.setter
+    def quadrupole_calibration(self, quadrupole_calibration) -> None:
+        if not hasattr(quadrupole_calibration, "jit"):
+            raise AttributeError("quadrupole_calibration must have a jit method")
+        self._quadrupole_calibration = quadrupole_calibration
+
+    @property
+    def config(self) -> CandidateScoringConfig:
+        return self._config
+
+    @config.setter
+    def config(self, config: CandidateScoringConfig) -> None:
+        config.validate()
+        self._config = config
+
+    # ---- marshalling -----------------------------------------------------------------------------
+    def assemble_candidates(self, candidates_df: pd.DataFrame, lib_precursor_idx: np.ndarray):
+        """Replaces assemble_score_group_container (scoring.py:273-353): returns the sorted candidates
+        frame, the ``adb_candidates_in`` struct (+keepalive) and the mask of rows sent to the device."""
+        precursor_columns = [
+            "channel", "flat_frag_start_idx", "flat_frag_stop_idx", "charge", "decoy", "channel",
+            self.precursor_mz_column,
+        ] + _get_isotope_column_names(self.precursors_flat_df.columns)
+        candidates_df = merge_missing_columns(
+            candidates_df, self.precursors_flat_df, precursor_columns, on=["precursor_idx"], how="left"
+        )
+        if "channel" not in candidates_df.columns:
+            candidates_df["channel"] = np.zeros(len(candidates_df), dtype=np.uint8)
+        if "i_0" not in candidates_df.columns:
+            candidates_df["i_0"] = np.ones(len(candidates_df), dtype=np.float32)
+        candidates_df = calculate_score_groups(candidates_df, group_channels=self.config.score_grouped)
+        candidates_schema.validate(candidates_df, warn_on_critical_values=True)
+
+        pidx = candidates_df["precursor_idx"].values
+        sg = candidates_df["score_group_idx"].values
+        # score_group.py:221-226: a precursor may appear once per score group
+        if len(pidx) > 1 and np.any((pidx[1:] == pidx[:-1]) & (sg[1:] == sg[:-1])):
+            raise ValueError("precursor_idx must be unique within a score group")
+        process = np.ones(len(candidates_df), dtype=bool)
+        if self.config.reference_channel >= 0 and len(candidates_df):
+            # score_group.py:49-63: groups without the reference channel are skipped entirely
+            has_ref = candidates_df["channel"].values == self.config.reference_channel
+            groups_with_ref = np.unique(sg[has_ref])
+            process = np.isin(sg, groups_with_ref)
+
+        lib_row = np.searchsorted(lib_precursor_idx, pidx)
+        lib_row = np.minimum(lib_row, max(len(lib_precursor_idx) - 1, 0))
+        if len(pidx) and not np.array_equal(lib_precursor_idx[lib_row], pidx):
+            raise ValueError("candidates_df contains precursor_idx values that are not in precursors_flat")
+        sel = np.flatnonzero(process)
+        cin, keep = _abi.make_candidates_in(
+            lib_row[sel], candidates_df["rank"].values[sel],
+            candidates_df["scan_start"].values[sel], candidates_df["scan_stop"].values[sel],
+            candidates_df["scan_center"].values[sel],
+            candidates_df["frame_start"].values[sel], candidates_df["frame_stop"].values[sel],
+            candidates_df["frame_center"].values[sel],
+        )
+        return candidates_df, cin, keep, sel
+
+    # ---- result collection (scoring.py:394-580) ---------------------------------------------------
+    def collect_candidates(self, candidates_df, psm, feature_columns=None, candidate_columns=None,
+                           precursor_df_columns=None) -> pd.DataFrame:
+        if feature_columns is None:
+            feature_columns = DEFAULT_FEATURE_COLUMNS.copy()
+        if candidate_columns is None:
+            candidate_columns = DEFAULT_CANDIDATE_COLUMNS.copy()
+        if precursor_df_columns is None:
+            precursor_df_columns = DEFAULT_PRECURSOR_COLUMNS.copy()
+        valid = psm["valid"].astype(bool)
+        candidates_psm_df = pd.DataFrame(psm["features"][valid], columns=feature_columns)
+        candidates_psm_df["precursor_idx"] = psm["precursor_idx"][valid]
+        candidates_psm_df["rank"] = psm["rank"][valid]
+        candidates_psm_df = self.merge_candidate_data(candidates_psm_df, candidates_df, candidate_columns)
+        candidates_psm_df = self.merge_precursor_data(
+            candidates_psm_df, self.precursors_flat_df, self.rt_column, self.mobility_column,
+            self.precursor_mz_column, precursor_df_columns,
+        )
+        candidates_psm_df["delta_rt"] = candidates_psm_df["rt_observed"] - candidates_psm_df[self.rt_column]
+        candidates_psm_df["n_K"] = candidates_psm_df["sequence"].str.count("K")
+        candidates_psm_df["n_R"] = candidates_psm_df["sequence"].str.count("R")
+        candidates_psm_df["n_P"] = candidates_psm_df["sequence"].str.count("P")
+        return candidates_psm_df
+
+    @staticmethod
+    def merge_candidate_data(df, candidates_df, candidate_columns=None):
+        if candidate_columns is None:
+            candidate_columns = DEFAULT_CANDIDATE_COLUMNS.copy()
+        candidate_columns += ["score"] if "score" in candidates_df.columns else []
+        return merge_missing_columns(df, candidates_df, candidate_columns, on=["precursor_idx", "rank"], how="left")
+
+    @staticmethod
+    def merge_precursor_data(df, precursors_flat_df, rt_column, mobility_column, precursor_mz_column,
+                             precursor_df_columns=None):
+        if precursor_df_columns is None:
+            precursor_df_columns = DEFAULT_PRECURSOR_COLUMNS.copy()
+        precursor_df_columns = precursor_df_columns + _get_isotope_column_names(precursors_flat_df.columns)
+        for col in [rt_column, mobility_column, precursor_mz_column]:
+            if col not in precursor_df_columns:
+                precursor_df_columns.append(col)
+        return merge_missing_columns(df, precursors_flat_df, precursor_df_columns, on=["precursor_idx"], how="left")
+
+    def collect_fragments(self, candidates_df, psm) -> pd.DataFrame:
+        mask = psm["fragment_mz_library"].reshape(-1) > 0  # output.py:72-90
+        top_k = psm["fragment_mz_library"].shape[1]
+        data = {
+            "precursor_idx": np.repeat(psm["precursor_idx"], top_k)[mask],
+            "rank": np.repeat(psm["rank"], top_k)[mask],
+        }
+        for col in FRAGMENT_COLUMNS[2:]:
+            data[col] = psm["fragment_" + col].reshape(-1)[mask]
+        df = pd.DataFrame(data)
+        return merge_missing_columns(df, self.precursors_flat_df, ["elution_group_idx", "decoy"],
+                                     on=["precursor_idx"], how="left")
+
+    # ---- call ----------------------------------------------------------------------------------
+    def __call__(self, candidates_df, thread_count=10, debug=False, include_decoy_fragment_features=False):
+        logger.info("Starting candidate scoring")
+        del thread_count, include_decoy_fragment_features  # the latter is unused by the reference as well
+
+        if "cardinality" not in self.fragments_flat.columns:  # scoring.py:368-375
+            logger.warning("Fragment cardinality column not found in fragment dataframe. Setting cardinality to 1.")
+            self.fragments_flat["cardinality"] = np.ones(len(self.fragments_flat), dtype=np.uint8)
+        lib_arrays = assemble_library_arrays(
+            self.precursors_flat_df, self.fragments_flat, self.rt_column, self.mobility_column,
+            self.precursor_mz_column, self.fragment_mz_column,
+        )
+        candidates_schema.validate(candidates_df, warn_on_critical_values=True)
+        sorted_df, cin, keep, sel = self.assemble_candidates(candidates_df, lib_arrays["precursor_idx"])
+        n_total = len(sorted_df)
+        if debug:  # scoring.py:628-631: only the first 10 score groups
+            logger.info("Debug mode enabled. Processing only the first 10 score groups")
+            first = np.unique(sorted_df["score_group_idx"].values)[:10]
+            in_first = np.isin(sorted_df["score_group_idx"].values[sel], first)
+            sel = sel[in_first]
+            cin, keep = _abi.make_candidates_in(*(keep[k][in_first] for k in (
+                "lib_row", "rank", "scan_start", "scan_stop", "scan_center", "frame_start", "frame_stop", "frame_center")))
+
+        quad = self.quadrupole_calibration.jit
+        cfg_struct = self.config.to_struct(quad_sigma=quad.sigma, quad_delta_mu=quad.delta_mu)
+        dev_raw = _lib.device_rawfile_for(self._dia_data, self._raw)
+        dev_lib = _lib.DeviceLibrary(lib_arrays, device=dev_raw.device)
+        try:
+            dev_out = _lib.score_candidates(dev_raw, dev_lib, cfg_struct, cin)
+        finally:
+            dev_lib.close()
+        self.last_timing = dev_raw.last_timing()
+
+        # scatter back to the OutputPsmDF layout over ALL candidates (skipped rows stay zero / invalid)
+        top_k = int(self.config.top_k_fragments)
+        if len(sel) == n_total:
+            psm = dev_out
+        else:
+            _, psm = _abi.alloc_scores_out(n_total, top_k)
+            for k, v in dev_out.items():
+                psm[k][sel] = v
+        psm["precursor_idx"] = sorted_df["precursor_idx"].values.astype(np.uint32)
+        psm["rank"] = sorted_df["rank"].values.astype(np.uint8)
+
+        logger.info("Finished candidate processing")
+        logger.info("Collecting candidate features")
+        candidate_features_df = self.collect_candidates(candidates_df, psm)
+        features_schema.validate(candidate_features_df, warn_on_critical_values=True)
+
+        logger.info("Collecting fragment features")
+        fragment_features_df = self.collect_fragments(candidates_df, psm)
+        fragment_features_schema.validate(fragment_features_df, warn_on_critical_values=True)
+
+        logger.info("Finished candidate scoring")
+        return candidate_features_df, fragment_features_df

@@ -191,7 +191,8 @@ int adb_select_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_sele
 int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scoring_config* cfg,
                          const adb_candidates_in* cand, adb_scores_out* out);
 
-/* rt / fragment_mz are f32 when is_f64 == 0, f64 otherwise (the reference computes in the array dtype).
+/* dtype flags (the reference computes in the array dtypes): is_f64 bit 0 = rt is f64 (else f32),
+ * bit 1 = fragment_mz is f64 (else f32).
  * valid: u8 [n_psm], in/out (the reference starts from all-true). */
 int adb_fragment_competition(int device, int64_t n_windows, const int64_t* window_start,
                              const int64_t* window_stop, int64_t n_psm, const void* rt,
@@ -199,25 +200,28 @@ int adb_fragment_competition(int device, int64_t n_windows, const int64_t* windo
                              int64_t n_frag, const void* fragment_mz, int32_t is_f64,
                              double rt_tol_seconds, double mass_tol_ppm, uint8_t* valid);
 
-/* ---- resident / staged variants used by bench.py and the sharded driver -------------------
- * Same kernels; inputs already in HBM, outputs stay in HBM.  Timing with CUDA events on the
- * handle's stream.  (Not needed by a reference-side binding.) */
-typedef struct adb_session adb_session_t;
-int adb_session_create(adb_rawfile_t* raw, adb_library_t* lib, adb_session_t** out);
-void adb_session_destroy(adb_session_t* s);
-/* upload configs + kernel, allocate device outputs for n_precursors*candidate_count rows */
-int adb_session_prepare_selection(adb_session_t* s, const adb_selection_config* cfg, const float* kernel,
-                                  int32_t kernel_h, int32_t kernel_w);
-/* run selection on device; device-side compaction (score > 0) feeds scoring; returns #candidates */
-int adb_session_run_selection(adb_session_t* s, int64_t* n_candidates, float* elapsed_ms);
-int adb_session_prepare_scoring(adb_session_t* s, const adb_scoring_config* cfg);
-int adb_session_run_scoring(adb_session_t* s, float* elapsed_ms);
-/* copy the device-resident results to host buffers (n rows as returned by run_selection) */
-int adb_session_fetch_candidates(adb_session_t* s, adb_candidates_out* out, int64_t* lib_row);
-int adb_session_fetch_scores(adb_session_t* s, adb_scores_out* out);
-/* device pointer + byte size of the packed score table [n, 46] f32 (for the NCCL all-gather) */
-int adb_session_score_table(adb_session_t* s, void** dev_ptr, int64_t* n_rows);
-int64_t adb_session_kernel_launches(const adb_session_t* s);
+/* ---- resident variants (bench.py `value`, the sharded driver) -------------------------------
+ * Same kernels; the raw file and library are already in HBM, results stay in HBM inside the raw
+ * handle's workspace until fetched.  (Not needed by a reference-side binding.) */
+/* selection + device-side compaction of rows with score > 0 (CandidateContainer.get_candidate_df_data,
+ * config_df.py:270-284) into scoring input order (library row, rank); returns the candidate count */
+int adb_select_candidates_resident(adb_rawfile_t* raw, adb_library_t* lib, const adb_selection_config* cfg,
+                                   const float* kernel, int32_t kernel_h, int32_t kernel_w, int64_t* n_candidates);
+/* scores the resident candidates; outputs stay on the device */
+int adb_score_candidates_resident(adb_rawfile_t* raw, adb_library_t* lib, const adb_scoring_config* cfg);
+/* D2H of the resident results: the full candidate container (n_precursors * candidate_count rows) ... */
+int adb_fetch_candidates(adb_rawfile_t* raw, adb_candidates_out* container);
+/* ... and the score tables of the n resident candidates with their identity (lib_row / rank may be NULL) */
+int adb_fetch_scores(adb_rawfile_t* raw, adb_scores_out* out, int64_t* lib_row, uint8_t* rank);
+/* device pointers of the resident score table: features f32 [n, 46], valid u8 [n], lib_row i64 [n], rank u8 [n] */
+int adb_resident_score_table(adb_rawfile_t* raw, void** features, void** valid, void** lib_row, void** rank,
+                             int64_t* n_rows);
+
+/* timing of the last call on this handle, CUDA events on the handle's stream (ms) + kernel launches so far */
+int adb_last_timing(const adb_rawfile_t* raw, float* h2d_ms, float* kernel_ms, float* d2h_ms);
+int64_t adb_kernel_launches(const adb_rawfile_t* raw);
+/* CUDA stream the handle launches on (cudaStream_t as void*) */
+void* adb_rawfile_stream(const adb_rawfile_t* raw);
 
 #ifdef __cplusplus
 }

@@ -113,10 +113,11 @@ def fragment_competition(window_start, window_stop, rt, frag_start, frag_stop, f
     we = _abi.as_c(window_stop, np.int64)
     fs = _abi.as_c(frag_start, np.int64)
     fe = _abi.as_c(frag_stop, np.int64)
-    is_f64 = int(np.asarray(fragment_mz).dtype == np.float64 or np.asarray(rt).dtype == np.float64)
-    dt = np.float64 if is_f64 else np.float32
-    rt_c = _abi.as_c(rt, dt)
-    mz_c = _abi.as_c(fragment_mz, dt)
+    rt_f64 = np.asarray(rt).dtype == np.float64
+    mz_f64 = np.asarray(fragment_mz).dtype == np.float64
+    is_f64 = int(rt_f64) | (int(mz_f64) << 1)
+    rt_c = _abi.as_c(rt, np.float64 if rt_f64 else np.float32)
+    mz_c = _abi.as_c(fragment_mz, np.float64 if mz_f64 else np.float32)
     v = np.ones(len(rt_c), np.uint8) if valid is None else _abi.as_c(valid, np.uint8).copy()
     rc = L.adbo_fragment_competition(C.c_int64(len(ws)), _abi.ptr(ws), _abi.ptr(we), C.c_int64(len(rt_c)),
                                      rt_c.ctypes.data_as(C.c_void_p), _abi.ptr(fs), _abi.ptr(fe), C.c_int64(len(mz_c)),

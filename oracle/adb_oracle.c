@@ -1307,11 +1307,11 @@ int adbo_fragment_competition(int64_t n_windows, const int64_t* window_start, co
         if (i == j) continue;
         if (!valid[j]) continue;
         double drt;
-        if (is_f64) drt = fabs(((const double*)rt)[i] - ((const double*)rt)[j]);
+        if (is_f64 & 1) drt = fabs(((const double*)rt)[i] - ((const double*)rt)[j]);
         else drt = (double)fabsf(((const float*)rt)[i] - ((const float*)rt)[j]);
         if (drt < rt_tol_seconds) {
           int ov;
-          if (is_f64)
+          if (is_f64 & 2)
             ov = overlap_f64((const double*)fragment_mz + frag_start_idx[i], (int)(frag_stop_idx[i] - frag_start_idx[i]),
                              (const double*)fragment_mz + frag_start_idx[j], (int)(frag_stop_idx[j] - frag_start_idx[j]), mass_tol_ppm);
           else

@@ -1,0 +1,278 @@
+"""GPU parity: the CUDA path (through the C ABI) vs the C oracle on identical seeded inputs, and vs the
+committed golden vectors of the reference.  Runs on the B200 box (``-m gpu``)."""
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+INT_COLS = ["precursor_idx", "rank", "scan_center", "scan_start", "scan_stop", "frame_center", "frame_start", "frame_stop"]
+FRAG_F32 = ["fragment_mz_library", "fragment_mz", "fragment_mz_observed", "fragment_height", "fragment_intensity",
+            "fragment_mass_error", "fragment_correlation"]
+FRAG_U8 = ["fragment_position", "fragment_number", "fragment_type", "fragment_charge", "fragment_loss_type"]
+# float tolerance of BASELINE.json north_star: 1e-4 relative (absolute floor 1e-6 on the feature scale)
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from alphadia_b200 import _lib
+
+    _lib.require_device()
+    return _lib
+
+
+def _device_objects(engine, name):
+    raw, pdf, fdf, lib, p = H.workload(name)
+    return raw, lib, p, engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+
+
+def assert_candidates_equal(a, b):
+    for c in INT_COLS:
+        assert np.array_equal(a[c], b[c]), c
+    assert np.array_equal(a["score"], b["score"]), "score (f32) must be bit-identical"
+
+
+def feature_scale_floor(F):
+    # absolute floor per feature column: 1e-6 of the column's typical magnitude, at least 1e-6
+    s = np.nanmedian(np.abs(F), axis=0)
+    return np.maximum(1e-6, 1e-6 * np.where(np.isfinite(s), s, 0.0))
+
+
+def assert_scores_close(a, b, what=""):
+    assert np.array_equal(a["valid"], b["valid"]), f"{what} valid mask"
+    v = a["valid"].astype(bool)
+    Fa, Fb = a["features"][v], b["features"][v]
+    nan_a, nan_b = np.isnan(Fa), np.isnan(Fb)
+    assert np.array_equal(nan_a, nan_b), f"{what} NaN pattern"
+    floor = feature_scale_floor(Fb)
+    err = np.abs(Fa - Fb) / np.maximum(np.maximum(np.abs(Fa), np.abs(Fb)), floor[None, :])
+    err = np.where(nan_a, 0.0, err)
+    worst = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() < RTOL, f"{what} feature {worst[1]} row {worst[0]}: {Fa[worst]} vs {Fb[worst]} (rel {err.max():.3e})"
+    for k in FRAG_U8:
+        assert np.array_equal(a[k], b[k]), f"{what} {k}"
+    for k in FRAG_F32:
+        x, y = a[k], b[k]
+        assert np.array_equal(x > 0, y > 0) or k not in ("fragment_mz_library", "fragment_mz"), k
+        e = H.rel_err(x, y, floor=1e-6).max() if x.size else 0.0
+        assert e < RTOL, f"{what} {k}: rel {e:.3e}"
+
+
+@pytest.mark.parametrize("name", ["config1", "parity_small"])
+def test_selection_matches_oracle_and_golden(engine, oracle_lib, name):
+    raw, lib, p, draw, dlib = _device_objects(engine, name)
+    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    kernel = H.default_kernel(raw)
+    got = engine.select_candidates(draw, dlib, cfg, kernel)
+    ref = oracle_lib.select_candidates(raw, lib, cfg, kernel)
+    assert_candidates_equal(got, ref)
+    g = H.load_golden(name)
+    if g is not None and str(g["input_checksum"]) == H.input_checksum(*H.workload(name)[:3]):
+        m = got["score"] > 0
+        assert m.sum() == len(g["cand_precursor_idx"])
+        for c in INT_COLS:
+            assert np.array_equal(got[c][m].astype(np.int64), g["cand_" + c].astype(np.int64)), c
+        assert np.array_equal(got["score"][m], g["cand_score"])
+    dlib.close(); draw.close()
+
+
+@pytest.mark.parametrize("kw", [dict(candidate_count=1), dict(candidate_count=5, join_close_candidates=True,
+                                                               join_close_candidates_scan_threshold=0.01),
+                                dict(use_weighted_score=False), dict(rt_tolerance=8.0), dict(rt_tolerance=400.0)])
+def test_selection_config_variants(engine, oracle_lib, kw):
+    raw, lib, p, draw, dlib = _device_objects(engine, "parity_small")
+    args = dict(kw)
+    rt_tol = args.pop("rt_tolerance", p["rt_tolerance"])
+    cfg = H.selection_config(rt_tol, **args).to_struct()
+    kernel = H.default_kernel(raw)
+    got = engine.select_candidates(draw, dlib, cfg, kernel)
+    ref = oracle_lib.select_candidates(raw, lib, cfg, kernel)
+    assert_candidates_equal(got, ref)
+    assert (got["score"] > 0).sum() > 0
+    dlib.close(); draw.close()
+
+
+SCORING_VARIANTS = {
+    "default": {},
+    "legacy": dict(quant_all=False, experimental_xic=False),
+    "k6": dict(top_k_fragments=6, top_k_isotopes=4, quant_window=2),
+    "qall_legacy_xic": dict(quant_all=True, experimental_xic=False),
+    "noqall_xic": dict(quant_all=False, experimental_xic=True),
+}
+
+
+def _candidates(oracle_lib, raw, lib, p):
+    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    arrs = oracle_lib.select_candidates(raw, lib, cfg, H.default_kernel(raw))
+    m = arrs["score"] > 0
+    return {c: arrs[c][m] for c in INT_COLS}
+
+
+@pytest.mark.parametrize("name", ["config1", "parity_small"])
+@pytest.mark.parametrize("variant", list(SCORING_VARIANTS))
+def test_scoring_matches_oracle(engine, oracle_lib, name, variant):
+    raw, lib, p, draw, dlib = _device_objects(engine, name)
+    cand = _candidates(oracle_lib, raw, lib, p)
+    cin, keep = H.candidates_in_from_arrays(lib, cand)
+    cfg = H.scoring_config(**SCORING_VARIANTS[variant]).to_struct()
+    got = engine.score_candidates(draw, dlib, cfg, cin)
+    ref = oracle_lib.score_candidates(raw, lib, cfg, cin)
+    assert ref["valid"].sum() > 50
+    assert_scores_close(got, ref, what=f"{name}/{variant}")
+    dlib.close(); draw.close()
+
+
+def test_scoring_matches_reference_golden(engine):
+    name = "parity_small"
+    g = H.load_golden(name)
+    raw, pdf, fdf, lib, p = H.workload(name)
+    if g is None or str(g["input_checksum"]) != H.input_checksum(raw, pdf, fdf):
+        pytest.skip("golden not applicable")
+    draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+    cand = {c: g["cand_" + c] for c in INT_COLS}
+    cin, keep = H.candidates_in_from_arrays(lib, cand)
+    got = engine.score_candidates(draw, dlib, H.scoring_config().to_struct(), cin)
+    v = got["valid"].astype(bool)
+    assert np.array_equal(keep["precursor_idx"][v], g["feat_precursor_idx"])
+    assert np.array_equal(keep["rank"][v], g["feat_rank"])
+    F, G = got["features"][v], g["feat_matrix"]
+    floor = feature_scale_floor(G)
+    err = np.abs(F - G) / np.maximum(np.maximum(np.abs(F), np.abs(G)), floor[None, :])
+    err = np.where(np.isnan(F) & np.isnan(G), 0.0, err)
+    assert err.max() < RTOL
+    dlib.close(); draw.close()
+
+
+def test_scoring_edge_cases(engine, oracle_lib):
+    """Ragged / degenerate candidates: empty table, tiny and huge windows, clamped limits, too few fragments."""
+    raw, pdf, fdf, lib, p = H.workload("parity_small")
+    draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+    cfg = H.scoring_config().to_struct()
+    L = raw.cycle_len
+    # empty
+    cin, _ = H.candidates_in_from_arrays(lib, {c: np.zeros(0, np.int64) for c in INT_COLS})
+    got = engine.score_candidates(draw, dlib, cfg, cin)
+    assert got["features"].shape == (0, 46)
+    # hand-made windows of many widths, including the first/last cycles of the run
+    rng = np.random.default_rng(5)
+    n = 400
+    pidx = rng.integers(0, len(pdf), n)
+    centers = rng.integers(0, raw.precursor_cycle_max_index, n)
+    half = rng.choice([0, 1, 2, 3, 7, 14, 40, 120], n)
+    c0 = np.clip(centers - half, 0, raw.precursor_cycle_max_index - 1)
+    c1 = np.clip(centers + half + 1, 1, raw.precursor_cycle_max_index)
+    cand = dict(precursor_idx=lib["precursor_idx"][pidx].astype(np.int64), rank=np.arange(n) % 7,
+                scan_center=np.zeros(n, np.int64), scan_start=np.zeros(n, np.int64), scan_stop=np.ones(n, np.int64),
+                frame_center=np.minimum(centers * L, raw.frame_max_index), frame_start=c0 * L,
+                frame_stop=np.minimum(c1 * L, raw.frame_max_index))
+    cin, keep = H.candidates_in_from_arrays(lib, cand)
+    got = engine.score_candidates(draw, dlib, cfg, cin)
+    ref = oracle_lib.score_candidates(raw, lib, cfg, cin)
+    assert_scores_close(got, ref, what="edge")
+    dlib.close(); draw.close()
+
+
+def test_operator_classes_end_to_end(engine, oracle_lib):
+    """The reference-shaped Python API: CandidateSelection -> CandidateScoring -> FragmentCompetition."""
+    from alphadia_b200 import CandidateScoring, CandidateSelection, FragmentCompetition
+    from alphadia_b200.scoring import DEFAULT_FEATURE_COLUMNS
+
+    raw, pdf, fdf, lib, p = H.workload("parity_small")
+    sel = CandidateSelection(raw, pdf.copy(), fdf.copy(), H.selection_config(p["rt_tolerance"]),
+                             rt_column="rt_library", mobility_column="mobility_library",
+                             precursor_mz_column="mz_library", fragment_mz_column="mz_library", fwhm_rt=5.0,
+                             fwhm_mobility=0.01)
+    cand_df = sel(thread_count=4)
+    assert list(cand_df.columns) == ["precursor_idx", "rank", "score", "scan_center", "scan_start", "scan_stop",
+                                     "frame_center", "frame_start", "frame_stop", "elution_group_idx", "decoy"]
+    ref = oracle_lib.select_candidates(raw, lib, H.selection_config(p["rt_tolerance"]).to_struct(), sel.kernel)
+    m = ref["score"] > 0
+    for c in INT_COLS:
+        assert np.array_equal(cand_df[c].values.astype(np.int64), ref[c][m].astype(np.int64))
+
+    scorer = CandidateScoring(dia_data=raw, precursors_flat=pdf.copy(), fragments_flat=fdf.copy(),
+                              config=H.scoring_config(), rt_column="rt_library", mobility_column="mobility_library",
+                              precursor_mz_column="mz_library", fragment_mz_column="mz_library")
+    feat_df, frag_df = scorer(cand_df.copy(), thread_count=4, include_decoy_fragment_features=True)
+    assert list(feat_df.columns[:46]) == DEFAULT_FEATURE_COLUMNS
+    for c in ["precursor_idx", "rank", "elution_group_idx", "decoy", "charge", "delta_rt", "n_K", "n_R", "n_P", "score",
+              "rt_library", "mz_library", "i_0", "proteins", "genes", "sequence"]:
+        assert c in feat_df.columns, c
+    assert list(frag_df.columns) == ["precursor_idx", "rank", "mz_library", "mz", "mz_observed", "height", "intensity",
+                                     "mass_error", "correlation", "position", "number", "type", "charge", "loss_type",
+                                     "elution_group_idx", "decoy"]
+    g = H.load_golden("parity_small")
+    if g is not None and str(g["input_checksum"]) == H.input_checksum(raw, pdf, fdf):
+        assert np.array_equal(feat_df["precursor_idx"].values, g["feat_precursor_idx"])
+        assert len(frag_df) == len(g["frag_mz_library"])
+        np.testing.assert_allclose(feat_df["delta_rt"].values, g["feat_delta_rt"], rtol=1e-4, atol=1e-4)
+
+    psm = feat_df.copy()
+    psm["proba"] = np.random.default_rng(12345).uniform(0, 1, size=len(psm))
+    fc = FragmentCompetition(rt_tol_seconds=3, mass_tol_ppm=15)
+    plan = fc.plan(psm.copy(), frag_df.copy(), raw.cycle)
+    ref_valid = oracle_lib.fragment_competition(plan.window_start, plan.window_stop, plan.rt, plan.frag_start,
+                                                plan.frag_stop, plan.fragment_mz, 3, 15)
+    kept = fc(psm.copy(), frag_df.copy(), raw.cycle)
+    assert np.array_equal(kept["_candidate_idx"].values, plan.psm_df["_candidate_idx"].values[ref_valid])
+
+
+@pytest.mark.parametrize("dtype_rt,dtype_mz", [(np.float32, np.float32), (np.float64, np.float32), (np.float64, np.float64)])
+def test_fragcomp_dense_competition(engine, oracle_lib, dtype_rt, dtype_mz):
+    """Many PSMs sharing fragments inside few windows (the golden runs have no collisions)."""
+    rng = np.random.default_rng(7)
+    n, nwin = 6000, 5
+    base = rng.uniform(200, 1800, size=(300, 12))
+    src = rng.integers(0, 300, n)
+    mz = base[src] * (1 + rng.normal(0, 4e-6, size=(n, 12)))
+    replace = rng.random((n, 12)) < 0.7
+    mz = np.where(replace, rng.uniform(200, 1800, size=(n, 12)), mz)
+    nfr = rng.integers(4, 13, n)
+    frag_start = np.concatenate([[0], np.cumsum(nfr)[:-1]])
+    frag_stop = frag_start + nfr
+    frag_mz = np.concatenate([np.sort(mz[i, : nfr[i]]) for i in range(n)]).astype(dtype_mz)
+    rt = rng.uniform(0, 600, n).astype(dtype_rt)
+    bounds = np.linspace(0, n, nwin + 1).astype(np.int64)
+    ws, we = bounds[:-1], bounds[1:]
+    ref = oracle_lib.fragment_competition(ws, we, rt, frag_start, frag_stop, frag_mz, 3.0, 15.0)
+    got = engine.fragment_competition(ws, we, rt, frag_start, frag_stop, frag_mz, 3.0, 15.0, device=0)
+    assert ref.sum() < n  # something was vetoed
+    assert np.array_equal(got, ref)
+
+
+def test_fragcomp_reference_known_answers(engine):
+    """Known-answer vectors of the reference's own unit tests (tests/unit_tests/fragcomp/test_fragcomp.py:38-58)."""
+    rt = np.array([10.0, 10.0, 10.0, 20.0, 20.0, 20.0])
+    valid_expected = np.array([True, True, False, True, False, True])
+    frag_start = np.array([0, 10, 20, 30, 40, 50])
+    frag_stop = frag_start + 10
+    fragment_mz = np.hstack([np.arange(100, 110), np.arange(200, 210), np.arange(100, 110),
+                             np.arange(100, 110), np.arange(100, 110), np.arange(200, 210)]).astype(np.float64)
+    got = engine.fragment_competition(np.array([0, 3]), np.array([3, 6]), rt, frag_start, frag_stop, fragment_mz, 10.0, 10.0, device=0)
+    assert np.array_equal(got, valid_expected)
+
+
+def test_resident_pipeline_matches_host_pipeline(engine):
+    raw, lib, p, draw, dlib = _device_objects(engine, "parity_small")
+    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    kernel = H.default_kernel(raw)
+    host = engine.select_candidates(draw, dlib, cfg, kernel)
+    n = engine.select_candidates_resident(draw, dlib, cfg, kernel)
+    m = host["score"] > 0
+    assert n == m.sum()
+    scfg = H.scoring_config().to_struct()
+    engine.score_candidates_resident(draw, dlib, scfg)
+    res = engine.fetch_scores(draw, n, 12)
+    cand = {c: host[c][m] for c in INT_COLS}
+    cin, keep = H.candidates_in_from_arrays(lib, cand)
+    ref = engine.score_candidates(draw, dlib, scfg, cin)
+    assert np.array_equal(res["rank"], keep["rank"])
+    assert np.array_equal(lib["precursor_idx"][res["lib_row"]], keep["precursor_idx"])
+    assert np.array_equal(res["valid"], ref["valid"])
+    assert np.array_equal(res["features"], ref["features"], equal_nan=True)
+    assert draw.kernel_launches > 0
+    dlib.close(); draw.close()

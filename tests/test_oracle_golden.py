@@ -1,0 +1,103 @@
+"""Pin the C oracle against golden vectors produced by the UNMODIFIED reference numba path
+(tests/golden/generate_golden.py, run in the build container).  CPU only."""
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+INT_COLS = ["precursor_idx", "rank", "scan_center", "scan_start", "scan_stop", "frame_center", "frame_start", "frame_stop"]
+FRAG_MAP = {
+    "mz_library": "fragment_mz_library", "mz": "fragment_mz", "mz_observed": "fragment_mz_observed",
+    "height": "fragment_height", "intensity": "fragment_intensity", "mass_error": "fragment_mass_error",
+    "correlation": "fragment_correlation", "position": "fragment_position", "number": "fragment_number",
+    "type": "fragment_type", "charge": "fragment_charge", "loss_type": "fragment_loss_type",
+}
+VARIANTS = {
+    "": {},
+    "_legacy": dict(quant_all=False, experimental_xic=False),
+    "_k6": dict(top_k_fragments=6, top_k_isotopes=4, quant_window=2),
+}
+# features whose reference value goes through BLAS dots (np.dot / np.corrcoef): summation order is
+# unspecified there, everything else must match the reference bit for bit.
+BLAS_FEATURES = {18, 19, 31, 32, 33, 34, 36}
+
+
+def _golden(name):
+    g = H.load_golden(name)
+    if g is None:
+        pytest.skip(f"golden {name} missing")
+    raw, pdf, fdf, lib, p = H.workload(name)
+    if str(g["input_checksum"]) != H.input_checksum(raw, pdf, fdf):
+        pytest.skip("synthetic generator output differs from the one the golden file was made with (numpy version?)")
+    return g, raw, lib, p
+
+
+@pytest.mark.parametrize("name", ["config1", "parity_small"])
+def test_gaussian_kernel_matches_reference(name):
+    g, raw, lib, p = _golden(name)
+    k = H.default_kernel(raw)
+    assert k.dtype == np.float32 and k.shape == g["sel_kernel"].shape
+    np.testing.assert_allclose(k, g["sel_kernel"], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("name", ["config1", "parity_small"])
+def test_selection_bit_exact_vs_reference(name, oracle_lib):
+    g, raw, lib, p = _golden(name)
+    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    arrs = oracle_lib.select_candidates(raw, lib, cfg, g["sel_kernel"])
+    m = arrs["score"] > 0
+    assert m.sum() == len(g["cand_precursor_idx"])
+    for c in INT_COLS:
+        assert np.array_equal(arrs[c][m].astype(np.int64), g["cand_" + c].astype(np.int64)), c
+    assert np.array_equal(arrs["score"][m], g["cand_score"])  # f32, bit-exact
+
+
+@pytest.mark.parametrize("name,tag", [("config1", ""), ("parity_small", ""), ("parity_small", "_legacy"), ("parity_small", "_k6")])
+def test_scoring_vs_reference(name, tag, oracle_lib):
+    g, raw, lib, p = _golden(name)
+    cand = {c: g["cand_" + c] for c in INT_COLS}
+    cin, keep = H.candidates_in_from_arrays(lib, cand)
+    cfg = H.scoring_config(**VARIANTS[tag]).to_struct()
+    arrs = oracle_lib.score_candidates(raw, lib, cfg, cin)
+    v = arrs["valid"].astype(bool)
+    assert np.array_equal(keep["precursor_idx"][v], g[f"feat{tag}_precursor_idx"])
+    assert np.array_equal(keep["rank"][v], g[f"feat{tag}_rank"])
+    F, G = arrs["features"][v], g[f"feat{tag}_matrix"]
+    for j in range(46):
+        same = (F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))
+        if j in BLAS_FEATURES:
+            assert H.rel_err(F[:, j], G[:, j]).max() < 1e-4, j  # tolerance of BASELINE.json north_star
+        else:
+            assert same.all(), f"feature {j} not bit-exact"
+    m = arrs["fragment_mz_library"] > 0
+    assert m.sum() == len(g[f"frag{tag}_mz_library"])
+    for k, v2 in FRAG_MAP.items():
+        a, b = arrs[v2][m], g[f"frag{tag}_{k}"]
+        if k == "correlation":
+            assert H.rel_err(a, b).max() < 1e-4
+        else:
+            assert np.array_equal(a, b), k
+
+
+@pytest.mark.parametrize("name", ["config1", "parity_small"])
+def test_fragcomp_vs_reference(name, oracle_lib):
+    """FragmentCompetition on the golden feature table with the golden pseudo-proba."""
+    from alphadia_b200.fragcomp import FragmentCompetition, plan_fragment_competition
+
+    g, raw, lib, p = _golden(name)
+    import pandas as pd
+
+    psm = pd.DataFrame({"precursor_idx": g["feat_precursor_idx"], "rank": g["feat_rank"],
+                        "rt_observed": g["feat_matrix"][:, 2], "mz_observed": g["feat_matrix"][:, 10],
+                        "proba": g["fc_proba"]})
+    frag = pd.DataFrame({"precursor_idx": g["frag_precursor_idx"], "rank": g["frag_rank"],
+                         "mz_observed": g["frag_mz_observed"]})
+    plan = plan_fragment_competition(psm, frag, raw.cycle)
+    valid = oracle_lib.fragment_competition(plan.window_start, plan.window_stop, plan.rt, plan.frag_start, plan.frag_stop,
+                                            plan.fragment_mz, 3, 15)
+    kept = plan.psm_df[valid]
+    assert np.array_equal(kept["precursor_idx"].values, g["fc_kept_precursor_idx"])
+    assert np.array_equal(kept["rank"].values, g["fc_kept_rank"])
+    assert np.array_equal(kept["_candidate_idx"].values, g["fc_kept_candidate_idx"])
+    assert FragmentCompetition is not None
