@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "adb_select_candidates", "adb_score_candidates", "adb_fragment_competition",
     "adb_select_candidates_resident", "adb_score_candidates_resident",
     "adb_fetch_candidates", "adb_fetch_scores", "adb_resident_score_table",
-    "adb_last_timing", "adb_kernel_launches",
+    "adb_last_timing", "adb_kernel_launches", "adb_last_main_kernel_ms",
 ]
 
 _lib = None
@@ -54,6 +54,8 @@ def load() -> C.CDLL:
     lib.adb_rawfile_stream.argtypes = [C.c_void_p]
     lib.adb_kernel_launches.restype = C.c_int64
     lib.adb_kernel_launches.argtypes = [C.c_void_p]
+    lib.adb_last_main_kernel_ms.restype = C.c_float
+    lib.adb_last_main_kernel_ms.argtypes = [C.c_void_p]
     lib.adb_rawfile_destroy.argtypes = [C.c_void_p]
     lib.adb_rawfile_destroy.restype = None
     lib.adb_library_destroy.argtypes = [C.c_void_p]
@@ -106,7 +108,8 @@ class DeviceRawFile:
     def last_timing(self) -> dict:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         self._lib.adb_last_timing(self.handle, C.byref(a), C.byref(b), C.byref(c))
-        return dict(h2d_ms=a.value, kernel_ms=b.value, d2h_ms=c.value)
+        return dict(h2d_ms=a.value, kernel_ms=b.value, d2h_ms=c.value,
+                    main_kernel_ms=float(self._lib.adb_last_main_kernel_ms(self.handle)))
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle:

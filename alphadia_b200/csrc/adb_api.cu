@@ -84,8 +84,8 @@ struct adb_rawfile {
   int64_t bytes = 0;
   std::vector<float> rt_host;  // host copy of rt_values (to bound the cycle window on the host)
   uint32_t* d_status = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  float h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 4,5 bracket the main kernel
+  float h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, main_kernel_ms = 0;
   int launches = 0;
   int sm_count = 148;
   // cached workspaces
@@ -291,8 +291,10 @@ int run_selection(adb_rawfile* raw, adb_library* lib, const adb_selection_config
     if (raw->sel_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)grid)) return 1;
     d_ws = raw->sel_ws.as<float>();
   }
+  CUDA_TRY(cudaEventRecord(raw->ev[4], st));
   adb_launch_select_ex(raw->dev, lib->dev, *cfg, raw->kern.as<double>(), kh, kw, raw->d_cont, 0, P, d_order, raw->d_status,
                        c_cap, max_layers, d_ws, ws_floats, grid, st, &raw->launches);
+  CUDA_TRY(cudaEventRecord(raw->ev[5], st));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -339,8 +341,10 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   int64_t c_max = std::max<int64_t>(c_max_hint, 32);
   int64_t ws_floats = (adb_score_workspace_floats(K, c_max) + 3) & ~(int64_t)3;
   if (raw->score_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)warps)) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[4], st));
   adb_launch_score(raw->dev, lib->dev, *cfg, raw->d_cand, raw->d_scores, raw->score_ws.as<float>(), ws_floats, warps,
                    raw->d_status, st, &raw->launches);
+  CUDA_TRY(cudaEventRecord(raw->ev[5], st));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -350,6 +354,7 @@ void finish_timing(adb_rawfile* raw) {
   cudaEventElapsedTime(&raw->h2d_ms, raw->ev[0], raw->ev[1]);
   cudaEventElapsedTime(&raw->kernel_ms, raw->ev[1], raw->ev[2]);
   cudaEventElapsedTime(&raw->d2h_ms, raw->ev[2], raw->ev[3]);
+  cudaEventElapsedTime(&raw->main_kernel_ms, raw->ev[4], raw->ev[5]);
 }
 
 }  // namespace
@@ -373,7 +378,7 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
   adb_rawfile* r = new adb_rawfile();
   r->device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&r->ev[i]));
+  for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&r->ev[i]));
   cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, device);
   DevRaw& v = r->dev;
   double* cyc; float *rt, *mob, *mz, *it; int64_t *ps, *pe;
@@ -419,7 +424,7 @@ void adb_rawfile_destroy(adb_rawfile_t* r) {
   DeviceBuffer* bufs[] = {&r->kern, &r->order_keys, &r->order_vals, &r->order_tmp, &r->sel_ws, &r->cont, &r->cand_in,
                           &r->flags, &r->offs, &r->scan_tmp, &r->count, &r->scores, &r->score_ws, &r->staging};
   for (DeviceBuffer* b : bufs) b->release();
-  for (int i = 0; i < 4; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
+  for (int i = 0; i < 6; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
   if (r->stream) cudaStreamDestroy(r->stream);
   delete r;
 }
@@ -617,6 +622,7 @@ int adb_last_timing(const adb_rawfile_t* raw, float* h2d_ms, float* kernel_ms, f
 }
 
 int64_t adb_kernel_launches(const adb_rawfile_t* raw) { return raw ? raw->launches : 0; }
+float adb_last_main_kernel_ms(const adb_rawfile_t* raw) { return raw ? raw->main_kernel_ms : 0.f; }
 
 int adb_fragment_competition(int device, int64_t n_windows, const int64_t* window_start, const int64_t* window_stop,
                              int64_t n_psm, const void* rt, const int64_t* frag_start_idx, const int64_t* frag_stop_idx,

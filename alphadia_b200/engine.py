@@ -1,0 +1,116 @@
+"""One hot-path "step" = candidate selection + candidate scoring of one library batch against one raw file.
+
+Two ways to run it, both through the C ABI:
+
+* ``resident_step``: raw file and library already in HBM, results stay in HBM
+  (``adb_select_candidates_resident`` -> device compaction -> ``adb_score_candidates_resident``).
+* ``host_step``: what the reference-facing operators do — library upload, selection with the candidate
+  container copied back, the ``score > 0`` filter on the host, candidate table upload, scoring, score and
+  fragment tables copied back.  Host buffers may be pinned by the caller.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from alphadia_b200 import _abi, _lib
+
+CAND_COLS = ("scan_start", "scan_stop", "scan_center", "frame_start", "frame_stop", "frame_center")
+
+
+class HotPath:
+    def __init__(self, raw, lib_arrays: dict, sel_cfg, score_cfg, kernel: np.ndarray, device: int | None = None,
+                 quad_sigma=(0.2, 0.2), quad_delta_mu=(0.0, 0.0)):
+        self.lib_arrays = lib_arrays
+        self.sel_struct = sel_cfg.to_struct() if hasattr(sel_cfg, "to_struct") else sel_cfg
+        self.score_struct = (score_cfg.to_struct(quad_sigma=quad_sigma, quad_delta_mu=quad_delta_mu)
+                             if hasattr(score_cfg, "to_struct") else score_cfg)
+        self.kernel = np.ascontiguousarray(kernel, dtype=np.float32)
+        self.dev_raw = _lib.DeviceRawFile(raw, device=device)
+        self.dev_lib = _lib.DeviceLibrary(lib_arrays, device=self.dev_raw.device)
+        self.n_precursors = self.dev_lib.n_precursors
+        self.top_k = int(self.score_struct.top_k_fragments)
+        self.n_candidates = 0
+        self._host_bufs = None
+
+    # ---- resident ---------------------------------------------------------------------------------
+    def resident_step(self) -> dict:
+        n = _lib.select_candidates_resident(self.dev_raw, self.dev_lib, self.sel_struct, self.kernel)
+        t_sel = self.dev_raw.last_timing()
+        _lib.score_candidates_resident(self.dev_raw, self.dev_lib, self.score_struct)
+        t_sc = self.dev_raw.last_timing()
+        self.n_candidates = n
+        return dict(n_candidates=n, select_ms=t_sel["kernel_ms"], score_ms=t_sc["kernel_ms"],
+                    select_kernel_ms=t_sel["main_kernel_ms"], score_kernel_ms=t_sc["main_kernel_ms"])
+
+    def fetch(self) -> dict:
+        return _lib.fetch_scores(self.dev_raw, self.n_candidates, self.top_k)
+
+    def score_table_pointers(self):
+        f, v, r, k = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_int64()
+        _lib.check(_lib.load().adb_resident_score_table(self.dev_raw.handle, C.byref(f), C.byref(v), C.byref(r),
+                                                        C.byref(k), C.byref(n)), "adb_resident_score_table")
+        return dict(features=f.value, valid=v.value, lib_row=r.value, rank=k.value, n=int(n.value))
+
+    # ---- host buffers (the operator path) -----------------------------------------------------------
+    def host_step(self, alloc=np.zeros) -> dict:
+        """alloc(shape, dtype) -> ndarray lets the caller provide pinned host memory."""
+        lib = _lib.load()
+        n_rows = int(self.n_precursors * self.sel_struct.candidate_count)
+        if self._host_bufs is None or self._host_bufs["n_rows"] != n_rows:
+            cont = {k: alloc(n_rows, dt) for k, dt in (
+                ("precursor_idx", np.uint32), ("rank", np.uint8), ("score", np.float32), ("scan_center", np.uint32),
+                ("scan_start", np.uint32), ("scan_stop", np.uint32), ("frame_center", np.uint32),
+                ("frame_start", np.uint32), ("frame_stop", np.uint32))}
+            self._host_bufs = dict(n_rows=n_rows, cont=cont, scores=None, scores_n=0)
+        cont = self._host_bufs["cont"]
+        # library H2D (the operators re-upload the library batch on every call)
+        dev_lib = _lib.DeviceLibrary(self.lib_arrays, device=self.dev_raw.device)
+        h2d = sum(int(v.nbytes) for v in self.lib_arrays.values())
+        try:
+            od = _abi.CandidatesOut()
+            od.n_rows = n_rows
+            for k, v in cont.items():
+                setattr(od, k, _abi.ptr(v))
+            _lib.check(lib.adb_select_candidates(self.dev_raw.handle, dev_lib.handle, C.byref(self.sel_struct),
+                                                 _abi.ptr(self.kernel), C.c_int32(self.kernel.shape[0]),
+                                                 C.c_int32(self.kernel.shape[1]), C.byref(od)), "adb_select_candidates")
+            d2h = sum(int(v.nbytes) for v in cont.values())
+            mask = cont["score"] > 0
+            rows = np.flatnonzero(mask)
+            n = len(rows)
+            cand = dict(lib_row=(rows // int(self.sel_struct.candidate_count)).astype(np.int64),
+                        rank=cont["rank"][rows])
+            for k in CAND_COLS:
+                cand[k] = cont[k][rows].astype(np.int64)
+            cin, keep = _abi.make_candidates_in(cand["lib_row"], cand["rank"], cand["scan_start"], cand["scan_stop"],
+                                                cand["scan_center"], cand["frame_start"], cand["frame_stop"],
+                                                cand["frame_center"])
+            h2d += sum(int(v.nbytes) for v in keep.values())
+            if self._host_bufs["scores"] is None or self._host_bufs["scores_n"] < n:
+                cap = int(n * 1.05) + 16
+                sc = dict(features=alloc((cap, _abi.NUM_FEATURES), np.float32), valid=alloc(cap, np.uint8))
+                for k in _abi.FRAG_F32:
+                    sc[k] = alloc((cap, self.top_k), np.float32)
+                for k in _abi.FRAG_U8:
+                    sc[k] = alloc((cap, self.top_k), np.uint8)
+                self._host_bufs["scores"], self._host_bufs["scores_n"] = sc, cap
+            sc = self._host_bufs["scores"]
+            so = _abi.ScoresOut()
+            for k, v in sc.items():
+                setattr(so, k, _abi.ptr(v))
+            _lib.check(lib.adb_score_candidates(self.dev_raw.handle, dev_lib.handle, C.byref(self.score_struct),
+                                                C.byref(cin), C.byref(so)), "adb_score_candidates")
+            d2h += n * (_abi.NUM_FEATURES * 4 + 1 + self.top_k * (7 * 4 + 5))
+        finally:
+            dev_lib.close()
+        self.n_candidates = n
+        return dict(n_candidates=n, h2d_bytes=h2d, d2h_bytes=d2h, valid=int(sc["valid"][:n].sum()),
+                    checksum=float(np.nansum(sc["features"][:n, 2])))
+
+    def close(self):
+        self.dev_lib.close()
+        self.dev_raw.close()

@@ -111,6 +111,9 @@ def make_library(
     for i in range(n_isotopes):
         prec[f"i_{i}"] = np.full(P, iso[i], dtype=np.float32)
     precursor_df = pd.DataFrame(prec)
+    if not with_strings:  # schema-required object columns only (cheap constants)
+        for col in ("proteins", "genes"):
+            precursor_df[col] = pd.Series(np.full(P, "P0", dtype=object), dtype=object)
     if with_strings:
         aa = np.array(list("ACDEFGHIKLMNPQRSTVWY"))
         letters = aa[rng.integers(0, 20, size=(P, 9))]

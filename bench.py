@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — precursor candidates scored per second (BASELINE.json metric) on synthetic DIA data.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # B200 arm (default workload: config3)
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # CPU arm: the oracle port on the host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU, weak scaling
+
+One "step" = candidate selection + candidate scoring of the whole library batch against one raw file
+(SURVEY.md §8d).  `value` is measured with raw file and library resident in HBM (results stay in HBM);
+`e2e` is measured through the C-ABI calls the reference-facing operators make, with pinned HOST buffers
+(library batch H2D, candidate container D2H, candidate table H2D, score + fragment tables D2H every step;
+the raw file is uploaded once per file, as `dia_data.to_jitclass()` is built once per file in the reference).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "precursor candidates scored/sec"
+UNIT = "candidates/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def build_workload(name: str, rank: int, n_precursors: int | None):
+    from alphadia_b200.config import CandidateScoringConfig, CandidateSelectionConfig
+    from alphadia_b200.kernel import GaussianKernel
+    from alphadia_b200.library import assemble_library_arrays
+    from alphadia_b200.synthetic import CONFIGS_3D, make_config_3d
+
+    seed = CONFIGS_3D[name]["seed"] + rank
+    t0 = time.time()
+    raw, pdf, fdf, p = make_config_3d(name, seed=seed, n_precursors=n_precursors, with_strings=False)
+    lib = assemble_library_arrays(pdf, fdf, "rt_library", "mobility_library", "mz_library", "mz_library")
+    # ClassicExtractionHandler parameters (reference extraction_handler.py:349-409) at target tolerances
+    sel = CandidateSelectionConfig()
+    sel.update({
+        "peak_len_rt": 10.0, "sigma_scale_rt": 0.5, "peak_len_mobility": 0.01, "sigma_scale_mobility": 1.0,
+        "top_k_precursors": 3, "kernel_size": 30, "f_mobility": 1.0, "f_rt": 0.99, "center_fraction": 0.5,
+        "min_size_mobility": 8, "min_size_rt": 3, "max_size_mobility": 20, "max_size_rt": 15,
+        "group_channels": False, "use_weighted_score": True, "join_close_candidates": False,
+        "join_close_candidates_scan_threshold": 0.6, "join_close_candidates_cycle_threshold": 0.6,
+        "top_k_fragments": 12, "exclude_shared_ions": True, "rt_tolerance": float(p["rt_tolerance"]),
+        "mobility_tolerance": 0.1, "candidate_count": 3, "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0,
+    })
+    sc = CandidateScoringConfig()
+    sc.update({
+        "score_grouped": False, "top_k_isotopes": 3, "reference_channel": -1, "precursor_mz_tolerance": 5,
+        "fragment_mz_tolerance": 10, "exclude_shared_ions": True, "quant_window": 3, "quant_all": True,
+        "experimental_xic": True, "top_k_fragments": 12,
+    })
+    kernel = GaussianKernel(raw, fwhm_rt=5.0, sigma_scale_rt=0.5, fwhm_mobility=0.01, sigma_scale_mobility=1.0,
+                            kernel_width=30, kernel_height=min(30, raw.scan_max_index + 1)).get_dense_matrix(verbose=False)
+    log(f"[rank {rank}] workload {name}: {len(pdf)} precursors, {len(fdf)} fragments, {len(raw.rt_values)} spectra, "
+        f"{raw.n_peaks} peaks ({(raw.n_peaks * 8) / 1e9:.2f} GB) generated in {time.time() - t0:.1f}s")
+    return raw, pdf, fdf, lib, p, sel, sc, kernel
+
+
+def algorithmic_bytes(raw, lib, c_sel_mean, c_sc_mean, n_obs=1.0, F=12, I=3, N=3, h=1.0):
+    """SURVEY.md §8d formulas (bytes the algorithm must touch per precursor / per candidate)."""
+    L = raw.cycle_len
+    counts = (raw.peak_stop_idx_list - raw.peak_start_idx_list).astype(np.float64)
+    is_ms1 = (np.arange(len(counts)) % L) == 0
+    p_ms1 = float(counts[is_ms1].mean())
+    p_ms2 = float(counts[~is_ms1].mean())
+    probe2 = 4 * math.ceil(math.log2(max(p_ms2, 2)))
+    probe1 = 4 * math.ceil(math.log2(max(p_ms1, 2)))
+    n_iso = lib["isotopes"].shape[1]
+    b_prec = (c_sel_mean * n_obs * (16 + F * (probe2 + 8 * h)) + c_sel_mean * (16 + I * (probe1 + 8 * h))
+              + (18 * F + 40 + 4 * n_iso) + 33 * N)
+    b_cand = (c_sc_mean * n_obs * (16 + F * (probe2 + 8 * h)) + c_sc_mean * (16 + I * (probe1 + 8 * h))
+              + (18 * F + 40) + 72 + (184 + 38 * F + 8))
+    return dict(b_prec=b_prec, b_cand=b_cand, p_ms1=p_ms1, p_ms2=p_ms2)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def pinned_alloc_factory():
+    import torch
+
+    keep = []
+
+    def alloc(shape, dtype):
+        n = int(np.prod(shape))
+        t = torch.empty(max(n, 1) * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)
+        keep.append(t)
+        return t.numpy()[: n * np.dtype(dtype).itemsize].view(dtype).reshape(shape)
+
+    alloc.keep = keep
+    return alloc
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_pass(raw, lib, sel, sc, kernel, rows, threads):
+    """Oracle port (CPU) on library rows [rows]: selection + scoring; returns (#candidates, seconds)."""
+    import oracle
+    from alphadia_b200 import _abi
+
+    sub = dict(lib)
+    for k in ("precursor_idx", "frag_start_idx", "frag_stop_idx", "charge", "rt", "mobility", "mz", "isotopes"):
+        sub[k] = np.ascontiguousarray(lib[k][rows])
+    t0 = time.perf_counter()
+    cont = oracle.select_candidates(raw, sub, sel.to_struct(), kernel, n_threads=threads)
+    t_sel = time.perf_counter() - t0
+    m = np.flatnonzero(cont["score"] > 0)
+    cc = int(sel.candidate_count)
+    cin, keep = _abi.make_candidates_in(m // cc, cont["rank"][m], cont["scan_start"][m], cont["scan_stop"][m],
+                                        cont["scan_center"][m], cont["frame_start"][m], cont["frame_stop"][m],
+                                        cont["frame_center"][m])
+    t0 = time.perf_counter()
+    out = oracle.score_candidates(raw, sub, sc.to_struct(), cin, n_threads=threads)
+    t_sc = time.perf_counter() - t0
+    return len(m), t_sel, t_sc, int(out["valid"].sum())
+
+
+def cpu_baseline(raw, lib, sel, sc, kernel, target_seconds=15.0):
+    import oracle
+
+    oracle.build()
+    threads = os.cpu_count() or 1
+    P = len(lib["precursor_idx"])
+    rng = np.random.default_rng(99)
+    perm = np.sort(rng.permutation(P)[: min(P, 2000)])
+    n, t_sel, t_sc, _ = cpu_reference_pass(raw, lib, sel, sc, kernel, perm, threads)  # pilot (also warms the threads)
+    rate = len(perm) / max(t_sel + t_sc, 1e-6)
+    size = int(min(P, max(2000, rate * target_seconds)))
+    rows = np.sort(rng.permutation(P)[:size])
+    n, t_sel, t_sc, valid = cpu_reference_pass(raw, lib, sel, sc, kernel, rows, threads)
+    return dict(value=n / (t_sel + t_sc), unit=UNIT, cores=threads, kind="port",
+                sample=f"{size} of {P} precursors (random subset, same raw file), selection {t_sel:.2f}s + scoring {t_sc:.2f}s, "
+                       f"{n} candidates, {valid} valid; oracle/adb_oracle.c with OpenMP",
+                precursors_per_s=size / t_sel, scoring_candidates_per_s=n / t_sc)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    raw, pdf, fdf, lib, p, sel, sc, kernel = build_workload(args.workload, 0, args.precursors)
+    import oracle
+
+    oracle.build()
+    threads = os.cpu_count() or 1
+    P = len(lib["precursor_idx"])
+    rng = np.random.default_rng(99)
+    pilot = np.sort(rng.permutation(P)[: min(P, 2000)])
+    n, t_sel, t_sc, _ = cpu_reference_pass(raw, lib, sel, sc, kernel, pilot, threads)
+    rate = len(pilot) / max(t_sel + t_sc, 1e-6)
+    budget = 120.0 / max(args.steps + args.warmup, 1)
+    size = int(min(P, max(2000, rate * min(budget, 20.0))))
+    times, cands = [], []
+    for s in range(args.warmup + args.steps):
+        rows = np.sort(rng.permutation(P)[:size])
+        n, t_sel, t_sc, valid = cpu_reference_pass(raw, lib, sel, sc, kernel, rows, threads)
+        if s >= args.warmup:
+            times.append(t_sel + t_sc); cands.append(n)
+    value = sum(cands) / sum(times)
+    sample = f"{size} of {P} precursors per step (random subset), all {threads} host threads (OpenMP), oracle port of the numba path"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": workload_description(args.workload, P), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_description(name, P):
+    from alphadia_b200.synthetic import CONFIGS_3D
+
+    c = CONFIGS_3D[name]
+    return (f"{name}: {P} precursors x 12 fragments, 3 candidates/precursor, synthetic Thermo-shape 3-D run "
+            f"{c['n_cycles']} cycles x (1 MS1 + {c['n_windows']} MS2), rt_tolerance {c['rt_tolerance']}s, ms1/ms2 5/10 ppm")
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("ADB_BENCH_WORKLOAD", "config3"))
+    ap.add_argument("--precursors", type=int, default=None, help="override the library size (debugging)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from alphadia_b200 import _lib
+    from alphadia_b200.engine import HotPath
+    from alphadia_b200.sharding import allgather_score_table, device_words_from_resident
+
+    _lib.require_device()  # no CPU fallback
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    raw, pdf, fdf, lib, p, sel, sc, kernel = build_workload(args.workload, rank, args.precursors)
+    t0 = time.time()
+    hp = HotPath(raw, lib, sel, sc, kernel, device=local_rank)
+    log(f"[rank {rank}] raw file + library resident in HBM ({hp.dev_raw.device_bytes / 1e9:.2f} GB raw) in {time.time() - t0:.1f}s")
+    lib_pidx_dev = torch.from_numpy(lib["precursor_idx"].astype(np.int64)).cuda(local_rank) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        r = hp.resident_step()
+        if world > 1:  # the single collective of the path: all-gather of the score table
+            words = device_words_from_resident(hp, lib_pidx_dev)
+            allgather_score_table(words)
+        return r
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    launches0 = hp.dev_raw.kernel_launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    stats = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        stats.append(one_step())
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ev1.record(); torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = hp.dev_raw.kernel_launches - launches0
+    # device time of the step = CUDA-event time on the engine's stream (selection + compaction + scoring)
+    dev_ms = sum(s["select_ms"] + s["score_ms"] for s in stats)
+    n_cand = stats[-1]["n_candidates"]
+    # the calls block; wall time additionally contains the host-side launch/sync gaps (and the all-gather)
+    t_rank = torch.tensor([t_wall, dev_ms / 1000.0, float(n_cand)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t_rank.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t_rank.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t_wall_max, dev_s_max, n_cand_total = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    else:
+        t_wall_max, dev_s_max, n_cand_total = t_wall, dev_ms / 1000.0, float(n_cand)
+    value = n_cand_total * args.steps / t_wall_max
+
+    # ---- e2e through the C ABI with pinned host buffers ------------------------------------------
+    alloc = pinned_alloc_factory()
+    hp.host_step(alloc)  # warm-up: allocates the pinned buffers
+    barrier()
+    t0 = time.perf_counter()
+    e2e_stats = [hp.host_step(alloc) for _ in range(args.e2e_steps)]
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    t_e = torch.tensor([t_e2e, float(e2e_stats[-1]["n_candidates"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tm = t_e.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t_e.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        t_e2e_max, n_e2e_total = float(tm[0]), float(ts[1])
+    else:
+        t_e2e_max, n_e2e_total = t_e2e, float(e2e_stats[-1]["n_candidates"])
+    e2e_value = n_e2e_total * args.e2e_steps / t_e2e_max
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel ------------------------------------------------------
+        L = raw.cycle_len
+        cont = _lib.fetch_candidates(hp.dev_raw, int(hp.n_precursors * sel.candidate_count))
+        m = cont["score"] > 0
+        c_sc = (cont["frame_stop"][m].astype(np.int64) // L - cont["frame_start"][m].astype(np.int64) // L)
+        c_sc_mean = float(c_sc.mean()) if m.any() else 0.0
+        cyc_rt = raw.rt_values[::L]
+        cyc_s = float(np.mean(np.diff(cyc_rt))) if len(cyc_rt) > 1 else 1.0
+        c_sel = 16 * math.ceil(max(2 * p["rt_tolerance"] / cyc_s, 30) / 16)
+        c_sel = min(c_sel, raw.precursor_cycle_max_index)
+        ab = algorithmic_bytes(raw, lib, c_sel, c_sc_mean)
+        sel_k = float(np.mean([s["select_kernel_ms"] for s in stats]))
+        sc_k = float(np.mean([s["score_kernel_ms"] for s in stats]))
+        peak, peak_src = measured_peaks()
+        if sel_k >= sc_k:
+            dom, dur, bytes_launch, unit_desc = "adb_select_kernel", sel_k, ab["b_prec"] * hp.n_precursors, f"{ab['b_prec']:.0f} B/precursor x {hp.n_precursors} precursors (C_sel={c_sel})"
+        else:
+            dom, dur, bytes_launch, unit_desc = "adb_score_kernel", sc_k, ab["b_cand"] * n_cand, f"{ab['b_cand']:.0f} B/candidate x {n_cand} candidates (C_sc={c_sc_mean:.1f})"
+        achieved = bytes_launch / (dur * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(dom)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "kernel": dom, "kernel_ms": dur, "algorithmic_bytes": unit_desc, "peak_source": peak_src,
+                    "other_kernel": {"adb_select_kernel_ms": sel_k, "adb_score_kernel_ms": sc_k,
+                                     "select_frac": ab["b_prec"] * hp.n_precursors / (sel_k * 1e-3) / 1e9 / peak,
+                                     "score_frac": ab["b_cand"] * n_cand / (sc_k * 1e-3) / 1e9 / peak}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            t0 = time.time()
+            cpu = cpu_baseline(raw, lib, sel, sc, kernel)
+            log(f"cpu baseline done in {time.time() - t0:.1f}s: {cpu['value']:.0f} candidates/s on {cpu['cores']} threads")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * t_wall_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": workload_description(args.workload, hp.n_precursors) + (f", one file per GPU x {world}" if world > 1 else ""),
+                       "candidates_per_step": n_cand_total, "l2": "inputs (raw file + library) exceed the 126 MB L2; no explicit flush",
+                       "device_ms_per_step": 1000.0 * dev_s_max / args.steps,
+                       "stage_ms": {"selection": float(np.mean([s["select_ms"] for s in stats])),
+                                    "scoring": float(np.mean([s["score_ms"] for s in stats]))},
+                       "precursors_per_s_selection": hp.n_precursors / (np.mean([s["select_ms"] for s in stats]) * 1e-3),
+                       "candidates_per_s_scoring": n_cand / (np.mean([s["score_ms"] for s in stats]) * 1e-3)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_stats[-1]["h2d_bytes"],
+                    "d2h_bytes_per_step": e2e_stats[-1]["d2h_bytes"], "steps": args.e2e_steps,
+                    "path": "adb_library_create + adb_select_candidates + adb_score_candidates with pinned host buffers"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    hp.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

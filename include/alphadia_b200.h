@@ -220,6 +220,8 @@ int adb_resident_score_table(adb_rawfile_t* raw, void** features, void** valid, 
 /* timing of the last call on this handle, CUDA events on the handle's stream (ms) + kernel launches so far */
 int adb_last_timing(const adb_rawfile_t* raw, float* h2d_ms, float* kernel_ms, float* d2h_ms);
 int64_t adb_kernel_launches(const adb_rawfile_t* raw);
+/* duration (ms, CUDA events on the handle's stream) of the selection / scoring kernel of the last call */
+float adb_last_main_kernel_ms(const adb_rawfile_t* raw);
 /* CUDA stream the handle launches on (cudaStream_t as void*) */
 void* adb_rawfile_stream(const adb_rawfile_t* raw);
 

@@ -249,9 +249,12 @@ static void conv_circular(const float* x, int n0, int n1, const float* k, int k0
       double acc = 0.0;
       for (int a = 0; a < k0; a++) {
         int ii = ((i + s0 - a) % n0 + n0) % n0;
+        const float* xr = x + (size_t)ii * n1;
+        const float* kr = k + (size_t)a * k1;
+        int jj = (j + s1) % n1; /* (j + s1 - b) mod n1 for b = 0, then step down with wrap */
         for (int b = 0; b < k1; b++) {
-          int jj = ((j + s1 - b) % n1 + n1) % n1;
-          acc = fma((double)k[a * k1 + b], (double)x[ii * n1 + jj], acc);
+          acc = fma((double)kr[b], (double)xr[jj], acc);
+          jj = (jj == 0) ? n1 - 1 : jj - 1;
         }
       }
       out[i * n1 + j] = (float)acc;
