@@ -1,0 +1,179 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/alphadia_b200.h declares; the
+product fails loudly without a GPU; host-side mirrors (configs, schemas, kernel, sharding) behave like the
+reference.  No device compute."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from alphadia_b200 import build
+
+    build.build()
+    from alphadia_b200 import _lib
+
+    return _lib
+
+
+def test_header_symbols_exported(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "alphadia_b200.h")).read()
+    declared = set(re.findall(r"\b(adb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 19
+    lib = built_lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(built_lib.EXPORTED_SYMBOLS)
+    assert lib.adb_version().decode().startswith("alphadia_b200")
+
+
+def test_struct_sizes_match_header(built_lib):
+    """ctypes mirrors must have the C layout (sizes computed by hand from the header's field lists)."""
+    from alphadia_b200 import _abi
+
+    assert C.sizeof(_abi.RawFile3DDesc) == 15 * 8
+    assert C.sizeof(_abi.LibraryDesc) == 8 + 8 * 8 + 8 + 8 + 9 * 8
+    assert C.sizeof(_abi.CandidatesOut) == 10 * 8
+    assert C.sizeof(_abi.CandidatesIn) == 9 * 8
+    assert C.sizeof(_abi.ScoresOut) == 14 * 8
+    assert C.sizeof(_abi.ScoringConfig) == 9 * 4 + 4 + 4 * 8
+    assert C.sizeof(_abi.SelectionConfig) == 22 * 8  # the two adjacent int32 flags share one 8-byte slot
+
+
+def test_no_cpu_fallback(built_lib):
+    if built_lib.load().adb_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    from alphadia_b200 import CandidateSelection, FragmentCompetition
+    from tests import helpers as H
+
+    raw, pdf, fdf, lib, p = H.workload("config1")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        built_lib.DeviceRawFile(raw)
+    sel = CandidateSelection(raw, pdf.copy(), fdf.copy(), H.selection_config(30.0), rt_column="rt_library",
+                             mobility_column="mobility_library", precursor_mz_column="mz_library",
+                             fragment_mz_column="mz_library")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sel()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        built_lib.fragment_competition([0], [1], np.zeros(1, np.float32), [0], [1], np.ones(1, np.float32), 3.0, 15.0)
+    assert FragmentCompetition is not None
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "alphadia_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "adb_oracle" not in src, f
+                assert "/root/reference" not in src, f
+
+
+# ---- config semantics (jit_config.py:84-138) ------------------------------------------------------
+def test_config_update_semantics():
+    from alphadia_b200.config import CandidateScoringConfig, CandidateSelectionConfig
+
+    c = CandidateScoringConfig()
+    c.update({"precursor_mz_tolerance": 4.7, "quant_all": True})
+    assert c.precursor_mz_tolerance == 4 and isinstance(c.precursor_mz_tolerance, int)  # int default truncates
+    with pytest.raises(ValueError):
+        c.update({"does_not_exist": 1})
+    s = CandidateSelectionConfig()
+    s.update({"rt_tolerance": 30, "candidate_count": 3.0})
+    assert isinstance(s.rt_tolerance, float) and s.candidate_count == 3
+    with pytest.raises(ValueError):
+        s.update({"feature_std": np.ones(2)})
+    st = s.to_struct()
+    assert st.rt_tolerance == 30.0 and st.candidate_count == 3 and st.kernel_size == 30
+    sc = c.to_struct()
+    assert sc.top_k_fragments == 12 and sc.quant_all == 1 and abs(sc.quad_sigma[0] - 0.2) < 1e-12
+    c.update({"top_k_fragments": 9999})
+    with pytest.raises(NotImplementedError):
+        c.to_struct()
+
+
+def test_schema_validation_casts_and_raises():
+    from alphadia_b200.validation import candidates_schema, fragments_flat_schema
+
+    df = pd.DataFrame({"mz_library": [500.0], "intensity": [1.0], "cardinality": [1], "type": [98], "loss_type": [0],
+                       "charge": [1], "number": [3], "position": [2]})
+    fragments_flat_schema.validate(df)
+    assert df["mz_library"].dtype == np.float32 and df["type"].dtype == np.uint8
+    with pytest.raises(ValueError, match="rank"):
+        candidates_schema.validate(pd.DataFrame({"elution_group_idx": [0], "precursor_idx": [0]}))
+
+
+@pytest.mark.parametrize("kernel_size,fwhm_rt,sigma_scale_rt", [(30, 5.0, 0.5), (30, 10.0, 1.0), (20, 2.0, 0.5), (31, 5.0, 0.1)])
+def test_gaussian_kernel_properties(kernel_size, fwhm_rt, sigma_scale_rt):
+    """tests/unit_tests/search/selection/test_kernel.py:35-67: even dims, finite, float32."""
+    from alphadia_b200.kernel import GaussianKernel
+    from tests import helpers as H
+
+    raw = H.workload("config1")[0]
+    k = GaussianKernel(raw, fwhm_rt=fwhm_rt, sigma_scale_rt=sigma_scale_rt, kernel_width=kernel_size,
+                       kernel_height=min(kernel_size, raw.scan_max_index + 1)).get_dense_matrix(verbose=False)
+    assert k.dtype == np.float32 and k.shape[0] % 2 == 0 and k.shape[1] % 2 == 0
+    assert np.all(np.isfinite(k)) and k.shape[0] == 2
+    assert np.argmax(k[1]) == k.shape[1] // 2
+
+
+# ---- sharding --------------------------------------------------------------------------------------
+def test_shard_library_partitions_exactly():
+    from alphadia_b200.sharding import shard_bounds, shard_library
+    from tests import helpers as H
+
+    raw, pdf, fdf, lib, p = H.workload("config1")
+    assert list(shard_bounds(10, 3)) == [0, 4, 7, 10]
+    assert list(shard_bounds(2, 4)) == [0, 1, 2, 2, 2]
+    seen = []
+    for r in range(3):
+        sp, sf = shard_library(pdf, fdf, r, 3)
+        seen.append(sp["precursor_idx"].values)
+        s0, s1 = sp["flat_frag_start_idx"].values, sp["flat_frag_stop_idx"].values
+        assert s0[0] == 0 and s1[-1] == len(sf)
+        # fragments of every precursor are unchanged
+        i = len(sp) // 2
+        orig = pdf[pdf["precursor_idx"] == sp["precursor_idx"].values[i]].iloc[0]
+        a = fdf["mz_library"].values[int(orig["flat_frag_start_idx"]): int(orig["flat_frag_stop_idx"])]
+        assert np.array_equal(a, sf["mz_library"].values[s0[i]: s1[i]])
+    assert np.array_equal(np.concatenate(seen), np.sort(pdf["precursor_idx"].values))
+
+
+def test_pack_unpack_score_table():
+    from alphadia_b200.sharding import pack_score_table, unpack_score_table
+
+    rng = np.random.default_rng(0)
+    f = rng.normal(size=(17, 46)).astype(np.float32)
+    f[3, 5] = np.nan
+    pidx = rng.integers(0, 2**32 - 1, 17, dtype=np.uint64).astype(np.uint32)
+    rank = rng.integers(0, 5, 17).astype(np.uint8)
+    valid = rng.integers(0, 2, 17).astype(np.uint8)
+    u = unpack_score_table(pack_score_table(f, pidx, rank, valid))
+    assert np.array_equal(u["features"].view(np.uint32), f.view(np.uint32))
+    assert np.array_equal(u["precursor_idx"], pidx) and np.array_equal(u["rank"], rank) and np.array_equal(u["valid"], valid)
+
+
+def test_sharded_selection_equals_unsharded(oracle_lib):
+    """Any partition of the precursors gives the same candidates (disjoint output rows)."""
+    from alphadia_b200.library import assemble_library_arrays
+    from alphadia_b200.sharding import shard_library
+    from tests import helpers as H
+
+    raw, pdf, fdf, lib, p = H.workload("config1")
+    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    kernel = H.default_kernel(raw)
+    full = oracle_lib.select_candidates(raw, lib, cfg, kernel)
+    parts = []
+    for r in range(2):
+        sp, sf = shard_library(pdf, fdf, r, 2)
+        sl = assemble_library_arrays(sp, sf, "rt_library", "mobility_library", "mz_library", "mz_library")
+        parts.append(oracle_lib.select_candidates(raw, sl, cfg, kernel))
+    for c in full:
+        assert np.array_equal(full[c], np.concatenate([q[c] for q in parts])), c

@@ -1,0 +1,199 @@
+"""Known-answer vectors taken from the reference's OWN unit tests, replayed against the
+C oracle and the host-side restatements.  CPU only."""
+
+import ctypes as C
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from alphadia_b200 import _abi
+from alphadia_b200.fragcomp import FragmentCompetition, candidate_hash
+from alphadia_b200.scoring import calculate_score_groups, merge_missing_columns
+
+
+# ---- tests/unit_tests/fragcomp/test_fragcomp.py:12-35 --------------------------------------------
+@pytest.mark.parametrize("a,b,expected", [
+    (np.arange(100, 1100, 100), np.arange(100, 1100, 100), 10),
+    (np.arange(100, 1100, 100), np.array([100]), 1),
+    (np.array([]), np.array([]), 0),
+    (np.arange(100, 1100, 100), np.array([]), 0),
+    (np.array([]), np.array([100, 200, 300, 400, 500, 600, 700, 801, 901, 1001]), 0),
+    (np.arange(100, 1100, 100), np.arange(101, 1101, 100), 0),
+])
+def test_fragment_overlap(oracle_lib, a, b, expected):
+    L = oracle_lib.lib()
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    L.adbo_fragment_overlap_f64.restype = C.c_int
+    got = L.adbo_fragment_overlap_f64(a.ctypes.data_as(C.c_void_p), C.c_int(len(a)), b.ctypes.data_as(C.c_void_p),
+                                      C.c_int(len(b)), C.c_double(10.0))
+    assert got == expected
+
+
+# ---- test_fragcomp.py:38-58 ------------------------------------------------------------------------
+def test_compete_for_fragments(oracle_lib):
+    rt = np.array([10.0, 20.0, 20.0, 10.0, 10.0, 20])
+    frag_start = np.array([0, 10, 20, 30, 40, 50])
+    frag_stop = np.array([10, 20, 30, 40, 50, 60])
+    fragment_mz = np.tile(np.arange(100, 110), 6).astype(np.float64)
+    valid = oracle_lib.fragment_competition(np.array([0, 3]), np.array([3, 6]), rt, frag_start, frag_stop, fragment_mz, 3, 15)
+    assert np.all(valid == np.array([True, True, False, True, False, True]))
+
+
+# ---- test_fragcomp.py:61-100 (the pandas preparation; the kernel is replaced by the oracle) ---------
+def test_fragment_competition_dataframes(oracle_lib):
+    psm_df = pd.DataFrame({
+        "precursor_idx": np.arange(6), "rank": np.zeros(6, dtype=np.uint8),
+        "rt_observed": np.array([10.0, 20.0, 20.0, 10.0, 10.0, 20]), "proba": np.array([0.1, 0.2, 0.3, 0.4, 0.5, 0.6]),
+        "mz_observed": np.array([150.0, 150.0, 150.0, 250.0, 250.0, 250.0]),
+    })
+    frag_df = pd.DataFrame({
+        "precursor_idx": np.repeat(np.arange(6), 10), "rank": np.zeros(60, dtype=np.uint8),
+        "mz_observed": np.tile(np.arange(100, 110), 6).astype(np.float64),
+    })
+    cycle = np.zeros((1, 3, 1, 2))
+    cycle[0, :, 0, 0] = [-1, 100, 200]
+    cycle[0, :, 0, 1] = [-1, 200, 300]
+    fc = FragmentCompetition()
+    plan = fc.plan(psm_df, frag_df, cycle)
+    assert plan.psm_df["_candidate_idx"].dtype == np.uint64
+    valid = oracle_lib.fragment_competition(plan.window_start, plan.window_stop, plan.rt, plan.frag_start, plan.frag_stop,
+                                            plan.fragment_mz, 3, 15)
+    kept = plan.psm_df[valid]
+    assert list(kept["precursor_idx"]) == [0, 1, 3, 5]
+
+
+# ---- test_fragcomp.py:103-113 ----------------------------------------------------------------------
+def test_candidate_hash():
+    h = candidate_hash(np.array([1, 2, 1000000], dtype=np.uint32), np.array([0, 1, 2], dtype=np.uint8))
+    assert h.dtype == np.uint64
+    assert np.all(h == np.array([1, 4294967298, 8590934592], dtype=np.uint64))
+
+
+# ---- tests/unit_tests/search/selection/test_fft.py:71-87: delta (*) ones == box --------------------
+@pytest.mark.parametrize("shape", [(64, 64), (32, 48)])
+def test_convolution_delta_box(oracle_lib, shape):
+    L = oracle_lib.lib()
+    x = np.zeros(shape, np.float32)
+    x[shape[0] // 2, shape[1] // 2] = 1.0
+    k = np.ones((20, 20), np.float32)
+    out = np.zeros(shape, np.float32)
+    L.adbo_conv_circular(_abi.ptr(x), C.c_int(shape[0]), C.c_int(shape[1]), _abi.ptr(k), C.c_int(20), C.c_int(20), _abi.ptr(out))
+    expect = np.zeros(shape, np.float32)
+    expect[shape[0] // 2 - 10: shape[0] // 2 + 10, shape[1] // 2 - 10: shape[1] // 2 + 10] = 1.0
+    assert np.allclose(out, expect, atol=1e-6)
+
+
+def test_convolution_is_circular(oracle_lib):
+    L = oracle_lib.lib()
+    x = np.zeros((2, 40), np.float32)
+    x[:, 1] = 1.0  # next to the left edge: the kernel support wraps around
+    k = np.random.default_rng(0).uniform(0.1, 1, (2, 30)).astype(np.float32)
+    out = np.zeros_like(x)
+    L.adbo_conv_circular(_abi.ptr(x), C.c_int(2), C.c_int(40), _abi.ptr(k), C.c_int(2), C.c_int(30), _abi.ptr(out))
+    # FFT definition (alphadia/search/selection/fft.py:158-167) in float64
+    F = np.fft.irfft2(np.fft.rfft2(x.astype(np.float64)) * np.fft.rfft2(k.astype(np.float64), x.shape), x.shape)
+    ref = np.roll(F, (-1, -15), axis=(0, 1))
+    assert np.allclose(out, ref, rtol=1e-5, atol=1e-6)
+    assert out[0, 39] > 0  # wrapped
+
+
+# ---- tests/unit_tests/raw_data/test_raw_data.py:26-175 get_frame_indices ----------------------------
+@pytest.mark.parametrize("rt,opt,mn,expected", [
+    ((10.0, 20.0), 1, 1, (10, 20)),
+    ((10.0, 20.0), 4, 1, (10, 30)),
+    ((10.0, 20.0), 4, 8, (10, 50)),
+    ((90.0, 95.0), 4, 1, (75, 95)),
+    ((90.0, 95.0), 4, 8, (55, 95)),
+    ((90.0, 95.0), 4, 1000, (5, 95)),
+])
+def test_get_frame_indices(oracle_lib, rt, opt, mn, expected):
+    L = oracle_lib.lib()
+    cycle = np.zeros((1, 5, 1, 2))
+    cycle[0, :, 0, 0] = [100.0, 200.0, 300.0, 400.0, 500.0]
+    cycle[0, :, 0, 1] = [200.0, 300.0, 400.0, 500.0, 600.0]
+
+    class Raw:
+        pass
+
+    r = Raw()
+    r.cycle = cycle
+    r.rt_values = np.arange(0, 100, 1).astype(np.float32)
+    r.mobility_values = np.array([0.0, 0.0], np.float32)
+    r.zeroth_frame = 0
+    r.precursor_cycle_max_index = 19
+    r.peak_start_idx_list = np.arange(0, 1000, 10, dtype=np.int64)
+    r.peak_stop_idx_list = r.peak_start_idx_list + 1
+    r.mz_values = np.linspace(100, 1000, 1000).astype(np.float32)
+    r.intensity_values = np.ones(1000, np.float32)
+    r.scan_max_index = 0
+    r.frame_max_index = 99
+    desc, keep = _abi.make_rawfile3d_desc(r)
+    out = np.zeros(2, np.int64)
+    center, tol = (rt[0] + rt[1]) / 2, (rt[1] - rt[0]) / 2
+    L.adbo_frame_indices(C.byref(desc), C.c_float(center), C.c_double(tol), C.c_int64(opt), C.c_int64(mn), _abi.ptr(out))
+    assert tuple(out) == expected
+
+
+# ---- tests/unit_tests/search/scoring/test_features.py:7-79 center_envelope_1d ------------------------
+@pytest.mark.parametrize("x,expected", [
+    ([1, 1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1, 1]),
+    ([100, 10, 1, 1, 1, 10, 100], [1, 1, 1, 1, 1, 1, 1]),
+    ([100, 0, 0, 1, 0, 0, 100], [0, 0, 0, 1, 0, 0, 0]),
+    ([1, 1, 1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1, 1, 1]),
+    ([100, 10, 1, 1, 1, 1, 10, 100], [1, 1, 1, 1, 1, 1, 1, 1]),
+    ([100, 0, 0, 1, 1, 0, 0, 100], [0, 0, 0, 1, 1, 0, 0, 0]),
+])
+def test_center_envelope(oracle_lib, x, expected):
+    L = oracle_lib.lib()
+    a = np.array([x], dtype=np.float32)
+    L.adbo_center_envelope(_abi.ptr(a), C.c_int(1), C.c_int(a.shape[1]))
+    np.testing.assert_array_almost_equal(a[0], np.array(expected, np.float32))
+
+
+# ---- tests/unit_tests/search/selection/test_search_utils.py:9-33 _symetric_limits_1d invariants ------
+def test_symetric_limits_invariants(oracle_lib):
+    L = oracle_lib.lib()
+    rng = np.random.default_rng(0)
+    for _ in range(1000):
+        n = int(rng.integers(1, 60))
+        a = rng.uniform(0, 10, n)
+        center = int(rng.integers(0, n))
+        f = float(rng.uniform(0.5, 1.0))
+        cf = float(rng.uniform(0.01, 0.9))
+        mn = int(rng.integers(0, 5))
+        mx = int(rng.integers(mn, 20))
+        out = np.zeros(2, np.int32)
+        L.adbo_symetric_limits_1d(_abi.ptr(a), C.c_int(n), C.c_int(center), C.c_double(f), C.c_double(cf), C.c_int(mn),
+                                  C.c_int(mx), out.ctypes.data_as(C.c_void_p))
+        assert 0 <= out[0] <= center < out[1] <= n
+        assert out[1] - out[0] <= 2 * max(mx, mn) + 1
+
+
+# ---- tests/unit_tests/search/scoring/test_scoring_utils.py:64-120 calculate_score_groups -------------
+def test_score_groups():
+    base = dict(precursor_idx=np.arange(10), elution_group_idx=np.array([0, 0, 0, 0, 0, 1, 1, 1, 1, 1]),
+                channel=np.array([0, 1, 2, 3, 0, 0, 1, 2, 3, 0]), decoy=np.array([0, 0, 0, 0, 1, 0, 0, 0, 0, 1]))
+    assert np.allclose(calculate_score_groups(pd.DataFrame(base))["score_group_idx"].values, np.arange(10))
+    got = calculate_score_groups(pd.DataFrame(base), group_channels=True)["score_group_idx"].values
+    assert np.allclose(got, np.array([0, 0, 0, 0, 1, 2, 2, 2, 2, 3]))
+    df = pd.DataFrame({**base, "rank": np.array([0, 1, 2, 3, 4, 0, 1, 2, 3, 4])})
+    assert np.allclose(calculate_score_groups(df, group_channels=True)["score_group_idx"].values, np.arange(10))
+    df = pd.DataFrame(dict(precursor_idx=np.arange(10), elution_group_idx=np.array([0, 0, 0, 0, 1, 1, 1, 1, 0, 0]),
+                           channel=np.array([0, 0, 1, 1, 0, 0, 1, 1, 0, 0]), decoy=np.array([0, 0, 0, 0, 0, 0, 0, 0, 1, 1]),
+                           rank=np.array([0, 1, 0, 1, 0, 1, 0, 1, 0, 1])))
+    got = calculate_score_groups(df, group_channels=True)["score_group_idx"].values
+    assert np.allclose(got, np.array([0, 0, 1, 1, 2, 3, 4, 4, 5, 5]))
+
+
+def test_merge_missing_columns():
+    left = pd.DataFrame([{"idx": 1, "col_1": 0, "col_2": 0}])
+    right = pd.DataFrame([{"idx": 1, "col_3": 0, "col_4": 0}])
+    df = merge_missing_columns(left, right, ["col_3"], on="idx")
+    assert list(df.columns) == ["idx", "col_1", "col_2", "col_3"]
+    with pytest.raises(ValueError):
+        merge_missing_columns(left, right, ["col_5"], on="idx")
+    with pytest.raises(ValueError):
+        merge_missing_columns(left, right, ["col_3"], on=None)
+    assert merge_missing_columns(left, right, ["col_1"], on="idx") is left
