@@ -194,6 +194,33 @@ size_t scores_bytes(int64_t n, int k) {
   return 4 * N * ADB_NUM_FEATURES + 7 * 4 * N * K + 5 * N * K + N + 15 * 256;
 }
 
+// m/z range of the file: spectra are sorted, so first/last peaks bound it
+__global__ void mz_range_kernel(DevRaw raw, float* out /* [2] = {min, max}, pre-set to {+inf, -inf} */) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= raw.n_spectra) return;
+  int64_t s = raw.peak_start[i], e = raw.peak_stop[i];
+  if (e <= s) return;
+  float lo = raw.mz[s], hi = raw.mz[e - 1];
+  // positive floats order like their bit patterns
+  atomicMin((unsigned int*)out, __float_as_uint(fmaxf(lo, 0.f)));
+  atomicMax((unsigned int*)(out + 1), __float_as_uint(fmaxf(hi, 0.f)));
+}
+
+__global__ void bucket_index_kernel(DevRaw raw, int32_t* table) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= raw.n_spectra * ADB_N_BUCKETS) return;
+  int64_t scan = t / ADB_N_BUCKETS;
+  int b = (int)(t % ADB_N_BUCKETS);
+  int64_t s = raw.peak_start[scan], e = raw.peak_stop[scan];
+  float edge = adb_bucket_edge(raw, b);
+  int64_t lo = s, hi = e;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (raw.mz[mid] < edge) lo = mid + 1; else hi = mid;
+  }
+  table[t] = (int32_t)(lo - s);
+}
+
 __global__ void order_key_kernel(DevRaw raw, DevLib lib, uint64_t* keys, int32_t* vals) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= lib.n_precursors) return;
@@ -205,6 +232,19 @@ __global__ void order_key_kernel(DevRaw raw, DevLib lib, uint64_t* keys, int32_t
   uint32_t rb = __float_as_uint(rt);
   rb = (rb & 0x80000000u) ? ~rb : (rb | 0x80000000u);  // order-preserving float -> uint
   keys[i] = ((uint64_t)win << 32) | rb;
+  vals[i] = (int32_t)i;
+}
+
+__global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn cand, uint64_t* keys, int32_t* vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cand.n) return;
+  float mz = lib.mz[cand.lib_row[i]];
+  uint32_t win = 0xFFFFu;
+  for (int64_t j = 0; j < raw.cycle_len; j++)
+    if ((double)mz <= raw.cycle[2 * j + 1] && (double)mz >= raw.cycle[2 * j]) { win = (uint32_t)j; break; }
+  int64_t fs = cand.frame_start[i];
+  uint32_t f = fs < 0 ? 0u : (fs > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)fs);
+  keys[i] = ((uint64_t)win << 32) | f;
   vals[i] = (int32_t)i;
 }
 
@@ -237,12 +277,9 @@ int run_selection(adb_rawfile* raw, adb_library* lib, const adb_selection_config
   const int64_t rows = P * cfg->candidate_count;
 
   CUDA_TRY(cudaEventRecord(raw->ev[0], st));
-  // kernel -> doubles on the device
+  // kernel as doubles; it travels in the kernel parameters (constant bank)
   std::vector<double> kd((size_t)kh * kw);
   for (size_t t = 0; t < kd.size(); t++) kd[t] = (double)kernel[t];
-  if (raw->kern.reserve(sizeof(double) * kd.size())) return 1;
-  CUDA_TRY(cudaMemcpyAsync(raw->kern.ptr, kd.data(), sizeof(double) * kd.size(), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaStreamSynchronize(st));  // kd goes out of scope below only after this point
   if (raw->cont.reserve(container_bytes(rows))) return 1;
   raw->d_cont = carve_container(raw->cont.ptr, rows);
   raw->cont_rows = rows;
@@ -279,20 +316,21 @@ int run_selection(adb_rawfile* raw, adb_library* lib, const adb_selection_config
   const size_t smem_limit = 200 * 1024;
   float* d_ws = nullptr;
   int64_t ws_floats = 0;
-  if (adb_select_smem_bytes(c_cap, max_layers) > smem_limit) {
-    // shrink the shared-memory layout; windows that do not fit use the HBM workspace
-    c_cap = (int)((smem_limit - sizeof(double) * 2 * ADB_MAX_KERNEL_W) / (sizeof(float) * max_layers + 2 * sizeof(double)));
-    c_cap = std::max(16, (c_cap / 16) * 16);
-    ws_floats = (int64_t)max_layers * c_upper + 6 * c_upper + 16;
+  if (adb_select_smem_bytes(c_cap, max_layers, kw) > smem_limit) {
+    // shrink the shared-memory layout; windows that do not fit use the per-slot HBM workspace
+    size_t per_slot = smem_limit / (size_t)adb_select_slots();
+    long long cc = ((long long)per_slot - 4LL * max_layers * (kw - 1) - 32) / (8 + 4LL * max_layers);
+    c_cap = (int)std::max<long long>(32, (cc / 16) * 16);
+    ws_floats = (int64_t)max_layers * (c_upper + kw) + 2 * c_upper + 16;
     ws_floats = (ws_floats + 3) & ~(int64_t)3;
   }
-  int grid = adb_select_resident_ctas(raw->device, c_cap, max_layers);
+  int grid = adb_select_resident_ctas(raw->device, c_cap, max_layers, kw);
   if (ws_floats > 0) {
-    if (raw->sel_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)grid)) return 1;
+    if (raw->sel_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)grid * (size_t)adb_select_slots())) return 1;
     d_ws = raw->sel_ws.as<float>();
   }
   CUDA_TRY(cudaEventRecord(raw->ev[4], st));
-  adb_launch_select_ex(raw->dev, lib->dev, *cfg, raw->kern.as<double>(), kh, kw, raw->d_cont, 0, P, d_order, raw->d_status,
+  adb_launch_select_ex(raw->dev, lib->dev, *cfg, kd.data(), kh, kw, raw->d_cont, 0, P, d_order, raw->d_status,
                        c_cap, max_layers, d_ws, ws_floats, grid, st, &raw->launches);
   CUDA_TRY(cudaEventRecord(raw->ev[5], st));
   CUDA_TRY(cudaGetLastError());
@@ -336,14 +374,33 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   raw->scores_k = K;
   // OutputPsmDF.__init__ zero-fills (scoring/output.py:42-70)
   CUDA_TRY(cudaMemsetAsync(raw->scores.ptr, 0, scores_bytes(std::max<int64_t>(n, 1), K), st));
-  int warps = adb_score_resident_warps(raw->device);
+  int tiles = adb_score_resident_tiles(raw->device, K);
   // HBM fallback scratch for candidates whose cube exceeds the shared-memory budget
   int64_t c_max = std::max<int64_t>(c_max_hint, 32);
   int64_t ws_floats = (adb_score_workspace_floats(K, c_max) + 3) & ~(int64_t)3;
-  if (raw->score_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)warps)) return 1;
+  if (raw->score_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)tiles)) return 1;
+  // processing order: (quad window of the precursor, frame_start) so that co-resident tiles read the same
+  // spectra; results do not depend on it (disjoint output rows)
+  int32_t* d_order = nullptr;
+  if (n > 1 && n < 2000000000LL) {
+    if (raw->order_keys.reserve(sizeof(uint64_t) * 2 * (size_t)n)) return 1;
+    if (raw->order_vals.reserve(sizeof(int32_t) * 2 * (size_t)n)) return 1;
+    uint64_t* k_in = raw->order_keys.as<uint64_t>();
+    uint64_t* k_out = k_in + n;
+    int32_t* v_in = raw->order_vals.as<int32_t>();
+    int32_t* v_out = v_in + n;
+    score_order_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->dev, lib->dev, raw->d_cand, k_in, v_in);
+    raw->launches++;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 48, st);
+    if (raw->order_tmp.reserve(tmp)) return 1;
+    cub::DeviceRadixSort::SortPairs(raw->order_tmp.ptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 48, st);
+    raw->launches += 4;
+    d_order = v_out;
+  }
   CUDA_TRY(cudaEventRecord(raw->ev[4], st));
-  adb_launch_score(raw->dev, lib->dev, *cfg, raw->d_cand, raw->d_scores, raw->score_ws.as<float>(), ws_floats, warps,
-                   raw->d_status, st, &raw->launches);
+  adb_launch_score(raw->dev, lib->dev, *cfg, raw->d_cand, raw->d_scores, raw->score_ws.as<float>(), ws_floats, tiles,
+                   d_order, raw->d_status, st, &raw->launches);
   CUDA_TRY(cudaEventRecord(raw->ev[5], st));
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -405,6 +462,39 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
       v.ms1_pos[v.n_ms1_pos++] = (int32_t)j;
     }
   r->rt_host.assign(d->rt_values, d->rt_values + d->n_spectra);
+  for (int64_t i = 0; i < d->n_spectra; i++)
+    if (d->peak_stop_idx[i] - d->peak_start_idx[i] > 2000000000LL || d->peak_stop_idx[i] < d->peak_start_idx[i] ||
+        d->peak_stop_idx[i] > d->n_peaks || d->peak_start_idx[i] < 0) {
+      adb_rawfile_destroy(r);
+      return fail("spectrum " + std::to_string(i) + " has an invalid peak index range");
+    }
+  {  // derived bucket index, built on the device
+    float init[2];
+    unsigned int inf_bits = 0x7f800000u, zero_bits = 0u;
+    memcpy(&init[0], &inf_bits, 4);
+    memcpy(&init[1], &zero_bits, 4);
+    float* d_rng = nullptr;
+    int32_t* d_tab = nullptr;
+    if (upload(init, 2, &d_rng, r->allocs, r->bytes, r->stream)) { adb_rawfile_destroy(r); return 1; }
+    size_t tab_n = (size_t)d->n_spectra * ADB_N_BUCKETS;
+    void* tp = nullptr;
+    if (cudaMalloc(&tp, tab_n * sizeof(int32_t)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc bucket index failed"); }
+    r->allocs.push_back(tp);
+    r->bytes += (int64_t)(tab_n * sizeof(int32_t));
+    d_tab = (int32_t*)tp;
+    mz_range_kernel<<<(unsigned)((d->n_spectra + 255) / 256), 256, 0, r->stream>>>(v, d_rng);
+    float rng[2] = {0.f, 0.f};
+    cudaMemcpyAsync(rng, d_rng, sizeof(rng), cudaMemcpyDeviceToHost, r->stream);
+    if (cudaStreamSynchronize(r->stream) != cudaSuccess) { adb_rawfile_destroy(r); return fail("m/z range kernel failed"); }
+    if (!(rng[1] > rng[0])) { rng[0] = 0.f; rng[1] = 1.f; }
+    v.bucket_lo = rng[0];
+    v.bucket_width = (rng[1] - rng[0]) / (float)ADB_N_BUCKETS * 1.0001f;
+    if (!(v.bucket_width > 0.f)) v.bucket_width = 1.f;
+    v.bucket_inv_width = 1.0f / v.bucket_width;
+    v.bucket_idx = d_tab;
+    bucket_index_kernel<<<(unsigned)((tab_n + 255) / 256), 256, 0, r->stream>>>(v, d_tab);
+    r->launches += 2;
+  }
   void* st = nullptr;
   if (cudaMalloc(&st, sizeof(uint32_t)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc status failed"); }
   r->d_status = (uint32_t*)st;

@@ -10,6 +10,7 @@
 #define ADB_MAX_MS1_POS 8        // MS1 spectra per DIA cycle
 #define ADB_MAX_KERNEL_W 64
 #define ADB_ISOTOPE_DIFF 1.0033548350700006
+#define ADB_N_BUCKETS 64         // m/z buckets per spectrum in the derived search index
 
 // status bits reported by kernels through a device word (-> adb_last_error on the host)
 #define ADB_STATUS_TOO_MANY_OBS 1u
@@ -37,6 +38,10 @@ struct DevRaw {
   int64_t frame_max_index;
   int32_t n_ms1_pos;                // cycle positions whose window overlaps [-1,-1]
   int32_t ms1_pos[ADB_MAX_MS1_POS];
+  // derived m/z bucket index (built once per file on the device, sized to stay L2-resident):
+  // bucket_idx[scan][b] = first peak (relative to peak_start[scan]) with mz >= bucket_lo + b * bucket_width
+  const int32_t* bucket_idx;        // [n_spectra][ADB_N_BUCKETS]
+  float bucket_lo, bucket_width, bucket_inv_width;
 };
 
 struct DevLib {
@@ -105,17 +110,18 @@ struct DevScoresOut {
 };
 
 // ---- launchers (implemented in the .cu files) --------------------------------------------
-void adb_launch_select_ex(const DevRaw& raw, const DevLib& lib, const adb_selection_config& cfg, const double* d_kernel,
+void adb_launch_select_ex(const DevRaw& raw, const DevLib& lib, const adb_selection_config& cfg, const double* h_kernel,
                           int kh, int kw, DevCandidatesOut out, int64_t row_begin, int64_t row_end, const int32_t* d_order,
-                          uint32_t* d_status, int c_cap, int max_layers, float* d_workspace, int64_t ws_floats_per_cta,
+                          uint32_t* d_status, int c_cap, int max_layers, float* d_workspace, int64_t ws_floats_per_slot,
                           int grid, cudaStream_t stream, int* n_launches);
-size_t adb_select_smem_bytes(int c_cap, int max_layers);
-int adb_select_resident_ctas(int device, int c_cap, int max_layers);
+size_t adb_select_smem_bytes(int c_cap, int max_layers, int kw);
+int adb_select_resident_ctas(int device, int c_cap, int max_layers, int kw);
+int adb_select_slots(void);
 
 void adb_launch_score(const DevRaw& raw, const DevLib& lib, const adb_scoring_config& cfg, DevCandidatesIn cand,
-                      DevScoresOut out, float* d_workspace, int64_t workspace_floats_per_warp, int n_resident_warps,
-                      uint32_t* d_status, cudaStream_t stream, int* n_launches);
-int adb_score_resident_warps(int device);
+                      DevScoresOut out, float* d_workspace, int64_t workspace_floats_per_tile, int n_resident_tiles,
+                      const int32_t* d_order, uint32_t* d_status, cudaStream_t stream, int* n_launches);
+int adb_score_resident_tiles(int device, int top_k);
 int64_t adb_score_workspace_floats(int top_k, int64_t c_max);
 
 void adb_launch_fragcomp(int64_t n_windows, const int64_t* d_ws, const int64_t* d_we, const void* d_rt,
@@ -133,6 +139,51 @@ __device__ __forceinline__ int64_t adb_lower_bound(const float* __restrict__ a, 
   while (lo < hi) {
     int64_t mid = (lo + hi) >> 1;
     if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// m/z edge of bucket b (the SAME float expression builds the index and routes the queries)
+__device__ __forceinline__ float adb_bucket_edge(const DevRaw& raw, int b) {
+  return __fmaf_rn((float)b, raw.bucket_width, raw.bucket_lo);
+}
+
+// One spectrum as a (pointer, length) view with 32-bit offsets.
+struct AdbSpectrum {
+  const float* mz;
+  const float* intensity;
+  int n;
+};
+
+__device__ __forceinline__ AdbSpectrum adb_spectrum(const DevRaw& raw, int64_t scan) {
+  int64_t start = __ldg(raw.peak_start + scan), stop = __ldg(raw.peak_stop + scan);
+  AdbSpectrum s;
+  s.mz = raw.mz + start;
+  s.intensity = raw.intensity + start;
+  s.n = (int)(stop - start);
+  return s;
+}
+
+// Search range [lo, hi] that contains the lower bound of v in one spectrum: the bucket index narrows it to
+// ~n/64 peaks with one 8-byte read of an L2-resident table.
+__device__ __forceinline__ void adb_bucket_range(const DevRaw& raw, int64_t scan, const AdbSpectrum& s, float v, int& lo, int& hi) {
+  int b = (int)((v - raw.bucket_lo) * raw.bucket_inv_width);
+  b = max(0, min(b, ADB_N_BUCKETS - 1));
+  while (b > 0 && adb_bucket_edge(raw, b) > v) b--;
+  while (b < ADB_N_BUCKETS - 1 && adb_bucket_edge(raw, b + 1) <= v) b++;
+  const int32_t* row = raw.bucket_idx + scan * ADB_N_BUCKETS;
+  lo = (b == 0) ? 0 : __ldg(row + b);
+  hi = (b == ADB_N_BUCKETS - 1) ? s.n : __ldg(row + b + 1);
+}
+
+// lower bound of v inside one spectrum (first index with mz >= v).  Same result as
+// np.searchsorted(mz[start:stop], v, "left") / _search_sorted_reference_left (alpharaw_jit.py:53-75).
+__device__ __forceinline__ int adb_spectrum_lower_bound(const DevRaw& raw, int64_t scan, const AdbSpectrum& s, float v) {
+  int lo, hi;
+  adb_bucket_range(raw, scan, s, v, lo, hi);
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(s.mz + mid) < v) lo = mid + 1; else hi = mid;
   }
   return lo;
 }

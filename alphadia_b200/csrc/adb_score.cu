@@ -5,7 +5,9 @@
 // transfer function / template / observation importance (scoring/quadrupole.py:80-115,261-335), profiles
 // (scoring/utils.py:26-66) and the 46 features (scoring/features/*.py).
 //
-// Mapping: ONE WARP PER CANDIDATE.
+// Mapping: ONE TILE PER CANDIDATE — a 16-lane half-warp when top_k_fragments <= 16 (two candidates per warp, so
+// the fragment-per-lane phases keep 12 of 16 lanes busy), a full warp otherwise.  Candidates are visited in
+// (quad window, frame_start) order so neighbouring tiles read the same spectra (L2/L1 reuse).
 //   * extraction: lanes stride over (spectrum, fragment) items with the fragment index fastest, so the 12
 //     lanes probing one spectrum share the first levels of their binary searches (same sectors);
 //     the per-cell m/z recurrence runs in ascending peak order inside one lane (order-dependent f32).
@@ -17,30 +19,33 @@
 //     cross-fragment statistics are short sequential loops over shared memory, executed by all lanes.
 //   * candidates whose cube does not fit the shared-memory scratch fall back to a per-warp HBM workspace
 //     through the same generic pointer.
+#include <cooperative_groups.h>
+
 #include "adb_common.cuh"
 
-#define FULL 0xffffffffu
-#define WARPS_PER_BLOCK 4
-#define SMEM_FLOATS_PER_WARP 3072  // 12 KB dynamic scratch per warp
+namespace cg = cooperative_groups;
+
+#define SCORE_THREADS 128
+#define SMEM_FLOATS_PER_TILE 1536  // 6 KB dynamic scratch per candidate tile; larger cubes use the HBM workspace
 
 namespace {
 
-struct WarpSmall {
+template <int TILE>
+struct TileSmall {
   // selected fragments, m/z sorted (FragmentContainer, fragment_container.py:12-45)
-  float mz_library[ADB_MAX_FRAGMENTS], mz[ADB_MAX_FRAGMENTS], intensity[ADB_MAX_FRAGMENTS];
-  float lo[ADB_MAX_FRAGMENTS], hi[ADB_MAX_FRAGMENTS];
-  uint8_t type[ADB_MAX_FRAGMENTS], loss_type[ADB_MAX_FRAGMENTS], charge[ADB_MAX_FRAGMENTS],
-      number[ADB_MAX_FRAGMENTS], position[ADB_MAX_FRAGMENTS];
-  int fmap[ADB_MAX_FRAGMENTS];        // masked fragment w -> selected fragment f
-  int sorted_idx[ADB_MAX_FRAGMENTS];  // np.argsort(intensity)[::-1] over masked fragments
-  int frame_peak[ADB_MAX_FRAGMENTS];
-  float fint[ADB_MAX_FRAGMENTS];      // fragments.intensity after apply_mask (sum 1)
-  float fin[ADB_MAX_FRAGMENTS];       // fragment_intensity_norm
-  float ofi[ADB_MAX_FRAGMENTS];       // observed_fragment_intensity
-  float cosv[ADB_MAX_FRAGMENTS];
-  float corr_list[ADB_MAX_FRAGMENTS];
-  float rfw[ADB_MAX_FRAGMENTS];
-  double area_norm[ADB_MAX_FRAGMENTS], ofh_mean[ADB_MAX_FRAGMENTS], mass_error[ADB_MAX_FRAGMENTS], ci[ADB_MAX_FRAGMENTS];
+  float mz_library[TILE], mz[TILE], intensity[TILE];
+  float lo[TILE], hi[TILE];
+  uint8_t type[TILE], loss_type[TILE], charge[TILE], number[TILE], position[TILE];
+  int fmap[TILE];        // masked fragment w -> selected fragment f
+  int sorted_idx[TILE];  // np.argsort(intensity)[::-1] over masked fragments
+  int frame_peak[TILE];
+  float fint[TILE];      // fragments.intensity after apply_mask (sum 1)
+  float fin[TILE];       // fragment_intensity_norm
+  float ofi[TILE];       // observed_fragment_intensity
+  float cosv[TILE];
+  float corr_list[TILE];
+  float rfw[TILE];
+  double area_norm[TILE], ofh_mean[TILE], mass_error[TILE], ci[TILE];
   double qtf[ADB_MAX_ISOTOPES * ADB_MAX_OBS];
   double esc[ADB_MAX_OBS], efc[ADB_MAX_OBS];
   double H[ADB_MAX_ISOTOPES], MZo[ADB_MAX_ISOTOPES];
@@ -49,9 +54,7 @@ struct WarpSmall {
   float spi[ADB_MAX_ISOTOPES], wspi[ADB_MAX_ISOTOPES];
   int pos[ADB_MAX_OBS];
   float feat[ADB_NUM_FEATURES];
-  // library fragment staging (before top-k)
-  float t_int[ADB_MAX_LIB_FRAGMENTS], t_mz[ADB_MAX_LIB_FRAGMENTS];
-  int t_src[ADB_MAX_LIB_FRAGMENTS], t_sel[ADB_MAX_FRAGMENTS];
+  int t_sel[TILE];
 };
 
 struct ScoreParams {
@@ -61,22 +64,23 @@ struct ScoreParams {
   DevCandidatesIn cand;
   DevScoresOut out;
   float* workspace;
-  long long ws_floats_per_warp;
+  long long ws_floats_per_tile;
   uint32_t* status;
+  const int32_t* order;  // processing order of the candidates (locality), may be null
 };
 
 // one (spectrum, query window) cell of get_dense(absolute_masses=True): alpharaw_jit.py:290-335.
 // prev_hi: upper bound of the previous (lower m/z) window when it overlaps this one, else -1.
 __device__ __forceinline__ void extract_cell(const DevRaw& raw, int64_t scan, float lo, float hi, float prev_hi,
                                              float& acc_i, float& acc_m) {
-  int64_t start = __ldg(raw.peak_start + scan), stop = __ldg(raw.peak_stop + scan);
-  int64_t idx = adb_lower_bound(raw.mz, start, stop, lo);
+  const AdbSpectrum sp = adb_spectrum(raw, scan);
+  int idx = adb_spectrum_lower_bound(raw, scan, sp, lo);
   if (prev_hi >= lo)  // the search cursor only moves forward: peaks taken by the previous window are gone
-    while (idx < stop && __ldg(raw.mz + idx) <= prev_hi) idx++;
-  while (idx < stop) {
-    float nm = __ldg(raw.mz + idx);
+    while (idx < sp.n && __ldg(sp.mz + idx) <= prev_hi) idx++;
+  while (idx < sp.n) {
+    float nm = __ldg(sp.mz + idx);
     if (!(nm <= hi)) break;
-    float ni = __ldg(raw.intensity + idx);
+    float ni = __ldg(sp.intensity + idx);
     ni = __fmul_rn(ni, ((double)ni > 1e-26) ? 1.0f : 0.0f);
     float num32 = __fadd_rn(__fmul_rn(acc_m, acc_i), __fmul_rn(ni, nm));
     float den32 = __fadd_rn(acc_i, ni);
@@ -104,7 +108,10 @@ __device__ double corrcoef01(const double* x, const float* yf, int n) {
   return (cxy / sqrt(cyy)) / sqrt(cxx);
 }
 
-__device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall& sm, float* smem_scratch, float* ws_scratch) {
+template <int TILE>
+__device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_block_tile<TILE>& tile, TileSmall<TILE>& sm,
+                          float* smem_scratch, float* ws_scratch) {
+  const int lane = (int)tile.thread_rank();
   const DevRaw& raw = P.raw;
   const DevLib& lib = P.lib;
   const adb_scoring_config& cfg = P.cfg;
@@ -132,45 +139,49 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     if (lane == 0) atomicOr(P.status, ADB_STATUS_TOO_MANY_LIB_FRAGMENTS);
     return;
   }
+  // staging of the library fragments (before top-k) in the tile's scratch
+  float* t_int = smem_scratch;
+  float* t_mz = smem_scratch + ADB_MAX_LIB_FRAGMENTS;
+  int* t_src = (int*)(smem_scratch + 2 * ADB_MAX_LIB_FRAGMENTS);
   int m = 0;
-  for (int base = 0; base < n_all; base += 32) {
+  for (int base = 0; base < n_all; base += TILE) {
     int j = base + lane;
     bool keep = j < n_all && (!cfg.exclude_shared_ions || lib.frag_cardinality[fs + j] <= 1);
-    unsigned b = __ballot_sync(FULL, keep);
+    unsigned b = tile.ballot(keep);
     if (keep) {
       int u = m + __popc(b & ((1u << lane) - 1u));
-      sm.t_src[u] = j;
-      sm.t_int[u] = lib.frag_intensity[fs + j];
-      sm.t_mz[u] = lib.frag_mz[fs + j];
+      t_src[u] = j;
+      t_int[u] = lib.frag_intensity[fs + j];
+      t_mz[u] = lib.frag_mz[fs + j];
     }
     m += __popc(b);
   }
-  __syncwarp();
-  const int F0 = min(min(m, K), ADB_MAX_FRAGMENTS);
-  for (int u = lane; u < m; u += 32) {  // descending-intensity position (stable argsort reversed)
-    float v = sm.t_int[u];
+  tile.sync();
+  const int F0 = min(min(m, K), TILE);
+  for (int u = lane; u < m; u += TILE) {  // descending-intensity position (stable argsort reversed)
+    float v = t_int[u];
     int rank_asc = 0;
-    for (int q = 0; q < m; q++) rank_asc += (sm.t_int[q] < v) || (sm.t_int[q] == v && q < u);
+    for (int q = 0; q < m; q++) rank_asc += (t_int[q] < v) || (t_int[q] == v && q < u);
     int r = m - 1 - rank_asc;
     if (r < F0) sm.t_sel[r] = u;
   }
-  __syncwarp();
-  for (int r = lane; r < F0; r += 32) {  // stable m/z order among the selected
+  tile.sync();
+  for (int r = lane; r < F0; r += TILE) {  // stable m/z order among the selected
     int u = sm.t_sel[r];
-    float v = sm.t_mz[u];
+    float v = t_mz[u];
     int rank2 = 0;
-    for (int q = 0; q < F0; q++) { float vq = sm.t_mz[sm.t_sel[q]]; rank2 += (vq < v) || (vq == v && q < r); }
-    int64_t g = fs + sm.t_src[u];
+    for (int q = 0; q < F0; q++) { float vq = t_mz[sm.t_sel[q]]; rank2 += (vq < v) || (vq == v && q < r); }
+    int64_t g = fs + t_src[u];
     sm.mz_library[rank2] = lib.frag_mz_library[g];
     sm.mz[rank2] = v;
-    sm.intensity[rank2] = sm.t_int[u];
+    sm.intensity[rank2] = t_int[u];
     sm.type[rank2] = lib.frag_type[g];
     sm.loss_type[rank2] = lib.frag_loss_type[g];
     sm.charge[rank2] = lib.frag_charge[g];
     sm.number[rank2] = lib.frag_number[g];
     sm.position[rank2] = lib.frag_position[g];
   }
-  __syncwarp();
+  tile.sync();
   const int F = F0;
   if (F <= 3) return;
 
@@ -187,16 +198,16 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     sm.lo_p[lane] = (float)((double)mz - d);
     sm.hi_p[lane] = (float)((double)mz + d);
   }
-  __syncwarp();
+  tile.sync();
   float mn = sm.iso_mz[0], mx = sm.iso_mz[0];
   for (int i = 1; i < nI; i++) { mn = fminf(mn, sm.iso_mz[i]); mx = fmaxf(mx, sm.iso_mz[i]); }
   const float q0 = (float)((double)mn - 0.5), q1 = (float)((double)mx + 0.5);  // candidate.py:203-205
 
   int nobs = 0;  // alpharaw_jit.py:19-50
-  for (int64_t base = 0; base < L; base += 32) {
+  for (int64_t base = 0; base < L; base += TILE) {
     int64_t j = base + lane;
     bool hit = j < L && ((double)q0 <= raw.cycle[2 * j + 1]) && ((double)q1 >= raw.cycle[2 * j]);
-    unsigned b = __ballot_sync(FULL, hit);
+    unsigned b = tile.ballot(hit);
     if (hit) {
       int u = nobs + __popc(b & ((1u << lane) - 1u));
       if (u < ADB_MAX_OBS) sm.pos[u] = (int)j;
@@ -220,21 +231,21 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
 
   // ---- scratch carve-up ----------------------------------------------------------------------
   const long long nFC = (long long)F * nobs * C;
-  long long need = 2 * nFC + 2LL * F * C + 2LL * nI * C + 2LL * nobs * C + C + 2 /*align*/ + 4LL * nobs * C + 4LL * C;
+  long long need = 2 * nFC + 1LL * F * C + 2LL * nI * C + 2LL * nobs * C + C + 2 /*align*/ + 4LL * nobs * C + 4LL * C;
   if (!cfg.experimental_xic) need += (long long)F * F;
   float* scratch = smem_scratch;
-  if (need > SMEM_FLOATS_PER_WARP) {
-    if (ws_scratch == nullptr || need > P.ws_floats_per_warp) {
+  if (need > SMEM_FLOATS_PER_TILE) {
+    if (ws_scratch == nullptr || need > P.ws_floats_per_tile) {
       if (lane == 0) atomicOr(P.status, ADB_STATUS_SCRATCH_OVERFLOW);
       return;
     }
     scratch = ws_scratch;
   }
   float* dfi = scratch;               // [F][nobs][C] intensity (one scan row)
-  float* dfm = dfi + nFC;             // [F][nobs][C] m/z channel
+  float* dfm = dfi + nFC;             // [F][nobs][C] m/z channel; dead after the fragment features ...
+  float* nrm = dfm;                   // ... then reused: [F][C] normalised / centred profiles
   float* bp = dfm + nFC;              // [F][C] best profile (enveloped)
-  float* nrm = bp + (long long)F * C; // [F][C] normalised profiles / centred profiles
-  float* dpi = nrm + (long long)F * C;// [I][C]
+  float* dpi = bp + (long long)F * C; // [I][C]
   float* dpm = dpi + (long long)nI * C;
   float* tmpl = dpm + (long long)nI * C;  // [nobs][C]
   float* tfp = tmpl + (long long)nobs * C;// [nobs][C] template frame profile
@@ -244,9 +255,10 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
   double* wtab = (double*)after;             // [nobs][2][C] exp(-0.1 dist) tables for fragments
   double* wtab_p = wtab + 2LL * nobs * C;    // [2][C] for precursors
   float* red = (float*)(wtab_p + 2LL * C);   // [F][F] legacy correlation accumulator
+  tile.sync();  // the staging area in the scratch is dead from here on
 
   // ---- candidate.py:216-223 fragment cube -------------------------------------------------------
-  for (long long t = lane; t < nFC; t += 32) {
+  for (long long t = lane; t < nFC; t += TILE) {
     int k = (int)(t % F);
     long long oc = t / F;
     int c = (int)(oc % C), o = (int)(oc / C);
@@ -259,7 +271,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     dfm[cell] = am;
   }
   // ---- candidate.py:239-269 MS1 cube with the observation collapse --------------------------------
-  for (int t = lane; t < nI * C; t += 32) {
+  for (int t = lane; t < nI * C; t += TILE) {
     int i = t % nI, c = t / nI;
     float s32 = 0.f;
     double smz = 0.0;
@@ -278,7 +290,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
   }
 
   // ---- quadrupole.py:80-115,261-301 transfer function (n_scans == 1) --------------------------------
-  for (int t = lane; t < nI * nobs; t += 32) {
+  for (int t = lane; t < nI * nobs; t += TILE) {
     int i = t / nobs, o = t % nobs;
     double mu1 = raw.cycle[2 * sm.pos[o] + 0] + cfg.quad_delta_mu[0];
     double mu2 = raw.cycle[2 * sm.pos[o] + 1] + cfg.quad_delta_mu[1];
@@ -286,32 +298,32 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     double a1 = (x - mu1) / cfg.quad_sigma[0], a2 = (x - mu2) / cfg.quad_sigma[1];
     sm.qtf[i * nobs + o] = 1.0 / (1.0 + exp(-a1)) - 1.0 / (1.0 + exp(-a2));
   }
-  __syncwarp();
+  tile.sync();
   if (lane < nobs) {  // candidate.py:287-289
     double s = 0;
     for (int i = 0; i < nI; i++) s = __dadd_rn(s, sm.qtf[i * nobs + lane]);
     sm.qmask[lane] = (float)(s / (double)nI);
   }
-  __syncwarp();
-  for (long long t = lane; t < nFC; t += 32) {  // candidate.py:290
+  tile.sync();
+  for (long long t = lane; t < nFC; t += TILE) {  // candidate.py:290
     int o = (int)((t / C) % nobs);
     dfi[t] = __fmul_rn(dfi[t], sm.qmask[o]);
   }
-  for (int t = lane; t < nobs * C; t += 32) {  // quadrupole.py:304-324 template
+  for (int t = lane; t < nobs * C; t += TILE) {  // quadrupole.py:304-324 template
     int o = t / C, c = t % C;
     double acc = 0;
     for (int i = 0; i < nI; i++)
       acc = __dadd_rn(acc, __dmul_rn((double)__fmul_rn(dpi[i * C + c], sm.iso_int[i]), sm.qtf[i * nobs + o]));
     tmpl[t] = (float)acc;
   }
-  __syncwarp();
+  tile.sync();
   // ---- quadrupole.py:327-335 observation importance ------------------------------------------------
   if (lane < nobs) {
     float sc = 0.f;
     for (int c = 0; c < C; c++) sc = __fadd_rn(sc, tmpl[lane * C + c]);
     sm.sti[lane] = twice(sc);  // sum_template_intensity, also used by the cosine score
   }
-  __syncwarp();
+  tile.sync();
   {
     float tot = 0.f;
     for (int o = 0; o < nobs; o++) tot = __fadd_rn(tot, sm.sti[o]);
@@ -329,24 +341,24 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     }
     fvalid = t_o > 0.f;
   }
-  const unsigned vb = __ballot_sync(FULL, fvalid);
+  const unsigned vb = tile.ballot(fvalid);
   const int Fv = __popc(vb);
   if (Fv < 2) return;
   if (fvalid) sm.fmap[__popc(vb & ((1u << lane) - 1u))] = lane;
-  __syncwarp();
+  tile.sync();
   const bool act = lane < Fv;          // lane w <-> masked fragment w
   const int f = act ? sm.fmap[lane] : 0;
   {  // fragment_container.py:119-120 renormalise, fragment_features.py:218
     float isum = 0.f;
     for (int w = 0; w < Fv; w++) isum = __fadd_rn(isum, sm.intensity[sm.fmap[w]]);
     if (act) sm.fint[lane] = __fdiv_rn(sm.intensity[f], isum);
-    __syncwarp();
+    tile.sync();
     float t = 0.f;
     for (int w = 0; w < Fv; w++) t = __fadd_rn(t, sm.fint[w]);
     if (act) sm.fin[lane] = __fdiv_rn(sm.fint[lane], t);
   }
   // ---- candidate.py:341 template frame profile with or_envelope (scoring/utils.py:46-53) -----------
-  for (int t = lane; t < nobs * C; t += 32) {
+  for (int t = lane; t < nobs * C; t += TILE) {
     int c = t % C;
     float x = twice(tmpl[t]);
     float res = x;
@@ -357,7 +369,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     tfp[t] = res;
   }
   // distance-weight tables for weighted_center_mean (features_utils.py:9-26)
-  for (int t = lane; t < 2 * C; t += 32) {  // precursor "centres" = (n_scans, n_observations) = (2, 1)
+  for (int t = lane; t < 2 * C; t += TILE) {  // precursor "centres" = (n_scans, n_observations) = (2, 1)
     int s = t / C, c = t % C;
     double ds = (double)s - 2.0, dc = (double)c - 1.0;
     wtab_p[t] = exp(-0.1 * sqrt(ds * ds + dc * dc));
@@ -377,17 +389,17 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     sm.esc[lane] = (any && isum > 0) ? ssum / isum : 0.0;
     sm.efc[lane] = (any && isum > 0) ? fsum / isum : 0.0;
   }
-  __syncwarp();
-  for (int t = lane; t < nobs * 2 * C; t += 32) {
+  tile.sync();
+  for (int t = lane; t < nobs * 2 * C; t += TILE) {
     int o = t / (2 * C), s = (t / C) % 2, c = t % C;
     double ds = (double)s - sm.esc[o], dc = (double)c - sm.efc[o];
     wtab[t] = exp(-0.1 * sqrt(ds * ds + dc * dc));
   }
-  __syncwarp();
+  tile.sync();
 
   float* fa = sm.feat;
-  for (int t = lane; t < ADB_NUM_FEATURES; t += 32) fa[t] = 0.f;
-  __syncwarp();
+  for (int t = lane; t < ADB_NUM_FEATURES; t += TILE) fa[t] = 0.f;
+  tile.sync();
   if (lane == 0) {
     fa[28] = (float)((double)Fv / (double)F);  // candidate.py:362
     // features/location_features.py:9-33
@@ -421,7 +433,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     sm.H[lane] = (any1 && w1 > 0) ? v1 / w1 : 0.0;
     sm.MZo[lane] = (any2 && w2 > 0) ? v2 / w2 : 0.0;
   }
-  __syncwarp();
+  tile.sync();
   if (lane == 0) {
     int amax = 0;
     for (int i = 1; i < nI; i++) if (sm.iso_int[i] > sm.iso_int[amax]) amax = i;
@@ -580,8 +592,8 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     for (int q = 0; q < Fv; q++) rank_asc += (sm.fint[q] < v) || (sm.fint[q] == v && q < lane);
     sm.sorted_idx[Fv - 1 - rank_asc] = lane;
   }
-  const unsigned anyh_b = __ballot_sync(FULL, anyh);
-  __syncwarp();
+  const unsigned anyh_b = tile.ballot(anyh);
+  tile.sync();
   // fragment-level outputs, candidate.py:403-442
   const size_t obase = (size_t)ci * (size_t)K;
   if (act && cfg.collect_fragments && lane < K) {
@@ -597,7 +609,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     P.out.fragment_charge[obase + lane] = sm.charge[f];
     P.out.fragment_loss_type[obase + lane] = sm.loss_type[f];
   }
-  __syncwarp();
+  tile.sync();
   if (lane == 0) {
     double sum_ofh = 0;
     for (int w = 0; w < Fv; w++) sum_ofh = __dadd_rn(sum_ofh, sm.ofh_mean[w]);
@@ -640,7 +652,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
       else { fa[44] = 0.f; fa[45] = 15.f; }
     }
   }
-  __syncwarp();
+  tile.sync();
 
   // ================= features/profile_features.py:18-206 =================
   // fragments_frame_profile accessor: the best observation's rows were enveloped in place when
@@ -666,8 +678,8 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
       float* nr = nrm + (long long)lane * C;
       for (int c = 0; c < C; c++) nr[c] = (cint > 0) ? (float)((double)isl(lane, f, c) / cint) : 0.f;
     }
-    __syncwarp();
-    for (int c = lane; c < C; c += 32) {  // median over fragments (scoring_utils.py:127-152)
+    tile.sync();
+    for (int c = lane; c < C; c += TILE) {  // median over fragments (scoring_utils.py:127-152)
       float vlo = 0.f, vhi = 0.f;
       for (int w = 0; w < Fv; w++) {
         float v = nrm[(long long)w * C + c];
@@ -678,7 +690,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
       }
       med[c] = (Fv & 1) ? vhi : (float)((double)__fadd_rn(vlo, vhi) / 2);
     }
-    __syncwarp();
+    tile.sync();
     // correlation_coefficient(median_profile, intensity_slice), scoring_utils.py:20-76
     float sx = 0.f;
     for (int c = 0; c < C; c++) sx = __fadd_rn(sx, med[c]);
@@ -701,7 +713,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
       double vxy = varx * ((double)vy32 / (double)C);
       sm.corr_list[lane] = (vxy == 0) ? 0.f : (float)(cov / sqrt(vxy));
     }
-    __syncwarp();
+    tile.sync();
     if (lane == 0) {
       int n3 = min(Fv, 3);
       float t = 0.f;
@@ -710,9 +722,9 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     }
   } else {
     // legacy: observation-weighted F x F correlation matrix (scoring/utils.py:513-571), float32
-    for (int t = lane; t < Fv * Fv; t += 32) red[t] = 0.f;
+    for (int t = lane; t < Fv * Fv; t += TILE) red[t] = 0.f;
     for (int o = 0; o < nobs; o++) {
-      __syncwarp();
+      tile.sync();
       if (act) {
         float s = 0.f;
         for (int c = 0; c < C; c++) s = __fadd_rn(s, ffp(lane, f, o, c));
@@ -722,8 +734,8 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
         for (int c = 0; c < C; c++) { float cv = __fsub_rn(ffp(lane, f, o, c), mean); cen[c] = cv; ss = __fadd_rn(ss, __fmul_rn(cv, cv)); }
         sm.rfw[lane] = sqrtf(__fdiv_rn(ss, (float)C));
       }
-      __syncwarp();
-      for (int t = lane; t < Fv * Fv; t += 32) {
+      tile.sync();
+      for (int t = lane; t < Fv * Fv; t += TILE) {
         int a = t / Fv, b = t % Fv;
         const float* ca = nrm + (long long)a * C;
         const float* cb = nrm + (long long)b * C;
@@ -735,13 +747,13 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
         red[t] = __fadd_rn(red[t], __fmul_rn(corr, sm.oi[o]));
       }
     }
-    __syncwarp();
+    tile.sync();
     if (act) {
       float t = 0.f;
       for (int g = 0; g < Fv; g++) t = __fadd_rn(t, __fmul_rn(red[lane * Fv + g], sm.fint[g]));
       sm.corr_list[lane] = t;
     }
-    __syncwarp();
+    tile.sync();
     if (lane == 0) {
       int n3 = min(Fv, 3);
       float t = 0.f;
@@ -789,7 +801,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
       sm.rfw[lane] = __fadd_rn(sm.rfw[lane], __fmul_rn(fw, sm.oi[o]));
       sm.frame_peak[lane] = am;
     }
-    __syncwarp();
+    tile.sync();
     if (lane == 0) {  // median frame peak of this observation (profile_features.py:193-204)
       double vlo = 0, vhi = 0;
       for (int w = 0; w < Fv; w++) {
@@ -803,7 +815,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
       double prev = (o == 0) ? 0.0 : sm.esc[0];
       sm.esc[0] = __dadd_rn(prev, __dmul_rn(delta, (double)sm.oi[o]));  // esc no longer needed
     }
-    __syncwarp();
+    tile.sync();
   }
   if (lane == 0) {
     float t31 = 0.f, t33 = 0.f, t38 = 0.f;
@@ -827,38 +839,50 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, int lane, WarpSmall&
     if (nb > 0) { fa[34] = (float)((double)sb / (double)min(nb, 3)); fa[35] = (float)nb; }
     if (ny > 0) { fa[36] = (float)((double)sy / (double)min(ny, 3)); fa[37] = (float)ny; }
   }
-  __syncwarp();
+  tile.sync();
   // ---- candidate.py:475-481 ---------------------------------------------------------------------
   if (act && cfg.collect_fragments && lane < K) P.out.fragment_correlation[obase + lane] = sm.corr_list[lane];
-  for (int t = lane; t < ADB_NUM_FEATURES; t += 32) P.out.features[(size_t)ci * ADB_NUM_FEATURES + t] = fa[t];
+  for (int t = lane; t < ADB_NUM_FEATURES; t += TILE) P.out.features[(size_t)ci * ADB_NUM_FEATURES + t] = fa[t];
   if (lane == 0) P.out.valid[ci] = 1;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) adb_score_kernel(const __grid_constant__ ScoreParams P) {
+template <int TILE>
+__global__ void __launch_bounds__(SCORE_THREADS) adb_score_kernel(const __grid_constant__ ScoreParams P) {
   extern __shared__ __align__(16) float dyn_smem[];
-  __shared__ WarpSmall small[WARPS_PER_BLOCK];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long gw = (long long)blockIdx.x * WARPS_PER_BLOCK + wib;
-  const long long n_warps = (long long)gridDim.x * WARPS_PER_BLOCK;
-  float* scratch = dyn_smem + (size_t)wib * SMEM_FLOATS_PER_WARP;
-  float* ws = P.workspace ? P.workspace + (size_t)gw * (size_t)P.ws_floats_per_warp : nullptr;
-  for (long long ci = gw; ci < P.cand.n; ci += n_warps) {
-    score_one(P, ci, lane, small[wib], scratch, ws);
-    __syncwarp();
+  constexpr int TILES = SCORE_THREADS / TILE;
+  __shared__ TileSmall<TILE> small[TILES];
+  cg::thread_block block = cg::this_thread_block();
+  cg::thread_block_tile<TILE> tile = cg::tiled_partition<TILE>(block);
+  const int tib = (int)(threadIdx.x / TILE);
+  const long long gt = (long long)blockIdx.x * TILES + tib;
+  const long long n_tiles = (long long)gridDim.x * TILES;
+  float* scratch = dyn_smem + (size_t)tib * SMEM_FLOATS_PER_TILE;
+  float* ws = P.workspace ? P.workspace + (size_t)gt * (size_t)P.ws_floats_per_tile : nullptr;
+  for (long long it = gt; it < P.cand.n; it += n_tiles) {
+    const long long ci = P.order ? (long long)P.order[it] : it;
+    score_one<TILE>(P, ci, tile, small[tib], scratch, ws);
+    tile.sync();
   }
+}
+
+template <int TILE>
+int resident_tiles(int device) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  int blocks_per_sm = 0;
+  size_t dyn = (size_t)(SCORE_THREADS / TILE) * SMEM_FLOATS_PER_TILE * sizeof(float);
+  cudaFuncSetAttribute(adb_score_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, adb_score_kernel<TILE>, SCORE_THREADS, dyn);
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  return sms * blocks_per_sm * (SCORE_THREADS / TILE);
 }
 
 }  // namespace
 
-int adb_score_resident_warps(int device) {
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  int blocks_per_sm = 0;
-  size_t dyn = (size_t)WARPS_PER_BLOCK * SMEM_FLOATS_PER_WARP * sizeof(float);
-  cudaFuncSetAttribute(adb_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, adb_score_kernel, WARPS_PER_BLOCK * 32, dyn);
-  if (blocks_per_sm < 1) blocks_per_sm = 1;
-  return sms * blocks_per_sm * WARPS_PER_BLOCK;
+int adb_score_tile(int top_k) { return top_k <= 16 ? 16 : 32; }
+
+int adb_score_resident_tiles(int device, int top_k) {
+  return top_k <= 16 ? resident_tiles<16>(device) : resident_tiles<32>(device);
 }
 
 int64_t adb_score_workspace_floats(int top_k, int64_t c_max) {
@@ -867,18 +891,25 @@ int64_t adb_score_workspace_floats(int top_k, int64_t c_max) {
 }
 
 void adb_launch_score(const DevRaw& raw, const DevLib& lib, const adb_scoring_config& cfg, DevCandidatesIn cand,
-                      DevScoresOut out, float* d_workspace, int64_t workspace_floats_per_warp, int n_resident_warps,
-                      uint32_t* d_status, cudaStream_t stream, int* n_launches) {
+                      DevScoresOut out, float* d_workspace, int64_t workspace_floats_per_tile, int n_resident_tiles,
+                      const int32_t* d_order, uint32_t* d_status, cudaStream_t stream, int* n_launches) {
   if (cand.n <= 0) return;
   ScoreParams P;
   P.raw = raw; P.lib = lib; P.cfg = cfg; P.cand = cand; P.out = out;
-  P.workspace = d_workspace; P.ws_floats_per_warp = workspace_floats_per_warp; P.status = d_status;
-  size_t dyn = (size_t)WARPS_PER_BLOCK * SMEM_FLOATS_PER_WARP * sizeof(float);
-  cudaFuncSetAttribute(adb_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  long long blocks = n_resident_warps / WARPS_PER_BLOCK;  // persistent: one resident wave, warps stride over candidates
-  long long needed = (cand.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  P.workspace = d_workspace; P.ws_floats_per_tile = workspace_floats_per_tile; P.status = d_status; P.order = d_order;
+  const int tile = adb_score_tile((int)cfg.top_k_fragments);
+  const int tiles_per_block = SCORE_THREADS / tile;
+  size_t dyn = (size_t)tiles_per_block * SMEM_FLOATS_PER_TILE * sizeof(float);
+  long long blocks = n_resident_tiles / tiles_per_block;  // persistent: one resident wave, tiles stride over candidates
+  long long needed = (cand.n + tiles_per_block - 1) / tiles_per_block;
   if (blocks > needed) blocks = needed;
   if (blocks < 1) blocks = 1;
-  adb_score_kernel<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, dyn, stream>>>(P);
+  if (tile == 16) {
+    cudaFuncSetAttribute(adb_score_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    adb_score_kernel<16><<<(unsigned)blocks, SCORE_THREADS, dyn, stream>>>(P);
+  } else {
+    cudaFuncSetAttribute(adb_score_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    adb_score_kernel<32><<<(unsigned)blocks, SCORE_THREADS, dyn, stream>>>(P);
+  }
   if (n_launches) (*n_launches)++;
 }
