@@ -94,7 +94,7 @@ __device__ __forceinline__ void extract_cell(const DevRaw& raw, int64_t scan, fl
 __device__ __forceinline__ float twice(float x) { return __fadd_rn(x, x); }  // sum over the 2 identical scan rows
 
 // np.corrcoef(x, y)[0, 1] as numba evaluates it (cov with 1/(n-1), divide by both std)
-__device__ double corrcoef01(const double* x, const float* yf, int n) {
+__device__ __noinline__ double corrcoef01(const double* x, const float* yf, int n) {
   double mx = 0, my = 0;
   for (int i = 0; i < n; i++) { mx = __dadd_rn(mx, x[i]); my = __dadd_rn(my, (double)yf[i]); }
   mx /= n; my /= n;
@@ -106,6 +106,34 @@ __device__ double corrcoef01(const double* x, const float* yf, int n) {
   double fact = 1.0 / (double)(n - 1);
   cxx *= fact; cyy *= fact; cxy *= fact;
   return (cxy / sqrt(cyy)) / sqrt(cxx);
+}
+
+// features_utils.py:9-26 weighted_center_mean of the intensity row r and the m/z row rm of one (fragment,
+// observation) cell over the two identical scan rows, with the tabulated distance weights wt[2][C]
+__device__ __noinline__ void weighted_center_mean_pair(const float* r, const float* rm, const double* wt, int C,
+                                                       double& h, double& mz) {
+  double v1 = 0, w1 = 0, v2 = 0, w2 = 0;
+  bool any1 = false, any2 = false;
+#pragma unroll 1
+  for (int s = 0; s < 2; s++)
+#pragma unroll 1
+    for (int c = 0; c < C; c++) {
+      double wgt = wt[s * C + c];
+      float a = r[c], b = rm[c];
+      if (a > 0.f) { any1 = true; v1 = __dadd_rn(v1, __dmul_rn((double)a, wgt)); w1 = __dadd_rn(w1, wgt); }
+      if (b > 0.f) { any2 = true; v2 = __dadd_rn(v2, __dmul_rn((double)b, wgt)); w2 = __dadd_rn(w2, wgt); }
+    }
+  h = (any1 && w1 > 0) ? v1 / w1 : 0.0;
+  mz = (any2 && w2 > 0) ? v2 / w2 : 0.0;
+}
+
+// sum over observations of fragments_frame_profile[f, :, c]; the best observation's row lives in bp when the
+// centre envelope mutated it (fragment_features.py:248-250)
+__device__ __noinline__ float frame_profile_obs_sum(const float* dfi_f, const float* bp_w, int nobs, int C, int c, int mutated_obs) {
+  float t = 0.f;
+#pragma unroll 1
+  for (int o = 0; o < nobs; o++) t = __fadd_rn(t, (o == mutated_obs) ? bp_w[c] : __fadd_rn(dfi_f[o * C + c], dfi_f[o * C + c]));
+  return t;
 }
 
 template <int TILE>
@@ -144,7 +172,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   float* t_mz = smem_scratch + ADB_MAX_LIB_FRAGMENTS;
   int* t_src = (int*)(smem_scratch + 2 * ADB_MAX_LIB_FRAGMENTS);
   int m = 0;
-  for (int base = 0; base < n_all; base += TILE) {
+  _Pragma("unroll 1") for (int base = 0; base < n_all; base += TILE) {
     int j = base + lane;
     bool keep = j < n_all && (!cfg.exclude_shared_ions || lib.frag_cardinality[fs + j] <= 1);
     unsigned b = tile.ballot(keep);
@@ -158,19 +186,19 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   }
   tile.sync();
   const int F0 = min(min(m, K), TILE);
-  for (int u = lane; u < m; u += TILE) {  // descending-intensity position (stable argsort reversed)
+  _Pragma("unroll 1") for (int u = lane; u < m; u += TILE) {  // descending-intensity position (stable argsort reversed)
     float v = t_int[u];
     int rank_asc = 0;
-    for (int q = 0; q < m; q++) rank_asc += (t_int[q] < v) || (t_int[q] == v && q < u);
+    _Pragma("unroll 1") for (int q = 0; q < m; q++) rank_asc += (t_int[q] < v) || (t_int[q] == v && q < u);
     int r = m - 1 - rank_asc;
     if (r < F0) sm.t_sel[r] = u;
   }
   tile.sync();
-  for (int r = lane; r < F0; r += TILE) {  // stable m/z order among the selected
+  _Pragma("unroll 1") for (int r = lane; r < F0; r += TILE) {  // stable m/z order among the selected
     int u = sm.t_sel[r];
     float v = t_mz[u];
     int rank2 = 0;
-    for (int q = 0; q < F0; q++) { float vq = t_mz[sm.t_sel[q]]; rank2 += (vq < v) || (vq == v && q < r); }
+    _Pragma("unroll 1") for (int q = 0; q < F0; q++) { float vq = t_mz[sm.t_sel[q]]; rank2 += (vq < v) || (vq == v && q < r); }
     int64_t g = fs + t_src[u];
     sm.mz_library[rank2] = lib.frag_mz_library[g];
     sm.mz[rank2] = v;
@@ -200,11 +228,11 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   }
   tile.sync();
   float mn = sm.iso_mz[0], mx = sm.iso_mz[0];
-  for (int i = 1; i < nI; i++) { mn = fminf(mn, sm.iso_mz[i]); mx = fmaxf(mx, sm.iso_mz[i]); }
+  _Pragma("unroll 1") for (int i = 1; i < nI; i++) { mn = fminf(mn, sm.iso_mz[i]); mx = fmaxf(mx, sm.iso_mz[i]); }
   const float q0 = (float)((double)mn - 0.5), q1 = (float)((double)mx + 0.5);  // candidate.py:203-205
 
   int nobs = 0;  // alpharaw_jit.py:19-50
-  for (int64_t base = 0; base < L; base += TILE) {
+  _Pragma("unroll 1") for (int64_t base = 0; base < L; base += TILE) {
     int64_t j = base + lane;
     bool hit = j < L && ((double)q0 <= raw.cycle[2 * j + 1]) && ((double)q1 >= raw.cycle[2 * j]);
     unsigned b = tile.ballot(hit);
@@ -258,7 +286,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   tile.sync();  // the staging area in the scratch is dead from here on
 
   // ---- candidate.py:216-223 fragment cube -------------------------------------------------------
-  for (long long t = lane; t < nFC; t += TILE) {
+  _Pragma("unroll 1") for (long long t = lane; t < nFC; t += TILE) {
     int k = (int)(t % F);
     long long oc = t / F;
     int c = (int)(oc % C), o = (int)(oc / C);
@@ -271,13 +299,13 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     dfm[cell] = am;
   }
   // ---- candidate.py:239-269 MS1 cube with the observation collapse --------------------------------
-  for (int t = lane; t < nI * C; t += TILE) {
+  _Pragma("unroll 1") for (int t = lane; t < nI * C; t += TILE) {
     int i = t % nI, c = t / nI;
     float s32 = 0.f;
     double smz = 0.0;
     int count = 0;
     float prev_hi = (i > 0) ? sm.hi_p[i - 1] : -1.0f;
-    for (int j = 0; j < raw.n_ms1_pos; j++) {
+    _Pragma("unroll 1") for (int j = 0; j < raw.n_ms1_pos; j++) {
       int64_t scan = (int64_t)raw.ms1_pos[j] + (cs + c) * L;
       float ai = 0.f, am = 0.f;
       extract_cell(raw, scan, sm.lo_p[i], sm.hi_p[i], prev_hi, ai, am);
@@ -290,7 +318,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   }
 
   // ---- quadrupole.py:80-115,261-301 transfer function (n_scans == 1) --------------------------------
-  for (int t = lane; t < nI * nobs; t += TILE) {
+  _Pragma("unroll 1") for (int t = lane; t < nI * nobs; t += TILE) {
     int i = t / nobs, o = t % nobs;
     double mu1 = raw.cycle[2 * sm.pos[o] + 0] + cfg.quad_delta_mu[0];
     double mu2 = raw.cycle[2 * sm.pos[o] + 1] + cfg.quad_delta_mu[1];
@@ -301,18 +329,18 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   tile.sync();
   if (lane < nobs) {  // candidate.py:287-289
     double s = 0;
-    for (int i = 0; i < nI; i++) s = __dadd_rn(s, sm.qtf[i * nobs + lane]);
+    _Pragma("unroll 1") for (int i = 0; i < nI; i++) s = __dadd_rn(s, sm.qtf[i * nobs + lane]);
     sm.qmask[lane] = (float)(s / (double)nI);
   }
   tile.sync();
-  for (long long t = lane; t < nFC; t += TILE) {  // candidate.py:290
+  _Pragma("unroll 1") for (long long t = lane; t < nFC; t += TILE) {  // candidate.py:290
     int o = (int)((t / C) % nobs);
     dfi[t] = __fmul_rn(dfi[t], sm.qmask[o]);
   }
-  for (int t = lane; t < nobs * C; t += TILE) {  // quadrupole.py:304-324 template
+  _Pragma("unroll 1") for (int t = lane; t < nobs * C; t += TILE) {  // quadrupole.py:304-324 template
     int o = t / C, c = t % C;
     double acc = 0;
-    for (int i = 0; i < nI; i++)
+    _Pragma("unroll 1") for (int i = 0; i < nI; i++)
       acc = __dadd_rn(acc, __dmul_rn((double)__fmul_rn(dpi[i * C + c], sm.iso_int[i]), sm.qtf[i * nobs + o]));
     tmpl[t] = (float)acc;
   }
@@ -320,23 +348,23 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   // ---- quadrupole.py:327-335 observation importance ------------------------------------------------
   if (lane < nobs) {
     float sc = 0.f;
-    for (int c = 0; c < C; c++) sc = __fadd_rn(sc, tmpl[lane * C + c]);
+    _Pragma("unroll 1") for (int c = 0; c < C; c++) sc = __fadd_rn(sc, tmpl[lane * C + c]);
     sm.sti[lane] = twice(sc);  // sum_template_intensity, also used by the cosine score
   }
   tile.sync();
   {
     float tot = 0.f;
-    for (int o = 0; o < nobs; o++) tot = __fadd_rn(tot, sm.sti[o]);
+    _Pragma("unroll 1") for (int o = 0; o < nobs; o++) tot = __fadd_rn(tot, sm.sti[o]);
     if (lane < nobs) sm.oi[lane] = (tot == 0.f) ? __fdiv_rn(1.0f, (float)nobs) : __fdiv_rn(sm.sti[lane], tot);
   }
   // ---- candidate.py:319-329 fragment mask --------------------------------------------------------
   bool fvalid = false;
   if (lane < F) {
     float t_o = 0.f;
-    for (int o = 0; o < nobs; o++) {
+    _Pragma("unroll 1") for (int o = 0; o < nobs; o++) {
       float t_c = 0.f;
       const float* r = dfi + ((long long)lane * nobs + o) * C;
-      for (int c = 0; c < C; c++) t_c = __fadd_rn(t_c, r[c]);
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) t_c = __fadd_rn(t_c, r[c]);
       t_o = __fadd_rn(t_o, twice(t_c));
     }
     fvalid = t_o > 0.f;
@@ -350,15 +378,15 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   const int f = act ? sm.fmap[lane] : 0;
   {  // fragment_container.py:119-120 renormalise, fragment_features.py:218
     float isum = 0.f;
-    for (int w = 0; w < Fv; w++) isum = __fadd_rn(isum, sm.intensity[sm.fmap[w]]);
+    _Pragma("unroll 1") for (int w = 0; w < Fv; w++) isum = __fadd_rn(isum, sm.intensity[sm.fmap[w]]);
     if (act) sm.fint[lane] = __fdiv_rn(sm.intensity[f], isum);
     tile.sync();
     float t = 0.f;
-    for (int w = 0; w < Fv; w++) t = __fadd_rn(t, sm.fint[w]);
+    _Pragma("unroll 1") for (int w = 0; w < Fv; w++) t = __fadd_rn(t, sm.fint[w]);
     if (act) sm.fin[lane] = __fdiv_rn(sm.fint[lane], t);
   }
   // ---- candidate.py:341 template frame profile with or_envelope (scoring/utils.py:46-53) -----------
-  for (int t = lane; t < nobs * C; t += TILE) {
+  _Pragma("unroll 1") for (int t = lane; t < nobs * C; t += TILE) {
     int c = t % C;
     float x = twice(tmpl[t]);
     float res = x;
@@ -369,7 +397,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     tfp[t] = res;
   }
   // distance-weight tables for weighted_center_mean (features_utils.py:9-26)
-  for (int t = lane; t < 2 * C; t += TILE) {  // precursor "centres" = (n_scans, n_observations) = (2, 1)
+  _Pragma("unroll 1") for (int t = lane; t < 2 * C; t += TILE) {  // precursor "centres" = (n_scans, n_observations) = (2, 1)
     int s = t / C, c = t % C;
     double ds = (double)s - 2.0, dc = (double)c - 1.0;
     wtab_p[t] = exp(-0.1 * sqrt(ds * ds + dc * dc));
@@ -378,11 +406,11 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     const float* r = tmpl + lane * C;
     double isum = 0, ssum = 0, fsum = 0;
     bool any = false;
-    for (int s = 0; s < 2; s++)
-      for (int c = 0; c < C; c++) { float v = r[c]; if (v > 0.f) { any = true; isum = __dadd_rn(isum, (double)v); } }
+    _Pragma("unroll 1") for (int s = 0; s < 2; s++)
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) { float v = r[c]; if (v > 0.f) { any = true; isum = __dadd_rn(isum, (double)v); } }
     if (any)
-      for (int s = 0; s < 2; s++)
-        for (int c = 0; c < C; c++) {
+      _Pragma("unroll 1") for (int s = 0; s < 2; s++)
+        _Pragma("unroll 1") for (int c = 0; c < C; c++) {
           float v = r[c];
           if (v > 0.f) { ssum = __dadd_rn(ssum, __dmul_rn((double)s, (double)v)); fsum = __dadd_rn(fsum, __dmul_rn((double)c, (double)v)); }
         }
@@ -390,7 +418,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     sm.efc[lane] = (any && isum > 0) ? fsum / isum : 0.0;
   }
   tile.sync();
-  for (int t = lane; t < nobs * 2 * C; t += TILE) {
+  _Pragma("unroll 1") for (int t = lane; t < nobs * 2 * C; t += TILE) {
     int o = t / (2 * C), s = (t / C) % 2, c = t % C;
     double ds = (double)s - sm.esc[o], dc = (double)c - sm.efc[o];
     wtab[t] = exp(-0.1 * sqrt(ds * ds + dc * dc));
@@ -398,7 +426,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   tile.sync();
 
   float* fa = sm.feat;
-  for (int t = lane; t < ADB_NUM_FEATURES; t += TILE) fa[t] = 0.f;
+  _Pragma("unroll 1") for (int t = lane; t < ADB_NUM_FEATURES; t += TILE) fa[t] = 0.f;
   tile.sync();
   if (lane == 0) {
     fa[28] = (float)((double)Fv / (double)F);  // candidate.py:362
@@ -414,36 +442,29 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   if (lane < nI) {
     const float* r = dpi + lane * C;
     float tc = 0.f;
-    for (int c = 0; c < C; c++) tc = __fadd_rn(tc, r[c]);
+    _Pragma("unroll 1") for (int c = 0; c < C; c++) tc = __fadd_rn(tc, r[c]);
     float spi = twice(tc);
     float wsp = 0.f;
-    for (int o = 0; o < nobs; o++) wsp = __fadd_rn(wsp, __fmul_rn(spi, sm.oi[o]));
+    _Pragma("unroll 1") for (int o = 0; o < nobs; o++) wsp = __fadd_rn(wsp, __fmul_rn(spi, sm.oi[o]));
     sm.spi[lane] = spi;
     sm.wspi[lane] = wsp;
     const float* rm = dpm + lane * C;
-    double v1 = 0, w1 = 0, v2 = 0, w2 = 0;
-    bool any1 = false, any2 = false;
-    for (int s = 0; s < 2; s++)
-      for (int c = 0; c < C; c++) {
-        double wt = wtab_p[s * C + c];
-        float a = r[c], b = rm[c];
-        if (a > 0.f) { any1 = true; v1 = __dadd_rn(v1, __dmul_rn((double)a, wt)); w1 = __dadd_rn(w1, wt); }
-        if (b > 0.f) { any2 = true; v2 = __dadd_rn(v2, __dmul_rn((double)b, wt)); w2 = __dadd_rn(w2, wt); }
-      }
-    sm.H[lane] = (any1 && w1 > 0) ? v1 / w1 : 0.0;
-    sm.MZo[lane] = (any2 && w2 > 0) ? v2 / w2 : 0.0;
+    double hh, mm;
+    weighted_center_mean_pair(r, rm, wtab_p, C, hh, mm);
+    sm.H[lane] = hh;
+    sm.MZo[lane] = mm;
   }
   tile.sync();
   if (lane == 0) {
     int amax = 0;
-    for (int i = 1; i < nI; i++) if (sm.iso_int[i] > sm.iso_int[amax]) amax = i;
+    _Pragma("unroll 1") for (int i = 1; i < nI; i++) if (sm.iso_int[i] > sm.iso_int[amax]) amax = i;
     fa[4] = sm.wspi[0];
     fa[5] = sm.wspi[amax];
     float t6 = 0.f, t7 = 0.f;
-    for (int i = 0; i < nI; i++) { t6 = __fadd_rn(t6, sm.wspi[i]); t7 = __fadd_rn(t7, __fmul_rn(sm.wspi[i], sm.iso_int[i])); }
+    _Pragma("unroll 1") for (int i = 0; i < nI; i++) { t6 = __fadd_rn(t6, sm.wspi[i]); t7 = __fadd_rn(t7, __fmul_rn(sm.wspi[i], sm.iso_int[i])); }
     fa[6] = t6; fa[7] = t7;
     double wme = 0;
-    for (int i = 0; i < nI; i++) if (sm.MZo[i] > 0) {
+    _Pragma("unroll 1") for (int i = 0; i < nI; i++) if (sm.MZo[i] > 0) {
       double me = (sm.MZo[i] - (double)sm.iso_mz[i]) / (double)sm.iso_mz[i] * 1e6;
       wme = __dadd_rn(wme, __dmul_rn(me, (double)sm.iso_int[i]));
     }
@@ -453,14 +474,14 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     fa[11] = (float)sm.H[0];
     fa[12] = (float)sm.H[amax];
     double t13 = 0, t14 = 0, hbar = 0;
-    for (int i = 0; i < nI; i++) { t13 = __dadd_rn(t13, sm.H[i]); t14 = __dadd_rn(t14, __dmul_rn(sm.H[i], (double)sm.iso_int[i])); }
+    _Pragma("unroll 1") for (int i = 0; i < nI; i++) { t13 = __dadd_rn(t13, sm.H[i]); t14 = __dadd_rn(t14, __dmul_rn(sm.H[i], (double)sm.iso_int[i])); }
     fa[13] = (float)t13; fa[14] = (float)t14;
     hbar = t13 / (double)nI;
     float sx = 0.f, sy = 0.f;
-    for (int i = 0; i < nI; i++) { sx = __fadd_rn(sx, sm.iso_int[i]); sy = __fadd_rn(sy, sm.spi[i]); }
+    _Pragma("unroll 1") for (int i = 0; i < nI; i++) { sx = __fadd_rn(sx, sm.iso_int[i]); sy = __fadd_rn(sy, sm.spi[i]); }
     double xbar = (double)sx / (double)nI, ybar = (double)sy / (double)nI;
     double num = 0, sxx = 0, syy = 0, num2 = 0, shh = 0;
-    for (int i = 0; i < nI; i++) {
+    _Pragma("unroll 1") for (int i = 0; i < nI; i++) {
       double a = (double)sm.iso_int[i] - xbar, b = (double)sm.spi[i] - ybar, h = sm.H[i] - hbar;
       num = __dadd_rn(num, __dmul_rn(a, b)); sxx = __dadd_rn(sxx, __dmul_rn(a, a)); syy = __dadd_rn(syy, __dmul_rn(b, b));
       num2 = __dadd_rn(num2, __dmul_rn(a, h)); shh = __dadd_rn(shh, __dmul_rn(h, h));
@@ -471,7 +492,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
 
   // ================= features/fragment_features.py:198-427 =================
   int best_obs = 0;
-  for (int o = 1; o < nobs; o++) if (sm.oi[o] > sm.oi[best_obs]) best_obs = o;
+  _Pragma("unroll 1") for (int o = 1; o < nobs; o++) if (sm.oi[o] > sm.oi[best_obs]) best_obs = o;
   const bool quant_all = cfg.quant_all != 0;
   int64_t qw = (int64_t)cfg.quant_window;
   if ((C / 2) - 1 < qw) qw = (C / 2) - 1;
@@ -486,16 +507,16 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     float* b = bp + (long long)lane * C;
     const float* d = dfi + (long long)f * nobs * C;
     if (quant_all) {
-      for (int c = 0; c < C; c++) { float t = 0.f; for (int o = 0; o < nobs; o++) t = __fadd_rn(t, twice(d[o * C + c])); b[c] = t; }
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) { float t = 0.f; _Pragma("unroll 1") for (int o = 0; o < nobs; o++) t = __fadd_rn(t, twice(d[o * C + c])); b[c] = t; }
     } else {
-      for (int c = 0; c < C; c++) b[c] = twice(d[best_obs * C + c]);
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) b[c] = twice(d[best_obs * C + c]);
     }
     // center_envelope_1d, fragment_features.py:71-159
     if (C % 2 == 0) {
       int cr = C / 2, cl = cr - 1;
       if (cl >= 0) {
         float left = b[cl], right = b[cr];
-        for (int i = 1; i <= cl; i++) {
+        _Pragma("unroll 1") for (int i = 1; i <= cl; i++) {
           b[cl - i] = fminf(left, b[cl - i]);
           left = (float)((double)__fadd_rn(b[cl - i], b[cl - i + 1]) * 0.5);
           b[cr + i] = fminf(right, b[cr + i]);
@@ -506,7 +527,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
       int cc = C / 2;
       float left = (float)((double)__fadd_rn(b[cc - 1], b[cc]) * 0.5);
       float right = (float)((double)__fadd_rn(b[cc + 1], b[cc]) * 0.5);
-      for (int i = 1; i <= cc; i++) {
+      _Pragma("unroll 1") for (int i = 1; i <= cc; i++) {
         b[cc - i] = fminf(left, b[cc - i]);
         left = (float)((double)__fadd_rn(b[cc - i], b[cc - i + 1]) * 0.5);
         b[cc + i] = fminf(right, b[cc + i]);
@@ -515,72 +536,58 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     }
     // trapezoid area over the quant window, fragment_features.py:253-273
     double area = 0;
-    for (int t = 0; t + 1 < wn; t++) {
+    _Pragma("unroll 1") for (int t = 0; t + 1 < wn; t++) {
       float drt = __fsub_rn(__ldg(raw.rt_values + frame_start + (int64_t)(w0 + t + 1) * L), __ldg(raw.rt_values + frame_start + (int64_t)(w0 + t) * L));
       float sum2 = __fadd_rn(b[w0 + t + 1], b[w0 + t]);
       area = __dadd_rn(area, __dmul_rn((double)__fmul_rn(sum2, drt), 0.5));
     }
     sm.area_norm[lane] = __dmul_rn(area, (double)qw);
     float ofi = 0.f;
-    for (int u = 0; u < wn; u++) ofi = __fadd_rn(ofi, b[w0 + u]);
+    _Pragma("unroll 1") for (int u = 0; u < wn; u++) ofi = __fadd_rn(ofi, b[w0 + u]);
     sm.ofi[lane] = ofi;
 
-    // per-observation: summed intensity (cosine), weighted-centre height and m/z
-    float fn2 = 0.f, dot = 0.f;
-    double ofh[ADB_MAX_OBS], ofmz[ADB_MAX_OBS];
+    // per-observation: summed intensity (cosine score) and the observation mask.  A weighted-centre height is
+    // > 0 exactly when the (f, o) cell row has signal (all weights are positive), i.e. when its f32 sum is > 0.
+    float fn2 = 0.f, dot = 0.f, wsum = 0.f;
+    unsigned obs_mask = 0u;
     const float* dm = dfm + (long long)f * nobs * C;
-#pragma unroll
-    for (int o = 0; o < ADB_MAX_OBS; o++) {
-      ofh[o] = 0; ofmz[o] = 0;
-      if (o < nobs) {
-        const float* r = d + o * C;
-        const float* rm = dm + o * C;
-        float tc = 0.f;
-        for (int c = 0; c < C; c++) tc = __fadd_rn(tc, r[c]);
-        float v = twice(tc);
-        fn2 = __fadd_rn(fn2, __fmul_rn(v, v));
-        dot = __fadd_rn(dot, __fmul_rn(v, sm.sti[o]));
-        double v1 = 0, wt1 = 0, v2 = 0, wt2 = 0;
-        bool any1 = false, any2 = false;
-        const double* wt = wtab + (long long)o * 2 * C;
-        for (int s = 0; s < 2; s++)
-          for (int c = 0; c < C; c++) {
-            double wgt = wt[s * C + c];
-            float a = r[c], bb = rm[c];
-            if (a > 0.f) { any1 = true; v1 = __dadd_rn(v1, __dmul_rn((double)a, wgt)); wt1 = __dadd_rn(wt1, wgt); }
-            if (bb > 0.f) { any2 = true; v2 = __dadd_rn(v2, __dmul_rn((double)bb, wgt)); wt2 = __dadd_rn(wt2, wgt); }
-          }
-        ofh[o] = (any1 && wt1 > 0) ? v1 / wt1 : 0.0;
-        ofmz[o] = (any2 && wt2 > 0) ? v2 / wt2 : 0.0;
-      }
+    _Pragma("unroll 1") for (int o = 0; o < nobs; o++) {
+      const float* r = d + o * C;
+      float tc = 0.f;
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) tc = __fadd_rn(tc, r[c]);
+      float v = twice(tc);
+      fn2 = __fadd_rn(fn2, __fmul_rn(v, v));
+      dot = __fadd_rn(dot, __fmul_rn(v, sm.sti[o]));
+      const bool mm = tc > 0.f;
+      if (mm && o < 32) obs_mask |= 1u << o;
+      wsum = __fadd_rn(wsum, mm ? sm.oi[o] : 0.0f);  // fragment_features.py:318-326
     }
+    anyh = obs_mask != 0u;
     {  // cosine_similarity_a1, features_utils.py:40-47
       float tn2 = 0.f;
-      for (int o = 0; o < nobs; o++) tn2 = __fadd_rn(tn2, __fmul_rn(sm.sti[o], sm.sti[o]));
+      _Pragma("unroll 1") for (int o = 0; o < nobs; o++) tn2 = __fadd_rn(tn2, __fmul_rn(sm.sti[o], sm.sti[o]));
       double div = (double)__fmul_rn(sqrtf(fn2), sqrtf(tn2)) + 0.0001;
       sm.cosv[lane] = (float)((double)dot / div);
     }
-    // fragment_features.py:312-336 observation-weighted means
-    float wsum = 0.f;
-#pragma unroll
-    for (int o = 0; o < ADB_MAX_OBS; o++)
-      if (o < nobs) { bool mm = ofh[o] > 0; anyh |= mm; wsum = __fadd_rn(wsum, mm ? sm.oi[o] : 0.0f); }
+    // fragment_features.py:312-336 observation-weighted means of the weighted-centre height and m/z
     double wtot = 0;
     int cnt = 0;
-#pragma unroll
-    for (int o = 0; o < ADB_MAX_OBS; o++)
-      if (o < nobs) {
-        double wv = (double)((ofh[o] > 0) ? sm.oi[o] : 0.0f) / ((double)wsum + 1e-20);
-        if (wv > 0) { wtot = __dadd_rn(wtot, wv); cnt++; }
-      }
+    _Pragma("unroll 1") for (int o = 0; o < nobs; o++) {
+      double wv = (double)(((obs_mask >> o) & 1u) ? sm.oi[o] : 0.0f) / ((double)wsum + 1e-20);
+      if (wv > 0) { wtot = __dadd_rn(wtot, wv); cnt++; }
+    }
     double a = 0, bsum = 0;
     if (cnt > 0) {
-#pragma unroll
-      for (int o = 0; o < ADB_MAX_OBS; o++)
-        if (o < nobs) {
-          double wv = (double)((ofh[o] > 0) ? sm.oi[o] : 0.0f) / ((double)wsum + 1e-20);
-          if (wv > 0) { double lw = wv / wtot; a = __dadd_rn(a, __dmul_rn(ofmz[o], lw)); bsum = __dadd_rn(bsum, __dmul_rn(ofh[o], lw)); }
+      _Pragma("unroll 1") for (int o = 0; o < nobs; o++) {
+        double wv = (double)(((obs_mask >> o) & 1u) ? sm.oi[o] : 0.0f) / ((double)wsum + 1e-20);
+        if (wv > 0) {
+          double h_o, mz_o;
+          weighted_center_mean_pair(d + o * C, dm + o * C, wtab + (long long)o * 2 * C, C, h_o, mz_o);
+          double lw = wv / wtot;
+          a = __dadd_rn(a, __dmul_rn(mz_o, lw));
+          bsum = __dadd_rn(bsum, __dmul_rn(h_o, lw));
         }
+      }
     }
     sm.ofh_mean[lane] = bsum;
     sm.ci[lane] = a;  // observed_fragment_mz_mean (slot reused below for centre intensities)
@@ -589,7 +596,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     // np.argsort(fragments.intensity)[::-1]
     float v = sm.fint[lane];
     int rank_asc = 0;
-    for (int q = 0; q < Fv; q++) rank_asc += (sm.fint[q] < v) || (sm.fint[q] == v && q < lane);
+    _Pragma("unroll 1") for (int q = 0; q < Fv; q++) rank_asc += (sm.fint[q] < v) || (sm.fint[q] == v && q < lane);
     sm.sorted_idx[Fv - 1 - rank_asc] = lane;
   }
   const unsigned anyh_b = tile.ballot(anyh);
@@ -612,20 +619,20 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   tile.sync();
   if (lane == 0) {
     double sum_ofh = 0;
-    for (int w = 0; w < Fv; w++) sum_ofh = __dadd_rn(sum_ofh, sm.ofh_mean[w]);
+    _Pragma("unroll 1") for (int w = 0; w < Fv; w++) sum_ofh = __dadd_rn(sum_ofh, sm.ofh_mean[w]);
     if (anyh_b != 0u) fa[18] = (float)corrcoef01(sm.area_norm, sm.fin, Fv);
     if (sum_ofh > 0.0) fa[19] = (float)corrcoef01(sm.ofh_mean, sm.fin, Fv);
     int n20 = 0, n21 = 0;
     float s22 = 0.f, s23 = 0.f, cacc = 0.f;
-    for (int w = 0; w < Fv; w++) if (sm.ofi[w] > 0.f) { n20++; s22 = __fadd_rn(s22, sm.fin[w]); cacc = __fadd_rn(cacc, sm.cosv[w]); }
-    for (int w = 0; w < Fv; w++) if (sm.ofh_mean[w] > 0.0) { n21++; s23 = __fadd_rn(s23, sm.fin[w]); }
+    _Pragma("unroll 1") for (int w = 0; w < Fv; w++) if (sm.ofi[w] > 0.f) { n20++; s22 = __fadd_rn(s22, sm.fin[w]); cacc = __fadd_rn(cacc, sm.cosv[w]); }
+    _Pragma("unroll 1") for (int w = 0; w < Fv; w++) if (sm.ofh_mean[w] > 0.0) { n21++; s23 = __fadd_rn(s23, sm.fin[w]); }
     fa[20] = (float)((double)n20 / (double)Fv);
     fa[21] = (float)((double)n21 / (double)Fv);
     fa[22] = s22; fa[23] = s23;
     if (n20 > 0) fa[24] = (float)((double)cacc / (double)n20);
     float sb = 0.f, sy = 0.f;
     int nb = 0, ny = 0, min_y = 255, max_b = 0;
-    for (int w = 0; w < Fv; w++) {
+    _Pragma("unroll 1") for (int w = 0; w < Fv; w++) {
       int ty = sm.type[sm.fmap[w]], po = sm.position[sm.fmap[w]];
       if (ty == 98) { sb = __fadd_rn(sb, sm.ofi[w]); nb++; max_b = max(max_b, po); }
       if (ty == 121) { sy = __fadd_rn(sy, sm.ofi[w]); ny++; min_y = min(min_y, po); }
@@ -635,14 +642,14 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     fa[27] = __fsub_rn(fa[25], fa[26]);
     int n3 = min(Fv, 3);
     double t41 = 0, t42 = 0;
-    for (int r = 0; r < n3; r++) t41 = __dadd_rn(t41, sm.mass_error[sm.sorted_idx[r]]);
-    for (int w = 0; w < Fv; w++) t42 = __dadd_rn(t42, sm.mass_error[w]);
+    _Pragma("unroll 1") for (int r = 0; r < n3; r++) t41 = __dadd_rn(t41, sm.mass_error[sm.sorted_idx[r]]);
+    _Pragma("unroll 1") for (int w = 0; w < Fv; w++) t42 = __dadd_rn(t42, sm.mass_error[w]);
     fa[41] = (float)(t41 / (double)n3);
     fa[42] = (float)(t42 / (double)Fv);
     if (nb > 0 && ny > 0) {
       int n_ov = 0;
       double sa = 0, se = 0;
-      for (int w = 0; w < Fv; w++) {
+      _Pragma("unroll 1") for (int w = 0; w < Fv; w++) {
         int ty = sm.type[sm.fmap[w]], po = sm.position[sm.fmap[w]];
         bool ov = (ty == 121 && po < max_b) || (ty == 98 && po > min_y);
         if (ov) { n_ov++; sa = __dadd_rn(sa, sm.area_norm[w]); se = __dadd_rn(se, sm.mass_error[w]); }
@@ -661,10 +668,9 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     if (!quant_all && o == best_obs) return bp[(long long)w * C + c];
     return twice(dfi[((long long)fidx * nobs + o) * C + c]);
   };
-  auto isl = [&](int w, int fidx, int c) -> float {  // fragments_frame_profile.sum(axis=1)
-    float t = 0.f;
-    for (int o = 0; o < nobs; o++) t = __fadd_rn(t, ffp(w, fidx, o, c));
-    return t;
+  // fragments_frame_profile.sum(axis=1)
+  auto isl = [&](int w, int fidx, int c) -> float {
+    return frame_profile_obs_sum(dfi + (long long)fidx * nobs * C, bp + (long long)w * C, nobs, C, c, quant_all ? -1 : best_obs);
   };
   if (cfg.experimental_xic) {
     int a0 = center - 1, a1 = center + 2;  // scoring_utils.py:100-110 python slice semantics
@@ -673,18 +679,18 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     const int wnn = max(a1 - a0, 0);
     if (act) {
       float t = 0.f;
-      for (int c = a0; c < a1; c++) t = __fadd_rn(t, isl(lane, f, c));
+      _Pragma("unroll 1") for (int c = a0; c < a1; c++) t = __fadd_rn(t, isl(lane, f, c));
       double cint = (double)t / (double)wnn;
       float* nr = nrm + (long long)lane * C;
-      for (int c = 0; c < C; c++) nr[c] = (cint > 0) ? (float)((double)isl(lane, f, c) / cint) : 0.f;
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) nr[c] = (cint > 0) ? (float)((double)isl(lane, f, c) / cint) : 0.f;
     }
     tile.sync();
-    for (int c = lane; c < C; c += TILE) {  // median over fragments (scoring_utils.py:127-152)
+    _Pragma("unroll 1") for (int c = lane; c < C; c += TILE) {  // median over fragments (scoring_utils.py:127-152)
       float vlo = 0.f, vhi = 0.f;
-      for (int w = 0; w < Fv; w++) {
+      _Pragma("unroll 1") for (int w = 0; w < Fv; w++) {
         float v = nrm[(long long)w * C + c];
         int rk = 0;
-        for (int u = 0; u < Fv; u++) { float vu = nrm[(long long)u * C + c]; rk += (vu < v) || (vu == v && u < w); }
+        _Pragma("unroll 1") for (int u = 0; u < Fv; u++) { float vu = nrm[(long long)u * C + c]; rk += (vu < v) || (vu == v && u < w); }
         if (rk == (Fv - 1) / 2) vlo = v;
         if (rk == Fv / 2) vhi = v;
       }
@@ -693,18 +699,18 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     tile.sync();
     // correlation_coefficient(median_profile, intensity_slice), scoring_utils.py:20-76
     float sx = 0.f;
-    for (int c = 0; c < C; c++) sx = __fadd_rn(sx, med[c]);
+    _Pragma("unroll 1") for (int c = 0; c < C; c++) sx = __fadd_rn(sx, med[c]);
     const double mxv = (double)sx / (double)C;
     double varx = 0;
-    for (int c = 0; c < C; c++) { double dd = (double)med[c] - mxv; varx = __dadd_rn(varx, __dmul_rn(dd, dd)); }
+    _Pragma("unroll 1") for (int c = 0; c < C; c++) { double dd = (double)med[c] - mxv; varx = __dadd_rn(varx, __dmul_rn(dd, dd)); }
     varx /= (double)C;
     if (act) {
       float sy = 0.f;
-      for (int c = 0; c < C; c++) sy = __fadd_rn(sy, isl(lane, f, c));
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) sy = __fadd_rn(sy, isl(lane, f, c));
       float myv = (float)((double)sy / (double)C);
       double cov = 0;
       float vy32 = 0.f;
-      for (int c = 0; c < C; c++) {
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) {
         float ym = __fsub_rn(isl(lane, f, c), myv);
         cov = __dadd_rn(cov, __dmul_rn((double)med[c] - mxv, (double)ym));
         vy32 = __fadd_rn(vy32, __fmul_rn(ym, ym));
@@ -717,30 +723,30 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     if (lane == 0) {
       int n3 = min(Fv, 3);
       float t = 0.f;
-      for (int r = 0; r < n3; r++) t = __fadd_rn(t, sm.corr_list[sm.sorted_idx[r]]);
+      _Pragma("unroll 1") for (int r = 0; r < n3; r++) t = __fadd_rn(t, sm.corr_list[sm.sorted_idx[r]]);
       fa[32] = (float)((double)t / (double)n3);
     }
   } else {
     // legacy: observation-weighted F x F correlation matrix (scoring/utils.py:513-571), float32
-    for (int t = lane; t < Fv * Fv; t += TILE) red[t] = 0.f;
-    for (int o = 0; o < nobs; o++) {
+    _Pragma("unroll 1") for (int t = lane; t < Fv * Fv; t += TILE) red[t] = 0.f;
+    _Pragma("unroll 1") for (int o = 0; o < nobs; o++) {
       tile.sync();
       if (act) {
         float s = 0.f;
-        for (int c = 0; c < C; c++) s = __fadd_rn(s, ffp(lane, f, o, c));
+        _Pragma("unroll 1") for (int c = 0; c < C; c++) s = __fadd_rn(s, ffp(lane, f, o, c));
         float mean = __fdiv_rn(s, (float)C);
         float ss = 0.f;
         float* cen = nrm + (long long)lane * C;
-        for (int c = 0; c < C; c++) { float cv = __fsub_rn(ffp(lane, f, o, c), mean); cen[c] = cv; ss = __fadd_rn(ss, __fmul_rn(cv, cv)); }
+        _Pragma("unroll 1") for (int c = 0; c < C; c++) { float cv = __fsub_rn(ffp(lane, f, o, c), mean); cen[c] = cv; ss = __fadd_rn(ss, __fmul_rn(cv, cv)); }
         sm.rfw[lane] = sqrtf(__fdiv_rn(ss, (float)C));
       }
       tile.sync();
-      for (int t = lane; t < Fv * Fv; t += TILE) {
+      _Pragma("unroll 1") for (int t = lane; t < Fv * Fv; t += TILE) {
         int a = t / Fv, b = t % Fv;
         const float* ca = nrm + (long long)a * C;
         const float* cb = nrm + (long long)b * C;
         float dot = 0.f;
-        for (int c = 0; c < C; c++) dot = __fadd_rn(dot, __fmul_rn(ca[c], cb[c]));
+        _Pragma("unroll 1") for (int c = 0; c < C; c++) dot = __fadd_rn(dot, __fmul_rn(ca[c], cb[c]));
         float cov = __fdiv_rn(dot, (float)C);
         float smx = __fmul_rn(sm.rfw[a], sm.rfw[b]);
         float corr = (float)((double)cov / ((double)smx + 1e-12));
@@ -750,42 +756,42 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     tile.sync();
     if (act) {
       float t = 0.f;
-      for (int g = 0; g < Fv; g++) t = __fadd_rn(t, __fmul_rn(red[lane * Fv + g], sm.fint[g]));
+      _Pragma("unroll 1") for (int g = 0; g < Fv; g++) t = __fadd_rn(t, __fmul_rn(red[lane * Fv + g], sm.fint[g]));
       sm.corr_list[lane] = t;
     }
     tile.sync();
     if (lane == 0) {
       int n3 = min(Fv, 3);
       float t = 0.f;
-      for (int a = 0; a < n3; a++) for (int b = 0; b < n3; b++) t = __fadd_rn(t, red[sm.sorted_idx[a] * Fv + sm.sorted_idx[b]]);
+      _Pragma("unroll 1") for (int a = 0; a < n3; a++) _Pragma("unroll 1") for (int b = 0; b < n3; b++) t = __fadd_rn(t, red[sm.sorted_idx[a] * Fv + sm.sorted_idx[b]]);
       fa[32] = (float)((double)t / (double)(n3 * n3));
     }
   }
   // template correlation, cycle fwhm, frame peak — lane w <-> fragment w
-  for (int o = 0; o < nobs; o++) {
+  _Pragma("unroll 1") for (int o = 0; o < nobs; o++) {
     // y statistics of the template frame profile (all lanes, sequential)
     const float* y = tfp + o * C;
     float ys = 0.f;
-    for (int c = 0; c < C; c++) ys = __fadd_rn(ys, y[c]);
+    _Pragma("unroll 1") for (int c = 0; c < C; c++) ys = __fadd_rn(ys, y[c]);
     const float ym = __fdiv_rn(ys, (float)C);
     float yss = 0.f;
-    for (int c = 0; c < C; c++) { float yc = __fsub_rn(y[c], ym); yss = __fadd_rn(yss, __fmul_rn(yc, yc)); }
+    _Pragma("unroll 1") for (int c = 0; c < C; c++) { float yc = __fsub_rn(y[c], ym); yss = __fadd_rn(yss, __fmul_rn(yc, yc)); }
     const float ystd = sqrtf(__fdiv_rn(yss, (float)C));
     if (act) {
       float xs = 0.f, mxv = 0.f;
       int am = 0;
-      for (int c = 0; c < C; c++) {
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) {
         float x = ffp(lane, f, o, c);
         xs = __fadd_rn(xs, x);
         if (c == 0 || x > mxv) { am = c; mxv = x; }
       }
       float xm = __fdiv_rn(xs, (float)C);
       float xss = 0.f;
-      for (int c = 0; c < C; c++) { float xc = __fsub_rn(ffp(lane, f, o, c), xm); xss = __fadd_rn(xss, __fmul_rn(xc, xc)); }
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) { float xc = __fsub_rn(ffp(lane, f, o, c), xm); xss = __fadd_rn(xss, __fmul_rn(xc, xc)); }
       float dot = 0.f;
       int na = 0;
       double half = (double)mxv / 2;
-      for (int c = 0; c < C; c++) {
+      _Pragma("unroll 1") for (int c = 0; c < C; c++) {
         float x = ffp(lane, f, o, c);
         dot = __fadd_rn(dot, __fmul_rn(__fsub_rn(x, xm), __fsub_rn(y[c], ym)));
         na += (double)x > half;
@@ -804,9 +810,9 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     tile.sync();
     if (lane == 0) {  // median frame peak of this observation (profile_features.py:193-204)
       double vlo = 0, vhi = 0;
-      for (int w = 0; w < Fv; w++) {
+      _Pragma("unroll 1") for (int w = 0; w < Fv; w++) {
         int v = sm.frame_peak[w], rk = 0;
-        for (int u = 0; u < Fv; u++) rk += (sm.frame_peak[u] < v) || (sm.frame_peak[u] == v && u < w);
+        _Pragma("unroll 1") for (int u = 0; u < Fv; u++) rk += (sm.frame_peak[u] < v) || (sm.frame_peak[u] == v && u < w);
         if (rk == (Fv - 1) / 2) vlo = (double)v;
         if (rk == Fv / 2) vhi = (double)v;
       }
@@ -819,7 +825,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   }
   if (lane == 0) {
     float t31 = 0.f, t33 = 0.f, t38 = 0.f;
-    for (int w = 0; w < Fv; w++) {
+    _Pragma("unroll 1") for (int w = 0; w < Fv; w++) {
       t31 = __fadd_rn(t31, sm.corr_list[w]);
       t33 = __fadd_rn(t33, __fmul_rn(sm.cosv[w], sm.fint[w]));
       t38 = __fadd_rn(t38, __fmul_rn(sm.rfw[w], sm.fint[w]));
@@ -831,7 +837,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     // profile_features.py:94-113 (the type mask indexes the sorted-index array by position)
     int nb = 0, ny = 0;
     float sb = 0.f, sy = 0.f;
-    for (int r = 0; r < Fv; r++) {
+    _Pragma("unroll 1") for (int r = 0; r < Fv; r++) {
       int ty = sm.type[sm.fmap[r]];
       if (ty == 98) { if (nb < 3) sb = __fadd_rn(sb, sm.corr_list[sm.sorted_idx[r]]); nb++; }
       if (ty == 121) { if (ny < 3) sy = __fadd_rn(sy, sm.corr_list[sm.sorted_idx[r]]); ny++; }
@@ -842,7 +848,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   tile.sync();
   // ---- candidate.py:475-481 ---------------------------------------------------------------------
   if (act && cfg.collect_fragments && lane < K) P.out.fragment_correlation[obase + lane] = sm.corr_list[lane];
-  for (int t = lane; t < ADB_NUM_FEATURES; t += TILE) P.out.features[(size_t)ci * ADB_NUM_FEATURES + t] = fa[t];
+  _Pragma("unroll 1") for (int t = lane; t < ADB_NUM_FEATURES; t += TILE) P.out.features[(size_t)ci * ADB_NUM_FEATURES + t] = fa[t];
   if (lane == 0) P.out.valid[ci] = 1;
 }
 
