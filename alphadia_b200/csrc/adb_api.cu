@@ -51,13 +51,14 @@ struct DeviceBuffer {  // grow-only cached device allocation
 };
 
 template <typename T>
-int upload(const T* host, int64_t n, T** dev, std::vector<void*>& allocs, int64_t& total, cudaStream_t stream) {
-  size_t bytes = sizeof(T) * (size_t)(n > 0 ? n : 1);
+int upload(const T* host, int64_t n, T** dev, std::vector<void*>& allocs, int64_t& total, cudaStream_t stream, int64_t pad = 0) {
+  size_t bytes = sizeof(T) * (size_t)((n > 0 ? n : 1) + pad);
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, bytes);
   if (e != cudaSuccess) return fail(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
   allocs.push_back(p);
   total += (int64_t)bytes;
+  if (pad > 0) cudaMemsetAsync((char*)p + sizeof(T) * (size_t)(n > 0 ? n : 0), 0, sizeof(T) * (size_t)pad, stream);
   if (n > 0) {
     e = cudaMemcpyAsync(p, host, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return fail(std::string("cudaMemcpy H2D failed: ") + cudaGetErrorString(e));
@@ -206,19 +207,23 @@ __global__ void mz_range_kernel(DevRaw raw, float* out /* [2] = {min, max}, pre-
   atomicMax((unsigned int*)(out + 1), __float_as_uint(fmaxf(hi, 0.f)));
 }
 
-__global__ void bucket_index_kernel(DevRaw raw, int32_t* table) {
+__global__ void bucket_index_kernel(DevRaw raw, uint32_t* table) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= raw.n_spectra * ADB_N_BUCKETS) return;
-  int64_t scan = t / ADB_N_BUCKETS;
-  int b = (int)(t % ADB_N_BUCKETS);
+  if (t >= raw.n_spectra * ADB_BUCKET_STRIDE) return;
+  int64_t scan = t / ADB_BUCKET_STRIDE;
+  int b = (int)(t % ADB_BUCKET_STRIDE);
   int64_t s = raw.peak_start[scan], e = raw.peak_stop[scan];
-  float edge = adb_bucket_edge(raw, b);
   int64_t lo = s, hi = e;
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if (raw.mz[mid] < edge) lo = mid + 1; else hi = mid;
+  if (b == 0) { hi = s; }
+  else if (b == ADB_N_BUCKETS) { lo = e; }
+  else {
+    float edge = adb_bucket_edge(raw, b);
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (raw.mz[mid] < edge) lo = mid + 1; else hi = mid;
+    }
   }
-  table[t] = (int32_t)(lo - s);
+  table[t] = (uint32_t)lo;
 }
 
 __global__ void order_key_kernel(DevRaw raw, DevLib lib, uint64_t* keys, int32_t* vals) {
@@ -431,6 +436,7 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
   if (!d || !out) return fail("null argument");
   if (d->cycle_len < 1 || d->n_spectra < 1) return fail("empty raw file");
   if (d->n_mobility < 1) return fail("mobility_values must not be empty");
+  if (d->n_peaks >= 4294967000LL) return fail("raw files with more than 2^32 peaks are not supported");
   if (set_device(device)) return 1;
   adb_rawfile* r = new adb_rawfile();
   r->device = device;
@@ -444,8 +450,8 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
       upload(d->mobility_values, d->n_mobility, &mob, r->allocs, r->bytes, r->stream) ||
       upload(d->peak_start_idx, d->n_spectra, &ps, r->allocs, r->bytes, r->stream) ||
       upload(d->peak_stop_idx, d->n_spectra, &pe, r->allocs, r->bytes, r->stream) ||
-      upload(d->mz_values, d->n_peaks, &mz, r->allocs, r->bytes, r->stream) ||
-      upload(d->intensity_values, d->n_peaks, &it, r->allocs, r->bytes, r->stream)) {
+      upload(d->mz_values, d->n_peaks, &mz, r->allocs, r->bytes, r->stream, ADB_MZ_PAD) ||
+      upload(d->intensity_values, d->n_peaks, &it, r->allocs, r->bytes, r->stream, ADB_MZ_PAD)) {
     adb_rawfile_destroy(r);
     return 1;
   }
@@ -474,14 +480,14 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
     memcpy(&init[0], &inf_bits, 4);
     memcpy(&init[1], &zero_bits, 4);
     float* d_rng = nullptr;
-    int32_t* d_tab = nullptr;
+    uint32_t* d_tab = nullptr;
     if (upload(init, 2, &d_rng, r->allocs, r->bytes, r->stream)) { adb_rawfile_destroy(r); return 1; }
-    size_t tab_n = (size_t)d->n_spectra * ADB_N_BUCKETS;
+    size_t tab_n = (size_t)d->n_spectra * ADB_BUCKET_STRIDE;
     void* tp = nullptr;
-    if (cudaMalloc(&tp, tab_n * sizeof(int32_t)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc bucket index failed"); }
+    if (cudaMalloc(&tp, tab_n * sizeof(uint32_t)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc bucket index failed"); }
     r->allocs.push_back(tp);
-    r->bytes += (int64_t)(tab_n * sizeof(int32_t));
-    d_tab = (int32_t*)tp;
+    r->bytes += (int64_t)(tab_n * sizeof(uint32_t));
+    d_tab = (uint32_t*)tp;
     mz_range_kernel<<<(unsigned)((d->n_spectra + 255) / 256), 256, 0, r->stream>>>(v, d_rng);
     float rng[2] = {0.f, 0.f};
     cudaMemcpyAsync(rng, d_rng, sizeof(rng), cudaMemcpyDeviceToHost, r->stream);
@@ -491,7 +497,7 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
     v.bucket_width = (rng[1] - rng[0]) / (float)ADB_N_BUCKETS * 1.0001f;
     if (!(v.bucket_width > 0.f)) v.bucket_width = 1.f;
     v.bucket_inv_width = 1.0f / v.bucket_width;
-    v.bucket_idx = d_tab;
+    v.bucket_abs = d_tab;
     bucket_index_kernel<<<(unsigned)((tab_n + 255) / 256), 256, 0, r->stream>>>(v, d_tab);
     r->launches += 2;
   }

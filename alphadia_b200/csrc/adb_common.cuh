@@ -11,6 +11,8 @@
 #define ADB_MAX_KERNEL_W 64
 #define ADB_ISOTOPE_DIFF 1.0033548350700006
 #define ADB_N_BUCKETS 64         // m/z buckets per spectrum in the derived search index
+#define ADB_BUCKET_STRIDE (ADB_N_BUCKETS + 1)
+#define ADB_MZ_PAD 16            // floats of padding behind mz/intensity so vector tail reads stay in bounds
 
 // status bits reported by kernels through a device word (-> adb_last_error on the host)
 #define ADB_STATUS_TOO_MANY_OBS 1u
@@ -39,8 +41,10 @@ struct DevRaw {
   int32_t n_ms1_pos;                // cycle positions whose window overlaps [-1,-1]
   int32_t ms1_pos[ADB_MAX_MS1_POS];
   // derived m/z bucket index (built once per file on the device, sized to stay L2-resident):
-  // bucket_idx[scan][b] = first peak (relative to peak_start[scan]) with mz >= bucket_lo + b * bucket_width
-  const int32_t* bucket_idx;        // [n_spectra][ADB_N_BUCKETS]
+  // bucket_abs[scan][b], b in [1, 63] = ABSOLUTE index of the first peak of the spectrum with
+  // mz >= bucket_lo + b * bucket_width; [scan][0] = peak_start[scan], [scan][64] = peak_stop[scan].
+  // One row therefore also replaces the peak_start/peak_stop reads of the reference.
+  const uint32_t* bucket_abs;       // [n_spectra][ADB_BUCKET_STRIDE]
   float bucket_lo, bucket_width, bucket_inv_width;
 };
 
@@ -148,44 +152,51 @@ __device__ __forceinline__ float adb_bucket_edge(const DevRaw& raw, int b) {
   return __fmaf_rn((float)b, raw.bucket_width, raw.bucket_lo);
 }
 
-// One spectrum as a (pointer, length) view with 32-bit offsets.
-struct AdbSpectrum {
-  const float* mz;
-  const float* intensity;
-  int n;
-};
-
-__device__ __forceinline__ AdbSpectrum adb_spectrum(const DevRaw& raw, int64_t scan) {
-  int64_t start = __ldg(raw.peak_start + scan), stop = __ldg(raw.peak_stop + scan);
-  AdbSpectrum s;
-  s.mz = raw.mz + start;
-  s.intensity = raw.intensity + start;
-  s.n = (int)(stop - start);
-  return s;
-}
-
-// Search range [lo, hi] that contains the lower bound of v in one spectrum: the bucket index narrows it to
-// ~n/64 peaks with one 8-byte read of an L2-resident table.
-__device__ __forceinline__ void adb_bucket_range(const DevRaw& raw, int64_t scan, const AdbSpectrum& s, float v, int& lo, int& hi) {
+__device__ __forceinline__ int adb_bucket_of(const DevRaw& raw, float v) {
   int b = (int)((v - raw.bucket_lo) * raw.bucket_inv_width);
   b = max(0, min(b, ADB_N_BUCKETS - 1));
   while (b > 0 && adb_bucket_edge(raw, b) > v) b--;
   while (b < ADB_N_BUCKETS - 1 && adb_bucket_edge(raw, b + 1) <= v) b++;
-  const int32_t* row = raw.bucket_idx + scan * ADB_N_BUCKETS;
-  lo = (b == 0) ? 0 : __ldg(row + b);
-  hi = (b == ADB_N_BUCKETS - 1) ? s.n : __ldg(row + b + 1);
+  return b;
 }
 
-// lower bound of v inside one spectrum (first index with mz >= v).  Same result as
-// np.searchsorted(mz[start:stop], v, "left") / _search_sorted_reference_left (alpharaw_jit.py:53-75).
-__device__ __forceinline__ int adb_spectrum_lower_bound(const DevRaw& raw, int64_t scan, const AdbSpectrum& s, float v) {
-  int lo, hi;
-  adb_bucket_range(raw, scan, s, v, lo, hi);
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(s.mz + mid) < v) lo = mid + 1; else hi = mid;
+// Range [lo, hi] (absolute peak indices) that contains the lower bound of v in spectrum `scan`, plus the
+// spectrum's end: three independent 4-byte reads of one L2-resident table row.
+__device__ __forceinline__ void adb_bucket_range(const DevRaw& raw, int64_t scan, float v, uint32_t& lo, uint32_t& hi, uint32_t& stop) {
+  const int b = adb_bucket_of(raw, v);
+  const uint32_t* row = raw.bucket_abs + scan * ADB_BUCKET_STRIDE;
+  lo = __ldg(row + b);
+  hi = __ldg(row + b + 1);
+  stop = __ldg(row + ADB_N_BUCKETS);
+}
+
+// Finish a lower-bound search once the range is <= 8 peaks: three independent aligned 16-byte reads cover it;
+// the answer is lo + #(elements of [lo, hi) below v) because the spectrum is sorted.
+__device__ __forceinline__ uint32_t adb_finish_lower_bound(const float* __restrict__ mz, uint32_t lo, uint32_t hi, float v) {
+  const uint32_t A = lo & ~3u;
+  const float4 x0 = __ldg(reinterpret_cast<const float4*>(mz + A));
+  const float4 x1 = __ldg(reinterpret_cast<const float4*>(mz + A + 4));
+  const float4 x2 = __ldg(reinterpret_cast<const float4*>(mz + A + 8));
+  const float e[12] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w};
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    uint32_t idx = A + j;
+    cnt += (idx >= lo && idx < hi && e[j] < v) ? 1u : 0u;
   }
-  return lo;
+  return lo + cnt;
+}
+
+// lower bound of v inside spectrum `scan` as an absolute peak index; same result as
+// np.searchsorted(mz[start:stop], v, "left") + start / _search_sorted_reference_left (alpharaw_jit.py:53-75).
+__device__ __forceinline__ uint32_t adb_spectrum_lower_bound(const DevRaw& raw, int64_t scan, float v, uint32_t& stop) {
+  uint32_t lo, hi;
+  adb_bucket_range(raw, scan, v, lo, hi, stop);
+  while (hi - lo > 8u) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(raw.mz + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return adb_finish_lower_bound(raw.mz, lo, hi, v);
 }
 
 __device__ __forceinline__ int64_t adb_wrap0(int64_t v, int64_t limit) {

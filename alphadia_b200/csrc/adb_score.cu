@@ -73,14 +73,14 @@ struct ScoreParams {
 // prev_hi: upper bound of the previous (lower m/z) window when it overlaps this one, else -1.
 __device__ __forceinline__ void extract_cell(const DevRaw& raw, int64_t scan, float lo, float hi, float prev_hi,
                                              float& acc_i, float& acc_m) {
-  const AdbSpectrum sp = adb_spectrum(raw, scan);
-  int idx = adb_spectrum_lower_bound(raw, scan, sp, lo);
+  uint32_t stop;
+  uint32_t idx = adb_spectrum_lower_bound(raw, scan, lo, stop);
   if (prev_hi >= lo)  // the search cursor only moves forward: peaks taken by the previous window are gone
-    while (idx < sp.n && __ldg(sp.mz + idx) <= prev_hi) idx++;
-  while (idx < sp.n) {
-    float nm = __ldg(sp.mz + idx);
+    while (idx < stop && __ldg(raw.mz + idx) <= prev_hi) idx++;
+  while (idx < stop) {
+    float nm = __ldg(raw.mz + idx);
     if (!(nm <= hi)) break;
-    float ni = __ldg(sp.intensity + idx);
+    float ni = __ldg(raw.intensity + idx);
     ni = __fmul_rn(ni, ((double)ni > 1e-26) ? 1.0f : 0.0f);
     float num32 = __fadd_rn(__fmul_rn(acc_m, acc_i), __fmul_rn(ni, nm));
     float den32 = __fadd_rn(acc_i, ni);

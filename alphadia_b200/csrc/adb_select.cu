@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(SEL_THREADS) adb_select_kernel(const __grid_co
           const SlotMeta& sl = slots[s];
           long long local = t - item_prefix[s];
           const int nL = sl.nF + sl.nI;
-          int k = (int)(local % nL), c = (int)(local / nL);
+          const int li = (int)local;
+          int k = li % nL, c = li / nL;
           lo[q] = sl.lo[k]; hi[q] = sl.hi[k];
           prev_hi[q] = (k > 0 && k != sl.nF) ? sl.hi[k - 1] : -1.0f;
           const bool ms1 = k >= sl.nF;
@@ -377,43 +378,41 @@ __global__ void __launch_bounds__(SEL_THREADS) adb_select_kernel(const __grid_co
         }
       }
       for (int o = 0; o < max_o; o++) {
-        AdbSpectrum sp[SEL_ILP];
-        int l[SEL_ILP], h[SEL_ILP];
+        uint32_t l[SEL_ILP], h[SEL_ILP], stop[SEL_ILP];
 #pragma unroll
         for (int q = 0; q < SEL_ILP; q++) {
-          sp[q].n = 0; sp[q].mz = raw.mz; sp[q].intensity = raw.intensity; l[q] = 0; h[q] = 0;
-          if (o < n_o[q]) {
-            int64_t scan = (int64_t)posv[q][o] + cyc_base[q];
-            sp[q] = adb_spectrum(raw, scan);
-            adb_bucket_range(raw, scan, sp[q], lo[q], l[q], h[q]);
-          }
+          l[q] = 0; h[q] = 0; stop[q] = 0;
+          if (o < n_o[q]) adb_bucket_range(raw, (int64_t)posv[q][o] + cyc_base[q], lo[q], l[q], h[q], stop[q]);
         }
         bool any = true;
         while (any) {  // interleaved binary searches: the SEL_ILP loads of a round are independent
           any = false;
           float v[SEL_ILP];
-          int mid[SEL_ILP];
+          uint32_t mid[SEL_ILP];
 #pragma unroll
           for (int q = 0; q < SEL_ILP; q++) {
             mid[q] = (l[q] + h[q]) >> 1;
-            v[q] = (l[q] < h[q]) ? __ldg(sp[q].mz + mid[q]) : 0.f;
+            v[q] = (h[q] - l[q] > 8u) ? __ldg(raw.mz + mid[q]) : 0.f;
           }
 #pragma unroll
           for (int q = 0; q < SEL_ILP; q++)
-            if (l[q] < h[q]) {
+            if (h[q] - l[q] > 8u) {
               if (v[q] < lo[q]) l[q] = mid[q] + 1; else h[q] = mid[q];
-              any |= (l[q] < h[q]);
+              any |= (h[q] - l[q] > 8u);
             }
         }
+        uint32_t idx[SEL_ILP];
+#pragma unroll
+        for (int q = 0; q < SEL_ILP; q++) idx[q] = (o < n_o[q]) ? adb_finish_lower_bound(raw.mz, l[q], h[q], lo[q]) : 0u;
 #pragma unroll
         for (int q = 0; q < SEL_ILP; q++)
           if (o < n_o[q]) {
-            int idx = l[q];
+            uint32_t i2 = idx[q];
             if (prev_hi[q] >= lo[q])
-              while (idx < sp[q].n && __ldg(sp[q].mz + idx) <= prev_hi[q]) idx++;
-            while (idx < sp[q].n && __ldg(sp[q].mz + idx) <= hi[q]) {
-              acc[q] = __fadd_rn(acc[q], __ldg(sp[q].intensity + idx));
-              idx++;
+              while (i2 < stop[q] && __ldg(raw.mz + i2) <= prev_hi[q]) i2++;
+            while (i2 < stop[q] && __ldg(raw.mz + i2) <= hi[q]) {
+              acc[q] = __fadd_rn(acc[q], __ldg(raw.intensity + i2));
+              i2++;
             }
           }
       }
