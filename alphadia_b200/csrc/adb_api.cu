@@ -89,6 +89,7 @@ struct adb_rawfile {
   float h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, main_kernel_ms = 0;
   int launches = 0;
   int sm_count = 148;
+  size_t ws_budget = 0;
   // cached workspaces
   DeviceBuffer kern, order_keys, order_vals, order_tmp, sel_ws;
   DeviceBuffer cont;       // candidate container (9 columns)
@@ -207,23 +208,25 @@ __global__ void mz_range_kernel(DevRaw raw, float* out /* [2] = {min, max}, pre-
   atomicMax((unsigned int*)(out + 1), __float_as_uint(fmaxf(hi, 0.f)));
 }
 
-__global__ void bucket_index_kernel(DevRaw raw, uint32_t* table) {
+__global__ void bucket_index_kernel(DevRaw raw, uint2* table) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= raw.n_spectra * ADB_BUCKET_STRIDE) return;
-  int64_t scan = t / ADB_BUCKET_STRIDE;
-  int b = (int)(t % ADB_BUCKET_STRIDE);
+  if (t >= raw.n_spectra * ADB_N_BUCKETS) return;
+  int64_t scan = t / ADB_N_BUCKETS;
+  int b = (int)(t % ADB_N_BUCKETS);
   int64_t s = raw.peak_start[scan], e = raw.peak_stop[scan];
-  int64_t lo = s, hi = e;
-  if (b == 0) { hi = s; }
-  else if (b == ADB_N_BUCKETS) { lo = e; }
-  else {
-    float edge = adb_bucket_edge(raw, b);
+  uint32_t first = (uint32_t)s, last = (uint32_t)e;
+  for (int side = 0; side < 2; side++) {
+    int bb = b + side;  // lower edge of bucket b, lower edge of bucket b + 1
+    if (bb == 0 || bb == ADB_N_BUCKETS) continue;
+    float edge = adb_bucket_edge(raw, bb);
+    int64_t lo = s, hi = e;
     while (lo < hi) {
       int64_t mid = (lo + hi) >> 1;
       if (raw.mz[mid] < edge) lo = mid + 1; else hi = mid;
     }
+    if (side == 0) first = (uint32_t)lo; else last = (uint32_t)lo;
   }
-  table[t] = (uint32_t)lo;
+  table[t] = make_uint2(first, last);
 }
 
 __global__ void order_key_kernel(DevRaw raw, DevLib lib, uint64_t* keys, int32_t* vals) {
@@ -313,30 +316,27 @@ int run_selection(adb_rawfile* raw, adb_library* lib, const adb_selection_config
     d_order = v_out;
   }
 
-  // geometry
+  // geometry: dense XIC buffer strides + chunking of the precursor list so the HBM workspace stays bounded
   const int64_t c_upper = cycle_window_upper_bound(raw, cfg->rt_tolerance, cfg->kernel_size);
   const int nI = (int)std::min<int64_t>(std::min<int64_t>(lib->dev.n_isotopes, cfg->top_k_precursors), ADB_MAX_ISOTOPES);
   const int max_layers = std::min(lib->max_lib_fragments, (int)ADB_MAX_LIB_FRAGMENTS) + nI;
-  int c_cap = (int)c_upper;
-  const size_t smem_limit = 200 * 1024;
-  float* d_ws = nullptr;
-  int64_t ws_floats = 0;
-  if (adb_select_smem_bytes(c_cap, max_layers, kw) > smem_limit) {
-    // shrink the shared-memory layout; windows that do not fit use the per-slot HBM workspace
-    size_t per_slot = smem_limit / (size_t)adb_select_slots();
-    long long cc = ((long long)per_slot - 4LL * max_layers * (kw - 1) - 32) / (8 + 4LL * max_layers);
-    c_cap = (int)std::max<long long>(32, (cc / 16) * 16);
-    ws_floats = (int64_t)max_layers * (c_upper + kw) + 2 * c_upper + 16;
-    ws_floats = (ws_floats + 3) & ~(int64_t)3;
+  const int c_cap = (int)c_upper;
+  if (c_cap > 4096) return fail("selection cycle window larger than 4096 cycles is not supported");
+  const size_t per_prec = adb_select_bytes_per_precursor(c_cap, max_layers);
+  if (raw->ws_budget == 0) {  // once per handle: cudaMemGetInfo is slow
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    raw->ws_budget = std::min<size_t>((size_t)8 << 30, free_b / 3);
   }
-  int grid = adb_select_resident_ctas(raw->device, c_cap, max_layers, kw);
-  if (ws_floats > 0) {
-    if (raw->sel_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)grid * (size_t)adb_select_slots())) return 1;
-    d_ws = raw->sel_ws.as<float>();
-  }
+  size_t budget = std::max(raw->ws_budget, raw->sel_ws.bytes);
+  int64_t chunk = (int64_t)std::max<size_t>(budget / per_prec, 1);
+  chunk = std::min<int64_t>(chunk, P);
+  if (per_prec > budget) return fail("selection window too large for the device workspace");
+  if (raw->sel_ws.reserve((size_t)chunk * per_prec + 4096)) return 1;
   CUDA_TRY(cudaEventRecord(raw->ev[4], st));
-  adb_launch_select_ex(raw->dev, lib->dev, *cfg, kd.data(), kh, kw, raw->d_cont, 0, P, d_order, raw->d_status,
-                       c_cap, max_layers, d_ws, ws_floats, grid, st, &raw->launches);
+  for (int64_t begin = 0; begin < P; begin += chunk)
+    adb_launch_select_chunk(raw->dev, lib->dev, *cfg, kd.data(), kw, raw->d_cont, begin, std::min<int64_t>(chunk, P - begin),
+                            d_order, raw->d_status, c_cap, max_layers, raw->sel_ws.ptr, raw->sm_count, st, &raw->launches);
   CUDA_TRY(cudaEventRecord(raw->ev[5], st));
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -480,14 +480,14 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
     memcpy(&init[0], &inf_bits, 4);
     memcpy(&init[1], &zero_bits, 4);
     float* d_rng = nullptr;
-    uint32_t* d_tab = nullptr;
+    uint2* d_tab = nullptr;
     if (upload(init, 2, &d_rng, r->allocs, r->bytes, r->stream)) { adb_rawfile_destroy(r); return 1; }
-    size_t tab_n = (size_t)d->n_spectra * ADB_BUCKET_STRIDE;
+    size_t tab_n = (size_t)d->n_spectra * ADB_N_BUCKETS;
     void* tp = nullptr;
-    if (cudaMalloc(&tp, tab_n * sizeof(uint32_t)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc bucket index failed"); }
+    if (cudaMalloc(&tp, tab_n * sizeof(uint2)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc bucket index failed"); }
     r->allocs.push_back(tp);
-    r->bytes += (int64_t)(tab_n * sizeof(uint32_t));
-    d_tab = (uint32_t*)tp;
+    r->bytes += (int64_t)(tab_n * sizeof(uint2));
+    d_tab = (uint2*)tp;
     mz_range_kernel<<<(unsigned)((d->n_spectra + 255) / 256), 256, 0, r->stream>>>(v, d_rng);
     float rng[2] = {0.f, 0.f};
     cudaMemcpyAsync(rng, d_rng, sizeof(rng), cudaMemcpyDeviceToHost, r->stream);
@@ -497,7 +497,7 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
     v.bucket_width = (rng[1] - rng[0]) / (float)ADB_N_BUCKETS * 1.0001f;
     if (!(v.bucket_width > 0.f)) v.bucket_width = 1.f;
     v.bucket_inv_width = 1.0f / v.bucket_width;
-    v.bucket_abs = d_tab;
+    v.bucket_pair = d_tab;
     bucket_index_kernel<<<(unsigned)((tab_n + 255) / 256), 256, 0, r->stream>>>(v, d_tab);
     r->launches += 2;
   }

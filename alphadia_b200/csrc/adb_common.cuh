@@ -10,8 +10,7 @@
 #define ADB_MAX_MS1_POS 8        // MS1 spectra per DIA cycle
 #define ADB_MAX_KERNEL_W 64
 #define ADB_ISOTOPE_DIFF 1.0033548350700006
-#define ADB_N_BUCKETS 64         // m/z buckets per spectrum in the derived search index
-#define ADB_BUCKET_STRIDE (ADB_N_BUCKETS + 1)
+#define ADB_N_BUCKETS 256        // m/z buckets per spectrum in the derived search index
 #define ADB_MZ_PAD 16            // floats of padding behind mz/intensity so vector tail reads stay in bounds
 
 // status bits reported by kernels through a device word (-> adb_last_error on the host)
@@ -41,10 +40,11 @@ struct DevRaw {
   int32_t n_ms1_pos;                // cycle positions whose window overlaps [-1,-1]
   int32_t ms1_pos[ADB_MAX_MS1_POS];
   // derived m/z bucket index (built once per file on the device, sized to stay L2-resident):
-  // bucket_abs[scan][b], b in [1, 63] = ABSOLUTE index of the first peak of the spectrum with
-  // mz >= bucket_lo + b * bucket_width; [scan][0] = peak_start[scan], [scan][64] = peak_stop[scan].
-  // One row therefore also replaces the peak_start/peak_stop reads of the reference.
-  const uint32_t* bucket_abs;       // [n_spectra][ADB_BUCKET_STRIDE]
+  // bucket_pair[scan][b] = {first, last+1} ABSOLUTE peak indices of the peaks of spectrum `scan` that fall into
+  // m/z bucket b (edges bucket_lo + b * bucket_width; bucket 0 starts at the spectrum start, the last bucket ends
+  // at the spectrum stop).  One 8-byte read replaces the peak_start/peak_stop reads of the reference and all but
+  // the last levels of the binary search.
+  const uint2* bucket_pair;         // [n_spectra][ADB_N_BUCKETS]
   float bucket_lo, bucket_width, bucket_inv_width;
 };
 
@@ -114,13 +114,11 @@ struct DevScoresOut {
 };
 
 // ---- launchers (implemented in the .cu files) --------------------------------------------
-void adb_launch_select_ex(const DevRaw& raw, const DevLib& lib, const adb_selection_config& cfg, const double* h_kernel,
-                          int kh, int kw, DevCandidatesOut out, int64_t row_begin, int64_t row_end, const int32_t* d_order,
-                          uint32_t* d_status, int c_cap, int max_layers, float* d_workspace, int64_t ws_floats_per_slot,
-                          int grid, cudaStream_t stream, int* n_launches);
-size_t adb_select_smem_bytes(int c_cap, int max_layers, int kw);
-int adb_select_resident_ctas(int device, int c_cap, int max_layers, int kw);
-int adb_select_slots(void);
+size_t adb_select_bytes_per_precursor(int c_cap, int max_layers);
+void adb_launch_select_chunk(const DevRaw& raw, const DevLib& lib, const adb_selection_config& cfg, const double* h_kernel,
+                             int kw, DevCandidatesOut out, int64_t chunk_begin, int64_t chunk_n, const int32_t* d_order,
+                             uint32_t* d_status, int c_cap, int max_layers, void* workspace, int sm_count,
+                             cudaStream_t stream, int* n_launches);
 
 void adb_launch_score(const DevRaw& raw, const DevLib& lib, const adb_scoring_config& cfg, DevCandidatesIn cand,
                       DevScoresOut out, float* d_workspace, int64_t workspace_floats_per_tile, int n_resident_tiles,
@@ -160,19 +158,17 @@ __device__ __forceinline__ int adb_bucket_of(const DevRaw& raw, float v) {
   return b;
 }
 
-// Range [lo, hi] (absolute peak indices) that contains the lower bound of v in spectrum `scan`, plus the
-// spectrum's end: three independent 4-byte reads of one L2-resident table row.
-__device__ __forceinline__ void adb_bucket_range(const DevRaw& raw, int64_t scan, float v, uint32_t& lo, uint32_t& hi, uint32_t& stop) {
-  const int b = adb_bucket_of(raw, v);
-  const uint32_t* row = raw.bucket_abs + scan * ADB_BUCKET_STRIDE;
-  lo = __ldg(row + b);
-  hi = __ldg(row + b + 1);
-  stop = __ldg(row + ADB_N_BUCKETS);
-}
+// Result of a lower-bound search inside one spectrum.
+struct AdbFound {
+  uint32_t idx;      // absolute index of the first peak with mz >= v (may equal the spectrum stop)
+  float mz_at_idx;   // mz[idx] when `inside`
+  bool inside;       // idx is known to lie inside the spectrum (idx < bucket end <= stop)
+};
 
-// Finish a lower-bound search once the range is <= 8 peaks: three independent aligned 16-byte reads cover it;
-// the answer is lo + #(elements of [lo, hi) below v) because the spectrum is sorted.
-__device__ __forceinline__ uint32_t adb_finish_lower_bound(const float* __restrict__ mz, uint32_t lo, uint32_t hi, float v) {
+// Finish a lower-bound search once the range [lo, hi) is <= 8 peaks: three independent aligned 16-byte reads
+// cover it; the answer is lo + #(elements of [lo, hi) below v) because the spectrum is sorted.  The value at the
+// answer is taken from the registers already loaded when possible.
+__device__ __forceinline__ AdbFound adb_finish_lower_bound(const float* __restrict__ mz, uint32_t lo, uint32_t hi, float v) {
   const uint32_t A = lo & ~3u;
   const float4 x0 = __ldg(reinterpret_cast<const float4*>(mz + A));
   const float4 x1 = __ldg(reinterpret_cast<const float4*>(mz + A + 4));
@@ -184,19 +180,38 @@ __device__ __forceinline__ uint32_t adb_finish_lower_bound(const float* __restri
     uint32_t idx = A + j;
     cnt += (idx >= lo && idx < hi && e[j] < v) ? 1u : 0u;
   }
-  return lo + cnt;
+  AdbFound f;
+  f.idx = lo + cnt;
+  f.inside = f.idx < hi;
+  const uint32_t j = f.idx - A;
+  float val = 0.f;
+#pragma unroll
+  for (int q = 0; q < 12; q++) val = (j == (uint32_t)q) ? e[q] : val;
+  f.mz_at_idx = val;
+  if (f.inside && j >= 12u) f.mz_at_idx = __ldg(mz + f.idx);  // cannot happen for ranges <= 8, kept for safety
+  return f;
 }
 
-// lower bound of v inside spectrum `scan` as an absolute peak index; same result as
-// np.searchsorted(mz[start:stop], v, "left") + start / _search_sorted_reference_left (alpharaw_jit.py:53-75).
-__device__ __forceinline__ uint32_t adb_spectrum_lower_bound(const DevRaw& raw, int64_t scan, float v, uint32_t& stop) {
-  uint32_t lo, hi;
-  adb_bucket_range(raw, scan, v, lo, hi, stop);
+__device__ __forceinline__ uint2 adb_bucket_pair(const DevRaw& raw, int64_t scan, float v) {
+  return __ldg(raw.bucket_pair + scan * ADB_N_BUCKETS + adb_bucket_of(raw, v));
+}
+
+__device__ __forceinline__ uint32_t adb_spectrum_stop(const DevRaw& raw, int64_t scan) {
+  return __ldg(&raw.bucket_pair[scan * ADB_N_BUCKETS + (ADB_N_BUCKETS - 1)].y);
+}
+
+// lower bound of v inside spectrum `scan`; same result as np.searchsorted(mz[start:stop], v, "left") + start /
+// _search_sorted_reference_left (alpharaw_jit.py:53-75).
+__device__ __forceinline__ AdbFound adb_spectrum_lower_bound(const DevRaw& raw, int64_t scan, float v) {
+  const uint2 r = adb_bucket_pair(raw, scan, v);
+  uint32_t lo = r.x, hi = r.y;
   while (hi - lo > 8u) {
     uint32_t mid = (lo + hi) >> 1;
     if (__ldg(raw.mz + mid) < v) lo = mid + 1; else hi = mid;
   }
-  return adb_finish_lower_bound(raw.mz, lo, hi, v);
+  AdbFound f = adb_finish_lower_bound(raw.mz, lo, hi, v);
+  f.inside = f.idx < r.y;
+  return f;
 }
 
 __device__ __forceinline__ int64_t adb_wrap0(int64_t v, int64_t limit) {

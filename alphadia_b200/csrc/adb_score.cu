@@ -73,8 +73,11 @@ struct ScoreParams {
 // prev_hi: upper bound of the previous (lower m/z) window when it overlaps this one, else -1.
 __device__ __forceinline__ void extract_cell(const DevRaw& raw, int64_t scan, float lo, float hi, float prev_hi,
                                              float& acc_i, float& acc_m) {
-  uint32_t stop;
-  uint32_t idx = adb_spectrum_lower_bound(raw, scan, lo, stop);
+  const AdbFound f = adb_spectrum_lower_bound(raw, scan, lo);
+  // common case: the first candidate peak is known (still in registers) and lies above the window -> no hit
+  if (f.inside && !(f.mz_at_idx <= hi) && !(prev_hi >= lo)) return;
+  const uint32_t stop = adb_spectrum_stop(raw, scan);
+  uint32_t idx = f.idx;
   if (prev_hi >= lo)  // the search cursor only moves forward: peaks taken by the previous window are gone
     while (idx < stop && __ldg(raw.mz + idx) <= prev_hi) idx++;
   while (idx < stop) {

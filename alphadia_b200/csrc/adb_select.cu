@@ -1,4 +1,4 @@
-// alphadia_b200 — candidate selection kernel (3-D raw files), sm_100a.
+// alphadia_b200 — candidate selection (3-D raw files), sm_100a: three kernels per chunk of precursors.
 //
 // Replaces _select_candidates_pjit (alphadia/search/selection/selection.py:78-203) and everything below it:
 // AlphaRawJIT.get_dense_intensity (jitclasses/alpharaw_jit.py:339-425), get_frame_indices
@@ -6,27 +6,36 @@
 // convolution with fp64 FMA accumulation — see DESIGN.md), _build_features/_build_candidates
 // (selection.py:206-226,367-526), find_peaks_1d / symetric_limits_2d (selection/utils.py:45-74,205-312).
 //
-// Mapping: a CTA of SEL_SLOTS warps works on SEL_SLOTS precursors at a time ("slots"); persistent CTAs stride
-// over groups of precursors in (quad window, RT) order so co-resident CTAs hit the same spectra in L2.
-//   phase 0  warp w <-> slot w: isotope m/z, fragment filter + m/z sort, RT window -> cycle window, quad windows
-//   phase 1  all threads over (slot, cycle, layer) items, layer fastest (neighbouring threads search the same
-//            spectrum); SEL_ILP independent searches in flight per thread; per-spectrum lower bounds go
-//            through the L2-resident m/z bucket index; XIC layers land in shared memory with a circular halo
-//   phase 2  all threads over (slot, cycle) cells: circular Gaussian smoothing of every layer (fp64 FMA from
-//            the kernel in the constant bank, kernel rows then columns ascending), log(x + 1) in fp64 rounded
-//            to f32, f32 layer sums -> score[slot][cycle]
-//   phase 3  warp w <-> slot w: strict 5-point peaks, top-N (warp arg-max), close-peak suppression,
-//            symmetric limits, write-out (integer-exact tail).
+// Precursors are visited in (quad window, RT) order so concurrently running CTAs hit the same spectra in L2.
+//   adb_select_plan_kernel     warp per precursor: isotope m/z, fragment filter + m/z sort, RT window -> cycle
+//                              window, quad windows, ppm windows -> a 40-byte plan + lo/hi rows in HBM
+//   adb_select_extract_kernel  thread per (precursor, cycle, layer) XIC cell at full occupancy, layer fastest
+//                              (neighbouring threads search the same spectrum), SEL_ILP independent searches in
+//                              flight per thread through the L2-resident m/z bucket index; dense XIC layers
+//                              [precursor][layer][cycle] f32 go to HBM (they stay in the 126 MB L2 for the consumer)
+//   adb_select_smooth_kernel   CTA per precursor, thread per cycle: layers streamed through a double-buffered
+//                              fp64 shared-memory row with circular halo (one f32->f64 conversion per element),
+//                              30-tap x 2-row Gaussian smoothing as fp64 FMA from the constant bank (kernel rows
+//                              then columns ascending), log(x + 1) in fp64 rounded to f32, f32 layer sums; then
+//                              warp 0: strict 5-point peaks, top-N (warp arg-max), close-peak suppression,
+//                              symmetric limits, write-out (integer-exact tail).
 #include "adb_common.cuh"
 
 #define FULL 0xffffffffu
-#define SEL_SLOTS 4
-#define SEL_THREADS (SEL_SLOTS * 32)
 #define SEL_ILP 4
 #define SEL_MAX_LAYERS (ADB_MAX_LIB_FRAGMENTS + ADB_MAX_ISOTOPES)
 #define SEL_MAX_CAND 16
+#define SEL_PLAN_THREADS 128
+#define SEL_EXTRACT_THREADS 256
 
 namespace {
+
+struct __align__(8) PrecPlan {
+  long long frame_lo;
+  int row, cs, C;
+  unsigned char ok, nF, nI, nobs;
+  short pos[ADB_MAX_OBS];
+};
 
 struct SelectParams {
   DevRaw raw;
@@ -35,15 +44,17 @@ struct SelectParams {
   double kern[2 * ADB_MAX_KERNEL_W];  // [2][kw] Gaussian kernel as doubles (constant bank)
   int kw;
   DevCandidatesOut out;
-  long long row_begin, row_end;
-  const int32_t* order;  // optional processing order of library rows
+  long long chunk_begin, chunk_n;  // positions [chunk_begin, chunk_begin + chunk_n) of the processing order
+  const int32_t* order;            // processing order of library rows (may be null = identity)
   uint32_t* status;
-  int c_cap;       // cycles per slot the shared-memory layout can hold
-  int layer_cap;   // layers per slot the shared-memory layout can hold
-  float* workspace;      // per-slot HBM fallback for oversized windows
-  long long ws_floats_per_slot;
+  int c_cap, layer_cap;            // strides of the dense buffer
+  PrecPlan* plan;                  // [chunk_n]
+  float* win_lo;                   // [chunk_n][layer_cap]
+  float* win_hi;                   // [chunk_n][layer_cap]
+  float* dense;                    // [chunk_n][layer_cap][c_cap]
 };
 
+// per-warp staging for the plan kernel / per-CTA state for the smoothing kernel
 struct SlotMeta {
   float lo[SEL_MAX_LAYERS], hi[SEL_MAX_LAYERS];
   float tmp_mz[ADB_MAX_LIB_FRAGMENTS];
@@ -51,7 +62,6 @@ struct SlotMeta {
   int pos[ADB_MAX_OBS];
   int nF, nI, nobs, C, ok;
   long long frame_lo, cs, row;
-  float* dense;    // [nL][C + kw - 1] with halo
   double* score;   // [C]
 };
 
@@ -265,271 +275,321 @@ __device__ void slot_finish(const SelectParams& P, SlotMeta& sl, int lane) {
   }
 }
 
-// smoothing of one layer at cycle c: out = sum_a sum_b k[a][b] * x[(c + kw/2 - b) mod C], a then b ascending.
-// ext[t] = x[(t - off) mod C] with off = kw - 1 - kw/2, so x[(c + kw/2 - b) mod C] = ext[c + kw - 1 - b].
-template <int KW>
-__device__ __forceinline__ float smooth_cell(const SelectParams& P, const float* ext, int c, int kw) {
-  double acc = 0.0;
-  if (KW > 0) {
-    double v[KW > 0 ? KW : 1];
-#pragma unroll
-    for (int u = 0; u < KW; u++) v[u] = (double)ext[c + u];
-#pragma unroll
-    for (int a = 0; a < 2; a++)
-#pragma unroll
-      for (int b = 0; b < KW; b++) acc = fma(P.kern[a * KW + b], v[KW - 1 - b], acc);
-  } else {
-    for (int a = 0; a < 2; a++)
-      for (int b = 0; b < kw; b++) acc = fma(P.kern[a * kw + b], (double)ext[c + kw - 1 - b], acc);
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_PLAN_THREADS) adb_select_plan_kernel(const __grid_constant__ SelectParams P) {
+  __shared__ SlotMeta slots[SEL_PLAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long it = (long long)blockIdx.x * (SEL_PLAN_THREADS / 32) + warp;
+  if (it >= P.chunk_n) return;
+  SlotMeta& sl = slots[warp];
+  const long long pos_in_order = P.chunk_begin + it;
+  const int64_t i = P.order ? (int64_t)P.order[pos_in_order] : (int64_t)pos_in_order;
+  slot_setup(P, sl, i, lane);
+  __syncwarp();
+  int ok = sl.ok;
+  if (ok && (sl.C > P.c_cap || sl.nF + sl.nI > P.layer_cap)) {  // cannot happen with the host-side bounds
+    if (lane == 0) atomicOr(P.status, ADB_STATUS_SCRATCH_OVERFLOW);
+    ok = 0;
   }
-  return (float)acc;
+  if (lane == 0) {
+    PrecPlan pl;
+    pl.frame_lo = sl.frame_lo; pl.row = (int)sl.row; pl.cs = (int)sl.cs; pl.C = sl.C;
+    pl.ok = (unsigned char)ok; pl.nF = (unsigned char)sl.nF; pl.nI = (unsigned char)sl.nI;
+    pl.nobs = (unsigned char)min(sl.nobs, ADB_MAX_OBS);
+    for (int o = 0; o < ADB_MAX_OBS; o++) pl.pos[o] = (short)((o < sl.nobs) ? sl.pos[o] : 0);
+    P.plan[it] = pl;
+  }
+  if (ok) {
+    const int nL = sl.nF + sl.nI;
+    for (int k = lane; k < nL; k += 32) {
+      P.win_lo[it * P.layer_cap + k] = sl.lo[k];
+      P.win_hi[it * P.layer_cap + k] = sl.hi[k];
+    }
+  }
 }
 
-template <int KW>
-__global__ void __launch_bounds__(SEL_THREADS) adb_select_kernel(const __grid_constant__ SelectParams P) {
-  extern __shared__ __align__(16) unsigned char dyn[];
-  __shared__ SlotMeta slots[SEL_SLOTS];
-  __shared__ long long item_prefix[SEL_SLOTS + 1];
-  __shared__ int cell_prefix[SEL_SLOTS + 1];
+// ---------------------------------------------------------------------------------------------------------
+// XIC extraction (alpharaw_jit.py:398-423).  One cell per item; hits are added in ascending peak order and the
+// observations (cycle positions) in ascending order inside one thread, so the f32 sums are bit-exact.
+__global__ void __launch_bounds__(SEL_EXTRACT_THREADS) adb_select_extract_kernel(const __grid_constant__ SelectParams P) {
   const DevRaw& raw = P.raw;
-  const adb_selection_config& cfg = P.cfg;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t L = raw.cycle_len;
-  const int kw = (KW > 0) ? KW : P.kw;
-  const int ext_stride_cap = P.c_cap + kw - 1;
-  // dynamic shared memory per slot: score doubles [c_cap] | dense floats [layer_cap][c_cap + kw - 1]
-  const size_t slot_bytes = sizeof(double) * (size_t)P.c_cap + sizeof(float) * (size_t)P.layer_cap * ext_stride_cap;
-  const size_t slot_bytes_al = (slot_bytes + 15) & ~(size_t)15;
-
-  const long long n_groups = (P.row_end - P.row_begin + SEL_SLOTS - 1) / SEL_SLOTS;
-  for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
-    __syncthreads();
-    // ---------------- phase 0 ----------------
-    {
-      SlotMeta& sl = slots[warp];
-      long long it = P.row_begin + g * SEL_SLOTS + warp;
-      if (it < P.row_end) {
-        const int64_t i = P.order ? (int64_t)P.order[it] : (int64_t)it;
-        slot_setup(P, sl, i, lane);
-      } else if (lane == 0) {
-        sl.ok = 0; sl.nF = 0; sl.nI = 0; sl.C = 0; sl.nobs = 0;
-      }
-      __syncwarp();
-      if (lane == 0) {
-        unsigned char* base = dyn + (size_t)warp * slot_bytes_al;
-        sl.score = (double*)base;
-        sl.dense = (float*)(base + sizeof(double) * (size_t)P.c_cap);
-        if (sl.ok && (sl.C > P.c_cap || sl.nF + sl.nI > P.layer_cap)) {  // HBM fallback for oversized windows
-          long long need = (long long)(sl.nF + sl.nI) * (sl.C + kw - 1) + 2LL * sl.C + 4;
-          if (P.workspace == nullptr || need > P.ws_floats_per_slot) {
-            atomicOr(P.status, ADB_STATUS_SCRATCH_OVERFLOW);
-            sl.ok = 0;
-          } else {
-            float* ws = P.workspace + ((size_t)blockIdx.x * SEL_SLOTS + warp) * (size_t)P.ws_floats_per_slot;
-            sl.score = (double*)ws;  // workspace slots are 16-byte aligned
-            sl.dense = ws + 2 * (size_t)sl.C;
-          }
-        }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      long long acc = 0;
-      int cacc = 0;
-      for (int s = 0; s < SEL_SLOTS; s++) {
-        item_prefix[s] = acc;
-        cell_prefix[s] = cacc;
-        if (slots[s].ok) { acc += (long long)(slots[s].nF + slots[s].nI) * slots[s].C; cacc += slots[s].C; }
-      }
-      item_prefix[SEL_SLOTS] = acc;
-      cell_prefix[SEL_SLOTS] = cacc;
-    }
-    __syncthreads();
-    // ---------------- phase 1: XICs (alpharaw_jit.py:398-423), SEL_ILP searches in flight per thread ----
-    const long long n_items = item_prefix[SEL_SLOTS];
-    for (long long t0 = tid; t0 < n_items; t0 += (long long)SEL_THREADS * SEL_ILP) {
-      float lo[SEL_ILP], hi[SEL_ILP], prev_hi[SEL_ILP], acc[SEL_ILP];
-      float* dst[SEL_ILP];
-      const int* posv[SEL_ILP];
-      long long cyc_base[SEL_ILP];
-      int n_o[SEL_ILP];
-      int max_o = 0;
+  const long long per_prec = (long long)P.layer_cap * P.c_cap;
+  const long long n_items = P.chunk_n * per_prec;
+  const long long stride = (long long)gridDim.x * SEL_EXTRACT_THREADS;
+  for (long long t0 = (long long)blockIdx.x * SEL_EXTRACT_THREADS + threadIdx.x; t0 < n_items; t0 += stride * SEL_ILP) {
+    float lo[SEL_ILP], hi[SEL_ILP], prev_hi[SEL_ILP], acc[SEL_ILP];
+    float* dst[SEL_ILP];
+    const short* posv[SEL_ILP];
+    long long cyc_base[SEL_ILP];
+    int n_o[SEL_ILP];
+    bool ms1[SEL_ILP];
+    int max_o = 0;
 #pragma unroll
-      for (int q = 0; q < SEL_ILP; q++) {
-        long long t = t0 + (long long)q * SEL_THREADS;
-        n_o[q] = 0; acc[q] = 0.f; dst[q] = nullptr; posv[q] = nullptr; lo[q] = 0.f; hi[q] = 0.f; prev_hi[q] = -1.f; cyc_base[q] = 0;
-        if (t < n_items) {
-          int s = 0;
-#pragma unroll
-          for (int z = 1; z < SEL_SLOTS; z++) s += (t >= item_prefix[z]);
-          const SlotMeta& sl = slots[s];
-          long long local = t - item_prefix[s];
-          const int nL = sl.nF + sl.nI;
-          const int li = (int)local;
-          int k = li % nL, c = li / nL;
-          lo[q] = sl.lo[k]; hi[q] = sl.hi[k];
-          prev_hi[q] = (k > 0 && k != sl.nF) ? sl.hi[k - 1] : -1.0f;
-          const bool ms1 = k >= sl.nF;
-          n_o[q] = ms1 ? raw.n_ms1_pos : sl.nobs;
-          posv[q] = ms1 ? raw.ms1_pos : sl.pos;
-          cyc_base[q] = (sl.cs + c) * L;
-          dst[q] = sl.dense + (size_t)k * (sl.C + kw - 1) + (kw - 1 - kw / 2) + c;
+    for (int q = 0; q < SEL_ILP; q++) {
+      const long long t = t0 + (long long)q * stride;
+      n_o[q] = 0; acc[q] = 0.f; dst[q] = nullptr; posv[q] = nullptr; lo[q] = 0.f; hi[q] = 0.f; prev_hi[q] = -1.f;
+      cyc_base[q] = 0; ms1[q] = false;
+      if (t < n_items) {
+        const long long it = t / per_prec;
+        const int local = (int)(t - it * per_prec);
+        const int k = local % P.layer_cap, c = local / P.layer_cap;  // layer fastest
+        const PrecPlan& pl = P.plan[it];
+        const int nL = (int)pl.nF + (int)pl.nI;
+        if (pl.ok && k < nL && c < pl.C) {
+          lo[q] = __ldg(P.win_lo + it * P.layer_cap + k);
+          hi[q] = __ldg(P.win_hi + it * P.layer_cap + k);
+          prev_hi[q] = (k > 0 && k != pl.nF) ? __ldg(P.win_hi + it * P.layer_cap + k - 1) : -1.0f;
+          ms1[q] = k >= pl.nF;
+          n_o[q] = ms1[q] ? raw.n_ms1_pos : (int)pl.nobs;
+          posv[q] = pl.pos;
+          cyc_base[q] = ((long long)pl.cs + c) * L;
+          dst[q] = P.dense + (it * P.layer_cap + k) * (long long)P.c_cap + c;
           max_o = max(max_o, n_o[q]);
         }
       }
-      for (int o = 0; o < max_o; o++) {
-        uint32_t l[SEL_ILP], h[SEL_ILP], stop[SEL_ILP];
+    }
+    for (int o = 0; o < max_o; o++) {
+      uint32_t l[SEL_ILP], h[SEL_ILP], bend[SEL_ILP];
+      int64_t scan[SEL_ILP];
+#pragma unroll
+      for (int q = 0; q < SEL_ILP; q++) {
+        l[q] = 0; h[q] = 0; bend[q] = 0; scan[q] = 0;
+        if (o < n_o[q]) {
+          scan[q] = (int64_t)(ms1[q] ? raw.ms1_pos[o] : (int)posv[q][o]) + cyc_base[q];
+          const uint2 r = adb_bucket_pair(raw, scan[q], lo[q]);
+          l[q] = r.x; h[q] = r.y; bend[q] = r.y;
+        }
+      }
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < SEL_ILP; q++) any |= (h[q] - l[q] > 8u);
+      while (any) {  // interleaved binary searches: the SEL_ILP loads of a round are independent
+        any = false;
+        float v[SEL_ILP];
+        uint32_t mid[SEL_ILP];
 #pragma unroll
         for (int q = 0; q < SEL_ILP; q++) {
-          l[q] = 0; h[q] = 0; stop[q] = 0;
-          if (o < n_o[q]) adb_bucket_range(raw, (int64_t)posv[q][o] + cyc_base[q], lo[q], l[q], h[q], stop[q]);
+          mid[q] = (l[q] + h[q]) >> 1;
+          v[q] = (h[q] - l[q] > 8u) ? __ldg(raw.mz + mid[q]) : 0.f;
         }
-        bool any = true;
-        while (any) {  // interleaved binary searches: the SEL_ILP loads of a round are independent
-          any = false;
-          float v[SEL_ILP];
-          uint32_t mid[SEL_ILP];
-#pragma unroll
-          for (int q = 0; q < SEL_ILP; q++) {
-            mid[q] = (l[q] + h[q]) >> 1;
-            v[q] = (h[q] - l[q] > 8u) ? __ldg(raw.mz + mid[q]) : 0.f;
-          }
-#pragma unroll
-          for (int q = 0; q < SEL_ILP; q++)
-            if (h[q] - l[q] > 8u) {
-              if (v[q] < lo[q]) l[q] = mid[q] + 1; else h[q] = mid[q];
-              any |= (h[q] - l[q] > 8u);
-            }
-        }
-        uint32_t idx[SEL_ILP];
-#pragma unroll
-        for (int q = 0; q < SEL_ILP; q++) idx[q] = (o < n_o[q]) ? adb_finish_lower_bound(raw.mz, l[q], h[q], lo[q]) : 0u;
 #pragma unroll
         for (int q = 0; q < SEL_ILP; q++)
-          if (o < n_o[q]) {
-            uint32_t i2 = idx[q];
-            if (prev_hi[q] >= lo[q])
-              while (i2 < stop[q] && __ldg(raw.mz + i2) <= prev_hi[q]) i2++;
-            while (i2 < stop[q] && __ldg(raw.mz + i2) <= hi[q]) {
-              acc[q] = __fadd_rn(acc[q], __ldg(raw.intensity + i2));
-              i2++;
-            }
+          if (h[q] - l[q] > 8u) {
+            if (v[q] < lo[q]) l[q] = mid[q] + 1; else h[q] = mid[q];
+            any |= (h[q] - l[q] > 8u);
           }
+      }
+      AdbFound f[SEL_ILP];
+#pragma unroll
+      for (int q = 0; q < SEL_ILP; q++) {
+        f[q].idx = 0; f[q].inside = true; f[q].mz_at_idx = 3.0e38f;
+        if (o < n_o[q]) { f[q] = adb_finish_lower_bound(raw.mz, l[q], h[q], lo[q]); f[q].inside = f[q].idx < bend[q]; }
       }
 #pragma unroll
       for (int q = 0; q < SEL_ILP; q++)
-        if (dst[q]) *dst[q] = acc[q];
+        if (o < n_o[q]) {
+          // common case: the first candidate peak (still in registers) lies above the window -> no hit
+          if (f[q].inside && !(f[q].mz_at_idx <= hi[q]) && !(prev_hi[q] >= lo[q])) continue;
+          const uint32_t stop = adb_spectrum_stop(raw, scan[q]);
+          uint32_t i2 = f[q].idx;
+          if (prev_hi[q] >= lo[q])
+            while (i2 < stop && __ldg(raw.mz + i2) <= prev_hi[q]) i2++;
+          while (i2 < stop && __ldg(raw.mz + i2) <= hi[q]) {
+            acc[q] = __fadd_rn(acc[q], __ldg(raw.intensity + i2));
+            i2++;
+          }
+        }
     }
-    __syncthreads();
-    // circular halo: ext[t] = x[(t - off) mod C], t in [0, C + kw - 1)
-    for (int s = 0; s < SEL_SLOTS; s++) {
-      const SlotMeta& sl = slots[s];
-      if (!sl.ok) continue;
-      const int C = sl.C, nL = sl.nF + sl.nI, stride = C + kw - 1, off = kw - 1 - kw / 2;
-      const int halo = kw - 1;
-      for (int t = tid; t < nL * halo; t += SEL_THREADS) {
-        int k = t / halo, u = t % halo;
-        float* row = sl.dense + (size_t)k * stride;
-        if (u < off) row[u] = row[u + C];
-        else row[C + u] = row[u];  // u in [off, kw-1): positions C+off .. C+kw-2 mirror off .. kw-2
-      }
-    }
-    __syncthreads();
-    // ---------------- phase 2: smooth + log-sum (selection.py:389-428) ----------------
-    {
-      const int n_cells = cell_prefix[SEL_SLOTS];
-      for (int t = tid; t < n_cells; t += SEL_THREADS) {
-        int s = 0;
 #pragma unroll
-        for (int z = 1; z < SEL_SLOTS; z++) s += (t >= cell_prefix[z]);
-        const SlotMeta& sl = slots[s];
-        const int c = t - cell_prefix[s];
-        const int stride = sl.C + kw - 1, nL = sl.nF + sl.nI;
-        float lf = 0.f, lp = 0.f;
-        for (int l = 0; l < nL; l++) {
-          float smooth = smooth_cell<KW>(P, sl.dense + (size_t)l * stride, c, kw);
-          float lg = (float)log((double)smooth + 1.0);
-          if (l < sl.nF) lf = __fadd_rn(lf, lg); else lp = __fadd_rn(lp, lg);
-        }
-        sl.score[c] = (double)__fadd_rn(lf, lp);  // raw feature, normalised below
-      }
+    for (int q = 0; q < SEL_ILP; q++)
+      if (dst[q]) *dst[q] = acc[q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// smoothing of one layer at cycles c0 .. c0+3: out[c] = sum_a sum_b k[a][b] * x[(c + kw/2 - b) mod C], a then b
+// ascending (fp64 FMA).  ext[t] = x[(t - off) mod C] with off = kw - 1 - kw/2, so x[(c + kw/2 - b) mod C] =
+// ext[c + kw - 1 - b].  Four adjacent cells share one register window of KW + 3 doubles (four independent FMA chains).
+template <int KW>
+__device__ __forceinline__ void smooth_cells4(const SelectParams& P, const double* ext, int c0, int kw, float out[4]) {
+  if (KW > 0) {
+    double v[(KW > 0 ? KW : 1) + 3];
+#pragma unroll
+    for (int u = 0; u < KW + 3; u++) v[u] = ext[c0 + u];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      double acc = 0.0;
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < KW; b++) acc = fma(P.kern[a * KW + b], v[q + KW - 1 - b], acc);
+      out[q] = (float)acc;
     }
-    __syncthreads();
-    // normalisation (selection.py:405-428), warp w <-> slot w
-    {
-      SlotMeta& sl = slots[warp];
-      if (sl.ok) {
-        const int C = sl.C;
-        double mean = cfg.use_weighted_score ? cfg.feature_mean : 0.0;
-        double stdv = cfg.use_weighted_score ? cfg.feature_std : 0.0;
-        const double wgt = cfg.use_weighted_score ? cfg.feature_weight : 1.0;
-        if (!cfg.use_weighted_score) {  // amean1 / astd1 over the (2, C) feature map; sequential, rare path
-          float accf = 0.f;
-          for (int s = 0; s < 2; s++) for (int c = 0; c < C; c++) accf = __fadd_rn(accf, (float)sl.score[c]);
-          mean = (double)accf / (double)(2 * C);
-          double v = 0;
-          for (int s = 0; s < 2; s++) for (int c = 0; c < C; c++) { double d = sl.score[c] - mean; v = __dadd_rn(v, __dmul_rn(d, d)); }
-          stdv = sqrt(v / (double)(2 * C));
-        }
-        __syncwarp();
-        for (int c = lane; c < C; c += 32) sl.score[c] = 0.0 + __dmul_rn(wgt, (sl.score[c] - mean)) / (stdv + 1e-6);
-        __syncwarp();
-        // ---------------- phase 3 ----------------
-        slot_finish(P, sl, lane);
-      }
+  } else {
+    for (int q = 0; q < 4; q++) {
+      double acc = 0.0;
+      for (int a = 0; a < 2; a++)
+        for (int b = 0; b < kw; b++) acc = fma(P.kern[a * kw + b], ext[c0 + q + kw - 1 - b], acc);
+      out[q] = (float)acc;
     }
   }
 }
 
-size_t select_smem_bytes(int c_cap, int layer_cap, int kw) {
-  size_t slot = sizeof(double) * (size_t)c_cap + sizeof(float) * (size_t)layer_cap * (size_t)(c_cap + kw - 1);
-  slot = (slot + 15) & ~(size_t)15;
-  return slot * SEL_SLOTS;
+#define SMOOTH_GROUPS 2  // groups of 4 adjacent cycles per thread (cycle windows up to 8 * blockDim)
+
+// dynamic shared memory: score doubles [c_cap] | two fp64 layer rows [c_cap + kw - 1 + 4]
+template <int KW>
+__global__ void adb_select_smooth_kernel(const __grid_constant__ SelectParams P) {
+  extern __shared__ __align__(16) double dyn_d[];
+  __shared__ SlotMeta sl;
+  const adb_selection_config& cfg = P.cfg;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int kw = (KW > 0) ? KW : P.kw;
+  const int off = kw - 1 - kw / 2;
+  const int row_alloc = P.c_cap + kw - 1 + 4;
+  double* score = dyn_d;
+  double* buf0 = dyn_d + ((P.c_cap + 3) & ~3);
+  double* buf1 = buf0 + ((row_alloc + 3) & ~3);
+  for (long long it = blockIdx.x; it < P.chunk_n; it += gridDim.x) {
+    const PrecPlan pl = P.plan[it];
+    if (!pl.ok) continue;  // uniform for the CTA
+    const int C = pl.C, nF = pl.nF, nL = (int)pl.nF + (int)pl.nI;
+    const int stride = C + kw - 1;
+    const float* dense = P.dense + it * (long long)P.layer_cap * P.c_cap;
+    __syncthreads();  // previous precursor's tail (warp 0) is done with the shared state
+    // layer 0 -> buf0 (with circular halo: ext[t] = x[(t - off) mod C]); the 4-double pad stays finite
+    for (int t = tid; t < stride + 4; t += nthr) {
+      int j = t - off; if (j < 0) j += C; else if (j >= C) j -= C;
+      buf0[t] = (t < stride) ? (double)__ldg(dense + j) : 0.0;
+      if (t >= stride) buf1[t] = 0.0;
+    }
+    __syncthreads();
+    float lf_r[SMOOTH_GROUPS][4], lp_r[SMOOTH_GROUPS][4];
+#pragma unroll
+    for (int g = 0; g < SMOOTH_GROUPS; g++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) { lf_r[g][q] = 0.f; lp_r[g][q] = 0.f; }
+    for (int l = 0; l < nL; l++) {
+      const double* cur = (l & 1) ? buf1 : buf0;
+      double* nxt = (l & 1) ? buf0 : buf1;
+      // prefetch the next layer into registers (global latency overlaps the smoothing below)
+      float pre[4] = {0.f, 0.f, 0.f, 0.f};
+      if (l + 1 < nL) {
+        const float* row = dense + (long long)(l + 1) * P.c_cap;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int t = tid + u * nthr;
+          if (t < stride) { int j = t - off; if (j < 0) j += C; else if (j >= C) j -= C; pre[u] = __ldg(row + j); }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < SMOOTH_GROUPS; g++) {
+        const int c0 = 4 * (tid + g * nthr);
+        if (c0 < C) {
+          float sm4[4];
+          smooth_cells4<KW>(P, cur, c0, kw, sm4);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            float lg = (float)log((double)sm4[q] + 1.0);
+            if (l < nF) lf_r[g][q] = __fadd_rn(lf_r[g][q], lg); else lp_r[g][q] = __fadd_rn(lp_r[g][q], lg);
+          }
+        }
+      }
+      if (l + 1 < nL) {
+        const float* row = dense + (long long)(l + 1) * P.c_cap;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int t = tid + u * nthr;
+          if (t < stride) nxt[t] = (double)pre[u];
+        }
+        for (int t = tid + 4 * nthr; t < stride; t += nthr) {
+          int j = t - off; if (j < 0) j += C; else if (j >= C) j -= C;
+          nxt[t] = (double)__ldg(row + j);
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int g = 0; g < SMOOTH_GROUPS; g++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int c = 4 * (tid + g * nthr) + q;
+        if (c < C) score[c] = (double)__fadd_rn(lf_r[g][q], lp_r[g][q]);  // raw feature (selection.py:221-224)
+      }
+    __syncthreads();
+    if (warp == 0) {
+      // normalisation (selection.py:405-428)
+      double mean = cfg.use_weighted_score ? cfg.feature_mean : 0.0;
+      double stdv = cfg.use_weighted_score ? cfg.feature_std : 0.0;
+      const double wgt = cfg.use_weighted_score ? cfg.feature_weight : 1.0;
+      if (!cfg.use_weighted_score) {  // amean1 / astd1 over the (2, C) feature map; sequential, rare path
+        float accf = 0.f;
+        for (int s = 0; s < 2; s++) for (int c = 0; c < C; c++) accf = __fadd_rn(accf, (float)score[c]);
+        mean = (double)accf / (double)(2 * C);
+        double v = 0;
+        for (int s = 0; s < 2; s++) for (int c = 0; c < C; c++) { double d = score[c] - mean; v = __dadd_rn(v, __dmul_rn(d, d)); }
+        stdv = sqrt(v / (double)(2 * C));
+      }
+      __syncwarp();
+      for (int c = lane; c < C; c += 32) score[c] = 0.0 + __dmul_rn(wgt, (score[c] - mean)) / (stdv + 1e-6);
+      if (lane == 0) { sl.C = C; sl.frame_lo = pl.frame_lo; sl.row = pl.row; sl.score = score; }
+      __syncwarp();
+      slot_finish(P, sl, lane);
+    }
+  }
+}
+
+size_t smooth_smem_bytes(int c_cap, int kw) { return sizeof(double) * ((size_t)((c_cap + 3) & ~3) + 2 * (size_t)((c_cap + kw - 1 + 4 + 3) & ~3)) + 16; }
+
+template <int KW>
+void launch_smooth(const SelectParams& P, int threads, long long grid, size_t dyn, cudaStream_t stream) {
+  cudaFuncSetAttribute(adb_select_smooth_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  adb_select_smooth_kernel<KW><<<(unsigned)grid, threads, dyn, stream>>>(P);
 }
 
 }  // namespace
 
-size_t adb_select_smem_bytes(int c_cap, int max_layers, int kw) { return select_smem_bytes(c_cap, max_layers, kw); }
-
-int adb_select_resident_ctas(int device, int c_cap, int max_layers, int kw) {
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  size_t dyn = select_smem_bytes(c_cap, max_layers, kw);
-  int per_sm = 0;
-  if (kw == 30) {
-    cudaFuncSetAttribute(adb_select_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adb_select_kernel<30>, SEL_THREADS, dyn);
-  } else {
-    cudaFuncSetAttribute(adb_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adb_select_kernel<0>, SEL_THREADS, dyn);
-  }
-  if (per_sm < 1) per_sm = 1;
-  return sms * per_sm;
+size_t adb_select_bytes_per_precursor(int c_cap, int max_layers) {
+  return sizeof(PrecPlan) + 2 * sizeof(float) * (size_t)max_layers + sizeof(float) * (size_t)max_layers * (size_t)c_cap;
 }
 
-int adb_select_slots(void) { return SEL_SLOTS; }
-
-void adb_launch_select_ex(const DevRaw& raw, const DevLib& lib, const adb_selection_config& cfg, const double* h_kernel,
-                          int kh, int kw, DevCandidatesOut out, int64_t row_begin, int64_t row_end, const int32_t* d_order,
-                          uint32_t* d_status, int c_cap, int max_layers, float* d_workspace, int64_t ws_floats_per_slot,
-                          int grid, cudaStream_t stream, int* n_launches) {
-  if (row_end <= row_begin) return;
-  (void)kh;
+// Runs plan + extract + smooth for positions [chunk_begin, chunk_begin + chunk_n) of the processing order.
+// `workspace` must hold chunk_n * adb_select_bytes_per_precursor(c_cap, max_layers) bytes (+ 256 for alignment).
+void adb_launch_select_chunk(const DevRaw& raw, const DevLib& lib, const adb_selection_config& cfg, const double* h_kernel,
+                             int kw, DevCandidatesOut out, int64_t chunk_begin, int64_t chunk_n, const int32_t* d_order,
+                             uint32_t* d_status, int c_cap, int max_layers, void* workspace, int sm_count,
+                             cudaStream_t stream, int* n_launches) {
+  if (chunk_n <= 0) return;
   SelectParams P;
   P.raw = raw; P.lib = lib; P.cfg = cfg; P.kw = kw; P.out = out;
   for (int t = 0; t < 2 * ADB_MAX_KERNEL_W; t++) P.kern[t] = (t < 2 * kw) ? h_kernel[t] : 0.0;
-  P.row_begin = row_begin; P.row_end = row_end; P.order = d_order; P.status = d_status;
-  P.c_cap = c_cap; P.layer_cap = max_layers; P.workspace = d_workspace; P.ws_floats_per_slot = ws_floats_per_slot;
-  size_t dyn = select_smem_bytes(c_cap, max_layers, kw);
-  long long n_groups = (row_end - row_begin + SEL_SLOTS - 1) / SEL_SLOTS;
-  if (grid > n_groups) grid = (int)n_groups;
-  if (grid < 1) grid = 1;
-  if (kw == 30) {
-    cudaFuncSetAttribute(adb_select_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    adb_select_kernel<30><<<grid, SEL_THREADS, dyn, stream>>>(P);
-  } else {
-    cudaFuncSetAttribute(adb_select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    adb_select_kernel<0><<<grid, SEL_THREADS, dyn, stream>>>(P);
-  }
-  if (n_launches) (*n_launches)++;
+  P.chunk_begin = chunk_begin; P.chunk_n = chunk_n; P.order = d_order; P.status = d_status;
+  P.c_cap = c_cap; P.layer_cap = max_layers;
+  char* w = (char*)workspace;
+  auto take = [&](size_t bytes) { char* r = w; w += (bytes + 255) & ~(size_t)255; return r; };
+  P.plan = (PrecPlan*)take(sizeof(PrecPlan) * (size_t)chunk_n);
+  P.win_lo = (float*)take(sizeof(float) * (size_t)chunk_n * max_layers);
+  P.win_hi = (float*)take(sizeof(float) * (size_t)chunk_n * max_layers);
+  P.dense = (float*)take(sizeof(float) * (size_t)chunk_n * max_layers * c_cap);
+
+  const int warps_per_block = SEL_PLAN_THREADS / 32;
+  adb_select_plan_kernel<<<(unsigned)((chunk_n + warps_per_block - 1) / warps_per_block), SEL_PLAN_THREADS, 0, stream>>>(P);
+
+  const long long n_items = (long long)chunk_n * max_layers * c_cap;
+  long long blocks = (n_items + (long long)SEL_EXTRACT_THREADS * SEL_ILP - 1) / ((long long)SEL_EXTRACT_THREADS * SEL_ILP);
+  const long long max_blocks = (long long)sm_count * 8 * 64;  // grid-stride beyond this
+  if (blocks > max_blocks) blocks = max_blocks;
+  adb_select_extract_kernel<<<(unsigned)blocks, SEL_EXTRACT_THREADS, 0, stream>>>(P);
+
+  int threads = (((c_cap + 3) / 4 + 31) / 32) * 32;  // 4 adjacent cycles per thread
+  if (threads > 512) threads = 512;
+  if (threads < 32) threads = 32;
+  const size_t dyn = smooth_smem_bytes(c_cap, kw);
+  long long grid = chunk_n;
+  if (grid > (long long)sm_count * 64) grid = (long long)sm_count * 64;
+  if (kw == 30) launch_smooth<30>(P, threads, grid, dyn, stream);
+  else launch_smooth<0>(P, threads, grid, dyn, stream);
+  if (n_launches) (*n_launches) += 3;
 }
