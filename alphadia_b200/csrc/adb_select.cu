@@ -19,10 +19,12 @@
 //                              then columns ascending), log(x + 1) in fp64 rounded to f32, f32 layer sums; then
 //                              warp 0: strict 5-point peaks, top-N (warp arg-max), close-peak suppression,
 //                              symmetric limits, write-out (integer-exact tail).
+#include <algorithm>
+
 #include "adb_common.cuh"
 
 #define FULL 0xffffffffu
-#define SEL_ILP 4
+#define SEL_ILP 2
 #define SEL_MAX_LAYERS (ADB_MAX_LIB_FRAGMENTS + ADB_MAX_ISOTOPES)
 #define SEL_MAX_CAND 16
 #define SEL_PLAN_THREADS 128
@@ -310,101 +312,103 @@ __global__ void __launch_bounds__(SEL_PLAN_THREADS) adb_select_plan_kernel(const
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// XIC extraction (alpharaw_jit.py:398-423).  One cell per item; hits are added in ascending peak order and the
-// observations (cycle positions) in ascending order inside one thread, so the f32 sums are bit-exact.
-__global__ void __launch_bounds__(SEL_EXTRACT_THREADS) adb_select_extract_kernel(const __grid_constant__ SelectParams P) {
+// XIC extraction (alpharaw_jit.py:398-423).  CTA per precursor, one XIC cell per item, layer fastest (neighbouring
+// threads search the same spectrum).  Hits are added in ascending peak order and the observations (cycle
+// positions) in ascending order inside one thread, so the f32 sums are bit-exact.
+__global__ void __launch_bounds__(SEL_EXTRACT_THREADS, 4) adb_select_extract_kernel(const __grid_constant__ SelectParams P) {
   const DevRaw& raw = P.raw;
   const int64_t L = raw.cycle_len;
-  const long long per_prec = (long long)P.layer_cap * P.c_cap;
-  const long long n_items = P.chunk_n * per_prec;
-  const long long stride = (long long)gridDim.x * SEL_EXTRACT_THREADS;
-  for (long long t0 = (long long)blockIdx.x * SEL_EXTRACT_THREADS + threadIdx.x; t0 < n_items; t0 += stride * SEL_ILP) {
-    float lo[SEL_ILP], hi[SEL_ILP], prev_hi[SEL_ILP], acc[SEL_ILP];
-    float* dst[SEL_ILP];
-    const short* posv[SEL_ILP];
-    long long cyc_base[SEL_ILP];
-    int n_o[SEL_ILP];
-    bool ms1[SEL_ILP];
-    int max_o = 0;
+  __shared__ PrecPlan spl;
+  __shared__ float s_lo[SEL_MAX_LAYERS], s_hi[SEL_MAX_LAYERS];
+  for (long long it = blockIdx.x; it < P.chunk_n; it += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) spl = P.plan[it];
+    __syncthreads();
+    if (!spl.ok) continue;
+    const int nF = spl.nF, nL = (int)spl.nF + (int)spl.nI, C = spl.C, nobs = spl.nobs;
+    for (int k = threadIdx.x; k < nL; k += SEL_EXTRACT_THREADS) {
+      s_lo[k] = P.win_lo[it * P.layer_cap + k];
+      s_hi[k] = P.win_hi[it * P.layer_cap + k];
+    }
+    __syncthreads();
+    float* dense = P.dense + it * (long long)P.layer_cap * P.c_cap;
+    const int n_items = nL * C;
+    for (int t0 = threadIdx.x; t0 < n_items; t0 += SEL_EXTRACT_THREADS * SEL_ILP) {
+      float lo[SEL_ILP], hi[SEL_ILP], prev_hi[SEL_ILP], acc[SEL_ILP];
+      int cell[SEL_ILP], n_o[SEL_ILP], cyc[SEL_ILP];
+      bool ms1[SEL_ILP];
+      int max_o = 0;
 #pragma unroll
-    for (int q = 0; q < SEL_ILP; q++) {
-      const long long t = t0 + (long long)q * stride;
-      n_o[q] = 0; acc[q] = 0.f; dst[q] = nullptr; posv[q] = nullptr; lo[q] = 0.f; hi[q] = 0.f; prev_hi[q] = -1.f;
-      cyc_base[q] = 0; ms1[q] = false;
-      if (t < n_items) {
-        const long long it = t / per_prec;
-        const int local = (int)(t - it * per_prec);
-        const int k = local % P.layer_cap, c = local / P.layer_cap;  // layer fastest
-        const PrecPlan& pl = P.plan[it];
-        const int nL = (int)pl.nF + (int)pl.nI;
-        if (pl.ok && k < nL && c < pl.C) {
-          lo[q] = __ldg(P.win_lo + it * P.layer_cap + k);
-          hi[q] = __ldg(P.win_hi + it * P.layer_cap + k);
-          prev_hi[q] = (k > 0 && k != pl.nF) ? __ldg(P.win_hi + it * P.layer_cap + k - 1) : -1.0f;
-          ms1[q] = k >= pl.nF;
-          n_o[q] = ms1[q] ? raw.n_ms1_pos : (int)pl.nobs;
-          posv[q] = pl.pos;
-          cyc_base[q] = ((long long)pl.cs + c) * L;
-          dst[q] = P.dense + (it * P.layer_cap + k) * (long long)P.c_cap + c;
+      for (int q = 0; q < SEL_ILP; q++) {
+        const int t = t0 + q * SEL_EXTRACT_THREADS;
+        n_o[q] = 0; acc[q] = 0.f; cell[q] = -1; lo[q] = 0.f; hi[q] = 0.f; prev_hi[q] = -1.f; cyc[q] = 0; ms1[q] = false;
+        if (t < n_items) {
+          const int k = t % nL, c = t / nL;  // layer fastest
+          lo[q] = s_lo[k]; hi[q] = s_hi[k];
+          prev_hi[q] = (k > 0 && k != nF) ? s_hi[k - 1] : -1.0f;
+          ms1[q] = k >= nF;
+          n_o[q] = ms1[q] ? raw.n_ms1_pos : nobs;
+          cyc[q] = spl.cs + c;
+          cell[q] = k * P.c_cap + c;
           max_o = max(max_o, n_o[q]);
         }
       }
-    }
-    for (int o = 0; o < max_o; o++) {
-      uint32_t l[SEL_ILP], h[SEL_ILP], bend[SEL_ILP];
-      int64_t scan[SEL_ILP];
-#pragma unroll
-      for (int q = 0; q < SEL_ILP; q++) {
-        l[q] = 0; h[q] = 0; bend[q] = 0; scan[q] = 0;
-        if (o < n_o[q]) {
-          scan[q] = (int64_t)(ms1[q] ? raw.ms1_pos[o] : (int)posv[q][o]) + cyc_base[q];
-          const uint2 r = adb_bucket_pair(raw, scan[q], lo[q]);
-          l[q] = r.x; h[q] = r.y; bend[q] = r.y;
-        }
-      }
-      bool any = false;
-#pragma unroll
-      for (int q = 0; q < SEL_ILP; q++) any |= (h[q] - l[q] > 8u);
-      while (any) {  // interleaved binary searches: the SEL_ILP loads of a round are independent
-        any = false;
-        float v[SEL_ILP];
-        uint32_t mid[SEL_ILP];
+      for (int o = 0; o < max_o; o++) {
+        uint32_t l[SEL_ILP], h[SEL_ILP], bend[SEL_ILP];
+        int64_t scan[SEL_ILP];
 #pragma unroll
         for (int q = 0; q < SEL_ILP; q++) {
-          mid[q] = (l[q] + h[q]) >> 1;
-          v[q] = (h[q] - l[q] > 8u) ? __ldg(raw.mz + mid[q]) : 0.f;
+          l[q] = 0; h[q] = 0; bend[q] = 0; scan[q] = 0;
+          if (o < n_o[q]) {
+            scan[q] = (int64_t)(ms1[q] ? raw.ms1_pos[o] : (int)spl.pos[o]) + (int64_t)cyc[q] * L;
+            const uint2 r = adb_bucket_pair(raw, scan[q], lo[q]);
+            l[q] = r.x; h[q] = r.y; bend[q] = r.y;
+          }
+        }
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < SEL_ILP; q++) any |= (h[q] - l[q] > 8u);
+        while (any) {  // interleaved binary searches: the SEL_ILP loads of a round are independent
+          any = false;
+          float v[SEL_ILP];
+          uint32_t mid[SEL_ILP];
+#pragma unroll
+          for (int q = 0; q < SEL_ILP; q++) {
+            mid[q] = (l[q] + h[q]) >> 1;
+            v[q] = (h[q] - l[q] > 8u) ? __ldg(raw.mz + mid[q]) : 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < SEL_ILP; q++)
+            if (h[q] - l[q] > 8u) {
+              if (v[q] < lo[q]) l[q] = mid[q] + 1; else h[q] = mid[q];
+              any |= (h[q] - l[q] > 8u);
+            }
+        }
+        AdbFound f[SEL_ILP];
+#pragma unroll
+        for (int q = 0; q < SEL_ILP; q++) {
+          f[q].idx = 0; f[q].inside = true; f[q].mz_at_idx = 3.0e38f;
+          if (o < n_o[q]) { f[q] = adb_finish_lower_bound(raw.mz, l[q], h[q], lo[q]); f[q].inside = f[q].idx < bend[q]; }
         }
 #pragma unroll
         for (int q = 0; q < SEL_ILP; q++)
-          if (h[q] - l[q] > 8u) {
-            if (v[q] < lo[q]) l[q] = mid[q] + 1; else h[q] = mid[q];
-            any |= (h[q] - l[q] > 8u);
+          if (o < n_o[q]) {
+            // common case: the first candidate peak (still in registers) lies above the window -> no hit
+            if (f[q].inside && !(f[q].mz_at_idx <= hi[q]) && !(prev_hi[q] >= lo[q])) continue;
+            const uint32_t stop = adb_spectrum_stop(raw, scan[q]);
+            uint32_t i2 = f[q].idx;
+            if (prev_hi[q] >= lo[q])
+              while (i2 < stop && __ldg(raw.mz + i2) <= prev_hi[q]) i2++;
+            while (i2 < stop && __ldg(raw.mz + i2) <= hi[q]) {
+              acc[q] = __fadd_rn(acc[q], __ldg(raw.intensity + i2));
+              i2++;
+            }
           }
-      }
-      AdbFound f[SEL_ILP];
-#pragma unroll
-      for (int q = 0; q < SEL_ILP; q++) {
-        f[q].idx = 0; f[q].inside = true; f[q].mz_at_idx = 3.0e38f;
-        if (o < n_o[q]) { f[q] = adb_finish_lower_bound(raw.mz, l[q], h[q], lo[q]); f[q].inside = f[q].idx < bend[q]; }
       }
 #pragma unroll
       for (int q = 0; q < SEL_ILP; q++)
-        if (o < n_o[q]) {
-          // common case: the first candidate peak (still in registers) lies above the window -> no hit
-          if (f[q].inside && !(f[q].mz_at_idx <= hi[q]) && !(prev_hi[q] >= lo[q])) continue;
-          const uint32_t stop = adb_spectrum_stop(raw, scan[q]);
-          uint32_t i2 = f[q].idx;
-          if (prev_hi[q] >= lo[q])
-            while (i2 < stop && __ldg(raw.mz + i2) <= prev_hi[q]) i2++;
-          while (i2 < stop && __ldg(raw.mz + i2) <= hi[q]) {
-            acc[q] = __fadd_rn(acc[q], __ldg(raw.intensity + i2));
-            i2++;
-          }
-        }
+        if (cell[q] >= 0) dense[cell[q]] = acc[q];
     }
-#pragma unroll
-    for (int q = 0; q < SEL_ILP; q++)
-      if (dst[q]) *dst[q] = acc[q];
   }
 }
 
@@ -577,10 +581,7 @@ void adb_launch_select_chunk(const DevRaw& raw, const DevLib& lib, const adb_sel
   const int warps_per_block = SEL_PLAN_THREADS / 32;
   adb_select_plan_kernel<<<(unsigned)((chunk_n + warps_per_block - 1) / warps_per_block), SEL_PLAN_THREADS, 0, stream>>>(P);
 
-  const long long n_items = (long long)chunk_n * max_layers * c_cap;
-  long long blocks = (n_items + (long long)SEL_EXTRACT_THREADS * SEL_ILP - 1) / ((long long)SEL_EXTRACT_THREADS * SEL_ILP);
-  const long long max_blocks = (long long)sm_count * 8 * 64;  // grid-stride beyond this
-  if (blocks > max_blocks) blocks = max_blocks;
+  long long blocks = std::min<long long>(chunk_n, (long long)sm_count * 64);  // CTA per precursor, grid-stride beyond
   adb_select_extract_kernel<<<(unsigned)blocks, SEL_EXTRACT_THREADS, 0, stream>>>(P);
 
   int threads = (((c_cap + 3) / 4 + 31) / 32) * 32;  // 4 adjacent cycles per thread
