@@ -330,3 +330,177 @@ def make_config_3d(name: str, *, seed: int | None = None, n_precursors: int | No
     )
     p["apex_rt"] = apex
     return raw, precursor_df, fragment_df, p
+
+
+# ======================================================================================
+# 4-D (timsTOF shape) runs: TimsTOFTransposeJIT layout
+# (reference alphadia/search/jitclasses/bruker_jit.py:20-137, built at alphadia/raw_data/bruker.py:119-152)
+# ======================================================================================
+@dataclass
+class RawFile4D:
+    cycle: np.ndarray  # f64 [1, Fr, Sc, 2] quad window per (frame in cycle, scan); MS1 frame = (-1, -1)
+    rt_values: np.ndarray  # f64 [n_frames] (frame 0 is the empty "zeroth" frame)
+    mobility_values: np.ndarray  # f64 [Sc], descending
+    mz_values: np.ndarray  # f64 [n_tof] ascending tof -> m/z grid
+    tof_indptr: np.ndarray  # i64 [n_tof + 1]  CSR by tof index
+    push_indices: np.ndarray  # u32 [n_events], ascending inside a tof row; push = frame * Sc + scan
+    intensity_values: np.ndarray  # u16 [n_events]
+    zeroth_frame: int = 1
+    has_mobility: bool = True
+    has_ms1: bool = True
+
+    @property
+    def scan_max_index(self) -> int:
+        return int(self.cycle.shape[2])
+
+    @property
+    def frame_max_index(self) -> int:
+        return int(len(self.rt_values))
+
+    @property
+    def precursor_cycle_max_index(self) -> int:
+        return self.frame_max_index // int(self.cycle.shape[1])
+
+    @property
+    def dia_mz_cycle(self) -> np.ndarray:
+        return np.ascontiguousarray(self.cycle.reshape(-1, 2))
+
+    @property
+    def dia_precursor_cycle(self) -> np.ndarray:
+        fr, sc = self.cycle.shape[1], self.cycle.shape[2]
+        return (np.arange(fr * sc, dtype=np.int64) // sc).astype(np.int64)
+
+    @property
+    def n_events(self) -> int:
+        return int(self.push_indices.shape[0])
+
+
+CONFIGS_4D = {
+    # small case the reference can run on the CPU in seconds (golden vectors)
+    "parity_4d": dict(
+        seed=21, n_precursors=240, n_cycles=90, n_ms2_frames=3, n_scans=96, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=0.6, mob_hi=1.30, mob_lo=0.70, tof_ppm=4.0, mz_lo=150.0, mz_hi=1900.0,
+        noise_per_push=6, rt_tolerance=12.0, mobility_tolerance=0.12, planted_fraction=0.7,
+    ),
+    # config 4 of BASELINE.json: 200k precursors, (1 + 8) x 928 cycle, 800 cycles
+    "config4": dict(
+        seed=4, n_precursors=200_000, n_cycles=800, n_ms2_frames=8, n_scans=928, quad_lo=400.0, quad_hi=1200.0,
+        cycle_seconds=0.95, mob_hi=1.45, mob_lo=0.65, tof_ppm=4.0, mz_lo=150.0, mz_hi=1900.0,
+        noise_per_push=40, rt_tolerance=50.0, mobility_tolerance=0.04, planted_fraction=0.5,
+    ),
+}
+
+
+def make_config_4d(name: str, *, seed: int | None = None, n_precursors: int | None = None, with_strings: bool = True):
+    """(raw4d, precursor_df, fragment_df, params) for a named timsTOF-shape configuration.
+
+    Geometry: every cycle = 1 MS1 frame + ``n_ms2_frames`` diaPASEF frames; each MS2 frame isolates two quadrupole
+    windows, the upper half of the m/z band in the upper-mobility half of the scans and the lower half in the
+    lower-mobility scans (a coarse diaPASEF diagonal).  m/z grid: geometric, ``tof_ppm`` spacing.
+    """
+    p = dict(CONFIGS_4D[name])
+    if seed is not None:
+        p["seed"] = seed
+    if n_precursors is not None:
+        p["n_precursors"] = n_precursors
+    rng = np.random.default_rng(p["seed"])
+    Fr, Sc, ncyc = p["n_ms2_frames"] + 1, p["n_scans"], p["n_cycles"]
+    n_frames = ncyc * Fr + 1  # + zeroth frame
+    frame_s = p["cycle_seconds"] / Fr
+    rt_values = np.concatenate([[0.0], (np.arange(ncyc * Fr) + 1) * frame_s]).astype(np.float64)
+    mobility_values = np.linspace(p["mob_hi"], p["mob_lo"], Sc).astype(np.float64)
+    n_tof = int(np.log(p["mz_hi"] / p["mz_lo"]) / (p["tof_ppm"] * 1e-6)) + 1
+    mz_grid = (p["mz_lo"] * np.exp(np.arange(n_tof) * p["tof_ppm"] * 1e-6)).astype(np.float64)
+
+    # quad windows: MS2 frame f (1-based) covers band f; scans [0, Sc/2) -> upper half of the band, rest -> lower half
+    band = (p["quad_hi"] - p["quad_lo"]) / p["n_ms2_frames"]
+    cycle = np.full((1, Fr, Sc, 2), -1.0, dtype=np.float64)
+    half = Sc // 2
+    for f in range(1, Fr):
+        lo = p["quad_lo"] + band * (f - 1)
+        cycle[0, f, :half, 0], cycle[0, f, :half, 1] = lo + band / 2, lo + band
+        cycle[0, f, half:, 0], cycle[0, f, half:, 1] = lo, lo + band / 2
+
+    # library: precursors live inside one (frame, half) window, mobility inside that half
+    P, F = p["n_precursors"], 12
+    run_s = rt_values[-1]
+    margin = min(60.0, run_s * 0.15)
+    precursor_df, fragment_df = make_library(P, rng, quad_lo=p["quad_lo"], quad_hi=p["quad_hi"], rt_lo=margin,
+                                             rt_hi=run_s - margin, with_strings=with_strings)
+    wf = rng.integers(1, Fr, size=P)
+    wh = rng.integers(0, 2, size=P)
+    wlo = p["quad_lo"] + band * (wf - 1) + np.where(wh == 0, band / 2, 0.0)
+    pmz = (wlo + rng.uniform(0.5, band / 2 - 3.5, size=P)).astype(np.float32)
+    precursor_df["mz_library"] = pmz
+    mob_span = (p["mob_hi"] - p["mob_lo"]) / 2
+    edge = p["mobility_tolerance"] * 1.2
+    mob = np.where(wh == 0, p["mob_hi"] - rng.uniform(edge, mob_span - edge, size=P),
+                   p["mob_hi"] - mob_span - rng.uniform(edge, mob_span - edge, size=P))
+    precursor_df["mobility_library"] = mob.astype(np.float32)
+
+    # ---- events: (tof, push, intensity) -------------------------------------------------------
+    n_push = n_frames * Sc
+    n_noise = int((n_push - Sc) * p["noise_per_push"])
+    ev_push = rng.integers(Sc, n_push, size=n_noise).astype(np.int64)  # frame 0 stays empty
+    ev_tof = rng.integers(0, n_tof, size=n_noise).astype(np.int64)
+    ev_int = np.minimum(rng.exponential(60.0, size=n_noise) + 10.0, 60000.0)
+
+    targets = np.flatnonzero(precursor_df["decoy"].values == 0)
+    n_plant = int(len(targets) * p["planted_fraction"])
+    planted = np.sort(rng.choice(targets, size=n_plant, replace=False)) if n_plant else np.zeros(0, np.int64)
+    apex_rt = np.full(P, np.nan)
+    apex_rt[planted] = precursor_df["rt_library"].values[planted] + rng.normal(0, 1.5, size=n_plant)
+    sig_push, sig_tof, sig_int = [], [], []
+    if n_plant:
+        rt_sigma, scan_sigma = 1.2, 3.0
+        hc = int(np.ceil(3 * rt_sigma / p["cycle_seconds"]))
+        hs = int(np.ceil(2.5 * scan_sigma))
+        c_off = np.arange(-hc, hc + 1)
+        s_off = np.arange(-hs, hs + 1)
+        apex_cycle = np.rint(apex_rt[planted] / p["cycle_seconds"]).astype(np.int64)
+        apex_scan = np.rint((p["mob_hi"] - mob[planted]) / (p["mob_hi"] - p["mob_lo"]) * (Sc - 1)).astype(np.int64)
+        cyc = apex_cycle[:, None, None] + c_off[None, :, None]      # (n, Wc, 1)
+        scn = apex_scan[:, None, None] + s_off[None, None, :]       # (n, 1, Ws)
+        ok = (cyc >= 0) & (cyc < ncyc) & (scn >= 0) & (scn < Sc)
+        shape_s = np.exp(-0.5 * (s_off[None, None, :] / scan_sigma) ** 2)
+        fs = precursor_df["flat_frag_start_idx"].values[planted].astype(np.int64)
+        fmz_all, fint_all = fragment_df["mz_library"].values.astype(np.float64), fragment_df["intensity"].values
+        pch = precursor_df["charge"].values[planted].astype(np.float64)
+
+        def add(frame_in_cycle, mz_target, amp):
+            frame = cyc * Fr + 1 + frame_in_cycle[:, None, None]
+            t = rt_values[np.clip(frame, 0, n_frames - 1)]
+            inten = amp[:, None, None] * np.exp(-0.5 * ((t - apex_rt[planted][:, None, None]) / rt_sigma) ** 2) * shape_s
+            tof = np.rint(np.log(mz_target / p["mz_lo"]) / (p["tof_ppm"] * 1e-6)).astype(np.int64)
+            tof = np.broadcast_to(tof[:, None, None], inten.shape)
+            m = ok & (inten > 12.0) & (tof >= 0) & (tof < n_tof)
+            push = frame * Sc + scn
+            sig_push.append(np.broadcast_to(push, inten.shape)[m])
+            sig_tof.append(tof[m])
+            sig_int.append(np.minimum(inten[m], 60000.0))
+
+        for k in range(F):
+            add(wf[planted], fmz_all[fs + k] * (1 + rng.normal(0, 1.5e-6, size=n_plant)), fint_all[fs + k] * 6000.0)
+        for i, ab in enumerate([0.5, 0.3, 0.15]):
+            add(np.zeros(n_plant, np.int64), (pmz[planted].astype(np.float64) + i * ISOTOPE_MASS_DIFF / pch)
+                * (1 + rng.normal(0, 1.5e-6, size=n_plant)), np.full(n_plant, ab * 20000.0))
+    all_push = np.concatenate([ev_push] + sig_push)
+    all_tof = np.concatenate([ev_tof] + sig_tof)
+    all_int = np.concatenate([ev_int] + sig_int)
+    key = all_tof * np.int64(n_push) + all_push
+    order = np.argsort(key, kind="stable")
+    key, all_int = key[order], all_int[order]
+    # merge duplicate (tof, push) events: detector events are unique per (push, tof)
+    first = np.ones(len(key), dtype=bool)
+    first[1:] = key[1:] != key[:-1]
+    grp = np.cumsum(first) - 1
+    summed = np.bincount(grp, weights=all_int)
+    key = key[first]
+    tof_u = key // n_push
+    push_u = (key % n_push).astype(np.uint32)
+    inten_u = np.minimum(np.rint(summed), 65535).astype(np.uint16)
+    tof_indptr = np.concatenate([[0], np.cumsum(np.bincount(tof_u, minlength=n_tof))]).astype(np.int64)
+    raw = RawFile4D(cycle=cycle, rt_values=rt_values, mobility_values=mobility_values, mz_values=mz_grid,
+                    tof_indptr=tof_indptr, push_indices=np.ascontiguousarray(push_u), intensity_values=inten_u)
+    p["apex_rt"] = apex_rt
+    return raw, precursor_df, fragment_df, p

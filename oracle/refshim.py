@@ -233,6 +233,39 @@ def ref(name: str):
     return importlib.import_module(name)
 
 
+class RefDiaData4D:
+    """Duck-typed DiaData for the reference classes, wrapping a RawFile4D (timsTOF layout).
+
+    Only the fields the hot path reads carry data (cycle, dia_mz_cycle, dia_precursor_cycle, mz_values, tof_indptr,
+    push_indices, intensity_values, rt_values, mobility_values, zeroth_frame, scan/frame_max_index); the remaining
+    constructor arguments of TimsTOFTransposeJIT (bruker_jit.py:56-137) are inert placeholders.
+    """
+
+    def __init__(self, raw):
+        self._raw = raw
+        self.cycle = raw.cycle
+        self.rt_values = raw.rt_values
+        self.mobility_values = raw.mobility_values
+        self.has_mobility = True
+        self.has_ms1 = True
+        self._jit = None
+
+    def to_jitclass(self):
+        if self._jit is None:
+            J = ref("alphadia.search.jitclasses.bruker_jit").TimsTOFTransposeJIT
+            r = self._raw
+            z1f = np.zeros(1, dtype=np.float64)
+            z1i = np.zeros(1, dtype=np.int64)
+            self._jit = J(
+                z1f, r.cycle, r.dia_mz_cycle, r.dia_precursor_cycle, int(r.frame_max_index), z1f, 65535, 0,
+                r.intensity_values, 1.0, float(r.mobility_values.max()), float(r.mobility_values.min()),
+                r.mobility_values, r.mz_values, z1i, 0, z1i, float(r.cycle.max()), float(r.cycle[r.cycle > 0].min()),
+                np.asfortranarray(np.zeros((2, 2), dtype=np.float64)), z1i, r.rt_values, int(r.scan_max_index),
+                int(len(r.mz_values)), 0, bool(r.zeroth_frame), r.push_indices, r.tof_indptr,
+            )
+        return self._jit
+
+
 class RefDiaData:
     """Duck-typed DiaData for the reference classes, wrapping a RawFile3D."""
 

@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from alphadia_b200.synthetic import make_config_3d  # noqa: E402
+from alphadia_b200.synthetic import CONFIGS_4D, make_config_3d, make_config_4d  # noqa: E402
 from oracle import refshim  # noqa: E402
 
 SELECTION_BASE = {
@@ -44,7 +44,9 @@ SCORING_BASE = {
 
 def input_checksum(raw, precursor_df, fragment_df) -> str:
     h = hashlib.sha256()
-    for a in (raw.mz_values, raw.intensity_values, raw.peak_start_idx_list, raw.rt_values,
+    index = raw.tof_indptr if hasattr(raw, "tof_indptr") else raw.peak_start_idx_list
+    extra = (raw.push_indices,) if hasattr(raw, "push_indices") else ()
+    for a in (raw.mz_values, raw.intensity_values, index, raw.rt_values, *extra,
               precursor_df["mz_library"].values, precursor_df["rt_library"].values,
               fragment_df["mz_library"].values, fragment_df["intensity"].values):
         h.update(np.ascontiguousarray(a).tobytes())
@@ -58,9 +60,14 @@ def prepare_library(precursor_df, fragment_df):
 
 
 def run(name: str, threads: int, variants: bool):
-    raw, precursor_df, fragment_df, p = make_config_3d(name)
+    is_4d = name in CONFIGS_4D
+    if is_4d:
+        raw, precursor_df, fragment_df, p = make_config_4d(name)
+        dia = refshim.RefDiaData4D(raw)
+    else:
+        raw, precursor_df, fragment_df, p = make_config_3d(name)
+        dia = refshim.RefDiaData(raw)
     chk = input_checksum(raw, precursor_df, fragment_df)
-    dia = refshim.RefDiaData(raw)
 
     sel_mod = refshim.ref("alphadia.search.selection.selection")
     cfg_mod = refshim.ref("alphadia.search.selection.config_df")
@@ -72,7 +79,8 @@ def run(name: str, threads: int, variants: bool):
 
     # ---------------- selection ----------------
     sel_cfg = cfg_mod.CandidateSelectionConfig()
-    sel_cfg.update({**SELECTION_BASE, "rt_tolerance": float(p["rt_tolerance"]), "mobility_tolerance": 0.1,
+    sel_cfg.update({**SELECTION_BASE, "rt_tolerance": float(p["rt_tolerance"]),
+                    "mobility_tolerance": float(p.get("mobility_tolerance", 0.1)),
                     "candidate_count": 3, "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0})
     sel = sel_mod.CandidateSelection(
         dia, precursor_df.copy(), fragment_df.copy(), sel_cfg,
@@ -126,6 +134,11 @@ def run(name: str, threads: int, variants: bool):
         score({"quant_all": False, "experimental_xic": False}, "_legacy")
         score({"top_k_fragments": 6, "top_k_isotopes": 4, "quant_window": 2}, "_k6")
 
+    if is_4d:  # fragment competition is only applied to non-mobility data (alphadia/fdr/fdr.py:19,157)
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+        return
     # ---------------- fragment competition ------------------
     psm = feat.copy()
     # deterministic pseudo-classifier output: lower proba = better (fdr.py sorts ascending)
