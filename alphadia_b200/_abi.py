@@ -34,6 +34,22 @@ class RawFile3DDesc(C.Structure):
     ]
 
 
+c_u16p = C.POINTER(C.c_uint16)
+
+
+class RawFile4DDesc(C.Structure):
+    _fields_ = [
+        ("cycle", c_f64p), ("frames_per_cycle", C.c_int64), ("scans", C.c_int64),
+        ("dia_precursor_cycle", c_i64p),
+        ("rt_values", c_f64p), ("n_frames", C.c_int64),
+        ("mobility_values", c_f64p),
+        ("mz_values", c_f64p), ("n_tof", C.c_int64),
+        ("tof_indptr", c_i64p), ("push_indices", c_u32p), ("intensity_values", c_u16p), ("n_events", C.c_int64),
+        ("zeroth_frame", C.c_int64), ("precursor_cycle_max_index", C.c_int64),
+        ("scan_max_index", C.c_int64), ("frame_max_index", C.c_int64),
+    ]
+
+
 class LibraryDesc(C.Structure):
     _fields_ = [
         ("n_precursors", C.c_int64),
@@ -102,6 +118,7 @@ class ScoresOut(C.Structure):
 _PTR = {
     np.dtype(np.float32): c_f32p, np.dtype(np.float64): c_f64p, np.dtype(np.int64): c_i64p,
     np.dtype(np.uint32): c_u32p, np.dtype(np.uint8): c_u8p, np.dtype(np.bool_): c_u8p,
+    np.dtype(np.uint16): c_u16p,
 }
 
 
@@ -132,6 +149,34 @@ def make_rawfile3d_desc(raw):
     d.mobility_values = ptr(keep["mob"]); d.n_mobility = len(keep["mob"])
     d.peak_start_idx = ptr(keep["ps"]); d.peak_stop_idx = ptr(keep["pe"])
     d.mz_values = ptr(keep["mz"]); d.intensity_values = ptr(keep["it"]); d.n_peaks = len(keep["mz"])
+    d.zeroth_frame = int(raw.zeroth_frame)
+    d.precursor_cycle_max_index = int(raw.precursor_cycle_max_index)
+    d.scan_max_index = int(raw.scan_max_index)
+    d.frame_max_index = int(raw.frame_max_index)
+    return d, keep
+
+
+def make_rawfile4d_desc(raw):
+    """Descriptor from a RawFile4D-like object (timsTOF layout, see alphadia_b200.raw_data.adapt_dia_data)."""
+    keep = dict(
+        cycle=as_c(raw.cycle, np.float64), dpc=as_c(raw.dia_precursor_cycle, np.int64),
+        rt=as_c(raw.rt_values, np.float64), mob=as_c(raw.mobility_values, np.float64),
+        mz=as_c(raw.mz_values, np.float64), indptr=as_c(raw.tof_indptr, np.int64),
+        push=as_c(raw.push_indices, np.uint32), it=as_c(raw.intensity_values, np.uint16),
+    )
+    cyc = keep["cycle"]
+    if cyc.ndim != 4 or cyc.shape[0] != 1 or cyc.shape[3] != 2:
+        raise ValueError(f"4-D raw file expects cycle of shape (1, frames, scans, 2), got {cyc.shape}")
+    if len(keep["dpc"]) != cyc.shape[1] * cyc.shape[2] or len(keep["mob"]) != cyc.shape[2]:
+        raise ValueError("dia_precursor_cycle / mobility_values do not match the cycle shape")
+    d = RawFile4DDesc()
+    d.cycle = ptr(cyc); d.frames_per_cycle = cyc.shape[1]; d.scans = cyc.shape[2]
+    d.dia_precursor_cycle = ptr(keep["dpc"])
+    d.rt_values = ptr(keep["rt"]); d.n_frames = len(keep["rt"])
+    d.mobility_values = ptr(keep["mob"])
+    d.mz_values = ptr(keep["mz"]); d.n_tof = len(keep["mz"])
+    d.tof_indptr = ptr(keep["indptr"]); d.push_indices = ptr(keep["push"]); d.intensity_values = ptr(keep["it"])
+    d.n_events = len(keep["push"])
     d.zeroth_frame = int(raw.zeroth_frame)
     d.precursor_cycle_max_index = int(raw.precursor_cycle_max_index)
     d.scan_max_index = int(raw.scan_max_index)

@@ -58,6 +58,28 @@ typedef struct {
   int64_t frame_max_index;           /* n_spectra - 1 */
 } adb_rawfile3d_desc;
 
+/* ---- raw file, 4-D (RT x ion mobility x m/z), the TimsTOFTransposeJIT fields the hot path reads
+ *      (alphadia/search/jitclasses/bruker_jit.py:20-137; CSR by tof index, built by raw_data/bruker.py:202-274) */
+typedef struct {
+  const double* cycle;                /* f64 [1, frames_per_cycle, scans, 2] quad window per (frame in cycle, scan) */
+  int64_t frames_per_cycle;           /* cycle.shape[1] */
+  int64_t scans;                      /* cycle.shape[2] */
+  const int64_t* dia_precursor_cycle; /* i64 [frames_per_cycle * scans] observation id of every cycle position */
+  const double* rt_values;            /* f64 [n_frames] */
+  int64_t n_frames;
+  const double* mobility_values;      /* f64 [scans], descending */
+  const double* mz_values;            /* f64 [n_tof] */
+  int64_t n_tof;
+  const int64_t* tof_indptr;          /* i64 [n_tof + 1] */
+  const uint32_t* push_indices;       /* u32 [n_events], ascending inside a tof row; push = frame * scan_max_index + scan */
+  const uint16_t* intensity_values;   /* u16 [n_events] */
+  int64_t n_events;
+  int64_t zeroth_frame;               /* 0/1 */
+  int64_t precursor_cycle_max_index;  /* frame_max_index / frames_per_cycle */
+  int64_t scan_max_index;
+  int64_t frame_max_index;
+} adb_rawfile4d_desc;
+
 /* ---- spectral library (flat), precursors sorted by precursor_idx -------------------------- */
 typedef struct {
   int64_t n_precursors;

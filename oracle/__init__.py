@@ -126,3 +126,29 @@ def fragment_competition(window_start, window_stop, rt, frag_start, frag_stop, f
     if rc != 0:
         raise RuntimeError("oracle fragcomp failed")
     return v.astype(bool)
+
+
+def select_candidates_4d(raw4d, lib_arrays, cfg_struct, kernel, n_threads=0):
+    """Oracle selection on a timsTOF-layout raw file."""
+    L = lib()
+    rd, k1 = _abi.make_rawfile4d_desc(raw4d)
+    ld, k2 = _abi.make_library_desc(lib_arrays)
+    od, arrs = _abi.alloc_candidates_out(int(ld.n_precursors * cfg_struct.candidate_count))
+    kernel = np.ascontiguousarray(kernel, dtype=np.float32)
+    rc = L.adbo_select_candidates_4d(C.byref(rd), C.byref(ld), C.byref(cfg_struct), _abi.ptr(kernel),
+                                     C.c_int32(kernel.shape[0]), C.c_int32(kernel.shape[1]), C.byref(od), C.c_int32(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle 4-D selection failed rc={rc}")
+    return arrs
+
+
+def score_candidates_4d(raw4d, lib_arrays, cfg_struct, cand_in_struct, n_threads=0):
+    L = lib()
+    rd, k1 = _abi.make_rawfile4d_desc(raw4d)
+    ld, k2 = _abi.make_library_desc(lib_arrays)
+    od, arrs = _abi.alloc_scores_out(int(cand_in_struct.n), int(cfg_struct.top_k_fragments))
+    rc = L.adbo_score_candidates_4d(C.byref(rd), C.byref(ld), C.byref(cfg_struct), C.byref(cand_in_struct), C.byref(od),
+                                    C.c_int32(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle 4-D scoring failed rc={rc}")
+    return arrs

@@ -667,10 +667,21 @@ typedef struct {
   int64_t F, nobs, C, I;
 } adbo_scoring_tap;
 
-static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib, const adb_scoring_config* cfg,
+/* raw-file view shared by the 3-D and 4-D scoring paths */
+typedef struct {
+  const adb_rawfile3d_desc* r3; /* exactly one of r3 / r4 is set */
+  const adb_rawfile4d_desc* r4;
+} rawview;
+
+static int extract_cubes_4d(const adb_rawfile4d_desc* raw, int64_t frame_start, int64_t frame_stop, int64_t scan_start,
+                            int64_t scan_stop, const float* mz, int n_q, float tol, float q0, float q1, float** out_i,
+                            float** out_m, int64_t* C_out, int64_t** obs_out);
+
+static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_scoring_config* cfg,
                       const adb_candidates_in* cand, int64_t ci, adb_scores_out* out, adbo_scoring_tap* tap) {
+  const adb_rawfile3d_desc* raw = rv->r3;
+  const adb_rawfile4d_desc* raw4 = rv->r4;
   const int K = (int)cfg->top_k_fragments;
-  const int S = 2;
   int64_t p = cand->lib_row[ci];
   float* feat = out->features + (size_t)ci * ADB_NUM_FEATURES;
 
@@ -713,76 +724,115 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
 
   int64_t frame_start = cand->frame_start[ci], frame_stop = cand->frame_stop[ci], frame_center = cand->frame_center[ci];
   int64_t scan_start = cand->scan_start[ci], scan_stop = cand->scan_stop[ci], scan_center = cand->scan_center[ci];
-  int64_t L = raw->cycle_len;
+  const int64_t L = raw4 ? raw4->frames_per_cycle : raw->cycle_len;
+  /* a 3-D file is carried as 2 identical scans (alpharaw_jit.py:205-206); a 4-D cube spans the candidate's scans */
+  const int S = raw4 ? (int)(scan_stop - scan_start) : 2;
+  if (S <= 0) return;
 
   /* candidate.py:203-205 quadrupole limit (float32 of float64 arithmetic) */
   float mn = iso_mz[0], mx = iso_mz[0];
   for (int j = 1; j < nI; j++) { if (iso_mz[j] < mn) mn = iso_mz[j]; if (iso_mz[j] > mx) mx = iso_mz[j]; }
   float q0 = (float)((double)mn - 0.5), q1 = (float)((double)mx + 0.5);
 
-  /* candidate.py:216-246 dense cubes */
+  /* candidate.py:216-246 dense cubes, always carried as [..][S][C] from here on */
   float lo[ADB_MAX_FRAGMENTS], hi[ADB_MAX_FRAGMENTS];
-  int64_t* pos_f = (int64_t*)malloc(sizeof(int64_t) * (size_t)L);
-  int64_t* pos_p = (int64_t*)malloc(sizeof(int64_t) * (size_t)L);
-  float *dfi, *dfm, *dpi_raw, *dpm_raw;
-  int64_t C, C2;
-  mass_range_f32tol(fr.mz, fr.n, cfg->fragment_mz_tolerance, lo, hi);
-  int nobs = get_dense_abs(raw, frame_start, frame_stop, lo, hi, fr.n, q0, q1, &dfi, &dfm, &C, pos_f);
-  if (C == 0 || fr.n <= 1) { free(dfi); free(dfm); free(pos_f); free(pos_p); return; } /* candidate.py:230-237 */
-  mass_range_f32tol(iso_mz, nI, cfg->precursor_mz_tolerance, lo, hi);
-  int nobs_p = get_dense_abs(raw, frame_start, frame_stop, lo, hi, nI, -1.0f, -1.0f, &dpi_raw, &dpm_raw, &C2, pos_p);
-
   int F = fr.n;
-  /* candidate.py:248-269 collapse MS1 observations.  dp*: [I][C] (scan rows identical) */
-  float* dpi = (float*)calloc((size_t)nI * (size_t)C, sizeof(float));
-  float* dpm = (float*)calloc((size_t)nI * (size_t)C, sizeof(float));
-  for (int i = 0; i < nI; i++)
-    for (int64_t c = 0; c < C; c++) {
-      float s32 = 0; double sm = 0; int count = 0;
-      for (int j = 0; j < nobs_p; j++) {
-        size_t cell = ((size_t)i * nobs_p + j) * C + c;
-        s32 = s32 + dpi_raw[cell];
-        sm += (double)dpm_raw[cell];
-        if (dpm_raw[cell] > 0) count++;
+  int64_t C = 0;
+  int nobs = 0;
+  int64_t* pos_f = NULL; /* observation ids: cycle positions (3-D) / dia_precursor_cycle values (4-D) */
+  float *dfi2 = NULL, *dfm2 = NULL, *dpi = NULL, *dpm = NULL;
+  if (raw4) {
+    int64_t* pos_p = NULL;
+    float *dpi_raw = NULL, *dpm_raw = NULL;
+    int64_t C2 = 0;
+    nobs = extract_cubes_4d(raw4, frame_start, frame_stop, scan_start, scan_stop, fr.mz, F, cfg->fragment_mz_tolerance, q0, q1,
+                            &dfi2, &dfm2, &C, &pos_f);
+    if (nobs <= 0 || C <= 0 || F <= 1) { free(dfi2); free(dfm2); free(pos_f); return; } /* candidate.py:230-237 */
+    int nobs_p = extract_cubes_4d(raw4, frame_start, frame_stop, scan_start, scan_stop, iso_mz, nI, cfg->precursor_mz_tolerance,
+                                  -1.0f, -1.0f, &dpi_raw, &dpm_raw, &C2, &pos_p);
+    if (nobs_p <= 0) { free(dfi2); free(dfm2); free(pos_f); free(dpi_raw); free(dpm_raw); free(pos_p); return; }
+    /* candidate.py:248-269 collapse MS1 observations */
+    dpi = (float*)calloc((size_t)nI * S * C, sizeof(float));
+    dpm = (float*)calloc((size_t)nI * S * C, sizeof(float));
+    for (int i = 0; i < nI; i++)
+      for (int sc = 0; sc < S; sc++)
+        for (int64_t c = 0; c < C; c++) {
+          float s32 = 0; double sm = 0; int count = 0;
+          for (int j = 0; j < nobs_p; j++) {
+            size_t cell = ((((size_t)i * nobs_p + j) * S) + sc) * C + c;
+            s32 = s32 + dpi_raw[cell];
+            sm += (double)dpm_raw[cell];
+            if (dpm_raw[cell] > 0) count++;
+          }
+          dpi[((size_t)i * S + sc) * C + c] = s32;
+          dpm[((size_t)i * S + sc) * C + c] = (float)(sm / ((double)count + 1e-6));
+        }
+    free(dpi_raw); free(dpm_raw); free(pos_p);
+  } else {
+    pos_f = (int64_t*)malloc(sizeof(int64_t) * (size_t)L);
+    int64_t* pos_p = (int64_t*)malloc(sizeof(int64_t) * (size_t)L);
+    float *dfi, *dfm, *dpi_raw, *dpm_raw;
+    int64_t C2;
+    mass_range_f32tol(fr.mz, fr.n, cfg->fragment_mz_tolerance, lo, hi);
+    nobs = get_dense_abs(raw, frame_start, frame_stop, lo, hi, fr.n, q0, q1, &dfi, &dfm, &C, pos_f);
+    if (C == 0 || fr.n <= 1) { free(dfi); free(dfm); free(pos_f); free(pos_p); return; } /* candidate.py:230-237 */
+    mass_range_f32tol(iso_mz, nI, cfg->precursor_mz_tolerance, lo, hi);
+    int nobs_p = get_dense_abs(raw, frame_start, frame_stop, lo, hi, nI, -1.0f, -1.0f, &dpi_raw, &dpm_raw, &C2, pos_p);
+    /* candidate.py:248-269 collapse MS1 observations; both scan rows are identical (alpharaw_jit.py:326-333) */
+    dpi = (float*)calloc((size_t)nI * S * C, sizeof(float));
+    dpm = (float*)calloc((size_t)nI * S * C, sizeof(float));
+    for (int i = 0; i < nI; i++)
+      for (int64_t c = 0; c < C; c++) {
+        float s32 = 0; double sm = 0; int count = 0;
+        for (int j = 0; j < nobs_p; j++) {
+          size_t cell = ((size_t)i * nobs_p + j) * C + c;
+          s32 = s32 + dpi_raw[cell];
+          sm += (double)dpm_raw[cell];
+          if (dpm_raw[cell] > 0) count++;
+        }
+        for (int sc = 0; sc < S; sc++) {
+          dpi[((size_t)i * S + sc) * C + c] = s32;
+          dpm[((size_t)i * S + sc) * C + c] = (float)(sm / ((double)count + 1e-6));
+        }
       }
-      dpi[(size_t)i * C + c] = s32;
-      dpm[(size_t)i * C + c] = (float)(sm / ((double)count + 1e-6));
-    }
-  free(dpi_raw); free(dpm_raw);
-
-  if (tap && tap->candidate == ci) {
-    tap->F = F; tap->nobs = nobs; tap->C = C; tap->I = nI;
-    size_t nf = (size_t)F * nobs * C;
-    if ((int64_t)(2 * nf) <= tap->capacity) { memcpy(tap->dense_fragments, dfi, 4 * nf); memcpy(tap->dense_fragments + nf, dfm, 4 * nf); }
-    size_t np_ = (size_t)nI * C;
-    if ((int64_t)(2 * np_) <= tap->capacity) { memcpy(tap->dense_precursors, dpi, 4 * np_); memcpy(tap->dense_precursors + np_, dpm, 4 * np_); }
+    free(dpi_raw); free(dpm_raw); free(pos_p);
+    dfi2 = (float*)malloc(sizeof(float) * (size_t)F * (nobs > 0 ? nobs : 1) * S * C);
+    dfm2 = (float*)malloc(sizeof(float) * (size_t)F * (nobs > 0 ? nobs : 1) * S * C);
+    for (int f = 0; f < F; f++)
+      for (int o = 0; o < nobs; o++)
+        for (int sc = 0; sc < S; sc++)
+          for (int64_t c = 0; c < C; c++) {
+            size_t src = ((size_t)f * nobs + o) * C + c;
+            size_t dst = (((size_t)f * nobs + o) * S + sc) * C + c;
+            dfi2[dst] = dfi[src];
+            dfm2[dst] = dfm[src];
+          }
+    free(dfi); free(dfm);
   }
+  (void)tap;
 
   /* candidate.py:279-284 + quadrupole.py:80-115,261-301: qtf[i][o][s'] with s' over arange(scan_start, scan_stop) */
   int nsc = (int)(scan_stop - scan_start);
   int fail = 0;
   if (!(nsc == 1 || nsc == S) || nobs == 0) fail = 1; /* numba would raise a broadcast error; row stays invalid */
-  int64_t cyc_S = 1; /* cycle.shape[2] for 3-D files */
+  const int64_t cyc_S = raw4 ? raw4->scans : 1; /* cycle.shape[2] */
+  const double* cyc = raw4 ? raw4->cycle : raw->cycle;
   double* qtf = (double*)calloc((size_t)nI * (size_t)(nobs > 0 ? nobs : 1) * (size_t)(nsc > 0 ? nsc : 1), sizeof(double));
   if (!fail)
     for (int i = 0; i < nI; i++)
       for (int o = 0; o < nobs; o++)
         for (int s = 0; s < nsc; s++) {
           int64_t sc = scan_start + s;
-          if (sc >= cyc_S) { fail = 1; continue; }
-          double mu1 = raw->cycle[(pos_f[o] * cyc_S + sc) * 2 + 0] + cfg->quad_delta_mu[0];
-          double mu2 = raw->cycle[(pos_f[o] * cyc_S + sc) * 2 + 1] + cfg->quad_delta_mu[1];
+          if (sc >= cyc_S || sc < 0) { fail = 1; continue; }
+          double mu1 = cyc[(pos_f[o] * cyc_S + sc) * 2 + 0] + cfg->quad_delta_mu[0];
+          double mu2 = cyc[(pos_f[o] * cyc_S + sc) * 2 + 1] + cfg->quad_delta_mu[1];
           double x = (double)iso_mz[i];
           double a1 = (x - mu1) / cfg->quad_sigma[0], a2 = (x - mu2) / cfg->quad_sigma[1];
           qtf[((size_t)i * nobs + o) * nsc + s] = 1 / (1 + exp(-a1)) - 1 / (1 + exp(-a2));
         }
-  if (fail) { free(qtf); free(dfi); free(dfm); free(dpi); free(dpm); free(pos_f); free(pos_p); return; }
+  if (fail) { free(qtf); free(dfi2); free(dfm2); free(dpi); free(dpm); free(pos_f); return; }
 
-  /* From here on the S = 2 scan rows of a 3-D cube are kept explicitly only where the reference's
-   * arithmetic depends on them.  qtf_mask (candidate.py:287-290) broadcasts over scans when nsc == 1. */
-  /* dense_fragments[0] *= qtf_mask */
-  float* dfi2 = (float*)malloc(sizeof(float) * (size_t)F * nobs * S * C); /* [F][nobs][S][C] */
-  float* dfm2 = (float*)malloc(sizeof(float) * (size_t)F * nobs * S * C);
+  /* dense_fragments[0] *= qtf_mask (candidate.py:287-290); the mask broadcasts over scans when nsc == 1 */
   for (int f = 0; f < F; f++)
     for (int o = 0; o < nobs; o++)
       for (int s = 0; s < S; s++) {
@@ -791,13 +841,10 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
         for (int i = 0; i < nI; i++) m += qtf[((size_t)i * nobs + o) * nsc + sq];
         float mask = (float)(m / (double)nI);
         for (int64_t c = 0; c < C; c++) {
-          size_t src = ((size_t)f * nobs + o) * C + c;
           size_t dst = (((size_t)f * nobs + o) * S + s) * C + c;
-          dfi2[dst] = dfi[src] * mask;
-          dfm2[dst] = dfm[src];
+          dfi2[dst] = dfi2[dst] * mask;
         }
       }
-  free(dfi); free(dfm);
 
   /* quadrupole.py:304-324 template[o][s][c] */
   float* tmpl = (float*)malloc(sizeof(float) * (size_t)nobs * S * C);
@@ -806,13 +853,11 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
       int sq = nsc == 1 ? 0 : s;
       for (int64_t c = 0; c < C; c++) {
         double t = 0;
-        for (int i = 0; i < nI; i++) t += (double)(float)(dpi[(size_t)i * C + c] * iso_int[i]) * qtf[((size_t)i * nobs + o) * nsc + sq];
+        for (int i = 0; i < nI; i++) t += (double)(float)(dpi[((size_t)i * S + s) * C + c] * iso_int[i]) * qtf[((size_t)i * nobs + o) * nsc + sq];
         tmpl[((size_t)o * S + s) * C + c] = (float)t;
       }
     }
   free(qtf);
-  if (tap && tap->candidate == ci && (int64_t)nobs * C <= tap->capacity)
-    for (int o = 0; o < nobs; o++) memcpy(tap->template_ + (size_t)o * C, tmpl + (size_t)o * S * C, 4 * (size_t)C);
 
   /* quadrupole.py:327-335 observation importance (float32) */
   float* oi = (float*)malloc(sizeof(float) * (size_t)nobs);
@@ -839,7 +884,7 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
     }
     fmask[f] = t_o > 0; Fv += fmask[f];
   }
-  if (Fv < 2) { free(dfi2); free(dfm2); free(tmpl); free(oi); free(dpi); free(dpm); free(pos_f); free(pos_p); return; }
+  if (Fv < 2) { free(dfi2); free(dfm2); free(tmpl); free(oi); free(dpi); free(dpm); free(pos_f); return; }
 
   /* compact cubes + fragment_container.py:104-120 apply_mask (renormalise intensities) */
   {
@@ -878,24 +923,30 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
   }
   or_envelope_rows(tfp, nobs, (int)C);
   or_envelope_rows(tsp, nobs, S);
-  (void)fsp; (void)tsp; /* only consumed by the has_mobility features */
 
   float fa[ADB_NUM_FEATURES];
   memset(fa, 0, sizeof(fa));
   fa[28] = (float)((double)Fv / (double)Fall); /* candidate.py:362 */
 
   /* features/location_features.py:9-33 */
-  fa[0] = raw->mobility_values[scan_start] - raw->mobility_values[scan_stop - 1];
-  fa[1] = raw->rt_values[frame_stop - 1] - raw->rt_values[frame_start];
-  fa[2] = raw->rt_values[frame_center];
-  fa[3] = raw->mobility_values[scan_center];
+  if (raw4) { /* float64 arrays in the timsTOF view */
+    fa[0] = (float)(raw4->mobility_values[scan_start] - raw4->mobility_values[scan_stop - 1]);
+    fa[1] = (float)(raw4->rt_values[frame_stop - 1] - raw4->rt_values[frame_start]);
+    fa[2] = (float)raw4->rt_values[frame_center];
+    fa[3] = (float)raw4->mobility_values[scan_center];
+  } else {
+    fa[0] = raw->mobility_values[scan_start] - raw->mobility_values[scan_stop - 1];
+    fa[1] = raw->rt_values[frame_stop - 1] - raw->rt_values[frame_start];
+    fa[2] = raw->rt_values[frame_center];
+    fa[3] = raw->mobility_values[scan_center];
+  }
 
   /* ---------------- features/precursor_features.py:14-102 ---------------- */
   {
     float spi[ADB_MAX_ISOTOPES]; /* sum_precursor_intensity [I][1] */
     for (int i = 0; i < nI; i++) {
       float t_s = 0;
-      for (int s = 0; s < S; s++) { float t_c = 0; for (int64_t c = 0; c < C; c++) t_c = t_c + dpi[(size_t)i * C + c]; t_s = t_s + t_c; }
+      for (int s = 0; s < S; s++) { float t_c = 0; for (int64_t c = 0; c < C; c++) t_c = t_c + dpi[((size_t)i * S + s) * C + c]; t_s = t_s + t_c; }
       spi[i] = t_s;
     }
     float wspi[ADB_MAX_ISOTOPES];
@@ -908,14 +959,10 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
     { float t = 0; for (int i = 0; i < nI; i++) t = t + wspi[i] * iso_int[i]; fa[7] = t; }
     /* precursor_features.py:52-65: "centres" are the sizes (n_scans, n_observations = 1) */
     double H[ADB_MAX_ISOTOPES], MZo[ADB_MAX_ISOTOPES];
-    float* cube = (float*)malloc(sizeof(float) * (size_t)S * C);
     for (int i = 0; i < nI; i++) {
-      for (int s = 0; s < S; s++) memcpy(cube + (size_t)s * C, dpi + (size_t)i * C, 4 * (size_t)C);
-      H[i] = weighted_center_mean(cube, S, (int)C, (double)S, 1.0);
-      for (int s = 0; s < S; s++) memcpy(cube + (size_t)s * C, dpm + (size_t)i * C, 4 * (size_t)C);
-      MZo[i] = weighted_center_mean(cube, S, (int)C, (double)S, 1.0);
+      H[i] = weighted_center_mean(dpi + (size_t)i * S * C, S, (int)C, (double)S, 1.0);
+      MZo[i] = weighted_center_mean(dpm + (size_t)i * S * C, S, (int)C, (double)S, 1.0);
     }
-    free(cube);
     double wme = 0;
     for (int i = 0; i < nI; i++) if (MZo[i] > 0) {
       double me = (MZo[i] - (double)iso_mz[i]) / (double)iso_mz[i] * 1e6;
@@ -973,9 +1020,14 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
     for (int f = 0; f < F; f++) {
       double area = 0;
       for (int64_t t = 0; t + 1 < wn; t++) {
-        float drt = raw->rt_values[frame_start + (w0 + t + 1) * L] - raw->rt_values[frame_start + (w0 + t) * L];
         float sum2 = bp[(size_t)f * C + w0 + t + 1] + bp[(size_t)f * C + w0 + t];
-        area += (double)(float)(sum2 * drt) * 0.5;
+        if (raw4) { /* float64 rt: (f32 + f32) * f64 * 0.5 */
+          double drt = raw4->rt_values[frame_start + (w0 + t + 1) * L] - raw4->rt_values[frame_start + (w0 + t) * L];
+          area += (double)sum2 * drt * 0.5;
+        } else {
+          float drt = raw->rt_values[frame_start + (w0 + t + 1) * L] - raw->rt_values[frame_start + (w0 + t) * L];
+          area += (double)(float)(sum2 * drt) * 0.5;
+        }
       }
       area_norm[f] = area * (double)qw;
       float t = 0;
@@ -1083,6 +1135,55 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
     }
   }
 
+  /* ---------------- features/fragment_features.py:430-480 fragment_mobility_correlation (has_mobility) ------- */
+  if (raw4) {
+    int idx[ADB_MAX_FRAGMENTS], nz = 0;
+    for (int f = 0; f < F; f++) {
+      float t_o = 0;
+      for (int o = 0; o < nobs; o++) { float t_s = 0; for (int sc = 0; sc < S; sc++) t_s = t_s + fsp[((size_t)f * nobs + o) * S + sc]; t_o = t_o + t_s; }
+      if (t_o > 0) idx[nz++] = f;
+    }
+    if (nz >= 3) {
+      float norm[ADB_MAX_FRAGMENTS];
+      { float t = 0; for (int a = 0; a < nz; a++) t = t + fr.intensity[idx[a]]; for (int a = 0; a < nz; a++) norm[a] = fr.intensity[idx[a]] / t; }
+      float* red = (float*)calloc((size_t)nz * nz, sizeof(float));
+      float* cen = (float*)malloc(sizeof(float) * (size_t)nz * S);
+      float stdv[ADB_MAX_FRAGMENTS];
+      for (int o = 0; o < nobs; o++) { /* scoring/utils.py:513-571 fragment_correlation on the scan profiles */
+        for (int a = 0; a < nz; a++) {
+          const float* r = fsp + ((size_t)idx[a] * nobs + o) * S;
+          float sm = 0; for (int sc = 0; sc < S; sc++) sm = sm + r[sc];
+          float mean = sm / (float)S;
+          float ss = 0;
+          for (int sc = 0; sc < S; sc++) { cen[(size_t)a * S + sc] = r[sc] - mean; ss = ss + cen[(size_t)a * S + sc] * cen[(size_t)a * S + sc]; }
+          stdv[a] = sqrtf(ss / (float)S);
+        }
+        for (int a = 0; a < nz; a++)
+          for (int b = 0; b < nz; b++) {
+            float dot = 0;
+            for (int sc = 0; sc < S; sc++) dot = dot + cen[(size_t)a * S + sc] * cen[(size_t)b * S + sc];
+            float cov = dot / (float)S;
+            float smx = stdv[a] * stdv[b];
+            float corr = (float)((double)cov / ((double)smx + 1e-12));
+            red[(size_t)a * nz + b] = red[(size_t)a * nz + b] + corr * oi[o];
+          }
+      }
+      float lsum = 0;
+      for (int a = 0; a < nz; a++) { float t = 0; for (int b = 0; b < nz; b++) t = t + red[(size_t)a * nz + b] * norm[b]; lsum = lsum + t; }
+      fa[29] = (float)((double)lsum / (double)nz);
+      free(red); free(cen);
+      /* template scan correlation: fragment_correlation_different against the template scan profile */
+      float* sub = (float*)malloc(sizeof(float) * (size_t)nz * nobs * S);
+      for (int a = 0; a < nz; a++) memcpy(sub + (size_t)a * nobs * S, fsp + (size_t)idx[a] * nobs * S, sizeof(float) * (size_t)nobs * S);
+      float* ct = (float*)malloc(sizeof(float) * (size_t)nobs * nz);
+      corr_with_template(sub, tsp, nz, nobs, S, ct);
+      float t30 = 0;
+      for (int a = 0; a < nz; a++) { float r = 0; for (int o = 0; o < nobs; o++) r = r + ct[(size_t)o * nz + a] * oi[o]; t30 = t30 + r * norm[a]; }
+      fa[30] = t30;
+      free(sub); free(ct);
+    }
+  }
+
   /* ---------------- features/profile_features.py:18-206 ---------------- */
   float corr_list[ADB_MAX_FRAGMENTS];
   {
@@ -1183,7 +1284,8 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
     }
     /* profile_features.py:117-146 cycle_fwhm */
     {
-      float rt_width = raw->rt_values[frame_stop - 1] - raw->rt_values[frame_start];
+      const double rt_width = raw4 ? raw4->rt_values[frame_stop - 1] - raw4->rt_values[frame_start]
+                                   : (double)(float)(raw->rt_values[frame_stop - 1] - raw->rt_values[frame_start]);
       float agg = 0;
       for (int f = 0; f < F; f++) {
         float ml = 0;
@@ -1200,6 +1302,26 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
         agg = agg + ml * fr.intensity[f];
       }
       fa[38] = agg;
+    }
+    /* profile_features.py:148-188 mobility_fwhm (has_mobility only) */
+    if (raw4) {
+      const double mobility_width = raw4->mobility_values[scan_start] - raw4->mobility_values[scan_stop - 1];
+      float agg = 0;
+      for (int f = 0; f < F; f++) {
+        float ml = 0;
+        for (int o = 0; o < nobs; o++) {
+          const float* r = fsp + ((size_t)f * nobs + o) * S;
+          float mxv = r[0];
+          for (int sc = 1; sc < S; sc++) if (r[sc] > mxv) mxv = r[sc];
+          double half = (double)mxv / 2;
+          int na = 0;
+          for (int sc = 0; sc < S; sc++) if ((double)r[sc] > half) na++;
+          float fw = (float)(((double)na / (double)S) * mobility_width);
+          ml = ml + fw * oi[o];
+        }
+        agg = agg + ml * fr.intensity[f];
+      }
+      fa[39] = agg;
     }
     /* profile_features.py:190-204 delta_frame_peak */
     {
@@ -1241,7 +1363,7 @@ static void score_one(const adb_rawfile3d_desc* raw, const adb_library_desc* lib
   memcpy(feat, fa, sizeof(fa));
   out->valid[ci] = 1;
 
-  free(dfi2); free(dfm2); free(tmpl); free(oi); free(dpi); free(dpm); free(pos_f); free(pos_p);
+  free(dfi2); free(dfm2); free(tmpl); free(oi); free(dpi); free(dpm); free(pos_f);
   free(ffp); free(fsp); free(tfp); free(tsp);
 }
 
@@ -1264,8 +1386,9 @@ int adbo_score_candidates(const adb_rawfile3d_desc* raw, const adb_library_desc*
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
+  rawview rv = {raw, NULL};
 #pragma omp parallel for schedule(dynamic, 16)
-  for (int64_t ci = 0; ci < cand->n; ci++) score_one(raw, lib, cfg, cand, ci, out, tap);
+  for (int64_t ci = 0; ci < cand->n; ci++) score_one(&rv, lib, cfg, cand, ci, out, tap);
   return 0;
 }
 
@@ -1344,4 +1467,384 @@ int adbo_num_threads(void) {
 #else
   return 1;
 #endif
+}
+
+
+/* ==========================================================================================
+ * 4-D (timsTOF) raw files — alphadia/search/jitclasses/bruker_jit.py
+ * ======================================================================================== */
+
+static int64_t searchsorted_left_f64(const double* a, int64_t n, double v) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+/* utils.py:24-88 get_frame_indices on float64 rt_values (bruker_jit.py:172-202); limits are float32 */
+static void get_frame_indices_tolerance_4d(const adb_rawfile4d_desc* raw, float rt, double tolerance, int64_t optimize_size,
+                                           int64_t min_size, int64_t out[2]) {
+  float lim[2] = {(float)((double)rt - tolerance), (float)((double)rt + tolerance)};
+  int64_t fi0 = searchsorted_left_f64(raw->rt_values, raw->n_frames, (double)lim[0]);
+  int64_t fi1 = searchsorted_left_f64(raw->rt_values, raw->n_frames, (double)lim[1]);
+  int64_t L = raw->frames_per_cycle;
+  int64_t c0 = (fi0 + raw->zeroth_frame) / L, c1 = (fi1 + raw->zeroth_frame) / L;
+  int64_t len = c1 - c0;
+  int64_t opt = len > min_size ? len : min_size;
+  opt = (int64_t)((double)optimize_size * ceil((double)opt / (double)optimize_size));
+  int64_t l0 = c0, l1 = c0 + opt;
+  int64_t pcmi = raw->precursor_cycle_max_index;
+  if (l1 > pcmi) { l1 = pcmi; l0 = pcmi - opt; if (l0 < 0) l0 = (pcmi % 2 == 0) ? 0 : 1; }
+  out[0] = l0 * L + raw->zeroth_frame;
+  out[1] = l1 * L + raw->zeroth_frame;
+}
+
+/* bruker_jit.py:204-271 get_scan_indices_tolerance: searchsorted(mobility_values[::-1], v, "right") */
+static void get_scan_indices_tolerance_4d(const adb_rawfile4d_desc* raw, float mobility, double tolerance,
+                                          int64_t optimize_size, int64_t out[2]) {
+  float lim[2] = {(float)((double)mobility + tolerance), (float)((double)mobility - tolerance)};
+  int64_t n = raw->scans, si[2];
+  for (int k = 0; k < 2; k++) { /* "right" on the ascending reversed array */
+    double v = (double)lim[k];
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (raw->mobility_values[n - 1 - mid] <= v) lo = mid + 1; else hi = mid; }
+    si[k] = raw->scan_max_index - lo;
+  }
+  int64_t scan_len = si[0] - si[1];
+  int64_t opt = (int64_t)((double)optimize_size * ceil((double)scan_len / (double)optimize_size));
+  int64_t l0 = si[0], l1 = si[0] - opt;
+  if (l1 < 0) { l1 = 0; l0 = opt; if (l0 > raw->scan_max_index) l0 = raw->scan_max_index; }
+  out[0] = l0; out[1] = l1;
+}
+
+/* push query of bruker_jit.py:315-350 as a predicate + the observation id of a push */
+typedef struct {
+  int64_t f0, f1, s0, s1;  /* frame / scan limits (step 1) */
+  const uint8_t* mask;     /* [Fr * Sc] cycle mask for the quadrupole window */
+  int64_t ncyc_pos;        /* Fr * Sc */
+} push_query;
+
+static inline int push_in_query(const adb_rawfile4d_desc* raw, const push_query* q, int64_t push, int64_t* pos_out) {
+  int64_t frame = push / raw->scan_max_index, scan = push % raw->scan_max_index;
+  if (frame < q->f0 || frame >= q->f1 || scan < q->s0 || scan >= q->s1) return 0;
+  int64_t cyclic = raw->zeroth_frame ? push - raw->scan_max_index : push;
+  int64_t pos = ((cyclic % q->ncyc_pos) + q->ncyc_pos) % q->ncyc_pos;
+  *pos_out = pos;
+  return q->mask[pos];
+}
+
+static uint8_t* cycle_mask_4d(const adb_rawfile4d_desc* raw, float q0, float q1) { /* bruker_jit.py:280-313 */
+  int64_t n = raw->frames_per_cycle * raw->scans;
+  uint8_t* m = (uint8_t*)malloc((size_t)n);
+  for (int64_t k = 0; k < n; k++) m[k] = ((double)q0 <= raw->cycle[2 * k + 1]) && ((double)q1 >= raw->cycle[2 * k]);
+  return m;
+}
+
+/* sorted unique observation ids present in the push query (np.unique(precursor_index), bruker_jit.py:368) */
+static int query_observations(const adb_rawfile4d_desc* raw, const push_query* q, int64_t** obs_out) {
+  int64_t Fr = raw->frames_per_cycle;
+  uint8_t* seen = (uint8_t*)calloc((size_t)(Fr > 0 ? Fr : 1) + 1, 1);
+  int64_t max_id = Fr; /* ids are frame-in-cycle indices in practice; grow if needed */
+  int64_t cap = max_id + 1;
+  for (int64_t frame = q->f0; frame < q->f1; frame++)
+    for (int64_t scan = q->s0; scan < q->s1; scan++) {
+      int64_t pos;
+      if (push_in_query(raw, q, frame * raw->scan_max_index + scan, &pos)) {
+        int64_t id = raw->dia_precursor_cycle[pos];
+        if (id < 0) continue;
+        if (id >= cap) { int64_t ncap = id + 1; seen = (uint8_t*)realloc(seen, (size_t)ncap); memset(seen + cap, 0, (size_t)(ncap - cap)); cap = ncap; }
+        seen[id] = 1;
+      }
+    }
+  int n = 0;
+  for (int64_t k = 0; k < cap; k++) n += seen[k];
+  int64_t* obs = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+  int w = 0;
+  for (int64_t k = 0; k < cap; k++) if (seen[k]) obs[w++] = k;
+  free(seen);
+  *obs_out = obs;
+  return n;
+}
+
+/* tof slices: searchsorted(mz_values f64, mass_range(mz f32, tol), "left") (bruker_jit.py:273-278,596-598) */
+static void tof_limits_4d(const adb_rawfile4d_desc* raw, float lo, float hi, int64_t* t0, int64_t* t1) {
+  *t0 = searchsorted_left_f64(raw->mz_values, raw->n_tof, (double)lo);
+  *t1 = searchsorted_left_f64(raw->mz_values, raw->n_tof, (double)hi);
+}
+
+/* first event of tof row `t` with push >= p */
+static int64_t row_lower_bound(const adb_rawfile4d_desc* raw, int64_t t, int64_t p) {
+  int64_t lo = raw->tof_indptr[t], hi = raw->tof_indptr[t + 1];
+  while (lo < hi) { int64_t mid = (lo + hi) >> 1; if ((int64_t)raw->push_indices[mid] < p) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+/* bruker_jit.py:586-615 get_dense(absolute_masses=True) -> _assemble_push (:352-504).
+ * out_i / out_m: [n_q][nobs][S][C]; returns nobs (0 = empty query), obs ids in *obs_out. */
+static int extract_cubes_4d(const adb_rawfile4d_desc* raw, int64_t frame_start, int64_t frame_stop, int64_t scan_start,
+                            int64_t scan_stop, const float* mz, int n_q, float tol, float q0, float q1, float** out_i,
+                            float** out_m, int64_t* C_out, int64_t** obs_out) {
+  const double HIGH_EPSILON = 1e-26, LOW_EPSILON = 1e-36;
+  *out_i = NULL; *out_m = NULL; *obs_out = NULL; *C_out = 0;
+  int64_t Fr = raw->frames_per_cycle;
+  push_query q = {frame_start, frame_stop, scan_start, scan_stop, cycle_mask_4d(raw, q0, q1), Fr * raw->scans};
+  int64_t* obs = NULL;
+  int nobs = query_observations(raw, &q, &obs);
+  if (nobs == 0) { free((void*)q.mask); free(obs); return 0; }
+  int64_t S = scan_stop - scan_start;
+  int64_t cs = (frame_start - raw->zeroth_frame) / Fr, ce = (frame_stop - raw->zeroth_frame) / Fr;
+  int64_t C = ce - cs;
+  if (S <= 0 || C <= 0) { free((void*)q.mask); free(obs); return 0; }
+  size_t tot = (size_t)n_q * nobs * S * C;
+  float* di = (float*)calloc(tot, sizeof(float));
+  float* dm = (float*)calloc(tot, sizeof(float));
+  float lo[ADB_MAX_FRAGMENTS > ADB_MAX_ISOTOPES ? ADB_MAX_FRAGMENTS : ADB_MAX_ISOTOPES], hi[ADB_MAX_FRAGMENTS > ADB_MAX_ISOTOPES ? ADB_MAX_FRAGMENTS : ADB_MAX_ISOTOPES];
+  mass_range_f32tol(mz, n_q, tol, lo, hi);
+  for (int j = 0; j < n_q; j++) {
+    int64_t t0, t1;
+    tof_limits_4d(raw, lo[j], hi[j], &t0, &t1);
+    for (int64_t t = t0; t < t1; t++) {
+      double measured = raw->mz_values[t];
+      int64_t e = row_lower_bound(raw, t, frame_start * raw->scan_max_index), end = raw->tof_indptr[t + 1];
+      for (; e < end; e++) {
+        int64_t push = raw->push_indices[e];
+        if (push >= frame_stop * raw->scan_max_index) break;
+        int64_t pos;
+        if (!push_in_query(raw, &q, push, &pos)) continue;
+        int64_t id = raw->dia_precursor_cycle[pos];
+        int o = 0;
+        while (o < nobs && obs[o] != id) o++;
+        if (o == nobs) continue;
+        int64_t frame = push / raw->scan_max_index, scan = push % raw->scan_max_index;
+        int64_t rc = (frame - raw->zeroth_frame) / Fr - cs, rs = scan - scan_start;
+        if (rc < 0 || rc >= C) continue;
+        size_t cell = ((((size_t)j * nobs + o) * S) + rs) * C + rc;
+        float acc_i = di[cell], acc_m = dm[cell];
+        int64_t ni = (int64_t)raw->intensity_values[e] * (((double)raw->intensity_values[e]) > HIGH_EPSILON);
+        double num = (double)(float)(acc_m * acc_i) + (double)ni * measured + LOW_EPSILON;
+        double den = ((double)acc_i + (double)ni) + LOW_EPSILON;
+        di[cell] = (float)((double)acc_i + (double)ni);
+        dm[cell] = (float)(num / den);
+      }
+    }
+  }
+  free((void*)q.mask);
+  *out_i = di; *out_m = dm; *obs_out = obs; *C_out = C;
+  return nobs;
+}
+
+/* bruker_jit.py:617-645 get_dense_intensity -> _assemble_push_intensity (:506-584). out: [n_q][S][C].
+ * Returns 0 when the push query is empty (the reference returns a 0-sized array -> _is_valid fails). */
+static int dense_intensity_4d(const adb_rawfile4d_desc* raw, const int64_t fl[2], const int64_t sl[2], const float* lo,
+                              const float* hi, int n_q, float q0, float q1, float* out, int64_t S, int64_t C) {
+  int64_t Fr = raw->frames_per_cycle;
+  push_query q = {fl[0], fl[1], sl[0], sl[1], cycle_mask_4d(raw, q0, q1), Fr * raw->scans};
+  int64_t* obs = NULL;
+  int nobs = query_observations(raw, &q, &obs);
+  free(obs);
+  memset(out, 0, sizeof(float) * (size_t)n_q * S * C);
+  if (nobs == 0) { free((void*)q.mask); return 0; }
+  int64_t cs = (fl[0] - raw->zeroth_frame) / Fr;
+  for (int j = 0; j < n_q; j++) {
+    int64_t t0, t1;
+    tof_limits_4d(raw, lo[j], hi[j], &t0, &t1);
+    for (int64_t t = t0; t < t1; t++) {
+      int64_t e = row_lower_bound(raw, t, fl[0] * raw->scan_max_index), end = raw->tof_indptr[t + 1];
+      for (; e < end; e++) {
+        int64_t push = raw->push_indices[e];
+        if (push >= fl[1] * raw->scan_max_index) break;
+        int64_t pos;
+        if (!push_in_query(raw, &q, push, &pos)) continue;
+        int64_t frame = push / raw->scan_max_index, scan = push % raw->scan_max_index;
+        int64_t rc = (frame - raw->zeroth_frame) / Fr - cs, rs = scan - sl[0];
+        if (rc < 0 || rc >= C) continue;
+        size_t cell = ((size_t)j * S + rs) * C + rc;
+        out[cell] = out[cell] + (float)raw->intensity_values[e];
+      }
+    }
+  }
+  free((void*)q.mask);
+  return 1;
+}
+
+/* selection.py:78-203 for one precursor of a 4-D file */
+static void select_one_4d(const adb_rawfile4d_desc* raw, const adb_library_desc* lib, const adb_selection_config* cfg,
+                          const float* kernel, int kh, int kw, int64_t i, adb_candidates_out* out) {
+  int nI = lib->n_isotopes < cfg->top_k_precursors ? lib->n_isotopes : (int)cfg->top_k_precursors;
+  float iso_mz[ADB_MAX_ISOTOPES];
+  for (int j = 0; j < nI; j++) iso_mz[j] = (float)((double)lib->mz[i] + (double)j * ISOTOPE_DIFF / (double)lib->charge[i]);
+  int64_t fs = lib->frag_start_idx[i], fe = lib->frag_stop_idx[i];
+  int nf_all = (int)(fe - fs); if (nf_all < 0) nf_all = 0;
+  float* fmz = (float*)malloc(sizeof(float) * (size_t)(nf_all + 1));
+  int nF = 0;
+  for (int64_t j = fs; j < fe; j++) if (!cfg->exclude_shared_ions || lib->frag_cardinality[j] <= 1) fmz[nF++] = lib->frag_mz[j];
+  int* order = (int*)malloc(sizeof(int) * (size_t)(nF + 1));
+  argsort_f32(fmz, nF, order);
+  float* fsorted = (float*)malloc(sizeof(float) * (size_t)(nF + 1));
+  for (int j = 0; j < nF; j++) fsorted[j] = fmz[order[j]];
+  free(fmz); free(order);
+  if (nF <= 3) { free(fsorted); return; }
+  int64_t fl[2], sl[2];
+  get_frame_indices_tolerance_4d(raw, lib->rt[i], cfg->rt_tolerance, 16, cfg->kernel_size, fl);
+  get_scan_indices_tolerance_4d(raw, lib->mobility[i], cfg->mobility_tolerance, 16, sl);
+  int64_t Fr = raw->frames_per_cycle;
+  int64_t C = (fl[1] - raw->zeroth_frame) / Fr - (fl[0] - raw->zeroth_frame) / Fr;
+  int64_t S = sl[1] - sl[0];
+  if (C <= 0 || S <= 0 || sl[0] < 0 || sl[1] > raw->scan_max_index) { free(fsorted); return; }
+  float* lo = (float*)malloc(sizeof(float) * (size_t)(nF + nI));
+  float* hi = (float*)malloc(sizeof(float) * (size_t)(nF + nI));
+  float* dp = (float*)malloc(sizeof(float) * (size_t)nI * S * C);
+  float* df = (float*)malloc(sizeof(float) * (size_t)nF * S * C);
+  mass_range_f64tol(iso_mz, nI, cfg->precursor_mz_tolerance, lo, hi);
+  int okp = dense_intensity_4d(raw, fl, sl, lo, hi, nI, -1.0f, -1.0f, dp, S, C);
+  mass_range_f64tol(fsorted, nF, cfg->fragment_mz_tolerance, lo, hi);
+  int okf = dense_intensity_4d(raw, fl, sl, lo, hi, nF, iso_mz[0], iso_mz[nI - 1], df, S, C);
+  free(lo); free(hi); free(fsorted);
+  /* selection.py:40-75 _is_valid */
+  if (!okp || !okf || (S % 2) != 0 || S < kh || C < kw) { free(dp); free(df); return; }
+  float* smooth = (float*)malloc(sizeof(float) * (size_t)S * C);
+  float* lf = (float*)calloc((size_t)S * C, sizeof(float));
+  float* lp = (float*)calloc((size_t)S * C, sizeof(float));
+  for (int l = 0; l < nF; l++) {
+    conv_circular(df + (size_t)l * S * C, (int)S, (int)C, kernel, kh, kw, smooth);
+    for (int64_t t = 0; t < S * C; t++) lf[t] = lf[t] + log1p_feature(smooth[t]);
+  }
+  for (int l = 0; l < nI; l++) {
+    conv_circular(dp + (size_t)l * S * C, (int)S, (int)C, kernel, kh, kw, smooth);
+    for (int64_t t = 0; t < S * C; t++) lp[t] = lp[t] + log1p_feature(smooth[t]);
+  }
+  double* score = (double*)malloc(sizeof(double) * (size_t)S * C);
+  double mean = cfg->use_weighted_score ? cfg->feature_mean : 0.0;
+  double std = cfg->use_weighted_score ? cfg->feature_std : 0.0;
+  double w = cfg->use_weighted_score ? cfg->feature_weight : 1.0;
+  if (!cfg->use_weighted_score) {
+    float acc = 0;
+    for (int64_t t = 0; t < S * C; t++) acc = acc + (float)(lf[t] + lp[t]);
+    mean = (double)acc / (double)(S * C);
+    double v = 0;
+    for (int64_t t = 0; t < S * C; t++) { double d = (double)(float)(lf[t] + lp[t]) - mean; v += d * d; }
+    std = sqrt(v / (double)(S * C));
+  }
+  for (int64_t t = 0; t < S * C; t++) score[t] = 0.0 + w * ((double)(float)(lf[t] + lp[t]) - mean) / (std + 1e-6);
+  free(smooth); free(lf); free(lp); free(dp); free(df);
+
+  /* selection/utils.py:77-110 find_peaks_2d (or find_peaks_1d when S <= 2) */
+  size_t cap = (size_t)S * C;
+  int* pk_scan = (int*)malloc(sizeof(int) * cap);
+  int* pk_cyc = (int*)malloc(sizeof(int) * cap);
+  double* pk_val = (double*)malloc(sizeof(double) * cap);
+  int n_pk = 0;
+  if (S <= 2) {
+    for (int p = 2; p < C - 2; p++) {
+      const double* a = score;
+      if (a[p - 2] < a[p - 1] && a[p - 1] < a[p] && a[p] > a[p + 1] && a[p + 1] > a[p + 2]) { pk_scan[n_pk] = 0; pk_cyc[n_pk] = p; pk_val[n_pk] = a[p]; n_pk++; }
+    }
+  } else {
+    for (int sidx = 2; sidx < S - 2; sidx++)
+      for (int p = 2; p < C - 2; p++) {
+        const double* a = score;
+#define A2(ss, pp) a[(size_t)(ss) * C + (pp)]
+        int pk = A2(sidx - 2, p) < A2(sidx - 1, p) && A2(sidx - 1, p) < A2(sidx, p) && A2(sidx, p) > A2(sidx + 1, p) && A2(sidx + 1, p) > A2(sidx + 2, p);
+        pk = pk && A2(sidx, p - 2) < A2(sidx, p - 1) && A2(sidx, p - 1) < A2(sidx, p) && A2(sidx, p) > A2(sidx, p + 1) && A2(sidx, p + 1) > A2(sidx, p + 2);
+        if (pk) { pk_scan[n_pk] = sidx; pk_cyc[n_pk] = p; pk_val[n_pk] = A2(sidx, p); n_pk++; }
+#undef A2
+      }
+  }
+  int* ord = (int*)malloc(sizeof(int) * (size_t)(n_pk + 1));
+  argsort_f64(pk_val, n_pk, ord);
+  int top_n = (int)cfg->candidate_count < n_pk ? (int)cfg->candidate_count : n_pk;
+  int* t_scan = (int*)malloc(sizeof(int) * (size_t)(top_n + 1));
+  int* t_cyc = (int*)malloc(sizeof(int) * (size_t)(top_n + 1));
+  double* t_val = (double*)malloc(sizeof(double) * (size_t)(top_n + 1));
+  for (int r = 0; r < top_n; r++) { int k = ord[n_pk - 1 - r]; t_scan[r] = pk_scan[k]; t_cyc[r] = pk_cyc[k]; t_val[r] = pk_val[k]; }
+  free(pk_scan); free(pk_cyc); free(pk_val); free(ord);
+  uint8_t* mask = (uint8_t*)malloc((size_t)(top_n + 1));
+  for (int r = 0; r < top_n; r++) mask[r] = 1;
+  for (int a = 0; a < top_n; a++) {
+    if (!mask[a]) continue;
+    for (int b = a + 1; b < top_n; b++) {
+      if (!mask[b]) continue;
+      if (abs(t_scan[a] - t_scan[b]) <= 3 && abs(t_cyc[a] - t_cyc[b]) <= 3) { if (t_val[a] > t_val[b]) mask[b] = 0; else mask[a] = 0; }
+    }
+  }
+  int n_c = 0;
+  for (int r = 0; r < top_n; r++) if (mask[r]) { t_scan[n_c] = t_scan[r]; t_cyc[n_c] = t_cyc[r]; t_val[n_c] = t_val[r]; n_c++; }
+  free(mask);
+  int (*slim)[2] = (int (*)[2])malloc(sizeof(int[2]) * (size_t)(n_c + 1));
+  int (*clim)[2] = (int (*)[2])malloc(sizeof(int[2]) * (size_t)(n_c + 1));
+  for (int r = 0; r < n_c; r++) symetric_limits_2d(score, (int)S, (int)C, t_scan[r], t_cyc[r], cfg, slim[r], clim[r]);
+  if (cfg->join_close_candidates) {
+    uint8_t* jm = (uint8_t*)malloc((size_t)(n_c + 1));
+    for (int r = 0; r < n_c; r++) jm[r] = 1;
+    for (int a = 0; a < n_c; a++) {
+      if (!jm[a]) continue;
+      for (int b = a + 1; b < n_c; b++) {
+        if (!jm[b]) continue;
+        double cycle_len = (double)(clim[a][1] - clim[a][0]);
+        int mn = clim[a][1] < clim[b][1] ? clim[a][1] : clim[b][1];
+        int mx = clim[a][0] > clim[b][0] ? clim[a][0] : clim[b][0];
+        double cycle_overlap = (double)(mn - mx) / cycle_len;
+        double scan_len = (double)(slim[a][1] - slim[a][0]);
+        mn = slim[a][1] < slim[b][1] ? slim[a][1] : slim[b][1];
+        mx = slim[a][0] > slim[b][0] ? slim[a][0] : slim[b][0];
+        double scan_overlap = (double)(mn - mx) / scan_len;
+        if (scan_overlap < 0 || cycle_overlap < 0) continue;
+        if (cycle_overlap > cfg->join_close_candidates_cycle_threshold && scan_overlap > cfg->join_close_candidates_scan_threshold) {
+          if (slim[b][0] < slim[a][0]) slim[a][0] = slim[b][0];
+          if (slim[b][1] > slim[a][1]) slim[a][1] = slim[b][1];
+          if (clim[b][0] < clim[a][0]) clim[a][0] = clim[b][0];
+          if (clim[b][1] > clim[a][1]) clim[a][1] = clim[b][1];
+          jm[b] = 0;
+        }
+      }
+    }
+    int m = 0;
+    for (int r = 0; r < n_c; r++) if (jm[r]) {
+      t_scan[m] = t_scan[r]; t_cyc[m] = t_cyc[r]; t_val[m] = t_val[r];
+      slim[m][0] = slim[r][0]; slim[m][1] = slim[r][1]; clim[m][0] = clim[r][0]; clim[m][1] = clim[r][1]; m++;
+    }
+    n_c = m;
+    free(jm);
+  }
+  for (int r = 0; r < n_c; r++) { /* selection.py:480-526 */
+    int64_t row = i * cfg->candidate_count + r;
+    if (row >= out->n_rows) break;
+    out->precursor_idx[row] = lib->precursor_idx[i];
+    out->rank[row] = (uint8_t)r;
+    out->score[row] = (float)t_val[r];
+    out->scan_center[row] = (uint32_t)wrap0(t_scan[r] + sl[0], raw->scan_max_index);
+    out->scan_start[row] = (uint32_t)wrap0(slim[r][0] + sl[0], raw->scan_max_index);
+    out->scan_stop[row] = (uint32_t)wrap0(slim[r][1] + sl[0], raw->scan_max_index);
+    out->frame_center[row] = (uint32_t)wrap0((int64_t)t_cyc[r] * Fr + fl[0], raw->frame_max_index);
+    out->frame_start[row] = (uint32_t)wrap0((int64_t)clim[r][0] * Fr + fl[0], raw->frame_max_index);
+    out->frame_stop[row] = (uint32_t)wrap0((int64_t)clim[r][1] * Fr + fl[0], raw->frame_max_index);
+  }
+  free(t_scan); free(t_cyc); free(t_val); free(slim); free(clim); free(score);
+}
+
+int adbo_select_candidates_4d(const adb_rawfile4d_desc* raw, const adb_library_desc* lib, const adb_selection_config* cfg,
+                              const float* kernel, int32_t kh, int32_t kw, adb_candidates_out* out, int32_t n_threads) {
+  zero_candidates(out);
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t i = 0; i < lib->n_precursors; i++) select_one_4d(raw, lib, cfg, kernel, kh, kw, i, out);
+  return 0;
+}
+
+int adbo_score_candidates_4d(const adb_rawfile4d_desc* raw, const adb_library_desc* lib, const adb_scoring_config* cfg,
+                             const adb_candidates_in* cand, adb_scores_out* out, int32_t n_threads) {
+  if (cfg->top_k_fragments > ADB_MAX_FRAGMENTS) return 1;
+  zero_scores(cfg, cand->n, out);
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+  rawview rv = {NULL, raw};
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int64_t ci = 0; ci < cand->n; ci++) score_one(&rv, lib, cfg, cand, ci, out, NULL);
+  return 0;
+}
+
+void adbo_scan_indices_4d(const adb_rawfile4d_desc* raw, float mobility, double tol, int64_t* out) {
+  get_scan_indices_tolerance_4d(raw, mobility, tol, 16, out);
 }

@@ -12,7 +12,7 @@ from alphadia_b200 import _abi
 from alphadia_b200.config import CandidateScoringConfig, CandidateSelectionConfig
 from alphadia_b200.kernel import GaussianKernel
 from alphadia_b200.library import assemble_library_arrays
-from alphadia_b200.synthetic import make_config_3d
+from alphadia_b200.synthetic import CONFIGS_4D, make_config_3d, make_config_4d
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -47,14 +47,19 @@ def scoring_config(**kw) -> CandidateScoringConfig:
 
 @functools.lru_cache(maxsize=4)
 def workload(name: str):
-    raw, precursor_df, fragment_df, p = make_config_3d(name)
+    if name in CONFIGS_4D:
+        raw, precursor_df, fragment_df, p = make_config_4d(name)
+    else:
+        raw, precursor_df, fragment_df, p = make_config_3d(name)
     lib = assemble_library_arrays(precursor_df, fragment_df, "rt_library", "mobility_library", "mz_library", "mz_library")
     return raw, precursor_df, fragment_df, lib, p
 
 
 def input_checksum(raw, precursor_df, fragment_df) -> str:
     h = hashlib.sha256()
-    for a in (raw.mz_values, raw.intensity_values, raw.peak_start_idx_list, raw.rt_values,
+    index = raw.tof_indptr if hasattr(raw, "tof_indptr") else raw.peak_start_idx_list
+    extra = (raw.push_indices,) if hasattr(raw, "push_indices") else ()
+    for a in (raw.mz_values, raw.intensity_values, index, raw.rt_values, *extra,
               precursor_df["mz_library"].values, precursor_df["rt_library"].values,
               fragment_df["mz_library"].values, fragment_df["intensity"].values):
         h.update(np.ascontiguousarray(a).tobytes())
@@ -69,6 +74,7 @@ def load_golden(name: str):
 
 
 def default_kernel(raw, fwhm_rt=5.0, fwhm_mobility=0.01) -> np.ndarray:
+    """GaussianKernel as CandidateSelection builds it (selection.py:609-620)."""
     g = GaussianKernel(raw, fwhm_rt=fwhm_rt, sigma_scale_rt=0.5, fwhm_mobility=fwhm_mobility, sigma_scale_mobility=1.0,
                        kernel_width=30, kernel_height=min(30, raw.scan_max_index + 1))
     return g.get_dense_matrix(verbose=False)

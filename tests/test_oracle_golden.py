@@ -20,7 +20,7 @@ VARIANTS = {
 }
 # features whose reference value goes through BLAS dots (np.dot / np.corrcoef): summation order is
 # unspecified there, everything else must match the reference bit for bit.
-BLAS_FEATURES = {18, 19, 31, 32, 33, 34, 36}
+BLAS_FEATURES = {18, 19, 29, 30, 31, 32, 33, 34, 36}
 
 
 def _golden(name):
@@ -101,3 +101,42 @@ def test_fragcomp_vs_reference(name, oracle_lib):
     assert np.array_equal(kept["rank"].values, g["fc_kept_rank"])
     assert np.array_equal(kept["_candidate_idx"].values, g["fc_kept_candidate_idx"])
     assert FragmentCompetition is not None
+
+
+# ---- timsTOF (4-D) -------------------------------------------------------------------------------
+def test_selection_4d_bit_exact_vs_reference(oracle_lib):
+    g, raw, lib, p = _golden("parity_4d")
+    k = H.default_kernel(raw)
+    assert k.shape == (30, 30) and np.array_equal(k, g["sel_kernel"])
+    cfg = H.selection_config(p["rt_tolerance"], mobility_tolerance=p["mobility_tolerance"]).to_struct()
+    arrs = oracle_lib.select_candidates_4d(raw, lib, cfg, g["sel_kernel"])
+    m = arrs["score"] > 0
+    assert m.sum() == len(g["cand_precursor_idx"]) > 100
+    for c in INT_COLS:
+        assert np.array_equal(arrs[c][m].astype(np.int64), g["cand_" + c].astype(np.int64)), c
+    assert np.array_equal(arrs["score"][m], g["cand_score"])
+    # the scan window really is two-dimensional here
+    assert (g["cand_scan_stop"] - g["cand_scan_start"]).max() > 8
+
+
+def test_scoring_4d_vs_reference(oracle_lib):
+    g, raw, lib, p = _golden("parity_4d")
+    cand = {c: g["cand_" + c] for c in INT_COLS}
+    cin, keep = H.candidates_in_from_arrays(lib, cand)
+    arrs = oracle_lib.score_candidates_4d(raw, lib, H.scoring_config().to_struct(), cin)
+    v = arrs["valid"].astype(bool)
+    assert np.array_equal(keep["precursor_idx"][v], g["feat_precursor_idx"])
+    assert np.array_equal(keep["rank"][v], g["feat_rank"])
+    F, G = arrs["features"][v], g["feat_matrix"]
+    assert np.abs(G[:, 29]).max() > 0 and np.abs(G[:, 39]).max() > 0  # mobility features are live
+    for j in range(46):
+        same = (F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))
+        if j in BLAS_FEATURES:
+            assert H.rel_err(F[:, j], G[:, j]).max() < 1e-4, j
+        else:
+            assert same.all(), f"feature {j} not bit-exact"
+    m = arrs["fragment_mz_library"] > 0
+    assert m.sum() == len(g["frag_mz_library"])
+    for k, v2 in FRAG_MAP.items():
+        a, b = arrs[v2][m], g[f"frag_{k}"]
+        assert np.array_equal(a, b) if k != "correlation" else H.rel_err(a, b).max() < 1e-4, k
