@@ -19,7 +19,7 @@ SO_PATH = os.path.join(HERE, "libalphadia_b200.so")
 # every symbol include/alphadia_b200.h declares
 EXPORTED_SYMBOLS = [
     "adb_last_error", "adb_version", "adb_device_count",
-    "adb_rawfile3d_create", "adb_rawfile_destroy", "adb_rawfile_device_bytes", "adb_rawfile_stream",
+    "adb_rawfile3d_create", "adb_rawfile4d_create", "adb_rawfile_destroy", "adb_rawfile_device_bytes", "adb_rawfile_stream",
     "adb_library_create", "adb_library_destroy",
     "adb_select_candidates", "adb_score_candidates", "adb_fragment_competition",
     "adb_select_candidates_resident", "adb_score_candidates_resident",
@@ -90,12 +90,19 @@ class DeviceRawFile:
         require_device()
         self._lib = load()
         self.device = current_device() if device is None else device
-        desc, keep = _abi.make_rawfile3d_desc(raw)
         h = C.c_void_p()
-        check(self._lib.adb_rawfile3d_create(C.byref(desc), C.c_int(self.device), C.byref(h)), "adb_rawfile3d_create")
+        self.is_4d = bool(getattr(raw, "is_4d", False)) or hasattr(raw, "tof_indptr")
+        if self.is_4d:
+            desc, keep = _abi.make_rawfile4d_desc(raw)
+            check(self._lib.adb_rawfile4d_create(C.byref(desc), C.c_int(self.device), C.byref(h)), "adb_rawfile4d_create")
+            self.cycle_len = int(desc.frames_per_cycle)
+            self.n_spectra = int(desc.n_frames)
+        else:
+            desc, keep = _abi.make_rawfile3d_desc(raw)
+            check(self._lib.adb_rawfile3d_create(C.byref(desc), C.c_int(self.device), C.byref(h)), "adb_rawfile3d_create")
+            self.cycle_len = int(desc.cycle_len)
+            self.n_spectra = int(desc.n_spectra)
         self.handle = h
-        self.cycle_len = int(desc.cycle_len)
-        self.n_spectra = int(desc.n_spectra)
 
     @property
     def device_bytes(self) -> int:

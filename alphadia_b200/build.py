@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "libalphadia_b200.so")
-SOURCES = ["adb_api.cu", "adb_select.cu", "adb_score.cu", "adb_misc.cu"]
+SOURCES = ["adb_api.cu", "adb_select.cu", "adb_score.cu", "adb_misc.cu", "adb_select4d.cu", "adb_score4d.cu"]
 HEADERS = [os.path.join(CSRC, "adb_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "alphadia_b200.h")]
 
 

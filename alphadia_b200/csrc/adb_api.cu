@@ -81,9 +81,12 @@ struct adb_rawfile {
   int device = 0;
   cudaStream_t stream = nullptr;
   DevRaw dev{};
+  int is4d = 0;    // timsTOF handle: dev4 is set instead of dev
+  DevRaw4 dev4{};
   std::vector<void*> allocs;
   int64_t bytes = 0;
   std::vector<float> rt_host;  // host copy of rt_values (to bound the cycle window on the host)
+  std::vector<double> rt4_host, mob4_host;  // 4-D: rt_values / mobility_values
   uint32_t* d_status = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 4,5 bracket the main kernel
   float h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, main_kernel_ms = 0;
@@ -98,6 +101,7 @@ struct adb_rawfile {
   DeviceBuffer scores;     // score outputs
   DeviceBuffer score_ws;
   DeviceBuffer staging;    // generic H2D staging
+  DeviceBuffer extent;     // 4-D: max scan / cycle extent of the resident candidates
   // resident state
   int64_t cont_rows = 0, cont_count = 0;
   DevCandidatesOut d_cont{};
@@ -272,9 +276,196 @@ int64_t cycle_window_upper_bound(const adb_rawfile* raw, double rt_tol, int64_t 
   return std::min<int64_t>(opt, std::max<int64_t>(raw->dev.precursor_cycle_max_index, 1));
 }
 
+
+// ---- 4-D (timsTOF) ---------------------------------------------------------------------------------
+// processing order by time: a tof-major raw file has no per-candidate locality except along the push axis, so
+// co-resident CTAs should work on the same time slice of every tof row (the slice then stays in L2)
+__global__ void order_key4_kernel(DevLib lib, uint64_t* keys, int32_t* vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= lib.n_precursors) return;
+  uint32_t rb = __float_as_uint(lib.rt[i]);
+  rb = (rb & 0x80000000u) ? ~rb : (rb | 0x80000000u);
+  keys[i] = (uint64_t)rb;
+  vals[i] = (int32_t)i;
+}
+
+__global__ void score_order_key4_kernel(DevCandidatesIn cand, uint64_t* keys, int32_t* vals) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cand.n) return;
+  int64_t fs = cand.frame_start[i];
+  keys[i] = fs < 0 ? 0ull : (uint64_t)fs;
+  vals[i] = (int32_t)i;
+}
+
+// max scan extent and frame extent of the candidates -> out[0], out[1]
+__global__ void cand_extent_kernel(DevCandidatesIn cand, unsigned long long* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cand.n) return;
+  int64_t s = cand.scan_stop[i] - cand.scan_start[i], f = cand.frame_stop[i] - cand.frame_start[i];
+  if (s > 0) atomicMax(out, (unsigned long long)s);
+  if (f > 0) atomicMax(out + 1, (unsigned long long)f);
+}
+
+// upper bounds of the selection window of any precursor: cycles (jitclasses/utils.py:62-70) and scans (bruker_jit.py:227-233)
+void window_upper_bounds_4d(const adb_rawfile* raw, double rt_tol, double mob_tol, int64_t kernel_size, int64_t* c_cap, int64_t* s_cap) {
+  const std::vector<double>& rt = raw->rt4_host;
+  const int64_t n = (int64_t)rt.size(), L = raw->dev4.Fr;
+  int64_t max_span = 0, j = 0;
+  for (int64_t i = 0; i < n; i++) {
+    if (j < i) j = i;
+    while (j < n && rt[j] <= rt[i] + 2.0 * rt_tol + 1e-3) j++;
+    max_span = std::max(max_span, j - i);
+  }
+  int64_t opt = std::max(max_span / L + 2, kernel_size);
+  opt = 16 * ((opt + 15) / 16);
+  *c_cap = std::min<int64_t>(opt, std::max<int64_t>(raw->dev4.precursor_cycle_max_index, 1));
+  const std::vector<double>& mob = raw->mob4_host;  // descending
+  const int64_t m = (int64_t)mob.size();
+  int64_t max_sc = 0;
+  j = 0;
+  for (int64_t i = 0; i < m; i++) {  // scans whose mobility lies within 2 * tol below mob[i]
+    if (j < i) j = i;
+    while (j < m && mob[j] >= mob[i] - 2.0 * mob_tol - 1e-6) j++;
+    max_sc = std::max(max_sc, j - i);
+  }
+  int64_t so = 16 * ((max_sc + 2 + 15) / 16);
+  *s_cap = std::min<int64_t>(so, std::max<int64_t>(raw->dev4.scan_max_index, 1));
+}
+
+int run_selection4d(adb_rawfile* raw, adb_library* lib, const adb_selection_config* cfg, const float* kernel, int32_t kh, int32_t kw) {
+  if (kh < 1 || kh > ADB_MAX_KERNEL_W || kw < 1 || kw > ADB_MAX_KERNEL_W)
+    return fail("kernel height and width must be in [1, " + std::to_string(ADB_MAX_KERNEL_W) + "]");
+  cudaStream_t st = raw->stream;
+  const int64_t P = lib->dev.n_precursors;
+  const int64_t rows = P * cfg->candidate_count;
+  CUDA_TRY(cudaEventRecord(raw->ev[0], st));
+  std::vector<double> kd((size_t)kh * kw);
+  for (size_t t = 0; t < kd.size(); t++) kd[t] = (double)kernel[t];
+  if (raw->kern.reserve(sizeof(double) * kd.size())) return 1;
+  CUDA_TRY(cudaMemcpyAsync(raw->kern.ptr, kd.data(), sizeof(double) * kd.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // kd is a local
+  if (raw->cont.reserve(container_bytes(rows))) return 1;
+  raw->d_cont = carve_container(raw->cont.ptr, rows);
+  raw->cont_rows = rows;
+  raw->cont_count = cfg->candidate_count;
+  CUDA_TRY(cudaEventRecord(raw->ev[1], st));
+  CUDA_TRY(cudaMemsetAsync(raw->cont.ptr, 0, container_bytes(rows), st));
+  int32_t* d_order = nullptr;
+  if (P > 1) {
+    if (raw->order_keys.reserve(sizeof(uint64_t) * 2 * (size_t)P)) return 1;
+    if (raw->order_vals.reserve(sizeof(int32_t) * 2 * (size_t)P)) return 1;
+    uint64_t* k_in = raw->order_keys.as<uint64_t>();
+    uint64_t* k_out = k_in + P;
+    int32_t* v_in = raw->order_vals.as<int32_t>();
+    int32_t* v_out = v_in + P;
+    order_key4_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(lib->dev, k_in, v_in);
+    raw->launches++;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)P, 0, 32, st);
+    if (raw->order_tmp.reserve(tmp)) return 1;
+    cub::DeviceRadixSort::SortPairs(raw->order_tmp.ptr, tmp, k_in, k_out, v_in, v_out, (int)P, 0, 32, st);
+    raw->launches += 4;
+    d_order = v_out;
+  }
+  int64_t c_cap = 0, s_cap = 0;
+  window_upper_bounds_4d(raw, cfg->rt_tolerance, cfg->mobility_tolerance, cfg->kernel_size, &c_cap, &s_cap);
+  if (c_cap > 4096 || s_cap > 4096 || c_cap * s_cap > (1 << 22)) return fail("selection window too large for the device workspace");
+  const int nI = (int)std::min<int64_t>(std::min<int64_t>(lib->dev.n_isotopes, cfg->top_k_precursors), ADB_MAX_ISOTOPES);
+  Select4Geometry g{(int)s_cap, (int)c_cap, std::min(lib->max_lib_fragments, (int)ADB_MAX_LIB_FRAGMENTS) + nI};
+  size_t dyn = 0;
+  int tile_in_smem = 0;
+  const int grid = adb_select4d_grid(raw->device, raw->dev4, g, kh, kw, &dyn, &tile_in_smem);
+  if (grid <= 0) return fail("selection kernel does not fit the shared memory of this device");
+  const size_t per_cta = adb_select4d_ws_bytes_per_cta(g);
+  if (raw->sel_ws.reserve(per_cta * (size_t)grid + 4096)) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[4], st));
+  adb_launch_select4d(raw->dev4, lib->dev, *cfg, raw->kern.as<double>(), kh, kw, raw->d_cont, P, d_order, raw->d_status, g,
+                      raw->sel_ws.ptr, per_cta, grid, dyn, tile_in_smem, st, &raw->launches);
+  CUDA_TRY(cudaEventRecord(raw->ev[5], st));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int run_scoring4d(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cfg, int64_t s_max, int64_t f_max) {
+  cudaStream_t st = raw->stream;
+  const int64_t n = raw->d_cand.n;
+  const int K = (int)cfg->top_k_fragments;
+  if (raw->scores.reserve(scores_bytes(std::max<int64_t>(n, 1), K))) return 1;
+  raw->d_scores = carve_scores(raw->scores.ptr, std::max<int64_t>(n, 1), K);
+  raw->scores_n = n;
+  raw->scores_k = K;
+  CUDA_TRY(cudaMemsetAsync(raw->scores.ptr, 0, scores_bytes(std::max<int64_t>(n, 1), K), st));
+  const int64_t L = raw->dev4.Fr;
+  const int64_t c_max = std::max<int64_t>(f_max / L + 2, 4);
+  s_max = std::max<int64_t>(std::min<int64_t>(s_max, raw->dev4.Sc), 1);
+  if (c_max > 4096) return fail("a candidate spans more than 4096 cycles");
+  const int nI = (int)std::min<int64_t>(std::min<int64_t>(lib->dev.n_isotopes, cfg->top_k_isotopes), ADB_MAX_ISOTOPES);
+  const int nobs_cap = (int)std::min<int64_t>(L, ADB_MAX_OBS4);
+  const int64_t ws_floats = adb_score4d_workspace_floats(K, nI, s_max, c_max, nobs_cap);
+  int warps = adb_score4d_resident_warps(raw->device);
+  if (raw->ws_budget == 0) {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    raw->ws_budget = std::min<size_t>((size_t)8 << 30, free_b / 3);
+  }
+  const size_t budget = std::max(raw->ws_budget, raw->score_ws.bytes);
+  const size_t per_warp = sizeof(float) * (size_t)ws_floats;
+  if (per_warp * 4 > budget) return fail("a candidate window exceeds the device scratch");
+  warps = (int)std::min<size_t>((size_t)warps, budget / per_warp);
+  warps = std::max(4, warps - warps % 4);
+  if (raw->score_ws.reserve(per_warp * (size_t)warps)) return 1;
+  int32_t* d_order = nullptr;
+  if (n > 1 && n < 2000000000LL) {
+    if (raw->order_keys.reserve(sizeof(uint64_t) * 2 * (size_t)n)) return 1;
+    if (raw->order_vals.reserve(sizeof(int32_t) * 2 * (size_t)n)) return 1;
+    uint64_t* k_in = raw->order_keys.as<uint64_t>();
+    uint64_t* k_out = k_in + n;
+    int32_t* v_in = raw->order_vals.as<int32_t>();
+    int32_t* v_out = v_in + n;
+    score_order_key4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->d_cand, k_in, v_in);
+    raw->launches++;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 32, st);
+    if (raw->order_tmp.reserve(tmp)) return 1;
+    cub::DeviceRadixSort::SortPairs(raw->order_tmp.ptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 32, st);
+    raw->launches += 4;
+    d_order = v_out;
+  }
+  CUDA_TRY(cudaEventRecord(raw->ev[4], st));
+  adb_launch_score4d(raw->dev4, lib->dev, *cfg, raw->d_cand, raw->d_scores, raw->score_ws.as<float>(), ws_floats, warps,
+                     (int)s_max, (int)c_max, d_order, raw->d_status, st, &raw->launches);
+  CUDA_TRY(cudaEventRecord(raw->ev[5], st));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// resident path: extents of the compacted candidates (4-D scratch sizing)
+int resident_extents(adb_rawfile* raw, int64_t* s_max, int64_t* f_max) {
+  cudaStream_t st = raw->stream;
+  if (raw->extent.reserve(2 * sizeof(unsigned long long))) return 1;
+  CUDA_TRY(cudaMemsetAsync(raw->extent.ptr, 0, 2 * sizeof(unsigned long long), st));
+  const int64_t n = raw->d_cand.n;
+  if (n > 0) {
+    cand_extent_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->d_cand, raw->extent.as<unsigned long long>());
+    raw->launches++;
+  }
+  unsigned long long h[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(h, raw->extent.ptr, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *s_max = (int64_t)h[0];
+  *f_max = (int64_t)h[1];
+  return 0;
+}
+
 int run_selection(adb_rawfile* raw, adb_library* lib, const adb_selection_config* cfg, const float* kernel,
                   int32_t kh, int32_t kw) {
   if (raw->device != lib->device) return fail("raw file and library live on different devices");
+  if (raw->is4d) {
+    if (cfg->candidate_count < 1 || cfg->candidate_count > 16) return fail("candidate_count must be in [1, 16]");
+    if (cfg->top_k_precursors < 1) return fail("top_k_precursors must be >= 1");
+    if (set_device(raw->device)) return 1;
+    return run_selection4d(raw, lib, cfg, kernel, kh, kw);
+  }
   if (kh != 2) return fail("3-D selection expects a kernel of height 2 (GaussianKernel with scan_max_index + 1 == 2)");
   if (kw < 1 || kw > ADB_MAX_KERNEL_W) return fail("kernel width must be in [1, " + std::to_string(ADB_MAX_KERNEL_W) + "]");
   if (cfg->candidate_count < 1 || cfg->candidate_count > 16) return fail("candidate_count must be in [1, 16]");
@@ -365,11 +556,12 @@ int run_compaction(adb_rawfile* raw) {
   return 0;
 }
 
-int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cfg, int64_t c_max_hint) {
+int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cfg, int64_t c_max_hint, int64_t s_max_hint = 0) {
   if (raw->device != lib->device) return fail("raw file and library live on different devices");
   if (cfg->top_k_fragments < 1 || cfg->top_k_fragments > ADB_MAX_FRAGMENTS)
     return fail("top_k_fragments must be in [1, " + std::to_string(ADB_MAX_FRAGMENTS) + "]");
   if (cfg->top_k_isotopes < 1) return fail("top_k_isotopes must be >= 1");
+  if (raw->is4d) return run_scoring4d(raw, lib, cfg, s_max_hint, c_max_hint /* frames */);
   cudaStream_t st = raw->stream;
   const int64_t n = raw->d_cand.n;
   const int K = (int)cfg->top_k_fragments;
@@ -511,6 +703,65 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
   return 0;
 }
 
+int adb_rawfile4d_create(const adb_rawfile4d_desc* d, int device, adb_rawfile_t** out) {
+  if (!d || !out) return fail("null argument");
+  if (d->frames_per_cycle < 1 || d->scans < 1 || d->n_frames < 1 || d->n_tof < 1) return fail("empty raw file");
+  if (d->scan_max_index != d->scans) return fail("scan_max_index must equal cycle.shape[2] (push = frame * scans + scan)");
+  if (d->n_events >= 4294967000LL) return fail("raw files with more than 2^32 events are not supported");
+  if (d->n_tof >= 2000000000LL) return fail("more than 2^31 tof bins are not supported");
+  if ((d->n_frames + 1) * d->scans > 0xFFFFFFFFLL) return fail("push indices exceed 32 bits");
+  const int64_t npos = d->frames_per_cycle * d->scans;
+  int unique = 1;
+  {  // observation ids: small non-negative integers; is every id bound to one frame of the cycle per scan?
+    std::vector<int> seen(64);
+    for (int64_t s = 0; s < d->scans; s++) {
+      std::fill(seen.begin(), seen.end(), 0);
+      for (int64_t f = 0; f < d->frames_per_cycle; f++) {
+        const int64_t id = d->dia_precursor_cycle[f * d->scans + s];
+        if (id >= 0 && id < 64 && seen[id]++) unique = 0;
+      }
+    }
+  }
+  for (int64_t t = 0; t < d->n_tof; t++)
+    if (d->tof_indptr[t + 1] < d->tof_indptr[t] || d->tof_indptr[t] < 0 || d->tof_indptr[t + 1] > d->n_events)
+      return fail("tof_indptr is not a valid CSR index (row " + std::to_string(t) + ")");
+  if (set_device(device)) return 1;
+  adb_rawfile* r = new adb_rawfile();
+  r->device = device;
+  r->is4d = 1;
+  CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&r->ev[i]));
+  cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, device);
+  DevRaw4& v = r->dev4;
+  double *cyc, *rt, *mob, *mz; int64_t *dpc, *ip; uint32_t* push; uint16_t* it;
+  if (upload(d->cycle, npos * 2, &cyc, r->allocs, r->bytes, r->stream) ||
+      upload(d->dia_precursor_cycle, npos, &dpc, r->allocs, r->bytes, r->stream) ||
+      upload(d->rt_values, d->n_frames, &rt, r->allocs, r->bytes, r->stream) ||
+      upload(d->mobility_values, d->scans, &mob, r->allocs, r->bytes, r->stream) ||
+      upload(d->mz_values, d->n_tof, &mz, r->allocs, r->bytes, r->stream) ||
+      upload(d->tof_indptr, d->n_tof + 1, &ip, r->allocs, r->bytes, r->stream) ||
+      upload(d->push_indices, d->n_events, &push, r->allocs, r->bytes, r->stream, 16) ||
+      upload(d->intensity_values, d->n_events, &it, r->allocs, r->bytes, r->stream, 16)) {
+    adb_rawfile_destroy(r);
+    return 1;
+  }
+  v.cycle = cyc; v.Fr = d->frames_per_cycle; v.Sc = d->scans; v.dia_precursor_cycle = dpc; v.rt_values = rt;
+  v.n_frames = d->n_frames; v.mobility_values = mob; v.mz_values = mz; v.n_tof = d->n_tof; v.tof_indptr = ip;
+  v.push = push; v.intensity = it; v.n_events = d->n_events; v.zeroth_frame = d->zeroth_frame;
+  v.precursor_cycle_max_index = d->precursor_cycle_max_index; v.scan_max_index = d->scan_max_index;
+  v.frame_max_index = d->frame_max_index; v.obs_unique_per_scan = unique;
+  r->rt4_host.assign(d->rt_values, d->rt_values + d->n_frames);
+  r->mob4_host.assign(d->mobility_values, d->mobility_values + d->scans);
+  void* st = nullptr;
+  if (cudaMalloc(&st, sizeof(uint32_t)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc status failed"); }
+  r->d_status = (uint32_t*)st;
+  cudaMemsetAsync(r->d_status, 0, sizeof(uint32_t), r->stream);
+  cudaError_t e = cudaStreamSynchronize(r->stream);
+  if (e != cudaSuccess) { adb_rawfile_destroy(r); return fail(std::string("raw file upload failed: ") + cudaGetErrorString(e)); }
+  *out = r;
+  return 0;
+}
+
 void adb_rawfile_destroy(adb_rawfile_t* r) {
   if (!r) return;
   cudaSetDevice(r->device);
@@ -518,7 +769,7 @@ void adb_rawfile_destroy(adb_rawfile_t* r) {
   for (void* p : r->allocs) cudaFree(p);
   if (r->d_status) cudaFree(r->d_status);
   DeviceBuffer* bufs[] = {&r->kern, &r->order_keys, &r->order_vals, &r->order_tmp, &r->sel_ws, &r->cont, &r->cand_in,
-                          &r->flags, &r->offs, &r->scan_tmp, &r->count, &r->scores, &r->score_ws, &r->staging};
+                          &r->flags, &r->offs, &r->scan_tmp, &r->count, &r->scores, &r->score_ws, &r->staging, &r->extent};
   for (DeviceBuffer* b : bufs) b->release();
   for (int i = 0; i < 6; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
   if (r->stream) cudaStreamDestroy(r->stream);
@@ -654,14 +905,15 @@ int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scori
   // H2D of the candidate table
   if (raw->cand_in.reserve(cand_in_bytes(std::max<int64_t>(n, 1)))) return 1;
   CandInPtrs c = carve_cand_in(raw->cand_in.ptr, std::max<int64_t>(n, 1));
-  int64_t c_max = 0;
+  int64_t c_max = 0, s_max = 0;
   if (n > 0) {
     const size_t N = (size_t)n;
-    const int64_t P = lib->dev.n_precursors, L = raw->dev.cycle_len;
+    const int64_t P = lib->dev.n_precursors, L = raw->is4d ? 1 : raw->dev.cycle_len;  // 4-D: extent in frames
     for (int64_t i = 0; i < n; i++) {
       if (cand->lib_row[i] < 0 || cand->lib_row[i] >= P) return fail("candidate " + std::to_string(i) + " refers to a precursor outside the library");
       if (cand->frame_start[i] >= 0 && cand->frame_stop[i] >= 0)
         c_max = std::max<int64_t>(c_max, cand->frame_stop[i] / L - cand->frame_start[i] / L);
+      s_max = std::max<int64_t>(s_max, cand->scan_stop[i] - cand->scan_start[i]);
     }
     CUDA_TRY(cudaMemcpyAsync(c.lib_row, cand->lib_row, 8 * N, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(c.rank, cand->rank, N, cudaMemcpyHostToDevice, st));
@@ -675,8 +927,8 @@ int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scori
   raw->d_cand = DevCandidatesIn{n, c.lib_row, c.rank, c.scan_start, c.scan_stop, c.scan_center, c.frame_start, c.frame_stop, c.frame_center};
   raw->n_cand = n;
   CUDA_TRY(cudaEventRecord(raw->ev[1], st));
-  if (c_max > 4096) return fail("a candidate spans more than 4096 cycles");
-  if (run_scoring(raw, lib, cfg, c_max)) return 1;
+  if (!raw->is4d && c_max > 4096) return fail("a candidate spans more than 4096 cycles");
+  if (run_scoring(raw, lib, cfg, c_max, s_max)) return 1;
   CUDA_TRY(cudaEventRecord(raw->ev[2], st));
   if (check_status(raw, "adb_score_candidates")) return 1;
   if (adb_fetch_scores(raw, out, nullptr, nullptr)) return 1;
@@ -691,7 +943,11 @@ int adb_score_candidates_resident(adb_rawfile_t* raw, adb_library_t* lib, const 
   cudaStream_t st = raw->stream;
   CUDA_TRY(cudaEventRecord(raw->ev[0], st));
   CUDA_TRY(cudaEventRecord(raw->ev[1], st));
-  if (run_scoring(raw, lib, cfg, 64)) return 1;  // selection emits at most 2 * max_size_rt - 1 cycles
+  if (raw->is4d) {
+    int64_t s_max = 0, f_max = 0;
+    if (resident_extents(raw, &s_max, &f_max)) return 1;
+    if (run_scoring(raw, lib, cfg, f_max, s_max)) return 1;
+  } else if (run_scoring(raw, lib, cfg, 64)) return 1;  // selection emits at most 2 * max_size_rt - 1 cycles
   CUDA_TRY(cudaEventRecord(raw->ev[2], st));
   if (check_status(raw, "adb_score_candidates_resident")) return 1;
   CUDA_TRY(cudaEventRecord(raw->ev[3], st));

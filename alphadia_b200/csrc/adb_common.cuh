@@ -48,6 +48,32 @@ struct DevRaw {
   float bucket_lo, bucket_width, bucket_inv_width;
 };
 
+// timsTOF (4-D) raw file resident in HBM: the TimsTOFTransposeJIT arrays the hot path reads
+// (alphadia/search/jitclasses/bruker_jit.py:20-137), CSR by tof index.
+struct DevRaw4 {
+  const double* cycle;                 // [Fr][Sc][2]
+  int64_t Fr, Sc;                      // cycle.shape[1], cycle.shape[2]
+  const int64_t* dia_precursor_cycle;  // [Fr * Sc]
+  const double* rt_values;             // [n_frames]
+  int64_t n_frames;
+  const double* mobility_values;       // [Sc], descending
+  const double* mz_values;             // [n_tof]
+  int64_t n_tof;
+  const int64_t* tof_indptr;           // [n_tof + 1]
+  const uint32_t* push;                // [n_events] ascending inside a tof row
+  const uint16_t* intensity;           // [n_events]
+  int64_t n_events;
+  int64_t zeroth_frame;
+  int64_t precursor_cycle_max_index;
+  int64_t scan_max_index;
+  int64_t frame_max_index;
+  // 1 when no observation id occurs in two different frames of the cycle at the same scan: then the events of one
+  // tof row always fall into distinct cube cells and may be processed concurrently (adb_score4d.cu)
+  int32_t obs_unique_per_scan;
+};
+
+#define ADB_MAX_OBS4 16  // observation ids (frames of the cycle) one 4-D candidate may hit
+
 struct DevLib {
   int64_t n_precursors;
   const uint32_t* precursor_idx;
@@ -129,6 +155,20 @@ int64_t adb_score_workspace_floats(int top_k, int64_t c_max);
 void adb_launch_fragcomp(int64_t n_windows, const int64_t* d_ws, const int64_t* d_we, const void* d_rt,
                          const int64_t* d_fs, const int64_t* d_fe, const void* d_mz, int is_f64, double rt_tol,
                          double ppm_tol, uint8_t* d_valid, cudaStream_t stream, int* n_launches);
+
+// 4-D (timsTOF) launchers
+struct Select4Geometry { int s_cap, c_cap, max_layers; };
+size_t adb_select4d_ws_bytes_per_cta(const Select4Geometry& g);
+int adb_select4d_grid(int device, const DevRaw4& raw, const Select4Geometry& g, int kh, int kw, size_t* dyn_smem, int* tile_in_smem);
+void adb_launch_select4d(const DevRaw4& raw, const DevLib& lib, const adb_selection_config& cfg, const double* d_kernel, int kh,
+                         int kw, DevCandidatesOut out, int64_t n, const int32_t* d_order, uint32_t* d_status,
+                         const Select4Geometry& g, void* workspace, size_t ws_per_cta, int grid, size_t dyn_smem,
+                         int tile_in_smem, cudaStream_t stream, int* n_launches);
+int adb_score4d_resident_warps(int device);
+int64_t adb_score4d_workspace_floats(int top_k, int n_iso, int64_t s_max, int64_t c_max, int nobs_cap);
+void adb_launch_score4d(const DevRaw4& raw, const DevLib& lib, const adb_scoring_config& cfg, DevCandidatesIn cand,
+                        DevScoresOut out, float* d_workspace, int64_t workspace_floats_per_warp, int n_resident_warps,
+                        int s_cap, int c_cap, const int32_t* d_order, uint32_t* d_status, cudaStream_t stream, int* n_launches);
 
 size_t adb_compact_temp_bytes(int64_t n_rows);
 void adb_launch_compact_ex(DevCandidatesOut cont, int64_t candidate_count, int* d_flags, int* d_offs, void* d_tmp,
@@ -212,6 +252,29 @@ __device__ __forceinline__ AdbFound adb_spectrum_lower_bound(const DevRaw& raw, 
   AdbFound f = adb_finish_lower_bound(raw.mz, lo, hi, v);
   f.inside = f.idx < r.y;
   return f;
+}
+
+// ---- 4-D helpers -----------------------------------------------------------------------------
+// np.searchsorted(a, v, "left") on float64
+__device__ __forceinline__ int64_t adb_lower_bound_f64(const double* __restrict__ a, int64_t n, double v) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// first event in [lo, hi) of a tof row whose push index is >= p (rows are sorted by push)
+__device__ __forceinline__ int64_t adb_row_lower_bound(const uint32_t* __restrict__ push, int64_t lo, int64_t hi, int64_t p) {
+  if (p <= 0) return lo;
+  if (p > 0xFFFFFFFFLL) return hi;
+  const uint32_t pv = (uint32_t)p;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg(push + mid) < pv) lo = mid + 1; else hi = mid;
+  }
+  return lo;
 }
 
 __device__ __forceinline__ int64_t adb_wrap0(int64_t v, int64_t limit) {

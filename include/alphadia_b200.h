@@ -9,6 +9,8 @@
  * Reference interfaces replaced (paths relative to the reference repo root):
  *   adb_rawfile3d_create   <- DiaData.to_jitclass() -> AlphaRawJIT(...)        alphadia/raw_data/alpharaw_wrapper.py:138-156,
  *                                                                               alphadia/search/jitclasses/alpharaw_jit.py:98-138
+ *   adb_rawfile4d_create   <- DiaData.to_jitclass() -> TimsTOFTransposeJIT(...) alphadia/raw_data/bruker.py:119-152,
+ *                                                                               alphadia/search/jitclasses/bruker_jit.py:20-137
  *   adb_library_create     <- PrecursorFlatContainer / FragmentContainer       alphadia/search/selection/config_df.py:184-223,
  *                                                                               alphadia/search/jitclasses/fragment_container.py:12-45
  *   adb_select_candidates  <- _select_candidates_pjit(range(n), ...)           alphadia/search/selection/selection.py:78-203,656-666
@@ -199,6 +201,9 @@ const char* adb_version(void);
 int adb_device_count(void);
 
 int adb_rawfile3d_create(const adb_rawfile3d_desc* desc, int device, adb_rawfile_t** out);
+/* timsTOF raw file: DiaData.to_jitclass() -> TimsTOFTransposeJIT(...) (alphadia/raw_data/bruker.py:119-152).  The
+ * same adb_select_candidates / adb_score_candidates entry points then run the 4-D kernels on the handle. */
+int adb_rawfile4d_create(const adb_rawfile4d_desc* desc, int device, adb_rawfile_t** out);
 void adb_rawfile_destroy(adb_rawfile_t* raw);
 int64_t adb_rawfile_device_bytes(const adb_rawfile_t* raw);
 

@@ -276,3 +276,161 @@ def test_resident_pipeline_matches_host_pipeline(engine):
     assert np.array_equal(res["features"], ref["features"], equal_nan=True)
     assert draw.kernel_launches > 0
     dlib.close(); draw.close()
+
+
+# ---- timsTOF (4-D) -------------------------------------------------------------------------------
+def _sel_cfg_4d(p, **kw):
+    args = dict(kw)
+    rt_tol = args.pop("rt_tolerance", p["rt_tolerance"])
+    mob_tol = args.pop("mobility_tolerance", p["mobility_tolerance"])
+    return H.selection_config(rt_tol, mobility_tolerance=mob_tol, **args).to_struct()
+
+
+def _candidates_4d(oracle_lib, raw, lib, p):
+    arrs = oracle_lib.select_candidates_4d(raw, lib, _sel_cfg_4d(p), H.default_kernel(raw))
+    m = arrs["score"] > 0
+    return {c: arrs[c][m] for c in INT_COLS}
+
+
+def test_selection_4d_matches_oracle_and_golden(engine, oracle_lib):
+    raw, lib, p, draw, dlib = _device_objects(engine, "parity_4d")
+    assert draw.is_4d
+    cfg = _sel_cfg_4d(p)
+    kernel = H.default_kernel(raw)
+    got = engine.select_candidates(draw, dlib, cfg, kernel)
+    ref = oracle_lib.select_candidates_4d(raw, lib, cfg, kernel)
+    assert (ref["score"] > 0).sum() > 100
+    assert_candidates_equal(got, ref)
+    g = H.load_golden("parity_4d")
+    if g is not None and str(g["input_checksum"]) == H.input_checksum(*H.workload("parity_4d")[:3]):
+        m = got["score"] > 0
+        assert m.sum() == len(g["cand_precursor_idx"])
+        for c in INT_COLS:
+            assert np.array_equal(got[c][m].astype(np.int64), g["cand_" + c].astype(np.int64)), c
+        assert np.array_equal(got["score"][m], g["cand_score"])
+    dlib.close(); draw.close()
+
+
+@pytest.mark.parametrize("kw", [dict(candidate_count=1), dict(candidate_count=5, join_close_candidates=True,
+                                                               join_close_candidates_scan_threshold=0.01),
+                                dict(use_weighted_score=False), dict(rt_tolerance=5.0), dict(mobility_tolerance=0.2),
+                                dict(rt_tolerance=100.0, mobility_tolerance=0.4)])
+def test_selection_4d_config_variants(engine, oracle_lib, kw):
+    raw, lib, p, draw, dlib = _device_objects(engine, "parity_4d")
+    cfg = _sel_cfg_4d(p, **kw)
+    kernel = H.default_kernel(raw)
+    got = engine.select_candidates(draw, dlib, cfg, kernel)
+    ref = oracle_lib.select_candidates_4d(raw, lib, cfg, kernel)
+    assert_candidates_equal(got, ref)
+    assert (got["score"] > 0).sum() > 0
+    dlib.close(); draw.close()
+
+
+@pytest.mark.parametrize("variant", list(SCORING_VARIANTS))
+def test_scoring_4d_matches_oracle(engine, oracle_lib, variant):
+    raw, lib, p, draw, dlib = _device_objects(engine, "parity_4d")
+    cand = _candidates_4d(oracle_lib, raw, lib, p)
+    cin, keep = H.candidates_in_from_arrays(lib, cand)
+    cfg = H.scoring_config(**SCORING_VARIANTS[variant]).to_struct()
+    got = engine.score_candidates(draw, dlib, cfg, cin)
+    ref = oracle_lib.score_candidates_4d(raw, lib, cfg, cin)
+    assert ref["valid"].sum() > 50
+    assert np.abs(ref["features"][:, 29]).max() > 0 and np.abs(ref["features"][:, 39]).max() > 0
+    assert_scores_close(got, ref, what=f"parity_4d/{variant}")
+    dlib.close(); draw.close()
+
+
+def test_scoring_4d_matches_reference_golden(engine):
+    name = "parity_4d"
+    g = H.load_golden(name)
+    raw, pdf, fdf, lib, p = H.workload(name)
+    if g is None or str(g["input_checksum"]) != H.input_checksum(raw, pdf, fdf):
+        pytest.skip("golden not applicable")
+    draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+    cand = {c: g["cand_" + c] for c in INT_COLS}
+    cin, keep = H.candidates_in_from_arrays(lib, cand)
+    got = engine.score_candidates(draw, dlib, H.scoring_config().to_struct(), cin)
+    v = got["valid"].astype(bool)
+    assert np.array_equal(keep["precursor_idx"][v], g["feat_precursor_idx"])
+    assert np.array_equal(keep["rank"][v], g["feat_rank"])
+    F, G = got["features"][v], g["feat_matrix"]
+    floor = feature_scale_floor(G)
+    err = np.abs(F - G) / np.maximum(np.maximum(np.abs(F), np.abs(G)), floor[None, :])
+    err = np.where(np.isnan(F) & np.isnan(G), 0.0, err)
+    assert err.max() < RTOL
+    dlib.close(); draw.close()
+
+
+def test_scoring_4d_edge_cases(engine, oracle_lib):
+    """Hand-made 4-D candidate windows: 1-scan and full-height windows, first/last cycles, huge windows."""
+    raw, pdf, fdf, lib, p = H.workload("parity_4d")
+    draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+    cfg = H.scoring_config().to_struct()
+    Fr, Sc, z = raw.cycle.shape[1], raw.cycle.shape[2], raw.zeroth_frame
+    cin, _ = H.candidates_in_from_arrays(lib, {c: np.zeros(0, np.int64) for c in INT_COLS})
+    assert engine.score_candidates(draw, dlib, cfg, cin)["features"].shape == (0, 46)
+    rng = np.random.default_rng(6)
+    n = 300
+    pidx = rng.integers(0, len(pdf), n)
+    ncyc = raw.precursor_cycle_max_index
+    centers = rng.integers(0, ncyc, n)
+    half = rng.choice([0, 1, 2, 3, 7, 14, 30], n)
+    c0 = np.clip(centers - half, 0, ncyc - 1)
+    c1 = np.clip(centers + half + 1, 1, ncyc)
+    sc_c = rng.integers(0, Sc, n)
+    sh = rng.choice([0, 1, 4, 9, 20, Sc], n)
+    s0 = np.clip(sc_c - sh, 0, Sc - 1)
+    s1 = np.clip(sc_c + sh + 1, 1, Sc)
+    cand = dict(precursor_idx=lib["precursor_idx"][pidx].astype(np.int64), rank=np.arange(n) % 7,
+                scan_center=sc_c, scan_start=s0, scan_stop=s1,
+                frame_center=np.minimum(centers * Fr + z, raw.frame_max_index - 1), frame_start=c0 * Fr + z,
+                frame_stop=np.minimum(c1 * Fr + z, raw.frame_max_index))
+    cin, keep = H.candidates_in_from_arrays(lib, cand)
+    got = engine.score_candidates(draw, dlib, cfg, cin)
+    ref = oracle_lib.score_candidates_4d(raw, lib, cfg, cin)
+    assert ref["valid"].sum() > 20
+    assert_scores_close(got, ref, what="edge4d")
+    dlib.close(); draw.close()
+
+
+def test_operator_classes_4d(engine, oracle_lib):
+    """CandidateSelection -> CandidateScoring on a timsTOF-shaped raw file through the reference-shaped API."""
+    from alphadia_b200 import CandidateScoring, CandidateSelection
+
+    raw, pdf, fdf, lib, p = H.workload("parity_4d")
+    scfg = H.selection_config(p["rt_tolerance"], mobility_tolerance=p["mobility_tolerance"])
+    sel = CandidateSelection(raw, pdf.copy(), fdf.copy(), scfg, rt_column="rt_library", mobility_column="mobility_library",
+                             precursor_mz_column="mz_library", fragment_mz_column="mz_library", fwhm_rt=5.0, fwhm_mobility=0.01)
+    assert sel.kernel.shape == (30, 30)
+    cand_df = sel(thread_count=4)
+    g = H.load_golden("parity_4d")
+    if g is not None and str(g["input_checksum"]) == H.input_checksum(raw, pdf, fdf):
+        for c in INT_COLS:
+            assert np.array_equal(cand_df[c].values.astype(np.int64), g["cand_" + c].astype(np.int64)), c
+    scorer = CandidateScoring(dia_data=raw, precursors_flat=pdf.copy(), fragments_flat=fdf.copy(), config=H.scoring_config(),
+                              rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+                              fragment_mz_column="mz_library")
+    feat_df, frag_df = scorer(cand_df.copy(), thread_count=4, include_decoy_fragment_features=True)
+    if g is not None and str(g["input_checksum"]) == H.input_checksum(raw, pdf, fdf):
+        assert np.array_equal(feat_df["precursor_idx"].values, g["feat_precursor_idx"])
+        assert len(frag_df) == len(g["frag_mz_library"])
+    assert feat_df["mobility_fwhm"].abs().max() > 0
+
+
+def test_resident_pipeline_4d(engine):
+    raw, lib, p, draw, dlib = _device_objects(engine, "parity_4d")
+    cfg = _sel_cfg_4d(p)
+    kernel = H.default_kernel(raw)
+    host = engine.select_candidates(draw, dlib, cfg, kernel)
+    n = engine.select_candidates_resident(draw, dlib, cfg, kernel)
+    m = host["score"] > 0
+    assert n == m.sum()
+    scfg = H.scoring_config().to_struct()
+    engine.score_candidates_resident(draw, dlib, scfg)
+    res = engine.fetch_scores(draw, n, 12)
+    cand = {c: host[c][m] for c in INT_COLS}
+    cin, keep = H.candidates_in_from_arrays(lib, cand)
+    ref = engine.score_candidates(draw, dlib, scfg, cin)
+    assert np.array_equal(res["valid"], ref["valid"])
+    assert np.array_equal(res["features"], ref["features"], equal_nan=True)
+    dlib.close(); draw.close()
