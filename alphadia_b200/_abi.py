@@ -104,6 +104,43 @@ class CandidatesIn(C.Structure):
     ]
 
 
+class CandidateTable(C.Structure):
+    """adb_candidate_table: compacted candidate rows (score > 0); the first nine fields are laid out like CandidatesIn."""
+    _fields_ = [
+        ("n", C.c_int64), ("lib_row", c_i64p), ("rank", c_u8p),
+        ("scan_start", c_i64p), ("scan_stop", c_i64p), ("scan_center", c_i64p),
+        ("frame_start", c_i64p), ("frame_stop", c_i64p), ("frame_center", c_i64p),
+        ("precursor_idx", c_u32p), ("score", c_f32p),
+    ]
+
+
+TABLE_COLUMNS = (("lib_row", np.int64), ("rank", np.uint8), ("scan_start", np.int64), ("scan_stop", np.int64),
+                 ("scan_center", np.int64), ("frame_start", np.int64), ("frame_stop", np.int64), ("frame_center", np.int64),
+                 ("precursor_idx", np.uint32), ("score", np.float32))
+
+
+def alloc_candidate_table(n: int, alloc=np.zeros):
+    """Host buffers for adb_fetch_candidate_table; ``alloc(shape, dtype)`` may hand out pinned memory."""
+    arrs = {k: alloc(max(n, 1), dt) for k, dt in TABLE_COLUMNS}
+    return arrs
+
+
+def candidate_table_struct(arrs: dict, n: int) -> CandidateTable:
+    d = CandidateTable()
+    d.n = n
+    for k, _ in TABLE_COLUMNS:
+        setattr(d, k, ptr(arrs[k]))
+    return d
+
+
+def candidates_in_from_table(arrs: dict, n: int) -> CandidatesIn:
+    d = CandidatesIn()
+    d.n = n
+    for k in ("lib_row", "rank", "scan_start", "scan_stop", "scan_center", "frame_start", "frame_stop", "frame_center"):
+        setattr(d, k, ptr(arrs[k]))
+    return d
+
+
 class ScoresOut(C.Structure):
     _fields_ = [
         ("features", c_f32p), ("valid", c_u8p),

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "adb_library_create", "adb_library_destroy",
     "adb_select_candidates", "adb_score_candidates", "adb_fragment_competition",
     "adb_select_candidates_resident", "adb_score_candidates_resident",
-    "adb_fetch_candidates", "adb_fetch_scores", "adb_resident_score_table",
+    "adb_fetch_candidates", "adb_fetch_candidate_table", "adb_fetch_scores", "adb_resident_score_table",
     "adb_last_timing", "adb_kernel_launches", "adb_last_main_kernel_ms",
 ]
 
@@ -208,6 +208,15 @@ def score_candidates_resident(dev_raw, dev_lib, cfg_struct) -> None:
 def fetch_candidates(dev_raw, n_rows: int) -> dict:
     od, arrs = _abi.alloc_candidates_out(n_rows)
     check(load().adb_fetch_candidates(dev_raw.handle, C.byref(od)), "adb_fetch_candidates")
+    return arrs
+
+
+def fetch_candidate_table(dev_raw, n: int, arrs: dict | None = None) -> dict:
+    """Rows with score > 0 of the last resident selection (container order), int64 index columns."""
+    if arrs is None:
+        arrs = _abi.alloc_candidate_table(n)
+    t = _abi.candidate_table_struct(arrs, n)
+    check(load().adb_fetch_candidate_table(dev_raw.handle, C.byref(t)), "adb_fetch_candidate_table")
     return arrs
 
 

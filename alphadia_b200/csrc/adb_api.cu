@@ -107,6 +107,10 @@ struct adb_rawfile {
   DevCandidatesOut d_cont{};
   int64_t n_cand = 0;
   DevCandidatesIn d_cand{};
+  const uint32_t* d_cand_pidx = nullptr;  // compacted precursor_idx / score of the resident candidates
+  const float* d_cand_score = nullptr;
+  cudaStream_t copy_stream = nullptr;     // D2H of finished scoring chunks overlaps the next chunk's kernel
+  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   DevScoresOut d_scores{};
   int64_t scores_n = 0;
   int scores_k = 0;
@@ -156,6 +160,8 @@ size_t container_bytes(int64_t n) { return 9 * (((size_t)n * 4 + 255) & ~(size_t
 struct CandInPtrs {
   int64_t *lib_row, *scan_start, *scan_stop, *scan_center, *frame_start, *frame_stop, *frame_center;
   uint8_t* rank;
+  uint32_t* precursor_idx;  // compacted container columns kept for adb_fetch_candidate_table
+  float* score;
 };
 CandInPtrs carve_cand_in(void* base, int64_t n) {
   CandInPtrs c{};
@@ -170,9 +176,11 @@ CandInPtrs carve_cand_in(void* base, int64_t n) {
   c.frame_stop = (int64_t*)take(8 * N);
   c.frame_center = (int64_t*)take(8 * N);
   c.rank = (uint8_t*)take(N);
+  c.precursor_idx = (uint32_t*)take(4 * N);
+  c.score = (float*)take(4 * N);
   return c;
 }
-size_t cand_in_bytes(int64_t n) { return 8 * (((size_t)n * 8 + 255) & ~(size_t)255) + 512; }
+size_t cand_in_bytes(int64_t n) { return 10 * (((size_t)n * 8 + 255) & ~(size_t)255) + 512; }
 
 DevScoresOut carve_scores(void* base, int64_t n, int k) {
   DevScoresOut s{};
@@ -247,7 +255,7 @@ __global__ void order_key_kernel(DevRaw raw, DevLib lib, uint64_t* keys, int32_t
   vals[i] = (int32_t)i;
 }
 
-__global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn cand, uint64_t* keys, int32_t* vals) {
+__global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn cand, int64_t chunk_len, uint64_t* keys, int32_t* vals) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cand.n) return;
   float mz = lib.mz[cand.lib_row[i]];
@@ -256,7 +264,7 @@ __global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn c
     if ((double)mz <= raw.cycle[2 * j + 1] && (double)mz >= raw.cycle[2 * j]) { win = (uint32_t)j; break; }
   int64_t fs = cand.frame_start[i];
   uint32_t f = fs < 0 ? 0u : (fs > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)fs);
-  keys[i] = ((uint64_t)win << 32) | f;
+  keys[i] = ((uint64_t)(i / chunk_len) << 48) | ((uint64_t)win << 32) | f;  // chunk (output row block), window, time
   vals[i] = (int32_t)i;
 }
 
@@ -546,7 +554,9 @@ int run_compaction(adb_rawfile* raw) {
   CUDA_TRY(cudaMemsetAsync(raw->count.ptr, 0, sizeof(int64_t), st));
   adb_launch_compact_ex(raw->d_cont, raw->cont_count, raw->flags.as<int>(), raw->offs.as<int>(), raw->scan_tmp.ptr, tmp,
                         c.lib_row, c.rank, c.scan_start, c.scan_stop, c.scan_center, c.frame_start, c.frame_stop,
-                        c.frame_center, raw->count.as<int64_t>(), st, &raw->launches);
+                        c.frame_center, c.precursor_idx, c.score, raw->count.as<int64_t>(), st, &raw->launches);
+  raw->d_cand_pidx = c.precursor_idx;
+  raw->d_cand_score = c.score;
   CUDA_TRY(cudaGetLastError());
   int64_t n = 0;
   CUDA_TRY(cudaMemcpyAsync(&n, raw->count.ptr, sizeof(n), cudaMemcpyDeviceToHost, st));
@@ -556,12 +566,40 @@ int run_compaction(adb_rawfile* raw) {
   return 0;
 }
 
-int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cfg, int64_t c_max_hint, int64_t s_max_hint = 0) {
+// D2H of rows [r0, r1) of the resident score tables into the caller's (row-major) host tables
+int copy_score_rows(adb_rawfile* raw, adb_scores_out* out, int64_t r0, int64_t r1, cudaStream_t st) {
+  if (r1 <= r0) return 0;
+  const size_t K = (size_t)raw->scores_k, a = (size_t)r0, N = (size_t)(r1 - r0);
+  const DevScoresOut& s = raw->d_scores;
+  CUDA_TRY(cudaMemcpyAsync(out->features + a * ADB_NUM_FEATURES, s.features + a * ADB_NUM_FEATURES, 4 * N * ADB_NUM_FEATURES, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out->valid + a, s.valid + a, N, cudaMemcpyDeviceToHost, st));
+  float* hf[] = {out->fragment_mz_library, out->fragment_mz, out->fragment_mz_observed, out->fragment_height,
+                 out->fragment_intensity, out->fragment_mass_error, out->fragment_correlation};
+  float* df[] = {s.fragment_mz_library, s.fragment_mz, s.fragment_mz_observed, s.fragment_height,
+                 s.fragment_intensity, s.fragment_mass_error, s.fragment_correlation};
+  for (int i = 0; i < 7; i++) CUDA_TRY(cudaMemcpyAsync(hf[i] + a * K, df[i] + a * K, 4 * N * K, cudaMemcpyDeviceToHost, st));
+  uint8_t* hu[] = {out->fragment_position, out->fragment_number, out->fragment_type, out->fragment_charge, out->fragment_loss_type};
+  uint8_t* du[] = {s.fragment_position, s.fragment_number, s.fragment_type, s.fragment_charge, s.fragment_loss_type};
+  for (int i = 0; i < 5; i++) CUDA_TRY(cudaMemcpyAsync(hu[i] + a * K, du[i] + a * K, N * K, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+// host_out != nullptr: the candidates are scored in up to 4 row blocks and every finished block is copied to the host on a
+// second stream while the next block is being scored
+int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cfg, int64_t c_max_hint, int64_t s_max_hint = 0,
+                adb_scores_out* host_out = nullptr) {
   if (raw->device != lib->device) return fail("raw file and library live on different devices");
   if (cfg->top_k_fragments < 1 || cfg->top_k_fragments > ADB_MAX_FRAGMENTS)
     return fail("top_k_fragments must be in [1, " + std::to_string(ADB_MAX_FRAGMENTS) + "]");
   if (cfg->top_k_isotopes < 1) return fail("top_k_isotopes must be >= 1");
-  if (raw->is4d) return run_scoring4d(raw, lib, cfg, s_max_hint, c_max_hint /* frames */);
+  if (raw->is4d) {
+    if (run_scoring4d(raw, lib, cfg, s_max_hint, c_max_hint /* frames */)) return 1;
+    if (host_out) {
+      CUDA_TRY(cudaEventRecord(raw->ev[2], raw->stream));
+      if (copy_score_rows(raw, host_out, 0, raw->scores_n, raw->stream)) return 1;
+    }
+    return 0;
+  }
   cudaStream_t st = raw->stream;
   const int64_t n = raw->d_cand.n;
   const int K = (int)cfg->top_k_fragments;
@@ -579,6 +617,8 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   // processing order: (quad window of the precursor, frame_start) so that co-resident tiles read the same
   // spectra; results do not depend on it (disjoint output rows)
   int32_t* d_order = nullptr;
+  const int n_chunks = (host_out && n >= 200000) ? 4 : 1;
+  const int64_t chunk_len = std::max<int64_t>((n + n_chunks - 1) / n_chunks, 1);
   if (n > 1 && n < 2000000000LL) {
     if (raw->order_keys.reserve(sizeof(uint64_t) * 2 * (size_t)n)) return 1;
     if (raw->order_vals.reserve(sizeof(int32_t) * 2 * (size_t)n)) return 1;
@@ -586,19 +626,42 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
     uint64_t* k_out = k_in + n;
     int32_t* v_in = raw->order_vals.as<int32_t>();
     int32_t* v_out = v_in + n;
-    score_order_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->dev, lib->dev, raw->d_cand, k_in, v_in);
+    score_order_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->dev, lib->dev, raw->d_cand, chunk_len, k_in, v_in);
     raw->launches++;
+    const int end_bit = n_chunks > 1 ? 52 : 48;
     size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 48, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, st);
     if (raw->order_tmp.reserve(tmp)) return 1;
-    cub::DeviceRadixSort::SortPairs(raw->order_tmp.ptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, 48, st);
+    cub::DeviceRadixSort::SortPairs(raw->order_tmp.ptr, tmp, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, st);
     raw->launches += 4;
     d_order = v_out;
   }
   CUDA_TRY(cudaEventRecord(raw->ev[4], st));
-  adb_launch_score(raw->dev, lib->dev, *cfg, raw->d_cand, raw->d_scores, raw->score_ws.as<float>(), ws_floats, tiles,
-                   d_order, raw->d_status, st, &raw->launches);
-  CUDA_TRY(cudaEventRecord(raw->ev[5], st));
+  if (n_chunks == 1 || d_order == nullptr) {
+    adb_launch_score(raw->dev, lib->dev, *cfg, raw->d_cand, raw->d_scores, raw->score_ws.as<float>(), ws_floats, tiles,
+                     d_order, raw->d_status, st, &raw->launches);
+    CUDA_TRY(cudaEventRecord(raw->ev[5], st));
+    if (host_out) {
+      CUDA_TRY(cudaEventRecord(raw->ev[2], st));
+      if (copy_score_rows(raw, host_out, 0, n, st)) return 1;
+    }
+  } else {
+    for (int k = 0; k < n_chunks; k++) {
+      const int64_t c0 = std::min<int64_t>(k * chunk_len, n), c1 = std::min<int64_t>(c0 + chunk_len, n);
+      if (c1 <= c0) continue;
+      DevCandidatesIn part = raw->d_cand;
+      part.n = c1 - c0;  // the kernel visits order[c0 .. c1): the (window, time)-sorted rows of block k
+      adb_launch_score(raw->dev, lib->dev, *cfg, part, raw->d_scores, raw->score_ws.as<float>(), ws_floats, tiles,
+                       d_order + c0, raw->d_status, st, &raw->launches);
+      CUDA_TRY(cudaEventRecord(raw->chunk_ev[k], st));
+      CUDA_TRY(cudaStreamWaitEvent(raw->copy_stream, raw->chunk_ev[k], 0));
+      if (copy_score_rows(raw, host_out, c0, c1, raw->copy_stream)) return 1;
+    }
+    CUDA_TRY(cudaEventRecord(raw->ev[5], st));
+    CUDA_TRY(cudaEventRecord(raw->ev[2], st));
+    CUDA_TRY(cudaEventRecord(raw->chunk_ev[7], raw->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, raw->chunk_ev[7], 0));  // the handle's stream is done when the copies are
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -634,6 +697,8 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
   r->device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&r->ev[i]));
+  CUDA_TRY(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreateWithFlags(&r->chunk_ev[i], cudaEventDisableTiming));
   cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, device);
   DevRaw& v = r->dev;
   double* cyc; float *rt, *mob, *mz, *it; int64_t *ps, *pe;
@@ -731,6 +796,8 @@ int adb_rawfile4d_create(const adb_rawfile4d_desc* d, int device, adb_rawfile_t*
   r->is4d = 1;
   CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&r->ev[i]));
+  CUDA_TRY(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreateWithFlags(&r->chunk_ev[i], cudaEventDisableTiming));
   cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, device);
   DevRaw4& v = r->dev4;
   double *cyc, *rt, *mob, *mz; int64_t *dpc, *ip; uint32_t* push; uint16_t* it;
@@ -772,6 +839,8 @@ void adb_rawfile_destroy(adb_rawfile_t* r) {
                           &r->flags, &r->offs, &r->scan_tmp, &r->count, &r->scores, &r->score_ws, &r->staging, &r->extent};
   for (DeviceBuffer* b : bufs) b->release();
   for (int i = 0; i < 6; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
+  for (int i = 0; i < 8; i++) if (r->chunk_ev[i]) cudaEventDestroy(r->chunk_ev[i]);
+  if (r->copy_stream) { cudaStreamSynchronize(r->copy_stream); cudaStreamDestroy(r->copy_stream); }
   if (r->stream) cudaStreamDestroy(r->stream);
   delete r;
 }
@@ -783,37 +852,47 @@ int adb_library_create(const adb_library_desc* d, int device, adb_library_t** ou
   if (!d || !out) return fail("null argument");
   if (d->n_isotopes < 1) return fail("library needs at least one isotope column");
   if (set_device(device)) return 1;
-  adb_library* l = new adb_library();
-  l->device = device;
-  cudaStream_t st = nullptr;  // default stream, synchronous
-  DevLib& v = l->dev;
   const int64_t P = d->n_precursors, NF = d->n_fragments;
-  uint32_t *a, *b, *c; uint8_t* ch; float *rt, *mob, *mz, *iso, *fl, *fm, *fi; uint8_t *t, *lt, *fc, *fn, *fp, *fcard;
-  if (upload(d->precursor_idx, P, &a, l->allocs, l->bytes, st) || upload(d->frag_start_idx, P, &b, l->allocs, l->bytes, st) ||
-      upload(d->frag_stop_idx, P, &c, l->allocs, l->bytes, st) || upload(d->charge, P, &ch, l->allocs, l->bytes, st) ||
-      upload(d->rt, P, &rt, l->allocs, l->bytes, st) || upload(d->mobility, P, &mob, l->allocs, l->bytes, st) ||
-      upload(d->mz, P, &mz, l->allocs, l->bytes, st) || upload(d->isotopes, P * d->n_isotopes, &iso, l->allocs, l->bytes, st) ||
-      upload(d->frag_mz_library, NF, &fl, l->allocs, l->bytes, st) || upload(d->frag_mz, NF, &fm, l->allocs, l->bytes, st) ||
-      upload(d->frag_intensity, NF, &fi, l->allocs, l->bytes, st) || upload(d->frag_type, NF, &t, l->allocs, l->bytes, st) ||
-      upload(d->frag_loss_type, NF, &lt, l->allocs, l->bytes, st) || upload(d->frag_charge, NF, &fc, l->allocs, l->bytes, st) ||
-      upload(d->frag_number, NF, &fn, l->allocs, l->bytes, st) || upload(d->frag_position, NF, &fp, l->allocs, l->bytes, st) ||
-      upload(d->frag_cardinality, NF, &fcard, l->allocs, l->bytes, st)) {
-    adb_library_destroy(l);
-    return 1;
-  }
-  v.n_precursors = P; v.precursor_idx = a; v.frag_start_idx = b; v.frag_stop_idx = c; v.charge = ch; v.rt = rt;
-  v.mobility = mob; v.mz = mz; v.isotopes = iso; v.n_isotopes = d->n_isotopes; v.n_fragments = NF;
-  v.frag_mz_library = fl; v.frag_mz = fm; v.frag_intensity = fi; v.frag_type = t; v.frag_loss_type = lt;
-  v.frag_charge = fc; v.frag_number = fn; v.frag_position = fp; v.frag_cardinality = fcard;
   int mx = 0;
   for (int64_t i = 0; i < P; i++) {
-    int64_t s = d->frag_start_idx[i], e = d->frag_stop_idx[i];
-    if (e > NF || s > e) { adb_library_destroy(l); return fail("fragment index range of precursor row " + std::to_string(i) + " is outside the fragment table"); }
+    const int64_t s = d->frag_start_idx[i], e = d->frag_stop_idx[i];
+    if (e > NF || s > e) return fail("fragment index range of precursor row " + std::to_string(i) + " is outside the fragment table");
     mx = std::max<int>(mx, (int)(e - s));
   }
+  adb_library* l = new adb_library();
+  l->device = device;
   l->max_lib_fragments = mx;
-  cudaError_t e = cudaDeviceSynchronize();
+  // one pooled allocation, asynchronous copies (they overlap when the caller's arrays are pinned), one synchronise
+  struct Item { const void* host; size_t bytes; size_t off; };
+  Item items[17];
+  size_t total = 0;
+  auto add = [&](int k, const void* h, size_t bytes) { items[k] = Item{h, bytes, total}; total += (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255; };
+  const size_t Pn = (size_t)std::max<int64_t>(P, 0), Fn = (size_t)std::max<int64_t>(NF, 0);
+  add(0, d->precursor_idx, 4 * Pn); add(1, d->frag_start_idx, 4 * Pn); add(2, d->frag_stop_idx, 4 * Pn); add(3, d->charge, Pn);
+  add(4, d->rt, 4 * Pn); add(5, d->mobility, 4 * Pn); add(6, d->mz, 4 * Pn); add(7, d->isotopes, 4 * Pn * (size_t)d->n_isotopes);
+  add(8, d->frag_mz_library, 4 * Fn); add(9, d->frag_mz, 4 * Fn); add(10, d->frag_intensity, 4 * Fn); add(11, d->frag_type, Fn);
+  add(12, d->frag_loss_type, Fn); add(13, d->frag_charge, Fn); add(14, d->frag_number, Fn); add(15, d->frag_position, Fn);
+  add(16, d->frag_cardinality, Fn);
+  void* pool = nullptr;
+  cudaError_t e = cudaMalloc(&pool, total + 256);
+  if (e != cudaSuccess) { delete l; return fail(std::string("cudaMalloc(library) failed: ") + cudaGetErrorString(e)); }
+  l->allocs.push_back(pool);
+  l->bytes = (int64_t)total;
+  for (int k = 0; k < 17 && e == cudaSuccess; k++)
+    if (items[k].bytes) e = cudaMemcpyAsync((char*)pool + items[k].off, items[k].host, items[k].bytes, cudaMemcpyHostToDevice, cudaStreamPerThread);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
   if (e != cudaSuccess) { adb_library_destroy(l); return fail(std::string("library upload failed: ") + cudaGetErrorString(e)); }
+  char* b = (char*)pool;
+  DevLib& v = l->dev;
+  v.n_precursors = P; v.n_isotopes = d->n_isotopes; v.n_fragments = NF;
+  v.precursor_idx = (const uint32_t*)(b + items[0].off); v.frag_start_idx = (const uint32_t*)(b + items[1].off);
+  v.frag_stop_idx = (const uint32_t*)(b + items[2].off); v.charge = (const uint8_t*)(b + items[3].off);
+  v.rt = (const float*)(b + items[4].off); v.mobility = (const float*)(b + items[5].off); v.mz = (const float*)(b + items[6].off);
+  v.isotopes = (const float*)(b + items[7].off); v.frag_mz_library = (const float*)(b + items[8].off);
+  v.frag_mz = (const float*)(b + items[9].off); v.frag_intensity = (const float*)(b + items[10].off);
+  v.frag_type = (const uint8_t*)(b + items[11].off); v.frag_loss_type = (const uint8_t*)(b + items[12].off);
+  v.frag_charge = (const uint8_t*)(b + items[13].off); v.frag_number = (const uint8_t*)(b + items[14].off);
+  v.frag_position = (const uint8_t*)(b + items[15].off); v.frag_cardinality = (const uint8_t*)(b + items[16].off);
   *out = l;
   return 0;
 }
@@ -841,6 +920,30 @@ int adb_fetch_candidates(adb_rawfile_t* raw, adb_candidates_out* out) {
   CUDA_TRY(cudaMemcpyAsync(out->frame_center, c.frame_center, 4 * N, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out->frame_start, c.frame_start, 4 * N, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out->frame_stop, c.frame_stop, 4 * N, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int adb_fetch_candidate_table(adb_rawfile_t* raw, adb_candidate_table* out) {
+  if (!raw || !out) return fail("null argument");
+  if (out->n != raw->n_cand) return fail("candidate table size mismatch (expected the count returned by adb_select_candidates_resident)");
+  if (!raw->d_cand_pidx) return fail("no resident candidate table (call adb_select_candidates_resident first)");
+  if (set_device(raw->device)) return 1;
+  cudaStream_t st = raw->stream;
+  const size_t N = (size_t)raw->n_cand;
+  const DevCandidatesIn& c = raw->d_cand;
+  if (N > 0) {
+    CUDA_TRY(cudaMemcpyAsync(out->lib_row, c.lib_row, 8 * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->rank, c.rank, N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->scan_start, c.scan_start, 8 * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->scan_stop, c.scan_stop, 8 * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->scan_center, c.scan_center, 8 * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->frame_start, c.frame_start, 8 * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->frame_stop, c.frame_stop, 8 * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->frame_center, c.frame_center, 8 * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->precursor_idx, raw->d_cand_pidx, 4 * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out->score, raw->d_cand_score, 4 * N, cudaMemcpyDeviceToHost, st));
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
@@ -928,11 +1031,9 @@ int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scori
   raw->n_cand = n;
   CUDA_TRY(cudaEventRecord(raw->ev[1], st));
   if (!raw->is4d && c_max > 4096) return fail("a candidate spans more than 4096 cycles");
-  if (run_scoring(raw, lib, cfg, c_max, s_max)) return 1;
-  CUDA_TRY(cudaEventRecord(raw->ev[2], st));
-  if (check_status(raw, "adb_score_candidates")) return 1;
-  if (adb_fetch_scores(raw, out, nullptr, nullptr)) return 1;
+  if (run_scoring(raw, lib, cfg, c_max, s_max, out)) return 1;  // records ev[2] between the kernels and the (remaining) D2H
   CUDA_TRY(cudaEventRecord(raw->ev[3], st));
+  if (check_status(raw, "adb_score_candidates")) return 1;
   finish_timing(raw);
   return 0;
 }

@@ -174,7 +174,8 @@ size_t adb_compact_temp_bytes(int64_t n_rows);
 void adb_launch_compact_ex(DevCandidatesOut cont, int64_t candidate_count, int* d_flags, int* d_offs, void* d_tmp,
                            size_t tmp_bytes, int64_t* d_lib_row, uint8_t* d_rank, int64_t* d_scan_start,
                            int64_t* d_scan_stop, int64_t* d_scan_center, int64_t* d_frame_start, int64_t* d_frame_stop,
-                           int64_t* d_frame_center, int64_t* d_count, cudaStream_t stream, int* n_launches);
+                           int64_t* d_frame_center, uint32_t* d_precursor_idx, float* d_score, int64_t* d_count,
+                           cudaStream_t stream, int* n_launches);
 
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ int64_t adb_lower_bound(const float* __restrict__ a, int64_t lo, int64_t hi, float v) {

@@ -85,12 +85,14 @@ __global__ void adb_flag_kernel(const float* __restrict__ score, int64_t n, int*
 __global__ void adb_scatter_kernel(DevCandidatesOut c, int64_t candidate_count, const int* __restrict__ flags,
                                    const int* __restrict__ offs, int64_t* lib_row, uint8_t* rank, int64_t* scan_start,
                                    int64_t* scan_stop, int64_t* scan_center, int64_t* frame_start, int64_t* frame_stop,
-                                   int64_t* frame_center, int64_t* count) {
+                                   int64_t* frame_center, uint32_t* precursor_idx, float* score, int64_t* count) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= c.n_rows) return;
   if (flags[t]) {
     int o = offs[t];
     lib_row[o] = t / candidate_count;
+    precursor_idx[o] = c.precursor_idx[t];
+    score[o] = c.score[t];
     rank[o] = c.rank[t];
     scan_start[o] = c.scan_start[t]; scan_stop[o] = c.scan_stop[t]; scan_center[o] = c.scan_center[t];
     frame_start[o] = c.frame_start[t]; frame_stop[o] = c.frame_stop[t]; frame_center[o] = c.frame_center[t];
@@ -125,13 +127,14 @@ size_t adb_compact_temp_bytes(int64_t n_rows) {
 void adb_launch_compact_ex(DevCandidatesOut cont, int64_t candidate_count, int* d_flags, int* d_offs, void* d_tmp,
                            size_t tmp_bytes, int64_t* d_lib_row, uint8_t* d_rank, int64_t* d_scan_start,
                            int64_t* d_scan_stop, int64_t* d_scan_center, int64_t* d_frame_start, int64_t* d_frame_stop,
-                           int64_t* d_frame_center, int64_t* d_count, cudaStream_t stream, int* n_launches) {
+                           int64_t* d_frame_center, uint32_t* d_precursor_idx, float* d_score, int64_t* d_count,
+                           cudaStream_t stream, int* n_launches) {
   if (cont.n_rows <= 0) return;
   unsigned blocks = (unsigned)((cont.n_rows + 255) / 256);
   adb_flag_kernel<<<blocks, 256, 0, stream>>>(cont.score, cont.n_rows, d_flags);
   cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_flags, d_offs, (int)cont.n_rows, stream);
   adb_scatter_kernel<<<blocks, 256, 0, stream>>>(cont, candidate_count, d_flags, d_offs, d_lib_row, d_rank, d_scan_start,
                                                  d_scan_stop, d_scan_center, d_frame_start, d_frame_stop, d_frame_center,
-                                                 d_count);
+                                                 d_precursor_idx, d_score, d_count);
   if (n_launches) (*n_launches) += 3;
 }

@@ -59,7 +59,7 @@ struct Sel4State {
   float iso_mz[ADB_MAX_ISOTOPES];
   int nF, nI, C, S, ok;
   long long f0, f1, s0, s1, cs, row;
-  int n_peaks, overflow;
+  int n_peaks, overflow, n_nzrows;
   int red_idx[S4_WARPS];
   double red_val[S4_WARPS];
   int top_idx[S4_MAX_CAND];
@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
   if (P.tile_in_smem) sp += sizeof(uint32_t) * cells_cap;
   unsigned short* rowlist = (unsigned short*)sp; sp += sizeof(unsigned short) * (size_t)P.s_cap * S4_LIST_CAP;
   unsigned short* rowcnt = (unsigned short*)sp; sp += sizeof(unsigned short) * (size_t)((P.s_cap + 7) & ~7);
+  unsigned short* nzrows = (unsigned short*)sp; sp += sizeof(unsigned short) * (size_t)((P.s_cap + 7) & ~7);  // non-empty rows, ascending
+  unsigned short* rowrank = (unsigned short*)sp; sp += sizeof(unsigned short) * (size_t)((P.s_cap + 7) & ~7);  // # non-empty rows <= r
   unsigned char* smask = sp;  // [Fr][S] bit 0: fragment quad window, bit 1: MS1
   // HBM workspace of this CTA
   char* wp = P.ws + (size_t)blockIdx.x * P.ws_per_cta;
@@ -325,52 +327,88 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
         if (lane == 0) rowcnt[r] = (unsigned short)min(cnt, 65535);
       }
       __syncthreads();
+      if (warp == 0) {  // ascending list of the non-empty tile rows
+        int M = 0;
+        for (int base = 0; base < S; base += 32) {
+          const int r = base + lane;
+          const bool ne = r < S && rowcnt[r] != 0;
+          const unsigned b = __ballot_sync(FULL, ne);
+          if (ne) nzrows[M + __popc(b & ((1u << lane) - 1u))] = (unsigned short)r;
+          if (r < S) rowrank[r] = (unsigned short)(M + __popc(b & ((2u << lane) - 1u)));
+          M += __popc(b);
+        }
+        if (lane == 0) st.n_nzrows = M;
+      }
+      __syncthreads();
       // ---- sparse circular smoothing + log-sum (fft.py:141-212, selection.py:206-226) ----------------
+      // out[i][j] = sum_a sum_b k[a][b] x[(i + sh - a) mod S][(j + sw - b) mod C], a then b ascending: for one output
+      // cell the input rows are visited downwards (circularly) from r0 = (i + sh) mod S, only the non-empty ones, and
+      // inside a row the columns downwards (circularly) from jc = (j + sw) mod C.
       float* lacc = (l < nF) ? lf : lp;
       const int segs = (C + 31) >> 5;
-      for (int u = warp; u < S * segs; u += S4_WARPS) {
-        const int i = u / segs, j = (u - i * segs) * 32 + lane;
-        int jc = min(j, C - 1) + sw;  // lanes beyond the row compute a discarded duplicate of the last cell
-        if (jc >= C) jc -= C;
-        double acc = 0.0;
-        bool any = false;
-        for (int a = 0; a < kh; a++) {
-          int r = i + sh - a;
-          if (r < 0) r += S; else if (r >= S) r -= S;
-          const int n = rowcnt[r];
-          if (n == 0) continue;  // warp-uniform
-          any = true;
-          const double* krow = s_kern + a * kw;
-          const uint32_t* trow = tile + r * C;
-          if (n <= S4_LIST_CAP) {
-            const unsigned short* lst = rowlist + r * S4_LIST_CAP;
-            for (int e = 0; e < n; e++) {  // columns <= jc, descending: b = jc - col ascending
-              const int col = lst[e];
-              const int b = jc - col;
-              if (b >= 0 && b < kw) acc = fma(krow[b], (double)__uint_as_float(trow[col]), acc);
-            }
-            for (int e = 0; e < n; e++) {  // wrapped columns > jc, descending: b = jc - col + C ascending
-              const int col = lst[e];
-              const int b = jc - col + C;
-              if (col > jc && b < kw) acc = fma(krow[b], (double)__uint_as_float(trow[col]), acc);
-            }
-          } else {
-            for (int b = 0; b < kw; b++) {
-              int col = jc - b;
-              if (col < 0) col += C;
-              const uint32_t v = trow[col];
-              if (v != 0u) acc = fma(krow[b], (double)__uint_as_float(v), acc);
+      const int M = st.n_nzrows;
+      if (M > 0)
+        for (int i = warp; i < S; i += S4_WARPS) {
+          int r0 = i + sh;
+          if (r0 >= S) r0 -= S;
+          const int k0 = rowrank[r0];
+          {  // no non-empty row inside the window of this output row?
+            int k = k0 - 1;
+            if (k < 0) k += M;
+            int a = r0 - (int)nzrows[k];
+            if (a < 0) a += S;
+            if (a >= kh) continue;
+          }
+          for (int seg = 0; seg < segs; seg++) {
+          const int j = seg * 32 + lane;
+          int jc = min(j, C - 1) + sw;  // lanes beyond the row compute a discarded duplicate of the last cell
+          if (jc >= C) jc -= C;
+          double acc = 0.0;
+          for (int step = 0; step < M; step++) {
+            int k = k0 - 1 - step;
+            if (k < 0) k += M;
+            const int r = nzrows[k];
+            int a = r0 - r;
+            if (a < 0) a += S;
+            if (a >= kh) break;  // a grows along the sequence; warp-uniform
+            const int n = rowcnt[r];
+            const double* krow = s_kern + a * kw;
+            const uint32_t* trow = tile + r * C;
+            if (n <= S4_LIST_CAP) {
+              const unsigned short* lst = rowlist + r * S4_LIST_CAP;
+              const int maxc = lst[0], minc = lst[n - 1];
+              const unsigned m1 = __ballot_sync(FULL, maxc > jc - kw && minc <= jc);
+              const unsigned m2 = __ballot_sync(FULL, maxc > jc + C - kw);
+              if (m1)
+                for (int e = 0; e < n; e++) {  // columns <= jc, descending: b = jc - col ascending
+                  const int col = lst[e];
+                  const int b = jc - col;
+                  if (b >= 0 && b < kw) acc = fma(krow[b], (double)__uint_as_float(trow[col]), acc);
+                }
+              if (m2)
+                for (int e = 0; e < n; e++) {  // wrapped columns > jc, descending: b = jc - col + C ascending
+                  const int col = lst[e];
+                  const int b = jc - col + C;
+                  if (col > jc && b < kw) acc = fma(krow[b], (double)__uint_as_float(trow[col]), acc);
+                }
+            } else {
+              for (int b = 0; b < kw; b++) {
+                int col = jc - b;
+                if (col < 0) col += C;
+                const uint32_t v = trow[col];
+                if (v != 0u) acc = fma(krow[b], (double)__uint_as_float(v), acc);
+              }
             }
           }
-        }
-        if (any && j < C) {
-          const float sm = (float)acc;
-          if (sm != 0.f) {
-            const float lg = (float)log((double)sm + 1.0);
-            lacc[i * C + j] = __fadd_rn(lacc[i * C + j], lg);
+          if (j < C) {
+            const float sm = (float)acc;
+            if (sm != 0.f) {
+              const float lg = (float)log((double)sm + 1.0);
+              lacc[i * C + j] = __fadd_rn(lacc[i * C + j], lg);
+            }
+          }
           }
         }
-      }
       __syncthreads();
     }
     // ---- score normalisation (selection.py:401-428) ---------------------------------------------------
@@ -523,7 +561,7 @@ size_t select4d_smem_bytes(const DevRaw4& raw, const Select4Geometry& g, int kh,
   size_t b = sizeof(double) * (size_t)kh * kw;
   if (tile_in_smem) b += sizeof(uint32_t) * (size_t)g.s_cap * g.c_cap;
   b += sizeof(unsigned short) * (size_t)g.s_cap * S4_LIST_CAP;
-  b += sizeof(unsigned short) * (size_t)((g.s_cap + 7) & ~7);
+  b += 3 * sizeof(unsigned short) * (size_t)((g.s_cap + 7) & ~7);
   b += (size_t)raw.Fr * g.s_cap;
   return b + 16;
 }

@@ -57,39 +57,44 @@ class HotPath:
 
     # ---- host buffers (the operator path) -----------------------------------------------------------
     def host_step(self, alloc=np.zeros) -> dict:
-        """alloc(shape, dtype) -> ndarray lets the caller provide pinned host memory."""
+        """What the reference-facing operators do, with caller-provided (pinned) host memory:
+        library batch H2D -> selection -> compacted candidate table D2H (CandidateSelection's DataFrame columns)
+        -> candidate table H2D -> scoring -> score + fragment tables D2H (row blocks overlap the scoring kernel).
+        ``alloc(shape, dtype) -> ndarray`` lets the caller provide pinned host memory."""
+        import time
+
         lib = _lib.load()
+        t_phase = {}
+        t_last = time.perf_counter()
+
+        def lap(name):
+            nonlocal t_last
+            now = time.perf_counter()
+            t_phase[name] = t_phase.get(name, 0.0) + (now - t_last) * 1e3
+            t_last = now
+
         n_rows = int(self.n_precursors * self.sel_struct.candidate_count)
         if self._host_bufs is None or self._host_bufs["n_rows"] != n_rows:
-            cont = {k: alloc(n_rows, dt) for k, dt in (
-                ("precursor_idx", np.uint32), ("rank", np.uint8), ("score", np.float32), ("scan_center", np.uint32),
-                ("scan_start", np.uint32), ("scan_stop", np.uint32), ("frame_center", np.uint32),
-                ("frame_start", np.uint32), ("frame_stop", np.uint32))}
-            self._host_bufs = dict(n_rows=n_rows, cont=cont, scores=None, scores_n=0)
-        cont = self._host_bufs["cont"]
-        # library H2D (the operators re-upload the library batch on every call)
-        dev_lib = _lib.DeviceLibrary(self.lib_arrays, device=self.dev_raw.device)
+            lib_host = {}
+            for k, v in self.lib_arrays.items():  # the library batch as the caller would hold it: (pinned) host arrays
+                buf = alloc(v.shape, v.dtype)
+                np.copyto(buf, v)
+                lib_host[k] = buf
+            self._host_bufs = dict(n_rows=n_rows, table=_abi.alloc_candidate_table(n_rows, alloc), lib=lib_host,
+                                   scores=None, scores_n=0)
+        table = self._host_bufs["table"]
+        dev_lib = _lib.DeviceLibrary(self._host_bufs["lib"], device=self.dev_raw.device)
         h2d = sum(int(v.nbytes) for v in self.lib_arrays.values())
+        lap("library_upload")
         try:
-            od = _abi.CandidatesOut()
-            od.n_rows = n_rows
-            for k, v in cont.items():
-                setattr(od, k, _abi.ptr(v))
-            _lib.check(lib.adb_select_candidates(self.dev_raw.handle, dev_lib.handle, C.byref(self.sel_struct),
-                                                 _abi.ptr(self.kernel), C.c_int32(self.kernel.shape[0]),
-                                                 C.c_int32(self.kernel.shape[1]), C.byref(od)), "adb_select_candidates")
-            d2h = sum(int(v.nbytes) for v in cont.values())
-            mask = cont["score"] > 0
-            rows = np.flatnonzero(mask)
-            n = len(rows)
-            cand = dict(lib_row=(rows // int(self.sel_struct.candidate_count)).astype(np.int64),
-                        rank=cont["rank"][rows])
-            for k in CAND_COLS:
-                cand[k] = cont[k][rows].astype(np.int64)
-            cin, keep = _abi.make_candidates_in(cand["lib_row"], cand["rank"], cand["scan_start"], cand["scan_stop"],
-                                                cand["scan_center"], cand["frame_start"], cand["frame_stop"],
-                                                cand["frame_center"])
-            h2d += sum(int(v.nbytes) for v in keep.values())
+            n = _lib.select_candidates_resident(self.dev_raw, dev_lib, self.sel_struct, self.kernel)
+            t_phase["select_call_device"] = dict(self.dev_raw.last_timing())
+            lap("select_call")
+            _lib.fetch_candidate_table(self.dev_raw, n, table)
+            d2h = n * (7 * 8 + 1 + 4 + 4)
+            lap("candidate_table_d2h")
+            cin = _abi.candidates_in_from_table(table, n)
+            h2d += n * (7 * 8 + 1)
             if self._host_bufs["scores"] is None or self._host_bufs["scores_n"] < n:
                 cap = int(n * 1.05) + 16
                 sc = dict(features=alloc((cap, _abi.NUM_FEATURES), np.float32), valid=alloc(cap, np.uint8))
@@ -102,14 +107,18 @@ class HotPath:
             so = _abi.ScoresOut()
             for k, v in sc.items():
                 setattr(so, k, _abi.ptr(v))
+            lap("host_glue")
             _lib.check(lib.adb_score_candidates(self.dev_raw.handle, dev_lib.handle, C.byref(self.score_struct),
                                                 C.byref(cin), C.byref(so)), "adb_score_candidates")
             d2h += n * (_abi.NUM_FEATURES * 4 + 1 + self.top_k * (7 * 4 + 5))
+            lap("score_call")
+            t_phase["score_call_device"] = dict(self.dev_raw.last_timing())
         finally:
             dev_lib.close()
         self.n_candidates = n
+        lap("library_free")
         return dict(n_candidates=n, h2d_bytes=h2d, d2h_bytes=d2h, valid=int(sc["valid"][:n].sum()),
-                    checksum=float(np.nansum(sc["features"][:n, 2])))
+                    checksum=float(np.nansum(sc["features"][:n, 2])), phases_ms=t_phase)
 
     def close(self):
         self.dev_lib.close()

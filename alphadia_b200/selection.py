@@ -81,14 +81,17 @@ class CandidateSelection:
         dev_raw = _lib.device_rawfile_for(self._dia_data, self._raw)
         dev_lib = _lib.DeviceLibrary(lib_arrays, device=dev_raw.device)
         try:
-            container = _lib.select_candidates(dev_raw, dev_lib, self.config_struct, self.kernel)
+            # selection + `score > 0` filter on the device (config_df.py:270-298 candidate_container_to_df);
+            # only the surviving rows travel back
+            n = _lib.select_candidates_resident(dev_raw, dev_lib, self.config_struct, self.kernel)
+            table = _lib.fetch_candidate_table(dev_raw, n)
         finally:
             dev_lib.close()
         self.last_timing = dev_raw.last_timing()
-
-        # config_df.py:270-298 candidate_container_to_df: keep score > 0
-        mask = container["score"] > 0
-        candidate_df = pd.DataFrame({c: container[c][mask] for c in CANDIDATE_COLUMNS})
+        container_dtypes = {"precursor_idx": np.uint32, "rank": np.uint8, "score": np.float32}
+        candidate_df = pd.DataFrame(
+            {c: table[c][:n].astype(container_dtypes.get(c, np.uint32), copy=False) for c in CANDIDATE_COLUMNS}
+        )
         # selection.py:670-676
         return candidate_df.merge(
             self.precursors_flat[["precursor_idx", "elution_group_idx", "decoy"]],

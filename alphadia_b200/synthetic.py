@@ -386,7 +386,7 @@ CONFIGS_4D = {
     "config4": dict(
         seed=4, n_precursors=200_000, n_cycles=800, n_ms2_frames=8, n_scans=928, quad_lo=400.0, quad_hi=1200.0,
         cycle_seconds=0.95, mob_hi=1.45, mob_lo=0.65, tof_ppm=4.0, mz_lo=150.0, mz_hi=1900.0,
-        noise_per_push=40, rt_tolerance=50.0, mobility_tolerance=0.04, planted_fraction=0.5,
+        noise_per_push=40, rt_tolerance=50.0, mobility_tolerance=0.04, planted_fraction=0.5, sorted_noise=True,
     ),
 }
 
@@ -441,9 +441,24 @@ def make_config_4d(name: str, *, seed: int | None = None, n_precursors: int | No
     # ---- events: (tof, push, intensity) -------------------------------------------------------
     n_push = n_frames * Sc
     n_noise = int((n_push - Sc) * p["noise_per_push"])
-    ev_push = rng.integers(Sc, n_push, size=n_noise).astype(np.int64)  # frame 0 stays empty
-    ev_tof = rng.integers(0, n_tof, size=n_noise).astype(np.int64)
-    ev_int = np.minimum(rng.exponential(60.0, size=n_noise) + 10.0, 60000.0)
+    if p.get("sorted_noise", False):
+        # large runs: draw the noise as a Poisson process over the (tof, push) key space, i.e. already in CSR order
+        # (cumulative exponential gaps), so that no 3e8-element sort is needed; frame 0 stays empty
+        span = n_push - Sc
+        total = float(n_tof) * float(span)
+        gaps = rng.exponential(total / n_noise, size=n_noise)
+        keys = np.cumsum(gaps)
+        del gaps
+        keys = keys[keys < total].astype(np.int64)
+        ev_tof = keys // span
+        ev_push = keys - ev_tof * span + Sc
+        del keys
+        n_noise = len(ev_tof)
+        ev_int = np.minimum(rng.exponential(60.0, size=n_noise).astype(np.float32) + 10.0, 60000.0)
+    else:
+        ev_push = rng.integers(Sc, n_push, size=n_noise).astype(np.int64)  # frame 0 stays empty
+        ev_tof = rng.integers(0, n_tof, size=n_noise).astype(np.int64)
+        ev_int = np.minimum(rng.exponential(60.0, size=n_noise) + 10.0, 60000.0)
 
     targets = np.flatnonzero(precursor_df["decoy"].values == 0)
     n_plant = int(len(targets) * p["planted_fraction"])
@@ -484,12 +499,29 @@ def make_config_4d(name: str, *, seed: int | None = None, n_precursors: int | No
         for i, ab in enumerate([0.5, 0.3, 0.15]):
             add(np.zeros(n_plant, np.int64), (pmz[planted].astype(np.float64) + i * ISOTOPE_MASS_DIFF / pch)
                 * (1 + rng.normal(0, 1.5e-6, size=n_plant)), np.full(n_plant, ab * 20000.0))
-    all_push = np.concatenate([ev_push] + sig_push)
-    all_tof = np.concatenate([ev_tof] + sig_tof)
-    all_int = np.concatenate([ev_int] + sig_int)
-    key = all_tof * np.int64(n_push) + all_push
-    order = np.argsort(key, kind="stable")
-    key, all_int = key[order], all_int[order]
+    if p.get("sorted_noise", False):
+        # the noise is sorted; sort the (much smaller) signal part and merge (a stable sort of two sorted runs is a merge)
+        s_key = np.concatenate(sig_tof) * np.int64(n_push) + np.concatenate(sig_push) if sig_push else np.zeros(0, np.int64)
+        s_int = np.concatenate(sig_int).astype(np.float32) if sig_int else np.zeros(0, np.float32)
+        so = np.argsort(s_key, kind="stable")
+        s_key, s_int = s_key[so], s_int[so]
+        n_key = ev_tof * np.int64(n_push) + ev_push
+        del ev_tof, ev_push
+        pos = np.searchsorted(n_key, s_key, side="left") + np.arange(len(s_key))
+        key = np.empty(len(n_key) + len(s_key), np.int64)
+        all_int = np.empty(len(key), np.float32)
+        is_sig = np.zeros(len(key), bool)
+        is_sig[pos] = True
+        key[is_sig], key[~is_sig] = s_key, n_key
+        all_int[is_sig], all_int[~is_sig] = s_int, ev_int
+        del n_key, ev_int, is_sig
+    else:
+        all_push = np.concatenate([ev_push] + sig_push)
+        all_tof = np.concatenate([ev_tof] + sig_tof)
+        all_int = np.concatenate([ev_int] + sig_int)
+        key = all_tof * np.int64(n_push) + all_push
+        order = np.argsort(key, kind="stable")
+        key, all_int = key[order], all_int[order]
     # merge duplicate (tof, push) events: detector events are unique per (push, tof)
     first = np.ones(len(key), dtype=bool)
     first[1:] = key[1:] != key[:-1]

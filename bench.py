@@ -8,7 +8,7 @@
 One "step" = candidate selection + candidate scoring of the whole library batch against one raw file
 (SURVEY.md §8d).  `value` is measured with raw file and library resident in HBM (results stay in HBM);
 `e2e` is measured through the C-ABI calls the reference-facing operators make, with pinned HOST buffers
-(library batch H2D, candidate container D2H, candidate table H2D, score + fragment tables D2H every step;
+(library batch H2D, compacted candidate table D2H, candidate table H2D, score + fragment tables D2H every step;
 the raw file is uploaded once per file, as `dia_data.to_jitclass()` is built once per file in the reference).
 """
 
@@ -51,11 +51,13 @@ def build_workload(name: str, rank: int, n_precursors: int | None):
     from alphadia_b200.config import CandidateScoringConfig, CandidateSelectionConfig
     from alphadia_b200.kernel import GaussianKernel
     from alphadia_b200.library import assemble_library_arrays
-    from alphadia_b200.synthetic import CONFIGS_3D, make_config_3d
+    from alphadia_b200.synthetic import CONFIGS_3D, CONFIGS_4D, make_config_3d, make_config_4d
 
-    seed = CONFIGS_3D[name]["seed"] + rank
+    is4d = name in CONFIGS_4D
+    seed = (CONFIGS_4D if is4d else CONFIGS_3D)[name]["seed"] + rank
     t0 = time.time()
-    raw, pdf, fdf, p = make_config_3d(name, seed=seed, n_precursors=n_precursors, with_strings=False)
+    make = make_config_4d if is4d else make_config_3d
+    raw, pdf, fdf, p = make(name, seed=seed, n_precursors=n_precursors, with_strings=False)
     lib = assemble_library_arrays(pdf, fdf, "rt_library", "mobility_library", "mz_library", "mz_library")
     # ClassicExtractionHandler parameters (reference extraction_handler.py:349-409) at target tolerances
     sel = CandidateSelectionConfig()
@@ -66,7 +68,8 @@ def build_workload(name: str, rank: int, n_precursors: int | None):
         "group_channels": False, "use_weighted_score": True, "join_close_candidates": False,
         "join_close_candidates_scan_threshold": 0.6, "join_close_candidates_cycle_threshold": 0.6,
         "top_k_fragments": 12, "exclude_shared_ions": True, "rt_tolerance": float(p["rt_tolerance"]),
-        "mobility_tolerance": 0.1, "candidate_count": 3, "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0,
+        "mobility_tolerance": float(p.get("mobility_tolerance", 0.1)), "candidate_count": 3,
+        "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0,
     })
     sc = CandidateScoringConfig()
     sc.update({
@@ -76,8 +79,12 @@ def build_workload(name: str, rank: int, n_precursors: int | None):
     })
     kernel = GaussianKernel(raw, fwhm_rt=5.0, sigma_scale_rt=0.5, fwhm_mobility=0.01, sigma_scale_mobility=1.0,
                             kernel_width=30, kernel_height=min(30, raw.scan_max_index + 1)).get_dense_matrix(verbose=False)
-    log(f"[rank {rank}] workload {name}: {len(pdf)} precursors, {len(fdf)} fragments, {len(raw.rt_values)} spectra, "
-        f"{raw.n_peaks} peaks ({(raw.n_peaks * 8) / 1e9:.2f} GB) generated in {time.time() - t0:.1f}s")
+    if is4d:
+        log(f"[rank {rank}] workload {name}: {len(pdf)} precursors, {len(fdf)} fragments, {len(raw.rt_values)} frames x "
+            f"{raw.scan_max_index} scans, {raw.n_events} events ({(raw.n_events * 6) / 1e9:.2f} GB) generated in {time.time() - t0:.1f}s")
+    else:
+        log(f"[rank {rank}] workload {name}: {len(pdf)} precursors, {len(fdf)} fragments, {len(raw.rt_values)} spectra, "
+            f"{raw.n_peaks} peaks ({(raw.n_peaks * 8) / 1e9:.2f} GB) generated in {time.time() - t0:.1f}s")
     return raw, pdf, fdf, lib, p, sel, sc, kernel
 
 
@@ -96,6 +103,25 @@ def algorithmic_bytes(raw, lib, c_sel_mean, c_sc_mean, n_obs=1.0, F=12, I=3, N=3
     b_cand = (c_sc_mean * n_obs * (16 + F * (probe2 + 8 * h)) + c_sc_mean * (16 + I * (probe1 + 8 * h))
               + (18 * F + 40) + 72 + (184 + 38 * F + 8))
     return dict(b_prec=b_prec, b_cand=b_cand, p_ms1=p_ms1, p_ms2=p_ms2)
+
+
+def algorithmic_bytes_4d(raw, lib, p, frames_sel, frames_sc, F=12, I=3, N=3):
+    """SURVEY.md §8d, 4-D form: per query (fragment / isotope) T tof rows; per row the CSR pointer pair (16 B), two
+    binary searches on the push axis (4 B probes) and the (push u32 + intensity u16) of the events inside the frame window."""
+    R = raw.n_events / max(len(raw.mz_values), 1)
+    probes = 2 * 4 * math.ceil(math.log2(max(R, 2)))
+    t2 = 2 * 10.0 / p["tof_ppm"]
+    t1 = 2 * 5.0 / p["tof_ppm"]
+    n_frames = len(raw.rt_values)
+    n_iso = lib["isotopes"].shape[1]
+
+    def per_window(frames):
+        h = R * frames / n_frames
+        return F * t2 * (16 + probes + 6 * h) + I * t1 * (16 + probes + 6 * h)
+
+    b_prec = per_window(frames_sel) + (18 * F + 40 + 4 * n_iso) + 33 * N
+    b_cand = per_window(frames_sc) + (18 * F + 40) + 72 + (184 + 38 * F + 8)
+    return dict(b_prec=b_prec, b_cand=b_cand, row_len=R, tof_rows_ms2=t2, tof_rows_ms1=t1)
 
 
 class ClockSampler:
@@ -174,8 +200,11 @@ def cpu_reference_pass(raw, lib, sel, sc, kernel, rows, threads):
     sub = dict(lib)
     for k in ("precursor_idx", "frag_start_idx", "frag_stop_idx", "charge", "rt", "mobility", "mz", "isotopes"):
         sub[k] = np.ascontiguousarray(lib[k][rows])
+    is4d = hasattr(raw, "tof_indptr")
+    o_select = oracle.select_candidates_4d if is4d else oracle.select_candidates
+    o_score = oracle.score_candidates_4d if is4d else oracle.score_candidates
     t0 = time.perf_counter()
-    cont = oracle.select_candidates(raw, sub, sel.to_struct(), kernel, n_threads=threads)
+    cont = o_select(raw, sub, sel.to_struct(), kernel, n_threads=threads)
     t_sel = time.perf_counter() - t0
     m = np.flatnonzero(cont["score"] > 0)
     cc = int(sel.candidate_count)
@@ -183,7 +212,7 @@ def cpu_reference_pass(raw, lib, sel, sc, kernel, rows, threads):
                                         cont["scan_center"][m], cont["frame_start"][m], cont["frame_stop"][m],
                                         cont["frame_center"][m])
     t0 = time.perf_counter()
-    out = oracle.score_candidates(raw, sub, sc.to_struct(), cin, n_threads=threads)
+    out = o_score(raw, sub, sc.to_struct(), cin, n_threads=threads)
     t_sc = time.perf_counter() - t0
     return len(m), t_sel, t_sc, int(out["valid"].sum())
 
@@ -242,8 +271,13 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_description(name, P):
-    from alphadia_b200.synthetic import CONFIGS_3D
+    from alphadia_b200.synthetic import CONFIGS_3D, CONFIGS_4D
 
+    if name in CONFIGS_4D:
+        c = CONFIGS_4D[name]
+        return (f"{name}: {P} precursors x 12 fragments, 3 candidates/precursor, synthetic timsTOF-shape 4-D run "
+                f"{c['n_cycles']} cycles x (1 MS1 + {c['n_ms2_frames']} diaPASEF frames) x {c['n_scans']} scans, "
+                f"rt_tolerance {c['rt_tolerance']}s, mobility_tolerance {c['mobility_tolerance']}, ms1/ms2 5/10 ppm")
     c = CONFIGS_3D[name]
     return (f"{name}: {P} precursors x 12 fragments, 3 candidates/precursor, synthetic Thermo-shape 3-D run "
             f"{c['n_cycles']} cycles x (1 MS1 + {c['n_windows']} MS2), rt_tolerance {c['rt_tolerance']}s, ms1/ms2 5/10 ppm")
@@ -348,26 +382,31 @@ def main():
     else:
         t_e2e_max, n_e2e_total = t_e2e, float(e2e_stats[-1]["n_candidates"])
     e2e_value = n_e2e_total * args.e2e_steps / t_e2e_max
+    log(f"[rank {rank}] e2e phases (ms, last step): {json.dumps(e2e_stats[-1].get('phases_ms', {}))}")
 
     if rank == 0:
         # ---- roofline of the dominant kernel ------------------------------------------------------
-        L = raw.cycle_len
+        is4d = hasattr(raw, "tof_indptr")
+        L = raw.cycle.shape[1]
         cont = _lib.fetch_candidates(hp.dev_raw, int(hp.n_precursors * sel.candidate_count))
         m = cont["score"] > 0
         c_sc = (cont["frame_stop"][m].astype(np.int64) // L - cont["frame_start"][m].astype(np.int64) // L)
         c_sc_mean = float(c_sc.mean()) if m.any() else 0.0
-        cyc_rt = raw.rt_values[::L]
+        cyc_rt = raw.rt_values[int(raw.zeroth_frame)::L] if is4d else raw.rt_values[::L]
         cyc_s = float(np.mean(np.diff(cyc_rt))) if len(cyc_rt) > 1 else 1.0
         c_sel = 16 * math.ceil(max(2 * p["rt_tolerance"] / cyc_s, 30) / 16)
         c_sel = min(c_sel, raw.precursor_cycle_max_index)
-        ab = algorithmic_bytes(raw, lib, c_sel, c_sc_mean)
+        if is4d:
+            ab = algorithmic_bytes_4d(raw, lib, p, c_sel * L, c_sc_mean * L)
+        else:
+            ab = algorithmic_bytes(raw, lib, c_sel, c_sc_mean)
         sel_k = float(np.mean([s["select_kernel_ms"] for s in stats]))
         sc_k = float(np.mean([s["score_kernel_ms"] for s in stats]))
         peak, peak_src = measured_peaks()
         if sel_k >= sc_k:
-            dom, dur, bytes_launch, unit_desc = "adb_select_kernel", sel_k, ab["b_prec"] * hp.n_precursors, f"{ab['b_prec']:.0f} B/precursor x {hp.n_precursors} precursors (C_sel={c_sel})"
+            dom, dur, bytes_launch, unit_desc = ("adb_select4d_kernel" if is4d else "adb_select_kernel"), sel_k, ab["b_prec"] * hp.n_precursors, f"{ab['b_prec']:.0f} B/precursor x {hp.n_precursors} precursors (C_sel={c_sel})"
         else:
-            dom, dur, bytes_launch, unit_desc = "adb_score_kernel", sc_k, ab["b_cand"] * n_cand, f"{ab['b_cand']:.0f} B/candidate x {n_cand} candidates (C_sc={c_sc_mean:.1f})"
+            dom, dur, bytes_launch, unit_desc = ("adb_score4d_kernel" if is4d else "adb_score_kernel"), sc_k, ab["b_cand"] * n_cand, f"{ab['b_cand']:.0f} B/candidate x {n_cand} candidates (C_sc={c_sc_mean:.1f})"
         achieved = bytes_launch / (dur * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
@@ -400,7 +439,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_stats[-1]["h2d_bytes"],
                     "d2h_bytes_per_step": e2e_stats[-1]["d2h_bytes"], "steps": args.e2e_steps,
-                    "path": "adb_library_create + adb_select_candidates + adb_score_candidates with pinned host buffers"},
+                    "path": "adb_library_create (H2D) + adb_select_candidates_resident + adb_fetch_candidate_table (D2H) + adb_score_candidates (candidate table H2D, score/fragment tables D2H in 4 row blocks overlapped with the kernel), pinned host buffers"},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }

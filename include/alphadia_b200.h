@@ -234,6 +234,24 @@ int adb_fragment_competition(int device, int64_t n_windows, const int64_t* windo
  * config_df.py:270-284) into scoring input order (library row, rank); returns the candidate count */
 int adb_select_candidates_resident(adb_rawfile_t* raw, adb_library_t* lib, const adb_selection_config* cfg,
                                    const float* kernel, int32_t kernel_h, int32_t kernel_w, int64_t* n_candidates);
+/* the compacted candidate table of the last adb_select_candidates_resident call: rows of the candidate container with
+ * score > 0 in container order (candidate_container_to_df, config_df.py:270-298), index columns already widened to
+ * int64 as Schema.validate does (validation/schemas.py:51-73), plus the library row of each precursor.  The int64
+ * columns have the layout of adb_candidates_in, so the table can be handed to adb_score_candidates as it is. */
+typedef struct {
+  int64_t n; /* must equal the count returned by adb_select_candidates_resident */
+  int64_t* lib_row;
+  uint8_t* rank;
+  int64_t* scan_start;
+  int64_t* scan_stop;
+  int64_t* scan_center;
+  int64_t* frame_start;
+  int64_t* frame_stop;
+  int64_t* frame_center;
+  uint32_t* precursor_idx;
+  float* score;
+} adb_candidate_table;
+int adb_fetch_candidate_table(adb_rawfile_t* raw, adb_candidate_table* out);
 /* scores the resident candidates; outputs stay on the device */
 int adb_score_candidates_resident(adb_rawfile_t* raw, adb_library_t* lib, const adb_scoring_config* cfg);
 /* D2H of the resident results: the full candidate container (n_precursors * candidate_count rows) ... */

@@ -434,3 +434,47 @@ def test_resident_pipeline_4d(engine):
     assert np.array_equal(res["valid"], ref["valid"])
     assert np.array_equal(res["features"], ref["features"], equal_nan=True)
     dlib.close(); draw.close()
+
+
+@pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
+def test_candidate_table_matches_container(engine, name):
+    """adb_fetch_candidate_table == the `score > 0` rows of the candidate container, in container order."""
+    raw, lib, p, draw, dlib = _device_objects(engine, name)
+    cfg = _sel_cfg_4d(p) if name == "parity_4d" else H.selection_config(p["rt_tolerance"]).to_struct()
+    kernel = H.default_kernel(raw)
+    host = engine.select_candidates(draw, dlib, cfg, kernel)
+    n = engine.select_candidates_resident(draw, dlib, cfg, kernel)
+    table = engine.fetch_candidate_table(draw, n)
+    m = host["score"] > 0
+    assert n == m.sum() > 0
+    for c in INT_COLS:
+        assert np.array_equal(table[c][:n].astype(np.int64), host[c][m].astype(np.int64)), c
+    assert np.array_equal(table["score"][:n], host["score"][m])
+    assert np.array_equal(lib["precursor_idx"][table["lib_row"][:n]], host["precursor_idx"][m])
+    # the table is scoring input as it is
+    from alphadia_b200 import _abi
+    cin = _abi.candidates_in_from_table(table, n)
+    got = engine.score_candidates(draw, dlib, H.scoring_config().to_struct(), cin)
+    cin2, keep = H.candidates_in_from_arrays(lib, {c: host[c][m] for c in INT_COLS})
+    ref = engine.score_candidates(draw, dlib, H.scoring_config().to_struct(), cin2)
+    assert np.array_equal(got["features"], ref["features"], equal_nan=True)
+    dlib.close(); draw.close()
+
+
+def test_chunked_scoring_equals_single_block(engine):
+    """>= 200k candidates are scored in 4 row blocks with overlapped D2H: same result as the resident single launch."""
+    raw, lib, p, draw, dlib = _device_objects(engine, "parity_small")
+    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    n = engine.select_candidates_resident(draw, dlib, cfg, H.default_kernel(raw))
+    table = engine.fetch_candidate_table(draw, n)
+    reps = 200000 // n + 1
+    big = {k: np.ascontiguousarray(np.tile(v[:n], reps)) for k, v in table.items()}
+    from alphadia_b200 import _abi
+    N = n * reps
+    assert N >= 200000
+    scfg = H.scoring_config().to_struct()
+    got = engine.score_candidates(draw, dlib, scfg, _abi.candidates_in_from_table(big, N))
+    one = engine.score_candidates(draw, dlib, scfg, _abi.candidates_in_from_table(table, n))
+    for k in ("features", "valid", "fragment_mz_observed", "fragment_correlation", "fragment_type"):
+        assert np.array_equal(got[k], np.concatenate([one[k]] * reps), equal_nan=True), k
+    dlib.close(); draw.close()
