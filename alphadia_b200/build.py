@@ -44,6 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(build_dir, exist_ok=True)
     common = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+    common += os.environ.get("ADB_NVCC_DEFS", "").split()  # tuning experiments only
     if verbose:
         common += ["-Xptxas", "-v"]
     for s in SOURCES:

@@ -255,16 +255,29 @@ __global__ void order_key_kernel(DevRaw raw, DevLib lib, uint64_t* keys, int32_t
   vals[i] = (int32_t)i;
 }
 
-__global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn cand, int64_t chunk_len, uint64_t* keys, int32_t* vals) {
+// processing order of the candidates: (output row block, quad window, time bucket of 32 cycles, cost class).  Candidates
+// that are resident together read the same spectra (L2 reuse) and the candidates of one CTA round cost about the same
+// (the scoring kernel runs its tiles in lock step).  Results do not depend on the order (disjoint output rows).
+__global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn cand, int64_t chunk_len, int n_iso,
+                                       uint64_t* keys, int32_t* vals) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cand.n) return;
-  float mz = lib.mz[cand.lib_row[i]];
+  const int64_t row = cand.lib_row[i];
+  const float mz = lib.mz[row];
+  const double q0 = (double)mz - 0.5, q1 = (double)mz + (double)(n_iso - 1) * ADB_ISOTOPE_DIFF / (double)lib.charge[row] + 0.5;
   uint32_t win = 0xFFFFu;
-  for (int64_t j = 0; j < raw.cycle_len; j++)
-    if ((double)mz <= raw.cycle[2 * j + 1] && (double)mz >= raw.cycle[2 * j]) { win = (uint32_t)j; break; }
-  int64_t fs = cand.frame_start[i];
-  uint32_t f = fs < 0 ? 0u : (fs > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)fs);
-  keys[i] = ((uint64_t)(i / chunk_len) << 48) | ((uint64_t)win << 32) | f;  // chunk (output row block), window, time
+  int nobs = 0;
+  for (int64_t j = 0; j < raw.cycle_len; j++) {
+    const double lo = raw.cycle[2 * j], hi = raw.cycle[2 * j + 1];
+    if (win == 0xFFFFu && (double)mz <= hi && (double)mz >= lo) win = (uint32_t)j;
+    nobs += (q0 <= hi) && (q1 >= lo);
+  }
+  const int64_t fs = cand.frame_start[i], fe = cand.frame_stop[i];
+  const int64_t L = raw.cycle_len;
+  const uint64_t bucket = fs < 0 ? 0ull : (uint64_t)min((long long)(fs / (L * 32)), 0xFFFFFFLL);
+  const long long cyc = max((long long)(fe / L - fs / L), 0LL);
+  const uint64_t cost = (uint64_t)min(cyc * (long long)max(nobs, 1), 255LL);
+  keys[i] = ((uint64_t)(i / chunk_len) << 48) | ((uint64_t)win << 32) | (bucket << 8) | cost;
   vals[i] = (int32_t)i;
 }
 
@@ -626,7 +639,8 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
     uint64_t* k_out = k_in + n;
     int32_t* v_in = raw->order_vals.as<int32_t>();
     int32_t* v_out = v_in + n;
-    score_order_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->dev, lib->dev, raw->d_cand, chunk_len, k_in, v_in);
+    score_order_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->dev, lib->dev, raw->d_cand, chunk_len,
+                                                                      (int)std::min<int64_t>(std::min<int64_t>(lib->dev.n_isotopes, cfg->top_k_isotopes), ADB_MAX_ISOTOPES), k_in, v_in);
     raw->launches++;
     const int end_bit = n_chunks > 1 ? 52 : 48;
     size_t tmp = 0;

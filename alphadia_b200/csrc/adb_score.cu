@@ -25,8 +25,14 @@
 
 namespace cg = cooperative_groups;
 
-#define SCORE_THREADS 128
-#define SMEM_FLOATS_PER_TILE 1536  // 6 KB dynamic scratch per candidate tile; larger cubes use the HBM workspace
+#ifndef SCORE_THREADS
+#define SCORE_THREADS 128  // threads per CTA; the tiles of a CTA move through the code in lock step (see adb_score_kernel)
+#endif
+#define SCORE_CTAS_PER_SM (512 / SCORE_THREADS)
+#define SCORE_PHASES 3     // CTA barriers inside one candidate round
+#ifndef SMEM_FLOATS_PER_TILE
+#define SMEM_FLOATS_PER_TILE 1024  // 4 KB dynamic scratch per candidate tile; larger cubes use the HBM workspace
+#endif
 
 namespace {
 
@@ -139,9 +145,13 @@ __device__ __noinline__ float frame_profile_obs_sum(const float* dfi_f, const fl
   return t;
 }
 
+// CTA-wide barrier that tiles of one warp may reach at different times (non-.aligned form)
+__device__ __forceinline__ void cta_phase_barrier() { asm volatile("barrier.sync 1;" ::: "memory"); }
+#define PHASE_BARRIER() do { cta_phase_barrier(); phase++; } while (0)
+
 template <int TILE>
-__device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_block_tile<TILE>& tile, TileSmall<TILE>& sm,
-                          float* smem_scratch, float* ws_scratch) {
+__device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::thread_block_tile<TILE>& tile, TileSmall<TILE>& sm,
+                               float* smem_scratch, float* ws_scratch, int& phase) {
   const int lane = (int)tile.thread_rank();
   const DevRaw& raw = P.raw;
   const DevLib& lib = P.lib;
@@ -320,6 +330,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     dpm[i * C + c] = (float)(smz / ((double)count + 1e-6));
   }
 
+  PHASE_BARRIER();  // ======== end of code region A (setup + extraction) ========
   // ---- quadrupole.py:80-115,261-301 transfer function (n_scans == 1) --------------------------------
   _Pragma("unroll 1") for (int t = lane; t < nI * nobs; t += TILE) {
     int i = t / nobs, o = t % nobs;
@@ -493,6 +504,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
     fa[16] = (float)(num2 / (sqrt(sxx * shh) + 1e-12));
   }
 
+  PHASE_BARRIER();  // ======== end of code region B (template, profiles, precursor features) ========
   // ================= features/fragment_features.py:198-427 =================
   int best_obs = 0;
   _Pragma("unroll 1") for (int o = 1; o < nobs; o++) if (sm.oi[o] > sm.oi[best_obs]) best_obs = o;
@@ -664,6 +676,7 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   }
   tile.sync();
 
+  PHASE_BARRIER();  // ======== end of code region C (fragment features) ========
   // ================= features/profile_features.py:18-206 =================
   // fragments_frame_profile accessor: the best observation's rows were enveloped in place when
   // quant_all is off (fragment_features.py:248-250, view semantics)
@@ -855,35 +868,45 @@ __device__ void score_one(const ScoreParams& P, int64_t ci, const cg::thread_blo
   if (lane == 0) P.out.valid[ci] = 1;
 }
 
+// The kernel body is ~110 KB of almost straight-line SASS, far beyond the 32 KB per-SM instruction cache: with independent
+// warps every warp streams the whole program from L2 for every candidate and the per-GPC instruction cache saturates
+// (ncu r1: gcc__cache_requests_type_instruction at 86 % of peak, SM i-cache hit rate 59 %).  So ONE CTA per SM runs all
+// its tiles through the program in lock step: the code is cut into four regions of <= 32 KB and a CTA barrier separates
+// them, so a region is fetched once per SM and round instead of once per warp.  The candidates of one round have the
+// same cost class (the processing order sorts by it), which keeps the barriers cheap.
 template <int TILE>
-__global__ void __launch_bounds__(SCORE_THREADS) adb_score_kernel(const __grid_constant__ ScoreParams P) {
+__global__ void __launch_bounds__(SCORE_THREADS, SCORE_CTAS_PER_SM) adb_score_kernel(const __grid_constant__ ScoreParams P) {
   extern __shared__ __align__(16) float dyn_smem[];
   constexpr int TILES = SCORE_THREADS / TILE;
-  __shared__ TileSmall<TILE> small[TILES];
+  TileSmall<TILE>* small = reinterpret_cast<TileSmall<TILE>*>(dyn_smem + (size_t)TILES * SMEM_FLOATS_PER_TILE);
   cg::thread_block block = cg::this_thread_block();
   cg::thread_block_tile<TILE> tile = cg::tiled_partition<TILE>(block);
   const int tib = (int)(threadIdx.x / TILE);
   const long long gt = (long long)blockIdx.x * TILES + tib;
-  const long long n_tiles = (long long)gridDim.x * TILES;
   float* scratch = dyn_smem + (size_t)tib * SMEM_FLOATS_PER_TILE;
   float* ws = P.workspace ? P.workspace + (size_t)gt * (size_t)P.ws_floats_per_tile : nullptr;
-  for (long long it = gt; it < P.cand.n; it += n_tiles) {
-    const long long ci = P.order ? (long long)P.order[it] : it;
-    score_one<TILE>(P, ci, tile, small[tib], scratch, ws);
-    tile.sync();
+  for (long long base = (long long)blockIdx.x * TILES; base < P.cand.n; base += (long long)gridDim.x * TILES) {
+    const long long it = base + tib;
+    int phase = 0;
+    if (it < P.cand.n) {
+      const long long ci = P.order ? (long long)P.order[it] : it;
+      score_one_body<TILE>(P, ci, tile, small[tib], scratch, ws, phase);
+    }
+    for (; phase < SCORE_PHASES + 1; phase++) cta_phase_barrier();  // regions skipped by this tile + end of round
   }
+}
+
+template <int TILE>
+size_t score_smem_bytes() {
+  constexpr int TILES = SCORE_THREADS / TILE;
+  return (size_t)TILES * SMEM_FLOATS_PER_TILE * sizeof(float) + (size_t)TILES * sizeof(TileSmall<TILE>);
 }
 
 template <int TILE>
 int resident_tiles(int device) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  int blocks_per_sm = 0;
-  size_t dyn = (size_t)(SCORE_THREADS / TILE) * SMEM_FLOATS_PER_TILE * sizeof(float);
-  cudaFuncSetAttribute(adb_score_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, adb_score_kernel<TILE>, SCORE_THREADS, dyn);
-  if (blocks_per_sm < 1) blocks_per_sm = 1;
-  return sms * blocks_per_sm * (SCORE_THREADS / TILE);
+  return sms * SCORE_CTAS_PER_SM * (SCORE_THREADS / TILE);
 }
 
 }  // namespace
@@ -908,15 +931,16 @@ void adb_launch_score(const DevRaw& raw, const DevLib& lib, const adb_scoring_co
   P.workspace = d_workspace; P.ws_floats_per_tile = workspace_floats_per_tile; P.status = d_status; P.order = d_order;
   const int tile = adb_score_tile((int)cfg.top_k_fragments);
   const int tiles_per_block = SCORE_THREADS / tile;
-  size_t dyn = (size_t)tiles_per_block * SMEM_FLOATS_PER_TILE * sizeof(float);
-  long long blocks = n_resident_tiles / tiles_per_block;  // persistent: one resident wave, tiles stride over candidates
+  long long blocks = n_resident_tiles / tiles_per_block;  // persistent: one CTA per SM, rounds of tiles_per_block candidates
   long long needed = (cand.n + tiles_per_block - 1) / tiles_per_block;
   if (blocks > needed) blocks = needed;
   if (blocks < 1) blocks = 1;
   if (tile == 16) {
+    const size_t dyn = score_smem_bytes<16>();
     cudaFuncSetAttribute(adb_score_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     adb_score_kernel<16><<<(unsigned)blocks, SCORE_THREADS, dyn, stream>>>(P);
   } else {
+    const size_t dyn = score_smem_bytes<32>();
     cudaFuncSetAttribute(adb_score_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     adb_score_kernel<32><<<(unsigned)blocks, SCORE_THREADS, dyn, stream>>>(P);
   }
