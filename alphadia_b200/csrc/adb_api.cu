@@ -281,6 +281,53 @@ __global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn c
   vals[i] = (int32_t)i;
 }
 
+
+// ---- m/z-major index of a 3-D raw file ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t ordered_bits(float v) {
+  uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// one warp per spectrum: key = (cycle position, m/z), value = peak index
+__global__ void mzindex_keys_kernel(DevRaw raw, uint64_t* keys, uint32_t* vals) {
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= raw.n_spectra) return;
+  const uint64_t pos = (uint64_t)(s % raw.cycle_len) << 32;
+  for (int64_t i = raw.peak_start[s] + lane; i < raw.peak_stop[s]; i += 32) {
+    keys[i] = pos | ordered_bits(raw.mz[i]);
+    vals[i] = (uint32_t)i;
+  }
+}
+
+__global__ void mzindex_gather_kernel(DevRaw raw, const uint64_t* keys, const uint32_t* vals, int64_t n, float* s_mz, float* s_int,
+                                      uint32_t* s_cyc) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  if ((keys[j] >> 32) >= (uint64_t)raw.cycle_len) { s_mz[j] = 3.0e38f; s_int[j] = 0.f; s_cyc[j] = 0xFFFFFFFFu; return; }  // not in a spectrum
+  const uint32_t i = vals[j];
+  int64_t lo = 0, hi = raw.n_spectra;  // spectrum of peak i: last s with peak_start[s] <= i and i < peak_stop[s]
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (raw.peak_stop[mid] <= (int64_t)i) lo = mid + 1; else hi = mid;
+  }
+  s_mz[j] = raw.mz[i];
+  s_int[j] = raw.intensity[i];
+  s_cyc[j] = (uint32_t)(lo / raw.cycle_len);
+}
+
+__global__ void mzindex_segments_kernel(const uint64_t* keys, int64_t n, int64_t L, int64_t* pos_start) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > L) return;
+  const uint64_t v = (uint64_t)p << 32;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  pos_start[p] = lo;
+}
+
 // upper bound of the selection cycle window: jitclasses/utils.py:62-70 over every possible precursor RT
 int64_t cycle_window_upper_bound(const adb_rawfile* raw, double rt_tol, int64_t kernel_size) {
   const std::vector<float>& rt = raw->rt_host;
@@ -534,7 +581,7 @@ int run_selection(adb_rawfile* raw, adb_library* lib, const adb_selection_config
   const int max_layers = std::min(lib->max_lib_fragments, (int)ADB_MAX_LIB_FRAGMENTS) + nI;
   const int c_cap = (int)c_upper;
   if (c_cap > 4096) return fail("selection cycle window larger than 4096 cycles is not supported");
-  const size_t per_prec = adb_select_bytes_per_precursor(c_cap, max_layers);
+  const size_t per_prec = adb_select_bytes_per_precursor(c_cap, max_layers, kw);
   if (raw->ws_budget == 0) {  // once per handle: cudaMemGetInfo is slow
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -771,6 +818,37 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
     v.bucket_pair = d_tab;
     bucket_index_kernel<<<(unsigned)((tab_n + 255) / 256), 256, 0, r->stream>>>(v, d_tab);
     r->launches += 2;
+  }
+  {  // derived m/z-major index (see DevRaw): stable radix sort of (cycle position, m/z) over all peaks
+    const int64_t n = d->n_peaks;
+    const size_t N = (size_t)std::max<int64_t>(n, 1);
+    float *s_mz = nullptr, *s_int = nullptr; uint32_t* s_cyc = nullptr; int64_t* pstart = nullptr;
+    auto dalloc = [&](void** p, size_t bytes) { if (cudaMalloc(p, bytes) != cudaSuccess) return 1; r->allocs.push_back(*p); r->bytes += (int64_t)bytes; return 0; };
+    if (dalloc((void**)&s_mz, 4 * (N + 64)) || dalloc((void**)&s_int, 4 * (N + 64)) || dalloc((void**)&s_cyc, 4 * (N + 64)) ||
+        dalloc((void**)&pstart, 8 * (size_t)(d->cycle_len + 1))) { adb_rawfile_destroy(r); return fail("cudaMalloc m/z index failed"); }
+    uint64_t *k_in = nullptr, *k_out = nullptr; uint32_t *v_in = nullptr, *v_out = nullptr; void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const int end_bit = 64;  // all-ones filler keys (peaks outside every spectrum) must sort last
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, r->stream);
+    bool ok = cudaMalloc((void**)&k_in, 8 * N) == cudaSuccess && cudaMalloc((void**)&k_out, 8 * N) == cudaSuccess &&
+              cudaMalloc((void**)&v_in, 4 * N) == cudaSuccess && cudaMalloc((void**)&v_out, 4 * N) == cudaSuccess &&
+              cudaMalloc(&tmp, tmp_bytes + 16) == cudaSuccess;
+    if (ok) {
+      cudaMemsetAsync(k_in, 0xFF, 8 * N, r->stream);  // peaks outside every spectrum sort to the end
+      cudaMemsetAsync(v_in, 0, 4 * N, r->stream);
+      mzindex_keys_kernel<<<(unsigned)((d->n_spectra * 32 + 255) / 256), 256, 0, r->stream>>>(v, k_in, v_in);
+      cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, r->stream);
+      if (n > 0) mzindex_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, s_mz, s_int, s_cyc);
+      mzindex_segments_kernel<<<(unsigned)((d->cycle_len + 1 + 255) / 256), 256, 0, r->stream>>>(k_out, n, d->cycle_len, pstart);
+      cudaMemsetAsync(s_mz + n, 0x7f, 4 * 64, r->stream);  // padding: huge m/z, never inside a window
+      cudaMemsetAsync(s_int + n, 0, 4 * 64, r->stream);
+      cudaMemsetAsync(s_cyc + n, 0xFF, 4 * 64, r->stream);
+      r->launches += 7;
+      ok = cudaStreamSynchronize(r->stream) == cudaSuccess;
+    }
+    cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(tmp);
+    if (!ok) { cudaGetLastError(); adb_rawfile_destroy(r); return fail("building the m/z-major index failed (out of device memory?)"); }
+    v.s_mz = s_mz; v.s_int = s_int; v.s_cyc = s_cyc; v.pos_start = pstart;
   }
   void* st = nullptr;
   if (cudaMalloc(&st, sizeof(uint32_t)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc status failed"); }

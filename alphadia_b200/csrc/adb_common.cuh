@@ -46,6 +46,14 @@ struct DevRaw {
   // the last levels of the binary search.
   const uint2* bucket_pair;         // [n_spectra][ADB_N_BUCKETS]
   float bucket_lo, bucket_width, bucket_inv_width;
+  // derived m/z-major index (built once per file on the device): for every cycle position p the peaks of ALL its
+  // spectra, stably sorted by m/z: segment [pos_start[p], pos_start[p + 1]) of (s_mz, s_int, s_cyc = cycle index).
+  // One search answers "which peaks of this quad window fall into this m/z window, in any cycle" — candidate selection
+  // extracts a whole XIC row (hundreds of cycles) with it instead of one binary search per spectrum.
+  const float* s_mz;
+  const float* s_int;
+  const uint32_t* s_cyc;
+  const int64_t* pos_start;         // [cycle_len + 1]
 };
 
 // timsTOF (4-D) raw file resident in HBM: the TimsTOFTransposeJIT arrays the hot path reads
@@ -140,7 +148,7 @@ struct DevScoresOut {
 };
 
 // ---- launchers (implemented in the .cu files) --------------------------------------------
-size_t adb_select_bytes_per_precursor(int c_cap, int max_layers);
+size_t adb_select_bytes_per_precursor(int c_cap, int max_layers, int kw);
 void adb_launch_select_chunk(const DevRaw& raw, const DevLib& lib, const adb_selection_config& cfg, const double* h_kernel,
                              int kw, DevCandidatesOut out, int64_t chunk_begin, int64_t chunk_n, const int32_t* d_order,
                              uint32_t* d_status, int c_cap, int max_layers, void* workspace, int sm_count,

@@ -20,11 +20,11 @@
 //                              warp 0: strict 5-point peaks, top-N (warp arg-max), close-peak suppression,
 //                              symmetric limits, write-out (integer-exact tail).
 #include <algorithm>
+#include <cstdlib>
 
 #include "adb_common.cuh"
 
 #define FULL 0xffffffffu
-#define SEL_ILP 2
 #define SEL_MAX_LAYERS (ADB_MAX_LIB_FRAGMENTS + ADB_MAX_ISOTOPES)
 #define SEL_MAX_CAND 16
 #define SEL_PLAN_THREADS 128
@@ -312,102 +312,101 @@ __global__ void __launch_bounds__(SEL_PLAN_THREADS) adb_select_plan_kernel(const
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// XIC extraction (alpharaw_jit.py:398-423).  CTA per precursor, one XIC cell per item, layer fastest (neighbouring
-// threads search the same spectrum).  Hits are added in ascending peak order and the observations (cycle
-// positions) in ascending order inside one thread, so the f32 sums are bit-exact.
-__global__ void __launch_bounds__(SEL_EXTRACT_THREADS, 4) adb_select_extract_kernel(const __grid_constant__ SelectParams P) {
+// XIC extraction (alpharaw_jit.py:398-423) through the m/z-major index: ONE WARP PER XIC ROW (precursor, layer).
+// The reference walks every spectrum of the cycle window and binary-searches each m/z window in it; here the peaks of
+// one cycle position are stored sorted by m/z across all cycles (DevRaw::s_mz/s_int/s_cyc), so a row needs one
+// warp-cooperative 32-ary search per observation and a scan over the few dozen peaks inside the m/z window; peaks whose
+// cycle lies outside [cs, cs + C) are skipped.  Bit-exactness: a cell sums its peaks in ascending m/z order and its
+// observations in ascending cycle-position order, exactly like the reference — the index is a STABLE sort, observations
+// are processed one after the other, and peaks of one 32-peak chunk that fall into the same cell are added in lane
+// order (match_any ranks).  The reference's forward-only cursor (a peak consumed by the previous, overlapping window is
+// not seen again) becomes the extra lower bound mz > hi[k - 1].
+#define SEL_ROWS_PER_CTA (SEL_EXTRACT_THREADS / 32)
+
+__device__ __forceinline__ int64_t warp_lower_bound_window(const float* __restrict__ mz, int64_t lo, int64_t hi, float v_lo, float prev_hi,
+                                                           int lane) {
+  // first index in [lo, hi) whose m/z is >= v_lo and > prev_hi ("before" = mz < v_lo || mz <= prev_hi, monotone)
+  while (hi - lo > 32) {
+    const int64_t n = hi - lo, step = (n + 31) >> 5;
+    const int64_t last = lo + min((int64_t)(lane + 1) * step, n) - 1;  // last element of sub-block `lane`
+    const float m = __ldg(mz + last);
+    const unsigned b = __ballot_sync(FULL, (m < v_lo) || (m <= prev_hi));
+    const int c = __popc(b);  // leading sub-blocks that lie completely before the window
+    const int64_t nlo = lo + min((int64_t)c * step, n);
+    hi = (c < 32) ? min(lo + (int64_t)(c + 1) * step, hi) : hi;
+    lo = nlo;
+  }
+  const int64_t i = lo + lane;
+  float m = 3.0e38f;
+  if (i < hi) m = __ldg(mz + i);
+  const unsigned b = __ballot_sync(FULL, i < hi && ((m < v_lo) || (m <= prev_hi)));
+  return lo + __popc(b);
+}
+
+// accumulates XIC row k of the planned precursor `pl` into row[0 .. C) (zeroed by the caller), executed by one warp
+__device__ __forceinline__ void extract_row(const SelectParams& P, const PrecPlan& pl, long long it, int k, float* row, int lane) {
   const DevRaw& raw = P.raw;
-  const int64_t L = raw.cycle_len;
-  __shared__ PrecPlan spl;
-  __shared__ float s_lo[SEL_MAX_LAYERS], s_hi[SEL_MAX_LAYERS];
-  for (long long it = blockIdx.x; it < P.chunk_n; it += gridDim.x) {
-    __syncthreads();
-    if (threadIdx.x == 0) spl = P.plan[it];
-    __syncthreads();
-    if (!spl.ok) continue;
-    const int nF = spl.nF, nL = (int)spl.nF + (int)spl.nI, C = spl.C, nobs = spl.nobs;
-    for (int k = threadIdx.x; k < nL; k += SEL_EXTRACT_THREADS) {
-      s_lo[k] = P.win_lo[it * P.layer_cap + k];
-      s_hi[k] = P.win_hi[it * P.layer_cap + k];
+  const int nF = pl.nF, C = pl.C;
+  const float lo = P.win_lo[it * P.layer_cap + k], hi = P.win_hi[it * P.layer_cap + k];
+  float prev_hi = (k > 0 && k != nF) ? P.win_hi[it * P.layer_cap + k - 1] : -1.0f;
+  if (!(prev_hi >= lo)) prev_hi = -1.0f;  // only an overlapping previous window moves the cursor past lo
+  const bool ms1 = k >= nF;
+  const int n_o = ms1 ? raw.n_ms1_pos : (int)pl.nobs;
+  const uint32_t cs = (uint32_t)pl.cs;
+  for (int o = 0; o < n_o; o++) {
+    const int p = ms1 ? raw.ms1_pos[o] : (int)pl.pos[o];
+    const int64_t seg1 = __ldg(raw.pos_start + p + 1);
+    int64_t idx = warp_lower_bound_window(raw.s_mz, __ldg(raw.pos_start + p), seg1, lo, prev_hi, lane);
+    while (idx < seg1) {  // chunks of 32 peaks in ascending m/z
+      const int64_t i = idx + lane;
+      const float m = __ldg(raw.s_mz + i);  // padded behind the last segment
+      const bool inw = i < seg1 && m <= hi;
+      const uint32_t c = __ldg(raw.s_cyc + i) - cs;
+      const bool take = inw && c < (uint32_t)C;
+      const unsigned tb = __ballot_sync(FULL, take);
+      if (tb) {
+        const float v = __ldg(raw.s_int + i);
+        const unsigned grp = __match_any_sync(FULL, take ? c : 0xFFFFFF00u + (uint32_t)lane);
+        const int rank = __popc(grp & ((1u << lane) - 1u));
+        const unsigned multi = __ballot_sync(FULL, take && rank > 0);
+        if (take && rank == 0) row[c] = __fadd_rn(row[c], v);
+        if (multi) {  // several peaks of this chunk fall into one cell: add them in lane (= m/z) order
+          int max_rank = rank;
+          for (int off = 16; off > 0; off >>= 1) max_rank = max(max_rank, __shfl_xor_sync(FULL, max_rank, off));
+          for (int r = 1; r <= max_rank; r++) {
+            __syncwarp();
+            if (take && rank == r) row[c] = __fadd_rn(row[c], v);
+          }
+        }
+        __syncwarp();
+      }
+      if (__ballot_sync(FULL, inw) != FULL) break;  // the window ended inside this chunk
+      idx += 32;
     }
-    __syncthreads();
-    float* dense = P.dense + it * (long long)P.layer_cap * P.c_cap;
-    const int n_items = nL * C;
-    for (int t0 = threadIdx.x; t0 < n_items; t0 += SEL_EXTRACT_THREADS * SEL_ILP) {
-      float lo[SEL_ILP], hi[SEL_ILP], prev_hi[SEL_ILP], acc[SEL_ILP];
-      int cell[SEL_ILP], n_o[SEL_ILP], cyc[SEL_ILP];
-      bool ms1[SEL_ILP];
-      int max_o = 0;
-#pragma unroll
-      for (int q = 0; q < SEL_ILP; q++) {
-        const int t = t0 + q * SEL_EXTRACT_THREADS;
-        n_o[q] = 0; acc[q] = 0.f; cell[q] = -1; lo[q] = 0.f; hi[q] = 0.f; prev_hi[q] = -1.f; cyc[q] = 0; ms1[q] = false;
-        if (t < n_items) {
-          const int k = t % nL, c = t / nL;  // layer fastest
-          lo[q] = s_lo[k]; hi[q] = s_hi[k];
-          prev_hi[q] = (k > 0 && k != nF) ? s_hi[k - 1] : -1.0f;
-          ms1[q] = k >= nF;
-          n_o[q] = ms1[q] ? raw.n_ms1_pos : nobs;
-          cyc[q] = spl.cs + c;
-          cell[q] = k * P.c_cap + c;
-          max_o = max(max_o, n_o[q]);
-        }
-      }
-      for (int o = 0; o < max_o; o++) {
-        uint32_t l[SEL_ILP], h[SEL_ILP], bend[SEL_ILP];
-        int64_t scan[SEL_ILP];
-#pragma unroll
-        for (int q = 0; q < SEL_ILP; q++) {
-          l[q] = 0; h[q] = 0; bend[q] = 0; scan[q] = 0;
-          if (o < n_o[q]) {
-            scan[q] = (int64_t)(ms1[q] ? raw.ms1_pos[o] : (int)spl.pos[o]) + (int64_t)cyc[q] * L;
-            const uint2 r = adb_bucket_pair(raw, scan[q], lo[q]);
-            l[q] = r.x; h[q] = r.y; bend[q] = r.y;
-          }
-        }
-        bool any = false;
-#pragma unroll
-        for (int q = 0; q < SEL_ILP; q++) any |= (h[q] - l[q] > 8u);
-        while (any) {  // interleaved binary searches: the SEL_ILP loads of a round are independent
-          any = false;
-          float v[SEL_ILP];
-          uint32_t mid[SEL_ILP];
-#pragma unroll
-          for (int q = 0; q < SEL_ILP; q++) {
-            mid[q] = (l[q] + h[q]) >> 1;
-            v[q] = (h[q] - l[q] > 8u) ? __ldg(raw.mz + mid[q]) : 0.f;
-          }
-#pragma unroll
-          for (int q = 0; q < SEL_ILP; q++)
-            if (h[q] - l[q] > 8u) {
-              if (v[q] < lo[q]) l[q] = mid[q] + 1; else h[q] = mid[q];
-              any |= (h[q] - l[q] > 8u);
-            }
-        }
-        AdbFound f[SEL_ILP];
-#pragma unroll
-        for (int q = 0; q < SEL_ILP; q++) {
-          f[q].idx = 0; f[q].inside = true; f[q].mz_at_idx = 3.0e38f;
-          if (o < n_o[q]) { f[q] = adb_finish_lower_bound(raw.mz, l[q], h[q], lo[q]); f[q].inside = f[q].idx < bend[q]; }
-        }
-#pragma unroll
-        for (int q = 0; q < SEL_ILP; q++)
-          if (o < n_o[q]) {
-            // common case: the first candidate peak (still in registers) lies above the window -> no hit
-            if (f[q].inside && !(f[q].mz_at_idx <= hi[q]) && !(prev_hi[q] >= lo[q])) continue;
-            const uint32_t stop = adb_spectrum_stop(raw, scan[q]);
-            uint32_t i2 = f[q].idx;
-            if (prev_hi[q] >= lo[q])
-              while (i2 < stop && __ldg(raw.mz + i2) <= prev_hi[q]) i2++;
-            while (i2 < stop && __ldg(raw.mz + i2) <= hi[q]) {
-              acc[q] = __fadd_rn(acc[q], __ldg(raw.intensity + i2));
-              i2++;
-            }
-          }
-      }
-#pragma unroll
-      for (int q = 0; q < SEL_ILP; q++)
-        if (cell[q] >= 0) dense[cell[q]] = acc[q];
+    __syncwarp();
+  }
+}
+
+// legacy pair (cycle windows too long for the fused kernel): rows to the dense HBM buffer, then adb_select_smooth_kernel
+__global__ void __launch_bounds__(SEL_EXTRACT_THREADS) adb_select_extract_kernel(const __grid_constant__ SelectParams P) {
+  __shared__ float s_row[SEL_ROWS_PER_CTA][1024];  // rows longer than 1024 cycles accumulate in the dense buffer itself
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n_rows = P.chunk_n * (long long)P.layer_cap;
+  for (long long task = (long long)blockIdx.x * SEL_ROWS_PER_CTA + warp; task < n_rows; task += (long long)gridDim.x * SEL_ROWS_PER_CTA) {
+    const long long it = task / P.layer_cap;
+    const int k = (int)(task - it * P.layer_cap);
+    const PrecPlan pl = P.plan[it];
+    const int nL = (int)pl.nF + (int)pl.nI, C = pl.C;
+    if (!pl.ok || k >= nL) continue;  // warp-uniform
+    float* out = P.dense + (it * (long long)P.layer_cap + k) * P.c_cap;
+    const bool in_smem = C <= 1024;
+    float* row = in_smem ? s_row[warp] : out;
+    for (int c = lane; c < C; c += 32) row[c] = 0.f;
+    __syncwarp();
+    extract_row(P, pl, it, k, row, lane);
+    if (in_smem) {
+      for (int c = lane; c < C; c += 32) out[c] = row[c];
+      __syncwarp();
     }
   }
 }
@@ -545,6 +544,121 @@ __global__ void adb_select_smooth_kernel(const __grid_constant__ SelectParams P)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused selection, ONE WARP PER PRECURSOR (cycle windows up to SEL_FUSED_MAX_C, kernel width <= 32), no CTA barriers:
+// the warp walks the XIC rows (layers) of its precursor in order; a row is extracted through the m/z-major index
+// straight into shared memory (with its circular halo), a bit mask marks its non-zero cycles, and the 2 x kw Gaussian
+// is evaluated over the NON-ZERO taps only — fma(k, 0, acc) == acc exactly, so skipping them reproduces the dense fp64
+// sum bit for bit, in the reference's tap order (kernel rows, then columns ascending = cycles descending).  > 97 % of
+// the XIC cells are zero; most smoothed cells have no tap at all and cost one funnel shift.  log(x + 1) is added to the
+// per-cell f32 layer sums as the rows come (layer order, selection.py:206-226); then the warp normalises, picks peaks
+// and writes the candidates (slot_finish).
+#define SEL_FUSED_THREADS 256
+#define SEL_FUSED_WARPS (SEL_FUSED_THREADS / 32)
+#define SEL_FUSED_MAX_C 1024
+
+struct FusedLayout { int kern_bytes, warp_bytes, score_off, lf_off, lp_off, ext_off, mask_off; size_t bytes; };
+__host__ __device__ inline FusedLayout fused_layout(int c_cap, int kw) {
+  FusedLayout f;
+  f.kern_bytes = (int)(sizeof(double) * 2 * (size_t)kw);
+  size_t b = 0;
+  f.score_off = (int)b; b += sizeof(double) * (size_t)((c_cap + 3) & ~3);
+  f.lf_off = (int)b; b += sizeof(float) * (size_t)((c_cap + 3) & ~3);
+  f.lp_off = (int)b; b += sizeof(float) * (size_t)((c_cap + 3) & ~3);
+  f.ext_off = (int)b; b += sizeof(float) * (size_t)((c_cap + kw + 3) & ~3);
+  f.mask_off = (int)b; b += sizeof(uint32_t) * (size_t)(((c_cap + kw + 31) / 32 + 2 + 1) & ~1);
+  f.warp_bytes = (int)b;
+  f.bytes = (size_t)f.kern_bytes + (size_t)SEL_FUSED_WARPS * b + 16;
+  return f;
+}
+
+__global__ void __launch_bounds__(SEL_FUSED_THREADS) adb_select_fused_kernel(const __grid_constant__ SelectParams P) {
+  extern __shared__ __align__(16) unsigned char dyn_f[];
+  __shared__ SlotMeta slots[SEL_FUSED_WARPS];
+  const adb_selection_config& cfg = P.cfg;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kw = P.kw, off = kw - 1 - kw / 2;
+  const FusedLayout fl = fused_layout(P.c_cap, kw);
+  double* skern = (double*)dyn_f;  // [2][kw]; divergent tap indices would serialise in the constant bank
+  unsigned char* wb = dyn_f + fl.kern_bytes + (size_t)warp * fl.warp_bytes;
+  double* score = (double*)(wb + fl.score_off);
+  float* lf = (float*)(wb + fl.lf_off);
+  float* lp = (float*)(wb + fl.lp_off);
+  float* ext = (float*)(wb + fl.ext_off);
+  uint32_t* mask = (uint32_t*)(wb + fl.mask_off);
+  SlotMeta& sl = slots[warp];
+  for (int t = tid; t < 2 * kw; t += SEL_FUSED_THREADS) skern[t] = P.kern[t];
+  __syncthreads();
+  const uint32_t kw_mask = (kw >= 32) ? 0xFFFFFFFFu : ((1u << kw) - 1u);
+  const long long n_warps = (long long)gridDim.x * SEL_FUSED_WARPS;
+  for (long long it = (long long)blockIdx.x * SEL_FUSED_WARPS + warp; it < P.chunk_n; it += n_warps) {
+    const PrecPlan pl = P.plan[it];
+    if (!pl.ok) continue;  // warp-uniform
+    const int C = pl.C, nF = pl.nF, nL = (int)pl.nF + (int)pl.nI;
+    const int stride = C + kw - 1;  // ext[t] = x[(t - off) mod C], so x[(c + kw/2 - b) mod C] = ext[c + kw - 1 - b]
+    const int n_words = (stride + 31) >> 5;
+    for (int c = lane; c < C; c += 32) { lf[c] = 0.f; lp[c] = 0.f; }
+    for (int k = 0; k < nL; k++) {
+      for (int t = lane; t < stride + 1; t += 32) ext[t] = 0.f;
+      __syncwarp();
+      extract_row(P, pl, it, k, ext + off, lane);
+      for (int t = lane; t < stride; t += 32)  // circular halo (C >= kw is guaranteed by the plan)
+        if (t < off) ext[t] = ext[t + C]; else if (t >= off + C) ext[t] = ext[t - C];
+      __syncwarp();
+      unsigned any_nz = 0;
+      for (int w = 0; w <= n_words; w++) {
+        const int t = w * 32 + lane;
+        const unsigned b = __ballot_sync(FULL, t < stride && ext[t] != 0.f);
+        if (lane == 0) mask[w] = b;
+        any_nz |= b;
+      }
+      __syncwarp();
+      if (!any_nz) continue;  // empty row: every smoothed cell is 0, log(0 + 1) adds nothing
+      float* lacc = (k < nF) ? lf : lp;
+      for (int c = lane; c < C; c += 32) {
+        const uint32_t w = __funnelshift_r(mask[c >> 5], mask[(c >> 5) + 1], c & 31) & kw_mask;  // taps t = c .. c + kw - 1
+        if (w) {
+          double acc = 0.0;
+#pragma unroll 1
+          for (int a = 0; a < 2; a++) {
+            const double* kr = skern + a * kw + (kw - 1);
+            uint32_t ww = w;
+            while (ww) {  // b ascending = t descending
+              const int hb = 31 - __clz(ww);
+              ww ^= 1u << hb;
+              acc = fma(kr[-hb], (double)ext[c + hb], acc);
+            }
+          }
+          const float sm = (float)acc;
+          if (sm != 0.f) lacc[c] = __fadd_rn(lacc[c], (float)log((double)sm + 1.0));
+        }
+      }
+      __syncwarp();
+    }
+    for (int c = lane; c < C; c += 32) score[c] = (double)__fadd_rn(lf[c], lp[c]);  // raw feature (selection.py:221-224)
+    __syncwarp();
+    // normalisation (selection.py:405-428)
+    double mean = cfg.use_weighted_score ? cfg.feature_mean : 0.0;
+    double stdv = cfg.use_weighted_score ? cfg.feature_std : 0.0;
+    const double wgt = cfg.use_weighted_score ? cfg.feature_weight : 1.0;
+    if (!cfg.use_weighted_score) {  // amean1 / astd1 over the (2, C) feature map; sequential, rare path
+      float accf = 0.f;
+      for (int s = 0; s < 2; s++) for (int c = 0; c < C; c++) accf = __fadd_rn(accf, (float)score[c]);
+      mean = (double)accf / (double)(2 * C);
+      double v = 0;
+      for (int s = 0; s < 2; s++) for (int c = 0; c < C; c++) { double d = score[c] - mean; v = __dadd_rn(v, __dmul_rn(d, d)); }
+      stdv = sqrt(v / (double)(2 * C));
+    }
+    __syncwarp();
+    for (int c = lane; c < C; c += 32) score[c] = 0.0 + __dmul_rn(wgt, (score[c] - mean)) / (stdv + 1e-6);
+    if (lane == 0) { sl.C = C; sl.frame_lo = pl.frame_lo; sl.row = pl.row; sl.score = score; }
+    __syncwarp();
+    slot_finish(P, sl, lane);
+    __syncwarp();
+  }
+}
+
 size_t smooth_smem_bytes(int c_cap, int kw) { return sizeof(double) * ((size_t)((c_cap + 3) & ~3) + 2 * (size_t)((c_cap + kw - 1 + 4 + 3) & ~3)) + 16; }
 
 template <int KW>
@@ -555,17 +669,26 @@ void launch_smooth(const SelectParams& P, int threads, long long grid, size_t dy
 
 }  // namespace
 
-size_t adb_select_bytes_per_precursor(int c_cap, int max_layers) {
-  return sizeof(PrecPlan) + 2 * sizeof(float) * (size_t)max_layers + sizeof(float) * (size_t)max_layers * (size_t)c_cap;
+// the fused kernel needs its rows in shared memory and a kernel width that fits one 32-bit tap mask
+bool adb_select_fused(int c_cap, int max_layers, int kw) {
+  if (getenv("ADB_SELECT_LEGACY")) return false;  // test hook: force the extract + dense-smoothing pair
+  return kw <= 32 && c_cap <= SEL_FUSED_MAX_C && fused_layout(c_cap, kw).bytes + SEL_FUSED_WARPS * sizeof(SlotMeta) + 1024 <= 200 * 1024;
 }
 
-// Runs plan + extract + smooth for positions [chunk_begin, chunk_begin + chunk_n) of the processing order.
-// `workspace` must hold chunk_n * adb_select_bytes_per_precursor(c_cap, max_layers) bytes (+ 256 for alignment).
+size_t adb_select_bytes_per_precursor(int c_cap, int max_layers, int kw) {
+  const size_t base = sizeof(PrecPlan) + 2 * sizeof(float) * (size_t)max_layers;
+  if (adb_select_fused(c_cap, max_layers, kw)) return base;
+  return base + sizeof(float) * (size_t)max_layers * (size_t)c_cap;
+}
+
+// Runs the selection for positions [chunk_begin, chunk_begin + chunk_n) of the processing order.
+// `workspace` must hold chunk_n * adb_select_bytes_per_precursor(c_cap, max_layers, kw) bytes (+ 1024 for alignment).
 void adb_launch_select_chunk(const DevRaw& raw, const DevLib& lib, const adb_selection_config& cfg, const double* h_kernel,
                              int kw, DevCandidatesOut out, int64_t chunk_begin, int64_t chunk_n, const int32_t* d_order,
                              uint32_t* d_status, int c_cap, int max_layers, void* workspace, int sm_count,
                              cudaStream_t stream, int* n_launches) {
   if (chunk_n <= 0) return;
+  const bool fused = adb_select_fused(c_cap, max_layers, kw);
   SelectParams P;
   P.raw = raw; P.lib = lib; P.cfg = cfg; P.kw = kw; P.out = out;
   for (int t = 0; t < 2 * ADB_MAX_KERNEL_W; t++) P.kern[t] = (t < 2 * kw) ? h_kernel[t] : 0.0;
@@ -576,12 +699,24 @@ void adb_launch_select_chunk(const DevRaw& raw, const DevLib& lib, const adb_sel
   P.plan = (PrecPlan*)take(sizeof(PrecPlan) * (size_t)chunk_n);
   P.win_lo = (float*)take(sizeof(float) * (size_t)chunk_n * max_layers);
   P.win_hi = (float*)take(sizeof(float) * (size_t)chunk_n * max_layers);
-  P.dense = (float*)take(sizeof(float) * (size_t)chunk_n * max_layers * c_cap);
+  P.dense = fused ? nullptr : (float*)take(sizeof(float) * (size_t)chunk_n * max_layers * c_cap);
 
   const int warps_per_block = SEL_PLAN_THREADS / 32;
   adb_select_plan_kernel<<<(unsigned)((chunk_n + warps_per_block - 1) / warps_per_block), SEL_PLAN_THREADS, 0, stream>>>(P);
 
-  long long blocks = std::min<long long>(chunk_n, (long long)sm_count * 64);  // CTA per precursor, grid-stride beyond
+  if (fused) {
+    const size_t dyn = fused_layout(c_cap, kw).bytes;
+    cudaFuncSetAttribute(adb_select_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adb_select_fused_kernel, SEL_FUSED_THREADS, dyn);
+    if (per_sm < 1) per_sm = 1;
+    const long long grid = std::min<long long>((chunk_n + SEL_FUSED_WARPS - 1) / SEL_FUSED_WARPS, (long long)sm_count * per_sm);  // persistent, warp per precursor
+    adb_select_fused_kernel<<<(unsigned)grid, SEL_FUSED_THREADS, dyn, stream>>>(P);
+    if (n_launches) (*n_launches) += 2;
+    return;
+  }
+  const long long rows = chunk_n * (long long)max_layers;  // warp per XIC row, grid-stride beyond the resident wave
+  long long blocks = std::min<long long>((rows + SEL_ROWS_PER_CTA - 1) / SEL_ROWS_PER_CTA, (long long)sm_count * 16);
   adb_select_extract_kernel<<<(unsigned)blocks, SEL_EXTRACT_THREADS, 0, stream>>>(P);
 
   int threads = (((c_cap + 3) / 4 + 31) / 32) * 32;  // 4 adjacent cycles per thread

@@ -478,3 +478,19 @@ def test_chunked_scoring_equals_single_block(engine):
     for k in ("features", "valid", "fragment_mz_observed", "fragment_correlation", "fragment_type"):
         assert np.array_equal(got[k], np.concatenate([one[k]] * reps), equal_nan=True), k
     dlib.close(); draw.close()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(rt_tolerance=400.0), dict(use_weighted_score=False, candidate_count=5)])
+def test_selection_legacy_pair_matches_oracle(engine, oracle_lib, monkeypatch, kw):
+    """Cycle windows too long for the fused kernel use the extract + dense-smoothing kernel pair; force it here."""
+    monkeypatch.setenv("ADB_SELECT_LEGACY", "1")
+    raw, lib, p, draw, dlib = _device_objects(engine, "parity_small")
+    args = dict(kw)
+    rt_tol = args.pop("rt_tolerance", p["rt_tolerance"])
+    cfg = H.selection_config(rt_tol, **args).to_struct()
+    kernel = H.default_kernel(raw)
+    got = engine.select_candidates(draw, dlib, cfg, kernel)
+    ref = oracle_lib.select_candidates(raw, lib, cfg, kernel)
+    assert_candidates_equal(got, ref)
+    assert (got["score"] > 0).sum() > 0
+    dlib.close(); draw.close()
