@@ -365,13 +365,27 @@ __global__ void score_order_key4_kernel(DevCandidatesIn cand, uint64_t* keys, in
   vals[i] = (int32_t)i;
 }
 
-// max scan extent and frame extent of the candidates -> out[0], out[1]
-__global__ void cand_extent_kernel(DevCandidatesIn cand, unsigned long long* out) {
+// max scan extent and frame extent of the candidates -> out[0], out[1]; out[2] != 0: a library row is out of range
+__global__ void cand_extent_kernel(DevCandidatesIn cand, int64_t n_precursors, unsigned long long* out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cand.n) return;
-  int64_t s = cand.scan_stop[i] - cand.scan_start[i], f = cand.frame_stop[i] - cand.frame_start[i];
-  if (s > 0) atomicMax(out, (unsigned long long)s);
-  if (f > 0) atomicMax(out + 1, (unsigned long long)f);
+  unsigned long long ms = 0ull, mf = 0ull, bad = 0ull;
+  if (i < cand.n) {
+    int64_t s = cand.scan_stop[i] - cand.scan_start[i], f = cand.frame_stop[i] - cand.frame_start[i];
+    if (cand.frame_start[i] < 0 || cand.frame_stop[i] < 0) f = 0;
+    ms = s > 0 ? (unsigned long long)s : 0ull;
+    mf = f > 0 ? (unsigned long long)f : 0ull;
+    bad = (cand.lib_row[i] < 0 || cand.lib_row[i] >= n_precursors) ? 1ull : 0ull;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    ms = max(ms, __shfl_xor_sync(0xffffffffu, ms, off));
+    mf = max(mf, __shfl_xor_sync(0xffffffffu, mf, off));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (ms) atomicMax(out, ms);
+    if (mf) atomicMax(out + 1, mf);
+    if (bad) atomicOr(out + 2, 1ull);
+  }
 }
 
 // upper bounds of the selection window of any precursor: cycles (jitclasses/utils.py:62-70) and scans (bruker_jit.py:227-233)
@@ -507,21 +521,22 @@ int run_scoring4d(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* 
   return 0;
 }
 
-// resident path: extents of the compacted candidates (4-D scratch sizing)
-int resident_extents(adb_rawfile* raw, int64_t* s_max, int64_t* f_max) {
+// extents of the device-resident candidate table (scratch sizing) + library-row validation
+int resident_extents(adb_rawfile* raw, int64_t* s_max, int64_t* f_max, int64_t n_precursors = (int64_t)1 << 62, int64_t* bad_row = nullptr) {
   cudaStream_t st = raw->stream;
-  if (raw->extent.reserve(2 * sizeof(unsigned long long))) return 1;
-  CUDA_TRY(cudaMemsetAsync(raw->extent.ptr, 0, 2 * sizeof(unsigned long long), st));
+  if (raw->extent.reserve(4 * sizeof(unsigned long long))) return 1;
+  CUDA_TRY(cudaMemsetAsync(raw->extent.ptr, 0, 4 * sizeof(unsigned long long), st));
   const int64_t n = raw->d_cand.n;
   if (n > 0) {
-    cand_extent_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->d_cand, raw->extent.as<unsigned long long>());
+    cand_extent_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->d_cand, n_precursors, raw->extent.as<unsigned long long>());
     raw->launches++;
   }
-  unsigned long long h[2] = {0, 0};
+  unsigned long long h[3] = {0, 0, 0};
   CUDA_TRY(cudaMemcpyAsync(h, raw->extent.ptr, sizeof(h), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   *s_max = (int64_t)h[0];
   *f_max = (int64_t)h[1];
+  if (bad_row) *bad_row = (int64_t)h[2];
   return 0;
 }
 
@@ -1100,16 +1115,8 @@ int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scori
   // H2D of the candidate table
   if (raw->cand_in.reserve(cand_in_bytes(std::max<int64_t>(n, 1)))) return 1;
   CandInPtrs c = carve_cand_in(raw->cand_in.ptr, std::max<int64_t>(n, 1));
-  int64_t c_max = 0, s_max = 0;
   if (n > 0) {
     const size_t N = (size_t)n;
-    const int64_t P = lib->dev.n_precursors, L = raw->is4d ? 1 : raw->dev.cycle_len;  // 4-D: extent in frames
-    for (int64_t i = 0; i < n; i++) {
-      if (cand->lib_row[i] < 0 || cand->lib_row[i] >= P) return fail("candidate " + std::to_string(i) + " refers to a precursor outside the library");
-      if (cand->frame_start[i] >= 0 && cand->frame_stop[i] >= 0)
-        c_max = std::max<int64_t>(c_max, cand->frame_stop[i] / L - cand->frame_start[i] / L);
-      s_max = std::max<int64_t>(s_max, cand->scan_stop[i] - cand->scan_start[i]);
-    }
     CUDA_TRY(cudaMemcpyAsync(c.lib_row, cand->lib_row, 8 * N, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(c.rank, cand->rank, N, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(c.scan_start, cand->scan_start, 8 * N, cudaMemcpyHostToDevice, st));
@@ -1121,6 +1128,11 @@ int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scori
   }
   raw->d_cand = DevCandidatesIn{n, c.lib_row, c.rank, c.scan_start, c.scan_stop, c.scan_center, c.frame_start, c.frame_stop, c.frame_center};
   raw->n_cand = n;
+  // validation and the scratch extents (longest candidate in frames / scans) are computed on the device
+  int64_t s_max = 0, f_max = 0, bad_row = 0;
+  if (resident_extents(raw, &s_max, &f_max, lib->dev.n_precursors, &bad_row)) return 1;
+  if (bad_row) return fail("a candidate refers to a precursor outside the library");
+  const int64_t c_max = raw->is4d ? f_max : f_max / raw->dev.cycle_len + 1;
   CUDA_TRY(cudaEventRecord(raw->ev[1], st));
   if (!raw->is4d && c_max > 4096) return fail("a candidate spans more than 4096 cycles");
   if (run_scoring(raw, lib, cfg, c_max, s_max, out)) return 1;  // records ev[2] between the kernels and the (remaining) D2H

@@ -28,7 +28,9 @@ namespace cg = cooperative_groups;
 #ifndef SCORE_THREADS
 #define SCORE_THREADS 128  // threads per CTA; the tiles of a CTA move through the code in lock step (see adb_score_kernel)
 #endif
+#ifndef SCORE_CTAS_PER_SM
 #define SCORE_CTAS_PER_SM (512 / SCORE_THREADS)
+#endif
 #define SCORE_PHASES 3     // CTA barriers inside one candidate round
 #ifndef SMEM_FLOATS_PER_TILE
 #define SMEM_FLOATS_PER_TILE 1024  // 4 KB dynamic scratch per candidate tile; larger cubes use the HBM workspace
