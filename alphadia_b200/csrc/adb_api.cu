@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -75,7 +76,17 @@ struct adb_library {
   std::vector<void*> allocs;
   int64_t bytes = 0;
   int max_lib_fragments = 0;
+  void* pool = nullptr;   // the single device allocation behind `dev`
+  size_t pool_bytes = 0;
 };
+
+namespace {
+// The operators upload a library batch per call; cudaMalloc/cudaFree of a 0.5 GB pool cost 10-100 ms and synchronise the
+// device, so one released pool per device is kept for the next adb_library_create.
+struct LibraryPoolCache { void* ptr = nullptr; size_t bytes = 0; };
+LibraryPoolCache g_pool_cache[64];
+std::mutex g_pool_mutex;
+}  // namespace
 
 struct adb_rawfile {
   int device = 0;
@@ -981,9 +992,20 @@ int adb_library_create(const adb_library_desc* d, int device, adb_library_t** ou
   add(12, d->frag_loss_type, Fn); add(13, d->frag_charge, Fn); add(14, d->frag_number, Fn); add(15, d->frag_position, Fn);
   add(16, d->frag_cardinality, Fn);
   void* pool = nullptr;
-  cudaError_t e = cudaMalloc(&pool, total + 256);
-  if (e != cudaSuccess) { delete l; return fail(std::string("cudaMalloc(library) failed: ") + cudaGetErrorString(e)); }
-  l->allocs.push_back(pool);
+  size_t pool_bytes = 0;
+  cudaError_t e = cudaSuccess;
+  if (device >= 0 && device < 64) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    LibraryPoolCache& c = g_pool_cache[device];
+    if (c.ptr && c.bytes >= total + 256) { pool = c.ptr; pool_bytes = c.bytes; c.ptr = nullptr; c.bytes = 0; }
+  }
+  if (!pool) {
+    pool_bytes = total + total / 16 + 256;
+    e = cudaMalloc(&pool, pool_bytes);
+    if (e != cudaSuccess) { delete l; return fail(std::string("cudaMalloc(library) failed: ") + cudaGetErrorString(e)); }
+  }
+  l->pool = pool;
+  l->pool_bytes = pool_bytes;
   l->bytes = (int64_t)total;
   for (int k = 0; k < 17 && e == cudaSuccess; k++)
     if (items[k].bytes) e = cudaMemcpyAsync((char*)pool + items[k].off, items[k].host, items[k].bytes, cudaMemcpyHostToDevice, cudaStreamPerThread);
@@ -1008,6 +1030,15 @@ void adb_library_destroy(adb_library_t* l) {
   if (!l) return;
   cudaSetDevice(l->device);
   for (void* p : l->allocs) cudaFree(p);
+  if (l->pool) {
+    void* to_free = l->pool;
+    if (l->device >= 0 && l->device < 64) {
+      std::lock_guard<std::mutex> lock(g_pool_mutex);
+      LibraryPoolCache& c = g_pool_cache[l->device];
+      if (!c.ptr || c.bytes < l->pool_bytes) { to_free = c.ptr; c.ptr = l->pool; c.bytes = l->pool_bytes; }  // keep the larger one
+    }
+    if (to_free) cudaFree(to_free);
+  }
   delete l;
 }
 

@@ -18,9 +18,10 @@
 //               the rare cell beyond that is recomputed sequentially in the reference's order.
 //     smooth    the tile is > 99 % zeros.  fma(k, 0, acc) == acc exactly, so the 30 x 30 circular Gaussian is
 //               evaluated over the NON-ZERO inputs only, in the reference's summation order (kernel rows, then
-//               kernel columns, ascending): per tile row a short descending column list (<= 16 entries; denser rows
-//               take the direct 30-tap loop).  fp64 FMA, one rounding to f32, log(x + 1) in fp64 rounded to f32,
-//               f32 layer sums — only for outputs that are non-zero.
+//               kernel columns, ascending): the tile rows carry their circular halo and a bit mask of their non-zero
+//               columns; an output cell visits only the non-empty rows inside its window and, per row, the set bits
+//               of its 30-column tap window (one funnel shift).  fp64 FMA, one rounding to f32, log(x + 1) in fp64
+//               rounded to f32, f32 layer sums — only for outputs that are non-zero.
 //   score     (x - mean) / (std + 1e-6) * w in fp64; strict 5-point maxima in both axes -> peak list; top-N by a
 //             block arg-max with the reference's tie order; close-peak suppression, symmetric limits, optional
 //             join of overlapping candidates, clamped write-out (integer-exact tail).
@@ -33,7 +34,6 @@
 #define S4_WARPS (S4_THREADS / 32)
 #define S4_MAX_LAYERS (ADB_MAX_LIB_FRAGMENTS + ADB_MAX_ISOTOPES)
 #define S4_MAX_CAND 16
-#define S4_LIST_CAP 16
 
 namespace {
 
@@ -231,12 +231,17 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
   // shared memory carve-up
   double* s_kern = (double*)dyn4;
   unsigned char* sp = dyn4 + sizeof(double) * (size_t)kh * kw;
+  // tile rows carry the circular halo: trow[t] = x[(t - off) mod C], t in [0, C + kw - 1), row stride cx_cap
+  const int off = kw - 1 - sw;
+  const int cx_cap = P.c_cap + kw;
+  const int mw_cap = (cx_cap + 31) / 32 + 1;  // mask words per row (+1 so the funnel shift may read one word beyond)
   uint32_t* tile = (uint32_t*)sp;
-  if (P.tile_in_smem) sp += sizeof(uint32_t) * cells_cap;
-  unsigned short* rowlist = (unsigned short*)sp; sp += sizeof(unsigned short) * (size_t)P.s_cap * S4_LIST_CAP;
+  if (P.tile_in_smem) sp += sizeof(uint32_t) * (size_t)P.s_cap * cx_cap;
+  uint32_t* rmask = (uint32_t*)sp; sp += sizeof(uint32_t) * (size_t)P.s_cap * mw_cap;  // non-zero columns of every tile row
   unsigned short* rowcnt = (unsigned short*)sp; sp += sizeof(unsigned short) * (size_t)((P.s_cap + 7) & ~7);
   unsigned short* nzrows = (unsigned short*)sp; sp += sizeof(unsigned short) * (size_t)((P.s_cap + 7) & ~7);  // non-empty rows, ascending
   unsigned short* rowrank = (unsigned short*)sp; sp += sizeof(unsigned short) * (size_t)((P.s_cap + 7) & ~7);  // # non-empty rows <= r
+  uint32_t* rowtouch = (uint32_t*)sp; sp += sizeof(uint32_t) * (size_t)(((P.s_cap + 31) / 32 + 1) & ~1);      // rows hit by the current layer
   unsigned char* smask = sp;  // [Fr][S] bit 0: fragment quad window, bit 1: MS1
   // HBM workspace of this CTA
   char* wp = P.ws + (size_t)blockIdx.x * P.ws_per_cta;
@@ -248,6 +253,7 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
   if (!P.tile_in_smem) tile = (uint32_t*)wp;
 
   for (int t = tid; t < kh * kw; t += S4_THREADS) s_kern[t] = P.kern[t];
+  for (long long t = tid; t < (long long)P.s_cap * cx_cap; t += S4_THREADS) tile[t] = 0u;  // rows are re-zeroed after use
   const uint32_t smi = (uint32_t)raw.scan_max_index;
   const uint32_t Fr = (uint32_t)raw.Fr, z = (uint32_t)raw.zeroth_frame;
 
@@ -283,8 +289,12 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
     for (int t = tid; t < cells; t += S4_THREADS) { lf[t] = 0.f; lp[t] = 0.f; }
 
     const long long p_lo = st.f0 * (long long)smi, p_hi = st.f1 * (long long)smi;
+    const int cx = C + kw - 1;            // used length of a tile row
+    const int n_words = (cx + 31) >> 5;
+    const uint32_t kw_mask = (kw >= 32) ? 0xFFFFFFFFu : ((1u << kw) - 1u);
     for (int l = 0; l < nL; l++) {
-      for (int t = tid; t < cells; t += S4_THREADS) tile[t] = 0u;
+      for (int t = tid; t < S; t += S4_THREADS) rowcnt[t] = 0;
+      for (int t = tid; t < (S + 31) / 32; t += S4_THREADS) rowtouch[t] = 0u;
       __syncthreads();
       // ---- XIC extraction (bruker_jit.py:506-584) ---------------------------------------------------
       const unsigned bit = (l < nF) ? 1u : 2u;
@@ -303,31 +313,39 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
           const long long rc = (long long)cyc - st.cs;
           if (rc < 0 || rc >= C) continue;
           if (!(smask[fic * S + (int)rs] & bit)) continue;
-          atomicAdd(&tile[(int)rs * C + (int)rc], (uint32_t)__ldg(raw.intensity + k));
+          atomicAdd(&tile[(int)rs * cx_cap + off + (int)rc], (uint32_t)__ldg(raw.intensity + k));
+          const uint32_t rbit = 1u << ((int)rs & 31);
+          if (!(rowtouch[(int)rs >> 5] & rbit)) atomicOr(&rowtouch[(int)rs >> 5], rbit);
         }
       }
       __syncthreads();
-      // ---- integer sums -> f32 bit patterns; per-row descending column lists of the non-zero cells -----
+      // ---- integer sums -> f32 bit patterns, circular halo, per-row masks of the non-zero columns ----------
       for (int r = warp; r < S; r += S4_WARPS) {
-        int cnt = 0;
-        for (int base = ((C - 1) >> 5) << 5; base >= 0; base -= 32) {
+        if (!((rowtouch[r >> 5] >> (r & 31)) & 1u)) continue;  // untouched rows are all zero; warp-uniform
+        uint32_t* trow = tile + r * cx_cap;
+        for (int base = 0; base < C; base += 32) {
           const int c = base + lane;
-          uint32_t v = (c < C) ? tile[r * C + c] : 0u;
+          const uint32_t v = (c < C) ? trow[off + c] : 0u;
           if (v != 0u) {
-            float fv = (v < (1u << 24)) ? (float)v : seq_cell_sum(raw, st, l, r, c, bit, smask);
-            tile[r * C + c] = __float_as_uint(fv);
+            const float fv = (v < (1u << 24)) ? (float)v : seq_cell_sum(raw, st, l, r, c, bit, smask);
+            trow[off + c] = __float_as_uint(fv);
           }
-          const unsigned b = __ballot_sync(FULL, v != 0u);
-          if (v != 0u) {
-            const int pos = cnt + __popc(b & ~((2u << lane) - 1u));  // higher columns first
-            if (pos < S4_LIST_CAP) rowlist[r * S4_LIST_CAP + pos] = (unsigned short)c;
-          }
-          cnt += __popc(b);
         }
-        if (lane == 0) rowcnt[r] = (unsigned short)min(cnt, 65535);
+        __syncwarp();
+        for (int t = lane; t < cx; t += 32)  // C >= kw is guaranteed by setup4 (_is_valid)
+          if (t < off) trow[t] = trow[t + C]; else if (t >= off + C) trow[t] = trow[t - C];
+        __syncwarp();
+        unsigned any = 0;
+        for (int w = 0; w <= n_words; w++) {
+          const int t = w * 32 + lane;
+          const unsigned b = __ballot_sync(FULL, t < cx && trow[t] != 0u);
+          if (lane == 0) rmask[r * mw_cap + w] = b;
+          any |= b;
+        }
+        if (lane == 0) rowcnt[r] = any ? 1 : 0;
       }
       __syncthreads();
-      if (warp == 0) {  // ascending list of the non-empty tile rows
+      if (warp == 0) {  // ascending list of the non-empty tile rows + rank of every row
         int M = 0;
         for (int base = 0; base < S; base += 32) {
           const int r = base + lane;
@@ -343,7 +361,8 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
       // ---- sparse circular smoothing + log-sum (fft.py:141-212, selection.py:206-226) ----------------
       // out[i][j] = sum_a sum_b k[a][b] x[(i + sh - a) mod S][(j + sw - b) mod C], a then b ascending: for one output
       // cell the input rows are visited downwards (circularly) from r0 = (i + sh) mod S, only the non-empty ones, and
-      // inside a row the columns downwards (circularly) from jc = (j + sw) mod C.
+      // inside a row x[(j + sw - b) mod C] = trow[j + kw - 1 - b]: the set bits of the row mask in [j, j + kw), from
+      // the highest (b = 0) down.
       float* lacc = (l < nF) ? lf : lp;
       const int segs = (C + 31) >> 5;
       const int M = st.n_nzrows;
@@ -360,55 +379,49 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
             if (a >= kh) continue;
           }
           for (int seg = 0; seg < segs; seg++) {
-          const int j = seg * 32 + lane;
-          int jc = min(j, C - 1) + sw;  // lanes beyond the row compute a discarded duplicate of the last cell
-          if (jc >= C) jc -= C;
-          double acc = 0.0;
-          for (int step = 0; step < M; step++) {
-            int k = k0 - 1 - step;
-            if (k < 0) k += M;
-            const int r = nzrows[k];
-            int a = r0 - r;
-            if (a < 0) a += S;
-            if (a >= kh) break;  // a grows along the sequence; warp-uniform
-            const int n = rowcnt[r];
-            const double* krow = s_kern + a * kw;
-            const uint32_t* trow = tile + r * C;
-            if (n <= S4_LIST_CAP) {
-              const unsigned short* lst = rowlist + r * S4_LIST_CAP;
-              const int maxc = lst[0], minc = lst[n - 1];
-              const unsigned m1 = __ballot_sync(FULL, maxc > jc - kw && minc <= jc);
-              const unsigned m2 = __ballot_sync(FULL, maxc > jc + C - kw);
-              if (m1)
-                for (int e = 0; e < n; e++) {  // columns <= jc, descending: b = jc - col ascending
-                  const int col = lst[e];
-                  const int b = jc - col;
-                  if (b >= 0 && b < kw) acc = fma(krow[b], (double)__uint_as_float(trow[col]), acc);
+            const int j = min(seg * 32 + lane, C - 1);  // lanes beyond the row compute a discarded duplicate of the last cell
+            double acc = 0.0;
+            bool any = false;
+            for (int step = 0; step < M; step++) {
+              int k = k0 - 1 - step;
+              if (k < 0) k += M;
+              const int r = nzrows[k];
+              int a = r0 - r;
+              if (a < 0) a += S;
+              if (a >= kh) break;  // a grows along the sequence; warp-uniform
+              const double* krow = s_kern + a * kw + (kw - 1);
+              const uint32_t* trow = tile + r * cx_cap + j;
+              const uint32_t* mrow = rmask + r * mw_cap + (j >> 5);
+              if (kw <= 32) {
+                uint32_t w = __funnelshift_r(mrow[0], mrow[1], j & 31) & kw_mask;  // taps t = j .. j + kw - 1
+                any |= (w != 0u);
+                while (w) {  // b ascending = t descending
+                  const int hb = 31 - __clz(w);
+                  w ^= 1u << hb;
+                  acc = fma(krow[-hb], (double)__uint_as_float(trow[hb]), acc);
                 }
-              if (m2)
-                for (int e = 0; e < n; e++) {  // wrapped columns > jc, descending: b = jc - col + C ascending
-                  const int col = lst[e];
-                  const int b = jc - col + C;
-                  if (col > jc && b < kw) acc = fma(krow[b], (double)__uint_as_float(trow[col]), acc);
+              } else {
+                for (int b = 0; b < kw; b++) {
+                  const uint32_t v = trow[kw - 1 - b];
+                  if (v != 0u) { any = true; acc = fma(krow[-(kw - 1 - b)], (double)__uint_as_float(v), acc); }
                 }
-            } else {
-              for (int b = 0; b < kw; b++) {
-                int col = jc - b;
-                if (col < 0) col += C;
-                const uint32_t v = trow[col];
-                if (v != 0u) acc = fma(krow[b], (double)__uint_as_float(v), acc);
+              }
+            }
+            if (any && seg * 32 + lane < C) {
+              const float sm = (float)acc;
+              if (sm != 0.f) {
+                const float lg = (float)log((double)sm + 1.0);
+                lacc[i * C + j] = __fadd_rn(lacc[i * C + j], lg);
               }
             }
           }
-          if (j < C) {
-            const float sm = (float)acc;
-            if (sm != 0.f) {
-              const float lg = (float)log((double)sm + 1.0);
-              lacc[i * C + j] = __fadd_rn(lacc[i * C + j], lg);
-            }
-          }
-          }
         }
+      __syncthreads();
+      for (int r = warp; r < S; r += S4_WARPS) {  // leave the tile all-zero for the next layer / precursor
+        if (!((rowtouch[r >> 5] >> (r & 31)) & 1u)) continue;
+        uint32_t* trow = tile + r * cx_cap;
+        for (int t = lane; t < cx; t += 32) trow[t] = 0u;
+      }
       __syncthreads();
     }
     // ---- score normalisation (selection.py:401-428) ---------------------------------------------------
@@ -558,10 +571,12 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
 }
 
 size_t select4d_smem_bytes(const DevRaw4& raw, const Select4Geometry& g, int kh, int kw, bool tile_in_smem) {
+  const size_t cx_cap = (size_t)g.c_cap + kw, mw_cap = (cx_cap + 31) / 32 + 1;
   size_t b = sizeof(double) * (size_t)kh * kw;
-  if (tile_in_smem) b += sizeof(uint32_t) * (size_t)g.s_cap * g.c_cap;
-  b += sizeof(unsigned short) * (size_t)g.s_cap * S4_LIST_CAP;
+  if (tile_in_smem) b += sizeof(uint32_t) * (size_t)g.s_cap * cx_cap;
+  b += sizeof(uint32_t) * (size_t)g.s_cap * mw_cap;
   b += 3 * sizeof(unsigned short) * (size_t)((g.s_cap + 7) & ~7);
+  b += sizeof(uint32_t) * (size_t)(((g.s_cap + 31) / 32 + 1) & ~1);
   b += (size_t)raw.Fr * g.s_cap;
   return b + 16;
 }
@@ -571,7 +586,7 @@ size_t select4d_smem_bytes(const DevRaw4& raw, const Select4Geometry& g, int kh,
 size_t adb_select4d_ws_bytes_per_cta(const Select4Geometry& g) {
   const size_t cells = (size_t)g.s_cap * g.c_cap;
   size_t b = 2 * sizeof(float) * cells + sizeof(double) * cells + (sizeof(double) + sizeof(int)) * (cells / 2 + 8) +
-             sizeof(uint32_t) * cells;
+             sizeof(uint32_t) * (size_t)g.s_cap * ((size_t)g.c_cap + ADB_MAX_KERNEL_W);  // tile with halo when it does not fit smem
   return (b + 255) & ~(size_t)255;
 }
 

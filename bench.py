@@ -382,7 +382,10 @@ def main():
     else:
         t_e2e_max, n_e2e_total = t_e2e, float(e2e_stats[-1]["n_candidates"])
     e2e_value = n_e2e_total * args.e2e_steps / t_e2e_max
-    log(f"[rank {rank}] e2e phases (ms, last step): {json.dumps(e2e_stats[-1].get('phases_ms', {}))}")
+    for k_step, st_ in enumerate(e2e_stats):
+        ph = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in st_.get("phases_ms", {}).items() if not isinstance(v, dict)}
+        log(f"[rank {rank}] e2e step {k_step} phases (ms): {json.dumps(ph)}")
+    log(f"[rank {rank}] e2e wall per step: {1000.0 * t_e2e / max(args.e2e_steps, 1):.1f} ms")
 
     if rank == 0:
         # ---- roofline of the dominant kernel ------------------------------------------------------
