@@ -688,6 +688,8 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
   };
   // fragments_frame_profile.sum(axis=1)
   auto isl = [&](int w, int fidx, int c) -> float {
+    if (nobs == 1)  // single observation: 0 + x == x exactly, no call
+      return quant_all ? twice(dfi[(long long)fidx * C + c]) : bp[(long long)w * C + c];
     return frame_profile_obs_sum(dfi + (long long)fidx * nobs * C, bp + (long long)w * C, nobs, C, c, quant_all ? -1 : best_obs);
   };
   if (cfg.experimental_xic) {
