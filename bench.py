@@ -411,15 +411,19 @@ def main():
         else:
             dom, dur, bytes_launch, unit_desc = ("adb_score4d_kernel" if is4d else "adb_score_kernel"), sc_k, ab["b_cand"] * n_cand, f"{ab['b_cand']:.0f} B/candidate x {n_cand} candidates (C_sc={c_sc_mean:.1f})"
         achieved = bytes_launch / (dur * 1e-3) / 1e9
-        traffic = None
+        traffic = None  # GB per launch: ncu DRAM bytes per unit (profiles/dram_traffic.json) x the units of this launch
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(dom)
+                ent = json.load(open(tpath)).get(dom) or {}
+                if ent.get("bytes_per_unit"):
+                    units = hp.n_precursors if ent.get("unit") == "precursor" else n_cand
+                    traffic = float(ent["bytes_per_unit"]) * units / 1e9
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": dom, "kernel_ms": dur, "algorithmic_bytes": unit_desc, "peak_source": peak_src,
+                    "traffic": traffic, "traffic_unit": "GB per launch (ncu dram bytes per unit x units)",
+                    "algorithmic_gb_per_launch": bytes_launch / 1e9, "kernel": dom, "kernel_ms": dur, "algorithmic_bytes": unit_desc, "peak_source": peak_src,
                     "other_kernel": {"adb_select_kernel_ms": sel_k, "adb_score_kernel_ms": sc_k,
                                      "select_frac": ab["b_prec"] * hp.n_precursors / (sel_k * 1e-3) / 1e9 / peak,
                                      "score_frac": ab["b_cand"] * n_cand / (sc_k * 1e-3) / 1e9 / peak}}

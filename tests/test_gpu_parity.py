@@ -594,3 +594,64 @@ def test_unsupported_inputs_fail_loudly(engine):
         cfg.top_k_fragments = 64
         engine.score_candidates(draw, dlib, cfg, H.candidates_in_from_arrays(lib0, bad)[0])
     dlib.close(); draw.close()
+
+
+def test_full_size_config2_properties(engine, oracle_lib):
+    """BASELINE.json config 2 at full size (50 k precursors, 91 200 spectra, 1.4e8 peaks): size-independent properties of the
+    candidate table (determinism, shard invariance, structural invariants) plus oracle parity on random subsamples."""
+    raw, pdf, fdf, lib, p = H.workload("config2")
+    P = len(lib["precursor_idx"])
+    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    kernel = H.default_kernel(raw)
+    draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+    full = engine.select_candidates(draw, dlib, cfg, kernel)
+    again = engine.select_candidates(draw, dlib, cfg, kernel)
+    for c in INT_COLS + ["score"]:
+        assert np.array_equal(full[c], again[c]), f"selection is not deterministic in {c}"
+    m = full["score"] > 0
+    assert m.sum() > 0.5 * 3 * P
+    # structural invariants of the candidate container (selection.py:480-526)
+    fs, fc, fe = (full[c][m].astype(np.int64) for c in ("frame_start", "frame_center", "frame_stop"))
+    assert (fs <= fc).all() and (fc < fe).all() and (fe <= raw.frame_max_index).all()
+    L = raw.cycle_len
+    assert ((fe - fs) // L <= 2 * 15 - 1).all() and ((fe - fs) // L >= 3 + 1).all()  # centre +- [3, 14] cycles, clipped at the run edges
+    rows = np.flatnonzero(m)
+    prec, rank = rows // 3, full["rank"][m].astype(np.int64)
+    assert np.array_equal(rank, rows % 3)  # ranks are the positions inside the precursor's block, no holes
+    sc = full["score"].reshape(P, 3)
+    assert (np.diff(np.where(sc > 0, sc, -np.inf), axis=1) <= 0).all()  # scores descend with rank
+    assert np.array_equal(full["precursor_idx"][m], lib["precursor_idx"][prec])
+    # shard invariance: two library halves == the whole library (bit-exact)
+    half = P // 2
+    prec_keys = ("precursor_idx", "frag_start_idx", "frag_stop_idx", "charge", "rt", "mobility", "mz", "isotopes")
+    parts = []
+    for sl in (slice(0, half), slice(half, P)):
+        sub = {k: (np.ascontiguousarray(v[sl]) if k in prec_keys else v) for k, v in lib.items()}
+        dsub = engine.DeviceLibrary(sub, device=0)
+        parts.append(engine.select_candidates(draw, dsub, cfg, kernel))
+        dsub.close()
+    for c in INT_COLS + ["score"]:
+        assert np.array_equal(np.concatenate([parts[0][c], parts[1][c]]), full[c]), f"shard invariance broken in {c}"
+    # oracle parity on a random subsample of precursors
+    rng = np.random.default_rng(3)
+    pick = np.sort(rng.choice(P, size=4000, replace=False))
+    sub = {k: (np.ascontiguousarray(v[pick]) if k in prec_keys else v) for k, v in lib.items()}
+    ref = oracle_lib.select_candidates(raw, sub, cfg, kernel)
+    idx = (pick[:, None] * 3 + np.arange(3)[None, :]).ravel()
+    for c in INT_COLS + ["score"]:
+        assert np.array_equal(full[c][idx], ref[c]), f"oracle parity (subsample) broken in {c}"
+    # scoring: the whole table on the device, a random subsample against the oracle, determinism
+    n = engine.select_candidates_resident(draw, dlib, cfg, kernel)
+    table = engine.fetch_candidate_table(draw, n)
+    from alphadia_b200 import _abi
+    scfg = H.scoring_config().to_struct()
+    got = engine.score_candidates(draw, dlib, scfg, _abi.candidates_in_from_table(table, n))
+    got2 = engine.score_candidates(draw, dlib, scfg, _abi.candidates_in_from_table(table, n))
+    assert np.array_equal(got["features"], got2["features"], equal_nan=True) and np.array_equal(got["valid"], got2["valid"])
+    assert got["valid"].sum() > 0.5 * n
+    pick_c = np.sort(rng.choice(n, size=6000, replace=False))
+    sub_t = {k: np.ascontiguousarray(v[:n][pick_c]) for k, v in table.items()}
+    ref_s = oracle_lib.score_candidates(raw, lib, scfg, _abi.candidates_in_from_table(sub_t, len(pick_c)))
+    got_s = {k: v[pick_c] for k, v in got.items()}
+    assert_scores_close(got_s, ref_s, what="config2 subsample")
+    dlib.close(); draw.close()
