@@ -34,6 +34,14 @@
 #define S4_WARPS (S4_THREADS / 32)
 #define S4_MAX_LAYERS (ADB_MAX_LIB_FRAGMENTS + ADB_MAX_ISOTOPES)
 #define S4_MAX_CAND 16
+#define S4_EVR_CAP 512            // cached (layer, tof row) event ranges per precursor; rows beyond are searched in place
+#ifndef S4_RB
+#define S4_RB 4                  // output rows per lane in the register-blocked smoothing
+#endif
+#ifndef S4_MIN_CTAS
+#define S4_MIN_CTAS 3
+#endif
+#define S4_BLOCKED_MIN_ROWS 4   // layers with at least this many non-empty rows take the blocked path
 
 namespace {
 
@@ -60,6 +68,8 @@ struct Sel4State {
   int nF, nI, C, S, ok;
   long long f0, f1, s0, s1, cs, row;
   int n_peaks, overflow, n_nzrows;
+  int rowoff[S4_MAX_LAYERS + 1];  // prefix sums of the tof-row counts of the layers
+  uint2 evr[S4_EVR_CAP];          // [first, last) event of every (layer, tof row) inside the frame window
   int red_idx[S4_WARPS];
   double red_val[S4_WARPS];
   int top_idx[S4_MAX_CAND];
@@ -220,7 +230,7 @@ __device__ void sym_limits_1d(const double* a, int C, int axis, int lo_o, int hi
   out[1] = min(center + limit + 1, n);
 }
 
-__global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_constant__ Select4Params P) {
+__global__ void __launch_bounds__(S4_THREADS, S4_MIN_CTAS) adb_select4d_kernel(const __grid_constant__ Select4Params P) {
   extern __shared__ __align__(16) unsigned char dyn4[];
   __shared__ Sel4State st;
   const DevRaw4& raw = P.raw;
@@ -289,6 +299,27 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
     for (int t = tid; t < cells; t += S4_THREADS) { lf[t] = 0.f; lp[t] = 0.f; }
 
     const long long p_lo = st.f0 * (long long)smi, p_hi = st.f1 * (long long)smi;
+    // every (layer, tof row) needs two binary searches on the push axis (dependent, mostly L2-missing loads): all of them
+    // are done here at once, one per thread, instead of a ~6 us latency chain in front of every layer
+    if (tid == 0) {
+      int acc = 0;
+      for (int l = 0; l < nL; l++) { st.rowoff[l] = acc; acc += max(st.t1[l] - st.t0[l], 0); }
+      st.rowoff[nL] = acc;
+    }
+    __syncthreads();
+    {
+      const int n_rows_all = min(st.rowoff[nL], S4_EVR_CAP);
+      for (int it2 = tid; it2 < 2 * n_rows_all; it2 += S4_THREADS) {
+        const int idx = it2 >> 1, which = it2 & 1;
+        int l = 0;
+        while (l + 1 < nL && st.rowoff[l + 1] <= idx) l++;
+        const int t = st.t0[l] + (idx - st.rowoff[l]);
+        const int64_t r0 = __ldg(raw.tof_indptr + t), r1 = __ldg(raw.tof_indptr + t + 1);
+        const uint32_t e = (uint32_t)adb_row_lower_bound(raw.push, r0, r1, which ? p_hi : p_lo);
+        if (which) st.evr[idx].y = e; else st.evr[idx].x = e;
+      }
+    }
+    __syncthreads();
     const int cx = C + kw - 1;            // used length of a tile row
     const int n_words = (cx + 31) >> 5;
     const uint32_t kw_mask = (kw >= 32) ? 0xFFFFFFFFu : ((1u << kw) - 1u);
@@ -299,10 +330,15 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
       // ---- XIC extraction (bruker_jit.py:506-584) ---------------------------------------------------
       const unsigned bit = (l < nF) ? 1u : 2u;
       for (int t = st.t0[l] + warp; t < st.t1[l]; t += S4_WARPS) {
-        const int64_t r0 = __ldg(raw.tof_indptr + t), r1 = __ldg(raw.tof_indptr + t + 1);
-        long long e = 0;
-        if (lane < 2) e = adb_row_lower_bound(raw.push, r0, r1, lane == 0 ? p_lo : p_hi);
-        const long long e1 = __shfl_sync(FULL, e, 1), e0 = __shfl_sync(FULL, e, 0);
+        const int ridx = st.rowoff[l] + (t - st.t0[l]);
+        long long e0, e1;
+        if (ridx < S4_EVR_CAP) { e0 = st.evr[ridx].x; e1 = st.evr[ridx].y; }
+        else {
+          const int64_t r0 = __ldg(raw.tof_indptr + t), r1 = __ldg(raw.tof_indptr + t + 1);
+          long long e = 0;
+          if (lane < 2) e = adb_row_lower_bound(raw.push, r0, r1, lane == 0 ? p_lo : p_hi);
+          e1 = __shfl_sync(FULL, e, 1); e0 = __shfl_sync(FULL, e, 0);
+        }
         for (long long k = e0 + lane; k < e1; k += 32) {
           const uint32_t push = __ldg(raw.push + k);
           const uint32_t frame = push / smi, scan = push - frame * smi;
@@ -345,8 +381,9 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
         if (lane == 0) rowcnt[r] = any ? 1 : 0;
       }
       __syncthreads();
-      if (warp == 0) {  // ascending list of the non-empty tile rows + rank of every row
-        int M = 0;
+      int M = 0;
+      {  // ascending list of the non-empty tile rows + rank of every row; every warp writes the same values, so no
+         // CTA barrier is needed before the warp reads them back
         for (int base = 0; base < S; base += 32) {
           const int r = base + lane;
           const bool ne = r < S && rowcnt[r] != 0;
@@ -355,9 +392,8 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
           if (r < S) rowrank[r] = (unsigned short)(M + __popc(b & ((2u << lane) - 1u)));
           M += __popc(b);
         }
-        if (lane == 0) st.n_nzrows = M;
+        __syncwarp();
       }
-      __syncthreads();
       // ---- sparse circular smoothing + log-sum (fft.py:141-212, selection.py:206-226) ----------------
       // out[i][j] = sum_a sum_b k[a][b] x[(i + sh - a) mod S][(j + sw - b) mod C], a then b ascending: for one output
       // cell the input rows are visited downwards (circularly) from r0 = (i + sh) mod S, only the non-empty ones, and
@@ -365,8 +401,83 @@ __global__ void __launch_bounds__(S4_THREADS) adb_select4d_kernel(const __grid_c
       // the highest (b = 0) down.
       float* lacc = (l < nF) ? lf : lp;
       const int segs = (C + 31) >> 5;
-      const int M = st.n_nzrows;
-      if (M > 0)
+      if (M >= S4_BLOCKED_MIN_ROWS && kw <= 32) {
+        // Dense blobs (an eluting peptide covers ~17 scans x 9 cycles): one lane owns an output column of S4_RB
+        // consecutive output rows, so every tap (row r, column t) is loaded once and feeds up to S4_RB accumulators with
+        // k[a_q][b], a_q = (r0_q - r) mod S.  Each accumulator must still see its taps in (a, b) ascending order: input
+        // rows are swept downwards twice — first the rows at or below r0_q (a = r0_q - r), then the circularly wrapped
+        // rows above it (a = r0_q - r + S) — and inside a row the taps from the highest set bit (b = 0) down.
+        const int n_blk = (S + S4_RB - 1) / S4_RB;
+        for (int item = warp; item < n_blk * segs; item += S4_WARPS) {  // segment-major: the warps share a blob's rows evenly
+          const int seg = item / n_blk, blk = item - seg * n_blk;
+          const int i0 = blk * S4_RB;
+          int r0q[S4_RB], r0_min = 1 << 30, r0_max = -1;
+#pragma unroll
+          for (int q = 0; q < S4_RB; q++) {
+            int r0 = i0 + q + sh;
+            if (r0 >= S) r0 -= S;
+            const bool live = i0 + q < S;
+            r0q[q] = live ? r0 : -(1 << 20);  // dead rows never match: a < 0 in sweep 0, a < 0 in sweep 1
+            if (live) { r0_min = min(r0_min, r0); r0_max = max(r0_max, r0); }
+          }
+          // list ranges of the two sweeps: rows in [r0_min - kh + 1, r0_max] and rows > r0_min + S - kh
+          const int k_top0 = (int)rowrank[r0_max] - 1;
+          const int r_low0 = r0_min - kh + 1, r_low1 = r0_min + S - kh;
+          const bool has0 = k_top0 >= 0 && (int)nzrows[k_top0] >= r_low0;
+          const bool has1 = (int)nzrows[M - 1] > r_low1;
+          if (!has0 && !has1) continue;  // warp-uniform
+          {
+            const int j = min(seg * 32 + lane, C - 1);
+            double acc[S4_RB];
+#pragma unroll
+            for (int q = 0; q < S4_RB; q++) acc[q] = 0.0;
+            uint32_t anyw = 0u;
+#pragma unroll 1
+            for (int sweep = 0; sweep < 2; sweep++) {
+              const int add = sweep ? S : 0;
+              const int k_top = sweep ? M - 1 : k_top0;
+              const int r_low = sweep ? r_low1 + 1 : r_low0;
+#pragma unroll 1
+              for (int k = k_top; k >= 0; k--) {
+                const int r = nzrows[k];
+                if (r < r_low) break;  // warp-uniform
+                const double* kq[S4_RB];
+                bool anyq = false;
+#pragma unroll
+                for (int q = 0; q < S4_RB; q++) {
+                  const int a = r0q[q] - r + add;  // sweep 0: r <= r0_q, sweep 1: r > r0_q (then a >= S - ... < kh only if wrapped)
+                  const bool ok = (unsigned)a < (unsigned)kh;
+                  kq[q] = ok ? s_kern + a * kw + (kw - 1) : nullptr;
+                  anyq |= ok;
+                }
+                if (!anyq) continue;  // warp-uniform
+                const uint32_t* mrow = rmask + r * mw_cap + (j >> 5);
+                uint32_t w = __funnelshift_r(mrow[0], mrow[1], j & 31) & kw_mask;  // taps t = j .. j + kw - 1
+                anyw |= w;
+                const uint32_t* trow = tile + r * cx_cap + j;
+                while (w) {  // b ascending = t descending
+                  const int hb = 31 - __clz(w);
+                  w ^= 1u << hb;
+                  const double v = (double)__uint_as_float(trow[hb]);
+#pragma unroll
+                  for (int q = 0; q < S4_RB; q++)
+                    if (kq[q]) acc[q] = fma(kq[q][-hb], v, acc[q]);
+                }
+              }
+            }
+            if (anyw && seg * 32 + lane < C) {
+#pragma unroll
+              for (int q = 0; q < S4_RB; q++) {
+                const float sm = (float)acc[q];
+                if (i0 + q < S && sm != 0.f) {
+                  const float lg = (float)log((double)sm + 1.0);
+                  lacc[(i0 + q) * C + j] = __fadd_rn(lacc[(i0 + q) * C + j], lg);
+                }
+              }
+            }
+          }
+        }
+      } else if (M > 0)
         for (int i = warp; i < S; i += S4_WARPS) {
           int r0 = i + sh;
           if (r0 >= S) r0 -= S;
