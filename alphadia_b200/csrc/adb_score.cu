@@ -273,8 +273,8 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
   const int C = (int)C64;
 
   // ---- scratch carve-up ----------------------------------------------------------------------
-  const long long nFC = (long long)F * nobs * C;
-  long long need = 2 * nFC + 1LL * F * C + 2LL * nI * C + 2LL * nobs * C + C + 2 /*align*/ + 4LL * nobs * C + 4LL * C;
+  const int nFC = F * nobs * C;  // <= 32 * 8 * 4096: 32-bit index arithmetic in the hot loops
+  long long need = 2LL * nFC + 1LL * F * C + 2LL * nI * C + 2LL * nobs * C + C + 2 /*align*/ + 4LL * nobs * C + 4LL * C;
   if (!cfg.experimental_xic) need += (long long)F * F;
   float* scratch = smem_scratch;
   if (need > SMEM_FLOATS_PER_TILE) {
@@ -301,15 +301,14 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
   tile.sync();  // the staging area in the scratch is dead from here on
 
   // ---- candidate.py:216-223 fragment cube -------------------------------------------------------
-  _Pragma("unroll 1") for (long long t = lane; t < nFC; t += TILE) {
-    int k = (int)(t % F);
-    long long oc = t / F;
-    int c = (int)(oc % C), o = (int)(oc / C);
+  _Pragma("unroll 1") for (int t = lane; t < nFC; t += TILE) {
+    const int k = t % F, oc = t / F;
+    const int c = oc % C, o = oc / C;
     int64_t scan = (int64_t)sm.pos[o] + (cs + c) * L;
     float ai = 0.f, am = 0.f;
     float prev_hi = (k > 0) ? sm.hi[k - 1] : -1.0f;
     extract_cell(raw, scan, sm.lo[k], sm.hi[k], prev_hi, ai, am);
-    long long cell = ((long long)k * nobs + o) * C + c;
+    const int cell = (k * nobs + o) * C + c;
     dfi[cell] = ai;
     dfm[cell] = am;
   }
@@ -349,8 +348,8 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
     sm.qmask[lane] = (float)(s / (double)nI);
   }
   tile.sync();
-  _Pragma("unroll 1") for (long long t = lane; t < nFC; t += TILE) {  // candidate.py:290
-    int o = (int)((t / C) % nobs);
+  _Pragma("unroll 1") for (int t = lane; t < nFC; t += TILE) {  // candidate.py:290
+    const int o = (t / C) % nobs;
     dfi[t] = __fmul_rn(dfi[t], sm.qmask[o]);
   }
   _Pragma("unroll 1") for (int t = lane; t < nobs * C; t += TILE) {  // quadrupole.py:304-324 template
@@ -379,7 +378,7 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
     float t_o = 0.f;
     _Pragma("unroll 1") for (int o = 0; o < nobs; o++) {
       float t_c = 0.f;
-      const float* r = dfi + ((long long)lane * nobs + o) * C;
+      const float* r = dfi + (lane * nobs + o) * C;
       _Pragma("unroll 1") for (int c = 0; c < C; c++) t_c = __fadd_rn(t_c, r[c]);
       t_o = __fadd_rn(t_o, twice(t_c));
     }
@@ -521,8 +520,8 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
   const int wn = max(w1 - w0, 0);
   bool anyh = false;
   if (act) {
-    float* b = bp + (long long)lane * C;
-    const float* d = dfi + (long long)f * nobs * C;
+    float* b = bp + lane * C;
+    const float* d = dfi + f * nobs * C;
     if (quant_all) {
       _Pragma("unroll 1") for (int c = 0; c < C; c++) { float t = 0.f; _Pragma("unroll 1") for (int o = 0; o < nobs; o++) t = __fadd_rn(t, twice(d[o * C + c])); b[c] = t; }
     } else {
@@ -567,7 +566,7 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
     // > 0 exactly when the (f, o) cell row has signal (all weights are positive), i.e. when its f32 sum is > 0.
     float fn2 = 0.f, dot = 0.f, wsum = 0.f;
     unsigned obs_mask = 0u;
-    const float* dm = dfm + (long long)f * nobs * C;
+    const float* dm = dfm + f * nobs * C;
     _Pragma("unroll 1") for (int o = 0; o < nobs; o++) {
       const float* r = d + o * C;
       float tc = 0.f;
@@ -599,7 +598,7 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
         double wv = (double)(((obs_mask >> o) & 1u) ? sm.oi[o] : 0.0f) / ((double)wsum + 1e-20);
         if (wv > 0) {
           double h_o, mz_o;
-          weighted_center_mean_pair(d + o * C, dm + o * C, wtab + (long long)o * 2 * C, C, h_o, mz_o);
+          weighted_center_mean_pair(d + o * C, dm + o * C, wtab + o * 2 * C, C, h_o, mz_o);
           double lw = wv / wtot;
           a = __dadd_rn(a, __dmul_rn(mz_o, lw));
           bsum = __dadd_rn(bsum, __dmul_rn(h_o, lw));
@@ -683,14 +682,14 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
   // fragments_frame_profile accessor: the best observation's rows were enveloped in place when
   // quant_all is off (fragment_features.py:248-250, view semantics)
   auto ffp = [&](int w, int fidx, int o, int c) -> float {
-    if (!quant_all && o == best_obs) return bp[(long long)w * C + c];
-    return twice(dfi[((long long)fidx * nobs + o) * C + c]);
+    if (!quant_all && o == best_obs) return bp[w * C + c];
+    return twice(dfi[(fidx * nobs + o) * C + c]);
   };
   // fragments_frame_profile.sum(axis=1)
   auto isl = [&](int w, int fidx, int c) -> float {
     if (nobs == 1)  // single observation: 0 + x == x exactly, no call
-      return quant_all ? twice(dfi[(long long)fidx * C + c]) : bp[(long long)w * C + c];
-    return frame_profile_obs_sum(dfi + (long long)fidx * nobs * C, bp + (long long)w * C, nobs, C, c, quant_all ? -1 : best_obs);
+      return quant_all ? twice(dfi[fidx * C + c]) : bp[w * C + c];
+    return frame_profile_obs_sum(dfi + fidx * nobs * C, bp + w * C, nobs, C, c, quant_all ? -1 : best_obs);
   };
   if (cfg.experimental_xic) {
     int a0 = center - 1, a1 = center + 2;  // scoring_utils.py:100-110 python slice semantics
@@ -701,16 +700,16 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
       float t = 0.f;
       _Pragma("unroll 1") for (int c = a0; c < a1; c++) t = __fadd_rn(t, isl(lane, f, c));
       double cint = (double)t / (double)wnn;
-      float* nr = nrm + (long long)lane * C;
+      float* nr = nrm + lane * C;
       _Pragma("unroll 1") for (int c = 0; c < C; c++) nr[c] = (cint > 0) ? (float)((double)isl(lane, f, c) / cint) : 0.f;
     }
     tile.sync();
     _Pragma("unroll 1") for (int c = lane; c < C; c += TILE) {  // median over fragments (scoring_utils.py:127-152)
       float vlo = 0.f, vhi = 0.f;
       _Pragma("unroll 1") for (int w = 0; w < Fv; w++) {
-        float v = nrm[(long long)w * C + c];
+        float v = nrm[w * C + c];
         int rk = 0;
-        _Pragma("unroll 1") for (int u = 0; u < Fv; u++) { float vu = nrm[(long long)u * C + c]; rk += (vu < v) || (vu == v && u < w); }
+        _Pragma("unroll 1") for (int u = 0; u < Fv; u++) { float vu = nrm[u * C + c]; rk += (vu < v) || (vu == v && u < w); }
         if (rk == (Fv - 1) / 2) vlo = v;
         if (rk == Fv / 2) vhi = v;
       }
@@ -756,15 +755,15 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
         _Pragma("unroll 1") for (int c = 0; c < C; c++) s = __fadd_rn(s, ffp(lane, f, o, c));
         float mean = __fdiv_rn(s, (float)C);
         float ss = 0.f;
-        float* cen = nrm + (long long)lane * C;
+        float* cen = nrm + lane * C;
         _Pragma("unroll 1") for (int c = 0; c < C; c++) { float cv = __fsub_rn(ffp(lane, f, o, c), mean); cen[c] = cv; ss = __fadd_rn(ss, __fmul_rn(cv, cv)); }
         sm.rfw[lane] = sqrtf(__fdiv_rn(ss, (float)C));
       }
       tile.sync();
       _Pragma("unroll 1") for (int t = lane; t < Fv * Fv; t += TILE) {
         int a = t / Fv, b = t % Fv;
-        const float* ca = nrm + (long long)a * C;
-        const float* cb = nrm + (long long)b * C;
+        const float* ca = nrm + a * C;
+        const float* cb = nrm + b * C;
         float dot = 0.f;
         _Pragma("unroll 1") for (int c = 0; c < C; c++) dot = __fadd_rn(dot, __fmul_rn(ca[c], cb[c]));
         float cov = __fdiv_rn(dot, (float)C);

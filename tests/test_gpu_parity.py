@@ -655,3 +655,57 @@ def test_full_size_config2_properties(engine, oracle_lib):
     got_s = {k: v[pick_c] for k, v in got.items()}
     assert_scores_close(got_s, ref_s, what="config2 subsample")
     dlib.close(); draw.close()
+
+
+def test_mid_size_4d_properties(engine, oracle_lib):
+    """A timsTOF-shaped run with 3 000 precursors (about 12x the golden case): determinism, shard invariance, structural
+    invariants on the whole candidate table, oracle parity on a random subsample (selection bit-exact, scores <= 1e-4)."""
+    from alphadia_b200.library import assemble_library_arrays
+    from alphadia_b200.synthetic import make_config_4d
+
+    raw, pdf, fdf, p = make_config_4d("parity_4d", n_precursors=3000, seed=77)
+    lib = assemble_library_arrays(pdf, fdf, "rt_library", "mobility_library", "mz_library", "mz_library")
+    P = len(lib["precursor_idx"])
+    cfg = _sel_cfg_4d(p)
+    kernel = H.default_kernel(raw)
+    draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+    full = engine.select_candidates(draw, dlib, cfg, kernel)
+    again = engine.select_candidates(draw, dlib, cfg, kernel)
+    for c in INT_COLS + ["score"]:
+        assert np.array_equal(full[c], again[c]), f"4-D selection is not deterministic in {c}"
+    m = full["score"] > 0
+    assert m.sum() > P
+    s0, sc_, s1 = (full[c][m].astype(np.int64) for c in ("scan_start", "scan_center", "scan_stop"))
+    f0, fc, f1 = (full[c][m].astype(np.int64) for c in ("frame_start", "frame_center", "frame_stop"))
+    assert (s0 <= sc_).all() and (sc_ < s1).all() and (s1 <= raw.scan_max_index).all()
+    assert (f0 <= fc).all() and (fc < f1).all() and (f1 <= raw.frame_max_index).all()
+    assert ((s1 - s0) <= 2 * 20 - 1).all()  # max_size_mobility = 20
+    prec_keys = ("precursor_idx", "frag_start_idx", "frag_stop_idx", "charge", "rt", "mobility", "mz", "isotopes")
+    half = P // 2
+    parts = []
+    for sl in (slice(0, half), slice(half, P)):
+        sub = {k: (np.ascontiguousarray(v[sl]) if k in prec_keys else v) for k, v in lib.items()}
+        dsub = engine.DeviceLibrary(sub, device=0)
+        parts.append(engine.select_candidates(draw, dsub, cfg, kernel))
+        dsub.close()
+    for c in INT_COLS + ["score"]:
+        assert np.array_equal(np.concatenate([parts[0][c], parts[1][c]]), full[c]), f"4-D shard invariance broken in {c}"
+    rng = np.random.default_rng(5)
+    pick = np.sort(rng.choice(P, size=250, replace=False))
+    sub = {k: (np.ascontiguousarray(v[pick]) if k in prec_keys else v) for k, v in lib.items()}
+    ref = oracle_lib.select_candidates_4d(raw, sub, cfg, kernel)
+    idx = (pick[:, None] * 3 + np.arange(3)[None, :]).ravel()
+    for c in INT_COLS + ["score"]:
+        assert np.array_equal(full[c][idx], ref[c]), f"4-D oracle parity (subsample) broken in {c}"
+    n = engine.select_candidates_resident(draw, dlib, cfg, kernel)
+    table = engine.fetch_candidate_table(draw, n)
+    from alphadia_b200 import _abi
+    scfg = H.scoring_config().to_struct()
+    got = engine.score_candidates(draw, dlib, scfg, _abi.candidates_in_from_table(table, n))
+    got2 = engine.score_candidates(draw, dlib, scfg, _abi.candidates_in_from_table(table, n))
+    assert np.array_equal(got["features"], got2["features"], equal_nan=True)
+    pick_c = np.sort(rng.choice(n, size=min(n, 1500), replace=False))
+    sub_t = {k: np.ascontiguousarray(v[:n][pick_c]) for k, v in table.items()}
+    ref_s = oracle_lib.score_candidates_4d(raw, lib, scfg, _abi.candidates_in_from_table(sub_t, len(pick_c)))
+    assert_scores_close({k: v[pick_c] for k, v in got.items()}, ref_s, what="4-D mid-size subsample")
+    dlib.close(); draw.close()
