@@ -90,7 +90,80 @@ def merge_missing_columns(left_df, right_df, right_columns, on=None, how="left")
         raise ValueError(f"Columns {on} must be present in right_df")
     if how not in ["left", "right", "inner", "outer"]:
         raise ValueError("Parameter how must be one of left, right, inner, outer")
+    fast = _merge_by_sorted_key(left_df, right_df, on, missing_from_left) if how == "left" else None
+    if fast is not None:
+        return fast
     return left_df.merge(right_df[on + missing_from_left], on=on, how=how)
+
+
+def _composite_key(df, on):
+    """int64 key for one integer column or an (id, small non-negative integer) pair such as (precursor_idx, rank)."""
+    cols = [df[c].values for c in on]
+    if not all(np.issubdtype(c.dtype, np.integer) for c in cols):
+        return None
+    if len(cols) == 1:
+        return cols[0].astype(np.int64, copy=False)
+    if len(cols) == 2:
+        a, b = cols[0].astype(np.int64, copy=False), cols[1].astype(np.int64, copy=False)
+        if len(a) and (a.min() < 0 or a.max() >= (1 << 46) or b.min() < 0 or b.max() >= (1 << 16)):
+            return None
+        return (a << 16) | b
+    return None
+
+
+def _merge_by_sorted_key(left_df, right_df, on, columns):
+    """Left merge as a gather: valid when the right keys are unique and every left key occurs in the right frame (the
+    result of ``DataFrame.merge(how="left")`` is then the left frame, in order, plus the gathered columns).  The pandas
+    hash merge costs seconds at millions of candidates; returns None when the preconditions do not hold."""
+    if len(left_df) == 0 or len(right_df) == 0:
+        return None
+    lk, rk = _composite_key(left_df, on), _composite_key(right_df, on)
+    if lk is None or rk is None:
+        return None
+    order = None
+    if len(rk) > 1 and not np.all(rk[1:] > rk[:-1]):
+        order = np.argsort(rk, kind="stable")
+        rk = rk[order]
+        if not np.all(rk[1:] > rk[:-1]):
+            return None  # duplicate keys on the right: a real merge multiplies rows
+    pos = np.searchsorted(rk, lk)
+    pos = np.minimum(pos, len(rk) - 1)
+    if not np.array_equal(rk[pos], lk):
+        return None  # unmatched left keys would become NaN rows
+    if order is not None:
+        pos = order[pos]
+    out = left_df.reset_index(drop=True)
+    for c in columns:
+        src = right_df[c]
+        if isinstance(src.dtype, np.dtype) and src.dtype != object:
+            out[c] = src.values[pos]
+        else:  # object / extension columns: keep the dtype (pandas would re-infer `str` from an object array)
+            out[c] = pd.Series(src.values[pos], index=out.index, dtype=src.dtype)
+    return out
+
+
+def count_residues(sequences, residues) -> list:
+    """``Series.str.count(r)`` for single-character patterns (scoring.py:461-463 n_K / n_R / n_P) without a Python call
+    per row: the distinct sequences are counted once as fixed-width code points and the counts are gathered.
+    Returns one int64 array per residue (a single array when ``residues`` is a single character)."""
+    single = isinstance(residues, str) and len(residues) == 1
+    res = [residues] if single else list(residues)
+    values = np.asarray(sequences, dtype=object)
+    if len(values) == 0:
+        out = [np.zeros(0, dtype=np.int64) for _ in res]
+        return out[0] if single else out
+    codes, uniques = pd.factorize(values, use_na_sentinel=True)
+    if (codes < 0).any() or not all(isinstance(u, str) for u in uniques[: min(len(uniques), 64)]):
+        out = [pd.Series(values).str.count(r).values for r in res]  # missing or non-string entries: pandas semantics
+        return out[0] if single else out
+    fixed = np.asarray(uniques, dtype=str)
+    width = fixed.dtype.itemsize // 4
+    if width == 0:
+        out = [np.zeros(len(values), dtype=np.int64) for _ in res]
+        return out[0] if single else out
+    points = fixed.view(np.uint32).reshape(len(fixed), width)
+    out = [(points == ord(r)).sum(axis=1).astype(np.int64)[codes] for r in res]
+    return out[0] if single else out
 
 
 def calculate_score_groups(input_df: pd.DataFrame, group_channels: bool = False) -> pd.DataFrame:
@@ -276,9 +349,8 @@ class CandidateScoring:
             self.precursor_mz_column, precursor_df_columns,
         )
         candidates_psm_df["delta_rt"] = candidates_psm_df["rt_observed"] - candidates_psm_df[self.rt_column]
-        candidates_psm_df["n_K"] = candidates_psm_df["sequence"].str.count("K")
-        candidates_psm_df["n_R"] = candidates_psm_df["sequence"].str.count("R")
-        candidates_psm_df["n_P"] = candidates_psm_df["sequence"].str.count("P")
+        n_k, n_r, n_p = count_residues(candidates_psm_df["sequence"].values, ["K", "R", "P"])
+        candidates_psm_df["n_K"], candidates_psm_df["n_R"], candidates_psm_df["n_P"] = n_k, n_r, n_p
         return candidates_psm_df
 
     @staticmethod
@@ -300,14 +372,12 @@ class CandidateScoring:
         return merge_missing_columns(df, precursors_flat_df, precursor_df_columns, on=["precursor_idx"], how="left")
 
     def collect_fragments(self, candidates_df, psm) -> pd.DataFrame:
-        mask = psm["fragment_mz_library"].reshape(-1) > 0  # output.py:72-90
+        rows = np.flatnonzero(psm["fragment_mz_library"].reshape(-1) > 0)  # output.py:72-90, as one gather index
         top_k = psm["fragment_mz_library"].shape[1]
-        data = {
-            "precursor_idx": np.repeat(psm["precursor_idx"], top_k)[mask],
-            "rank": np.repeat(psm["rank"], top_k)[mask],
-        }
+        cand = rows // top_k
+        data = {"precursor_idx": psm["precursor_idx"][cand], "rank": psm["rank"][cand]}
         for col in FRAGMENT_COLUMNS[2:]:
-            data[col] = psm["fragment_" + col].reshape(-1)[mask]
+            data[col] = psm["fragment_" + col].reshape(-1)[rows]
         df = pd.DataFrame(data)
         return merge_missing_columns(df, self.precursors_flat_df, ["elution_group_idx", "decoy"],
                                      on=["precursor_idx"], how="left")

@@ -57,8 +57,10 @@ class Schema:
     @staticmethod
     def _warn_on_critical_values(df: pd.DataFrame) -> None:
         for col in df.columns:
-            if np.issubdtype(df[col].dtype, np.floating):
+            if isinstance(df[col].dtype, np.dtype) and np.issubdtype(df[col].dtype, np.floating):  # extension dtypes (str) are skipped
                 v = df[col].values
+                if np.isfinite(v).all():  # the common case costs one pass
+                    continue
                 n_nan = int(np.isnan(v).sum())
                 n_inf = int(np.isinf(v).sum())
                 if n_nan:

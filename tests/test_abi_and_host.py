@@ -177,3 +177,51 @@ def test_sharded_selection_equals_unsharded(oracle_lib):
         parts.append(oracle_lib.select_candidates(raw, sl, cfg, kernel))
     for c in full:
         assert np.array_equal(full[c], np.concatenate([q[c] for q in parts])), c
+
+
+def test_fast_merge_equals_pandas_merge():
+    """merge_missing_columns' gather path must return exactly what DataFrame.merge(how='left') returns."""
+    import pandas as pd
+
+    from alphadia_b200.scoring import _merge_by_sorted_key, merge_missing_columns
+
+    rng = np.random.default_rng(0)
+    right = pd.DataFrame({"precursor_idx": rng.permutation(5000).astype(np.uint32), "a": rng.normal(size=5000).astype(np.float32),
+                          "b": rng.integers(0, 9, 5000).astype(np.uint8), "s": np.array([f"PEP{k}K" for k in range(5000)], dtype=object)})
+    left = pd.DataFrame({"precursor_idx": rng.integers(0, 5000, 20000).astype(np.uint32), "x": rng.normal(size=20000)})
+    left.index = left.index[::-1]  # a non-default index must not leak into the result
+    fast = merge_missing_columns(left, right, ["a", "b", "s", "x"], on="precursor_idx")
+    slow = left.merge(right[["precursor_idx", "a", "b", "s"]], on=["precursor_idx"], how="left")
+    pd.testing.assert_frame_equal(fast, slow)
+    # sorted right, two keys
+    cand = pd.DataFrame({"precursor_idx": np.repeat(np.arange(3000, dtype=np.uint32), 3), "rank": np.tile(np.arange(3, dtype=np.uint8), 3000)})
+    cand["score"] = rng.normal(size=len(cand)).astype(np.float32)
+    psm = cand.sample(frac=0.7, random_state=1)[["precursor_idx", "rank"]].reset_index(drop=True)
+    fast = merge_missing_columns(psm, cand, ["score"], on=["precursor_idx", "rank"])
+    slow = psm.merge(cand[["precursor_idx", "rank", "score"]], on=["precursor_idx", "rank"], how="left")
+    pd.testing.assert_frame_equal(fast, slow)
+    # preconditions that must fall back to pandas: unmatched keys, duplicate right keys
+    assert _merge_by_sorted_key(pd.DataFrame({"precursor_idx": np.array([7000], np.uint32)}), right, ["precursor_idx"], ["a"]) is None
+    dup = pd.concat([right, right.iloc[:1]])
+    assert _merge_by_sorted_key(left, dup, ["precursor_idx"], ["a"]) is None
+    out = merge_missing_columns(pd.DataFrame({"precursor_idx": np.array([1, 7000], np.uint32)}), right, ["a"], on="precursor_idx")
+    assert np.isnan(out["a"].values[1])
+
+
+def test_count_residues_equals_str_count():
+    import pandas as pd
+
+    from alphadia_b200.scoring import count_residues
+
+    rng = np.random.default_rng(1)
+    alphabet = np.array(list("ACDEFGHIKLMNPQRSTVWY"))
+    seqs = np.array(["".join(rng.choice(alphabet, size=rng.integers(0, 40))) for _ in range(3000)], dtype=object)
+    col = seqs[rng.integers(0, len(seqs), 20000)]
+    for r in "KRP":
+        assert np.array_equal(count_residues(col, r), pd.Series(col).str.count(r).values)
+    for got, r in zip(count_residues(col, ["K", "R", "P"]), "KRP"):
+        assert np.array_equal(got, pd.Series(col).str.count(r).values)
+    with_nan = col.copy()
+    with_nan[5] = np.nan
+    a, b = count_residues(with_nan, "K"), pd.Series(with_nan).str.count("K").values
+    assert np.array_equal(np.isnan(a.astype(float)), np.isnan(b.astype(float))) and np.array_equal(a[:5], b[:5])
