@@ -709,3 +709,38 @@ def test_mid_size_4d_properties(engine, oracle_lib):
     ref_s = oracle_lib.score_candidates_4d(raw, lib, scfg, _abi.candidates_in_from_table(sub_t, len(pick_c)))
     assert_scores_close({k: v[pick_c] for k, v in got.items()}, ref_s, what="4-D mid-size subsample")
     dlib.close(); draw.close()
+
+
+def test_4d_repeated_observation_ids(engine, oracle_lib):
+    """Two frames of the cycle carry the same observation id (e.g. two MS1 frames per cycle): events of one tof row can then
+    fall into the same cube cell, the scoring kernel must process each query sequentially (DevRaw4::obs_unique_per_scan = 0)."""
+    from types import SimpleNamespace
+
+    raw0, pdf, fdf, lib, p = H.workload("parity_4d")
+    fr, sc = raw0.cycle.shape[1], raw0.cycle.shape[2]
+    cycle = raw0.cycle.copy()
+    cycle[0, 2, :, :] = -1.0                       # frame 2 of the cycle becomes a second MS1 frame ...
+    dpc = raw0.dia_precursor_cycle.copy()
+    dpc[2 * sc:3 * sc] = 0                         # ... with the observation id of the first one
+    dpc[3 * sc:4 * sc] = 1                         # and the last MS2 frame reuses id 1: repeated ids among MS2 frames as well
+    cycle[0, 3, :, :] = cycle[0, 1, :, :]
+    raw = SimpleNamespace(cycle=cycle, rt_values=raw0.rt_values, mobility_values=raw0.mobility_values, mz_values=raw0.mz_values,
+                          tof_indptr=raw0.tof_indptr, push_indices=raw0.push_indices, intensity_values=raw0.intensity_values,
+                          dia_precursor_cycle=dpc, zeroth_frame=raw0.zeroth_frame, scan_max_index=raw0.scan_max_index,
+                          frame_max_index=raw0.frame_max_index, precursor_cycle_max_index=raw0.precursor_cycle_max_index,
+                          has_mobility=True, is_4d=True)
+    cfg = _sel_cfg_4d(p)
+    kernel = H.default_kernel(raw0)
+    draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+    got = engine.select_candidates(draw, dlib, cfg, kernel)
+    ref = oracle_lib.select_candidates_4d(raw, lib, cfg, kernel)
+    assert_candidates_equal(got, ref)
+    m = got["score"] > 0
+    assert m.sum() > 50
+    cin, keep = H.candidates_in_from_arrays(lib, {c: got[c][m] for c in INT_COLS})
+    scfg = H.scoring_config().to_struct()
+    s_got = engine.score_candidates(draw, dlib, scfg, cin)
+    s_ref = oracle_lib.score_candidates_4d(raw, lib, scfg, cin)
+    assert s_ref["valid"].sum() > 20
+    assert_scores_close(s_got, s_ref, what="repeated observation ids")
+    dlib.close(); draw.close()
