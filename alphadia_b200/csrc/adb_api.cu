@@ -11,6 +11,10 @@
 
 #include "adb_common.cuh"
 
+#ifndef ADB_SCORE_BLOCKS
+#define ADB_SCORE_BLOCKS 4  // row blocks of a scoring call whose D2H overlaps the next block's kernel (<= 7)
+#endif
+
 namespace {
 
 thread_local std::string g_error;
@@ -703,7 +707,7 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   // processing order: (quad window of the precursor, frame_start) so that co-resident tiles read the same
   // spectra; results do not depend on it (disjoint output rows)
   int32_t* d_order = nullptr;
-  const int n_chunks = (host_out && n >= 200000) ? 4 : 1;
+  const int n_chunks = (host_out && n >= 200000) ? ADB_SCORE_BLOCKS : 1;
   const int64_t chunk_len = std::max<int64_t>((n + n_chunks - 1) / n_chunks, 1);
   if (n > 1 && n < 2000000000LL) {
     if (raw->order_keys.reserve(sizeof(uint64_t) * 2 * (size_t)n)) return 1;

@@ -125,14 +125,17 @@ __device__ __noinline__ void weighted_center_mean_pair(const float* r, const flo
                                                        double& h, double& mz) {
   double v1 = 0, w1 = 0, v2 = 0, w2 = 0;
   bool any1 = false, any2 = false;
+  // branch-free: a cell that is not > 0 adds +0.0, which leaves the (non-negative) running sums bit-identical
 #pragma unroll 1
   for (int s = 0; s < 2; s++)
-#pragma unroll 1
+#pragma unroll 4
     for (int c = 0; c < C; c++) {
-      double wgt = wt[s * C + c];
-      float a = r[c], b = rm[c];
-      if (a > 0.f) { any1 = true; v1 = __dadd_rn(v1, __dmul_rn((double)a, wgt)); w1 = __dadd_rn(w1, wgt); }
-      if (b > 0.f) { any2 = true; v2 = __dadd_rn(v2, __dmul_rn((double)b, wgt)); w2 = __dadd_rn(w2, wgt); }
+      const double wgt = wt[s * C + c];
+      const float a = r[c], b = rm[c];
+      const bool pa = a > 0.f, pb = b > 0.f;
+      any1 |= pa; any2 |= pb;
+      v1 = __dadd_rn(v1, pa ? __dmul_rn((double)a, wgt) : 0.0); w1 = __dadd_rn(w1, pa ? wgt : 0.0);
+      v2 = __dadd_rn(v2, pb ? __dmul_rn((double)b, wgt) : 0.0); w2 = __dadd_rn(w2, pb ? wgt : 0.0);
     }
   h = (any1 && w1 > 0) ? v1 / w1 : 0.0;
   mz = (any2 && w2 > 0) ? v2 / w2 : 0.0;

@@ -554,7 +554,9 @@ __global__ void adb_select_smooth_kernel(const __grid_constant__ SelectParams P)
 // the XIC cells are zero; most smoothed cells have no tap at all and cost one funnel shift.  log(x + 1) is added to the
 // per-cell f32 layer sums as the rows come (layer order, selection.py:206-226); then the warp normalises, picks peaks
 // and writes the candidates (slot_finish).
+#ifndef SEL_FUSED_THREADS
 #define SEL_FUSED_THREADS 256
+#endif
 #define SEL_FUSED_WARPS (SEL_FUSED_THREADS / 32)
 #define SEL_FUSED_MAX_C 1024
 
