@@ -27,7 +27,7 @@ def build(force: bool = False) -> str:
     if not force and os.path.exists(SO_PATH):
         if os.path.getmtime(SO_PATH) >= max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
             return SO_PATH
-    cmd = ["gcc", "-O2", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC", "-Wall",
+    cmd = ["gcc", "-O2", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC", "-Wall", "-Wno-maybe-uninitialized",
            "-o", SO_PATH, SRC, "-lm"]
     subprocess.check_call(cmd)
     return SO_PATH

@@ -6,7 +6,7 @@
  * never links, imports or calls it and fails loudly when its CUDA extension is missing.
  *
  * Parity status: PINNED against the live reference (numba path of /root/reference run in the
- * build container through oracle/refshim.py) by the golden vectors in tests/golden/*.npz
+ * build container through oracle/refshim.py) by the golden vectors in tests/golden (npz files)
  * (tests/test_oracle_golden.py).  The one arithmetic dependency that is not available
  * (rocket-fft 0.2.5 / pocketfft behind alphadia/search/selection/fft.py) is replaced on BOTH
  * sides by its mathematical definition: direct circular same-size convolution with fp64 FMA
@@ -17,7 +17,7 @@
  * (float32 array (+,-,*,/) int scalar -> float32; float64 scalar -> float64; float32 scalar /
  * int64 scalar -> float64; np.sum / np.mean accumulate sequentially in the array dtype).
  *
- * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp -shared -fPIC (oracle/build.py).
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp -shared -fPIC (oracle/__init__.py build()).
  */
 #include <math.h>
 #include <stdint.h>
