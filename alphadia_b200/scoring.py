@@ -111,6 +111,24 @@ def _composite_key(df, on):
     return None
 
 
+def _positions_in_sorted_unique(sorted_keys: np.ndarray, keys: np.ndarray):
+    """Index of every key in a strictly ascending key array, or None when a key is missing.  Consecutive keys (the usual
+    ``precursor_idx = 0 .. P-1``) are resolved by subtraction instead of a binary search per row."""
+    n = len(sorted_keys)
+    if n == 0:
+        return None if len(keys) else np.zeros(0, dtype=np.int64)
+    first, last = int(sorted_keys[0]), int(sorted_keys[-1])
+    if last - first == n - 1 and (n < 2 or bool(np.all(sorted_keys[1:] > sorted_keys[:-1]))):  # consecutive values
+        pos = keys.astype(np.int64, copy=False) - first
+        if len(pos) and (pos.min() < 0 or pos.max() >= n):
+            return None
+        return pos
+    pos = np.minimum(np.searchsorted(sorted_keys, keys), n - 1)
+    if not np.array_equal(sorted_keys[pos], keys):
+        return None
+    return pos
+
+
 def _merge_by_sorted_key(left_df, right_df, on, columns):
     """Left merge as a gather: valid when the right keys are unique and every left key occurs in the right frame (the
     result of ``DataFrame.merge(how="left")`` is then the left frame, in order, plus the gathered columns).  The pandas
@@ -126,9 +144,8 @@ def _merge_by_sorted_key(left_df, right_df, on, columns):
         rk = rk[order]
         if not np.all(rk[1:] > rk[:-1]):
             return None  # duplicate keys on the right: a real merge multiplies rows
-    pos = np.searchsorted(rk, lk)
-    pos = np.minimum(pos, len(rk) - 1)
-    if not np.array_equal(rk[pos], lk):
+    pos = _positions_in_sorted_unique(rk, lk)
+    if pos is None:
         return None  # unmatched left keys would become NaN rows
     if order is not None:
         pos = order[pos]
@@ -316,9 +333,8 @@ class CandidateScoring:
             groups_with_ref = np.unique(sg[has_ref])
             process = np.isin(sg, groups_with_ref)
 
-        lib_row = np.searchsorted(lib_precursor_idx, pidx)
-        lib_row = np.minimum(lib_row, max(len(lib_precursor_idx) - 1, 0))
-        if len(pidx) and not np.array_equal(lib_precursor_idx[lib_row], pidx):
+        lib_row = _positions_in_sorted_unique(lib_precursor_idx.astype(np.int64, copy=False), pidx.astype(np.int64, copy=False))
+        if lib_row is None:
             raise ValueError("candidates_df contains precursor_idx values that are not in precursors_flat")
         sel = np.flatnonzero(process)
         cin, keep = _abi.make_candidates_in(
