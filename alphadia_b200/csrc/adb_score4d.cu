@@ -1061,7 +1061,10 @@ __device__ void score_one_4d(const Score4Params& P, int64_t ci, Small4& sm, floa
   if (lane == 0) P.out.valid[ci] = 1;
 }
 
-__global__ void __launch_bounds__(SC4_THREADS) adb_score4d_kernel(const __grid_constant__ Score4Params P) {
+#ifndef SC4_MIN_CTAS
+#define SC4_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(SC4_THREADS, SC4_MIN_CTAS) adb_score4d_kernel(const __grid_constant__ Score4Params P) {
   __shared__ Small4 small[SC4_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long gw = (long long)blockIdx.x * SC4_WARPS + warp;
