@@ -297,6 +297,12 @@ CONFIGS_3D = {
         cycle_seconds=1.0, n_noise_ms2=1500, n_noise_ms1=4000, rt_tolerance=100.0,
         planted_fraction=0.5, max_planted=60_000,
     ),
+    # many short cycles, few peaks: with a huge rt_tolerance the selection window exceeds 1024 cycles (legacy kernel pair)
+    "long_run": dict(
+        seed=31, n_precursors=300, n_cycles=1400, n_windows=3, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=0.5, n_noise_ms2=60, n_noise_ms1=120, rt_tolerance=2000.0,
+        planted_fraction=0.7, max_planted=None,
+    ),
     # config 5 (per file): 500k precursors
     "config5": dict(
         seed=50, n_precursors=500_000, n_cycles=1200, n_windows=75, quad_lo=400.0, quad_hi=1000.0,

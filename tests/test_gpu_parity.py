@@ -744,3 +744,21 @@ def test_4d_repeated_observation_ids(engine, oracle_lib):
     assert s_ref["valid"].sum() > 20
     assert_scores_close(s_got, s_ref, what="repeated observation ids")
     dlib.close(); draw.close()
+
+
+def test_selection_windows_longer_than_1024_cycles(engine, oracle_lib):
+    """rt_tolerance larger than the run: every precursor's window spans all 1400 cycles, which takes the extract +
+    dense-smoothing kernel pair with XIC rows accumulated directly in the HBM buffer."""
+    raw, pdf, fdf, lib, p = H.workload("long_run")
+    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    kernel = H.default_kernel(raw)
+    draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+    got = engine.select_candidates(draw, dlib, cfg, kernel)
+    ref = oracle_lib.select_candidates(raw, lib, cfg, kernel)
+    assert_candidates_equal(got, ref)
+    m = got["score"] > 0
+    assert m.sum() > 100
+    cin, keep = H.candidates_in_from_arrays(lib, {c: got[c][m] for c in INT_COLS})
+    scfg = H.scoring_config().to_struct()
+    assert_scores_close(engine.score_candidates(draw, dlib, scfg, cin), oracle_lib.score_candidates(raw, lib, scfg, cin), what="long_run")
+    dlib.close(); draw.close()
