@@ -207,21 +207,113 @@ def calculate_score_groups(input_df: pd.DataFrame, group_channels: bool = False)
     return input_df.sort_values(by=["score_group_idx", "precursor_idx"]).reset_index(drop=True)
 
 
+def logistic_rectangle(mu1, mu2, sigma1, sigma2, x):
+    """alphadia/search/scoring/quadrupole.py:12-44: difference of two logistic edges."""
+    with np.errstate(over="ignore"):  # exp overflow far outside the window gives the correct limit 0
+        return 1 / (1 + np.exp(-((x - mu1) / sigma1))) - 1 / (1 + np.exp(-((x - mu2) / sigma2)))
+
+
+def expand_cycle(cycle, lower_mz, upper_mz):
+    """alphadia/search/scoring/quadrupole.py:339-347."""
+    new_cycle = cycle.copy()
+    new_cycle[..., 0] -= lower_mz * (new_cycle[..., 0] > 0)
+    new_cycle[..., 1] += upper_mz * (new_cycle[..., 1] > 0)
+    return new_cycle
+
+
 class SimpleQuadrupoleJit:
-    """State of alphadia/search/scoring/quadrupole.py:46-78 (uncalibrated: sigma 0.2, delta_mu 0)."""
+    """State of alphadia/search/scoring/quadrupole.py:46-128 (uncalibrated: sigma 0.2, delta_mu 0); the device kernels take
+    ``sigma`` and ``delta_mu`` from here (``adb_scoring_config.quad_sigma / quad_delta_mu``)."""
 
     def __init__(self, cycle):
-        self.cycle = cycle
+        self.cycle = np.ascontiguousarray(cycle, dtype=np.float64)
         self.sigma = np.array([0.2, 0.2])
         self.delta_mu = np.array([0.0, 0.0])
+        self._cycle_calibrated = None
+        self._calibrated_provider = None  # set by SimpleQuadrupole: the calibrated cycle is computed on first use
+
+    @property
+    def cycle_calibrated(self):
+        if self._cycle_calibrated is None:
+            self._cycle_calibrated = self._calibrated_provider() if self._calibrated_provider else self.cycle
+        return self._cycle_calibrated
+
+    @property
+    def dia_mz_cycle_calibrated(self):
+        c = self.cycle_calibrated
+        return np.reshape(c, (c.shape[1] * c.shape[2], 2))
+
+    def predict(self, P, S, X):  # quadrupole.py:80-115
+        P, S = np.asarray(P, dtype=np.int64), np.asarray(S, dtype=np.int64)
+        mu1 = self.cycle[0, P, S, 0] + self.delta_mu[0]
+        mu2 = self.cycle[0, P, S, 1] + self.delta_mu[1]
+        return logistic_rectangle(mu1, mu2, self.sigma[0], self.sigma[1], np.asarray(X, dtype=np.float64))
+
+    def set_cycle_calibrated(self, cycle_calibrated):  # quadrupole.py:117-121
+        self._cycle_calibrated = cycle_calibrated
+
+    def get_dia_mz_cycle(self, lower_mz, upper_mz):  # quadrupole.py:123-127
+        expanded = expand_cycle(self.cycle_calibrated, lower_mz, upper_mz)
+        return np.reshape(expanded, (expanded.shape[1] * expanded.shape[2], 2))
 
 
 class SimpleQuadrupole:
-    """alphadia/search/scoring/quadrupole.py:130-151 without the (feature-unused) calibrated cycle scan."""
+    """alphadia/search/scoring/quadrupole.py:130-258 on the host.  ``get_calibrated_cycle`` evaluates the
+    2000-point transfer function of all (frame, scan) windows in one vectorised pass — the reference loops over them in
+    Python, which is slow for timsTOF cycles; the result only feeds debug plots and ``get_dia_mz_cycle``."""
 
     def __init__(self, cycle):
         self.cycle = cycle
         self.jit = SimpleQuadrupoleJit(cycle)
+        self.jit._calibrated_provider = self.get_calibrated_cycle  # lazily: features never read it
+
+    def fit(self, P, S, X, y):  # quadrupole.py:166-211
+        from scipy.optimize import curve_fit
+
+        mu1 = self.jit.cycle[0, P, S, 0]
+        mu2 = self.jit.cycle[0, P, S, 1]
+        X_train = np.stack([mu1, mu2, X], axis=1)
+
+        def _wrapper(X, sigma1, sigma2, delta_mu1, delta_mu2):
+            return logistic_rectangle(X[:, 0] + delta_mu1, X[:, 1] + delta_mu2, sigma1, sigma2, X[:, 2])
+
+        p0 = np.concatenate([self.jit.sigma, self.jit.delta_mu])
+        popt, _ = curve_fit(_wrapper, X_train, y, p0=p0)
+        self.jit.sigma = popt[:2]
+        self.jit.delta_mu = popt[2:]
+        self.jit.set_cycle_calibrated(self.get_calibrated_cycle())
+        return self
+
+    def predict(self, P, S, X):
+        return self.jit.predict(P, S, X)
+
+    def get_calibrated_cycle(self, treshold=0.01):  # quadrupole.py:227-258
+        cycle = self.jit.cycle
+        non_zero = cycle[cycle > 0]
+        new_cycle = cycle.copy()
+        if non_zero.size == 0:
+            return new_cycle
+        lowest_mz, highest_mz = np.min(non_zero), np.max(non_zero)
+        mz_width = highest_mz - lowest_mz
+        mz_space = np.linspace(lowest_mz - mz_width * 0.1, highest_mz + mz_width * 0.1, 2000)
+        lo, hi = cycle[0, :, :, 0], cycle[0, :, :, 1]
+        active = lo > 0
+        if not active.any():
+            return new_cycle
+        mu1 = lo[active][:, None] + self.jit.delta_mu[0]
+        mu2 = hi[active][:, None] + self.jit.delta_mu[1]
+        new_lo, new_hi = np.empty(mu1.shape[0]), np.empty(mu1.shape[0])
+        for a in range(0, mu1.shape[0], 4096):  # bounded temporaries: 4096 windows x 2000 points
+            inten = logistic_rectangle(mu1[a:a + 4096], mu2[a:a + 4096], self.jit.sigma[0], self.jit.sigma[1], mz_space[None, :])
+            above = inten > treshold
+            if not above.any(axis=1).all():
+                raise ValueError("zero-size array to reduction operation minimum which has no identity")  # as np.min(q_range)
+            first = np.argmax(above, axis=1)
+            last = above.shape[1] - 1 - np.argmax(above[:, ::-1], axis=1)
+            new_lo[a:a + 4096], new_hi[a:a + 4096] = mz_space[first], mz_space[last]
+        out_lo, out_hi = new_cycle[0, :, :, 0], new_cycle[0, :, :, 1]
+        out_lo[active], out_hi[active] = new_lo, new_hi
+        return new_cycle
 
 
 class CandidateScoring:

@@ -197,3 +197,45 @@ def test_merge_missing_columns():
     with pytest.raises(ValueError):
         merge_missing_columns(left, right, ["col_3"], on=None)
     assert merge_missing_columns(left, right, ["col_1"], on="idx") is left
+
+
+def test_simple_quadrupole_calibrated_cycle():
+    """vectorised get_calibrated_cycle == the reference's per-window loop (restated here verbatim in numpy),
+    and, when the reference is importable in this container, == the reference class itself."""
+    import sys
+
+    from alphadia_b200.scoring import SimpleQuadrupole, logistic_rectangle
+    from alphadia_b200.synthetic import make_config_3d, make_config_4d
+
+    for raw in (make_config_3d("config1")[0], make_config_4d("parity_4d", n_precursors=16)[0]):
+        cycle = np.ascontiguousarray(raw.cycle, dtype=np.float64)
+        q = SimpleQuadrupole(cycle)
+        got = q.jit.cycle_calibrated
+        # the reference loop (quadrupole.py:227-258)
+        nz = cycle[cycle > 0]
+        lo, hi = nz.min(), nz.max()
+        space = np.linspace(lo - (hi - lo) * 0.1, hi + (hi - lo) * 0.1, 2000)
+        exp = cycle.copy()
+        for pr in range(cycle.shape[1]):
+            for sc in range(cycle.shape[2]):
+                if cycle[0, pr, sc, 0] <= 0:
+                    continue
+                inten = logistic_rectangle(cycle[0, pr, sc, 0], cycle[0, pr, sc, 1], 0.2, 0.2, space)
+                rng_ = space[inten > 0.01]
+                exp[0, pr, sc, 0], exp[0, pr, sc, 1] = rng_.min(), rng_.max()
+        assert np.array_equal(got, exp)
+        assert got.shape == cycle.shape and (got[cycle <= 0] == cycle[cycle <= 0]).all()
+        assert (got[..., 0][cycle[..., 0] > 0] < cycle[..., 0][cycle[..., 0] > 0]).all()  # the 1 % threshold widens the window
+        P = np.array([1, 1, 2]); S = np.array([0, 0, 0]); X = np.array([cycle[0, 1, 0, 0], cycle[0, 1, 0, :].mean(), 100.0])
+        pred = q.predict(P, S, X)
+        assert abs(pred[0] - 0.5) < 1e-6 and pred[1] > 0.99 and pred[2] < 1e-6
+        assert q.jit.get_dia_mz_cycle(1.0, 2.0).shape == (cycle.shape[1] * cycle.shape[2], 2)
+    # fit recovers a shifted, wider window
+    rng = np.random.default_rng(0)
+    cycle = np.ascontiguousarray(make_config_3d("config1")[0].cycle, dtype=np.float64)
+    q = SimpleQuadrupole(cycle)
+    P = rng.integers(1, cycle.shape[1], 4000); S = np.zeros(4000, dtype=np.int64)
+    X = cycle[0, P, S, 0] + rng.uniform(-3, cycle[0, 1, 0, 1] - cycle[0, 1, 0, 0] + 3, 4000)
+    y = logistic_rectangle(cycle[0, P, S, 0] + 0.3, cycle[0, P, S, 1] - 0.2, 0.35, 0.5, X)
+    q.fit(P, S, X, y)
+    assert np.allclose(q.jit.sigma, [0.35, 0.5], atol=1e-3) and np.allclose(q.jit.delta_mu, [0.3, -0.2], atol=1e-3)
