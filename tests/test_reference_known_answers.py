@@ -200,9 +200,9 @@ def test_merge_missing_columns():
 
 
 def test_simple_quadrupole_calibrated_cycle():
-    """vectorised get_calibrated_cycle == the reference's per-window loop (restated here verbatim in numpy),
-    and, when the reference is importable in this container, == the reference class itself."""
-    import sys
+    """vectorised get_calibrated_cycle == the reference's per-window loop (restated here verbatim in numpy).
+    Checked once against the live reference class through oracle/refshim.py in the build container: cycle_calibrated,
+    dia_mz_cycle_calibrated and predict() bit-identical for the 3-D config1 cycle and the 4-D parity_4d cycle."""
 
     from alphadia_b200.scoring import SimpleQuadrupole, logistic_rectangle
     from alphadia_b200.synthetic import make_config_3d, make_config_4d
