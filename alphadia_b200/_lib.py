@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "adb_last_error", "adb_version", "adb_device_count",
     "adb_rawfile3d_create", "adb_rawfile4d_create", "adb_rawfile_destroy", "adb_rawfile_device_bytes", "adb_rawfile_stream",
     "adb_library_create", "adb_library_destroy",
-    "adb_select_candidates", "adb_score_candidates", "adb_fragment_competition",
+    "adb_select_candidates", "adb_score_candidates", "adb_fragment_competition", "adb_transpose_csr",
     "adb_select_candidates_resident", "adb_score_candidates_resident",
     "adb_fetch_candidates", "adb_fetch_candidate_table", "adb_fetch_scores", "adb_resident_score_table",
     "adb_last_timing", "adb_kernel_launches", "adb_last_main_kernel_ms",
@@ -250,3 +250,24 @@ def fragment_competition(window_start, window_stop, rt, frag_start, frag_stop, f
                                        C.c_double(ppm_tol), _abi.ptr(valid)),
           "adb_fragment_competition")
     return valid.astype(bool)
+
+
+def transpose_csr(tof_indices, push_indptr, n_tof_indices: int, values, device: int | None = None):
+    """Device version of ``_transpose(tof_indices, push_indptr, n_tof_indices, values)`` (alphadia/raw_data/bruker.py:202-274):
+    returns ``(push_indices u32, tof_indptr i64, new_values)`` of the tof-major CSR."""
+    require_device()
+    lib = load()
+    tof = _abi.as_c(tof_indices, np.uint32)
+    ptr_ = _abi.as_c(push_indptr, np.int64)
+    vals = _abi.as_c(values, np.uint16)
+    if len(ptr_) < 1 or len(tof) != len(vals):
+        raise ValueError("tof_indices and values must have the same length and push_indptr at least one entry")
+    n, n_push = len(tof), len(ptr_) - 1
+    push_out = np.zeros(n, np.uint32)
+    indptr_out = np.zeros(int(n_tof_indices) + 1, np.int64)
+    vals_out = np.zeros(n, np.uint16)
+    dev = current_device() if device is None else device
+    check(lib.adb_transpose_csr(C.c_int(dev), C.c_int64(n), C.c_int64(n_push), C.c_int64(int(n_tof_indices)), _abi.ptr(tof),
+                                _abi.ptr(ptr_), _abi.ptr(vals), _abi.ptr(push_out), _abi.ptr(indptr_out), _abi.ptr(vals_out)),
+          "adb_transpose_csr")
+    return push_out, indptr_out, vals_out

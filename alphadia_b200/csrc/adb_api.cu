@@ -297,6 +297,36 @@ __global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn c
 }
 
 
+
+// ---- CSR transpose of a timsTOF raw file (push-major -> tof-major), alphadia/raw_data/bruker.py:155-274 ----------
+__global__ void transpose_push_of_event_kernel(const int64_t* __restrict__ push_indptr, int64_t n_push, uint32_t* push_of_event,
+                                               uint32_t* idx) {
+  const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per push
+  const int lane = threadIdx.x & 31;
+  if (p >= n_push) return;
+  for (int64_t i = push_indptr[p] + lane; i < push_indptr[p + 1]; i += 32) { push_of_event[i] = (uint32_t)p; idx[i] = (uint32_t)i; }
+}
+
+__global__ void transpose_gather_kernel(const uint32_t* __restrict__ idx, const uint32_t* __restrict__ push_of_event,
+                                        const uint16_t* __restrict__ values, int64_t n, uint32_t* push_out, uint16_t* values_out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t i = idx[j];
+  push_out[j] = push_of_event[i];
+  values_out[j] = values[i];
+}
+
+__global__ void transpose_indptr_kernel(const uint32_t* __restrict__ sorted_tof, int64_t n, int64_t n_tof, int64_t* tof_indptr) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tof) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)sorted_tof[mid] < t) lo = mid + 1; else hi = mid;
+  }
+  tof_indptr[t] = lo;
+}
+
 // ---- m/z-major index of a 3-D raw file ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t ordered_bits(float v) {
   uint32_t b = __float_as_uint(v);
@@ -1248,6 +1278,53 @@ int adb_fragment_competition(int device, int64_t n_windows, const int64_t* windo
   if (e == cudaSuccess) e = cudaMemcpy(valid, b_valid.ptr, (size_t)n_psm, cudaMemcpyDeviceToHost);
   cleanup();
   if (e != cudaSuccess) return fail(std::string("fragcomp kernel failed: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int adb_transpose_csr(int device, int64_t n_values, int64_t n_push, int64_t n_tof, const uint32_t* tof_indices,
+                      const int64_t* push_indptr, const uint16_t* values, uint32_t* push_indices_out, int64_t* tof_indptr_out,
+                      uint16_t* values_out) {
+  if (n_values < 0 || n_push < 0 || n_tof < 0) return fail("negative size");
+  if (!push_indptr || !tof_indptr_out) return fail("null argument");
+  if (n_values > 0 && (!tof_indices || !values || !push_indices_out || !values_out)) return fail("null argument");
+  if (n_values >= 4294967000LL || n_push >= 4294967000LL) return fail("more than 2^32 events or pushes are not supported");
+  if (push_indptr[0] != 0 || push_indptr[n_push] != n_values) return fail("push_indptr does not span the value array");
+  for (int64_t p = 0; p < n_push; p++)
+    if (push_indptr[p + 1] < push_indptr[p]) return fail("push_indptr is not monotone (push " + std::to_string(p) + ")");
+  if (set_device(device)) return 1;
+  const size_t N = (size_t)std::max<int64_t>(n_values, 1);
+  DeviceBuffer b_tof, b_tof_sorted, b_idx, b_idx_sorted, b_push, b_ptr, b_val, b_push_out, b_val_out, b_indptr, b_tmp;
+  DeviceBuffer* all[] = {&b_tof, &b_tof_sorted, &b_idx, &b_idx_sorted, &b_push, &b_ptr, &b_val, &b_push_out, &b_val_out, &b_indptr, &b_tmp};
+  auto cleanup = [&]() { for (DeviceBuffer* b : all) b->release(); };
+  const int end_bit = 32;  // all key bits: out-of-range tof indices must sort last so they can be detected
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)n_values, 0, end_bit, (cudaStream_t)0);
+  if (b_tof.reserve(4 * N) || b_tof_sorted.reserve(4 * N) || b_idx.reserve(4 * N) || b_idx_sorted.reserve(4 * N) || b_push.reserve(4 * N) ||
+      b_ptr.reserve(8 * (size_t)(n_push + 1)) || b_val.reserve(2 * N) || b_push_out.reserve(4 * N) || b_val_out.reserve(2 * N) ||
+      b_indptr.reserve(8 * (size_t)(n_tof + 1)) || b_tmp.reserve(tmp_bytes + 16)) { cleanup(); return 1; }
+  cudaError_t e = cudaSuccess;
+  auto h2d = [&](void* d, const void* h, size_t bytes) { if (e == cudaSuccess && bytes) e = cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice); };
+  h2d(b_tof.ptr, tof_indices, 4 * (size_t)n_values); h2d(b_ptr.ptr, push_indptr, 8 * (size_t)(n_push + 1)); h2d(b_val.ptr, values, 2 * (size_t)n_values);
+  if (e != cudaSuccess) { cleanup(); return fail(std::string("transpose H2D failed: ") + cudaGetErrorString(e)); }
+  if (n_values > 0) {
+    transpose_push_of_event_kernel<<<(unsigned)((n_push * 32 + 255) / 256), 256>>>(b_ptr.as<int64_t>(), n_push, b_push.as<uint32_t>(), b_idx.as<uint32_t>());
+    // stable radix sort by tof index: the input is push-major, so pushes stay ascending inside every tof row (bruker.py:165-182)
+    cub::DeviceRadixSort::SortPairs(b_tmp.ptr, tmp_bytes, b_tof.as<uint32_t>(), b_tof_sorted.as<uint32_t>(), b_idx.as<uint32_t>(),
+                                    b_idx_sorted.as<uint32_t>(), (int)n_values, 0, end_bit, (cudaStream_t)0);
+    transpose_gather_kernel<<<(unsigned)((n_values + 255) / 256), 256>>>(b_idx_sorted.as<uint32_t>(), b_push.as<uint32_t>(), b_val.as<uint16_t>(),
+                                                                       n_values, b_push_out.as<uint32_t>(), b_val_out.as<uint16_t>());
+  }
+  transpose_indptr_kernel<<<(unsigned)((n_tof + 1 + 255) / 256), 256>>>(b_tof_sorted.as<uint32_t>(), n_values, n_tof, b_indptr.as<int64_t>());
+  uint32_t last_tof = 0;
+  if (n_values > 0) e = cudaMemcpy(&last_tof, b_tof_sorted.as<uint32_t>() + (n_values - 1), 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess && n_values > 0 && (int64_t)last_tof >= n_tof) { cleanup(); return fail("a tof index is >= n_tof_indices"); }
+  auto d2h = [&](void* h, const void* d, size_t bytes) { if (e == cudaSuccess && bytes) e = cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost); };
+  d2h(push_indices_out, b_push_out.ptr, 4 * (size_t)n_values); d2h(values_out, b_val_out.ptr, 2 * (size_t)n_values);
+  d2h(tof_indptr_out, b_indptr.ptr, 8 * (size_t)(n_tof + 1));
+  cleanup();
+  if (e != cudaSuccess) return fail(std::string("transpose failed: ") + cudaGetErrorString(e));
   return 0;
 }
 

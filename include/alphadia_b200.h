@@ -227,6 +227,14 @@ int adb_fragment_competition(int device, int64_t n_windows, const int64_t* windo
                              int64_t n_frag, const void* fragment_mz, int32_t is_f64,
                              double rt_tol_seconds, double mass_tol_ppm, uint8_t* valid);
 
+/* Load-time CSR transpose of a timsTOF raw file, push-major -> tof-major: replaces _transpose / _transpose_chunk
+ * (alphadia/raw_data/bruker.py:155-274).  In: tof_indices u32 [n_values] (column index of every event, events
+ * ordered by push), push_indptr i64 [n_push + 1], values u16 [n_values].  Out (caller-allocated): push_indices u32 [n_values]
+ * ascending inside every tof row, tof_indptr i64 [n_tof + 1], values u16 [n_values] — one stable device radix sort. */
+int adb_transpose_csr(int device, int64_t n_values, int64_t n_push, int64_t n_tof, const uint32_t* tof_indices,
+                      const int64_t* push_indptr, const uint16_t* values, uint32_t* push_indices_out,
+                      int64_t* tof_indptr_out, uint16_t* values_out);
+
 /* ---- resident variants (bench.py `value`, the sharded driver) -------------------------------
  * Same kernels; the raw file and library are already in HBM, results stay in HBM inside the raw
  * handle's workspace until fetched.  (Not needed by a reference-side binding.) */

@@ -152,3 +152,20 @@ def score_candidates_4d(raw4d, lib_arrays, cfg_struct, cand_in_struct, n_threads
     if rc != 0:
         raise RuntimeError(f"oracle 4-D scoring failed rc={rc}")
     return arrs
+
+
+def transpose_csr(tof_indices, push_indptr, n_tof_indices, values):
+    """C restatement of ``_transpose`` (alphadia/raw_data/bruker.py:202-274)."""
+    L = lib()
+    tof = _abi.as_c(tof_indices, np.uint32)
+    ptr_ = _abi.as_c(push_indptr, np.int64)
+    vals = _abi.as_c(values, np.uint16)
+    n, n_push = len(tof), len(ptr_) - 1
+    push_out = np.zeros(n, np.uint32)
+    indptr_out = np.zeros(int(n_tof_indices) + 1, np.int64)
+    vals_out = np.zeros(n, np.uint16)
+    rc = L.adbo_transpose_csr(C.c_int64(n), C.c_int64(n_push), C.c_int64(int(n_tof_indices)), _abi.ptr(tof), _abi.ptr(ptr_),
+                              _abi.ptr(vals), _abi.ptr(push_out), _abi.ptr(indptr_out), _abi.ptr(vals_out))
+    if rc != 0:
+        raise RuntimeError("adbo_transpose_csr failed (tof index out of range)")
+    return push_out, indptr_out, vals_out

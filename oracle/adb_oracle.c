@@ -1856,3 +1856,28 @@ int adbo_score_candidates_4d(const adb_rawfile4d_desc* raw, const adb_library_de
 void adbo_scan_indices_4d(const adb_rawfile4d_desc* raw, float mobility, double tol, int64_t* out) {
   get_scan_indices_tolerance_4d(raw, mobility, tol, 16, out);
 }
+
+
+/* ==========================================================================================
+ * timsTOF load-time transpose — alphadia/raw_data/bruker.py:202-274 (_transpose, _transpose_chunk)
+ * push-major CSR (rows = pushes, columns = tof indices) -> tof-major CSR; the chunked scatter of the
+ * reference visits the events in push order for every tof chunk, i.e. a stable counting sort by tof index.
+ * ======================================================================================== */
+int adbo_transpose_csr(int64_t n_values, int64_t n_push, int64_t n_tof, const uint32_t* tof_indices, const int64_t* push_indptr,
+                       const uint16_t* values, uint32_t* push_indices_out, int64_t* tof_indptr_out, uint16_t* values_out) {
+  uint32_t* count = (uint32_t*)calloc((size_t)(n_tof > 0 ? n_tof : 1), sizeof(uint32_t));
+  for (int64_t i = 0; i < n_values; i++) { if ((int64_t)tof_indices[i] >= n_tof) { free(count); return 1; } count[tof_indices[i]]++; } /* :238-240 */
+  tof_indptr_out[0] = 0;
+  for (int64_t t = 0; t < n_tof; t++) tof_indptr_out[t + 1] = tof_indptr_out[t] + count[t]; /* :243-246 */
+  memset(count, 0, sizeof(uint32_t) * (size_t)(n_tof > 0 ? n_tof : 1));
+  for (int64_t p = 0; p < n_push; p++) /* :171-182 */
+    for (int64_t idx = push_indptr[p]; idx < push_indptr[p + 1]; idx++) {
+      uint32_t t = tof_indices[idx];
+      int64_t dst = tof_indptr_out[t] + count[t];
+      push_indices_out[dst] = (uint32_t)p;
+      values_out[dst] = values[idx];
+      count[t]++;
+    }
+  free(count);
+  return 0;
+}

@@ -162,8 +162,34 @@ def run(name: str, threads: int, variants: bool):
     print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def transpose_inputs(seed: int = 5, n_push: int = 1500, n_tof: int = 257):
+    """Push-major CSR of a small synthetic timsTOF file: ragged pushes (20 % empty), ascending tof indices inside a push."""
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, 24, n_push)
+    counts[rng.random(n_push) < 0.2] = 0
+    push_indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    tof = np.concatenate([np.sort(rng.choice(n_tof, size=c, replace=False)) for c in counts] + [np.zeros(0, np.int64)]).astype(np.uint32)
+    values = rng.integers(1, 60000, len(tof)).astype(np.uint16)
+    return tof, push_indptr, n_tof, values
+
+
+def run_transpose():
+    """Golden vectors of the load-time CSR transpose: the reference's _transpose (alphadia/raw_data/bruker.py:202-274)."""
+    refshim.install()
+    bruker = refshim.ref("alphadia.raw_data.bruker")
+    tof, push_indptr, n_tof, values = transpose_inputs()
+    push_indices, tof_indptr, new_values = bruker._transpose(tof, push_indptr, n_tof, values)
+    path = os.path.join(HERE, "transpose_small.npz")
+    np.savez_compressed(path, push_indices=push_indices, tof_indptr=tof_indptr, new_values=new_values,
+                        input_checksum=hashlib.sha256(tof.tobytes() + push_indptr.tobytes() + values.tobytes()).hexdigest())
+    print(f"[transpose] wrote {path} ({os.path.getsize(path) / 1e3:.1f} kB)", flush=True)
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or ["config1", "parity_small"]
     threads = int(os.environ.get("ADB_THREADS", os.cpu_count() or 1))
     for i, n in enumerate(names):
-        run(n, threads, variants=(n == "parity_small"))
+        if n == "transpose":
+            run_transpose()
+        else:
+            run(n, threads, variants=(n == "parity_small"))

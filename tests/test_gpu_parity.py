@@ -762,3 +762,36 @@ def test_selection_windows_longer_than_1024_cycles(engine, oracle_lib):
     scfg = H.scoring_config().to_struct()
     assert_scores_close(engine.score_candidates(draw, dlib, scfg, cin), oracle_lib.score_candidates(raw, lib, scfg, cin), what="long_run")
     dlib.close(); draw.close()
+
+
+def test_transpose_csr_matches_oracle_and_golden(engine, oracle_lib):
+    """adb_transpose_csr == the oracle == the reference's _transpose golden; ragged and degenerate inputs."""
+    import os
+
+    from tests.test_oracle_golden import _transpose_inputs
+
+    tof, push_indptr, n_tof, values = _transpose_inputs()
+    got = engine.transpose_csr(tof, push_indptr, n_tof, values, device=0)
+    g = np.load(os.path.join(H.GOLDEN_DIR, "transpose_small.npz"), allow_pickle=False)
+    for a, k in zip(got, ("push_indices", "tof_indptr", "new_values")):
+        assert np.array_equal(a, g[k]) and a.dtype == g[k].dtype, k
+    # a larger ragged case against the oracle, then the real layout: the synthetic timsTOF file, transposed back and forth
+    tof, push_indptr, n_tof, values = _transpose_inputs(seed=9, n_push=200_000, n_tof=40_000)
+    ref = oracle_lib.transpose_csr(tof, push_indptr, n_tof, values)
+    got = engine.transpose_csr(tof, push_indptr, n_tof, values, device=0)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    raw = H.workload("parity_4d")[0]
+    n_push = raw.frame_max_index * raw.scan_max_index
+    tof_of = np.repeat(np.arange(len(raw.mz_values), dtype=np.uint32), np.diff(raw.tof_indptr))
+    back = np.argsort(raw.push_indices, kind="stable")  # tof-major -> push-major (tof ascending inside a push)
+    pm_tof, pm_val = tof_of[back], raw.intensity_values[back]
+    pm_indptr = np.concatenate([[0], np.cumsum(np.bincount(raw.push_indices, minlength=n_push))]).astype(np.int64)
+    push_indices, tof_indptr, new_values = engine.transpose_csr(pm_tof, pm_indptr, len(raw.mz_values), pm_val, device=0)
+    assert np.array_equal(push_indices, raw.push_indices) and np.array_equal(tof_indptr, raw.tof_indptr)
+    assert np.array_equal(new_values, raw.intensity_values)
+    # degenerate inputs and the error path
+    p0, i0, v0 = engine.transpose_csr(np.zeros(0, np.uint32), np.zeros(5, np.int64), 7, np.zeros(0, np.uint16), device=0)
+    assert len(p0) == 0 and np.array_equal(i0, np.zeros(8, np.int64))
+    with pytest.raises(RuntimeError, match="n_tof_indices"):
+        engine.transpose_csr(np.array([1, 9], np.uint32), np.array([0, 2], np.int64), 5, np.array([1, 2], np.uint16), device=0)

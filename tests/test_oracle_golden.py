@@ -140,3 +140,40 @@ def test_scoring_4d_vs_reference(oracle_lib):
     for k, v2 in FRAG_MAP.items():
         a, b = arrs[v2][m], g[f"frag_{k}"]
         assert np.array_equal(a, b) if k != "correlation" else H.rel_err(a, b).max() < 1e-4, k
+
+
+# ---- timsTOF load-time CSR transpose --------------------------------------------------
+def _transpose_inputs(seed=5, n_push=1500, n_tof=257):
+    """Same generator as tests/golden/generate_golden.py::transpose_inputs."""
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, 24, n_push)
+    counts[rng.random(n_push) < 0.2] = 0
+    push_indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    tof = np.concatenate([np.sort(rng.choice(n_tof, size=c, replace=False)) for c in counts] + [np.zeros(0, np.int64)]).astype(np.uint32)
+    values = rng.integers(1, 60000, len(tof)).astype(np.uint16)
+    return tof, push_indptr, n_tof, values
+
+
+def test_transpose_oracle_vs_reference_golden(oracle_lib):
+    import hashlib
+    import os
+
+    g = np.load(os.path.join(H.GOLDEN_DIR, "transpose_small.npz"), allow_pickle=False)
+    tof, push_indptr, n_tof, values = _transpose_inputs()
+    assert str(g["input_checksum"]) == hashlib.sha256(tof.tobytes() + push_indptr.tobytes() + values.tobytes()).hexdigest()
+    push_indices, tof_indptr, new_values = oracle_lib.transpose_csr(tof, push_indptr, n_tof, values)
+    assert np.array_equal(push_indices, g["push_indices"]) and push_indices.dtype == g["push_indices"].dtype
+    assert np.array_equal(tof_indptr, g["tof_indptr"]) and tof_indptr.dtype == g["tof_indptr"].dtype
+    assert np.array_equal(new_values, g["new_values"]) and new_values.dtype == g["new_values"].dtype
+    # independent restatement: stable sort by tof index; and the round trip back to push-major order
+    order = np.argsort(tof, kind="stable")
+    push_of = np.repeat(np.arange(len(push_indptr) - 1, dtype=np.uint32), np.diff(push_indptr))
+    assert np.array_equal(push_of[order], push_indices) and np.array_equal(values[order], new_values)
+    tof_of = np.repeat(np.arange(n_tof, dtype=np.uint32), np.diff(tof_indptr))
+    back = np.lexsort((tof_of, push_indices))
+    assert np.array_equal(tof_of[back], tof) and np.array_equal(new_values[back], values)
+    # ragged edges: no events at all, a single push, every event in one tof row
+    p0, i0, v0 = oracle_lib.transpose_csr(np.zeros(0, np.uint32), np.zeros(5, np.int64), 7, np.zeros(0, np.uint16))
+    assert len(p0) == 0 and np.array_equal(i0, np.zeros(8, np.int64))
+    p1, i1, v1 = oracle_lib.transpose_csr(np.full(4, 3, np.uint32), np.array([0, 1, 1, 3, 4], np.int64), 5, np.array([9, 8, 7, 6], np.uint16))
+    assert np.array_equal(p1, [0, 2, 2, 3]) and np.array_equal(i1, [0, 0, 0, 0, 4, 4]) and np.array_equal(v1, [9, 8, 7, 6])
