@@ -795,3 +795,50 @@ def test_transpose_csr_matches_oracle_and_golden(engine, oracle_lib):
     assert len(p0) == 0 and np.array_equal(i0, np.zeros(8, np.int64))
     with pytest.raises(RuntimeError, match="n_tof_indices"):
         engine.transpose_csr(np.array([1, 9], np.uint32), np.array([0, 2], np.int64), 5, np.array([1, 2], np.uint16), device=0)
+
+
+def test_multiplexed_score_groups_and_reference_channel(engine, oracle_lib):
+    """MultiplexingRequantificationHandler settings (score_grouped=True, reference_channel=0): candidates of the channels
+    of one elution group form a score group; groups without the reference channel are skipped entirely
+    (score_group.py:49-63), the others are scored candidate by candidate exactly like the ungrouped path."""
+    from alphadia_b200 import CandidateScoring, CandidateSelection
+
+    raw, pdf, fdf, lib, p = H.workload("parity_small")
+    pdf = pdf.copy()
+    n = len(pdf)
+    # three channels per elution group: precursors 3k, 3k+1, 3k+2 share elution group k and carry channels 0 / 4 / 8;
+    # every fifth group lacks channel 0
+    pdf["elution_group_idx"] = (np.arange(n) // 3).astype(np.uint32)
+    pdf["decoy"] = ((np.arange(n) // 3) % 2).astype(np.uint8)
+    ch = np.array([0, 4, 8], dtype=np.uint32)[np.arange(n) % 3]
+    ch[(np.arange(n) // 3) % 5 == 0] = np.array([12, 4, 8], dtype=np.uint32)[np.arange(n) % 3][(np.arange(n) // 3) % 5 == 0]
+    pdf["channel"] = ch
+    sel = CandidateSelection(raw, pdf.copy(), fdf.copy(), H.selection_config(p["rt_tolerance"], candidate_count=1),
+                             rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+                             fragment_mz_column="mz_library", fwhm_rt=5.0, fwhm_mobility=0.01)
+    cand_df = sel()
+    cfg = H.scoring_config(score_grouped=True, reference_channel=0)
+    scorer = CandidateScoring(dia_data=raw, precursors_flat=pdf.copy(), fragments_flat=fdf.copy(), config=cfg,
+                              rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+                              fragment_mz_column="mz_library")
+    feat_df, frag_df = scorer(cand_df.copy())
+    # a score group has the reference channel only if the channel-0 precursor itself produced a candidate
+    cand_channel = pdf.set_index("precursor_idx")["channel"].reindex(cand_df["precursor_idx"]).values
+    groups_with_ref = set(cand_df["elution_group_idx"].values[cand_channel == 0])
+    assert 0 < len(groups_with_ref) < cand_df["elution_group_idx"].nunique()
+    assert len(feat_df) > 50
+    assert set(feat_df["elution_group_idx"]).issubset(groups_with_ref)
+    # the same candidates through the ungrouped configuration: identical feature rows for the processed groups
+    scorer0 = CandidateScoring(dia_data=raw, precursors_flat=pdf.copy(), fragments_flat=fdf.copy(), config=H.scoring_config(),
+                               rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+                               fragment_mz_column="mz_library")
+    feat0, _ = scorer0(cand_df.copy())
+    keep0 = feat0[feat0["elution_group_idx"].isin(groups_with_ref)].sort_values(["precursor_idx", "rank"]).reset_index(drop=True)
+    got = feat_df.sort_values(["precursor_idx", "rank"]).reset_index(drop=True)
+    assert np.array_equal(got["precursor_idx"].values, keep0["precursor_idx"].values)
+    from alphadia_b200.scoring import DEFAULT_FEATURE_COLUMNS
+    assert np.array_equal(got[DEFAULT_FEATURE_COLUMNS].values, keep0[DEFAULT_FEATURE_COLUMNS].values, equal_nan=True)
+    # a precursor twice in one score group is rejected like in the reference (score_group.py:221-226)
+    dup = pd.concat([cand_df, cand_df.iloc[:1]], ignore_index=True)
+    with pytest.raises(ValueError, match="unique within a score group"):
+        scorer(dup)
