@@ -588,6 +588,8 @@ int resident_extents(adb_rawfile* raw, int64_t* s_max, int64_t* f_max, int64_t n
 int run_selection(adb_rawfile* raw, adb_library* lib, const adb_selection_config* cfg, const float* kernel,
                   int32_t kh, int32_t kw) {
   if (raw->device != lib->device) return fail("raw file and library live on different devices");
+  if (lib->dev.n_precursors * std::max<int64_t>(cfg->candidate_count, 1) >= 2000000000LL)
+    return fail("library batch too large: n_precursors * candidate_count must stay below 2e9 (split the library)");
   if (raw->is4d) {
     if (cfg->candidate_count < 1 || cfg->candidate_count > 16) return fail("candidate_count must be in [1, 16]");
     if (cfg->top_k_precursors < 1) return fail("top_k_precursors must be >= 1");
@@ -889,7 +891,7 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
     uint64_t *k_in = nullptr, *k_out = nullptr; uint32_t *v_in = nullptr, *v_out = nullptr; void* tmp = nullptr;
     size_t tmp_bytes = 0;
     const int end_bit = 64;  // all-ones filler keys (peaks outside every spectrum) must sort last
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, r->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)n, 0, end_bit, r->stream);
     bool ok = cudaMalloc((void**)&k_in, 8 * N) == cudaSuccess && cudaMalloc((void**)&k_out, 8 * N) == cudaSuccess &&
               cudaMalloc((void**)&v_in, 4 * N) == cudaSuccess && cudaMalloc((void**)&v_out, 4 * N) == cudaSuccess &&
               cudaMalloc(&tmp, tmp_bytes + 16) == cudaSuccess;
@@ -897,7 +899,7 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
       cudaMemsetAsync(k_in, 0xFF, 8 * N, r->stream);  // peaks outside every spectrum sort to the end
       cudaMemsetAsync(v_in, 0, 4 * N, r->stream);
       mzindex_keys_kernel<<<(unsigned)((d->n_spectra * 32 + 255) / 256), 256, 0, r->stream>>>(v, k_in, v_in);
-      cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, r->stream);
+      cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)n, 0, end_bit, r->stream);
       if (n > 0) mzindex_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, s_mz, s_int, s_cyc);
       mzindex_segments_kernel<<<(unsigned)((d->cycle_len + 1 + 255) / 256), 256, 0, r->stream>>>(k_out, n, d->cycle_len, pstart);
       cudaMemsetAsync(s_mz + n, 0x7f, 4 * 64, r->stream);  // padding: huge m/z, never inside a window
@@ -1299,7 +1301,7 @@ int adb_transpose_csr(int device, int64_t n_values, int64_t n_push, int64_t n_to
   const int end_bit = 32;  // all key bits: out-of-range tof indices must sort last so they can be detected
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)n_values, 0, end_bit, (cudaStream_t)0);
+                                  (uint32_t*)nullptr, (int64_t)n_values, 0, end_bit, (cudaStream_t)0);
   if (b_tof.reserve(4 * N) || b_tof_sorted.reserve(4 * N) || b_idx.reserve(4 * N) || b_idx_sorted.reserve(4 * N) || b_push.reserve(4 * N) ||
       b_ptr.reserve(8 * (size_t)(n_push + 1)) || b_val.reserve(2 * N) || b_push_out.reserve(4 * N) || b_val_out.reserve(2 * N) ||
       b_indptr.reserve(8 * (size_t)(n_tof + 1)) || b_tmp.reserve(tmp_bytes + 16)) { cleanup(); return 1; }
@@ -1311,7 +1313,7 @@ int adb_transpose_csr(int device, int64_t n_values, int64_t n_push, int64_t n_to
     transpose_push_of_event_kernel<<<(unsigned)((n_push * 32 + 255) / 256), 256>>>(b_ptr.as<int64_t>(), n_push, b_push.as<uint32_t>(), b_idx.as<uint32_t>());
     // stable radix sort by tof index: the input is push-major, so pushes stay ascending inside every tof row (bruker.py:165-182)
     cub::DeviceRadixSort::SortPairs(b_tmp.ptr, tmp_bytes, b_tof.as<uint32_t>(), b_tof_sorted.as<uint32_t>(), b_idx.as<uint32_t>(),
-                                    b_idx_sorted.as<uint32_t>(), (int)n_values, 0, end_bit, (cudaStream_t)0);
+                                    b_idx_sorted.as<uint32_t>(), (int64_t)n_values, 0, end_bit, (cudaStream_t)0);
     transpose_gather_kernel<<<(unsigned)((n_values + 255) / 256), 256>>>(b_idx_sorted.as<uint32_t>(), b_push.as<uint32_t>(), b_val.as<uint16_t>(),
                                                                        n_values, b_push_out.as<uint32_t>(), b_val_out.as<uint16_t>());
   }
