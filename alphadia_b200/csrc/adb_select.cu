@@ -1,4 +1,4 @@
-// alphadia_b200 — candidate selection (3-D raw files), sm_100a: three kernels per chunk of precursors.
+// alphadia_b200 — candidate selection (3-D raw files), sm_100a.
 //
 // Replaces _select_candidates_pjit (alphadia/search/selection/selection.py:78-203) and everything below it:
 // AlphaRawJIT.get_dense_intensity (jitclasses/alpharaw_jit.py:339-425), get_frame_indices
@@ -6,19 +6,19 @@
 // convolution with fp64 FMA accumulation — see DESIGN.md), _build_features/_build_candidates
 // (selection.py:206-226,367-526), find_peaks_1d / symetric_limits_2d (selection/utils.py:45-74,205-312).
 //
-// Precursors are visited in (quad window, RT) order so concurrently running CTAs hit the same spectra in L2.
+// Precursors are visited in (quad window, RT) order so concurrently running warps hit the same index segment in L2.
 //   adb_select_plan_kernel     warp per precursor: isotope m/z, fragment filter + m/z sort, RT window -> cycle
 //                              window, quad windows, ppm windows -> a 40-byte plan + lo/hi rows in HBM
-//   adb_select_extract_kernel  thread per (precursor, cycle, layer) XIC cell at full occupancy, layer fastest
-//                              (neighbouring threads search the same spectrum), SEL_ILP independent searches in
-//                              flight per thread through the L2-resident m/z bucket index; dense XIC layers
-//                              [precursor][layer][cycle] f32 go to HBM (they stay in the 126 MB L2 for the consumer)
-//   adb_select_smooth_kernel   CTA per precursor, thread per cycle: layers streamed through a double-buffered
-//                              fp64 shared-memory row with circular halo (one f32->f64 conversion per element),
-//                              30-tap x 2-row Gaussian smoothing as fp64 FMA from the constant bank (kernel rows
-//                              then columns ascending), log(x + 1) in fp64 rounded to f32, f32 layer sums; then
-//                              warp 0: strict 5-point peaks, top-N (warp arg-max), close-peak suppression,
-//                              symmetric limits, write-out (integer-exact tail).
+//   adb_select_fused_kernel    WARP PER PRECURSOR (cycle windows <= 1024, kernel width <= 32): every XIC row (layer) is
+//                              extracted through the m/z-major index (one warp-cooperative 32-ary search + a scan of
+//                              the few dozen peaks inside the ppm window, any cycle), lands in shared memory with its
+//                              circular halo and a bit mask of its non-zero cycles, and is smoothed over the non-zero
+//                              taps only (bit-identical to the dense fp64 sum); log(x + 1) goes into per-cell f32 layer
+//                              sums; the warp then finds strict 5-point peaks, top-N (warp arg-max), suppresses close
+//                              peaks, computes the symmetric limits and writes the candidates (integer-exact tail).
+//   legacy pair                longer windows / wider kernels: adb_select_extract_kernel (warp per XIC row, same index
+//                              extraction, rows to a dense HBM buffer) + adb_select_smooth_kernel (CTA per precursor,
+//                              dense 30-tap x 2-row fp64 smoothing, 4 cells per thread).
 #include <algorithm>
 #include <cstdlib>
 
