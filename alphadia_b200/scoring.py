@@ -150,13 +150,15 @@ def _merge_by_sorted_key(left_df, right_df, on, columns):
     if order is not None:
         pos = order[pos]
     out = left_df.reset_index(drop=True)
+    new_cols = {}
     for c in columns:
         src = right_df[c]
         if isinstance(src.dtype, np.dtype) and src.dtype != object:
-            out[c] = src.values[pos]
+            new_cols[c] = src.values[pos]
         else:  # object / extension columns: keep the dtype (pandas would re-infer `str` from an object array)
-            out[c] = pd.Series(src.values[pos], index=out.index, dtype=src.dtype)
-    return out
+            new_cols[c] = pd.Series(src.values[pos], index=out.index, dtype=src.dtype)
+    # one concat instead of one block-manager insert per column
+    return pd.concat([out, pd.DataFrame(new_cols, index=out.index, copy=False)], axis=1)
 
 
 def count_residues(sequences, residues) -> list:
@@ -183,14 +185,36 @@ def count_residues(sequences, residues) -> list:
     return out[0] if single else out
 
 
+def _sorted_by(df: pd.DataFrame, by) -> pd.DataFrame:
+    """``df.sort_values(by=by)`` for numeric key columns (stable lexicographic order), skipping the row gather when the
+    frame is already in order — the usual case for a candidate table that comes straight from the selection."""
+    if len(df) < 2:
+        return df
+    keys = [df[c].values for c in by]
+    if not all(isinstance(k, np.ndarray) and k.dtype.kind in "iub" for k in keys):
+        return df.sort_values(by=by)
+    keys = [k.astype(np.int64, copy=False) for k in keys]
+    in_order = np.ones(len(df) - 1, dtype=bool)
+    tie = np.ones(len(df) - 1, dtype=bool)
+    for k in keys:  # lexicographic "previous row <= next row"
+        in_order &= ~(tie & (k[1:] < k[:-1]))
+        tie &= k[1:] == k[:-1]
+        if not in_order.all():
+            break
+    if in_order.all():
+        return df
+    return df.take(np.lexsort(tuple(reversed(keys))))
+
+
 def calculate_score_groups(input_df: pd.DataFrame, group_channels: bool = False) -> pd.DataFrame:
     """alphadia/search/scoring/utils.py:269-410."""
     if "rank" in input_df.columns:
-        input_df = input_df.sort_values(by=["elution_group_idx", "decoy", "rank", "precursor_idx"])
+        input_df = _sorted_by(input_df, ["elution_group_idx", "decoy", "rank", "precursor_idx"])
         rank_values = input_df["rank"].values
     else:
-        input_df = input_df.sort_values(by=["elution_group_idx", "decoy", "precursor_idx"])
+        input_df = _sorted_by(input_df, ["elution_group_idx", "decoy", "precursor_idx"])
         rank_values = np.zeros(len(input_df), dtype=np.uint32)
+    input_df = input_df.reset_index(drop=True)
     if group_channels:
         eg = input_df["elution_group_idx"].values
         decoy = input_df["decoy"].values
@@ -202,9 +226,10 @@ def calculate_score_groups(input_df: pd.DataFrame, group_channels: bool = False)
             change[1:] = (eg[1:] != eg[:-1]) | (decoy[1:] != decoy[:-1]) | (rank_values[1:] != rank_values[:-1])
             groups = np.cumsum(change).astype(np.uint32)
         input_df["score_group_idx"] = groups
-    else:
-        input_df["score_group_idx"] = np.arange(len(input_df), dtype=np.uint32)
-    return input_df.sort_values(by=["score_group_idx", "precursor_idx"]).reset_index(drop=True)
+        return _sorted_by(input_df, ["score_group_idx", "precursor_idx"]).reset_index(drop=True)
+    # one group per candidate: score_group_idx ascends with the row, the final sort of the reference is the identity
+    input_df["score_group_idx"] = np.arange(len(input_df), dtype=np.uint32)
+    return input_df
 
 
 def logistic_rectangle(mu1, mu2, sigma1, sigma2, x):
@@ -448,7 +473,8 @@ class CandidateScoring:
         if precursor_df_columns is None:
             precursor_df_columns = DEFAULT_PRECURSOR_COLUMNS.copy()
         valid = psm["valid"].astype(bool)
-        candidates_psm_df = pd.DataFrame(psm["features"][valid], columns=feature_columns)
+        features = psm["features"] if valid.all() else psm["features"][valid]
+        candidates_psm_df = pd.DataFrame(features, columns=feature_columns, copy=False)  # one block, no second copy
         candidates_psm_df["precursor_idx"] = psm["precursor_idx"][valid]
         candidates_psm_df["rank"] = psm["rank"][valid]
         candidates_psm_df = self.merge_candidate_data(candidates_psm_df, candidates_df, candidate_columns)
@@ -486,7 +512,7 @@ class CandidateScoring:
         data = {"precursor_idx": psm["precursor_idx"][cand], "rank": psm["rank"][cand]}
         for col in FRAGMENT_COLUMNS[2:]:
             data[col] = psm["fragment_" + col].reshape(-1)[rows]
-        df = pd.DataFrame(data)
+        df = pd.DataFrame(data, copy=False)  # the gathered columns are fresh arrays: no consolidation copy
         return merge_missing_columns(df, self.precursors_flat_df, ["elution_group_idx", "decoy"],
                                      on=["precursor_idx"], how="left")
 

@@ -225,3 +225,31 @@ def test_count_residues_equals_str_count():
     with_nan[5] = np.nan
     a, b = count_residues(with_nan, "K"), pd.Series(with_nan).str.count("K").values
     assert np.array_equal(np.isnan(a.astype(float)), np.isnan(b.astype(float))) and np.array_equal(a[:5], b[:5])
+
+
+def test_calculate_score_groups_equals_pandas_sort():
+    """The lexsort / already-sorted shortcut must reproduce the reference's two sort_values calls (scoring/utils.py:269-410)."""
+    import pandas as pd
+
+    from alphadia_b200.scoring import calculate_score_groups
+
+    def reference(df, group_channels):
+        df = df.sort_values(by=["elution_group_idx", "decoy", "rank", "precursor_idx"])
+        if group_channels:
+            eg, dc, rk = df["elution_group_idx"].values, df["decoy"].values, df["rank"].values
+            change = np.zeros(len(df), dtype=bool)
+            change[1:] = (eg[1:] != eg[:-1]) | (dc[1:] != dc[:-1]) | (rk[1:] != rk[:-1])
+            df["score_group_idx"] = np.cumsum(change).astype(np.uint32)
+        else:
+            df["score_group_idx"] = np.arange(len(df), dtype=np.uint32)
+        return df.sort_values(by=["score_group_idx", "precursor_idx"]).reset_index(drop=True)
+
+    rng = np.random.default_rng(2)
+    n = 5000
+    base = pd.DataFrame({"precursor_idx": rng.permutation(n).astype(np.uint32), "elution_group_idx": rng.integers(0, 900, n).astype(np.uint32),
+                         "decoy": rng.integers(0, 2, n).astype(np.uint8), "rank": rng.integers(0, 3, n).astype(np.uint8),
+                         "x": rng.normal(size=n)})
+    already = base.sort_values(by=["elution_group_idx", "decoy", "rank", "precursor_idx"]).reset_index(drop=True)
+    for df in (base, already, base.iloc[:1], base.iloc[:0]):
+        for gc in (False, True):
+            pd.testing.assert_frame_equal(calculate_score_groups(df.copy(), group_channels=gc), reference(df.copy(), gc))
