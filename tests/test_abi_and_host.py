@@ -39,6 +39,8 @@ def test_struct_sizes_match_header(built_lib):
     from alphadia_b200 import _abi
 
     assert C.sizeof(_abi.RawFile3DDesc) == 15 * 8
+    assert C.sizeof(_abi.RawFile4DDesc) == 17 * 8
+    assert C.sizeof(_abi.CandidateTable) == 11 * 8
     assert C.sizeof(_abi.LibraryDesc) == 8 + 8 * 8 + 8 + 8 + 9 * 8
     assert C.sizeof(_abi.CandidatesOut) == 10 * 8
     assert C.sizeof(_abi.CandidatesIn) == 9 * 8
@@ -63,6 +65,8 @@ def test_no_cpu_fallback(built_lib):
         sel()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         built_lib.fragment_competition([0], [1], np.zeros(1, np.float32), [0], [1], np.ones(1, np.float32), 3.0, 15.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        built_lib.transpose_csr(np.zeros(1, np.uint32), np.array([0, 1], np.int64), 4, np.ones(1, np.uint16))
     assert FragmentCompetition is not None
 
 
