@@ -257,3 +257,22 @@ def test_calculate_score_groups_equals_pandas_sort():
     for df in (base, already, base.iloc[:1], base.iloc[:0]):
         for gc in (False, True):
             pd.testing.assert_frame_equal(calculate_score_groups(df.copy(), group_channels=gc), reference(df.copy(), gc))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs without a GPU and prints one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "config1",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "precursor candidates scored/sec" and d["unit"] == "candidates/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
