@@ -689,10 +689,15 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
     return twice(dfi[(fidx * nobs + o) * C + c]);
   };
   // fragments_frame_profile.sum(axis=1)
+  // with several observations every lane sums its row once into the second F x C block of the (dead) m/z channel
+  float* isl_rows = dfm + F * C;  // valid when nobs >= 2: nFC >= 2 F C, and nrm only uses the first block
+  if (cfg.experimental_xic && nobs > 1 && act)
+    _Pragma("unroll 1") for (int c = 0; c < C; c++)
+      isl_rows[lane * C + c] = frame_profile_obs_sum(dfi + f * nobs * C, bp + lane * C, nobs, C, c, quant_all ? -1 : best_obs);
   auto isl = [&](int w, int fidx, int c) -> float {
     if (nobs == 1)  // single observation: 0 + x == x exactly, no call
       return quant_all ? twice(dfi[fidx * C + c]) : bp[w * C + c];
-    return frame_profile_obs_sum(dfi + fidx * nobs * C, bp + w * C, nobs, C, c, quant_all ? -1 : best_obs);
+    return isl_rows[w * C + c];
   };
   if (cfg.experimental_xic) {
     int a0 = center - 1, a1 = center + 2;  // scoring_utils.py:100-110 python slice semantics
