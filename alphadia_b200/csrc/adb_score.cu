@@ -835,14 +835,16 @@ __device__ void score_one_body(const ScoreParams& P, int64_t ci, const cg::threa
       sm.frame_peak[lane] = am;
     }
     tile.sync();
-    if (lane == 0) {  // median frame peak of this observation (profile_features.py:193-204)
-      double vlo = 0, vhi = 0;
-      _Pragma("unroll 1") for (int w = 0; w < Fv; w++) {
-        int v = sm.frame_peak[w], rk = 0;
-        _Pragma("unroll 1") for (int u = 0; u < Fv; u++) rk += (sm.frame_peak[u] < v) || (sm.frame_peak[u] == v && u < w);
-        if (rk == (Fv - 1) / 2) vlo = (double)v;
-        if (rk == Fv / 2) vhi = (double)v;
-      }
+    if (act) {  // median frame peak of this observation (profile_features.py:193-204): every lane ranks its own value
+      const int v = sm.frame_peak[lane];
+      int rk = 0;
+      _Pragma("unroll 1") for (int u = 0; u < Fv; u++) rk += (sm.frame_peak[u] < v) || (sm.frame_peak[u] == v && u < lane);
+      if (rk == (Fv - 1) / 2) sm.t_sel[0] = v;  // ranks are a permutation: exactly one lane holds each order statistic
+      if (rk == Fv / 2) sm.t_sel[1] = v;
+    }
+    tile.sync();
+    if (lane == 0) {
+      const double vlo = (double)sm.t_sel[0], vhi = (double)sm.t_sel[1];
       float medp = (float)((Fv & 1) ? vhi : (vlo + vhi) / 2);
       double delta = (double)medp - floor((double)C / 2);
       double prev = (o == 0) ? 0.0 : sm.esc[0];
