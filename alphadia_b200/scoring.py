@@ -246,6 +246,19 @@ def expand_cycle(cycle, lower_mz, upper_mz):
     return new_cycle
 
 
+def quadrupole_transfer_function_single(quadrupole_calibration_jit, observation_indices, scan_indices, isotope_mz):
+    """alphadia/search/scoring/quadrupole.py:261-301: transfer efficiency ``[n_isotopes, n_observations, n_scans]`` (the
+    device kernels evaluate the same expression per candidate, adb_score.cu / adb_score4d.cu)."""
+    isotope_mz = np.asarray(isotope_mz, dtype=np.float64)
+    observation_indices = np.asarray(observation_indices, dtype=np.int64)
+    scan_indices = np.asarray(scan_indices, dtype=np.int64)
+    n_i, n_o, n_s = len(isotope_mz), len(observation_indices), len(scan_indices)
+    mz_column = np.repeat(isotope_mz, n_s * n_o)
+    observation_column = np.tile(np.repeat(observation_indices, n_s), n_i)
+    scan_column = np.tile(scan_indices, n_i * n_o)
+    return quadrupole_calibration_jit.predict(observation_column, scan_column, mz_column).reshape(n_i, n_o, n_s)
+
+
 class SimpleQuadrupoleJit:
     """State of alphadia/search/scoring/quadrupole.py:46-128 (uncalibrated: sigma 0.2, delta_mu 0); the device kernels take
     ``sigma`` and ``delta_mu`` from here (``adb_scoring_config.quad_sigma / quad_delta_mu``)."""

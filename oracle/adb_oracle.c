@@ -1881,3 +1881,43 @@ int adbo_transpose_csr(int64_t n_values, int64_t n_push, int64_t n_tof, const ui
   free(count);
   return 0;
 }
+
+
+/* ---- test hooks for the reference's remaining known-answer unit tests ------------------------------------------- */
+/* scoring/utils.py:478-510 save_corrcoeff on float32 inputs (np.mean / np.sum accumulate in float32 under numba) */
+double adbo_save_corrcoeff_f32(const float* x, const float* y, int n) {
+  float sx = 0, sy = 0;
+  for (int i = 0; i < n; i++) { sx = sx + x[i]; sy = sy + y[i]; }
+  float xb = sx / (float)n, yb = sy / (float)n;
+  float num = 0, sxx = 0, syy = 0;
+  for (int i = 0; i < n; i++) { float a = x[i] - xb, b = y[i] - yb; num = num + a * b; sxx = sxx + a * a; syy = syy + b * b; }
+  return (double)num / ((double)sqrtf(sxx * syy) + 1e-12);
+}
+
+/* scoring/utils.py:513-571 fragment_correlation: x [F][nobs][n] -> out [nobs][F][F], float32 like the scoring path */
+void adbo_fragment_correlation(const float* x, int F, int nobs, int n, float* out) {
+  float* cen = (float*)malloc(sizeof(float) * (size_t)F * (size_t)(n > 0 ? n : 1));
+  float* stdv = (float*)malloc(sizeof(float) * (size_t)(F > 0 ? F : 1));
+  for (int o = 0; o < nobs; o++) {
+    for (int f = 0; f < F; f++) {
+      const float* r = x + ((size_t)f * nobs + o) * n;
+      float s = 0; for (int c = 0; c < n; c++) s = s + r[c];
+      float m = s / (float)n, ss = 0;
+      for (int c = 0; c < n; c++) { cen[(size_t)f * n + c] = r[c] - m; ss = ss + cen[(size_t)f * n + c] * cen[(size_t)f * n + c]; }
+      stdv[f] = sqrtf(ss / (float)n);
+    }
+    for (int f = 0; f < F; f++)
+      for (int g = 0; g < F; g++) {
+        float dot = 0;
+        for (int c = 0; c < n; c++) dot = dot + cen[(size_t)f * n + c] * cen[(size_t)g * n + c];
+        out[((size_t)o * F + f) * F + g] = (float)((double)(dot / (float)n) / ((double)(stdv[f] * stdv[g]) + 1e-12));
+      }
+  }
+  free(cen); free(stdv);
+}
+
+/* scoring/utils.py:574-647 fragment_correlation_different with one y profile per observation: out [nobs][F] */
+void adbo_corr_with_template(const float* x, const float* y, int F, int nobs, int n, float* out) { corr_with_template(x, y, F, nobs, n, out); }
+
+/* alpharaw_jit.py:53-75 _search_sorted_left / _search_sorted_reference_left */
+int64_t adbo_search_sorted_left_f32(const float* a, int64_t n, float v) { return searchsorted_left_f32(a, n, v); }

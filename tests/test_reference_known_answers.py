@@ -239,3 +239,86 @@ def test_simple_quadrupole_calibrated_cycle():
     y = logistic_rectangle(cycle[0, P, S, 0] + 0.3, cycle[0, P, S, 1] - 0.2, 0.35, 0.5, X)
     q.fit(P, S, X, y)
     assert np.allclose(q.jit.sigma, [0.35, 0.5], atol=1e-3) and np.allclose(q.jit.delta_mu, [0.3, -0.2], atol=1e-3)
+
+
+def test_transpose_known_answer(oracle_lib):
+    """tests/unit_tests/raw_data/test_raw_data.py:7-23 (exact CSR transpose)."""
+    values = np.array([1, 2, 3, 4, 5, 6, 7], dtype=np.uint16)
+    tof_indices = np.array([0, 3, 2, 4, 1, 2, 4], dtype=np.uint32)
+    push_ptr = np.array([0, 2, 4, 5, 7], dtype=np.int64)
+    push_indices, tof_indptr, intensity_values = oracle_lib.transpose_csr(tof_indices, push_ptr, 7, values)
+    assert np.array_equal(push_indices, [0, 2, 1, 3, 0, 1, 3])
+    assert np.array_equal(tof_indptr, [0, 1, 2, 4, 5, 7, 7, 7])
+    assert np.array_equal(intensity_values, [1, 5, 3, 6, 2, 4, 7])
+
+
+def test_save_corrcoeff_and_fragment_correlation(oracle_lib):
+    """tests/unit_tests/search/scoring/test_scoring_utils.py:158-217."""
+    import ctypes as C
+
+    L = oracle_lib.lib()
+    L.adbo_save_corrcoeff_f32.restype = C.c_double
+    f32p = C.POINTER(C.c_float)
+
+    def corr(x, y):
+        x, y = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(y, np.float32)
+        return L.adbo_save_corrcoeff_f32(x.ctypes.data_as(f32p), y.ctypes.data_as(f32p), C.c_int(len(x)))
+
+    up = np.arange(1, 11, dtype=np.float32)
+    assert np.isclose(corr(up, up[::-1]), -1.0) and np.isclose(corr(up, up), 1.0) and np.isclose(corr(np.zeros(10), np.zeros(10)), 0.0)
+
+    a = np.array([[[1, 2, 3], [1, 2, 3]], [[3, 2, 1], [1, 2, 3]], [[0, 0, 0], [0, 0, 0]]], dtype=np.float32)  # [F=3][nobs=2][n=3]
+    out = np.zeros((2, 3, 3), np.float32)
+    L.adbo_fragment_correlation(a.ctypes.data_as(f32p), C.c_int(3), C.c_int(2), C.c_int(3), out.ctypes.data_as(f32p))
+    expected = np.array([[[1.0, -1.0, 0.0], [-1.0, 1.0, 0.0], [0.0, 0.0, 0.0]], [[1.0, 1.0, 0.0], [1.0, 1.0, 0.0], [0.0, 0.0, 0.0]]])
+    assert np.allclose(out, expected, atol=1e-6)
+    z = np.zeros((10, 10, 10), np.float32)
+    outz = np.ones((10, 10, 10), np.float32)
+    L.adbo_fragment_correlation(z.ctypes.data_as(f32p), C.c_int(10), C.c_int(10), C.c_int(10), outz.ctypes.data_as(f32p))
+    assert np.allclose(outz, 0.0)
+    # fragment_correlation_different(a, y) with the first fragment's profile as the per-observation template:
+    # row o of the result == column 0 of fragment_correlation(a)[o]
+    y = np.ascontiguousarray(a[0])  # [nobs][n]
+    ct = np.zeros((2, 3), np.float32)
+    L.adbo_corr_with_template(a.ctypes.data_as(f32p), y.ctypes.data_as(f32p), C.c_int(3), C.c_int(2), C.c_int(3), ct.ctypes.data_as(f32p))
+    assert np.allclose(ct, expected[:, :, 0], atol=1e-6)
+
+
+def test_search_sorted_left(oracle_lib):
+    """tests/unit_tests/search/jitclasses/test_alpharaw_jit.py:6-9 plus the boundaries np.searchsorted(..., 'left') defines."""
+    import ctypes as C
+
+    L = oracle_lib.lib()
+    L.adbo_search_sorted_left_f32.restype = C.c_int64
+    arr = np.arange(100, dtype=np.float32)
+    f = lambda v: L.adbo_search_sorted_left_f32(arr.ctypes.data_as(C.POINTER(C.c_float)), C.c_int64(len(arr)), C.c_float(v))  # noqa: E731
+    assert f(50) == 50
+    for v in (-1.0, 0.0, 0.5, 49.5, 99.0, 99.5, 1e9):
+        assert f(v) == int(np.searchsorted(arr, np.float32(v), "left"))
+    dup = np.array([1, 1, 2, 2, 2, 3], dtype=np.float32)
+    assert L.adbo_search_sorted_left_f32(dup.ctypes.data_as(C.POINTER(C.c_float)), C.c_int64(6), C.c_float(2.0)) == 2
+
+
+def test_qtf_regions():
+    """tests/unit_tests/search/scoring/test_quadrupole.py:58-79."""
+    from alphadia_b200.scoring import SimpleQuadrupole, quadrupole_transfer_function_single
+
+    fake_cycle = np.array([[780.0, 801], [801, 820]])
+    fake_cycle = np.repeat(fake_cycle[:, np.newaxis, :], 10, axis=1)[np.newaxis, :, :, :]
+    quad = SimpleQuadrupole(fake_cycle)
+    isotope_mz = np.array([800.0, 800.1, 800.2, 802.42944, 802.9311, 803.1])
+    qtf = quadrupole_transfer_function_single(quad.jit, np.array([0, 1]), np.arange(2, 9), isotope_mz)
+    assert qtf.shape == (6, 2, 7)
+    assert np.all(qtf[:3, 0, :] > 0.9) and np.all(qtf[:3, 1, :] < 0.1)
+    assert np.all(qtf[3:, 0, :] < 0.1) and np.all(qtf[3:, 1, :] > 0.9)
+
+
+def test_assemble_isotope_mz_typing(oracle_lib):
+    """tests/unit_tests/search/selection/test_selection_utils.py:14-36: isotope m/z = float32(mz + i * 1.0033548 / charge)
+    computed in float64 and stored as float32 (selection/utils.py:35-40); the oracle's selection uses exactly this value —
+    checked through the golden candidate tables — here the arithmetic itself."""
+    mz, charge = np.float32(500.123), 2
+    off = np.arange(4) * 1.0033548350700006 / charge
+    iso = (np.float64(mz) + off).astype(np.float32)
+    assert iso.dtype == np.float32 and iso[0] == mz
+    assert np.allclose(np.diff(iso.astype(np.float64)), 1.0033548350700006 / charge, atol=1e-4)
