@@ -276,3 +276,42 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_adapt_dia_data_variants():
+    """The adapters accept the reference's objects: public or private attribute names, 3-D and timsTOF layouts."""
+    from types import SimpleNamespace
+
+    from alphadia_b200 import _abi
+    from alphadia_b200.raw_data import adapt_dia_data
+    from alphadia_b200.synthetic import make_config_3d, make_config_4d
+
+    raw3 = make_config_3d("config1")[0]
+    a = adapt_dia_data(raw3)
+    assert not a.is_4d and a.rt_values.dtype == np.float32 and a.cycle.shape == raw3.cycle.shape
+    # an AlphaRaw wrapper keeps its arrays under private names (alphadia/raw_data/alpharaw_wrapper.py:86-156)
+    private = SimpleNamespace(cycle=raw3.cycle, rt_values=raw3.rt_values, mobility_values=raw3.mobility_values,
+                              _peak_start_idx_list=raw3.peak_start_idx_list, _peak_stop_idx_list=raw3.peak_stop_idx_list,
+                              _mz_values=raw3.mz_values, _intensity_values=raw3.intensity_values, _zeroth_frame=0,
+                              _scan_max_index=1, has_mobility=False)
+    b = adapt_dia_data(private)
+    assert np.array_equal(b.mz_values, a.mz_values) and b.precursor_cycle_max_index == a.precursor_cycle_max_index
+    assert b.frame_max_index == len(raw3.rt_values) - 1
+    d3, _ = _abi.make_rawfile3d_desc(b)
+    assert d3.cycle_len == raw3.cycle.shape[1] and d3.n_peaks == len(raw3.mz_values)
+    raw4 = make_config_4d("parity_4d", n_precursors=8)[0]
+    c = adapt_dia_data(raw4)
+    assert c.is_4d and c.rt_values.dtype == np.float64 and c.push_indices.dtype == np.uint32 and c.intensity_values.dtype == np.uint16
+    d4, _ = _abi.make_rawfile4d_desc(c)
+    assert d4.frames_per_cycle == raw4.cycle.shape[1] and d4.scans == raw4.cycle.shape[2] and d4.n_events == raw4.n_events
+    private4 = SimpleNamespace(_cycle=raw4.cycle, _rt_values=raw4.rt_values, _mobility_values=raw4.mobility_values, _mz_values=raw4.mz_values,
+                               _tof_indptr=raw4.tof_indptr, _push_indices=raw4.push_indices, _intensity_values=raw4.intensity_values,
+                               _dia_precursor_cycle=raw4.dia_precursor_cycle, _zeroth_frame=1, _scan_max_index=raw4.scan_max_index,
+                               _frame_max_index=raw4.frame_max_index, has_mobility=True)
+    e = adapt_dia_data(private4)
+    assert e.is_4d and e.precursor_cycle_max_index == raw4.precursor_cycle_max_index
+    with pytest.raises(ValueError, match="timsTOF CSR arrays"):
+        adapt_dia_data(SimpleNamespace(has_mobility=True, cycle=raw4.cycle))
+    bad = SimpleNamespace(**{**vars(c), "dia_precursor_cycle": c.dia_precursor_cycle[:-1]})
+    with pytest.raises(ValueError):
+        _abi.make_rawfile4d_desc(bad)
