@@ -291,7 +291,9 @@ __global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn c
   const int64_t L = raw.cycle_len;
   const uint64_t bucket = fs < 0 ? 0ull : (uint64_t)min((long long)(fs / (L * 32)), 0xFFFFFFLL);
   const long long cyc = max((long long)(fe / L - fs / L), 0LL);
-  const uint64_t cost = (uint64_t)min(cyc * (long long)max(nobs, 1), 255LL);
+  // cost class = (observations, cycles): the two candidates that share a warp and the tiles of a lock-step round then
+  // run loops of identical trip counts (less divergence than sorting by the product)
+  const uint64_t cost = ((uint64_t)min(max(nobs, 1), 3) << 6) | (uint64_t)min(cyc, 63LL);
   keys[i] = ((uint64_t)(i / chunk_len) << 48) | ((uint64_t)win << 32) | (bucket << 8) | cost;
   vals[i] = (int32_t)i;
 }
