@@ -15,6 +15,8 @@ its checks (duplicate precursor in a score group, missing reference channel) are
 from __future__ import annotations
 
 import logging
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import pandas as pd
@@ -183,6 +185,16 @@ def count_residues(sequences, residues) -> list:
     points = fixed.view(np.uint32).reshape(len(fixed), width)
     out = [(points == ord(r)).sum(axis=1).astype(np.int64)[codes] for r in res]
     return out[0] if single else out
+
+
+def _run_column_tasks(tasks: dict, n_rows: int) -> dict:
+    """Evaluate ``{column: (function, array)}`` and keep the column order; large tables use a small thread pool."""
+    if n_rows < (1 << 20) or len(tasks) < 2:
+        return {c: f(a) for c, (f, a) in tasks.items()}
+    workers = min(8, len(tasks), os.cpu_count() or 1)
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        futures = {c: pool.submit(f, a) for c, (f, a) in tasks.items()}
+        return {c: fut.result() for c, fut in futures.items()}
 
 
 def _sorted_by(df: pd.DataFrame, by) -> pd.DataFrame:
@@ -519,15 +531,43 @@ class CandidateScoring:
         return merge_missing_columns(df, precursors_flat_df, precursor_df_columns, on=["precursor_idx"], how="left")
 
     def collect_fragments(self, candidates_df, psm) -> pd.DataFrame:
-        rows = np.flatnonzero(psm["fragment_mz_library"].reshape(-1) > 0)  # output.py:72-90, as one gather index
-        top_k = psm["fragment_mz_library"].shape[1]
-        cand = rows // top_k
-        data = {"precursor_idx": psm["precursor_idx"][cand], "rank": psm["rank"][cand]}
+        """output.py:72-90 + scoring.py:520-580: one row per fragment slot with ``mz_library > 0``.  The slot mask is
+        applied column by column on a few threads (numpy releases the GIL inside the gathers), candidate-level columns
+        are expanded with per-candidate slot counts, and ``elution_group_idx`` / ``decoy`` are looked up once per
+        candidate instead of once per fragment row."""
+        lib_mz = psm["fragment_mz_library"]
+        n, top_k = lib_mz.shape
+        mask = lib_mz.reshape(-1) > 0
+        n_rows = int(np.count_nonzero(mask))
+        if n_rows == mask.size:  # every slot filled: the flat arrays are the columns
+            def slots(a):
+                return a.reshape(-1)
+
+            def per_candidate(a):
+                return np.repeat(a, top_k)
+        else:
+            counts = np.count_nonzero(mask.reshape(n, top_k), axis=1)
+
+            def slots(a):
+                return a.reshape(-1)[mask]
+
+            def per_candidate(a):
+                return np.repeat(a, counts)
+
+        tasks = {"precursor_idx": (per_candidate, psm["precursor_idx"]), "rank": (per_candidate, psm["rank"])}
         for col in FRAGMENT_COLUMNS[2:]:
-            data[col] = psm["fragment_" + col].reshape(-1)[rows]
-        df = pd.DataFrame(data, copy=False)  # the gathered columns are fresh arrays: no consolidation copy
-        return merge_missing_columns(df, self.precursors_flat_df, ["elution_group_idx", "decoy"],
-                                     on=["precursor_idx"], how="left")
+            tasks[col] = (slots, psm["fragment_" + col])
+        right_columns = ["elution_group_idx", "decoy"]
+        per_cand_df = merge_missing_columns(pd.DataFrame({"precursor_idx": psm["precursor_idx"]}), self.precursors_flat_df,
+                                            right_columns, on=["precursor_idx"], how="left")
+        lookup_per_candidate = len(per_cand_df) == n  # False only if precursors_flat repeats a precursor_idx
+        if lookup_per_candidate:
+            for col in right_columns:
+                tasks[col] = (per_candidate, per_cand_df[col].values)
+        df = pd.DataFrame(_run_column_tasks(tasks, n_rows), copy=False)  # fresh arrays: no consolidation copy
+        if lookup_per_candidate:
+            return df
+        return merge_missing_columns(df, self.precursors_flat_df, right_columns, on=["precursor_idx"], how="left")
 
     # ---- call ----------------------------------------------------------------------------------
     def __call__(self, candidates_df, thread_count=10, debug=False, include_decoy_fragment_features=False):

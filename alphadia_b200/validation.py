@@ -56,10 +56,27 @@ class Schema:
 
     @staticmethod
     def _warn_on_critical_values(df: pd.DataFrame) -> None:
+        """validation/base.py:120-152 (NaN / Inf counts per float column).  ``sum`` is finite only if every element is,
+        so the common all-finite case costs one read and no temporary; columns that are strided views into one shared
+        2-D array (a feature matrix wrapped in a DataFrame) are cleared by a single pass over that array."""
+        floats = []
         for col in df.columns:
-            if isinstance(df[col].dtype, np.dtype) and np.issubdtype(df[col].dtype, np.floating):  # extension dtypes (str) are skipped
-                v = df[col].values
-                if np.isfinite(v).all():  # the common case costs one pass
+            dtype = df[col].dtype
+            if isinstance(dtype, np.dtype) and np.issubdtype(dtype, np.floating):  # extension dtypes (str) are skipped
+                floats.append((col, df[col].values))
+        shared: dict = {}
+        for _, v in floats:
+            base = v.base
+            if isinstance(base, np.ndarray) and base.dtype == v.dtype and not v.flags.c_contiguous:
+                entry = shared.setdefault(id(base), [base, 0])
+                entry[1] += 1
+        finite_bases = set()
+        with np.errstate(over="ignore", invalid="ignore"):
+            for key, (base, n_cols) in shared.items():
+                if base.size <= 2 * n_cols * max(len(df), 1) and np.isfinite(base.sum()):
+                    finite_bases.add(key)
+            for col, v in floats:
+                if id(v.base) in finite_bases or np.isfinite(v.sum()):
                     continue
                 n_nan = int(np.isnan(v).sum())
                 n_inf = int(np.isinf(v).sum())

@@ -192,4 +192,4 @@ if __name__ == "__main__":
         if n == "transpose":
             run_transpose()
         else:
-            run(n, threads, variants=(n == "parity_small"))
+            run(n, threads, variants=(n in ("parity_small", "parity_4d")))

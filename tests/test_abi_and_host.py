@@ -259,6 +259,84 @@ def test_calculate_score_groups_equals_pandas_sort():
             pd.testing.assert_frame_equal(calculate_score_groups(df.copy(), group_channels=gc), reference(df.copy(), gc))
 
 
+def test_collect_fragments_equals_mask_gather_and_merge():
+    """collect_fragments (threaded column gathers, per-candidate lookup) == the reference's flat mask + merge
+    (output.py:72-90, scoring.py:520-580) for ragged, full, empty and duplicated-library cases."""
+    import pandas as pd
+
+    from alphadia_b200 import _abi
+    from alphadia_b200.scoring import FRAGMENT_COLUMNS, CandidateScoring
+    from tests import helpers as H
+
+    raw, pdf, fdf, lib, p = H.workload("config1")
+    op = CandidateScoring(dia_data=raw, precursors_flat=pdf, fragments_flat=fdf, rt_column="rt_library",
+                          mobility_column="mobility_library", precursor_mz_column="mz_library", fragment_mz_column="mz_library")
+
+    def reference(psm, precursors):
+        mask = psm["fragment_mz_library"].reshape(-1) > 0
+        top_k = psm["fragment_mz_library"].shape[1]
+        data = {"precursor_idx": np.repeat(psm["precursor_idx"], top_k)[mask], "rank": np.repeat(psm["rank"], top_k)[mask]}
+        for col in FRAGMENT_COLUMNS[2:]:
+            data[col] = psm["fragment_" + col].reshape(-1)[mask]
+        return pd.DataFrame(data).merge(precursors[["precursor_idx", "elution_group_idx", "decoy"]], on=["precursor_idx"], how="left")
+
+    def make_psm(n, top_k, fill, seed):
+        rng = np.random.default_rng(seed)
+        _, psm = _abi.alloc_scores_out(n, top_k)
+        for k, v in psm.items():
+            if k.startswith("fragment_"):
+                v[:] = rng.integers(1, 200, v.shape).astype(v.dtype)
+        psm["fragment_mz_library"][rng.random((n, top_k)) >= fill] = 0
+        if n > 3:
+            psm["fragment_mz_library"][n // 2] = 0  # a candidate without any row
+        psm["precursor_idx"] = rng.integers(0, len(pdf), n).astype(np.uint32)
+        psm["rank"] = rng.integers(0, 3, n).astype(np.uint8)
+        return psm
+
+    for n, top_k, fill in [(500, 12, 0.7), (500, 12, 1.1), (40, 6, 0.0), (0, 12, 0.5), (1, 12, 0.5), (100_000, 12, 0.9)]:
+        psm = make_psm(n, top_k, fill, seed=n + top_k)
+        if fill > 1:
+            psm["fragment_mz_library"][:] = 1.0
+        got, ref = op.collect_fragments(None, psm), reference(psm, op.precursors_flat_df)
+        pd.testing.assert_frame_equal(got, ref)
+        assert list(got.columns) == FRAGMENT_COLUMNS + ["elution_group_idx", "decoy"]
+    # a library that repeats a precursor_idx multiplies rows in the reference's merge: same here
+    dup = pd.concat([op.precursors_flat_df, op.precursors_flat_df.iloc[:3]], ignore_index=True)
+    op._precursors_flat_df = dup
+    psm = make_psm(300, 12, 0.5, seed=9)
+    psm["precursor_idx"][:50] = dup["precursor_idx"].values[0]
+    pd.testing.assert_frame_equal(op.collect_fragments(None, psm), reference(psm, dup))
+
+
+def test_warn_on_critical_values_counts(caplog):
+    """NaN / Inf warnings per float column (validation/base.py:120-152), also for strided views of one shared matrix."""
+    import logging
+
+    import pandas as pd
+
+    from alphadia_b200.validation import Schema
+
+    m = np.ones((1000, 5), dtype=np.float32)
+    m[3, 1] = np.nan
+    m[4:6, 1] = np.inf
+    m[7, 4] = -np.inf
+    df = pd.DataFrame(m, columns=list("abcde"), copy=False)
+    df["f"] = np.full(1000, 3.0e38, dtype=np.float32)  # finite values whose f32 sum overflows: no warning
+    df["g"] = np.arange(1000)
+    df["h"] = pd.Series(["x"] * 1000, dtype=object)
+    with caplog.at_level(logging.WARNING):
+        Schema._warn_on_critical_values(df)
+    msgs = [r.getMessage() for r in caplog.records]
+    assert sum("b has 1 NaNs" in x for x in msgs) == 1 and sum("b has 2 Infs" in x for x in msgs) == 1
+    assert sum("e has 1 Infs" in x for x in msgs) == 1 and len(msgs) == 3
+    caplog.clear()
+    clean = pd.DataFrame(np.ones((1000, 5), dtype=np.float32), columns=list("abcde"), copy=False)
+    with caplog.at_level(logging.WARNING):
+        Schema._warn_on_critical_values(clean)
+        Schema._warn_on_critical_values(clean.iloc[:0])
+    assert not caplog.records
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` runs without a GPU and prints one JSON line with the contract's keys."""
     import json

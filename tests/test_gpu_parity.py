@@ -130,25 +130,37 @@ def test_scoring_matches_oracle(engine, oracle_lib, name, variant):
     dlib.close(); draw.close()
 
 
-def test_scoring_matches_reference_golden(engine):
-    name = "parity_small"
+GOLDEN_TAGS = {"": "default", "_legacy": "legacy", "_k6": "k6"}
+
+
+def _check_scores_against_golden(engine, name, tag):
     g = H.load_golden(name)
     raw, pdf, fdf, lib, p = H.workload(name)
-    if g is None or str(g["input_checksum"]) != H.input_checksum(raw, pdf, fdf):
+    if g is None or str(g["input_checksum"]) != H.input_checksum(raw, pdf, fdf) or f"feat{tag}_matrix" not in g:
         pytest.skip("golden not applicable")
     draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
     cand = {c: g["cand_" + c] for c in INT_COLS}
     cin, keep = H.candidates_in_from_arrays(lib, cand)
-    got = engine.score_candidates(draw, dlib, H.scoring_config().to_struct(), cin)
+    cfg = H.scoring_config(**SCORING_VARIANTS[GOLDEN_TAGS[tag]]).to_struct()
+    got = engine.score_candidates(draw, dlib, cfg, cin)
     v = got["valid"].astype(bool)
-    assert np.array_equal(keep["precursor_idx"][v], g["feat_precursor_idx"])
-    assert np.array_equal(keep["rank"][v], g["feat_rank"])
-    F, G = got["features"][v], g["feat_matrix"]
+    assert np.array_equal(keep["precursor_idx"][v], g[f"feat{tag}_precursor_idx"])
+    assert np.array_equal(keep["rank"][v], g[f"feat{tag}_rank"])
+    F, G = got["features"][v], g[f"feat{tag}_matrix"]
     floor = feature_scale_floor(G)
     err = np.abs(F - G) / np.maximum(np.maximum(np.abs(F), np.abs(G)), floor[None, :])
     err = np.where(np.isnan(F) & np.isnan(G), 0.0, err)
     assert err.max() < RTOL
+    m = got["fragment_mz_library"] > 0
+    assert m.sum() == len(g[f"frag{tag}_mz_library"])
+    assert np.array_equal(got["fragment_mz_library"][m], g[f"frag{tag}_mz_library"])
+    assert np.array_equal(got["fragment_number"][m], g[f"frag{tag}_number"])
     dlib.close(); draw.close()
+
+
+@pytest.mark.parametrize("tag", list(GOLDEN_TAGS))
+def test_scoring_matches_reference_golden(engine, tag):
+    _check_scores_against_golden(engine, "parity_small", tag)
 
 
 def test_scoring_edge_cases(engine, oracle_lib):
@@ -344,25 +356,9 @@ def test_scoring_4d_matches_oracle(engine, oracle_lib, variant):
     dlib.close(); draw.close()
 
 
-def test_scoring_4d_matches_reference_golden(engine):
-    name = "parity_4d"
-    g = H.load_golden(name)
-    raw, pdf, fdf, lib, p = H.workload(name)
-    if g is None or str(g["input_checksum"]) != H.input_checksum(raw, pdf, fdf):
-        pytest.skip("golden not applicable")
-    draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
-    cand = {c: g["cand_" + c] for c in INT_COLS}
-    cin, keep = H.candidates_in_from_arrays(lib, cand)
-    got = engine.score_candidates(draw, dlib, H.scoring_config().to_struct(), cin)
-    v = got["valid"].astype(bool)
-    assert np.array_equal(keep["precursor_idx"][v], g["feat_precursor_idx"])
-    assert np.array_equal(keep["rank"][v], g["feat_rank"])
-    F, G = got["features"][v], g["feat_matrix"]
-    floor = feature_scale_floor(G)
-    err = np.abs(F - G) / np.maximum(np.maximum(np.abs(F), np.abs(G)), floor[None, :])
-    err = np.where(np.isnan(F) & np.isnan(G), 0.0, err)
-    assert err.max() < RTOL
-    dlib.close(); draw.close()
+@pytest.mark.parametrize("tag", list(GOLDEN_TAGS))
+def test_scoring_4d_matches_reference_golden(engine, tag):
+    _check_scores_against_golden(engine, "parity_4d", tag)
 
 
 def test_scoring_4d_edge_cases(engine, oracle_lib):

@@ -119,15 +119,18 @@ def test_selection_4d_bit_exact_vs_reference(oracle_lib):
     assert (g["cand_scan_stop"] - g["cand_scan_start"]).max() > 8
 
 
-def test_scoring_4d_vs_reference(oracle_lib):
+@pytest.mark.parametrize("tag", ["", "_legacy", "_k6"])
+def test_scoring_4d_vs_reference(tag, oracle_lib):
     g, raw, lib, p = _golden("parity_4d")
+    if f"feat{tag}_matrix" not in g:
+        pytest.skip(f"golden parity_4d has no {tag} variant")
     cand = {c: g["cand_" + c] for c in INT_COLS}
     cin, keep = H.candidates_in_from_arrays(lib, cand)
-    arrs = oracle_lib.score_candidates_4d(raw, lib, H.scoring_config().to_struct(), cin)
+    arrs = oracle_lib.score_candidates_4d(raw, lib, H.scoring_config(**VARIANTS[tag]).to_struct(), cin)
     v = arrs["valid"].astype(bool)
-    assert np.array_equal(keep["precursor_idx"][v], g["feat_precursor_idx"])
-    assert np.array_equal(keep["rank"][v], g["feat_rank"])
-    F, G = arrs["features"][v], g["feat_matrix"]
+    assert np.array_equal(keep["precursor_idx"][v], g[f"feat{tag}_precursor_idx"])
+    assert np.array_equal(keep["rank"][v], g[f"feat{tag}_rank"])
+    F, G = arrs["features"][v], g[f"feat{tag}_matrix"]
     assert np.abs(G[:, 29]).max() > 0 and np.abs(G[:, 39]).max() > 0  # mobility features are live
     for j in range(46):
         same = (F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))
@@ -136,9 +139,9 @@ def test_scoring_4d_vs_reference(oracle_lib):
         else:
             assert same.all(), f"feature {j} not bit-exact"
     m = arrs["fragment_mz_library"] > 0
-    assert m.sum() == len(g["frag_mz_library"])
+    assert m.sum() == len(g[f"frag{tag}_mz_library"])
     for k, v2 in FRAG_MAP.items():
-        a, b = arrs[v2][m], g[f"frag_{k}"]
+        a, b = arrs[v2][m], g[f"frag{tag}_{k}"]
         assert np.array_equal(a, b) if k != "correlation" else H.rel_err(a, b).max() < 1e-4, k
 
 
