@@ -383,7 +383,7 @@ class CandidateScoring:
         quadrupole_calibration=None,
     ):
         self._dia_data = dia_data
-        self._raw = adapt_dia_data(dia_data)
+        self._raw_arrays = None  # adapted on first use, like the reference's dia_data.to_jitclass() (scoring.py:622)
 
         precursors_flat_schema.validate(precursors_flat, warn_on_critical_values=True)
         self.precursors_flat_df = precursors_flat
@@ -392,7 +392,7 @@ class CandidateScoring:
         self.fragments_flat = fragments_flat
 
         if quadrupole_calibration is None:
-            self.quadrupole_calibration = SimpleQuadrupole(self._raw.cycle)
+            self.quadrupole_calibration = SimpleQuadrupole(dia_data.cycle)  # scoring.py:210
         else:
             self.quadrupole_calibration = quadrupole_calibration
 
@@ -407,6 +407,12 @@ class CandidateScoring:
     @property
     def dia_data(self):
         return self._dia_data
+
+    @property
+    def _raw(self):
+        if self._raw_arrays is None:
+            self._raw_arrays = adapt_dia_data(self._dia_data)
+        return self._raw_arrays
 
     @property
     def precursors_flat_df(self) -> pd.DataFrame:
@@ -497,11 +503,17 @@ class CandidateScoring:
             candidate_columns = DEFAULT_CANDIDATE_COLUMNS.copy()
         if precursor_df_columns is None:
             precursor_df_columns = DEFAULT_PRECURSOR_COLUMNS.copy()
-        valid = psm["valid"].astype(bool)
-        features = psm["features"] if valid.all() else psm["features"][valid]
+        if hasattr(psm, "to_precursor_df"):  # an OutputPsmDF-like object (output.py:92-97), as the reference passes
+            precursor_idx, rank, features = psm.to_precursor_df()
+        else:  # the arrays adb_score_candidates filled
+            valid = psm["valid"].astype(bool)
+            if valid.all():
+                precursor_idx, rank, features = psm["precursor_idx"], psm["rank"], psm["features"]
+            else:
+                precursor_idx, rank, features = psm["precursor_idx"][valid], psm["rank"][valid], psm["features"][valid]
         candidates_psm_df = pd.DataFrame(features, columns=feature_columns, copy=False)  # one block, no second copy
-        candidates_psm_df["precursor_idx"] = psm["precursor_idx"][valid]
-        candidates_psm_df["rank"] = psm["rank"][valid]
+        candidates_psm_df["precursor_idx"] = precursor_idx
+        candidates_psm_df["rank"] = rank
         candidates_psm_df = self.merge_candidate_data(candidates_psm_df, candidates_df, candidate_columns)
         candidates_psm_df = self.merge_precursor_data(
             candidates_psm_df, self.precursors_flat_df, self.rt_column, self.mobility_column,

@@ -2,7 +2,7 @@
 allocates the output arrays, so that the pandas / numpy glue around ``adb_score_candidates`` can be profiled on a box
 without a GPU.  The numbers say nothing about the kernels.
 
-    python profiles/profile_host_glue.py [n_precursors] [--cprofile]
+    python profiles/profile_host_glue.py [n_precursors] [--valid-frac=0.6] [--cprofile]
 """
 
 from __future__ import annotations
@@ -31,6 +31,7 @@ class _Raw:
 
 def main():
     n_prec = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 500_000
+    valid_frac = float(next((a.split("=")[1] for a in sys.argv if a.startswith("--valid-frac=")), 1.0))
     rng = np.random.default_rng(0)
     pdf, fdf = make_library(n_prec, rng, quad_lo=400, quad_hi=1000, rt_lo=60, rt_hi=1100)
     n_cand = 3 * n_prec
@@ -46,9 +47,10 @@ def main():
 
     def fake_score(dev_raw, dev_lib, cfg, cin):
         _, arrs = _abi.alloc_scores_out(int(cin.n), int(cfg.top_k_fragments))
-        arrs["valid"][:] = 1
+        valid = np.random.default_rng(1).random(int(cin.n)) < valid_frac
+        arrs["valid"][:] = valid
         arrs["features"][:] = 1.0
-        arrs["fragment_mz_library"][:, :12] = 500.0
+        arrs["fragment_mz_library"][valid, :12] = 500.0
         return arrs
 
     class FakeLib:

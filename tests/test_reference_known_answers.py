@@ -322,3 +322,74 @@ def test_assemble_isotope_mz_typing(oracle_lib):
     iso = (np.float64(mz) + off).astype(np.float32)
     assert iso.dtype == np.float32 and iso[0] == mz
     assert np.allclose(np.diff(iso.astype(np.float64)), 1.0033548350700006 / charge, atol=1e-4)
+
+
+def test_collect_candidates_table():
+    """tests/unit_tests/search/scoring/test_scoring.py:110-221 — the boundary schema of the feature table: the 46 feature
+    columns in order, ids, candidate and precursor columns, delta_rt and residue counts.  Built like the reference's test:
+    mocked DiaData and quadrupole, an OutputPsmDF-like object handing over (precursor_idx, rank, features)."""
+    from unittest.mock import Mock
+
+    import pandas as pd
+
+    from alphadia_b200.config import CandidateScoringConfig
+    from alphadia_b200.scoring import DEFAULT_FEATURE_COLUMNS, CandidateScoring
+
+    precursors = pd.DataFrame({
+        "elution_group_idx": np.array([0, 1], dtype=np.uint32), "precursor_idx": np.array([0, 1], dtype=np.uint32),
+        "channel": np.array([0, 0], dtype=np.uint32), "decoy": np.array([0, 1], dtype=np.uint8),
+        "flat_frag_start_idx": np.array([0, 5], dtype=np.uint32), "flat_frag_stop_idx": np.array([5, 10], dtype=np.uint32),
+        "charge": np.array([2, 3], dtype=np.uint8), "rt_library": np.array([100.0, 200.0], dtype=np.float32),
+        "mobility_library": np.array([0.8, 0.9], dtype=np.float32), "mz_library": np.array([500.0, 600.0], dtype=np.float32),
+        "proteins": ["P1", "P2"], "genes": ["G1", "G2"], "sequence": ["PEPTIDEK", "ANOTHERR"], "mods": ["", ""],
+        "mod_sites": ["", ""], "i_0": np.array([1.0, 1.0], dtype=np.float32),
+    })
+    fragments = pd.DataFrame({
+        "mz_library": np.array([200.0, 300.0, 400.0], dtype=np.float32), "intensity": np.array([1000.0, 2000.0, 1500.0], dtype=np.float32),
+        "cardinality": np.array([1, 1, 1], dtype=np.uint8), "type": np.array([0, 1, 0], dtype=np.uint8),
+        "loss_type": np.array([0, 0, 0], dtype=np.uint8), "charge": np.array([1, 1, 2], dtype=np.uint8),
+        "number": np.array([1, 2, 3], dtype=np.uint8), "position": np.array([1, 2, 3], dtype=np.uint8),
+    })
+    dia_data = Mock()
+    dia_data.cycle = Mock()
+    quadrupole = Mock()
+    quadrupole.jit = Mock()
+    op = CandidateScoring(dia_data=dia_data, precursors_flat=precursors, fragments_flat=fragments, quadrupole_calibration=quadrupole,
+                          config=CandidateScoringConfig(), rt_column="rt_library", mobility_column="mobility_library",
+                          precursor_mz_column="mz_library", fragment_mz_column="mz_library")
+    features = np.array([
+        [1.0, 2.0, 100.5, 0.85, 1000.0, 800.0, 1500.0, 900.0, 0.1, 0.05, 500.1, 900.0, 700.0, 1400.0, 850.0,
+         0.95, 0.90, 10.0, 0.85, 0.80, 0.75, 0.70, 0.65, 0.60, 0.55, 2000.0, 1800.0, 200.0, 0.15, 0.88, 0.82,
+         0.78, 0.92, 0.86, 0.84, 5.0, 0.89, 6.0, 20.0, 15.0, 2.5, 0.02, 0.01, 3.0, 500.0, 0.03],
+        [1.5, 2.5, 200.5, 0.90, 1100.0, 850.0, 1600.0, 950.0, 0.15, 0.08, 600.1, 950.0, 750.0, 1450.0, 900.0,
+         0.96, 0.91, 12.0, 0.87, 0.82, 0.77, 0.72, 0.67, 0.62, 0.57, 2100.0, 1900.0, 200.0, 0.18, 0.90, 0.84,
+         0.80, 0.94, 0.88, 0.86, 6.0, 0.91, 7.0, 22.0, 17.0, 3.0, 0.025, 0.015, 4.0, 550.0, 0.035],
+    ], dtype=np.float32)
+    psm = Mock()
+    psm.to_precursor_df.return_value = (np.array([0, 1]), np.array([1, 1]), features)
+    candidates = pd.DataFrame({
+        "precursor_idx": [0, 1], "rank": [1, 1], "elution_group_idx": [0, 1], "scan_center": [100, 200],
+        "scan_start": [90, 190], "scan_stop": [110, 210], "frame_center": [50, 100], "frame_start": [45, 95],
+        "frame_stop": [55, 105],
+    })
+    result = op.collect_candidates(candidates, psm)
+
+    assert list(result.columns[:46]) == DEFAULT_FEATURE_COLUMNS and list(result.columns[46:48]) == ["precursor_idx", "rank"]
+    assert np.array_equal(result[DEFAULT_FEATURE_COLUMNS].values, features)
+    expected = {
+        "precursor_idx": [0, 1], "rank": [1, 1],
+        "elution_group_idx": [0, 1], "frame_center": [50, 100], "frame_stop": [55, 105], "scan_stop": [110, 210],
+        "frame_start": [45, 95], "scan_start": [90, 190], "scan_center": [100, 200],
+        "flat_frag_stop_idx": [5, 10], "mod_sites": ["", ""], "mz_library": [500.0, 600.0], "decoy": [0, 1], "charge": [2, 3],
+        "mods": ["", ""], "rt_library": [100.0, 200.0], "proteins": ["P1", "P2"], "channel": [0, 0], "genes": ["G1", "G2"],
+        "flat_frag_start_idx": [0, 5], "mobility_library": [0.8, 0.9], "i_0": [1.0, 1.0], "sequence": ["PEPTIDEK", "ANOTHERR"],
+        "delta_rt": [0.5, 0.5], "n_K": [1, 0], "n_R": [0, 2], "n_P": [2, 0],
+    }
+    assert set(result.columns) == set(DEFAULT_FEATURE_COLUMNS) | set(expected)
+    assert list(result.columns[-4:]) == ["delta_rt", "n_K", "n_R", "n_P"]
+    exp_df = pd.DataFrame(expected)[list(result.columns[46:])]
+    pd.testing.assert_frame_equal(result[list(result.columns[46:])], exp_df, check_dtype=False)
+    # the array form adb_score_candidates fills gives the same table, invalid rows dropped
+    arrays = dict(features=np.vstack([features, np.zeros((1, 46), np.float32)]), valid=np.array([1, 1, 0], np.uint8),
+                  precursor_idx=np.array([0, 1, 1], np.uint32), rank=np.array([1, 1, 2], np.uint8))
+    pd.testing.assert_frame_equal(op.collect_candidates(candidates, arrays), result, check_dtype=False)
