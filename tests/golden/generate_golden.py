@@ -1,6 +1,6 @@
 """Generate golden vectors by running the UNMODIFIED reference numba path (CPU, this container).
 
-    python tests/golden/generate_golden.py [config1 parity_small ...]
+    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants ...]
 
 Needs /root/reference (read-only) and numba; pays ~6 min of JIT once per process.  Writes
 ``tests/golden/<name>.npz`` — inputs are NOT stored (they are regenerated from the seed by
@@ -162,6 +162,70 @@ def run(name: str, threads: int, variants: bool):
     print(f"[{name}] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def run_variants(threads: int):
+    """Configuration variants of the selection (3-D and 4-D) and the multiplexed scoring set-up
+    (score_grouped / reference_channel, multiplexing_requantification_handler.py:120-149) -> tests/golden/variants.npz."""
+    from tests.helpers import SELECTION_VARIANTS, multiplexed_library
+
+    sel_mod = refshim.ref("alphadia.search.selection.selection")
+    cfg_mod = refshim.ref("alphadia.search.selection.config_df")
+    sc_mod = refshim.ref("alphadia.search.scoring.scoring")
+    sccfg_mod = refshim.ref("alphadia.search.scoring.config")
+    out = {}
+
+    def select(dia, precursor_df, fragment_df, p, updates):
+        cfg = cfg_mod.CandidateSelectionConfig()
+        cfg.update({**SELECTION_BASE, "rt_tolerance": float(p["rt_tolerance"]),
+                    "mobility_tolerance": float(p.get("mobility_tolerance", 0.1)),
+                    "candidate_count": 3, "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0, **updates})
+        sel = sel_mod.CandidateSelection(
+            dia, precursor_df.copy(), fragment_df.copy(), cfg, rt_column="rt_library", mobility_column="mobility_library",
+            precursor_mz_column="mz_library", fragment_mz_column="mz_library", fwhm_rt=5.0, fwhm_mobility=0.01)
+        return sel(thread_count=threads)
+
+    for name, variants in SELECTION_VARIANTS.items():
+        if name in CONFIGS_4D:
+            raw, precursor_df, fragment_df, p = make_config_4d(name)
+            dia = refshim.RefDiaData4D(raw)
+        else:
+            raw, precursor_df, fragment_df, p = make_config_3d(name)
+            dia = refshim.RefDiaData(raw)
+        out[f"{name}__input_checksum"] = np.array(input_checksum(raw, precursor_df, fragment_df))
+        for tag, updates in variants.items():
+            t0 = time.perf_counter()
+            cand = select(dia, precursor_df, fragment_df, p, updates)
+            print(f"[variants] {name}/{tag}: {len(cand)} candidates in {time.perf_counter() - t0:.1f}s", flush=True)
+            for c in cand.columns:
+                out[f"{name}__{tag}__cand_{c}"] = cand[c].values
+
+    # multiplexed scoring on the 3-D case
+    raw, precursor_df, fragment_df, p = make_config_3d("parity_small")
+    dia = refshim.RefDiaData(raw)
+    mpdf = multiplexed_library(precursor_df)
+    cand = select(dia, mpdf, fragment_df, p, {"candidate_count": 1})
+    for c in cand.columns:
+        out[f"mplex__cand_{c}"] = cand[c].values
+    for tag, updates in {"ref0": {"score_grouped": True, "reference_channel": 0},
+                         "grouped": {"score_grouped": True, "reference_channel": -1}}.items():
+        sc_cfg = sccfg_mod.CandidateScoringConfig()
+        sc_cfg.update({**SCORING_BASE, "precursor_mz_tolerance": 5, "fragment_mz_tolerance": 10, **updates})
+        scorer = sc_mod.CandidateScoring(
+            dia_data=dia, precursors_flat=mpdf.copy(), fragments_flat=fragment_df.copy(), config=sc_cfg,
+            rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+            fragment_mz_column="mz_library")
+        t0 = time.perf_counter()
+        feat, frag = scorer(cand.copy(), thread_count=threads, include_decoy_fragment_features=True)
+        print(f"[variants] mplex/{tag}: {len(feat)} rows, {len(frag)} fragment rows in {time.perf_counter() - t0:.1f}s", flush=True)
+        out[f"mplex__{tag}__feat_matrix"] = feat[sc_mod.DEFAULT_FEATURE_COLUMNS].values.astype(np.float32)
+        for c in ("precursor_idx", "rank", "elution_group_idx", "channel", "decoy"):
+            out[f"mplex__{tag}__feat_{c}"] = feat[c].values
+        for c in ("precursor_idx", "rank", "mz_library", "number", "intensity", "elution_group_idx", "decoy"):
+            out[f"mplex__{tag}__frag_{c}"] = frag[c].values
+    path = os.path.join(HERE, "variants.npz")
+    np.savez_compressed(path, **out)
+    print(f"[variants] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def transpose_inputs(seed: int = 5, n_push: int = 1500, n_tof: int = 257):
     """Push-major CSR of a small synthetic timsTOF file: ragged pushes (20 % empty), ascending tof indices inside a push."""
     rng = np.random.default_rng(seed)
@@ -191,5 +255,7 @@ if __name__ == "__main__":
     for i, n in enumerate(names):
         if n == "transpose":
             run_transpose()
+        elif n == "variants":
+            run_variants(threads)
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d")))

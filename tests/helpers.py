@@ -32,6 +32,42 @@ SCORING_BASE = {
 }
 
 
+# configuration variants pinned against the live reference in tests/golden/variants.npz (generate_golden.py variants)
+SELECTION_VARIANTS = {
+    "parity_small": {
+        "c1": dict(candidate_count=1),
+        "join": dict(candidate_count=5, join_close_candidates=True, join_close_candidates_scan_threshold=0.01),
+        "unweighted": dict(use_weighted_score=False),
+        "rt8": dict(rt_tolerance=8.0),
+        "rt400": dict(rt_tolerance=400.0),
+        "k6": dict(top_k_fragments=6, top_k_precursors=2),
+    },
+    "parity_4d": {
+        "c1": dict(candidate_count=1),
+        "join": dict(candidate_count=5, join_close_candidates=True, join_close_candidates_scan_threshold=0.01),
+        "unweighted": dict(use_weighted_score=False),
+        "rt5": dict(rt_tolerance=5.0),
+        "mob02": dict(mobility_tolerance=0.2),
+        "wide": dict(rt_tolerance=100.0, mobility_tolerance=0.4),
+    },
+}
+
+
+def multiplexed_library(precursor_df):
+    """Three channels (0 / 4 / 8) per elution group, every fifth group without channel 0 (it carries 12 instead): the
+    shape MultiplexingRequantificationHandler scores with score_grouped=True, reference_channel=0."""
+    pdf = precursor_df.copy()
+    n = len(pdf)
+    group = np.arange(n) // 3
+    pdf["elution_group_idx"] = group.astype(np.uint32)
+    pdf["decoy"] = (group % 2).astype(np.uint8)
+    ch = np.array([0, 4, 8], dtype=np.uint32)[np.arange(n) % 3]
+    no_ref = group % 5 == 0
+    ch[no_ref] = np.array([12, 4, 8], dtype=np.uint32)[np.arange(n) % 3][no_ref]
+    pdf["channel"] = ch
+    return pdf
+
+
 def selection_config(rt_tolerance: float, **kw) -> CandidateSelectionConfig:
     c = CandidateSelectionConfig()
     c.update({**SELECTION_BASE, "rt_tolerance": float(rt_tolerance), "mobility_tolerance": 0.1, "candidate_count": 3,

@@ -86,7 +86,8 @@ def test_selection_matches_oracle_and_golden(engine, oracle_lib, name):
 
 @pytest.mark.parametrize("kw", [dict(candidate_count=1), dict(candidate_count=5, join_close_candidates=True,
                                                                join_close_candidates_scan_threshold=0.01),
-                                dict(use_weighted_score=False), dict(rt_tolerance=8.0), dict(rt_tolerance=400.0)])
+                                dict(use_weighted_score=False), dict(rt_tolerance=8.0), dict(rt_tolerance=400.0),
+                                dict(top_k_fragments=6, top_k_precursors=2)])
 def test_selection_config_variants(engine, oracle_lib, kw):
     raw, lib, p, draw, dlib = _device_objects(engine, "parity_small")
     args = dict(kw)
@@ -330,7 +331,7 @@ def test_selection_4d_matches_oracle_and_golden(engine, oracle_lib):
 @pytest.mark.parametrize("kw", [dict(candidate_count=1), dict(candidate_count=5, join_close_candidates=True,
                                                                join_close_candidates_scan_threshold=0.01),
                                 dict(use_weighted_score=False), dict(rt_tolerance=5.0), dict(mobility_tolerance=0.2),
-                                dict(rt_tolerance=100.0, mobility_tolerance=0.4)])
+                                dict(rt_tolerance=100.0, mobility_tolerance=0.4), dict(top_k_fragments=6, top_k_precursors=2)])
 def test_selection_4d_config_variants(engine, oracle_lib, kw):
     raw, lib, p, draw, dlib = _device_objects(engine, "parity_4d")
     cfg = _sel_cfg_4d(p, **kw)

@@ -145,6 +145,108 @@ def test_scoring_4d_vs_reference(tag, oracle_lib):
         assert np.array_equal(a, b) if k != "correlation" else H.rel_err(a, b).max() < 1e-4, k
 
 
+# ---- configuration variants and the multiplexed set-up (tests/golden/variants.npz) ---------------------
+def _variants(name):
+    import os
+
+    path = os.path.join(H.GOLDEN_DIR, "variants.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden variants.npz missing")
+    g = np.load(path, allow_pickle=False)
+    raw, pdf, fdf, lib, p = H.workload(name)
+    if str(g[f"{name}__input_checksum"]) != H.input_checksum(raw, pdf, fdf):
+        pytest.skip("synthetic generator output differs from the one the golden file was made with (numpy version?)")
+    return g, raw, pdf, fdf, lib, p
+
+
+@pytest.mark.parametrize("name,tag", [(n, t) for n, v in H.SELECTION_VARIANTS.items() for t in v])
+def test_selection_variants_bit_exact_vs_reference(name, tag, oracle_lib):
+    g, raw, pdf, fdf, lib, p = _variants(name)
+    kw = dict(H.SELECTION_VARIANTS[name][tag])
+    rt_tol = kw.pop("rt_tolerance", p["rt_tolerance"])
+    if "mobility_tolerance" in p:
+        kw.setdefault("mobility_tolerance", p["mobility_tolerance"])
+    cfg = H.selection_config(rt_tol, **kw).to_struct()
+    select = oracle_lib.select_candidates_4d if "mobility_tolerance" in p else oracle_lib.select_candidates
+    arrs = select(raw, lib, cfg, H.default_kernel(raw))
+    m = arrs["score"] > 0
+    key = f"{name}__{tag}__cand_"
+    assert m.sum() == len(g[key + "precursor_idx"]) > 0
+    for c in INT_COLS:
+        assert np.array_equal(arrs[c][m].astype(np.int64), g[key + c].astype(np.int64)), c
+    if tag == "unweighted":
+        # amean1 / astd1 (selection/utils.py:113-126) are compiled as callees of the fastmath `_build_candidates`
+        # (selection.py:367) and inherit its flag: their f32 sum is vector-reduced in an order that depends on the
+        # host's SIMD width (compiled on their own they are sequential and equal to the oracle bit for bit).  The
+        # f32 score is therefore compared within the float tolerance; observed difference <= 6e-6.
+        assert H.rel_err(arrs["score"][m], g[key + "score"]).max() < 1e-4
+    else:
+        assert np.array_equal(arrs["score"][m], g[key + "score"])  # f32, bit-exact
+
+
+@pytest.mark.parametrize("tag,cfg_kw", [("ref0", dict(score_grouped=True, reference_channel=0)),
+                                        ("grouped", dict(score_grouped=True, reference_channel=-1))])
+def test_multiplexed_scoring_vs_reference(tag, cfg_kw, oracle_lib, monkeypatch):
+    """score_grouped / reference_channel (multiplexing_requantification_handler.py:120-149) through the HOST side of
+    CandidateScoring — score groups, the skip of groups without the reference channel, the order and content of both
+    result tables — against the live reference.  There is no GPU here, so the one device call is replaced by the oracle
+    for this test only; tests/test_gpu_parity.py::test_multiplexed_score_groups_and_reference_channel runs the real one."""
+    import pandas as pd
+
+    from alphadia_b200 import _lib
+    from alphadia_b200.library import assemble_library_arrays
+    from alphadia_b200.scoring import DEFAULT_FEATURE_COLUMNS, CandidateScoring
+
+    g, raw, pdf, fdf, lib, p = _variants("parity_small")
+    mpdf = H.multiplexed_library(pdf)
+    mlib = assemble_library_arrays(mpdf, fdf, "rt_library", "mobility_library", "mz_library", "mz_library")
+    arrs = oracle_lib.select_candidates(raw, mlib, H.selection_config(p["rt_tolerance"], candidate_count=1).to_struct(),
+                                        H.default_kernel(raw))
+    m = arrs["score"] > 0
+    for c in INT_COLS:
+        assert np.array_equal(arrs[c][m].astype(np.int64), g["mplex__cand_" + c].astype(np.int64)), c
+    cand_df = pd.DataFrame({c: g["mplex__cand_" + c] for c in INT_COLS + ["score", "elution_group_idx", "decoy"]})
+
+    class HostRaw:
+        device = 0
+
+        def __init__(self, arrays):
+            self.arrays = arrays
+
+        def last_timing(self):
+            return {}
+
+    class HostLibrary:
+        def __init__(self, arrays, device=0):
+            self.arrays = arrays
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(_lib, "device_rawfile_for", lambda dia_data, adapted: HostRaw(adapted))
+    monkeypatch.setattr(_lib, "DeviceLibrary", HostLibrary)
+    monkeypatch.setattr(_lib, "score_candidates",
+                        lambda dev_raw, dev_lib, cfg, cin: oracle_lib.score_candidates(dev_raw.arrays, dev_lib.arrays, cfg, cin))
+    scorer = CandidateScoring(dia_data=raw, precursors_flat=mpdf.copy(), fragments_flat=fdf.copy(), config=H.scoring_config(**cfg_kw),
+                              rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+                              fragment_mz_column="mz_library")
+    feat, frag = scorer(cand_df.copy())
+    key = f"mplex__{tag}__"
+    assert len(feat) == len(g[key + "feat_precursor_idx"]) > 50
+    if tag == "ref0":
+        assert len(feat) < len(g["mplex__grouped__feat_precursor_idx"])  # groups without channel 0 were skipped
+    for c in ("precursor_idx", "rank", "elution_group_idx", "channel", "decoy"):
+        assert np.array_equal(feat[c].values, g[key + "feat_" + c]), c  # same rows in the same order
+    F, G = feat[DEFAULT_FEATURE_COLUMNS].values, g[key + "feat_matrix"]
+    for j in range(46):
+        if j in BLAS_FEATURES:
+            assert H.rel_err(F[:, j], G[:, j]).max() < 1e-4, j
+        else:
+            assert ((F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))).all(), f"feature {j} not bit-exact"
+    for c in ("precursor_idx", "rank", "mz_library", "number", "intensity", "elution_group_idx", "decoy"):
+        assert np.array_equal(frag[c].values, g[key + "frag_" + c]), c
+
+
 # ---- timsTOF load-time CSR transpose (SURVEY 8f.3) --------------------------------------------------
 def _transpose_inputs(seed=5, n_push=1500, n_tof=257):
     """Same generator as tests/golden/generate_golden.py::transpose_inputs."""
