@@ -20,6 +20,7 @@ c_f64p = C.POINTER(C.c_double)
 c_i64p = C.POINTER(C.c_int64)
 c_u32p = C.POINTER(C.c_uint32)
 c_u8p = C.POINTER(C.c_uint8)
+c_u64p = C.POINTER(C.c_uint64)
 
 
 class RawFile3DDesc(C.Structure):
@@ -155,7 +156,7 @@ class ScoresOut(C.Structure):
 _PTR = {
     np.dtype(np.float32): c_f32p, np.dtype(np.float64): c_f64p, np.dtype(np.int64): c_i64p,
     np.dtype(np.uint32): c_u32p, np.dtype(np.uint8): c_u8p, np.dtype(np.bool_): c_u8p,
-    np.dtype(np.uint16): c_u16p,
+    np.dtype(np.uint16): c_u16p, np.dtype(np.uint64): c_u64p,
 }
 
 

@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "adb_rawfile3d_create", "adb_rawfile4d_create", "adb_rawfile_destroy", "adb_rawfile_device_bytes", "adb_rawfile_stream",
     "adb_library_create", "adb_library_destroy",
     "adb_select_candidates", "adb_score_candidates", "adb_fragment_competition", "adb_transpose_csr",
+    "adb_q_values", "adb_keep_best",
     "adb_select_candidates_resident", "adb_score_candidates_resident",
     "adb_fetch_candidates", "adb_fetch_candidate_table", "adb_fetch_scores", "adb_resident_score_table",
     "adb_last_timing", "adb_kernel_launches", "adb_last_main_kernel_ms",
@@ -271,3 +272,29 @@ def transpose_csr(tof_indices, push_indptr, n_tof_indices: int, values, device: 
                                 _abi.ptr(ptr_), _abi.ptr(vals), _abi.ptr(push_out), _abi.ptr(indptr_out), _abi.ptr(vals_out)),
           "adb_transpose_csr")
     return push_out, indptr_out, vals_out
+
+
+def q_values(score, decoy, extra_key, device: int | None = None):
+    """``adb_q_values``: ``(order i64, qval f64)`` of get_q_values (alphadia/fdr/fdr.py:226-297) — ``order`` is the row
+    permutation of ``sort_values([score, decoy, *extra])``, ``qval`` is in that sorted order."""
+    require_device()
+    sc, dc, ek = _abi.as_c(score, np.float64), _abi.as_c(decoy, np.uint8), _abi.as_c(extra_key, np.uint64)
+    if not len(sc) == len(dc) == len(ek):
+        raise ValueError("score, decoy and extra_key must have the same length")
+    order, qval = np.zeros(len(sc), np.int64), np.zeros(len(sc), np.float64)
+    dev = current_device() if device is None else device
+    check(load().adb_q_values(C.c_int(dev), C.c_int64(len(sc)), _abi.ptr(sc), _abi.ptr(dc), _abi.ptr(ek), _abi.ptr(order),
+                              _abi.ptr(qval)), "adb_q_values")
+    return order, qval
+
+
+def keep_best(score, group_key, device: int | None = None):
+    """``adb_keep_best``: u8 mask of the best (lowest score, earliest) row of every group (alphadia/fdr/fdr.py:195-224)."""
+    require_device()
+    sc, gk = _abi.as_c(score, np.float64), _abi.as_c(group_key, np.uint64)
+    if len(sc) != len(gk):
+        raise ValueError("score and group_key must have the same length")
+    keep = np.zeros(len(sc), np.uint8)
+    dev = current_device() if device is None else device
+    check(load().adb_keep_best(C.c_int(dev), C.c_int64(len(sc)), _abi.ptr(sc), _abi.ptr(gk), _abi.ptr(keep)), "adb_keep_best")
+    return keep

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "adb_common.cuh"
 
@@ -1329,6 +1330,183 @@ int adb_transpose_csr(int device, int64_t n_values, int64_t n_push, int64_t n_to
   d2h(tof_indptr_out, b_indptr.ptr, 8 * (size_t)(n_tof + 1));
   cleanup();
   if (e != cudaSuccess) return fail(std::string("transpose failed: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// FDR bookkeeping next to fragment competition: q-values and best-row-per-group, alphadia/fdr/fdr.py:195-297.
+// Both are "stable multi-column sort, then a scan"; the sorts are least-significant-key-first passes of the stable
+// cub::DeviceRadixSort over (key, row index) pairs.
+namespace {
+
+__device__ __forceinline__ uint64_t ordered_bits64(double v) {
+  uint64_t b = (uint64_t)__double_as_longlong(v);
+  if ((b << 1) == 0) b = 0;  // -0.0 and +0.0 compare equal in pandas' sort: give them one key
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void fdr_minor_key_kernel(const uint8_t* __restrict__ decoy, const uint64_t* __restrict__ extra, int64_t n, uint64_t* keys,
+                                     uint32_t* idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = ((uint64_t)(decoy ? decoy[i] : 0) << 63) | extra[i];  // (decoy, extra) in one key; extra < 2^63 is checked on the host
+  idx[i] = (uint32_t)i;
+}
+
+__global__ void fdr_score_key_kernel(const double* __restrict__ score, const uint32_t* __restrict__ perm, int64_t n, uint64_t* keys,
+                                     uint32_t* idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = perm ? perm[i] : (uint32_t)i;
+  keys[i] = ordered_bits64(score[r]);
+  if (idx) idx[i] = (uint32_t)i;
+}
+
+__global__ void fdr_gather_u64_kernel(const uint64_t* __restrict__ src, const uint32_t* __restrict__ perm, int64_t n, uint64_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[perm[i]];
+}
+
+__global__ void fdr_gather_decoy_kernel(const uint8_t* __restrict__ decoy, const uint32_t* __restrict__ perm, int64_t n, int64_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int64_t)decoy[perm[i]];
+}
+
+// fdr.py:288-293: decoy_cumsum / target_cumsum in float64, written back to front for the running minimum
+__global__ void fdr_ratio_reversed_kernel(const int64_t* __restrict__ decoy_cumsum, int64_t n, double* fdr_reversed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t d = decoy_cumsum[i];
+  fdr_reversed[n - 1 - i] = (double)d / (double)((i + 1) - d);
+}
+
+__global__ void fdr_unreverse_kernel(const double* __restrict__ q_reversed, const uint32_t* __restrict__ perm, int64_t n, double* qval,
+                                     int64_t* order) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  qval[i] = q_reversed[n - 1 - i];
+  order[i] = (int64_t)perm[i];
+}
+
+__global__ void fdr_group_head_kernel(const uint64_t* __restrict__ sorted_group, const uint32_t* __restrict__ perm, int64_t n, uint8_t* keep) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0 || sorted_group[i] != sorted_group[i - 1]) keep[perm[i]] = 1;
+}
+
+struct RunningMin {  // np.minimum.accumulate (fdr.py:213); no NaN can occur: i + 1 >= 1 makes 0/0 impossible
+  __host__ __device__ __forceinline__ double operator()(double a, double b) const { return b < a ? b : a; }
+};
+
+int fdr_check_scores(const double* score, int64_t n, const char* what) {
+  for (int64_t i = 0; i < n; i++)
+    if (score[i] != score[i]) return fail(std::string(what) + ": NaN score in row " + std::to_string(i));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int adb_q_values(int device, int64_t n, const double* score, const uint8_t* decoy, const uint64_t* extra_key, int64_t* order_out,
+                 double* qval_out) {
+  if (n < 0) return fail("negative size");
+  if (n == 0) return 0;
+  if (!score || !decoy || !extra_key || !order_out || !qval_out) return fail("null argument");
+  if (n >= 2147483000LL) return fail("more than 2^31 rows are not supported");
+  if (fdr_check_scores(score, n, "adb_q_values")) return 1;
+  for (int64_t i = 0; i < n; i++) {
+    if (decoy[i] > 1) return fail("decoy column must hold 0 (target) or 1 (decoy)");
+    if (extra_key[i] >> 63) return fail("extra sort key must be below 2^63");
+  }
+  if (set_device(device)) return 1;
+  const size_t N = (size_t)n;
+  DeviceBuffer b_score, b_decoy, b_extra, b_key, b_key2, b_idx, b_idx2, b_cum, b_f, b_tmp;
+  DeviceBuffer* all[] = {&b_score, &b_decoy, &b_extra, &b_key, &b_key2, &b_idx, &b_idx2, &b_cum, &b_f, &b_tmp};
+  auto cleanup = [&]() { for (DeviceBuffer* b : all) b->release(); };
+  size_t sort_bytes = 0, sum_bytes = 0, min_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, n, 0, 64, (cudaStream_t)0);
+  cub::DeviceScan::InclusiveSum(nullptr, sum_bytes, (const int64_t*)nullptr, (int64_t*)nullptr, n, (cudaStream_t)0);
+  cub::DeviceScan::InclusiveScan(nullptr, min_bytes, (const double*)nullptr, (double*)nullptr, RunningMin(), n, (cudaStream_t)0);
+  const size_t tmp_bytes = std::max(sort_bytes, std::max(sum_bytes, min_bytes));
+  if (b_score.reserve(8 * N) || b_decoy.reserve(N) || b_extra.reserve(8 * N) || b_key.reserve(8 * N) || b_key2.reserve(8 * N) ||
+      b_idx.reserve(4 * N) || b_idx2.reserve(4 * N) || b_cum.reserve(8 * N) || b_f.reserve(8 * N) || b_tmp.reserve(tmp_bytes + 16)) {
+    cleanup();
+    return 1;
+  }
+  cudaError_t e = cudaSuccess;
+  auto h2d = [&](void* d, const void* h, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice); };
+  h2d(b_score.ptr, score, 8 * N); h2d(b_decoy.ptr, decoy, N); h2d(b_extra.ptr, extra_key, 8 * N);
+  if (e != cudaSuccess) { cleanup(); return fail(std::string("adb_q_values H2D failed: ") + cudaGetErrorString(e)); }
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  size_t tb = tmp_bytes;
+  // df.sort_values([score, decoy, *extra]) (fdr.py:283-285): minor keys first, then the score; both passes are stable
+  fdr_minor_key_kernel<<<grid, 256>>>(b_decoy.as<uint8_t>(), b_extra.as<uint64_t>(), n, b_key.as<uint64_t>(), b_idx.as<uint32_t>());
+  cub::DeviceRadixSort::SortPairs(b_tmp.ptr, tb, b_key.as<uint64_t>(), b_key2.as<uint64_t>(), b_idx.as<uint32_t>(), b_idx2.as<uint32_t>(),
+                                  n, 0, 64, (cudaStream_t)0);
+  fdr_score_key_kernel<<<grid, 256>>>(b_score.as<double>(), b_idx2.as<uint32_t>(), n, b_key.as<uint64_t>(), nullptr);
+  tb = tmp_bytes;
+  cub::DeviceRadixSort::SortPairs(b_tmp.ptr, tb, b_key.as<uint64_t>(), b_key2.as<uint64_t>(), b_idx2.as<uint32_t>(), b_idx.as<uint32_t>(),
+                                  n, 0, 64, (cudaStream_t)0);
+  // cumulative decoys / cumulative targets, then the running minimum from the back (fdr.py:286-293, 211-214)
+  fdr_gather_decoy_kernel<<<grid, 256>>>(b_decoy.as<uint8_t>(), b_idx.as<uint32_t>(), n, b_key.as<int64_t>());
+  tb = tmp_bytes;
+  cub::DeviceScan::InclusiveSum(b_tmp.ptr, tb, b_key.as<int64_t>(), b_cum.as<int64_t>(), n, (cudaStream_t)0);
+  fdr_ratio_reversed_kernel<<<grid, 256>>>(b_cum.as<int64_t>(), n, b_f.as<double>());
+  tb = tmp_bytes;
+  cub::DeviceScan::InclusiveScan(b_tmp.ptr, tb, b_f.as<double>(), b_key2.as<double>(), RunningMin(), n, (cudaStream_t)0);
+  fdr_unreverse_kernel<<<grid, 256>>>(b_key2.as<double>(), b_idx.as<uint32_t>(), n, b_f.as<double>(), b_cum.as<int64_t>());
+  e = cudaGetLastError();
+  auto d2h = [&](void* h, const void* d, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost); };
+  d2h(qval_out, b_f.ptr, 8 * N); d2h(order_out, b_cum.ptr, 8 * N);
+  cleanup();
+  if (e != cudaSuccess) return fail(std::string("adb_q_values failed: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int adb_keep_best(int device, int64_t n, const double* score, const uint64_t* group_key, uint8_t* keep_out) {
+  if (n < 0) return fail("negative size");
+  if (n == 0) return 0;
+  if (!score || !group_key || !keep_out) return fail("null argument");
+  if (n >= 2147483000LL) return fail("more than 2^31 rows are not supported");
+  if (fdr_check_scores(score, n, "adb_keep_best")) return 1;
+  if (set_device(device)) return 1;
+  const size_t N = (size_t)n;
+  DeviceBuffer b_score, b_group, b_key, b_key2, b_idx, b_idx2, b_keep, b_tmp;
+  DeviceBuffer* all[] = {&b_score, &b_group, &b_key, &b_key2, &b_idx, &b_idx2, &b_keep, &b_tmp};
+  auto cleanup = [&]() { for (DeviceBuffer* b : all) b->release(); };
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, n, 0, 64, (cudaStream_t)0);
+  if (b_score.reserve(8 * N) || b_group.reserve(8 * N) || b_key.reserve(8 * N) || b_key2.reserve(8 * N) || b_idx.reserve(4 * N) ||
+      b_idx2.reserve(4 * N) || b_keep.reserve(N) || b_tmp.reserve(tmp_bytes + 16)) {
+    cleanup();
+    return 1;
+  }
+  cudaError_t e = cudaSuccess;
+  auto h2d = [&](void* d, const void* h, size_t bytes) { if (e == cudaSuccess) e = cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice); };
+  h2d(b_score.ptr, score, 8 * N); h2d(b_group.ptr, group_key, 8 * N);
+  if (e == cudaSuccess) e = cudaMemset(b_keep.ptr, 0, N);
+  if (e != cudaSuccess) { cleanup(); return fail(std::string("adb_keep_best H2D failed: ") + cudaGetErrorString(e)); }
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  size_t tb = tmp_bytes;
+  // sort_values([score, *group]) then groupby(group).head(1) (fdr.py:219-224) keeps, per group, the lowest score and among
+  // equal scores the earliest row: order the rows by (group, score, row) and take every group's first
+  fdr_score_key_kernel<<<grid, 256>>>(b_score.as<double>(), nullptr, n, b_key.as<uint64_t>(), b_idx.as<uint32_t>());
+  cub::DeviceRadixSort::SortPairs(b_tmp.ptr, tb, b_key.as<uint64_t>(), b_key2.as<uint64_t>(), b_idx.as<uint32_t>(), b_idx2.as<uint32_t>(),
+                                  n, 0, 64, (cudaStream_t)0);
+  fdr_gather_u64_kernel<<<grid, 256>>>(b_group.as<uint64_t>(), b_idx2.as<uint32_t>(), n, b_key.as<uint64_t>());
+  tb = tmp_bytes;
+  cub::DeviceRadixSort::SortPairs(b_tmp.ptr, tb, b_key.as<uint64_t>(), b_key2.as<uint64_t>(), b_idx2.as<uint32_t>(), b_idx.as<uint32_t>(),
+                                  n, 0, 64, (cudaStream_t)0);
+  fdr_group_head_kernel<<<grid, 256>>>(b_key2.as<uint64_t>(), b_idx.as<uint32_t>(), n, b_keep.as<uint8_t>());
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(keep_out, b_keep.ptr, N, cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail(std::string("adb_keep_best failed: ") + cudaGetErrorString(e));
   return 0;
 }
 

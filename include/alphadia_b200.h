@@ -235,6 +235,20 @@ int adb_transpose_csr(int device, int64_t n_values, int64_t n_push, int64_t n_to
                       const int64_t* push_indptr, const uint16_t* values, uint32_t* push_indices_out,
                       int64_t* tof_indptr_out, uint16_t* values_out);
 
+/* FDR bookkeeping around fragment competition (both called by perform_fdr, alphadia/fdr/fdr.py:157-186).
+ *
+ * adb_q_values replaces get_q_values + _fdr_to_q_values (fdr.py:195-297): rows are ordered like
+ * df.sort_values([score, decoy, *extra_sort_columns]) (stable), fdr = cumsum(decoy) / cumsum(1 - decoy) in float64 and
+ * qval = running minimum of fdr from the back.  In: score f64 [n] (no NaN), decoy u8 [n] in {0, 1}, extra_key u64 [n] < 2^63
+ * (the tie-break columns packed order-preservingly, usually precursor_idx).  Out (caller-allocated): order i64 [n] = row
+ * index of the i-th sorted row (df.iloc[order] is the sorted frame), qval f64 [n] in sorted order. */
+int adb_q_values(int device, int64_t n, const double* score, const uint8_t* decoy, const uint64_t* extra_key,
+                 int64_t* order_out, double* qval_out);
+/* adb_keep_best replaces keep_best (fdr.py:195-224): per group the row with the lowest score, ties to the earliest row.
+ * In: score f64 [n] (no NaN), group_key u64 [n] (equal key <=> same group).  Out: keep u8 [n], 1 for the surviving rows
+ * (df[keep].reset_index(drop=True) is the reference's result). */
+int adb_keep_best(int device, int64_t n, const double* score, const uint64_t* group_key, uint8_t* keep_out);
+
 /* ---- resident variants (bench.py `value`, the sharded driver) -------------------------------
  * Same kernels; the raw file and library are already in HBM, results stay in HBM inside the raw
  * handle's workspace until fetched.  (Not needed by a reference-side binding.) */

@@ -169,3 +169,33 @@ def transpose_csr(tof_indices, push_indptr, n_tof_indices, values):
     if rc != 0:
         raise RuntimeError("adbo_transpose_csr failed (tof index out of range)")
     return push_out, indptr_out, vals_out
+
+
+def q_values(score, decoy, extra_key):
+    """C restatement of ``get_q_values`` (alphadia/fdr/fdr.py:226-297): ``(order, qval)``."""
+    L = lib()
+    sc, dc, ek = _abi.as_c(score, np.float64), _abi.as_c(decoy, np.uint8), _abi.as_c(extra_key, np.uint64)
+    n = len(sc)
+    order, qval = np.zeros(n, np.int64), np.zeros(n, np.float64)
+    L.adbo_q_values.restype = None
+    L.adbo_q_values(C.c_int64(n), _abi.ptr(sc), _abi.ptr(dc), _abi.ptr(ek), _abi.ptr(order), _abi.ptr(qval))
+    return order, qval
+
+
+def keep_best(score, group_key):
+    """C restatement of ``keep_best`` (alphadia/fdr/fdr.py:195-224): the u8 mask of surviving rows."""
+    L = lib()
+    sc, gk = _abi.as_c(score, np.float64), _abi.as_c(group_key, np.uint64)
+    keep = np.zeros(len(sc), np.uint8)
+    L.adbo_keep_best.restype = None
+    L.adbo_keep_best(C.c_int64(len(sc)), _abi.ptr(sc), _abi.ptr(gk), _abi.ptr(keep))
+    return keep
+
+
+def fdr_to_q_values(fdr_values):
+    L = lib()
+    f = _abi.as_c(fdr_values, np.float64)
+    q = np.zeros(len(f), np.float64)
+    L.adbo_fdr_to_q_values.restype = None
+    L.adbo_fdr_to_q_values(_abi.ptr(f), C.c_int64(len(f)), _abi.ptr(q))
+    return q

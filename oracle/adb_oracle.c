@@ -1883,6 +1883,65 @@ int adbo_transpose_csr(int64_t n_values, int64_t n_push, int64_t n_tof, const ui
 }
 
 
+/* ==========================================================================================
+ * FDR bookkeeping — alphadia/fdr/fdr.py:195-297 (keep_best, _fdr_to_q_values, get_q_values)
+ * pandas' multi-column sort_values is a stable lexicographic sort; restated as a bottom-up merge sort of row indices.
+ * ======================================================================================== */
+typedef struct { const double* score; const uint8_t* decoy; const uint64_t* key; int mode; } FdrCmp;
+/* mode 0: (score, decoy, key) — get_q_values; mode 1: (key, score) — per-group order of keep_best */
+static int fdr_less_equal(const FdrCmp* c, int64_t a, int64_t b) {
+  if (c->mode == 0) {
+    if (c->score[a] != c->score[b]) return c->score[a] < c->score[b];
+    if (c->decoy[a] != c->decoy[b]) return c->decoy[a] < c->decoy[b];
+    return c->key[a] <= c->key[b];
+  }
+  if (c->key[a] != c->key[b]) return c->key[a] < c->key[b];
+  return c->score[a] <= c->score[b];
+}
+static void fdr_stable_sort(const FdrCmp* c, int64_t n, int64_t* idx) {
+  int64_t* tmp = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+  for (int64_t i = 0; i < n; i++) idx[i] = i;
+  for (int64_t w = 1; w < n; w *= 2) {
+    for (int64_t lo = 0; lo < n; lo += 2 * w) {
+      int64_t mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n, a = lo, b = mid, k = lo;
+      while (a < mid && b < hi) tmp[k++] = fdr_less_equal(c, idx[a], idx[b]) ? idx[a++] : idx[b++]; /* ties: left first */
+      while (a < mid) tmp[k++] = idx[a++];
+      while (b < hi) tmp[k++] = idx[b++];
+    }
+    memcpy(idx, tmp, sizeof(int64_t) * (size_t)n);
+  }
+  free(tmp);
+}
+
+/* fdr.py:211-214 */
+void adbo_fdr_to_q_values(const double* fdr, int64_t n, double* q) {
+  double m = 0;
+  for (int64_t i = n - 1; i >= 0; i--) { m = (i == n - 1 || fdr[i] < m) ? fdr[i] : m; q[i] = m; }
+}
+
+/* fdr.py:280-296: order_out = row index of each sorted row, qval_out in sorted order */
+void adbo_q_values(int64_t n, const double* score, const uint8_t* decoy, const uint64_t* extra_key, int64_t* order_out, double* qval_out) {
+  FdrCmp c = {score, decoy, extra_key, 0};
+  fdr_stable_sort(&c, n, order_out);
+  double* fdr = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  int64_t d = 0, t = 0;
+  for (int64_t i = 0; i < n; i++) { d += decoy[order_out[i]]; t += 1 - decoy[order_out[i]]; fdr[i] = (double)d / (double)t; }
+  adbo_fdr_to_q_values(fdr, n, qval_out);
+  free(fdr);
+}
+
+/* fdr.py:219-224: sort by (score, group), first row of every group, back in original order */
+void adbo_keep_best(int64_t n, const double* score, const uint64_t* group_key, uint8_t* keep_out) {
+  FdrCmp c = {score, NULL, group_key, 1};
+  int64_t* idx = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+  fdr_stable_sort(&c, n, idx);
+  for (int64_t i = 0; i < n; i++) keep_out[i] = 0;
+  for (int64_t i = 0; i < n; i++)
+    if (i == 0 || group_key[idx[i]] != group_key[idx[i - 1]]) keep_out[idx[i]] = 1;
+  free(idx);
+}
+
+
 /* ---- test hooks for the reference's remaining known-answer unit tests ------------------------------------------- */
 /* scoring/utils.py:478-510 save_corrcoeff on float32 inputs (np.mean / np.sum accumulate in float32 under numba) */
 double adbo_save_corrcoeff_f32(const float* x, const float* y, int n) {

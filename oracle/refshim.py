@@ -217,7 +217,7 @@ def install() -> None:
     ar.thermo = _stub_module("alpharaw.thermo", ThermoRawData=type("ThermoRawData", (_Base,), {}))
 
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.colors",
-                 "matplotlib.figure", "matplotlib.axes", "seaborn"):
+                 "matplotlib.figure", "matplotlib.axes", "matplotlib.ticker", "seaborn"):
         if name not in sys.modules:
             sys.modules[name] = _AnyModule(name)
 

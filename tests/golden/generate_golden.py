@@ -1,6 +1,6 @@
 """Generate golden vectors by running the UNMODIFIED reference numba path (CPU, this container).
 
-    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants ...]
+    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr ...]
 
 Needs /root/reference (read-only) and numba; pays ~6 min of JIT once per process.  Writes
 ``tests/golden/<name>.npz`` — inputs are NOT stored (they are regenerated from the seed by
@@ -226,6 +226,30 @@ def run_variants(threads: int):
     print(f"[variants] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def run_fdr():
+    """get_q_values / keep_best of the unmodified reference (alphadia/fdr/fdr.py:195-297) -> tests/golden/fdr_small.npz."""
+    from tests.helpers import fdr_inputs
+
+    fdr = refshim.ref("alphadia.fdr.fdr")
+    df = fdr_inputs()
+    out = {"input_checksum": np.array(hashlib.sha256(df.to_numpy().tobytes() + df.index.to_numpy().tobytes()).hexdigest())}
+    q = fdr.get_q_values(df.copy(), "proba", "_decoy")
+    out["q_row"], out["q_index"], out["q_qval"] = q["row"].values, q.index.values, q["qval"].values
+    q2 = fdr.get_q_values(df.copy(), "proba", "_decoy", extra_sort_columns=["precursor_idx", "rank"])
+    out["q2_row"], out["q2_qval"] = q2["row"].values, q2["qval"].values
+    for tag, cols in {"precursor": ["precursor_idx"], "channel_eg": ["elution_group_idx", "channel"], "eg": ["elution_group_idx"],
+                      "default": None}.items():
+        kept = fdr.keep_best(df.copy(), group_columns=cols)
+        out[f"keep_{tag}_row"] = kept["row"].values
+        assert np.array_equal(kept.index.values, np.arange(len(kept)))
+    # the sequence perform_fdr runs (fdr.py:157-186): q-values, best per group, q-values again
+    final = fdr.get_q_values(fdr.keep_best(q, group_columns=["elution_group_idx", "channel"]), "proba", "_decoy")
+    out["final_row"], out["final_qval"] = final["row"].values, final["qval"].values
+    path = os.path.join(HERE, "fdr_small.npz")
+    np.savez_compressed(path, **out)
+    print(f"[fdr] {len(df)} rows -> q-values {len(q)}, final {len(final)}; wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def transpose_inputs(seed: int = 5, n_push: int = 1500, n_tof: int = 257):
     """Push-major CSR of a small synthetic timsTOF file: ragged pushes (20 % empty), ascending tof indices inside a push."""
     rng = np.random.default_rng(seed)
@@ -257,5 +281,7 @@ if __name__ == "__main__":
             run_transpose()
         elif n == "variants":
             run_variants(threads)
+        elif n == "fdr":
+            run_fdr()
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d")))

@@ -139,3 +139,26 @@ def rel_err(a, b, floor=1e-6):
     d = np.where(both_nan, 0.0, d)
     d = np.where(np.isnan(d), np.inf, d)
     return d
+
+
+def fdr_inputs(seed: int = 11, n: int = 6000):
+    """PSM table for the FDR bookkeeping tests (tests/golden/fdr_small.npz): probabilities with many exact ties, several
+    ranks per precursor, three channels, a shuffled non-default index, and the best scores held by decoys (so that the
+    first FDR values are x / 0)."""
+    import pandas as pd
+
+    rng = np.random.default_rng(seed)
+    precursor_idx = rng.integers(0, n // 3, n).astype(np.uint32)
+    proba = np.round(rng.random(n), 2)  # 101 distinct values: ties everywhere
+    decoy = (rng.random(n) < 0.45).astype(np.uint8)
+    best = np.argsort(proba, kind="stable")[:3]
+    proba[best] = [-1.0, -0.5, -0.0]  # negative scores and a signed zero sort first
+    decoy[best] = 1
+    decoy[proba == 0.0] = 1
+    df = pd.DataFrame({
+        "precursor_idx": precursor_idx, "rank": rng.integers(0, 3, n).astype(np.uint8),
+        "elution_group_idx": (precursor_idx // 2).astype(np.uint32), "channel": (4 * rng.integers(0, 3, n)).astype(np.uint32),
+        "proba": proba, "_decoy": decoy.astype(np.float64), "row": np.arange(n),
+    })
+    df.index = rng.permutation(n) + 100
+    return df

@@ -839,3 +839,49 @@ def test_multiplexed_score_groups_and_reference_channel(engine, oracle_lib):
     dup = pd.concat([cand_df, cand_df.iloc[:1]], ignore_index=True)
     with pytest.raises(ValueError, match="unique within a score group"):
         scorer(dup)
+
+
+def test_fdr_bookkeeping(engine, oracle_lib):
+    """adb_q_values / adb_keep_best == the oracle == the live reference's get_q_values / keep_best
+    (tests/golden/fdr_small.npz) == the reference's own unit-test vectors; bit-exact (integer order, float64 q-values)."""
+    import hashlib
+    import os
+
+    from alphadia_b200 import fdr
+    from tests.test_reference_known_answers import FDR_KNOWN_ANSWERS
+
+    for check in FDR_KNOWN_ANSWERS:
+        check(fdr)
+    df = H.fdr_inputs()
+    path = os.path.join(H.GOLDEN_DIR, "fdr_small.npz")
+    g = np.load(path, allow_pickle=False) if os.path.exists(path) else None
+    if g is not None and str(g["input_checksum"]) == hashlib.sha256(df.to_numpy().tobytes() + df.index.to_numpy().tobytes()).hexdigest():
+        q = fdr.get_q_values(df.copy(), "proba", "_decoy")
+        assert np.array_equal(q["row"].values, g["q_row"]) and np.array_equal(q.index.values, g["q_index"])
+        assert np.array_equal(q["qval"].values, g["q_qval"])
+        q2 = fdr.get_q_values(df.copy(), "proba", "_decoy", extra_sort_columns=["precursor_idx", "rank"])
+        assert np.array_equal(q2["row"].values, g["q2_row"]) and np.array_equal(q2["qval"].values, g["q2_qval"])
+        for tag, cols in {"precursor": ["precursor_idx"], "channel_eg": ["elution_group_idx", "channel"], "eg": ["elution_group_idx"],
+                          "default": None}.items():
+            assert np.array_equal(fdr.keep_best(df.copy(), group_columns=cols)["row"].values, g[f"keep_{tag}_row"]), tag
+        final = fdr.get_q_values(fdr.keep_best(q, group_columns=["elution_group_idx", "channel"]), "proba", "_decoy")
+        assert np.array_equal(final["row"].values, g["final_row"]) and np.array_equal(final["qval"].values, g["final_qval"])
+    # larger random tables against the oracle: heavy ties, negative / zero / huge scores, all-decoy and all-target runs
+    rng = np.random.default_rng(3)
+    for n, levels in [(1, 1), (2, 1), (1000, 7), (300_000, 5000), (300_000, 10 ** 9)]:
+        score = rng.integers(-levels, levels + 1, n) / max(levels, 1) * rng.choice([1.0, 1e-300, 1e300])
+        decoy = (rng.random(n) < rng.choice([0.0, 0.5, 1.0])).astype(np.uint8)
+        extra = rng.integers(0, max(n // 4, 1), n).astype(np.uint64)
+        o_dev, q_dev = engine.q_values(score, decoy, extra)
+        o_ref, q_ref = oracle_lib.q_values(score, decoy, extra)
+        assert np.array_equal(o_dev, o_ref), f"q-value order n={n}"
+        assert np.array_equal(q_dev, q_ref, equal_nan=True), f"q-values n={n}"
+        group = rng.integers(0, max(n // 3, 1), n).astype(np.uint64) << np.uint64(rng.integers(0, 40))
+        assert np.array_equal(engine.keep_best(score, group), oracle_lib.keep_best(score, group)), f"keep_best n={n}"
+    # loud failures
+    with pytest.raises(RuntimeError, match="NaN"):
+        engine.q_values(np.array([0.1, np.nan]), np.array([0, 1], np.uint8), np.array([0, 1], np.uint64))
+    with pytest.raises(RuntimeError, match="NaN"):
+        engine.keep_best(np.array([np.nan]), np.array([0], np.uint64))
+    with pytest.raises(ValueError, match="_decoy"):
+        fdr.get_q_values(pd.DataFrame({"precursor_idx": [0], "proba": [0.5], "_decoy": [2]}))

@@ -282,3 +282,46 @@ def test_transpose_oracle_vs_reference_golden(oracle_lib):
     assert len(p0) == 0 and np.array_equal(i0, np.zeros(8, np.int64))
     p1, i1, v1 = oracle_lib.transpose_csr(np.full(4, 3, np.uint32), np.array([0, 1, 1, 3, 4], np.int64), 5, np.array([9, 8, 7, 6], np.uint16))
     assert np.array_equal(p1, [0, 2, 2, 3]) and np.array_equal(i1, [0, 0, 0, 0, 4, 4]) and np.array_equal(v1, [9, 8, 7, 6])
+
+
+# ---- FDR bookkeeping: get_q_values / keep_best of the live reference ------------------------
+def _fdr_golden():
+    import hashlib
+    import os
+
+    path = os.path.join(H.GOLDEN_DIR, "fdr_small.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden fdr_small.npz missing")
+    g = np.load(path, allow_pickle=False)
+    df = H.fdr_inputs()
+    if str(g["input_checksum"]) != hashlib.sha256(df.to_numpy().tobytes() + df.index.to_numpy().tobytes()).hexdigest():
+        pytest.skip("fdr_inputs differs from the one the golden file was made with (numpy version?)")
+    return g, df
+
+
+def host_fdr_with_oracle(monkeypatch, oracle_lib):
+    """alphadia_b200.fdr with its two device calls replaced by the oracle (CPU tests of the host packing only)."""
+    from alphadia_b200 import _lib, fdr
+
+    monkeypatch.setattr(_lib, "q_values", lambda score, decoy, extra, device=None: oracle_lib.q_values(score, decoy, extra))
+    monkeypatch.setattr(_lib, "keep_best", lambda score, group, device=None: oracle_lib.keep_best(score, group))
+    return fdr
+
+
+def test_fdr_oracle_and_host_packing_vs_reference(oracle_lib, monkeypatch):
+    g, df = _fdr_golden()
+    fdr = host_fdr_with_oracle(monkeypatch, oracle_lib)
+    q = fdr.get_q_values(df.copy(), "proba", "_decoy")
+    assert np.array_equal(q["row"].values, g["q_row"]) and np.array_equal(q.index.values, g["q_index"])
+    assert np.array_equal(q["qval"].values, g["q_qval"])  # float64, bit-exact
+    # the three best rows are decoys: their FDR is x / 0 = inf, which the running minimum from the back removes
+    assert (q["_decoy"].values[:3] == 1).all() and np.isfinite(g["q_qval"]).all()
+    q2 = fdr.get_q_values(df.copy(), "proba", "_decoy", extra_sort_columns=["precursor_idx", "rank"])
+    assert np.array_equal(q2["row"].values, g["q2_row"]) and np.array_equal(q2["qval"].values, g["q2_qval"])
+    for tag, cols in {"precursor": ["precursor_idx"], "channel_eg": ["elution_group_idx", "channel"], "eg": ["elution_group_idx"],
+                      "default": None}.items():
+        kept = fdr.keep_best(df.copy(), group_columns=cols)
+        assert np.array_equal(kept["row"].values, g[f"keep_{tag}_row"]), tag
+        assert np.array_equal(kept.index.values, np.arange(len(kept)))
+    final = fdr.get_q_values(fdr.keep_best(q, group_columns=["elution_group_idx", "channel"]), "proba", "_decoy")
+    assert np.array_equal(final["row"].values, g["final_row"]) and np.array_equal(final["qval"].values, g["final_qval"])

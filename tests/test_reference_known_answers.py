@@ -393,3 +393,50 @@ def test_collect_candidates_table():
     arrays = dict(features=np.vstack([features, np.zeros((1, 46), np.float32)]), valid=np.array([1, 1, 0], np.uint8),
                   precursor_idx=np.array([0, 1, 1], np.uint32), rank=np.array([1, 1, 2], np.uint8))
     pd.testing.assert_frame_equal(op.collect_candidates(candidates, arrays), result, check_dtype=False)
+
+
+# ---- tests/unit_tests/fdr/test_fdr.py:12-123 keep_best, _fdr_to_q_values, get_q_values -----------------------
+def test_fdr_known_answers(oracle_lib, monkeypatch):
+    """The reference's own vectors through the host mirror alphadia_b200.fdr; the two device calls are replaced by the
+    oracle here (no GPU), tests/test_gpu_parity.py::test_fdr_bookkeeping replays them on the device."""
+    from tests.test_oracle_golden import host_fdr_with_oracle
+
+    fdr = host_fdr_with_oracle(monkeypatch, oracle_lib)
+    for check in FDR_KNOWN_ANSWERS:
+        check(fdr)
+    q = oracle_lib.fdr_to_q_values(np.array([0.2, 0.1, 0.05, 0.3, 0.26, 0.25, 0.5]))
+    assert np.allclose(q, np.array([0.05, 0.05, 0.05, 0.25, 0.25, 0.25, 0.5]))
+
+
+def _known_keep_best(fdr):
+    test_df = pd.DataFrame({"precursor_idx": [0, 0, 0, 1, 1, 1, 2, 2, 2], "channel": [0, 0, 1, 0, 1, 1, 0, 0, 1],
+                            "proba": [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9]})
+    best = fdr.keep_best(test_df, score_column="proba", group_columns=["precursor_idx"])
+    assert best.shape[0] == 3 and np.allclose(best["proba"].values, [0.1, 0.4, 0.7])
+    best = fdr.keep_best(test_df, score_column="proba", group_columns=["channel", "precursor_idx"])
+    assert best.shape[0] == 6 and np.allclose(best["proba"].values, [0.1, 0.3, 0.4, 0.5, 0.7, 0.9])
+
+
+def _known_keep_best_2(fdr):
+    test_df = pd.DataFrame({"channel": [0, 0, 0, 4, 4, 4, 8, 8, 8], "elution_group_idx": [0, 1, 2, 0, 1, 2, 0, 1, 2],
+                            "proba": [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.1, 0.2, 0.3]})
+    pd.testing.assert_frame_equal(fdr.keep_best(test_df, group_columns=["channel", "elution_group_idx"]), test_df)
+    for col in ("elution_group_idx", "precursor_idx"):
+        test_df = pd.DataFrame({"channel": [0, 0, 0, 4, 4, 4, 8, 8, 8], col: [0, 0, 1, 0, 0, 1, 0, 0, 1],
+                                "proba": [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.1, 0.2, 0.3]})
+        expected = pd.DataFrame({"channel": [0, 0, 4, 4, 8, 8], col: [0, 1, 0, 1, 0, 1], "proba": [0.1, 0.3, 0.4, 0.6, 0.1, 0.3]})
+        pd.testing.assert_frame_equal(fdr.keep_best(test_df, group_columns=["channel", col]), expected)
+
+
+def _known_q_values(fdr):
+    test_df = pd.DataFrame({"precursor_idx": [0, 1, 2, 3, 4, 5, 6, 7, 8, 9],
+                            "proba": [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0], "_decoy": [0, 0, 0, 1, 0, 0, 1, 1, 1, 1]})
+    out = fdr.get_q_values(test_df, "proba", "_decoy")
+    assert np.allclose(out["qval"].values, [0.0, 0.0, 0.0, 0.2, 0.2, 0.2, 0.4, 0.6, 0.8, 1.0])
+    assert list(out.columns) == ["precursor_idx", "proba", "_decoy", "qval"] and "qval" not in test_df.columns
+    empty = fdr.get_q_values(test_df.iloc[:0], "proba", "_decoy")
+    assert len(empty) == 0 and "qval" in empty.columns
+    assert len(fdr.keep_best(test_df.iloc[:0], group_columns=["precursor_idx"])) == 0
+
+
+FDR_KNOWN_ANSWERS = [_known_keep_best, _known_keep_best_2, _known_q_values]
