@@ -284,6 +284,131 @@ def test_transpose_oracle_vs_reference_golden(oracle_lib):
     assert np.array_equal(p1, [0, 2, 2, 3]) and np.array_equal(i1, [0, 0, 0, 0, 4, 4]) and np.array_equal(v1, [9, 8, 7, 6])
 
 
+# ---- CandidateSelection.__call__ host side: the returned table (columns, order, dtypes) vs the reference's -------------
+@pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
+def test_candidate_selection_table_vs_reference(name, oracle_lib, monkeypatch):
+    """selection.py:622-676 + config_df.py:258-298: same columns in the same order with the same dtypes and values as the
+    DataFrame the reference returned.  No GPU here: the two device calls are replaced by the oracle for this test only
+    (tests/test_gpu_parity.py::test_operator_classes_end_to_end / _4d run the real ones)."""
+    from alphadia_b200 import _abi, _lib
+    from alphadia_b200.selection import CandidateSelection
+
+    g, raw, lib, p = _golden(name)
+    _, pdf, fdf, _, _ = H.workload(name)
+    state = {}
+
+    class HostRaw:
+        device = 0
+
+        def __init__(self, arrays):
+            self.arrays = arrays
+
+        def last_timing(self):
+            return {}
+
+    class HostLibrary:
+        def __init__(self, arrays, device=0):
+            self.arrays = arrays
+
+        def close(self):
+            pass
+
+    def select_resident(dev_raw, dev_lib, cfg, kernel):
+        select = oracle_lib.select_candidates_4d if name == "parity_4d" else oracle_lib.select_candidates
+        arrs = select(dev_raw.arrays, dev_lib.arrays, cfg, kernel)
+        keep = arrs["score"] > 0  # adb_fetch_candidate_table: rows with score > 0 in container order
+        state["table"] = {c: arrs[c][keep] for c in INT_COLS + ["score"]}
+        return int(keep.sum())
+
+    def fetch_table(dev_raw, n, arrs=None):
+        table = _abi.alloc_candidate_table(n)
+        for c, v in state["table"].items():
+            table[c][:n] = v
+        return table
+
+    monkeypatch.setattr(_lib, "device_rawfile_for", lambda dia_data, adapted: HostRaw(adapted))
+    monkeypatch.setattr(_lib, "DeviceLibrary", HostLibrary)
+    monkeypatch.setattr(_lib, "select_candidates_resident", select_resident)
+    monkeypatch.setattr(_lib, "fetch_candidate_table", fetch_table)
+    kw = {"mobility_tolerance": p["mobility_tolerance"]} if "mobility_tolerance" in p else {}
+    sel = CandidateSelection(raw, pdf.copy(), fdf.copy(), H.selection_config(p["rt_tolerance"], **kw), rt_column="rt_library",
+                             mobility_column="mobility_library", precursor_mz_column="mz_library", fragment_mz_column="mz_library",
+                             fwhm_rt=5.0, fwhm_mobility=0.01)
+    assert np.array_equal(sel.kernel, g["sel_kernel"]) or np.allclose(sel.kernel, g["sel_kernel"], rtol=1e-6, atol=0)
+    df = sel(thread_count=4)
+    expected_columns = ["precursor_idx", "rank", "score", "scan_center", "scan_start", "scan_stop", "frame_center", "frame_start",
+                        "frame_stop", "elution_group_idx", "decoy"]
+    assert list(df.columns) == expected_columns
+    for c in expected_columns:
+        assert df[c].dtype == g["cand_" + c].dtype, (c, df[c].dtype, g["cand_" + c].dtype)
+        assert np.array_equal(df[c].values, g["cand_" + c]), c
+    assert np.array_equal(df.index.values, np.arange(len(df)))
+
+
+@pytest.mark.parametrize("name,tag", [("parity_small", ""), ("parity_small", "_k6"), ("parity_4d", ""), ("parity_4d", "_legacy")])
+def test_candidate_scoring_tables_vs_reference(name, tag, oracle_lib, monkeypatch):
+    """scoring.py:582-661: both returned DataFrames — column sets, the fixed part of the column order, dtypes, row order and
+    values — against the tables the reference returned for the same candidates.  The device call is replaced by the oracle
+    for this CPU test only (the GPU operator tests run the real one)."""
+    import pandas as pd
+
+    from alphadia_b200 import _lib
+    from alphadia_b200.scoring import DEFAULT_FEATURE_COLUMNS, FRAGMENT_COLUMNS, CandidateScoring
+
+    g, raw, lib, p = _golden(name)
+    _, pdf, fdf, _, _ = H.workload(name)
+    score = oracle_lib.score_candidates_4d if name == "parity_4d" else oracle_lib.score_candidates
+
+    class HostRaw:
+        device = 0
+
+        def __init__(self, arrays):
+            self.arrays = arrays
+
+        def last_timing(self):
+            return {}
+
+    class HostLibrary:
+        def __init__(self, arrays, device=0):
+            self.arrays = arrays
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(_lib, "device_rawfile_for", lambda dia_data, adapted: HostRaw(adapted))
+    monkeypatch.setattr(_lib, "DeviceLibrary", HostLibrary)
+    monkeypatch.setattr(_lib, "score_candidates", lambda dev_raw, dev_lib, cfg, cin: score(dev_raw.arrays, dev_lib.arrays, cfg, cin))
+    cand_df = pd.DataFrame({c: g["cand_" + c] for c in INT_COLS + ["score", "elution_group_idx", "decoy"]})
+    scorer = CandidateScoring(dia_data=raw, precursors_flat=pdf.copy(), fragments_flat=fdf.copy(), config=H.scoring_config(**VARIANTS[tag]),
+                              rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+                              fragment_mz_column="mz_library")
+    feat, frag = scorer(cand_df.copy())
+    # feature table: the reference builds the merged column lists from sets, so only the fixed parts of the order are pinned
+    ref_cols = [str(c) for c in g[f"feat{tag}_columns"]]
+    assert set(feat.columns) == set(ref_cols)
+    assert list(feat.columns[:48]) == ref_cols[:48] == DEFAULT_FEATURE_COLUMNS + ["precursor_idx", "rank"]
+    assert list(feat.columns[-4:]) == ref_cols[-4:] == ["delta_rt", "n_K", "n_R", "n_P"]
+    for c in ("precursor_idx", "rank", "n_K", "n_R", "n_P", "score", "frame_start", "frame_stop", "decoy", "charge"):
+        assert feat[c].dtype == g[f"feat{tag}_{c}"].dtype, (c, feat[c].dtype)
+        assert np.array_equal(feat[c].values, g[f"feat{tag}_{c}"]), c
+    assert feat["delta_rt"].dtype == np.float32 and np.array_equal(feat["delta_rt"].values, g[f"feat{tag}_delta_rt"])
+    F, G = feat[DEFAULT_FEATURE_COLUMNS].values, g[f"feat{tag}_matrix"]
+    assert F.dtype == np.float32
+    for j in range(46):
+        if j in BLAS_FEATURES:
+            assert H.rel_err(F[:, j], G[:, j]).max() < 1e-4, j
+        else:
+            assert ((F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))).all(), f"feature {j} not bit-exact"
+    # fragment table: exact column order, dtypes, rows
+    assert list(frag.columns) == FRAGMENT_COLUMNS + ["elution_group_idx", "decoy"]
+    for c in frag.columns:
+        assert frag[c].dtype == g[f"frag{tag}_{c}"].dtype, (c, frag[c].dtype)
+        if c == "correlation":
+            assert H.rel_err(frag[c].values, g[f"frag{tag}_{c}"]).max() < 1e-4
+        else:
+            assert np.array_equal(frag[c].values, g[f"frag{tag}_{c}"]), c
+
+
 # ---- FDR bookkeeping (SURVEY 8f.2): get_q_values / keep_best of the live reference ------------------------
 def _fdr_golden():
     import hashlib
