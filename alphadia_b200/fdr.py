@@ -1,6 +1,7 @@
-"""FDR bookkeeping around fragment competition — drop-ins for ``get_q_values`` and ``keep_best``
-(alphadia/fdr/fdr.py:195-297; both are called by ``perform_fdr``, fdr.py:157-186, once before and once after
-``FragmentCompetition``).  SURVEY 8f.2; the classifier itself is not part of this package.
+"""FDR bookkeeping around fragment competition — drop-ins for ``get_q_values``, ``keep_best`` and the ``perform_fdr``
+sequence that calls them (alphadia/fdr/fdr.py:25-297: classifier -> q-values -> fragment competition -> best per group ->
+q-values).  SURVEY 8f.2; the classifier itself is not part of this package: ``perform_fdr`` takes the caller's classifier
+object (``fit`` / ``predict_proba``), exactly like the reference.
 
 Same signatures, same returned DataFrames (row order, index, columns).  The multi-column stable sorts and the scans run on
 the device behind ``adb_q_values`` / ``adb_keep_best``; the host only packs the key columns.  No CPU fallback.
@@ -8,10 +9,17 @@ the device behind ``adb_q_values`` / ``adb_keep_best``; the host only packs the 
 
 from __future__ import annotations
 
+import logging
+
 import numpy as np
 import pandas as pd
 
 from alphadia_b200 import _lib
+from alphadia_b200.fragcomp import FragmentCompetition
+
+logger = logging.getLogger()
+
+max_dia_cycle_shape = 2  # fdr.py:19: fragment competition only for data without ion mobility
 
 
 def _integer_columns(df: pd.DataFrame, columns) -> list | None:
@@ -90,3 +98,70 @@ def keep_best(df: pd.DataFrame, score_column: str = "proba", group_columns: list
     df = df.reset_index(drop=True)
     keep = _lib.keep_best(df[score_column].to_numpy().astype(np.float64, copy=False), _pack_groups(df, group_columns))
     return df[keep.astype(bool)].reset_index(drop=True)
+
+
+def perform_fdr(  # fdr.py:25-192
+    classifier,
+    available_columns: list[str],
+    df_target: pd.DataFrame,
+    df_decoy: pd.DataFrame,
+    *,
+    competitive: bool = False,
+    group_channels: bool = True,
+    figure_path: str | None = None,
+    df_fragments: pd.DataFrame | None = None,
+    dia_cycle: np.ndarray | None = None,
+    fdr_heuristic: float = 0.1,
+    random_state: int | None = None,
+) -> pd.DataFrame:
+    """Same flow and result as the reference: drop rows with missing features, fit the caller's classifier on an 80 % split,
+    predict, q-values, fragment competition on the rows below ``fdr_heuristic`` (3-D data only), best row per group,
+    q-values again.  Sorts, scans and the competition run on the device; the classifier is the caller's."""
+    from sklearn.model_selection import train_test_split
+
+    target_len, decoy_len = len(df_target), len(df_decoy)
+    df_target.dropna(subset=available_columns, inplace=True)
+    df_decoy.dropna(subset=available_columns, inplace=True)
+    if target_len - len(df_target) > 0:
+        logger.warning(f"dropped {target_len - len(df_target)} target PSMs due to missing features")
+    if decoy_len - len(df_decoy) > 0:
+        logger.warning(f"dropped {decoy_len - len(df_decoy)} decoy PSMs due to missing features")
+    if np.abs(len(df_target) - len(df_decoy)) / ((len(df_target) + len(df_decoy)) / 2) > 0.1:
+        logger.warning(f"FDR calculation for {len(df_target)} target and {len(df_decoy)} decoy PSMs")
+        logger.warning("FDR calculation may be inaccurate as there is more than 10% difference in the number of target and decoy PSMs")
+    if random_state is not None:
+        logger.info(f"Using random state {random_state} for FDR calculation")
+
+    X = np.concatenate([df_target[available_columns].to_numpy(), df_decoy[available_columns].to_numpy()])
+    y = np.concatenate([np.zeros(len(df_target)), np.ones(len(df_decoy))])
+    try:  # fdr/utils.py:16-52 train_test_split_
+        X_train, _, y_train, _ = train_test_split(X, y, test_size=0.2, random_state=random_state)
+    except ValueError:
+        logger.warning("Too few PSMs for FDR classification, assigning qval=1.0 and proba=1.0 to all PSMs.")
+        psm_df = pd.concat([df_target, df_decoy])
+        psm_df["qval"] = 1.0
+        psm_df["proba"] = 1.0
+        return psm_df
+    classifier.fit(X_train, y_train)
+
+    psm_df = pd.concat([df_target, df_decoy])
+    psm_df["_decoy"] = y
+    if competitive:
+        group_columns = ["elution_group_idx", "channel"] if group_channels else ["elution_group_idx"]
+    else:
+        group_columns = ["precursor_idx"]
+    psm_df["proba"] = classifier.predict_proba(X)[:, 1]
+    psm_df = get_q_values(psm_df, "proba", "_decoy")  # already sorted by [proba, _decoy, precursor_idx] (fdr.py:151-155)
+
+    if dia_cycle is not None and dia_cycle.shape[2] <= max_dia_cycle_shape:
+        start_idx = psm_df["qval"].searchsorted(fdr_heuristic, side="left")
+        if start_idx == 0:
+            start_idx = len(psm_df)
+        if df_fragments is not None:
+            psm_df = FragmentCompetition()(psm_df.iloc[:start_idx], df_fragments, dia_cycle)
+
+    psm_df = keep_best(psm_df, group_columns=group_columns)
+    psm_df = get_q_values(psm_df, "proba", "_decoy")
+    if figure_path is not None:
+        logger.info("FDR figures are drawn by the reference's plot_fdr (alphadia/fdr/plotting.py); skipped here")
+    return psm_df

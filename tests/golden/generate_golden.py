@@ -1,6 +1,6 @@
 """Generate golden vectors by running the UNMODIFIED reference numba path (CPU, this container).
 
-    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr ...]
+    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ...]
 
 Needs /root/reference (read-only) and numba; pays ~6 min of JIT once per process.  Writes
 ``tests/golden/<name>.npz`` — inputs are NOT stored (they are regenerated from the seed by
@@ -250,6 +250,31 @@ def run_fdr():
     print(f"[fdr] {len(df)} rows -> q-values {len(q)}, final {len(final)}; wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def run_perform_fdr():
+    """perform_fdr of the unmodified reference (alphadia/fdr/fdr.py:25-192) with a deterministic stand-in classifier on the
+    scoring golden of parity_small -> tests/golden/perform_fdr_small.npz."""
+    from tests.helpers import FDR_FEATURE_COLUMNS, PERFORM_FDR_CASES, PseudoClassifier, perform_fdr_inputs
+
+    fdr = refshim.ref("alphadia.fdr.fdr")
+    g = np.load(os.path.join(HERE, "parity_small.npz"), allow_pickle=False)
+    raw = make_config_3d("parity_small")[0]
+    out = {"source_checksum": g["input_checksum"]}
+    for tag, case in PERFORM_FDR_CASES.items():
+        df_target, df_decoy, frag = perform_fdr_inputs(g)
+        res = fdr.perform_fdr(PseudoClassifier(), FDR_FEATURE_COLUMNS, df_target, df_decoy, competitive=case["competitive"],
+                              group_channels=case["group_channels"], df_fragments=frag if case["fragments"] else None,
+                              dia_cycle=raw.cycle, random_state=7)
+        print(f"[perform_fdr] {tag}: {len(df_target)} targets + {len(df_decoy)} decoys -> {len(res)} rows, "
+              f"{int((res['qval'] <= 0.01).sum())} at 1% FDR", flush=True)
+        for c in ("precursor_idx", "rank", "proba", "qval", "_decoy"):
+            out[f"{tag}__{c}"] = res[c].values
+        out[f"{tag}__index"] = res.index.values
+        out[f"{tag}__columns"] = np.array(list(res.columns))
+    path = os.path.join(HERE, "perform_fdr_small.npz")
+    np.savez_compressed(path, **out)
+    print(f"[perform_fdr] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def transpose_inputs(seed: int = 5, n_push: int = 1500, n_tof: int = 257):
     """Push-major CSR of a small synthetic timsTOF file: ragged pushes (20 % empty), ascending tof indices inside a push."""
     rng = np.random.default_rng(seed)
@@ -283,5 +308,7 @@ if __name__ == "__main__":
             run_variants(threads)
         elif n == "fdr":
             run_fdr()
+        elif n == "perform_fdr":
+            run_perform_fdr()
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d")))

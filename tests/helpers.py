@@ -162,3 +162,44 @@ def fdr_inputs(seed: int = 11, n: int = 6000):
     })
     df.index = rng.permutation(n) + 100
     return df
+
+
+class PseudoClassifier:
+    """Deterministic stand-in for the FDR classifier (fit is a no-op): probability of being a decoy from two correlation
+    features, rounded to two decimals so that ties occur.  Used identically by the golden generator (reference
+    perform_fdr) and by the tests (alphadia_b200.fdr.perform_fdr)."""
+
+    def fit(self, X, y):
+        self.fitted_rows = len(X)
+
+    def predict_proba(self, X):
+        z = np.clip(0.5 * (X[:, 0] + X[:, 1]), 0.0, 1.0)
+        p = np.round(1.0 - z, 2)
+        return np.stack([1.0 - p, p], axis=1)
+
+
+FDR_FEATURE_COLUMNS = ["intensity_correlation", "top3_frame_correlation", "mean_observation_score"]
+
+
+def perform_fdr_inputs(g):
+    """(df_target, df_decoy, df_fragments) from the scoring golden of parity_small; elution groups pair precursor 2k (target)
+    with 2k + 1 (decoy) so that the competitive mode has something to decide."""
+    import pandas as pd
+
+    from alphadia_b200.scoring import DEFAULT_FEATURE_COLUMNS
+
+    psm = pd.DataFrame(g["feat_matrix"], columns=DEFAULT_FEATURE_COLUMNS)
+    psm["precursor_idx"] = g["feat_precursor_idx"]
+    psm["rank"] = g["feat_rank"]
+    psm["decoy"] = g["feat_decoy"]
+    psm["elution_group_idx"] = (g["feat_precursor_idx"] // 2).astype(np.uint32)
+    psm["channel"] = np.zeros(len(psm), dtype=np.uint32)
+    frag = pd.DataFrame({"precursor_idx": g["frag_precursor_idx"], "rank": g["frag_rank"], "mz_observed": g["frag_mz_observed"]})
+    return psm[psm["decoy"] == 0].copy(), psm[psm["decoy"] == 1].copy(), frag
+
+
+PERFORM_FDR_CASES = {
+    "competitive_fragments": dict(competitive=True, group_channels=True, fragments=True),
+    "competitive_no_channels": dict(competitive=True, group_channels=False, fragments=True),
+    "plain": dict(competitive=False, group_channels=True, fragments=False),
+}

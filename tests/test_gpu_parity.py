@@ -885,3 +885,12 @@ def test_fdr_bookkeeping(engine, oracle_lib):
         engine.keep_best(np.array([np.nan]), np.array([0], np.uint64))
     with pytest.raises(ValueError, match="_decoy"):
         fdr.get_q_values(pd.DataFrame({"precursor_idx": [0], "proba": [0.5], "_decoy": [2]}))
+
+
+def test_perform_fdr_matches_reference_golden(engine):
+    """The perform_fdr sequence (q-values -> fragment competition -> best per group -> q-values) on the device against the
+    reference's perform_fdr run with the same stand-in classifier (tests/golden/perform_fdr_small.npz)."""
+    from alphadia_b200 import fdr
+    from tests.test_oracle_golden import check_perform_fdr_against_golden
+
+    check_perform_fdr_against_golden(fdr)

@@ -430,6 +430,8 @@ def host_fdr_with_oracle(monkeypatch, oracle_lib):
 
     monkeypatch.setattr(_lib, "q_values", lambda score, decoy, extra, device=None: oracle_lib.q_values(score, decoy, extra))
     monkeypatch.setattr(_lib, "keep_best", lambda score, group, device=None: oracle_lib.keep_best(score, group))
+    monkeypatch.setattr(_lib, "fragment_competition", lambda ws, we, rt, fs, fe, mz, rt_tol, ppm, device=None:
+                        oracle_lib.fragment_competition(ws, we, rt, fs, fe, mz, rt_tol, ppm).astype(bool))
     return fdr
 
 
@@ -450,3 +452,32 @@ def test_fdr_oracle_and_host_packing_vs_reference(oracle_lib, monkeypatch):
         assert np.array_equal(kept.index.values, np.arange(len(kept)))
     final = fdr.get_q_values(fdr.keep_best(q, group_columns=["elution_group_idx", "channel"]), "proba", "_decoy")
     assert np.array_equal(final["row"].values, g["final_row"]) and np.array_equal(final["qval"].values, g["final_qval"])
+
+
+def check_perform_fdr_against_golden(fdr):
+    """alphadia_b200.fdr.perform_fdr == the reference's perform_fdr (fdr.py:25-192) with the same stand-in classifier:
+    same rows in the same order, same index, same columns, probabilities and q-values bit-identical."""
+    import os
+
+    path = os.path.join(H.GOLDEN_DIR, "perform_fdr_small.npz")
+    g_scores = H.load_golden("parity_small")
+    if not os.path.exists(path) or g_scores is None:
+        pytest.skip("golden perform_fdr_small.npz missing")
+    g = np.load(path, allow_pickle=False)
+    if str(g["source_checksum"]) != str(g_scores["input_checksum"]):
+        pytest.skip("perform_fdr golden was made from another scoring golden")
+    raw = H.workload("parity_small")[0]
+    for tag, case in H.PERFORM_FDR_CASES.items():
+        df_target, df_decoy, frag = H.perform_fdr_inputs(g_scores)
+        res = fdr.perform_fdr(H.PseudoClassifier(), H.FDR_FEATURE_COLUMNS, df_target, df_decoy, competitive=case["competitive"],
+                              group_channels=case["group_channels"], df_fragments=frag if case["fragments"] else None,
+                              dia_cycle=raw.cycle, random_state=7)
+        assert list(res.columns) == [str(c) for c in g[f"{tag}__columns"]], tag
+        assert np.array_equal(res.index.values, g[f"{tag}__index"]), tag
+        for c in ("precursor_idx", "rank", "proba", "qval", "_decoy"):
+            assert np.array_equal(res[c].values, g[f"{tag}__{c}"]), (tag, c)
+        assert 0 < len(res) < len(df_target) + len(df_decoy)
+
+
+def test_perform_fdr_vs_reference(oracle_lib, monkeypatch):
+    check_perform_fdr_against_golden(host_fdr_with_oracle(monkeypatch, oracle_lib))
