@@ -388,6 +388,14 @@ CONFIGS_4D = {
         cycle_seconds=0.6, mob_hi=1.30, mob_lo=0.70, tof_ppm=4.0, mz_lo=150.0, mz_hi=1900.0,
         noise_per_push=6, rt_tolerance=12.0, mobility_tolerance=0.12, planted_fraction=0.7,
     ),
+    # like parity_4d, but every MS2 frame isolates ONE window on all scans and neighbouring windows overlap by 60 Th: about a
+    # third of the precursors are seen by two frames of the cycle (two observations per candidate in scoring)
+    "parity_4d_overlap": dict(
+        seed=23, n_precursors=240, n_cycles=90, n_ms2_frames=3, n_scans=96, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=0.6, mob_hi=1.30, mob_lo=0.70, tof_ppm=4.0, mz_lo=150.0, mz_hi=1900.0,
+        noise_per_push=6, rt_tolerance=12.0, mobility_tolerance=0.12, planted_fraction=0.7,
+        diagonal=False, window_overlap=30.0,
+    ),
     # config 4 of BASELINE.json: 200k precursors, (1 + 8) x 928 cycle, 800 cycles
     "config4": dict(
         seed=4, n_precursors=200_000, n_cycles=800, n_ms2_frames=8, n_scans=928, quad_lo=400.0, quad_hi=1200.0,
@@ -422,10 +430,14 @@ def make_config_4d(name: str, *, seed: int | None = None, n_precursors: int | No
     band = (p["quad_hi"] - p["quad_lo"]) / p["n_ms2_frames"]
     cycle = np.full((1, Fr, Sc, 2), -1.0, dtype=np.float64)
     half = Sc // 2
+    diagonal, overlap = p.get("diagonal", True), float(p.get("window_overlap", 0.0))
     for f in range(1, Fr):
         lo = p["quad_lo"] + band * (f - 1)
-        cycle[0, f, :half, 0], cycle[0, f, :half, 1] = lo + band / 2, lo + band
-        cycle[0, f, half:, 0], cycle[0, f, half:, 1] = lo, lo + band / 2
+        if diagonal:
+            cycle[0, f, :half, 0], cycle[0, f, :half, 1] = lo + band / 2, lo + band
+            cycle[0, f, half:, 0], cycle[0, f, half:, 1] = lo, lo + band / 2
+        else:  # one window per frame on all scans, widened so that neighbouring frames overlap
+            cycle[0, f, :, 0], cycle[0, f, :, 1] = lo - overlap, lo + band + overlap
 
     # library: precursors live inside one (frame, half) window, mobility inside that half
     P, F = p["n_precursors"], 12
@@ -435,8 +447,12 @@ def make_config_4d(name: str, *, seed: int | None = None, n_precursors: int | No
                                              rt_hi=run_s - margin, with_strings=with_strings)
     wf = rng.integers(1, Fr, size=P)
     wh = rng.integers(0, 2, size=P)
-    wlo = p["quad_lo"] + band * (wf - 1) + np.where(wh == 0, band / 2, 0.0)
-    pmz = (wlo + rng.uniform(0.5, band / 2 - 3.5, size=P)).astype(np.float32)
+    if diagonal:
+        wlo = p["quad_lo"] + band * (wf - 1) + np.where(wh == 0, band / 2, 0.0)
+        pmz = (wlo + rng.uniform(0.5, band / 2 - 3.5, size=P)).astype(np.float32)
+    else:
+        wlo = p["quad_lo"] + band * (wf - 1)
+        pmz = (wlo + rng.uniform(0.5, band - 3.5, size=P)).astype(np.float32)
     precursor_df["mz_library"] = pmz
     mob_span = (p["mob_hi"] - p["mob_lo"]) / 2
     edge = p["mobility_tolerance"] * 1.2
@@ -501,7 +517,14 @@ def make_config_4d(name: str, *, seed: int | None = None, n_precursors: int | No
             sig_int.append(np.minimum(inten[m], 60000.0))
 
         for k in range(F):
-            add(wf[planted], fmz_all[fs + k] * (1 + rng.normal(0, 1.5e-6, size=n_plant)), fint_all[fs + k] * 6000.0)
+            jittered = fmz_all[fs + k] * (1 + rng.normal(0, 1.5e-6, size=n_plant))
+            add(wf[planted], jittered, fint_all[fs + k] * 6000.0)
+            if not diagonal:  # the neighbouring frames whose widened window also isolates the precursor see it too (weaker)
+                for step in (-1, 1):
+                    nf = wf[planted] + step
+                    nlo = p["quad_lo"] + band * (nf - 1) - overlap
+                    seen = (nf >= 1) & (nf < Fr) & (pmz[planted] >= nlo) & (pmz[planted] <= nlo + band + 2 * overlap)
+                    add(np.where(seen, nf, wf[planted]), jittered, np.where(seen, fint_all[fs + k] * 3000.0, 0.0))
         for i, ab in enumerate([0.5, 0.3, 0.15]):
             add(np.zeros(n_plant, np.int64), (pmz[planted].astype(np.float64) + i * ISOTOPE_MASS_DIFF / pch)
                 * (1 + rng.normal(0, 1.5e-6, size=n_plant)), np.full(n_plant, ab * 20000.0))

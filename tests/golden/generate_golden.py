@@ -311,4 +311,4 @@ if __name__ == "__main__":
         elif n == "perform_fdr":
             run_perform_fdr()
         else:
-            run(n, threads, variants=(n in ("parity_small", "parity_4d")))
+            run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap")))

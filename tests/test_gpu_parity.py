@@ -894,3 +894,29 @@ def test_perform_fdr_matches_reference_golden(engine):
     from tests.test_oracle_golden import check_perform_fdr_against_golden
 
     check_perform_fdr_against_golden(fdr)
+
+
+def test_4d_two_observations_per_candidate(engine, oracle_lib):
+    """timsTOF file whose neighbouring quadrupole windows overlap (parity_4d_overlap): about a fifth of the candidates are
+    seen by two frames of the cycle, so the 4-D scoring kernel runs with n_observations = 2 (observation importance,
+    collapsed MS1, per-observation profiles)."""
+    name = "parity_4d_overlap"
+    raw, lib, p, draw, dlib = _device_objects(engine, name)
+    cfg = _sel_cfg_4d(p)
+    kernel = H.default_kernel(raw)
+    got = engine.select_candidates(draw, dlib, cfg, kernel)
+    ref = oracle_lib.select_candidates_4d(raw, lib, cfg, kernel)
+    assert_candidates_equal(got, ref)
+    m = got["score"] > 0
+    assert m.sum() > 100
+    cin, keep = H.candidates_in_from_arrays(lib, {c: got[c][m] for c in INT_COLS})
+    for variant in ("default", "legacy", "k6"):
+        scfg = H.scoring_config(**SCORING_VARIANTS[variant]).to_struct()
+        s_got = engine.score_candidates(draw, dlib, scfg, cin)
+        s_ref = oracle_lib.score_candidates_4d(raw, lib, scfg, cin)
+        v = s_ref["valid"].astype(bool)
+        assert (s_ref["features"][v, 17] == 2).sum() >= 10 and (s_ref["features"][v, 17] == 1).sum() >= 10
+        assert_scores_close(s_got, s_ref, what=f"{name}/{variant}")
+    dlib.close(); draw.close()
+    for tag in GOLDEN_TAGS:
+        _check_scores_against_golden(engine, name, tag) if H.load_golden(name) is not None else None
