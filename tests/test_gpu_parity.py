@@ -918,5 +918,5 @@ def test_4d_two_observations_per_candidate(engine, oracle_lib):
         assert (s_ref["features"][v, 17] == 2).sum() >= 10 and (s_ref["features"][v, 17] == 1).sum() >= 10
         assert_scores_close(s_got, s_ref, what=f"{name}/{variant}")
     dlib.close(); draw.close()
-    for tag in GOLDEN_TAGS:
-        _check_scores_against_golden(engine, name, tag) if H.load_golden(name) is not None else None
+    # the oracle itself is pinned against the live reference on this file (tests/golden/parity_4d_overlap.npz,
+    # tests/test_oracle_golden.py::test_scoring_4d_vs_reference[parity_4d_overlap-*])

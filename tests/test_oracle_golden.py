@@ -104,8 +104,9 @@ def test_fragcomp_vs_reference(name, oracle_lib):
 
 
 # ---- timsTOF (4-D) -------------------------------------------------------------------------------
-def test_selection_4d_bit_exact_vs_reference(oracle_lib):
-    g, raw, lib, p = _golden("parity_4d")
+@pytest.mark.parametrize("name", ["parity_4d", "parity_4d_overlap"])
+def test_selection_4d_bit_exact_vs_reference(name, oracle_lib):
+    g, raw, lib, p = _golden(name)
     k = H.default_kernel(raw)
     assert k.shape == (30, 30) and np.array_equal(k, g["sel_kernel"])
     cfg = H.selection_config(p["rt_tolerance"], mobility_tolerance=p["mobility_tolerance"]).to_struct()
@@ -120,10 +121,14 @@ def test_selection_4d_bit_exact_vs_reference(oracle_lib):
 
 
 @pytest.mark.parametrize("tag", ["", "_legacy", "_k6"])
-def test_scoring_4d_vs_reference(tag, oracle_lib):
-    g, raw, lib, p = _golden("parity_4d")
+@pytest.mark.parametrize("name", ["parity_4d", "parity_4d_overlap"])
+def test_scoring_4d_vs_reference(name, tag, oracle_lib):
+    g, raw, lib, p = _golden(name)
     if f"feat{tag}_matrix" not in g:
-        pytest.skip(f"golden parity_4d has no {tag} variant")
+        pytest.skip(f"golden {name} has no {tag} variant")
+    if name == "parity_4d_overlap":  # neighbouring windows overlap: candidates seen by two frames of the cycle
+        n_obs = g[f"feat{tag}_matrix"][:, 17]
+        assert (n_obs == 2).sum() >= 10 and (n_obs == 1).sum() >= 10
     cand = {c: g["cand_" + c] for c in INT_COLS}
     cin, keep = H.candidates_in_from_arrays(lib, cand)
     arrs = oracle_lib.score_candidates_4d(raw, lib, H.scoring_config(**VARIANTS[tag]).to_struct(), cin)
