@@ -1,6 +1,6 @@
 """Generate golden vectors by running the UNMODIFIED reference numba path (CPU, this container).
 
-    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ...]
+    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ragged ...]
 
 Needs /root/reference (read-only) and numba; pays ~6 min of JIT once per process.  Writes
 ``tests/golden/<name>.npz`` — inputs are NOT stored (they are regenerated from the seed by
@@ -275,6 +275,53 @@ def run_perform_fdr():
     print(f"[perform_fdr] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def run_ragged(threads: int):
+    """Selection and scoring of the unmodified reference on ragged libraries (tests.helpers.ragged_library_frames), 3-D and
+    4-D -> tests/golden/ragged.npz."""
+    from tests.helpers import ragged_library_frames
+
+    sel_mod = refshim.ref("alphadia.search.selection.selection")
+    cfg_mod = refshim.ref("alphadia.search.selection.config_df")
+    sc_mod = refshim.ref("alphadia.search.scoring.scoring")
+    sccfg_mod = refshim.ref("alphadia.search.scoring.config")
+    out = {}
+    for name in ("parity_small", "parity_4d"):
+        if name in CONFIGS_4D:
+            raw, precursor_df, fragment_df, p = make_config_4d(name)
+            dia = refshim.RefDiaData4D(raw)
+        else:
+            raw, precursor_df, fragment_df, p = make_config_3d(name)
+            dia = refshim.RefDiaData(raw)
+        out[f"{name}__input_checksum"] = np.array(input_checksum(raw, precursor_df, fragment_df))
+        pdf, fdf = ragged_library_frames(precursor_df, fragment_df, float(np.max(raw.rt_values)))
+        cfg = cfg_mod.CandidateSelectionConfig()
+        cfg.update({**SELECTION_BASE, "rt_tolerance": float(p["rt_tolerance"]),
+                    "mobility_tolerance": float(p.get("mobility_tolerance", 0.1)),
+                    "candidate_count": 3, "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0})
+        sel = sel_mod.CandidateSelection(
+            dia, pdf.copy(), fdf.copy(), cfg, rt_column="rt_library", mobility_column="mobility_library",
+            precursor_mz_column="mz_library", fragment_mz_column="mz_library", fwhm_rt=5.0, fwhm_mobility=0.01)
+        cand = sel(thread_count=threads)
+        print(f"[ragged] {name}: {len(cand)} candidates", flush=True)
+        for c in cand.columns:
+            out[f"{name}__cand_{c}"] = cand[c].values
+        sc_cfg = sccfg_mod.CandidateScoringConfig()
+        sc_cfg.update({**SCORING_BASE, "precursor_mz_tolerance": 5, "fragment_mz_tolerance": 10})
+        scorer = sc_mod.CandidateScoring(
+            dia_data=dia, precursors_flat=pdf.copy(), fragments_flat=fdf.copy(), config=sc_cfg, rt_column="rt_library",
+            mobility_column="mobility_library", precursor_mz_column="mz_library", fragment_mz_column="mz_library")
+        feat, frag = scorer(cand.copy(), thread_count=threads, include_decoy_fragment_features=True)
+        print(f"[ragged] {name}: {len(feat)} feature rows, {len(frag)} fragment rows", flush=True)
+        out[f"{name}__feat_matrix"] = feat[sc_mod.DEFAULT_FEATURE_COLUMNS].values.astype(np.float32)
+        out[f"{name}__feat_precursor_idx"] = feat["precursor_idx"].values
+        out[f"{name}__feat_rank"] = feat["rank"].values
+        for c in frag.columns:
+            out[f"{name}__frag_{c}"] = frag[c].values
+    path = os.path.join(HERE, "ragged.npz")
+    np.savez_compressed(path, **out)
+    print(f"[ragged] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def transpose_inputs(seed: int = 5, n_push: int = 1500, n_tof: int = 257):
     """Push-major CSR of a small synthetic timsTOF file: ragged pushes (20 % empty), ascending tof indices inside a push."""
     rng = np.random.default_rng(seed)
@@ -310,5 +357,7 @@ if __name__ == "__main__":
             run_fdr()
         elif n == "perform_fdr":
             run_perform_fdr()
+        elif n == "ragged":
+            run_ragged(threads)
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap")))

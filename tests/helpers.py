@@ -203,3 +203,32 @@ PERFORM_FDR_CASES = {
     "competitive_no_channels": dict(competitive=True, group_channels=False, fragments=True),
     "plain": dict(competitive=False, group_channels=True, fragments=False),
 }
+
+
+def ragged_library_frames(precursor_df, fragment_df, rt_max: float, seed: int = 17):
+    """Library shapes the reference meets in practice, as DataFrames (tests/golden/ragged.npz): 0-12 fragments for every
+    fifth precursor, shared ions (cardinality 2), duplicate and nearly identical fragment m/z, retention times before and
+    after the run, charges 1-4."""
+    rng = np.random.default_rng(seed)
+    pdf, fdf = precursor_df.copy(), fragment_df.copy()
+    P = len(pdf)
+    start = pdf["flat_frag_start_idx"].values.astype(np.int64)
+    stop = pdf["flat_frag_stop_idx"].values.copy()
+    for i in range(0, P, 5):
+        stop[i] = start[i] + int(rng.integers(0, 13))
+    pdf["flat_frag_stop_idx"] = stop
+    card = fdf["cardinality"].values.copy()
+    card[rng.random(len(card)) < 0.15] = 2
+    fdf["cardinality"] = card
+    mz = fdf["mz_library"].values.copy()
+    for i in range(1, P, 7):
+        s = start[i]
+        mz[s + 1] = mz[s]
+        mz[s + 3] = np.float32(mz[s + 2] * (1 + 6e-6))
+    fdf["mz_library"] = mz
+    rt = pdf["rt_library"].values.copy()
+    rt[::11] = np.float32(-50.0)
+    rt[5::13] = np.float32(rt_max + 500.0)
+    pdf["rt_library"] = rt
+    pdf["charge"] = rng.integers(1, 5, size=P).astype(np.uint8)
+    return pdf, fdf

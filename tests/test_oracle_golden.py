@@ -289,6 +289,52 @@ def test_transpose_oracle_vs_reference_golden(oracle_lib):
     assert np.array_equal(p1, [0, 2, 2, 3]) and np.array_equal(i1, [0, 0, 0, 0, 4, 4]) and np.array_equal(v1, [9, 8, 7, 6])
 
 
+# ---- ragged libraries (tests/golden/ragged.npz) ---------------------------------------------------------------
+@pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
+def test_ragged_library_vs_reference(name, oracle_lib):
+    """0-12 fragments per precursor, shared ions, duplicate fragment m/z, retention times outside the run, charges 1-4:
+    selection bit-exact and scoring at the usual bar against the live reference."""
+    import os
+
+    from alphadia_b200.library import assemble_library_arrays
+
+    path = os.path.join(H.GOLDEN_DIR, "ragged.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden ragged.npz missing")
+    g = np.load(path, allow_pickle=False)
+    raw, pdf0, fdf0, _, p = H.workload(name)
+    if f"{name}__input_checksum" not in g or str(g[f"{name}__input_checksum"]) != H.input_checksum(raw, pdf0, fdf0):
+        pytest.skip("golden not applicable")
+    pdf, fdf = H.ragged_library_frames(pdf0, fdf0, float(np.max(raw.rt_values)))
+    lib = assemble_library_arrays(pdf, fdf, "rt_library", "mobility_library", "mz_library", "mz_library")
+    is4d = "mobility_tolerance" in p
+    kw = {"mobility_tolerance": p["mobility_tolerance"]} if is4d else {}
+    cfg = H.selection_config(p["rt_tolerance"], **kw).to_struct()
+    arrs = (oracle_lib.select_candidates_4d if is4d else oracle_lib.select_candidates)(raw, lib, cfg, H.default_kernel(raw))
+    m = arrs["score"] > 0
+    key = f"{name}__cand_"
+    assert m.sum() == len(g[key + "precursor_idx"]) > 100
+    for c in INT_COLS:
+        assert np.array_equal(arrs[c][m].astype(np.int64), g[key + c].astype(np.int64)), c
+    assert np.array_equal(arrs["score"][m], g[key + "score"])
+    cin, keep = H.candidates_in_from_arrays(lib, {c: g[key + c] for c in INT_COLS})
+    sc = (oracle_lib.score_candidates_4d if is4d else oracle_lib.score_candidates)(raw, lib, H.scoring_config().to_struct(), cin)
+    v = sc["valid"].astype(bool)
+    assert np.array_equal(keep["precursor_idx"][v], g[f"{name}__feat_precursor_idx"])
+    assert np.array_equal(keep["rank"][v], g[f"{name}__feat_rank"])
+    F, G = sc["features"][v], g[f"{name}__feat_matrix"]
+    for j in range(46):
+        if j in BLAS_FEATURES:
+            assert H.rel_err(F[:, j], G[:, j]).max() < 1e-4, j
+        else:
+            assert ((F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))).all(), f"feature {j} not bit-exact"
+    fm = sc["fragment_mz_library"] > 0
+    assert fm.sum() == len(g[f"{name}__frag_mz_library"])
+    for k, v2 in FRAG_MAP.items():
+        a, b = sc[v2][fm], g[f"{name}__frag_{k}"]
+        assert np.array_equal(a, b) if k != "correlation" else H.rel_err(a, b).max() < 1e-4, k
+
+
 # ---- CandidateSelection.__call__ host side: the returned table (columns, order, dtypes) vs the reference's -------------
 @pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
 def test_candidate_selection_table_vs_reference(name, oracle_lib, monkeypatch):
