@@ -532,3 +532,32 @@ def check_perform_fdr_against_golden(fdr):
 
 def test_perform_fdr_vs_reference(oracle_lib, monkeypatch):
     check_perform_fdr_against_golden(host_fdr_with_oracle(monkeypatch, oracle_lib))
+
+
+def test_fdr_key_packing(oracle_lib, monkeypatch):
+    """Host packing of tie-break and group columns: lexicographic order of several integer columns, non-integer group
+    columns, and the inputs that must be refused."""
+    import pandas as pd
+
+    fdr = host_fdr_with_oracle(monkeypatch, oracle_lib)
+    rng = np.random.default_rng(5)
+    n = 4000
+    df = pd.DataFrame({"proba": np.round(rng.random(n), 1), "_decoy": rng.integers(0, 2, n), "a": rng.integers(0, 2 ** 20, n),
+                       "b": rng.integers(0, 2 ** 31, n).astype(np.int64), "flag": rng.random(n) < 0.5,
+                       "name": rng.choice(np.array(["x", "y", "zz", "w"], dtype=object), n), "f": np.round(rng.random(n), 1)})
+    df.loc[::7, "a"] = 5  # ties in the first extra column so that the second decides
+    got = fdr.get_q_values(df, extra_sort_columns=["a", "b"])
+    ref = df.sort_values(["proba", "_decoy", "a", "b"])
+    assert np.array_equal(got.index.values, ref.index.values)
+    got = fdr.get_q_values(df, extra_sort_columns=[])
+    assert np.array_equal(got.index.values, df.sort_values(["proba", "_decoy"], kind="stable").index.values)
+    for cols in (["name"], ["name", "a"], ["f"], ["flag", "a"], ["a", "b"]):
+        kept = fdr.keep_best(df, group_columns=cols)
+        ref = df.reset_index(drop=True).sort_values(["proba", *cols]).groupby(cols).head(1).sort_index().reset_index(drop=True)
+        pd.testing.assert_frame_equal(kept, ref)
+    with pytest.raises(NotImplementedError):
+        fdr.get_q_values(df.assign(a=-df["a"]), extra_sort_columns=["a"])
+    with pytest.raises(NotImplementedError):
+        fdr.get_q_values(df, extra_sort_columns=["name"])
+    with pytest.raises(NotImplementedError):
+        fdr.get_q_values(df.assign(a=df["a"].values.astype(np.int64) * 2 ** 30, b=df["b"].values * 2 ** 10), extra_sort_columns=["a", "b"])
