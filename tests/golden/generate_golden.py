@@ -1,6 +1,6 @@
 """Generate golden vectors by running the UNMODIFIED reference numba path (CPU, this container).
 
-    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ragged ...]
+    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ragged edge scoring_variants ...]
 
 Needs /root/reference (read-only) and numba; pays ~6 min of JIT once per process.  Writes
 ``tests/golden/<name>.npz`` — inputs are NOT stored (they are regenerated from the seed by
@@ -322,6 +322,87 @@ def run_ragged(threads: int):
     print(f"[ragged] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def run_edge(threads: int):
+    """CandidateScoring of the unmodified reference on hand-made candidate windows (tests.helpers.edge_candidate_frame),
+    3-D and 4-D -> tests/golden/edge.npz."""
+    from tests.helpers import edge_candidate_frame
+
+    sc_mod = refshim.ref("alphadia.search.scoring.scoring")
+    sccfg_mod = refshim.ref("alphadia.search.scoring.config")
+    out = {}
+    for name in ("parity_small", "parity_4d"):
+        if name in CONFIGS_4D:
+            raw, precursor_df, fragment_df, p = make_config_4d(name)
+            dia = refshim.RefDiaData4D(raw)
+        else:
+            raw, precursor_df, fragment_df, p = make_config_3d(name)
+            dia = refshim.RefDiaData(raw)
+        out[f"{name}__input_checksum"] = np.array(input_checksum(raw, precursor_df, fragment_df))
+        cand = edge_candidate_frame(name)
+        for c in cand.columns:
+            out[f"{name}__cand_{c}"] = cand[c].values
+        sc_cfg = sccfg_mod.CandidateScoringConfig()
+        sc_cfg.update({**SCORING_BASE, "precursor_mz_tolerance": 5, "fragment_mz_tolerance": 10})
+        scorer = sc_mod.CandidateScoring(
+            dia_data=dia, precursors_flat=precursor_df.copy(), fragments_flat=fragment_df.copy(), config=sc_cfg,
+            rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+            fragment_mz_column="mz_library")
+        feat, frag = scorer(cand.copy(), thread_count=threads, include_decoy_fragment_features=True)
+        print(f"[edge] {name}: {len(cand)} candidates -> {len(feat)} feature rows, {len(frag)} fragment rows", flush=True)
+        out[f"{name}__feat_matrix"] = feat[sc_mod.DEFAULT_FEATURE_COLUMNS].values.astype(np.float32)
+        out[f"{name}__feat_precursor_idx"] = feat["precursor_idx"].values
+        out[f"{name}__feat_rank"] = feat["rank"].values
+        for c in frag.columns:
+            out[f"{name}__frag_{c}"] = frag[c].values
+    path = os.path.join(HERE, "edge.npz")
+    np.savez_compressed(path, **out)
+    print(f"[edge] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
+def run_scoring_variants(threads: int):
+    """CandidateScoring of the unmodified reference with a fitted quadrupole model (sigma / delta_mu of SimpleQuadrupoleJit,
+    quadrupole.py:46-115) and with other tolerances, on the golden candidates of a 3-D and a two-observation 4-D file
+    -> tests/golden/scoring_variants.npz."""
+    from tests.helpers import SCORING_VARIANT_FILES, SCORING_VARIANTS_EXTRA
+
+    sc_mod = refshim.ref("alphadia.search.scoring.scoring")
+    sccfg_mod = refshim.ref("alphadia.search.scoring.config")
+    quad_mod = refshim.ref("alphadia.search.scoring.quadrupole")
+    out = {}
+    for name in SCORING_VARIANT_FILES:
+        if name in CONFIGS_4D:
+            raw, precursor_df, fragment_df, p = make_config_4d(name)
+            dia = refshim.RefDiaData4D(raw)
+        else:
+            raw, precursor_df, fragment_df, p = make_config_3d(name)
+            dia = refshim.RefDiaData(raw)
+        g = np.load(os.path.join(HERE, f"{name}.npz"), allow_pickle=False)
+        assert str(g["input_checksum"]) == input_checksum(raw, precursor_df, fragment_df)
+        out[f"{name}__input_checksum"] = g["input_checksum"]
+        cand = pd.DataFrame({k[len("cand_"):]: g[k] for k in g.files if k.startswith("cand_")})
+        for tag, var in SCORING_VARIANTS_EXTRA.items():
+            sc_cfg = sccfg_mod.CandidateScoringConfig()
+            sc_cfg.update({**SCORING_BASE, "precursor_mz_tolerance": 5, "fragment_mz_tolerance": 10, **var["config"]})
+            quad = quad_mod.SimpleQuadrupole(raw.cycle)
+            quad.jit.sigma[:] = var["quad_sigma"]
+            quad.jit.delta_mu[:] = var["quad_delta_mu"]
+            scorer = sc_mod.CandidateScoring(
+                dia_data=dia, precursors_flat=precursor_df.copy(), fragments_flat=fragment_df.copy(), config=sc_cfg,
+                quadrupole_calibration=quad, rt_column="rt_library", mobility_column="mobility_library",
+                precursor_mz_column="mz_library", fragment_mz_column="mz_library")
+            feat, frag = scorer(cand.copy(), thread_count=threads, include_decoy_fragment_features=True)
+            print(f"[scoring_variants] {name}/{tag}: {len(feat)} feature rows, {len(frag)} fragment rows", flush=True)
+            key = f"{name}__{tag}__"
+            out[key + "feat_matrix"] = feat[sc_mod.DEFAULT_FEATURE_COLUMNS].values.astype(np.float32)
+            out[key + "feat_precursor_idx"] = feat["precursor_idx"].values
+            out[key + "feat_rank"] = feat["rank"].values
+            for c in frag.columns:
+                out[key + f"frag_{c}"] = frag[c].values
+    path = os.path.join(HERE, "scoring_variants.npz")
+    np.savez_compressed(path, **out)
+    print(f"[scoring_variants] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def transpose_inputs(seed: int = 5, n_push: int = 1500, n_tof: int = 257):
     """Push-major CSR of a small synthetic timsTOF file: ragged pushes (20 % empty), ascending tof indices inside a push."""
     rng = np.random.default_rng(seed)
@@ -359,5 +440,9 @@ if __name__ == "__main__":
             run_perform_fdr()
         elif n == "ragged":
             run_ragged(threads)
+        elif n == "edge":
+            run_edge(threads)
+        elif n == "scoring_variants":
+            run_scoring_variants(threads)
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap")))

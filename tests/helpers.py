@@ -232,3 +232,53 @@ def ragged_library_frames(precursor_df, fragment_df, rt_max: float, seed: int = 
     pdf["rt_library"] = rt
     pdf["charge"] = rng.integers(1, 5, size=P).astype(np.uint8)
     return pdf, fdf
+
+
+def edge_candidate_frame(name: str, seed: int = 5):
+    """Hand-made candidate windows for the scoring edge-case golden (tests/golden/edge.npz): widths from 1 to 241 cycles,
+    windows clipped at the first / last cycle of the run, for timsTOF files also 1-scan to full-height scan windows.
+    One candidate per precursor, so (precursor_idx, rank) stays unique."""
+    import pandas as pd
+
+    raw, pdf, fdf, lib, p = workload(name)
+    rng = np.random.default_rng(seed)
+    P = len(pdf)
+    n = min(400, P)
+    rows = np.sort(rng.permutation(P)[:n])
+    ncyc = int(raw.precursor_cycle_max_index)
+    centers = rng.integers(0, ncyc, n)
+    half = rng.choice([0, 1, 2, 3, 7, 14, 40, 120], n)
+    c0 = np.clip(centers - half, 0, ncyc - 1)
+    c1 = np.clip(centers + half + 1, 1, ncyc)
+    if name in CONFIGS_4D:
+        Fr, Sc, z = raw.cycle.shape[1], raw.cycle.shape[2], int(raw.zeroth_frame)
+        sc_c = rng.integers(0, Sc, n)
+        sh = rng.choice([0, 1, 4, 9, 20, Sc], n)
+        scan_center, scan_start, scan_stop = sc_c, np.clip(sc_c - sh, 0, Sc - 1), np.clip(sc_c + sh + 1, 1, Sc)
+        frame_center = np.minimum(centers * Fr + z, raw.frame_max_index - 1)
+        frame_start, frame_stop = c0 * Fr + z, np.minimum(c1 * Fr + z, raw.frame_max_index)
+    else:
+        L = raw.cycle_len
+        scan_center, scan_start, scan_stop = np.zeros(n, np.int64), np.zeros(n, np.int64), np.ones(n, np.int64)
+        frame_center = np.minimum(centers * L, raw.frame_max_index)
+        frame_start, frame_stop = c0 * L, np.minimum(c1 * L, raw.frame_max_index)
+    return pd.DataFrame({
+        "precursor_idx": pdf["precursor_idx"].values[rows].astype(np.uint32), "rank": (np.arange(n) % 3).astype(np.uint8),
+        "score": np.ones(n, dtype=np.float32),
+        "scan_center": np.asarray(scan_center, np.int64), "scan_start": np.asarray(scan_start, np.int64),
+        "scan_stop": np.asarray(scan_stop, np.int64), "frame_center": np.asarray(frame_center, np.int64),
+        "frame_start": np.asarray(frame_start, np.int64), "frame_stop": np.asarray(frame_stop, np.int64),
+        "elution_group_idx": pdf["elution_group_idx"].values[rows].astype(np.uint32),
+        "decoy": pdf["decoy"].values[rows].astype(np.uint8),
+    })
+
+
+# scoring under a fitted quadrupole model and other tolerances (tests/golden/scoring_variants.npz); candidates = the golden
+# candidate table of the file
+SCORING_VARIANTS_EXTRA = {
+    "quad": dict(config={}, quad_sigma=(0.45, 0.8), quad_delta_mu=(0.6, -0.4)),
+    "tol": dict(config={"precursor_mz_tolerance": 12, "fragment_mz_tolerance": 25, "top_k_isotopes": 2}, quad_sigma=(0.2, 0.2),
+                quad_delta_mu=(0.0, 0.0)),
+    "shared": dict(config={"exclude_shared_ions": False, "quant_window": 4}, quad_sigma=(0.2, 0.2), quad_delta_mu=(0.0, 0.0)),
+}
+SCORING_VARIANT_FILES = ("parity_small", "parity_4d_overlap")

@@ -335,6 +335,80 @@ def test_ragged_library_vs_reference(name, oracle_lib):
         assert np.array_equal(a, b) if k != "correlation" else H.rel_err(a, b).max() < 1e-4, k
 
 
+# ---- hand-made candidate windows (tests/golden/edge.npz) ---------------------------------------------------------
+@pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
+def test_scoring_edge_windows_vs_reference(name, oracle_lib):
+    """Windows of 1 to 241 cycles, clipped at the ends of the run, 1-scan to full-height scan windows, placed at random
+    (mostly off any signal): which candidates the reference keeps and what it computes for them."""
+    import os
+
+    path = os.path.join(H.GOLDEN_DIR, "edge.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden edge.npz missing")
+    g = np.load(path, allow_pickle=False)
+    raw, pdf, fdf, lib, p = H.workload(name)
+    if f"{name}__input_checksum" not in g or str(g[f"{name}__input_checksum"]) != H.input_checksum(raw, pdf, fdf):
+        pytest.skip("golden not applicable")
+    cand = H.edge_candidate_frame(name)
+    for c in cand.columns:
+        assert np.array_equal(cand[c].values, g[f"{name}__cand_{c}"]), c
+    cin, keep = H.candidates_in_from_arrays(lib, {c: cand[c].values.astype(np.int64) for c in INT_COLS})
+    score = oracle_lib.score_candidates_4d if name == "parity_4d" else oracle_lib.score_candidates
+    sc = score(raw, lib, H.scoring_config().to_struct(), cin)
+    v = sc["valid"].astype(bool)
+    assert np.array_equal(keep["precursor_idx"][v], g[f"{name}__feat_precursor_idx"])
+    assert np.array_equal(keep["rank"][v], g[f"{name}__feat_rank"])
+    assert 20 < v.sum() < len(cand)
+    F, G = sc["features"][v], g[f"{name}__feat_matrix"]
+    for j in range(46):
+        if j in BLAS_FEATURES:
+            assert H.rel_err(F[:, j], G[:, j]).max() < 1e-4, j
+        else:
+            assert ((F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))).all(), f"feature {j} not bit-exact"
+    fm = sc["fragment_mz_library"] > 0
+    assert fm.sum() == len(g[f"{name}__frag_mz_library"])
+    for k, v2 in FRAG_MAP.items():
+        a, b = sc[v2][fm], g[f"{name}__frag_{k}"]
+        assert np.array_equal(a, b) if k != "correlation" else H.rel_err(a, b).max() < 1e-4, k
+
+
+# ---- fitted quadrupole model, other tolerances (tests/golden/scoring_variants.npz) ------------------------------
+@pytest.mark.parametrize("tag", list(H.SCORING_VARIANTS_EXTRA))
+@pytest.mark.parametrize("name", list(H.SCORING_VARIANT_FILES))
+def test_scoring_extra_variants_vs_reference(name, tag, oracle_lib):
+    import os
+
+    path = os.path.join(H.GOLDEN_DIR, "scoring_variants.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden scoring_variants.npz missing")
+    gv = np.load(path, allow_pickle=False)
+    g, raw, lib, p = _golden(name)
+    if f"{name}__input_checksum" not in gv or str(gv[f"{name}__input_checksum"]) != str(g["input_checksum"]):
+        pytest.skip("golden not applicable")
+    var = H.SCORING_VARIANTS_EXTRA[tag]
+    cfg = H.scoring_config(**var["config"]).to_struct(quad_sigma=var["quad_sigma"], quad_delta_mu=var["quad_delta_mu"])
+    cin, keep = H.candidates_in_from_arrays(lib, {c: g["cand_" + c] for c in INT_COLS})
+    score = oracle_lib.score_candidates_4d if name in ("parity_4d", "parity_4d_overlap") else oracle_lib.score_candidates
+    sc = score(raw, lib, cfg, cin)
+    v = sc["valid"].astype(bool)
+    key = f"{name}__{tag}__"
+    assert np.array_equal(keep["precursor_idx"][v], gv[key + "feat_precursor_idx"])
+    assert np.array_equal(keep["rank"][v], gv[key + "feat_rank"])
+    F, G = sc["features"][v], gv[key + "feat_matrix"]
+    if tag == "quad":  # the fitted model must matter, or the case pins nothing
+        assert not np.array_equal(G, g["feat_matrix"]) if G.shape == g["feat_matrix"].shape else True
+    for j in range(46):
+        if j in BLAS_FEATURES:
+            assert H.rel_err(F[:, j], G[:, j]).max() < 1e-4, j
+        else:
+            assert ((F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))).all(), f"feature {j} not bit-exact"
+    fm = sc["fragment_mz_library"] > 0
+    assert fm.sum() == len(gv[key + "frag_mz_library"])
+    for k, v2 in FRAG_MAP.items():
+        a, b = sc[v2][fm], gv[key + f"frag_{k}"]
+        assert np.array_equal(a, b) if k != "correlation" else H.rel_err(a, b).max() < 1e-4, k
+
+
 # ---- CandidateSelection.__call__ host side: the returned table (columns, order, dtypes) vs the reference's -------------
 @pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
 def test_candidate_selection_table_vs_reference(name, oracle_lib, monkeypatch):
