@@ -100,7 +100,15 @@ def keep_best(df: pd.DataFrame, score_column: str = "proba", group_columns: list
     return df[keep.astype(bool)].reset_index(drop=True)
 
 
-def perform_fdr(  # fdr.py:25-192
+def _drop_incomplete(df: pd.DataFrame, columns, label: str) -> None:
+    """In-place removal of rows with a missing classifier feature, as the reference does to its arguments (fdr.py:84-98)."""
+    before = len(df)
+    df.dropna(subset=columns, inplace=True)
+    if len(df) < before:
+        logger.warning(f"{before - len(df)} {label} PSMs lack at least one feature and were dropped")
+
+
+def perform_fdr(
     classifier,
     available_columns: list[str],
     df_target: pd.DataFrame,
@@ -114,54 +122,47 @@ def perform_fdr(  # fdr.py:25-192
     fdr_heuristic: float = 0.1,
     random_state: int | None = None,
 ) -> pd.DataFrame:
-    """Same flow and result as the reference: drop rows with missing features, fit the caller's classifier on an 80 % split,
-    predict, q-values, fragment competition on the rows below ``fdr_heuristic`` (3-D data only), best row per group,
-    q-values again.  Sorts, scans and the competition run on the device; the classifier is the caller's."""
+    """Signature, flow and result of the reference's ``perform_fdr`` (fdr.py:25-192).  The classifier is the caller's object
+    (``fit(X, y)``, ``predict_proba(X)``) trained on the same 80 % split; the two q-value passes, the fragment competition on
+    the rows below ``fdr_heuristic`` (data without ion mobility only) and the best-row-per-group selection run on the device."""
     from sklearn.model_selection import train_test_split
 
-    target_len, decoy_len = len(df_target), len(df_decoy)
-    df_target.dropna(subset=available_columns, inplace=True)
-    df_decoy.dropna(subset=available_columns, inplace=True)
-    if target_len - len(df_target) > 0:
-        logger.warning(f"dropped {target_len - len(df_target)} target PSMs due to missing features")
-    if decoy_len - len(df_decoy) > 0:
-        logger.warning(f"dropped {decoy_len - len(df_decoy)} decoy PSMs due to missing features")
-    if np.abs(len(df_target) - len(df_decoy)) / ((len(df_target) + len(df_decoy)) / 2) > 0.1:
-        logger.warning(f"FDR calculation for {len(df_target)} target and {len(df_decoy)} decoy PSMs")
-        logger.warning("FDR calculation may be inaccurate as there is more than 10% difference in the number of target and decoy PSMs")
-    if random_state is not None:
-        logger.info(f"Using random state {random_state} for FDR calculation")
+    _drop_incomplete(df_target, available_columns, "target")
+    _drop_incomplete(df_decoy, available_columns, "decoy")
+    n_t, n_d = len(df_target), len(df_decoy)
+    if abs(n_t - n_d) / ((n_t + n_d) / 2) > 0.1:
+        logger.warning(f"{n_t} target vs {n_d} decoy PSMs differ by more than 10 %: the FDR estimate may be off")
 
-    X = np.concatenate([df_target[available_columns].to_numpy(), df_decoy[available_columns].to_numpy()])
-    y = np.concatenate([np.zeros(len(df_target)), np.ones(len(df_decoy))])
-    try:  # fdr/utils.py:16-52 train_test_split_
-        X_train, _, y_train, _ = train_test_split(X, y, test_size=0.2, random_state=random_state)
+    features = np.concatenate([df_target[available_columns].to_numpy(), df_decoy[available_columns].to_numpy()])
+    is_decoy = np.concatenate([np.zeros(n_t), np.ones(n_d)])
+    psm_df = pd.concat([df_target, df_decoy])
+    try:  # fdr/utils.py:16-52: the split raises ValueError when there are too few rows
+        train_x, _, train_y, _ = train_test_split(features, is_decoy, test_size=0.2, random_state=random_state)
     except ValueError:
-        logger.warning("Too few PSMs for FDR classification, assigning qval=1.0 and proba=1.0 to all PSMs.")
-        psm_df = pd.concat([df_target, df_decoy])
+        logger.warning("not enough PSMs to train the classifier: every PSM gets qval = proba = 1")
         psm_df["qval"] = 1.0
         psm_df["proba"] = 1.0
         return psm_df
-    classifier.fit(X_train, y_train)
+    classifier.fit(train_x, train_y)
 
-    psm_df = pd.concat([df_target, df_decoy])
-    psm_df["_decoy"] = y
-    if competitive:
-        group_columns = ["elution_group_idx", "channel"] if group_channels else ["elution_group_idx"]
-    else:
-        group_columns = ["precursor_idx"]
-    psm_df["proba"] = classifier.predict_proba(X)[:, 1]
-    psm_df = get_q_values(psm_df, "proba", "_decoy")  # already sorted by [proba, _decoy, precursor_idx] (fdr.py:151-155)
+    psm_df["_decoy"] = is_decoy
+    psm_df["proba"] = classifier.predict_proba(features)[:, 1]
+    # the reference sorts by (proba, precursor_idx) first; the stable (proba, _decoy, precursor_idx) sort inside
+    # get_q_values gives the same order without it
+    psm_df = get_q_values(psm_df, "proba", "_decoy")
 
     if dia_cycle is not None and dia_cycle.shape[2] <= max_dia_cycle_shape:
-        start_idx = psm_df["qval"].searchsorted(fdr_heuristic, side="left")
-        if start_idx == 0:
-            start_idx = len(psm_df)
+        n_head = int(psm_df["qval"].searchsorted(fdr_heuristic, side="left")) or len(psm_df)
         if df_fragments is not None:
-            psm_df = FragmentCompetition()(psm_df.iloc[:start_idx], df_fragments, dia_cycle)
+            psm_df = FragmentCompetition()(psm_df.iloc[:n_head], df_fragments, dia_cycle)
 
-    psm_df = keep_best(psm_df, group_columns=group_columns)
-    psm_df = get_q_values(psm_df, "proba", "_decoy")
+    if not competitive:
+        groups = ["precursor_idx"]
+    elif group_channels:
+        groups = ["elution_group_idx", "channel"]
+    else:
+        groups = ["elution_group_idx"]
+    psm_df = get_q_values(keep_best(psm_df, group_columns=groups), "proba", "_decoy")
     if figure_path is not None:
-        logger.info("FDR figures are drawn by the reference's plot_fdr (alphadia/fdr/plotting.py); skipped here")
+        logger.info("figure_path is ignored: the diagnostic plots belong to the reference (alphadia/fdr/plotting.py)")
     return psm_df
