@@ -1,6 +1,6 @@
 """Generate golden vectors by running the UNMODIFIED reference numba path (CPU, this container).
 
-    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ragged edge scoring_variants ...]
+    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ragged edge scoring_variants fragcomp_dense ...]
 
 Needs /root/reference (read-only) and numba; pays ~6 min of JIT once per process.  Writes
 ``tests/golden/<name>.npz`` — inputs are NOT stored (they are regenerated from the seed by
@@ -403,6 +403,26 @@ def run_scoring_variants(threads: int):
     print(f"[scoring_variants] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def run_fragcomp_dense(threads: int):
+    """_compete_for_fragments of the unmodified reference (fragcomp/fragcomp.py:51-143) on a collision-rich table, for the
+    dtype combinations the workflow produces -> tests/golden/fragcomp_dense.npz."""
+    from tests.helpers import FRAGCOMP_DTYPES, fragcomp_dense_inputs
+
+    fc_mod = refshim.ref("alphadia.fragcomp.fragcomp")
+    refshim.ref("alphatims.utils").set_threads(threads)
+    out = {}
+    for tag, (dtype_rt, dtype_mz) in FRAGCOMP_DTYPES.items():
+        ws, we, rt, fs, fe, mz = fragcomp_dense_inputs(dtype_rt, dtype_mz)
+        valid = np.ones(len(rt)).astype(bool)
+        fc_mod._compete_for_fragments(np.arange(len(ws)), ws, we, rt, fs, fe, mz, 3, 15, valid)
+        print(f"[fragcomp_dense] {tag}: {int(valid.sum())} of {len(valid)} PSMs keep their fragments", flush=True)
+        out[f"{tag}__valid"] = valid
+        out[f"{tag}__checksum"] = np.array(hashlib.sha256(rt.tobytes() + mz.tobytes()).hexdigest())
+    path = os.path.join(HERE, "fragcomp_dense.npz")
+    np.savez_compressed(path, **out)
+    print(f"[fragcomp_dense] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def transpose_inputs(seed: int = 5, n_push: int = 1500, n_tof: int = 257):
     """Push-major CSR of a small synthetic timsTOF file: ragged pushes (20 % empty), ascending tof indices inside a push."""
     rng = np.random.default_rng(seed)
@@ -444,5 +464,7 @@ if __name__ == "__main__":
             run_edge(threads)
         elif n == "scoring_variants":
             run_scoring_variants(threads)
+        elif n == "fragcomp_dense":
+            run_fragcomp_dense(threads)
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap")))

@@ -282,3 +282,25 @@ SCORING_VARIANTS_EXTRA = {
     "shared": dict(config={"exclude_shared_ions": False, "quant_window": 4}, quad_sigma=(0.2, 0.2), quad_delta_mu=(0.0, 0.0)),
 }
 SCORING_VARIANT_FILES = ("parity_small", "parity_4d_overlap")
+
+
+def fragcomp_dense_inputs(dtype_rt=np.float64, dtype_mz=np.float32, seed: int = 7, n: int = 6000, nwin: int = 5,
+                          rt_span: float = 40.0, p_replace: float = 0.45):
+    """Many PSMs that share fragments inside few windows (tests/golden/fragcomp_dense.npz): 300 base spectra reused with a
+    4 ppm jitter, 45 % of the fragments replaced at random, 4-12 fragments per PSM, all inside 40 s of retention time."""
+    rng = np.random.default_rng(seed)
+    base = rng.uniform(200, 1800, size=(300, 12))
+    src = rng.integers(0, 300, n)
+    mz = base[src] * (1 + rng.normal(0, 4e-6, size=(n, 12)))
+    replace = rng.random((n, 12)) < p_replace
+    mz = np.where(replace, rng.uniform(200, 1800, size=(n, 12)), mz)
+    nfr = rng.integers(4, 13, n)
+    frag_start = np.concatenate([[0], np.cumsum(nfr)[:-1]]).astype(np.int64)
+    frag_stop = frag_start + nfr
+    frag_mz = np.concatenate([np.sort(mz[i, : nfr[i]]) for i in range(n)]).astype(dtype_mz)
+    rt = rng.uniform(0, rt_span, n).astype(dtype_rt)
+    bounds = np.linspace(0, n, nwin + 1).astype(np.int64)
+    return bounds[:-1], bounds[1:], rt, frag_start, frag_stop, frag_mz
+
+
+FRAGCOMP_DTYPES = {"f32_f32": (np.float32, np.float32), "f64_f32": (np.float64, np.float32), "f64_f64": (np.float64, np.float64)}

@@ -103,6 +103,25 @@ def test_fragcomp_vs_reference(name, oracle_lib):
     assert FragmentCompetition is not None
 
 
+@pytest.mark.parametrize("tag", list(H.FRAGCOMP_DTYPES))
+def test_fragcomp_dense_vs_reference(tag, oracle_lib):
+    """512 of 6000 PSMs lose the competition in this table (the synthetic runs above have almost no collisions): the greedy
+    veto in probability order (fragcomp.py:110-143), compared with the reference's mask for every rt / m/z dtype pair."""
+    import hashlib
+    import os
+
+    path = os.path.join(H.GOLDEN_DIR, "fragcomp_dense.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden fragcomp_dense.npz missing")
+    g = np.load(path, allow_pickle=False)
+    ws, we, rt, fs, fe, mz = H.fragcomp_dense_inputs(*H.FRAGCOMP_DTYPES[tag])
+    if str(g[f"{tag}__checksum"]) != hashlib.sha256(rt.tobytes() + mz.tobytes()).hexdigest():
+        pytest.skip("inputs differ from the ones the golden file was made with (numpy version?)")
+    valid = oracle_lib.fragment_competition(ws, we, rt, fs, fe, mz, 3, 15).astype(bool)
+    assert 100 < (~g[f"{tag}__valid"]).sum() < 3000
+    assert np.array_equal(valid, g[f"{tag}__valid"])
+
+
 # ---- timsTOF (4-D) -------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["parity_4d", "parity_4d_overlap"])
 def test_selection_4d_bit_exact_vs_reference(name, oracle_lib):
