@@ -1,6 +1,6 @@
 """Generate golden vectors by running the UNMODIFIED reference numba path (CPU, this container).
 
-    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ragged edge scoring_variants fragcomp_dense ...]
+    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ragged edge scoring_variants fragcomp_dense variants2 ...]
 
 Needs /root/reference (read-only) and numba; pays ~6 min of JIT once per process.  Writes
 ``tests/golden/<name>.npz`` — inputs are NOT stored (they are regenerated from the seed by
@@ -423,6 +423,42 @@ def run_fragcomp_dense(threads: int):
     print(f"[fragcomp_dense] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def run_variants2(threads: int):
+    """More selection variants of the unmodified reference (peak-limit parameters, kernel widths), 3-D and 4-D
+    -> tests/golden/variants2.npz."""
+    from tests.helpers import SELECTION_VARIANTS2
+
+    sel_mod = refshim.ref("alphadia.search.selection.selection")
+    cfg_mod = refshim.ref("alphadia.search.selection.config_df")
+    out = {}
+    for name in ("parity_small", "parity_4d"):
+        if name in CONFIGS_4D:
+            raw, precursor_df, fragment_df, p = make_config_4d(name)
+            dia = refshim.RefDiaData4D(raw)
+        else:
+            raw, precursor_df, fragment_df, p = make_config_3d(name)
+            dia = refshim.RefDiaData(raw)
+        out[f"{name}__input_checksum"] = np.array(input_checksum(raw, precursor_df, fragment_df))
+        for tag, updates in SELECTION_VARIANTS2.items():
+            updates = dict(updates)
+            fwhm_rt, fwhm_mobility = updates.pop("fwhm_rt", 5.0), updates.pop("fwhm_mobility", 0.01)
+            cfg = cfg_mod.CandidateSelectionConfig()
+            cfg.update({**SELECTION_BASE, "rt_tolerance": float(p["rt_tolerance"]),
+                        "mobility_tolerance": float(p.get("mobility_tolerance", 0.1)),
+                        "candidate_count": 3, "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0, **updates})
+            sel = sel_mod.CandidateSelection(
+                dia, precursor_df.copy(), fragment_df.copy(), cfg, rt_column="rt_library", mobility_column="mobility_library",
+                precursor_mz_column="mz_library", fragment_mz_column="mz_library", fwhm_rt=fwhm_rt, fwhm_mobility=fwhm_mobility)
+            cand = sel(thread_count=threads)
+            print(f"[variants2] {name}/{tag}: {len(cand)} candidates", flush=True)
+            out[f"{name}__{tag}__kernel"] = np.asarray(sel.kernel)
+            for c in cand.columns:
+                out[f"{name}__{tag}__cand_{c}"] = cand[c].values
+    path = os.path.join(HERE, "variants2.npz")
+    np.savez_compressed(path, **out)
+    print(f"[variants2] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def transpose_inputs(seed: int = 5, n_push: int = 1500, n_tof: int = 257):
     """Push-major CSR of a small synthetic timsTOF file: ragged pushes (20 % empty), ascending tof indices inside a push."""
     rng = np.random.default_rng(seed)
@@ -466,5 +502,7 @@ if __name__ == "__main__":
             run_scoring_variants(threads)
         elif n == "fragcomp_dense":
             run_fragcomp_dense(threads)
+        elif n == "variants2":
+            run_variants2(threads)
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap")))

@@ -304,3 +304,12 @@ def fragcomp_dense_inputs(dtype_rt=np.float64, dtype_mz=np.float32, seed: int = 
 
 
 FRAGCOMP_DTYPES = {"f32_f32": (np.float32, np.float32), "f64_f32": (np.float64, np.float32), "f64_f64": (np.float64, np.float64)}
+
+
+# further selection variants (tests/golden/variants2.npz): peak-limit parameters and the smoothing kernel's widths
+# ("fwhm_rt" / "fwhm_mobility" are constructor arguments of CandidateSelection, everything else is configuration)
+SELECTION_VARIANTS2 = {
+    "limits": dict(f_rt=0.8, f_mobility=0.9, center_fraction=0.3, min_size_rt=5, max_size_rt=25, min_size_mobility=4,
+                   max_size_mobility=12),
+    "kernel": dict(fwhm_rt=9.0, fwhm_mobility=0.025, sigma_scale_rt=0.8, sigma_scale_mobility=0.6),
+}

@@ -208,6 +208,42 @@ def test_selection_variants_bit_exact_vs_reference(name, tag, oracle_lib):
         assert np.array_equal(arrs["score"][m], g[key + "score"])  # f32, bit-exact
 
 
+@pytest.mark.parametrize("tag", list(H.SELECTION_VARIANTS2))
+@pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
+def test_selection_variants2_bit_exact_vs_reference(name, tag, oracle_lib):
+    """Peak-limit parameters (symetric_limits_2d, selection/utils.py:276-312) and other widths of the smoothing kernel
+    (selection/kernel.py:98-218): the kernel matrix and the candidate table against the live reference."""
+    import os
+
+    from alphadia_b200.kernel import GaussianKernel
+
+    path = os.path.join(H.GOLDEN_DIR, "variants2.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden variants2.npz missing")
+    g = np.load(path, allow_pickle=False)
+    raw, pdf, fdf, lib, p = H.workload(name)
+    if str(g[f"{name}__input_checksum"]) != H.input_checksum(raw, pdf, fdf):
+        pytest.skip("golden not applicable")
+    kw = dict(H.SELECTION_VARIANTS2[tag])
+    fwhm_rt, fwhm_mobility = kw.pop("fwhm_rt", 5.0), kw.pop("fwhm_mobility", 0.01)
+    if "mobility_tolerance" in p:
+        kw.setdefault("mobility_tolerance", p["mobility_tolerance"])
+    config = H.selection_config(p["rt_tolerance"], **kw)
+    kernel = GaussianKernel(raw, fwhm_rt=fwhm_rt, sigma_scale_rt=config.sigma_scale_rt, fwhm_mobility=fwhm_mobility,
+                            sigma_scale_mobility=config.sigma_scale_mobility, kernel_width=config.kernel_size,
+                            kernel_height=min(config.kernel_size, raw.scan_max_index + 1)).get_dense_matrix(verbose=False)
+    key = f"{name}__{tag}__"
+    assert kernel.shape == g[key + "kernel"].shape and kernel.dtype == g[key + "kernel"].dtype
+    np.testing.assert_allclose(kernel, g[key + "kernel"], rtol=1e-6, atol=0)
+    select = oracle_lib.select_candidates_4d if "mobility_tolerance" in p else oracle_lib.select_candidates
+    arrs = select(raw, lib, config.to_struct(), g[key + "kernel"])
+    m = arrs["score"] > 0
+    assert m.sum() == len(g[key + "cand_precursor_idx"]) > 0
+    for c in INT_COLS:
+        assert np.array_equal(arrs[c][m].astype(np.int64), g[key + "cand_" + c].astype(np.int64)), c
+    assert np.array_equal(arrs["score"][m], g[key + "cand_score"])
+
+
 @pytest.mark.parametrize("tag,cfg_kw", [("ref0", dict(score_grouped=True, reference_channel=0)),
                                         ("grouped", dict(score_grouped=True, reference_channel=-1))])
 def test_multiplexed_scoring_vs_reference(tag, cfg_kw, oracle_lib, monkeypatch):
