@@ -690,3 +690,25 @@ def test_fdr_key_packing(oracle_lib, monkeypatch):
         fdr.get_q_values(df, extra_sort_columns=["name"])
     with pytest.raises(NotImplementedError):
         fdr.get_q_values(df.assign(a=df["a"].values.astype(np.int64) * 2 ** 30, b=df["b"].values * 2 ** 10), extra_sort_columns=["a", "b"])
+
+
+@pytest.mark.parametrize("n,levels", [(1, 1), (2, 1), (1000, 7), (50_000, 300), (50_000, 10 ** 9)])
+def test_fdr_oracle_equals_pandas_formulation(n, levels, oracle_lib):
+    """Random tables (heavy ties, negative and huge scores, all-target / all-decoy runs): the oracle against the reference's
+    formulation written out with pandas (sort_values, cumsum, minimum.accumulate; sort_values, groupby.head, sort_index)."""
+    import pandas as pd
+
+    rng = np.random.default_rng(n + levels % 1000)
+    score = rng.integers(-levels, levels + 1, n) / max(levels, 1) * rng.choice([1.0, 1e-300, 1e300])
+    decoy = (rng.random(n) < rng.choice([0.0, 0.5, 1.0])).astype(np.uint8)
+    extra = rng.integers(0, max(n // 4, 1), n).astype(np.uint64)
+    order, q = oracle_lib.q_values(score, decoy, extra)
+    df = pd.DataFrame({"s": score, "d": decoy, "e": extra}).sort_values(["s", "d", "e"])
+    assert np.array_equal(df.index.values, order)
+    with np.errstate(all="ignore"):
+        fdr_values = np.cumsum(df["d"].values) / np.cumsum(1 - df["d"].values.astype(np.int64))
+    assert np.array_equal(np.flip(np.minimum.accumulate(np.flip(fdr_values))), q, equal_nan=True)
+    group = rng.integers(0, max(n // 3, 1), n).astype(np.uint64) << np.uint64(rng.integers(0, 40))
+    keep = oracle_lib.keep_best(score, group)
+    best = pd.DataFrame({"s": score, "g": group}).sort_values(["s", "g"]).groupby("g").head(1).sort_index()
+    assert np.array_equal(np.flatnonzero(keep), best.index.values)
