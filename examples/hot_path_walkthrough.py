@@ -6,6 +6,7 @@
 1. ``CandidateSelection(dia_data, precursors_flat, fragments_flat, config, ...)()``  -> candidates DataFrame
 2. ``CandidateScoring(dia_data=..., ...)(candidates_df)``                            -> (features_df, fragments_df)
 3. ``FragmentCompetition()(psm_df, fragments_df, dia_data.cycle)``                    -> surviving PSMs
+4. ``keep_best`` / ``get_q_values`` (alphadia_b200.fdr)                                -> best row per group with q-values
 
 `dia_data` is whatever the reference passes around (an AlphaRaw / TimsTOFTranspose wrapper or its jitclass); here it is a
 synthetic run from ``alphadia_b200.synthetic`` so that the script has no external inputs.  The classes, their arguments and
@@ -56,3 +57,10 @@ if not getattr(raw, "has_mobility", False):  # the reference runs fragment compe
     psm_df["proba"] = np.random.default_rng(0).uniform(0, 1, len(psm_df))  # stands in for the FDR classifier's output
     kept = FragmentCompetition(rt_tol_seconds=3, mass_tol_ppm=15)(psm_df, fragments_df.copy(), raw.cycle)
     print(f"fragment competition: {len(kept)} of {len(psm_df)} PSMs keep their fragments ({time.perf_counter() - t2:.2f} s)")
+    # the bookkeeping perform_fdr runs around it (alphadia/fdr/fdr.py:157-186): best row per elution group, then q-values
+    from alphadia_b200.fdr import get_q_values, keep_best
+
+    kept = kept.assign(_decoy=kept["decoy"].values, channel=0)
+    q_df = get_q_values(keep_best(kept, group_columns=["elution_group_idx", "channel"]), "proba", "_decoy")
+    print(f"q-values: {len(q_df)} best-per-group PSMs, {int((q_df['qval'] <= 0.01).sum())} at q <= 0.01 "
+          "(with the random stand-in probabilities this only reflects the target / decoy ratio of the scored rows)")
