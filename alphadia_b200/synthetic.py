@@ -285,6 +285,12 @@ CONFIGS_3D = {
         cycle_seconds=1.0, n_noise_ms2=400, n_noise_ms1=800, rt_tolerance=25.0,
         planted_fraction=0.6, max_planted=None,
     ),
+    # 20 library fragments per precursor: selection smooths 20 fragment layers, scoring picks its top 12 (or 6) of 20
+    "parity_f20": dict(
+        seed=31, n_precursors=300, n_cycles=120, n_windows=12, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=1.0, n_noise_ms2=400, n_noise_ms1=800, rt_tolerance=25.0,
+        planted_fraction=0.6, max_planted=None, n_fragments=20,
+    ),
     # config 2: 50k precursors, Thermo shape (91 200 spectra, ~1.4e8 peaks)
     "config2": dict(
         seed=2, n_precursors=50_000, n_cycles=1200, n_windows=75, quad_lo=400.0, quad_hi=1000.0,
@@ -325,7 +331,7 @@ def make_config_3d(name: str, *, seed: int | None = None, n_precursors: int | No
     margin = min(60.0, run_s * 0.15)
     precursor_df, fragment_df = make_library(
         p["n_precursors"], rng, quad_lo=p["quad_lo"], quad_hi=p["quad_hi"],
-        rt_lo=margin, rt_hi=run_s - margin, with_strings=with_strings,
+        rt_lo=margin, rt_hi=run_s - margin, with_strings=with_strings, n_fragments=p.get("n_fragments", 12),
     )
     raw, apex = make_run_3d(
         precursor_df, fragment_df, rng,

@@ -41,7 +41,7 @@ def test_gaussian_kernel_matches_reference(name):
     np.testing.assert_allclose(k, g["sel_kernel"], rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize("name", ["config1", "parity_small"])
+@pytest.mark.parametrize("name", ["config1", "parity_small", "parity_f20"])
 def test_selection_bit_exact_vs_reference(name, oracle_lib):
     g, raw, lib, p = _golden(name)
     cfg = H.selection_config(p["rt_tolerance"]).to_struct()
@@ -53,7 +53,8 @@ def test_selection_bit_exact_vs_reference(name, oracle_lib):
     assert np.array_equal(arrs["score"][m], g["cand_score"])  # f32, bit-exact
 
 
-@pytest.mark.parametrize("name,tag", [("config1", ""), ("parity_small", ""), ("parity_small", "_legacy"), ("parity_small", "_k6")])
+@pytest.mark.parametrize("name,tag", [("config1", ""), ("parity_small", ""), ("parity_small", "_legacy"), ("parity_small", "_k6"),
+                                      ("parity_f20", ""), ("parity_f20", "_legacy"), ("parity_f20", "_k6")])
 def test_scoring_vs_reference(name, tag, oracle_lib):
     g, raw, lib, p = _golden(name)
     cand = {c: g["cand_" + c] for c in INT_COLS}
@@ -80,7 +81,7 @@ def test_scoring_vs_reference(name, tag, oracle_lib):
             assert np.array_equal(a, b), k
 
 
-@pytest.mark.parametrize("name", ["config1", "parity_small"])
+@pytest.mark.parametrize("name", ["config1", "parity_small", "parity_f20"])
 def test_fragcomp_vs_reference(name, oracle_lib):
     """FragmentCompetition on the golden feature table with the golden pseudo-proba."""
     from alphadia_b200.fragcomp import FragmentCompetition, plan_fragment_competition
