@@ -402,6 +402,12 @@ CONFIGS_4D = {
         noise_per_push=6, rt_tolerance=12.0, mobility_tolerance=0.12, planted_fraction=0.7,
         diagonal=False, window_overlap=30.0,
     ),
+    # parity_4d with 20 library fragments per precursor
+    "parity_4d_f20": dict(
+        seed=27, n_precursors=200, n_cycles=90, n_ms2_frames=3, n_scans=96, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=0.6, mob_hi=1.30, mob_lo=0.70, tof_ppm=4.0, mz_lo=150.0, mz_hi=1900.0,
+        noise_per_push=6, rt_tolerance=12.0, mobility_tolerance=0.12, planted_fraction=0.7, n_fragments=20,
+    ),
     # config 4 of BASELINE.json: 200k precursors, (1 + 8) x 928 cycle, 800 cycles
     "config4": dict(
         seed=4, n_precursors=200_000, n_cycles=800, n_ms2_frames=8, n_scans=928, quad_lo=400.0, quad_hi=1200.0,
@@ -446,11 +452,11 @@ def make_config_4d(name: str, *, seed: int | None = None, n_precursors: int | No
             cycle[0, f, :, 0], cycle[0, f, :, 1] = lo - overlap, lo + band + overlap
 
     # library: precursors live inside one (frame, half) window, mobility inside that half
-    P, F = p["n_precursors"], 12
+    P, F = p["n_precursors"], p.get("n_fragments", 12)
     run_s = rt_values[-1]
     margin = min(60.0, run_s * 0.15)
     precursor_df, fragment_df = make_library(P, rng, quad_lo=p["quad_lo"], quad_hi=p["quad_hi"], rt_lo=margin,
-                                             rt_hi=run_s - margin, with_strings=with_strings)
+                                             rt_hi=run_s - margin, with_strings=with_strings, n_fragments=F)
     wf = rng.integers(1, Fr, size=P)
     wh = rng.integers(0, 2, size=P)
     if diagonal:

@@ -505,4 +505,4 @@ if __name__ == "__main__":
         elif n == "variants2":
             run_variants2(threads)
         else:
-            run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap", "parity_f20")))
+            run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap", "parity_f20", "parity_4d_f20")))

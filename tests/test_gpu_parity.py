@@ -992,19 +992,20 @@ def test_extra_ragged_frames(engine, oracle_lib, name):
 
 
 @extra_gpu
-def test_extra_twenty_fragment_library(engine, oracle_lib):
-    """parity_f20: 20 library fragments per precursor (20 selection layers; scoring keeps the top 12 or 6 by library intensity)."""
-    name = "parity_f20"
+@pytest.mark.parametrize("name", ["parity_f20", "parity_4d_f20"])
+def test_extra_twenty_fragment_library(engine, oracle_lib, name):
+    """20 library fragments per precursor (20 selection layers; scoring keeps the top 12 or 6 by library intensity), 3-D and 4-D."""
     raw, lib, p, draw, dlib = _device_objects(engine, name)
-    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    is4d = draw.is_4d
+    cfg = _sel_cfg_4d(p) if is4d else H.selection_config(p["rt_tolerance"]).to_struct()
     kernel = H.default_kernel(raw)
     got = engine.select_candidates(draw, dlib, cfg, kernel)
-    ref = oracle_lib.select_candidates(raw, lib, cfg, kernel)
+    ref = (oracle_lib.select_candidates_4d if is4d else oracle_lib.select_candidates)(raw, lib, cfg, kernel)
     assert_candidates_equal(got, ref)
     m = got["score"] > 0
     cin, keep = H.candidates_in_from_arrays(lib, {c: got[c][m] for c in INT_COLS})
+    score = oracle_lib.score_candidates_4d if is4d else oracle_lib.score_candidates
     for variant in ("default", "legacy", "k6"):
         scfg = H.scoring_config(**SCORING_VARIANTS[variant]).to_struct()
-        assert_scores_close(engine.score_candidates(draw, dlib, scfg, cin), oracle_lib.score_candidates(raw, lib, scfg, cin),
-                            what=f"{name}/{variant}")
+        assert_scores_close(engine.score_candidates(draw, dlib, scfg, cin), score(raw, lib, scfg, cin), what=f"{name}/{variant}")
     dlib.close(); draw.close()

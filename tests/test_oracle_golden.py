@@ -124,7 +124,7 @@ def test_fragcomp_dense_vs_reference(tag, oracle_lib):
 
 
 # ---- timsTOF (4-D) -------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["parity_4d", "parity_4d_overlap"])
+@pytest.mark.parametrize("name", ["parity_4d", "parity_4d_overlap", "parity_4d_f20"])
 def test_selection_4d_bit_exact_vs_reference(name, oracle_lib):
     g, raw, lib, p = _golden(name)
     k = H.default_kernel(raw)
@@ -141,7 +141,7 @@ def test_selection_4d_bit_exact_vs_reference(name, oracle_lib):
 
 
 @pytest.mark.parametrize("tag", ["", "_legacy", "_k6"])
-@pytest.mark.parametrize("name", ["parity_4d", "parity_4d_overlap"])
+@pytest.mark.parametrize("name", ["parity_4d", "parity_4d_overlap", "parity_4d_f20"])
 def test_scoring_4d_vs_reference(name, tag, oracle_lib):
     g, raw, lib, p = _golden(name)
     if f"feat{tag}_matrix" not in g:
