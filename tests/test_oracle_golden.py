@@ -685,6 +685,15 @@ def test_fdr_key_packing(oracle_lib, monkeypatch):
         kept = fdr.keep_best(df, group_columns=cols)
         ref = df.reset_index(drop=True).sort_values(["proba", *cols]).groupby(cols).head(1).sort_index().reset_index(drop=True)
         pd.testing.assert_frame_equal(kept, ref)
+    # float32 probabilities (what a torch classifier hands back): same order and q-values as pandas on the float32 column
+    df32 = df.assign(proba=rng.random(n).astype(np.float32).round(2), precursor_idx=df["a"])
+    got = fdr.get_q_values(df32)
+    ref = df32.sort_values(["proba", "_decoy", "precursor_idx"])
+    assert got["proba"].dtype == np.float32 and np.array_equal(got.index.values, ref.index.values)
+    d = ref["_decoy"].to_numpy()
+    with np.errstate(all="ignore"):
+        expect = np.flip(np.minimum.accumulate(np.flip(np.cumsum(d) / np.cumsum(1 - d))))
+    assert np.array_equal(got["qval"].values, expect)
     with pytest.raises(NotImplementedError):
         fdr.get_q_values(df.assign(a=-df["a"]), extra_sort_columns=["a"])
     with pytest.raises(NotImplementedError):
