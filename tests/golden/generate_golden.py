@@ -1,6 +1,6 @@
 """Generate golden vectors by running the UNMODIFIED reference numba path (CPU, this container).
 
-    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ragged edge scoring_variants fragcomp_dense variants2 ...]
+    python tests/golden/generate_golden.py [config1 parity_small parity_4d transpose variants fdr perform_fdr ragged edge scoring_variants fragcomp_dense variants2 iso2 ...]
 
 Needs /root/reference (read-only) and numba; pays ~6 min of JIT once per process.  Writes
 ``tests/golden/<name>.npz`` — inputs are NOT stored (they are regenerated from the seed by
@@ -459,6 +459,45 @@ def run_variants2(threads: int):
     print(f"[variants2] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def run_iso2(threads: int):
+    """Library with only two isotope columns (i_0, i_1) while top_k_precursors = top_k_isotopes = 3: selection and scoring of
+    the unmodified reference on parity_small -> tests/golden/iso2.npz."""
+    sel_mod = refshim.ref("alphadia.search.selection.selection")
+    cfg_mod = refshim.ref("alphadia.search.selection.config_df")
+    sc_mod = refshim.ref("alphadia.search.scoring.scoring")
+    sccfg_mod = refshim.ref("alphadia.search.scoring.config")
+    name = "parity_small"
+    raw, precursor_df, fragment_df, p = make_config_3d(name)
+    dia = refshim.RefDiaData(raw)
+    out = {"input_checksum": np.array(input_checksum(raw, precursor_df, fragment_df))}
+    pdf = precursor_df.drop(columns=["i_2", "i_3"])
+    cfg = cfg_mod.CandidateSelectionConfig()
+    cfg.update({**SELECTION_BASE, "rt_tolerance": float(p["rt_tolerance"]), "mobility_tolerance": 0.1,
+                "candidate_count": 3, "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0})
+    sel = sel_mod.CandidateSelection(
+        dia, pdf.copy(), fragment_df.copy(), cfg, rt_column="rt_library", mobility_column="mobility_library",
+        precursor_mz_column="mz_library", fragment_mz_column="mz_library", fwhm_rt=5.0, fwhm_mobility=0.01)
+    cand = sel(thread_count=threads)
+    print(f"[iso2] {len(cand)} candidates", flush=True)
+    for c in cand.columns:
+        out[f"cand_{c}"] = cand[c].values
+    sc_cfg = sccfg_mod.CandidateScoringConfig()
+    sc_cfg.update({**SCORING_BASE, "precursor_mz_tolerance": 5, "fragment_mz_tolerance": 10})
+    scorer = sc_mod.CandidateScoring(
+        dia_data=dia, precursors_flat=pdf.copy(), fragments_flat=fragment_df.copy(), config=sc_cfg, rt_column="rt_library",
+        mobility_column="mobility_library", precursor_mz_column="mz_library", fragment_mz_column="mz_library")
+    feat, frag = scorer(cand.copy(), thread_count=threads, include_decoy_fragment_features=True)
+    print(f"[iso2] {len(feat)} feature rows, {len(frag)} fragment rows", flush=True)
+    out["feat_matrix"] = feat[sc_mod.DEFAULT_FEATURE_COLUMNS].values.astype(np.float32)
+    out["feat_precursor_idx"] = feat["precursor_idx"].values
+    out["feat_rank"] = feat["rank"].values
+    for c in frag.columns:
+        out[f"frag_{c}"] = frag[c].values
+    path = os.path.join(HERE, "iso2.npz")
+    np.savez_compressed(path, **out)
+    print(f"[iso2] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def transpose_inputs(seed: int = 5, n_push: int = 1500, n_tof: int = 257):
     """Push-major CSR of a small synthetic timsTOF file: ragged pushes (20 % empty), ascending tof indices inside a push."""
     rng = np.random.default_rng(seed)
@@ -504,5 +543,7 @@ if __name__ == "__main__":
             run_fragcomp_dense(threads)
         elif n == "variants2":
             run_variants2(threads)
+        elif n == "iso2":
+            run_iso2(threads)
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap", "parity_f20", "parity_4d_f20")))

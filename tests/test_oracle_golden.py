@@ -465,6 +465,44 @@ def test_scoring_extra_variants_vs_reference(name, tag, oracle_lib):
         assert np.array_equal(a, b) if k != "correlation" else H.rel_err(a, b).max() < 1e-4, k
 
 
+# ---- library with fewer isotope columns than top_k_precursors / top_k_isotopes (tests/golden/iso2.npz) -------------
+def test_two_isotope_library_vs_reference(oracle_lib):
+    import os
+
+    from alphadia_b200.library import assemble_library_arrays
+
+    path = os.path.join(H.GOLDEN_DIR, "iso2.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden iso2.npz missing")
+    g = np.load(path, allow_pickle=False)
+    raw, pdf0, fdf, _, p = H.workload("parity_small")
+    if str(g["input_checksum"]) != H.input_checksum(raw, pdf0, fdf):
+        pytest.skip("golden not applicable")
+    lib = assemble_library_arrays(pdf0.drop(columns=["i_2", "i_3"]), fdf, "rt_library", "mobility_library", "mz_library", "mz_library")
+    assert lib["isotopes"].shape[1] == 2
+    arrs = oracle_lib.select_candidates(raw, lib, H.selection_config(p["rt_tolerance"]).to_struct(), H.default_kernel(raw))
+    m = arrs["score"] > 0
+    assert m.sum() == len(g["cand_precursor_idx"]) > 100
+    for c in INT_COLS:
+        assert np.array_equal(arrs[c][m].astype(np.int64), g["cand_" + c].astype(np.int64)), c
+    assert np.array_equal(arrs["score"][m], g["cand_score"])
+    cin, keep = H.candidates_in_from_arrays(lib, {c: g["cand_" + c] for c in INT_COLS})
+    sc = oracle_lib.score_candidates(raw, lib, H.scoring_config().to_struct(), cin)
+    v = sc["valid"].astype(bool)
+    assert np.array_equal(keep["precursor_idx"][v], g["feat_precursor_idx"]) and np.array_equal(keep["rank"][v], g["feat_rank"])
+    F, G = sc["features"][v], g["feat_matrix"]
+    for j in range(46):
+        if j in BLAS_FEATURES:
+            assert H.rel_err(F[:, j], G[:, j]).max() < 1e-4, j
+        else:
+            assert ((F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))).all(), f"feature {j} not bit-exact"
+    fm = sc["fragment_mz_library"] > 0
+    assert fm.sum() == len(g["frag_mz_library"])
+    for k, v2 in FRAG_MAP.items():
+        a, b = sc[v2][fm], g[f"frag_{k}"]
+        assert np.array_equal(a, b) if k != "correlation" else H.rel_err(a, b).max() < 1e-4, k
+
+
 # ---- CandidateSelection.__call__ host side: the returned table (columns, order, dtypes) vs the reference's -------------
 @pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
 def test_candidate_selection_table_vs_reference(name, oracle_lib, monkeypatch):
