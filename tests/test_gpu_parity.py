@@ -1009,3 +1009,21 @@ def test_extra_twenty_fragment_library(engine, oracle_lib, name):
         scfg = H.scoring_config(**SCORING_VARIANTS[variant]).to_struct()
         assert_scores_close(engine.score_candidates(draw, dlib, scfg, cin), score(raw, lib, scfg, cin), what=f"{name}/{variant}")
     dlib.close(); draw.close()
+
+
+@extra_gpu
+def test_extra_two_isotope_library(engine, oracle_lib):
+    """Library with two isotope columns under top_k_precursors = top_k_isotopes = 3 (oracle pinned in tests/golden/iso2.npz)."""
+    from alphadia_b200.library import assemble_library_arrays
+
+    raw, pdf0, fdf, _, p = H.workload("parity_small")
+    lib = assemble_library_arrays(pdf0.drop(columns=["i_2", "i_3"]), fdf, "rt_library", "mobility_library", "mz_library", "mz_library")
+    draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+    cfg, kernel = H.selection_config(p["rt_tolerance"]).to_struct(), H.default_kernel(raw)
+    got = engine.select_candidates(draw, dlib, cfg, kernel)
+    assert_candidates_equal(got, oracle_lib.select_candidates(raw, lib, cfg, kernel))
+    m = got["score"] > 0
+    cin, keep = H.candidates_in_from_arrays(lib, {c: got[c][m] for c in INT_COLS})
+    scfg = H.scoring_config().to_struct()
+    assert_scores_close(engine.score_candidates(draw, dlib, scfg, cin), oracle_lib.score_candidates(raw, lib, scfg, cin), what="iso2")
+    dlib.close(); draw.close()
