@@ -922,14 +922,10 @@ def test_4d_two_observations_per_candidate(engine, oracle_lib):
     # tests/test_oracle_golden.py::test_scoring_4d_vs_reference[parity_4d_overlap-*])
 
 
-# ---- cases pinned on the CPU at the end of round 1 (oracle == live reference) that have not had a GPU run yet: enable with
-# ADB_EXTRA_GPU_TESTS=1 ----------------------------------------------------------------------
-import os  # noqa: E402
-
-extra_gpu = pytest.mark.skipif(not os.environ.get("ADB_EXTRA_GPU_TESTS"), reason="set ADB_EXTRA_GPU_TESTS=1 (not yet run on a GPU)")
+# ---- cases whose oracle is pinned against the live reference by dedicated golden files (variants2, scoring_variants, ragged,
+# parity_f20, parity_4d_f20, iso2): device vs oracle ------------------------------------------------------------------------
 
 
-@extra_gpu
 @pytest.mark.parametrize("tag", list(H.SELECTION_VARIANTS2))
 @pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
 def test_extra_selection_variants2(engine, oracle_lib, name, tag):
@@ -950,7 +946,6 @@ def test_extra_selection_variants2(engine, oracle_lib, name, tag):
     dlib.close(); draw.close()
 
 
-@extra_gpu
 @pytest.mark.parametrize("tag", list(H.SCORING_VARIANTS_EXTRA))
 @pytest.mark.parametrize("name", list(H.SCORING_VARIANT_FILES))
 def test_extra_scoring_variants(engine, oracle_lib, name, tag):
@@ -967,7 +962,6 @@ def test_extra_scoring_variants(engine, oracle_lib, name, tag):
     dlib.close(); draw.close()
 
 
-@extra_gpu
 @pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
 def test_extra_ragged_frames(engine, oracle_lib, name):
     from alphadia_b200.library import assemble_library_arrays
@@ -991,7 +985,6 @@ def test_extra_ragged_frames(engine, oracle_lib, name):
     dlib.close(); draw.close()
 
 
-@extra_gpu
 @pytest.mark.parametrize("name", ["parity_f20", "parity_4d_f20"])
 def test_extra_twenty_fragment_library(engine, oracle_lib, name):
     """20 library fragments per precursor (20 selection layers; scoring keeps the top 12 or 6 by library intensity), 3-D and 4-D."""
@@ -1011,7 +1004,6 @@ def test_extra_twenty_fragment_library(engine, oracle_lib, name):
     dlib.close(); draw.close()
 
 
-@extra_gpu
 def test_extra_two_isotope_library(engine, oracle_lib):
     """Library with two isotope columns under top_k_precursors = top_k_isotopes = 3 (oracle pinned in tests/golden/iso2.npz)."""
     from alphadia_b200.library import assemble_library_arrays
