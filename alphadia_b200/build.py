@@ -15,8 +15,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "libalphadia_b200.so")
-SOURCES = ["adb_api.cu", "adb_select.cu", "adb_score.cu", "adb_misc.cu", "adb_select4d.cu", "adb_score4d.cu"]
-HEADERS = [os.path.join(CSRC, "adb_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "alphadia_b200.h")]
+SOURCES = ["adb_api.cu", "adb_select.cu", "adb_score.cu", "adb_score_dp.cu", "adb_misc.cu", "adb_select4d.cu", "adb_score4d.cu"]
+# per-file flags: the data-parallel scoring passes are written in plain arithmetic and must not be FMA-contracted
+EXTRA_FLAGS = {"adb_score_dp.cu": ["--fmad=false"]}
+HEADERS = [os.path.join(CSRC, "adb_common.cuh"), os.path.join(CSRC, "adb_score_dp.cuh"), os.path.join(os.path.dirname(HERE), "include", "alphadia_b200.h")]
 
 
 def nvcc_path() -> str:
@@ -50,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in SOURCES:
         obj = os.path.join(build_dir, s.replace(".cu", ".o"))
         objs.append(obj)
-        procs.append((s, subprocess.Popen(common + ["-c", os.path.join(CSRC, s), "-o", obj],
+        procs.append((s, subprocess.Popen(common + EXTRA_FLAGS.get(s, []) + ["-c", os.path.join(CSRC, s), "-o", obj],
                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for s, p in procs:

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -12,6 +13,9 @@
 
 #include "adb_common.cuh"
 
+#ifndef ADB_SCORE_DP_BATCH
+#define ADB_SCORE_DP_BATCH (1 << 19)  // candidates per batch of the data-parallel scoring passes
+#endif
 #ifndef ADB_SCORE_BLOCKS
 #define ADB_SCORE_BLOCKS 4  // row blocks of a scoring call whose D2H overlaps the next block's kernel (<= 7)
 #endif
@@ -116,6 +120,9 @@ struct adb_rawfile {
   DeviceBuffer flags, offs, scan_tmp, count;
   DeviceBuffer scores;     // score outputs
   DeviceBuffer score_ws;
+  DeviceBuffer dp_plan;    // per-batch plan arrays of the data-parallel scoring passes
+  float* dp_cube = nullptr;   // = score_ws.ptr, the batch workspace of the passes
+  size_t dp_cube_floats = 0;
   DeviceBuffer staging;    // generic H2D staging
   DeviceBuffer extent;     // 4-D: max scan / cycle extent of the resident candidates
   // resident state
@@ -691,6 +698,20 @@ int run_compaction(adb_rawfile* raw) {
   return 0;
 }
 
+// grows the batch workspace of the data-parallel scoring passes (called between two batches, stream idle)
+int grow_dp_cube(void* owner, size_t floats) {
+  adb_rawfile* raw = (adb_rawfile*)owner;
+  if (raw->score_ws.reserve(sizeof(float) * floats)) return 1;
+  raw->dp_cube = raw->score_ws.as<float>();
+  raw->dp_cube_floats = raw->score_ws.bytes / sizeof(float);
+  return 0;
+}
+
+bool use_tile_scoring() {  // ADB_SCORE_TILE=1: the r1 tile-per-candidate kernel (A/B measurements only)
+  const char* e = getenv("ADB_SCORE_TILE");
+  return e && e[0] == '1';
+}
+
 // D2H of rows [r0, r1) of the resident score tables into the caller's (row-major) host tables
 int copy_score_rows(adb_rawfile* raw, adb_scores_out* out, int64_t r0, int64_t r1, cudaStream_t st) {
   if (r1 <= r0) return 0;
@@ -734,11 +755,32 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   raw->scores_k = K;
   // OutputPsmDF.__init__ zero-fills (scoring/output.py:42-70)
   CUDA_TRY(cudaMemsetAsync(raw->scores.ptr, 0, scores_bytes(std::max<int64_t>(n, 1), K), st));
+  const bool tile_path = use_tile_scoring();
   int tiles = adb_score_resident_tiles(raw->device, K);
-  // HBM fallback scratch for candidates whose cube exceeds the shared-memory budget
   int64_t c_max = std::max<int64_t>(c_max_hint, 32);
   int64_t ws_floats = (adb_score_workspace_floats(K, c_max) + 3) & ~(int64_t)3;
-  if (raw->score_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)tiles)) return 1;
+  const int KS = std::max(1, std::min(K, std::min(lib->max_lib_fragments, (int)ADB_MAX_LIB_FRAGMENTS)));
+  const int nIcap = (int)std::min<int64_t>(std::min<int64_t>(lib->dev.n_isotopes, cfg->top_k_isotopes), ADB_MAX_ISOTOPES);
+  const int64_t dp_batch = std::max<int64_t>(std::min<int64_t>(n, ADB_SCORE_DP_BATCH), 1);
+  if (tile_path) {
+    // HBM fallback scratch for candidates whose cube exceeds the shared-memory budget
+    if (raw->score_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)tiles)) return 1;
+  } else {
+    if (raw->dp_plan.reserve(adb_score_dp_plan_bytes(dp_batch, KS, nIcap, nullptr))) return 1;
+    raw->dp_cube = raw->score_ws.as<float>();
+    raw->dp_cube_floats = raw->score_ws.bytes / sizeof(float);
+  }
+  auto launch = [&](DevCandidatesIn part, const int32_t* order) -> int {
+    if (tile_path) {
+      adb_launch_score(raw->dev, lib->dev, *cfg, part, raw->d_scores, raw->score_ws.as<float>(), ws_floats, tiles, order,
+                       raw->d_status, st, &raw->launches);
+      return 0;
+    }
+    if (adb_launch_score_dp(raw->dev, lib->dev, *cfg, part, raw->d_scores, K, KS, order, dp_batch, raw->dp_plan.ptr, &raw->dp_cube,
+                            &raw->dp_cube_floats, grow_dp_cube, raw, raw->d_status, st, &raw->launches))
+      return g_error.empty() ? fail("data-parallel scoring failed") : 1;
+    return 0;
+  };
   // processing order: (quad window of the precursor, frame_start) so that co-resident tiles read the same
   // spectra; results do not depend on it (disjoint output rows)
   int32_t* d_order = nullptr;
@@ -764,8 +806,7 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   }
   CUDA_TRY(cudaEventRecord(raw->ev[4], st));
   if (n_chunks == 1 || d_order == nullptr) {
-    adb_launch_score(raw->dev, lib->dev, *cfg, raw->d_cand, raw->d_scores, raw->score_ws.as<float>(), ws_floats, tiles,
-                     d_order, raw->d_status, st, &raw->launches);
+    if (launch(raw->d_cand, d_order)) return 1;
     CUDA_TRY(cudaEventRecord(raw->ev[5], st));
     if (host_out) {
       CUDA_TRY(cudaEventRecord(raw->ev[2], st));
@@ -777,8 +818,7 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
       if (c1 <= c0) continue;
       DevCandidatesIn part = raw->d_cand;
       part.n = c1 - c0;  // the kernel visits order[c0 .. c1): the (window, time)-sorted rows of block k
-      adb_launch_score(raw->dev, lib->dev, *cfg, part, raw->d_scores, raw->score_ws.as<float>(), ws_floats, tiles,
-                       d_order + c0, raw->d_status, st, &raw->launches);
+      if (launch(part, d_order + c0)) return 1;
       CUDA_TRY(cudaEventRecord(raw->chunk_ev[k], st));
       CUDA_TRY(cudaStreamWaitEvent(raw->copy_stream, raw->chunk_ev[k], 0));
       if (copy_score_rows(raw, host_out, c0, c1, raw->copy_stream)) return 1;
@@ -993,7 +1033,7 @@ void adb_rawfile_destroy(adb_rawfile_t* r) {
   for (void* p : r->allocs) cudaFree(p);
   if (r->d_status) cudaFree(r->d_status);
   DeviceBuffer* bufs[] = {&r->kern, &r->order_keys, &r->order_vals, &r->order_tmp, &r->sel_ws, &r->cont, &r->cand_in,
-                          &r->flags, &r->offs, &r->scan_tmp, &r->count, &r->scores, &r->score_ws, &r->staging, &r->extent};
+                          &r->flags, &r->offs, &r->scan_tmp, &r->count, &r->scores, &r->score_ws, &r->dp_plan, &r->staging, &r->extent};
   for (DeviceBuffer* b : bufs) b->release();
   for (int i = 0; i < 6; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
   for (int i = 0; i < 8; i++) if (r->chunk_ev[i]) cudaEventDestroy(r->chunk_ev[i]);

@@ -158,6 +158,12 @@ void adb_launch_score(const DevRaw& raw, const DevLib& lib, const adb_scoring_co
                       DevScoresOut out, float* d_workspace, int64_t workspace_floats_per_tile, int n_resident_tiles,
                       const int32_t* d_order, uint32_t* d_status, cudaStream_t stream, int* n_launches);
 int adb_score_resident_tiles(int device, int top_k);
+// data-parallel scoring passes (adb_score_dp.cu)
+size_t adb_score_dp_plan_bytes(int64_t nb, int KS, int nIcap, size_t* scan_tmp_bytes);
+int adb_launch_score_dp(const DevRaw& raw, const DevLib& lib, const adb_scoring_config& cfg, DevCandidatesIn cand, DevScoresOut out,
+                        int out_k, int KS, const int32_t* d_order, int64_t batch, void* plan, float** cube, size_t* cube_floats,
+                        int (*grow)(void* owner, size_t floats), void* owner, uint32_t* d_status, cudaStream_t stream,
+                        int* n_launches);
 int64_t adb_score_workspace_floats(int top_k, int64_t c_max);
 
 void adb_launch_fragcomp(int64_t n_windows, const int64_t* d_ws, const int64_t* d_we, const void* d_rt,

@@ -1,0 +1,135 @@
+// alphadia_b200 — candidate scoring, 3-D raw files: kernels and launcher of the data-parallel passes (adb_score_dp.cuh).
+//
+// Compiled with --fmad=false: the pass bodies are written in plain arithmetic and must not be contracted (the reference
+// accumulates sequentially in f32 / f64 without FMA).
+#include <algorithm>
+
+#include <cub/device/device_scan.cuh>
+
+#include "adb_score_dp.cuh"
+
+namespace {
+
+constexpr int DP_THREADS = 256;
+
+__global__ void __launch_bounds__(DP_THREADS) dp_setup_kernel(const __grid_constant__ DpParams P) {
+  const int64_t j = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
+  if (j < P.n) dp_setup(P, j);
+  if (j == P.n) P.need[j] = 0;  // the scan runs over n + 1 entries: off[n] = total
+}
+
+// thread t <-> (slot, row): rows 0 .. KS-1 are the fragment rows, KS .. KS+nIcap-1 the isotope rows
+__global__ void __launch_bounds__(DP_THREADS) dp_extract_kernel(const __grid_constant__ DpParams P) {
+  const int64_t t = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
+  const int rows = P.KS + P.nIcap;
+  const int64_t j = t / rows;
+  if (j < P.n) dp_extract(P, j, (int)(t - j * rows));
+}
+
+__global__ void __launch_bounds__(DP_THREADS) dp_template_kernel(const __grid_constant__ DpParams P) {
+  const int64_t j = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
+  if (j < P.n) dp_template(P, j);
+}
+
+__global__ void __launch_bounds__(DP_THREADS) dp_fragment_kernel(const __grid_constant__ DpParams P) {
+  const int64_t t = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
+  const int64_t j = t / P.KS;
+  if (j < P.n) dp_fragment(P, j, (int)(t - j * P.KS));
+}
+
+__global__ void __launch_bounds__(DP_THREADS) dp_median_kernel(const __grid_constant__ DpParams P) {
+  const int64_t t = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
+  const int64_t j = t / DP_MED_LANES;
+  if (j < P.n) dp_median(P, j, (int)(t % DP_MED_LANES));
+}
+
+__global__ void __launch_bounds__(DP_THREADS) dp_corr_kernel(const __grid_constant__ DpParams P) {
+  const int64_t t = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
+  const int64_t j = t / P.KS;
+  if (j < P.n) dp_corr(P, j, (int)(t - j * P.KS));
+}
+
+__global__ void __launch_bounds__(DP_THREADS) dp_aggregate_kernel(const __grid_constant__ DpParams P) {
+  const int64_t j = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
+  if (j < P.n) dp_aggregate(P, j);
+}
+
+__global__ void __launch_bounds__(DP_THREADS) dp_write_kernel(const __grid_constant__ DpParams P) {
+  const int64_t t = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
+  const int64_t j = t / P.KS;
+  if (j < P.n) dp_write(P, j, (int)(t - j * P.KS));
+}
+
+inline unsigned blocks_for(int64_t threads) { return (unsigned)((threads + DP_THREADS - 1) / DP_THREADS); }
+
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+}  // namespace
+
+// bytes of the per-batch plan arrays (everything except the cube)
+size_t adb_score_dp_plan_bytes(int64_t nb, int KS, int nIcap, size_t* scan_tmp_bytes) {
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int64_t*)nullptr, (int64_t*)nullptr, (int)(nb + 1));
+  if (scan_tmp_bytes) *scan_tmp_bytes = tmp;
+  const size_t N = (size_t)nb;
+  return align256(N) * 3 + align256(4 * N) * 2 + align256(2 * N * ADB_MAX_OBS) + align256(4 * N * (size_t)KS) +
+         align256(8 * N * (size_t)nIcap * ADB_MAX_OBS) + align256(4 * N * ADB_MAX_OBS) + align256(8 * (N + 1)) * 2 + align256(tmp) + 256;
+}
+
+// Scores candidates order[0 .. cand_n) in batches of `batch` slots.  plan: adb_score_dp_plan_bytes(batch, ...) bytes;
+// cube: grow-only float workspace (*cube / *cube_floats, reallocated through `grow` when a batch needs more).
+// Returns 0, or 1 when the workspace could not be grown (message through `grow`'s owner).
+int adb_launch_score_dp(const DevRaw& raw, const DevLib& lib, const adb_scoring_config& cfg, DevCandidatesIn cand, DevScoresOut out,
+                        int out_k, int KS, const int32_t* d_order, int64_t batch, void* plan, float** cube, size_t* cube_floats,
+                        int (*grow)(void* owner, size_t floats), void* owner, uint32_t* d_status, cudaStream_t stream,
+                        int* n_launches) {
+  if (cand.n <= 0) return 0;
+  DpParams P;
+  P.raw = raw; P.lib = lib; P.cfg = cfg; P.cand = cand; P.out = out;
+  P.out_k = out_k;
+  P.order = d_order;
+  P.KS = KS;
+  P.nIcap = (int)std::min<int64_t>(std::min<int64_t>(lib.n_isotopes, cfg.top_k_isotopes), ADB_MAX_ISOTOPES);
+  P.status = d_status;
+  size_t tmp = 0;
+  adb_score_dp_plan_bytes(batch, KS, P.nIcap, &tmp);
+  const size_t N = (size_t)batch;
+  char* p = (char*)plan;
+  auto take = [&](size_t bytes) { char* r = p; p += align256(bytes); return r; };
+  P.state = (uint8_t*)take(N);
+  P.F = (uint8_t*)take(N);
+  P.nobs = (uint8_t*)take(N);
+  P.C = (int32_t*)take(4 * N);
+  P.cs = (int32_t*)take(4 * N);
+  P.pos = (uint16_t*)take(2 * N * ADB_MAX_OBS);
+  P.fsel = (uint32_t*)take(4 * N * (size_t)KS);
+  P.qtf = (double*)take(8 * N * (size_t)P.nIcap * ADB_MAX_OBS);
+  P.qmask = (float*)take(4 * N * ADB_MAX_OBS);
+  P.need = (int64_t*)take(8 * (N + 1));
+  int64_t* off = (int64_t*)take(8 * (N + 1));
+  P.off = off;
+  void* scan_tmp = take(tmp);
+  for (int64_t base = 0; base < cand.n; base += batch) {
+    P.base = base;
+    P.n = std::min<int64_t>(batch, cand.n - base);
+    P.cube = *cube;
+    dp_setup_kernel<<<blocks_for(P.n + 1), DP_THREADS, 0, stream>>>(P);
+    cub::DeviceScan::ExclusiveSum(scan_tmp, tmp, (const int64_t*)P.need, off, (int)(P.n + 1), stream);
+    int64_t total = 0;
+    if (cudaMemcpyAsync(&total, off + P.n, sizeof(total), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) return 1;
+    if ((size_t)total > *cube_floats) {
+      if (grow(owner, (size_t)total)) return 1;
+    }
+    P.cube = *cube;
+    dp_extract_kernel<<<blocks_for(P.n * (P.KS + P.nIcap)), DP_THREADS, 0, stream>>>(P);
+    dp_template_kernel<<<blocks_for(P.n), DP_THREADS, 0, stream>>>(P);
+    dp_fragment_kernel<<<blocks_for(P.n * P.KS), DP_THREADS, 0, stream>>>(P);
+    if (cfg.experimental_xic) dp_median_kernel<<<blocks_for(P.n * DP_MED_LANES), DP_THREADS, 0, stream>>>(P);
+    dp_corr_kernel<<<blocks_for(P.n * P.KS), DP_THREADS, 0, stream>>>(P);
+    dp_aggregate_kernel<<<blocks_for(P.n), DP_THREADS, 0, stream>>>(P);
+    if (cfg.collect_fragments) dp_write_kernel<<<blocks_for(P.n * P.KS), DP_THREADS, 0, stream>>>(P);
+    if (n_launches) *n_launches += 7 + (cfg.experimental_xic ? 1 : 0) + (cfg.collect_fragments ? 1 : 0);
+  }
+  return 0;
+}

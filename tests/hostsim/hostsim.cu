@@ -1,0 +1,101 @@
+// TEST INFRASTRUCTURE — runs the pass bodies of alphadia_b200/csrc/adb_score_dp.cuh thread by thread on the CPU.
+//
+// The scoring kernels are plain data-parallel passes (no warp-level cooperation), so the same source compiles as host
+// code; tests/test_hostsim.py compares this emulation with the oracle on machines without a GPU.  The product never loads
+// this library (it is not part of libalphadia_b200.so).  Built by tests/hostsim/__init__.py with the nvcc host compiler.
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "../../alphadia_b200/csrc/adb_score_dp.cuh"
+
+extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_desc* ld, const adb_scoring_config* cfg,
+                                 const adb_candidates_in* cand, adb_scores_out* out, int32_t out_k, int32_t KS, int64_t batch,
+                                 const int32_t* order, uint32_t* status_out) {
+  DevRaw raw{};
+  raw.cycle = d->cycle; raw.cycle_len = d->cycle_len; raw.rt_values = d->rt_values; raw.n_spectra = d->n_spectra;
+  raw.mobility_values = d->mobility_values; raw.n_mobility = d->n_mobility; raw.peak_start = d->peak_start_idx;
+  raw.peak_stop = d->peak_stop_idx; raw.mz = d->mz_values; raw.intensity = d->intensity_values; raw.n_peaks = d->n_peaks;
+  raw.zeroth_frame = d->zeroth_frame; raw.precursor_cycle_max_index = d->precursor_cycle_max_index;
+  raw.scan_max_index = d->scan_max_index; raw.frame_max_index = d->frame_max_index;
+  raw.n_ms1_pos = 0;
+  for (int64_t j = 0; j < d->cycle_len; j++)
+    if ((-1.0 <= d->cycle[2 * j + 1]) && (-1.0 >= d->cycle[2 * j]) && raw.n_ms1_pos < ADB_MAX_MS1_POS) raw.ms1_pos[raw.n_ms1_pos++] = (int32_t)j;
+  // m/z-major index: peaks of every cycle position, stably sorted by m/z (adb_api.cu builds the same with a radix sort)
+  const int64_t L = d->cycle_len;
+  std::vector<int64_t> idx;
+  std::vector<int64_t> spec_of;
+  idx.reserve((size_t)d->n_peaks); spec_of.reserve((size_t)d->n_peaks);
+  std::vector<int64_t> pos_start((size_t)L + 1, 0);
+  for (int64_t pos = 0; pos < L; pos++) {
+    pos_start[(size_t)pos] = (int64_t)idx.size();
+    const size_t seg0 = idx.size();
+    for (int64_t s = pos; s < d->n_spectra; s += L)
+      for (int64_t i = d->peak_start_idx[s]; i < d->peak_stop_idx[s]; i++) { idx.push_back(i); spec_of.push_back(s); }
+    std::vector<size_t> perm(idx.size() - seg0);
+    std::iota(perm.begin(), perm.end(), (size_t)0);
+    std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return d->mz_values[idx[seg0 + a]] < d->mz_values[idx[seg0 + b]]; });
+    std::vector<int64_t> i2(perm.size()), s2(perm.size());
+    for (size_t t = 0; t < perm.size(); t++) { i2[t] = idx[seg0 + perm[t]]; s2[t] = spec_of[seg0 + perm[t]]; }
+    std::copy(i2.begin(), i2.end(), idx.begin() + seg0);
+    std::copy(s2.begin(), s2.end(), spec_of.begin() + seg0);
+  }
+  pos_start[(size_t)L] = (int64_t)idx.size();
+  std::vector<float> s_mz(idx.size() + 1), s_int(idx.size() + 1);
+  std::vector<uint32_t> s_cyc(idx.size() + 1);
+  for (size_t t = 0; t < idx.size(); t++) {
+    s_mz[t] = d->mz_values[idx[t]]; s_int[t] = d->intensity_values[idx[t]]; s_cyc[t] = (uint32_t)(spec_of[t] / L);
+  }
+  raw.s_mz = s_mz.data(); raw.s_int = s_int.data(); raw.s_cyc = s_cyc.data(); raw.pos_start = pos_start.data();
+
+  DevLib lib{};
+  lib.n_precursors = ld->n_precursors; lib.precursor_idx = ld->precursor_idx; lib.frag_start_idx = ld->frag_start_idx;
+  lib.frag_stop_idx = ld->frag_stop_idx; lib.charge = ld->charge; lib.rt = ld->rt; lib.mobility = ld->mobility; lib.mz = ld->mz;
+  lib.isotopes = ld->isotopes; lib.n_isotopes = ld->n_isotopes; lib.n_fragments = ld->n_fragments;
+  lib.frag_mz_library = ld->frag_mz_library; lib.frag_mz = ld->frag_mz; lib.frag_intensity = ld->frag_intensity;
+  lib.frag_type = ld->frag_type; lib.frag_loss_type = ld->frag_loss_type; lib.frag_charge = ld->frag_charge;
+  lib.frag_number = ld->frag_number; lib.frag_position = ld->frag_position; lib.frag_cardinality = ld->frag_cardinality;
+
+  DpParams P{};
+  P.raw = raw; P.lib = lib; P.cfg = *cfg;
+  P.cand = DevCandidatesIn{cand->n, cand->lib_row, cand->rank, cand->scan_start, cand->scan_stop, cand->scan_center,
+                           cand->frame_start, cand->frame_stop, cand->frame_center};
+  P.out = DevScoresOut{out->features, out->valid, out->fragment_mz_library, out->fragment_mz, out->fragment_mz_observed,
+                       out->fragment_height, out->fragment_intensity, out->fragment_mass_error, out->fragment_correlation,
+                       out->fragment_position, out->fragment_number, out->fragment_type, out->fragment_charge, out->fragment_loss_type};
+  P.out_k = out_k; P.order = order; P.KS = KS;
+  P.nIcap = (int)std::min<int64_t>(std::min<int64_t>(lib.n_isotopes, cfg->top_k_isotopes), ADB_MAX_ISOTOPES);
+  uint32_t status = 0;
+  P.status = &status;
+  const size_t N = (size_t)std::max<int64_t>(batch, 1);
+  std::vector<uint8_t> state(N), F(N), nobs(N);
+  std::vector<int32_t> C(N), cs(N);
+  std::vector<uint16_t> pos(N * ADB_MAX_OBS);
+  std::vector<uint32_t> fsel(N * (size_t)KS);
+  std::vector<double> qtf(N * (size_t)P.nIcap * ADB_MAX_OBS);
+  std::vector<float> qmask(N * ADB_MAX_OBS);
+  std::vector<int64_t> need(N + 1), off(N + 1);
+  P.state = state.data(); P.F = F.data(); P.nobs = nobs.data(); P.C = C.data(); P.cs = cs.data(); P.pos = pos.data();
+  P.fsel = fsel.data(); P.qtf = qtf.data(); P.qmask = qmask.data(); P.need = need.data(); P.off = off.data();
+  std::vector<float> cube;
+  for (int64_t base = 0; base < cand->n; base += batch) {
+    P.base = base;
+    P.n = std::min<int64_t>(batch, cand->n - base);
+    for (int64_t j = 0; j < P.n; j++) dp_setup(P, j);
+    need[(size_t)P.n] = 0;
+    int64_t run = 0;
+    for (int64_t j = 0; j <= P.n; j++) { off[(size_t)j] = run; run += need[(size_t)j]; }
+    cube.assign((size_t)run + 4, -12345.0f);  // poison: a pass that reads what no pass wrote shows up as a mismatch
+    P.cube = cube.data();
+    const int rows = P.KS + P.nIcap;
+    for (int64_t t = 0; t < P.n * rows; t++) dp_extract(P, t / rows, (int)(t % rows));
+    for (int64_t j = 0; j < P.n; j++) dp_template(P, j);
+    for (int64_t t = 0; t < P.n * P.KS; t++) dp_fragment(P, t / P.KS, (int)(t % P.KS));
+    if (cfg->experimental_xic) for (int64_t t = 0; t < P.n * DP_MED_LANES; t++) dp_median(P, t / DP_MED_LANES, (int)(t % DP_MED_LANES));
+    for (int64_t t = 0; t < P.n * P.KS; t++) dp_corr(P, t / P.KS, (int)(t % P.KS));
+    for (int64_t j = 0; j < P.n; j++) dp_aggregate(P, j);
+    if (cfg->collect_fragments) for (int64_t t = 0; t < P.n * P.KS; t++) dp_write(P, t / P.KS, (int)(t % P.KS));
+  }
+  if (status_out) *status_out = status;
+  return 0;
+}
