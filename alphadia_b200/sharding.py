@@ -101,6 +101,67 @@ def allgather_score_table(local_words, group=None):
     return out.cpu().numpy().view(np.uint32) if is_numpy else out
 
 
+class ScoreTableGather:
+    """The one collective of the sharded path with preallocated device buffers (NCCL): no per-step allocation, no host
+    synchronisation and no concatenation copy.  ``capacity`` is a static upper bound of a rank's rows (precursors x
+    candidate_count of the largest shard), so the table collective does not have to wait for the row counts; the counts
+    travel in a second, 8-byte collective and stay on the device until someone asks for the compact table."""
+
+    def __init__(self, capacity: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.capacity = int(capacity)
+        self.local = torch.zeros((self.capacity, ROW_WORDS), dtype=torch.int32, device=device)
+        self.gathered = torch.empty((self.world, self.capacity, ROW_WORDS), dtype=torch.int32, device=device)
+        self.n_local = torch.zeros(1, dtype=torch.int64, device=device)
+        self.sizes = torch.zeros(self.world, dtype=torch.int64, device=device)
+
+    def pack_resident(self, hot_path, lib_precursor_idx_dev) -> int:
+        """Packs the resident score table of ``hot_path`` into ``self.local[:n]`` (device-side, torch ops)."""
+        import torch
+
+        p = hot_path.score_table_pointers()
+        n = p["n"]
+        if n > self.capacity:
+            raise ValueError(f"score table has {n} rows, gather capacity is {self.capacity}")
+        self.n_local.fill_(n)
+        if n == 0:
+            return 0
+        dev = self.local.device
+        feats = torch.as_tensor(_CudaArrayView(p["features"], (n, 46), "<f4"), device=dev)
+        valid = torch.as_tensor(_CudaArrayView(p["valid"], (n,), "|u1"), device=dev)
+        rank = torch.as_tensor(_CudaArrayView(p["rank"], (n,), "|u1"), device=dev)
+        lib_row = torch.as_tensor(_CudaArrayView(p["lib_row"], (n,), "<i8"), device=dev)
+        w = self.local[:n]
+        w[:, :46] = feats.view(torch.int32)
+        w[:, 46] = lib_precursor_idx_dev[lib_row].to(torch.int32)
+        w[:, 47] = rank.to(torch.int32) | (valid.to(torch.int32) << 8)
+        return n
+
+    def allgather(self):
+        """THE collective (+ the 8-byte row-count exchange).  Returns ``(gathered [world, capacity, 48], sizes [world])``, both on
+        the device; rows beyond ``sizes[r]`` of block r are padding."""
+        import torch.distributed as dist
+
+        if self.world == 1:
+            self.gathered[0].copy_(self.local)
+            self.sizes.copy_(self.n_local)
+        else:
+            dist.all_gather_into_tensor(self.sizes, self.n_local, group=self.group)
+            dist.all_gather_into_tensor(self.gathered.view(self.world * self.capacity, ROW_WORDS), self.local, group=self.group)
+        return self.gathered, self.sizes
+
+    def compact(self):
+        """The gathered table without padding, in rank order (synchronises: the row counts come to the host)."""
+        import torch
+
+        sizes = self.sizes.cpu().tolist()
+        return torch.cat([self.gathered[r, : int(sizes[r])] for r in range(self.world)], dim=0)
+
+
 class _CudaArrayView:
     """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
 

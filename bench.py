@@ -217,6 +217,60 @@ def cpu_reference_pass(raw, lib, sel, sc, kernel, rows, threads):
     return len(m), t_sel, t_sc, int(out["valid"].sum())
 
 
+def parity_spot_check(hp, raw, lib, sel, sc, kernel, cont_gpu, n_prec=800, seed=7):
+    """Outside the timed region: the oracle selects and scores a random subsample of the library (>= 2000 candidate rows) on
+    the host and the result is compared with what the timed device path left in HBM for the same precursors — candidate
+    container rows bit for bit, the 46 features within 1e-4 relative, the per-fragment tables."""
+    import oracle
+    from alphadia_b200 import _abi, _lib
+
+    oracle.build()
+    is4d = hasattr(raw, "tof_indptr")
+    P, cc = int(hp.n_precursors), int(sel.candidate_count)
+    rng = np.random.default_rng(seed)
+    rows = np.sort(rng.permutation(P)[: min(P, n_prec)])
+    sub = dict(lib)
+    for k in ("precursor_idx", "frag_start_idx", "frag_stop_idx", "charge", "rt", "mobility", "mz", "isotopes"):
+        sub[k] = np.ascontiguousarray(lib[k][rows])
+    threads = os.cpu_count() or 1
+    ref = (oracle.select_candidates_4d if is4d else oracle.select_candidates)(raw, sub, sel.to_struct(), kernel, n_threads=threads)
+    take = (rows[:, None] * cc + np.arange(cc)[None, :]).ravel()
+    int_cols = ("precursor_idx", "rank", "scan_center", "scan_start", "scan_stop", "frame_center", "frame_start", "frame_stop")
+    int_exact = all(np.array_equal(cont_gpu[c][take], ref[c]) for c in int_cols)
+    score_exact = bool(np.array_equal(cont_gpu["score"][take].view(np.uint32), ref["score"].view(np.uint32)))
+    m = np.flatnonzero(ref["score"] > 0)
+    cin, keep = _abi.make_candidates_in(m // cc, ref["rank"][m], ref["scan_start"][m], ref["scan_stop"][m], ref["scan_center"][m],
+                                        ref["frame_start"][m], ref["frame_stop"][m], ref["frame_center"][m])
+    ref_sc = (oracle.score_candidates_4d if is4d else oracle.score_candidates)(raw, sub, sc.to_struct(), cin, n_threads=threads)
+    got = hp.fetch()  # every row the timed step scored, with its (library row, rank)
+    key_gpu = got["lib_row"].astype(np.int64) * 256 + got["rank"].astype(np.int64)
+    order = np.argsort(key_gpu, kind="stable")
+    key_ref = rows[m // cc].astype(np.int64) * 256 + ref["rank"][m].astype(np.int64)
+    at = np.searchsorted(key_gpu[order], key_ref)
+    found = (at < len(order)) & (key_gpu[order][np.minimum(at, len(order) - 1)] == key_ref)
+    sel_rows = order[np.minimum(at, len(order) - 1)]
+    valid_exact = bool(found.all() and np.array_equal(got["valid"][sel_rows], ref_sc["valid"]))
+    v = ref_sc["valid"].astype(bool) & found
+    Fa, Fb = got["features"][sel_rows][v].astype(np.float64), ref_sc["features"][v].astype(np.float64)
+    s_med = np.nanmedian(np.abs(Fb), axis=0) if len(Fb) else np.zeros(Fb.shape[1])
+    floor = np.maximum(1e-6, 1e-6 * np.where(np.isfinite(s_med), s_med, 0.0))
+    both_nan = np.isnan(Fa) & np.isnan(Fb)
+    err = np.where(both_nan, 0.0, np.abs(Fa - Fb) / np.maximum(np.maximum(np.abs(Fa), np.abs(Fb)), floor[None, :]))
+    err = np.where(np.isnan(err), np.inf, err)
+    frag_u8 = all(np.array_equal(got[k][sel_rows][v], ref_sc[k][v]) for k in _abi.FRAG_U8)
+    frag_rel = 0.0
+    for k in _abi.FRAG_F32:
+        a, b = got[k][sel_rows][v].astype(np.float64), ref_sc[k][v].astype(np.float64)
+        d = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-6)
+        frag_rel = max(frag_rel, float(d.max()) if d.size else 0.0)
+    return {"n": int(len(m)), "precursors": int(len(rows)), "valid": int(v.sum()), "int_exact": bool(int_exact and score_exact and frag_u8),
+            "selection_score_bit_exact": score_exact, "valid_exact": valid_exact, "max_rel": float(err.max()) if err.size else 0.0,
+            "fragment_table_max_rel": frag_rel, "features_bit_identical_frac": float((Fa == Fb).mean()) if Fa.size else 1.0,
+            "tolerance": 1e-4,
+            "checked": "candidate container rows (8 integer columns + f32 score, bit for bit), valid mask, 46 features, 12 per-fragment "
+                       "columns of a random library subsample, device results of the timed step vs oracle/adb_oracle.c"}
+
+
 def cpu_baseline(raw, lib, sel, sc, kernel, target_seconds=15.0):
     import oracle
 
@@ -294,6 +348,8 @@ def main():
     ap.add_argument("--precursors", type=int, default=None, help="override the library size (debugging)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check of the timed results")
+    ap.add_argument("--parity-precursors", type=int, default=800)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -309,7 +365,7 @@ def main():
 
     from alphadia_b200 import _lib
     from alphadia_b200.engine import HotPath
-    from alphadia_b200.sharding import allgather_score_table, device_words_from_resident
+    from alphadia_b200.sharding import ScoreTableGather
 
     _lib.require_device()  # no CPU fallback
     torch.cuda.set_device(local_rank)
@@ -328,11 +384,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    gather = None
+    if world > 1:  # preallocated buffers of the single collective: one all-gather of the packed score table
+        gather = ScoreTableGather(int(hp.n_precursors * sel.candidate_count), torch.device("cuda", local_rank))
+
     def one_step():
         r = hp.resident_step()
-        if world > 1:  # the single collective of the path: all-gather of the score table
-            words = device_words_from_resident(hp, lib_pidx_dev)
-            allgather_score_table(words)
+        if gather is not None:
+            gather.pack_resident(hp, lib_pidx_dev)
+            gather.allgather()
         return r
 
     for _ in range(args.warmup):
@@ -365,6 +425,22 @@ def main():
     else:
         t_wall_max, dev_s_max, n_cand_total = t_wall, dev_ms / 1000.0, float(n_cand)
     value = n_cand_total * args.steps / t_wall_max
+
+    # ---- N > 1: the gathered table on every rank must hold every rank's local table (outside the timed region) ----
+    gather_check = None
+    if gather is not None:
+        g_all, sizes = gather.allgather()
+        n_loc = int(gather.n_local.item())
+        local_sum = gather.local[:n_loc].to(torch.int64).sum().reshape(1)
+        sums = torch.zeros(world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(sums, local_sum)
+        sizes_h = sizes.cpu().tolist()
+        ok = all(int(g_all[r, : int(sizes_h[r])].to(torch.int64).sum().item()) == int(sums[r].item()) for r in range(world))
+        ok = ok and bool(torch.equal(g_all[rank, :n_loc], gather.local[:n_loc]))
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_check = {"ok": bool(flag.item() == 1), "rows_per_rank": [int(x) for x in sizes_h],
+                        "what": "on every rank: word checksum of each gathered block == the owner's local checksum, own block bit-identical"}
 
     # ---- e2e through the C ABI with pinned host buffers ------------------------------------------
     alloc = pinned_alloc_factory()
@@ -427,6 +503,11 @@ def main():
                     "other_kernel": {"adb_select_kernel_ms": sel_k, "adb_score_kernel_ms": sc_k,
                                      "select_frac": ab["b_prec"] * hp.n_precursors / (sel_k * 1e-3) / 1e9 / peak,
                                      "score_frac": ab["b_cand"] * n_cand / (sc_k * 1e-3) / 1e9 / peak}}
+        parity = None
+        if not args.no_parity:
+            t0 = time.time()
+            parity = parity_spot_check(hp, raw, lib, sel, sc, kernel, cont, n_prec=args.parity_precursors)
+            log(f"parity spot check done in {time.time() - t0:.1f}s: {json.dumps(parity)}")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             t0 = time.time()
@@ -450,6 +531,10 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
+        if parity is not None:
+            line["parity"] = parity
+        if gather_check is not None:
+            line["gather_check"] = gather_check
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -313,3 +313,49 @@ SELECTION_VARIANTS2 = {
                    max_size_mobility=12),
     "kernel": dict(fwhm_rt=9.0, fwhm_mobility=0.025, sigma_scale_rt=0.8, sigma_scale_mobility=0.6),
 }
+
+
+def patch_device_with_oracle(monkeypatch, oracle_lib, is4d: bool = False):
+    """CPU tests of the HOST side of the operator classes: the device entry points of ``alphadia_b200._lib`` are replaced by
+    the oracle for the duration of one test (there is no GPU and no CPU fallback in the product; the GPU tests run the real
+    calls)."""
+    from alphadia_b200 import _abi, _lib
+
+    int_cols = ["precursor_idx", "rank", "scan_center", "scan_start", "scan_stop", "frame_center", "frame_start", "frame_stop"]
+    state = {}
+
+    class HostRaw:
+        device = 0
+
+        def __init__(self, arrays):
+            self.arrays = arrays
+
+        def last_timing(self):
+            return {}
+
+    class HostLibrary:
+        def __init__(self, arrays, device=0):
+            self.arrays = arrays
+
+        def close(self):
+            pass
+
+    def select_resident(dev_raw, dev_lib, cfg, kernel):
+        select = oracle_lib.select_candidates_4d if is4d else oracle_lib.select_candidates
+        arrs = select(dev_raw.arrays, dev_lib.arrays, cfg, kernel)
+        keep = arrs["score"] > 0  # adb_fetch_candidate_table: rows with score > 0 in container order
+        state["table"] = {c: arrs[c][keep] for c in int_cols + ["score"]}
+        return int(keep.sum())
+
+    def fetch_table(dev_raw, n, arrs=None):
+        table = _abi.alloc_candidate_table(n)
+        for c, v in state["table"].items():
+            table[c][:n] = v
+        return table
+
+    score = oracle_lib.score_candidates_4d if is4d else oracle_lib.score_candidates
+    monkeypatch.setattr(_lib, "device_rawfile_for", lambda dia_data, adapted: HostRaw(adapted))
+    monkeypatch.setattr(_lib, "DeviceLibrary", HostLibrary)
+    monkeypatch.setattr(_lib, "select_candidates_resident", select_resident)
+    monkeypatch.setattr(_lib, "fetch_candidate_table", fetch_table)
+    monkeypatch.setattr(_lib, "score_candidates", lambda dev_raw, dev_lib, cfg, cin: score(dev_raw.arrays, dev_lib.arrays, cfg, cin))

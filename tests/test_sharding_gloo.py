@@ -40,7 +40,9 @@ def _worker(rank, world, port, q):
 
     import oracle
     from alphadia_b200.library import assemble_library_arrays
-    from alphadia_b200.sharding import allgather_score_table, shard_library
+    import torch
+
+    from alphadia_b200.sharding import ScoreTableGather, allgather_score_table, shard_library
     from tests import helpers as H
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -51,6 +53,12 @@ def _worker(rank, world, port, q):
     sl = assemble_library_arrays(sp, sf, "rt_library", "mobility_library", "mz_library", "mz_library")
     local = _score_library(oracle, H, raw, sl)
     full = allgather_score_table(local)
+    # the preallocated form of the same collective (what bench.py uses with NCCL): capacity = the largest shard's row bound
+    g = ScoreTableGather(len(pdf) * 3, torch.device("cpu"))
+    g.local[: local.shape[0]] = torch.from_numpy(local.view(np.int32))
+    g.n_local.fill_(local.shape[0])
+    g.allgather()
+    assert np.array_equal(g.compact().numpy().view(np.uint32), full)
     q.put((rank, local.shape[0], full))
     dist.barrier()
     dist.destroy_process_group()
