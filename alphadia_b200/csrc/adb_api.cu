@@ -14,7 +14,7 @@
 #include "adb_common.cuh"
 
 #ifndef ADB_SCORE_DP_BATCH
-#define ADB_SCORE_DP_BATCH (1 << 19)  // candidates per batch of the data-parallel scoring passes
+#define ADB_SCORE_DP_BATCH (1 << 19)  // candidates per batch of the data-parallel scoring passes (x 72 rows < 2^32)
 #endif
 #ifndef ADB_SCORE_BLOCKS
 #define ADB_SCORE_BLOCKS 4  // row blocks of a scoring call whose D2H overlaps the next block's kernel (<= 7)
@@ -356,10 +356,10 @@ __global__ void mzindex_keys_kernel(DevRaw raw, uint64_t* keys, uint32_t* vals) 
 }
 
 __global__ void mzindex_gather_kernel(DevRaw raw, const uint64_t* keys, const uint32_t* vals, int64_t n, float* s_mz, float* s_int,
-                                      uint32_t* s_cyc) {
+                                      uint32_t* s_cyc, uint64_t n_segments) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  if ((keys[j] >> 32) >= (uint64_t)raw.cycle_len) { s_mz[j] = 3.0e38f; s_int[j] = 0.f; s_cyc[j] = 0xFFFFFFFFu; return; }  // not in a spectrum
+  if ((keys[j] >> 32) >= n_segments) { s_mz[j] = 3.0e38f; s_int[j] = 0.f; s_cyc[j] = 0xFFFFFFFFu; return; }  // not in a spectrum
   const uint32_t i = vals[j];
   int64_t lo = 0, hi = raw.n_spectra;  // spectrum of peak i: last s with peak_start[s] <= i and i < peak_stop[s]
   while (lo < hi) {
@@ -381,6 +381,38 @@ __global__ void mzindex_segments_kernel(const uint64_t* keys, int64_t n, int64_t
     if (keys[mid] < v) lo = mid + 1; else hi = mid;
   }
   pos_start[p] = lo;
+}
+
+// ---- time-blocked m/z index of a 3-D raw file (candidate scoring) -------------------------------------------
+// one warp per spectrum: key = (cycle position * n_time_blocks + time block, m/z), value = peak index
+__global__ void tbindex_keys_kernel(DevRaw raw, int ntb, uint64_t* keys, uint32_t* vals) {
+  const int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= raw.n_spectra) return;
+  const uint64_t seg = (uint64_t)((s % raw.cycle_len) * ntb + (s / raw.cycle_len) / ADB_TB_CYCLES) << 32;
+  for (int64_t i = raw.peak_start[s] + lane; i < raw.peak_stop[s]; i += 32) {
+    keys[i] = seg | ordered_bits(raw.mz[i]);
+    vals[i] = (uint32_t)i;
+  }
+}
+
+// tb_bucket[seg][b] = first sorted peak whose key is >= (seg, lower edge of bucket b); b == nb: end of the segment
+__global__ void tbindex_bucket_kernel(DevRaw raw, const uint64_t* keys, int64_t n, int64_t n_seg, uint32_t* table) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = raw.tb_nb + 1;
+  if (t >= n_seg * per) return;
+  const int64_t seg = t / per;
+  const int b = (int)(t - seg * per);
+  uint64_t v;
+  if (b == 0) v = (uint64_t)seg << 32;
+  else if (b == raw.tb_nb) v = (uint64_t)(seg + 1) << 32;
+  else v = ((uint64_t)seg << 32) | ordered_bits(adb_tb_edge(raw, b));
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  table[t] = (uint32_t)lo;
 }
 
 // upper bound of the selection cycle window: jitclasses/utils.py:62-70 over every possible precursor RT
@@ -943,7 +975,7 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
       cudaMemsetAsync(v_in, 0, 4 * N, r->stream);
       mzindex_keys_kernel<<<(unsigned)((d->n_spectra * 32 + 255) / 256), 256, 0, r->stream>>>(v, k_in, v_in);
       cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)n, 0, end_bit, r->stream);
-      if (n > 0) mzindex_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, s_mz, s_int, s_cyc);
+      if (n > 0) mzindex_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, s_mz, s_int, s_cyc, (uint64_t)d->cycle_len);
       mzindex_segments_kernel<<<(unsigned)((d->cycle_len + 1 + 255) / 256), 256, 0, r->stream>>>(k_out, n, d->cycle_len, pstart);
       cudaMemsetAsync(s_mz + n, 0x7f, 4 * 64, r->stream);  // padding: huge m/z, never inside a window
       cudaMemsetAsync(s_int + n, 0, 4 * 64, r->stream);
@@ -954,6 +986,47 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
     cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(tmp);
     if (!ok) { cudaGetLastError(); adb_rawfile_destroy(r); return fail("building the m/z-major index failed (out of device memory?)"); }
     v.s_mz = s_mz; v.s_int = s_int; v.s_cyc = s_cyc; v.pos_start = pstart;
+  }
+  {  // derived time-blocked m/z index (see DevRaw): stable radix sort of (cycle position, time block, m/z) over all peaks
+    const int64_t n = d->n_peaks;
+    const size_t N = (size_t)std::max<int64_t>(n, 1);
+    const int64_t n_cycles = (d->n_spectra + d->cycle_len - 1) / d->cycle_len;
+    const int ntb = (int)std::max<int64_t>((n_cycles + ADB_TB_CYCLES - 1) / ADB_TB_CYCLES, 1);
+    const int64_t n_seg = d->cycle_len * ntb;
+    int nb = 64;  // about 8 peaks per bucket of an average segment
+    while (nb < 4096 && (int64_t)nb * 8 * n_seg < n) nb *= 2;
+    v.tb_ntb = ntb; v.tb_nb = nb;
+    v.tb_lo = v.bucket_lo;
+    v.tb_width = v.bucket_width * (float)ADB_N_BUCKETS / (float)nb;
+    if (!(v.tb_width > 0.f)) v.tb_width = 1.f;
+    v.tb_inv_width = 1.0f / v.tb_width;
+    float *t_mz = nullptr, *t_int = nullptr; uint32_t *t_cyc = nullptr, *t_tab = nullptr;
+    auto dalloc = [&](void** p, size_t bytes) { if (cudaMalloc(p, bytes) != cudaSuccess) return 1; r->allocs.push_back(*p); r->bytes += (int64_t)bytes; return 0; };
+    const size_t tab_n = (size_t)n_seg * (size_t)(nb + 1);
+    if (dalloc((void**)&t_mz, 4 * (N + 64)) || dalloc((void**)&t_int, 4 * (N + 64)) || dalloc((void**)&t_cyc, 4 * (N + 64)) ||
+        dalloc((void**)&t_tab, 4 * tab_n)) { adb_rawfile_destroy(r); return fail("cudaMalloc time-blocked m/z index failed"); }
+    uint64_t *k_in = nullptr, *k_out = nullptr; uint32_t *v_in = nullptr, *v_out = nullptr; void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)n, 0, 64, r->stream);
+    bool ok = cudaMalloc((void**)&k_in, 8 * N) == cudaSuccess && cudaMalloc((void**)&k_out, 8 * N) == cudaSuccess &&
+              cudaMalloc((void**)&v_in, 4 * N) == cudaSuccess && cudaMalloc((void**)&v_out, 4 * N) == cudaSuccess &&
+              cudaMalloc(&tmp, tmp_bytes + 16) == cudaSuccess;
+    if (ok) {
+      cudaMemsetAsync(k_in, 0xFF, 8 * N, r->stream);  // peaks outside every spectrum sort to the end
+      cudaMemsetAsync(v_in, 0, 4 * N, r->stream);
+      tbindex_keys_kernel<<<(unsigned)((d->n_spectra * 32 + 255) / 256), 256, 0, r->stream>>>(v, ntb, k_in, v_in);
+      cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)n, 0, 64, r->stream);
+      if (n > 0) mzindex_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, t_mz, t_int, t_cyc, (uint64_t)n_seg);
+      tbindex_bucket_kernel<<<(unsigned)((tab_n + 255) / 256), 256, 0, r->stream>>>(v, k_out, n, n_seg, t_tab);
+      cudaMemsetAsync(t_mz + n, 0x7f, 4 * 64, r->stream);  // padding: huge m/z, never inside a window
+      cudaMemsetAsync(t_int + n, 0, 4 * 64, r->stream);
+      cudaMemsetAsync(t_cyc + n, 0xFF, 4 * 64, r->stream);
+      r->launches += 7;
+      ok = cudaStreamSynchronize(r->stream) == cudaSuccess;
+    }
+    cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(tmp);
+    if (!ok) { cudaGetLastError(); adb_rawfile_destroy(r); return fail("building the time-blocked m/z index failed (out of device memory?)"); }
+    v.tb_mz = t_mz; v.tb_int = t_int; v.tb_cyc = t_cyc; v.tb_bucket = t_tab;
   }
   void* st = nullptr;
   if (cudaMalloc(&st, sizeof(uint32_t)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc status failed"); }

@@ -54,7 +54,37 @@ struct DevRaw {
   const float* s_int;
   const uint32_t* s_cyc;
   const int64_t* pos_start;         // [cycle_len + 1]
+  // derived time-blocked m/z index (built once per file on the device), used by candidate scoring: segment
+  // (cycle position p, time block t = cycle / ADB_TB_CYCLES) holds the peaks of the <= ADB_TB_CYCLES spectra of position p in
+  // that block, stably sorted by m/z.  A scoring window of ~10 cycles touches 1-2 segments and finds ~1 peak of its ppm
+  // window in each; tb_bucket[seg][b] is the absolute index of the first peak of the segment at or above the lower edge
+  // of m/z bucket b (entry tb_nb = segment end), so a query is one table read + a search over a handful of peaks.
+  const float* tb_mz;
+  const float* tb_int;
+  const uint32_t* tb_cyc;
+  const uint32_t* tb_bucket;        // [cycle_len * tb_ntb][tb_nb + 1]
+  int32_t tb_ntb, tb_nb;
+  float tb_lo, tb_width, tb_inv_width;
 };
+
+#define ADB_TB_CYCLES 32
+
+// m/z edge of bucket b of the time-blocked index (the SAME float expression builds the table and routes the queries)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline float adb_tb_edge(const DevRaw& raw, int b) { return fmaf((float)b, raw.tb_width, raw.tb_lo); }
+
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int adb_tb_bucket_of(const DevRaw& raw, float v) {
+  int b = (int)((v - raw.tb_lo) * raw.tb_inv_width);
+  b = b < 0 ? 0 : (b > raw.tb_nb - 1 ? raw.tb_nb - 1 : b);
+  while (b > 0 && adb_tb_edge(raw, b) > v) b--;
+  while (b < raw.tb_nb - 1 && adb_tb_edge(raw, b + 1) <= v) b++;
+  return b;
+}
 
 // timsTOF (4-D) raw file resident in HBM: the TimsTOFTransposeJIT arrays the hot path reads
 // (alphadia/search/jitclasses/bruker_jit.py:20-137), CSR by tof index.

@@ -19,34 +19,34 @@ __global__ void __launch_bounds__(DP_THREADS) dp_setup_kernel(const __grid_const
 }
 
 // thread t <-> (slot, row): rows 0 .. KS-1 are the fragment rows, KS .. KS+nIcap-1 the isotope rows
-__global__ void __launch_bounds__(DP_THREADS) dp_extract_kernel(const __grid_constant__ DpParams P) {
-  const int64_t t = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
-  const int rows = P.KS + P.nIcap;
-  const int64_t j = t / rows;
+__global__ void __launch_bounds__(DP_THREADS, 4) dp_extract_kernel(const __grid_constant__ DpParams P) {
+  const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;  // a batch has < 2^32 rows: 32-bit index arithmetic
+  const uint32_t rows = (uint32_t)(P.KS + P.nIcap);
+  const uint32_t j = t / rows;
   if (j < P.n) dp_extract(P, j, (int)(t - j * rows));
 }
 
-__global__ void __launch_bounds__(DP_THREADS) dp_template_kernel(const __grid_constant__ DpParams P) {
+__global__ void __launch_bounds__(DP_THREADS, 3) dp_template_kernel(const __grid_constant__ DpParams P) {
   const int64_t j = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
   if (j < P.n) dp_template(P, j);
 }
 
-__global__ void __launch_bounds__(DP_THREADS) dp_fragment_kernel(const __grid_constant__ DpParams P) {
-  const int64_t t = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
-  const int64_t j = t / P.KS;
-  if (j < P.n) dp_fragment(P, j, (int)(t - j * P.KS));
+__global__ void __launch_bounds__(DP_THREADS, 3) dp_fragment_kernel(const __grid_constant__ DpParams P) {
+  const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
+  const uint32_t j = t / (uint32_t)P.KS;
+  if (j < P.n) dp_fragment(P, j, (int)(t - j * (uint32_t)P.KS));
 }
 
 __global__ void __launch_bounds__(DP_THREADS) dp_median_kernel(const __grid_constant__ DpParams P) {
-  const int64_t t = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
-  const int64_t j = t / DP_MED_LANES;
+  const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
+  const uint32_t j = t / DP_MED_LANES;
   if (j < P.n) dp_median(P, j, (int)(t % DP_MED_LANES));
 }
 
 __global__ void __launch_bounds__(DP_THREADS) dp_corr_kernel(const __grid_constant__ DpParams P) {
-  const int64_t t = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
-  const int64_t j = t / P.KS;
-  if (j < P.n) dp_corr(P, j, (int)(t - j * P.KS));
+  const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
+  const uint32_t j = t / (uint32_t)P.KS;
+  if (j < P.n) dp_corr(P, j, (int)(t - j * (uint32_t)P.KS));
 }
 
 __global__ void __launch_bounds__(DP_THREADS) dp_aggregate_kernel(const __grid_constant__ DpParams P) {
@@ -55,9 +55,9 @@ __global__ void __launch_bounds__(DP_THREADS) dp_aggregate_kernel(const __grid_c
 }
 
 __global__ void __launch_bounds__(DP_THREADS) dp_write_kernel(const __grid_constant__ DpParams P) {
-  const int64_t t = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
-  const int64_t j = t / P.KS;
-  if (j < P.n) dp_write(P, j, (int)(t - j * P.KS));
+  const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
+  const uint32_t j = t / (uint32_t)P.KS;
+  if (j < P.n) dp_write(P, j, (int)(t - j * (uint32_t)P.KS));
 }
 
 inline unsigned blocks_for(int64_t threads) { return (unsigned)((threads + DP_THREADS - 1) / DP_THREADS); }

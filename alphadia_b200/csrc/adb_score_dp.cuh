@@ -15,8 +15,8 @@
 //   dp_setup      per candidate           fragment selection / m/z sort, isotope windows, quad-window hits, cycle window,
 //                                         quadrupole transfer function; size of the candidate's workspace block
 //   (exclusive scan of the block sizes -> block offsets)
-//   dp_extract    per (candidate, row)    one XIC row (fragment x observation, or isotope) through the m/z-major index:
-//                                         one search + a scan of the peaks inside the ppm window, any cycle
+//   dp_extract    per (candidate, row)    one XIC row (fragment x observation, or isotope) through the time-blocked m/z index:
+//                                         per 32-cycle block one bucket read + a scan of the ~1 peaks inside the ppm window
 //   dp_template   per candidate           template, observation importance, distance-weight tables, precursor features
 //   dp_fragment   per (candidate, frag)   fragment mask, best profile + envelope, area, weighted centres, mass error, cosine,
 //                                         normalised profile, template correlation, FWHM, frame peak
@@ -235,33 +235,40 @@ ADB_HD void dp_setup(const DpParams& P, int64_t j) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// dp_extract: get_dense(absolute_masses=True), alpharaw_jit.py:208-337, one XIC row per thread through the m/z-major index
+// dp_extract: get_dense(absolute_masses=True), alpharaw_jit.py:208-337, one XIC row per thread through the time-blocked m/z index
 // ------------------------------------------------------------------------------------------------------------------
-// All peaks of cycle position `ps` whose m/z lies in [lo, hi] (minus the ones the previous, overlapping window already
-// consumed: the reference's search cursor only moves forward), ascending m/z = the order the reference meets them inside
-// each spectrum; peaks of cycles outside [cs, cs + C) are skipped.  Cell recurrence: alpharaw_jit.py:300-333.
+// All peaks of cycle position `ps` and cycles [cs, cs + C) whose m/z lies in [lo, hi] (minus the ones the previous, overlapping
+// window already consumed: the reference's search cursor only moves forward), through the time-blocked m/z index: per time
+// block one bucket-table read, a short search and a scan of the (about one) peaks inside the ppm window.  Inside a cell the
+// peaks arrive in ascending m/z = the order the reference meets them in the spectrum.  Cell recurrence: alpharaw_jit.py:300-333.
 ADB_HD void dp_extract_row(const DevRaw& raw, int ps, float lo, float hi, float prev_hi, int cs, int C, float* di, float* dm, int stride) {
-  int64_t a = ADB_LD(raw.pos_start + ps), b = ADB_LD(raw.pos_start + ps + 1);
-  const int64_t seg1 = b;
-  while (a < b) {  // first peak of the segment with m/z >= lo
-    const int64_t mid = (a + b) >> 1;
-    if (ADB_LD(raw.s_mz + mid) < lo) a = mid + 1; else b = mid;
-  }
   const bool overlap = prev_hi >= lo;
-  for (int64_t i = a; i < seg1; i++) {
-    const float nm = ADB_LD(raw.s_mz + i);
-    if (!(nm <= hi)) break;
-    if (overlap && nm <= prev_hi) continue;
-    const uint32_t c = ADB_LD(raw.s_cyc + i) - (uint32_t)cs;
-    if (c >= (uint32_t)C) continue;
-    float ni = ADB_LD(raw.s_int + i);
-    ni = ni * (((double)ni > 1e-26) ? 1.0f : 0.0f);
-    const float acc_i = di[c * stride], acc_m = dm[c * stride];
-    const float num32 = acc_m * acc_i + ni * nm;
-    const float den32 = acc_i + ni;
-    const double nd = ((double)num32 + 1e-36) / ((double)den32 + 1e-36);
-    di[c * stride] = den32;
-    dm[c * stride] = (float)nd;
+  const int bk = adb_tb_bucket_of(raw, lo);
+  const int tb0 = cs / ADB_TB_CYCLES, tb1 = (cs + C - 1) / ADB_TB_CYCLES;
+  for (int tb = tb0; tb <= tb1; tb++) {
+    const uint32_t* tab = raw.tb_bucket + (size_t)(ps * raw.tb_ntb + tb) * (size_t)(raw.tb_nb + 1);
+    uint32_t a = ADB_LD(tab + bk), b = ADB_LD(tab + bk + 1);
+    const uint32_t seg1 = ADB_LD(tab + raw.tb_nb);
+    while (b - a > 8u) {  // first peak of the bucket with m/z >= lo
+      const uint32_t mid = (a + b) >> 1;
+      if (ADB_LD(raw.tb_mz + mid) < lo) a = mid + 1; else b = mid;
+    }
+    for (uint32_t i = a; i < seg1; i++) {
+      const float nm = ADB_LD(raw.tb_mz + i);
+      if (nm < lo) continue;
+      if (!(nm <= hi)) break;
+      if (overlap && nm <= prev_hi) continue;
+      const uint32_t c = ADB_LD(raw.tb_cyc + i) - (uint32_t)cs;
+      if (c >= (uint32_t)C) continue;
+      float ni = ADB_LD(raw.tb_int + i);
+      ni = ni * (((double)ni > 1e-26) ? 1.0f : 0.0f);
+      const float acc_i = di[c * stride], acc_m = dm[c * stride];
+      const float num32 = acc_m * acc_i + ni * nm;
+      const float den32 = acc_i + ni;
+      const double nd = ((double)num32 + 1e-36) / ((double)den32 + 1e-36);
+      di[c * stride] = den32;
+      dm[c * stride] = (float)nd;
+    }
   }
 }
 

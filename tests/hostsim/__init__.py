@@ -41,7 +41,7 @@ def lib():
     return _lib
 
 
-def score_candidates(raw, lib_arrays, cfg_struct, cand_in, *, batch=64, order=None, ks=None):
+def score_candidates(raw, lib_arrays, cfg_struct, cand_in, *, batch=64, order=None, ks=None, n_buckets=0):
     """Same signature and result dict as oracle.score_candidates / _lib.score_candidates."""
     L = lib()
     rd, k1 = _abi.make_rawfile3d_desc(raw)
@@ -57,7 +57,7 @@ def score_candidates(raw, lib_arrays, cfg_struct, cand_in, *, batch=64, order=No
         order = np.ascontiguousarray(order, dtype=np.int32)
         order_p = order.ctypes.data_as(C.POINTER(C.c_int32))
     rc = L.adb_hostsim_score(C.byref(rd), C.byref(ld), C.byref(cfg_struct), C.byref(cand_in), C.byref(od), C.c_int32(K), C.c_int32(KS),
-                             C.c_int64(batch), order_p, C.byref(status))
+                             C.c_int64(batch), order_p, C.c_int32(n_buckets), C.byref(status))
     if rc != 0:
         raise RuntimeError("hostsim failed")
     arrs["status"] = status.value

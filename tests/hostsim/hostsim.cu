@@ -11,7 +11,7 @@
 
 extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_desc* ld, const adb_scoring_config* cfg,
                                  const adb_candidates_in* cand, adb_scores_out* out, int32_t out_k, int32_t KS, int64_t batch,
-                                 const int32_t* order, uint32_t* status_out) {
+                                 const int32_t* order, int32_t nb_override, uint32_t* status_out) {
   DevRaw raw{};
   raw.cycle = d->cycle; raw.cycle_len = d->cycle_len; raw.rt_values = d->rt_values; raw.n_spectra = d->n_spectra;
   raw.mobility_values = d->mobility_values; raw.n_mobility = d->n_mobility; raw.peak_start = d->peak_start_idx;
@@ -21,17 +21,37 @@ extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_
   raw.n_ms1_pos = 0;
   for (int64_t j = 0; j < d->cycle_len; j++)
     if ((-1.0 <= d->cycle[2 * j + 1]) && (-1.0 >= d->cycle[2 * j]) && raw.n_ms1_pos < ADB_MAX_MS1_POS) raw.ms1_pos[raw.n_ms1_pos++] = (int32_t)j;
-  // m/z-major index: peaks of every cycle position, stably sorted by m/z (adb_api.cu builds the same with a radix sort)
+  // time-blocked m/z index: peaks of every (cycle position, block of ADB_TB_CYCLES cycles), stably sorted by m/z, plus the
+  // bucket table (adb_api.cu builds the same with a radix sort and binary searches); nb_override exercises several bucket widths
   const int64_t L = d->cycle_len;
-  std::vector<int64_t> idx;
-  std::vector<int64_t> spec_of;
+  const int64_t n_cycles = (d->n_spectra + L - 1) / L;
+  const int ntb = (int)std::max<int64_t>((n_cycles + ADB_TB_CYCLES - 1) / ADB_TB_CYCLES, 1);
+  const int64_t n_seg = L * ntb;
+  float mz_min = 3.0e38f, mz_max = 0.f;
+  for (int64_t s = 0; s < d->n_spectra; s++)
+    if (d->peak_stop_idx[s] > d->peak_start_idx[s]) {
+      mz_min = std::min(mz_min, std::max(d->mz_values[d->peak_start_idx[s]], 0.f));
+      mz_max = std::max(mz_max, std::max(d->mz_values[d->peak_stop_idx[s] - 1], 0.f));
+    }
+  if (!(mz_max > mz_min)) { mz_min = 0.f; mz_max = 1.f; }
+  int nb = 64;
+  while (nb < 4096 && (int64_t)nb * 8 * n_seg < d->n_peaks) nb *= 2;
+  if (nb_override > 0) nb = nb_override;
+  raw.tb_ntb = ntb; raw.tb_nb = nb; raw.tb_lo = mz_min;
+  raw.tb_width = (mz_max - mz_min) / (float)nb * 1.0001f;
+  if (!(raw.tb_width > 0.f)) raw.tb_width = 1.f;
+  raw.tb_inv_width = 1.0f / raw.tb_width;
+  std::vector<int64_t> idx, spec_of;
   idx.reserve((size_t)d->n_peaks); spec_of.reserve((size_t)d->n_peaks);
-  std::vector<int64_t> pos_start((size_t)L + 1, 0);
-  for (int64_t pos = 0; pos < L; pos++) {
-    pos_start[(size_t)pos] = (int64_t)idx.size();
+  std::vector<uint32_t> table((size_t)n_seg * (size_t)(nb + 1));
+  for (int64_t seg = 0; seg < n_seg; seg++) {
+    const int64_t pos = seg / ntb, tb = seg % ntb;
     const size_t seg0 = idx.size();
-    for (int64_t s = pos; s < d->n_spectra; s += L)
+    for (int64_t cyc = tb * ADB_TB_CYCLES; cyc < std::min<int64_t>((tb + 1) * ADB_TB_CYCLES, n_cycles); cyc++) {
+      const int64_t s = cyc * L + pos;
+      if (s >= d->n_spectra) continue;
       for (int64_t i = d->peak_start_idx[s]; i < d->peak_stop_idx[s]; i++) { idx.push_back(i); spec_of.push_back(s); }
+    }
     std::vector<size_t> perm(idx.size() - seg0);
     std::iota(perm.begin(), perm.end(), (size_t)0);
     std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return d->mz_values[idx[seg0 + a]] < d->mz_values[idx[seg0 + b]]; });
@@ -39,14 +59,22 @@ extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_
     for (size_t t = 0; t < perm.size(); t++) { i2[t] = idx[seg0 + perm[t]]; s2[t] = spec_of[seg0 + perm[t]]; }
     std::copy(i2.begin(), i2.end(), idx.begin() + seg0);
     std::copy(s2.begin(), s2.end(), spec_of.begin() + seg0);
+    uint32_t* tab = table.data() + (size_t)seg * (size_t)(nb + 1);
+    size_t cur = seg0;
+    tab[0] = (uint32_t)seg0;
+    for (int b = 1; b < nb; b++) {
+      const float edge = adb_tb_edge(raw, b);
+      while (cur < idx.size() && d->mz_values[idx[cur]] < edge) cur++;
+      tab[b] = (uint32_t)cur;
+    }
+    tab[nb] = (uint32_t)idx.size();
   }
-  pos_start[(size_t)L] = (int64_t)idx.size();
   std::vector<float> s_mz(idx.size() + 1), s_int(idx.size() + 1);
   std::vector<uint32_t> s_cyc(idx.size() + 1);
   for (size_t t = 0; t < idx.size(); t++) {
     s_mz[t] = d->mz_values[idx[t]]; s_int[t] = d->intensity_values[idx[t]]; s_cyc[t] = (uint32_t)(spec_of[t] / L);
   }
-  raw.s_mz = s_mz.data(); raw.s_int = s_int.data(); raw.s_cyc = s_cyc.data(); raw.pos_start = pos_start.data();
+  raw.tb_mz = s_mz.data(); raw.tb_int = s_int.data(); raw.tb_cyc = s_cyc.data(); raw.tb_bucket = table.data();
 
   DevLib lib{};
   lib.n_precursors = ld->n_precursors; lib.precursor_idx = ld->precursor_idx; lib.frag_start_idx = ld->frag_start_idx;
