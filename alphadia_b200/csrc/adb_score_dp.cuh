@@ -241,8 +241,9 @@ ADB_HD void dp_setup(const DpParams& P, int64_t j) {
 // window already consumed: the reference's search cursor only moves forward), through the time-blocked m/z index: per time
 // block one bucket-table read, a short search and a scan of the (about one) peaks inside the ppm window.  Inside a cell the
 // peaks arrive in ascending m/z = the order the reference meets them in the spectrum.  Cell recurrence: alpharaw_jit.py:300-333.
-ADB_HD void dp_extract_row(const DevRaw& raw, int ps, float lo, float hi, float prev_hi, int cs, int C, float* di, float* dm, int stride) {
+ADB_HD bool dp_extract_row(const DevRaw& raw, int ps, float lo, float hi, float prev_hi, int cs, int C, float* di, float* dm, int stride) {
   const bool overlap = prev_hi >= lo;
+  bool any = false;
   const int bk = adb_tb_bucket_of(raw, lo);
   const int tb0 = cs / ADB_TB_CYCLES, tb1 = (cs + C - 1) / ADB_TB_CYCLES;
   for (int tb = tb0; tb <= tb1; tb++) {
@@ -268,8 +269,10 @@ ADB_HD void dp_extract_row(const DevRaw& raw, int ps, float lo, float hi, float 
       const double nd = ((double)num32 + 1e-36) / ((double)den32 + 1e-36);
       di[c * stride] = den32;
       dm[c * stride] = (float)nd;
+      any = true;
     }
   }
+  return any;
 }
 
 // r < KS: fragment row r (all observations); r >= KS: isotope row r - KS
@@ -292,9 +295,11 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
       float* di = blk + l.dfi + (o * C) * F + k;
       float* dm = blk + l.dfm + (o * C) * F + k;
       for (int c = 0; c < C; c++) { di[c * F] = 0.f; dm[c * F] = 0.f; }
-      dp_extract_row(raw, P.pos[j * ADB_MAX_OBS + o], lo, hi, prev_hi, cs, C, di, dm, F);
-      const float qm = P.qmask[j * ADB_MAX_OBS + o];  // candidate.py:290
-      for (int c = 0; c < C; c++) di[c * F] = di[c * F] * qm;
+      // candidate.py:290; an untouched row stays +0 (0 * qmask is a zero of either sign: nothing downstream tells them apart)
+      if (dp_extract_row(raw, P.pos[j * ADB_MAX_OBS + o], lo, hi, prev_hi, cs, C, di, dm, F)) {
+        const float qm = P.qmask[j * ADB_MAX_OBS + o];
+        for (int c = 0; c < C; c++) di[c * F] = di[c * F] * qm;
+      }
     }
     return;
   }
@@ -311,11 +316,12 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
   float* dm = blk + l.dpm + i;
   if (raw.n_ms1_pos == 1) {
     for (int c = 0; c < C; c++) { di[c * nI] = 0.f; dm[c * nI] = 0.f; }
-    dp_extract_row(raw, raw.ms1_pos[0], lo, hi, prev_hi, cs, C, di, dm, nI);
+    if (!dp_extract_row(raw, raw.ms1_pos[0], lo, hi, prev_hi, cs, C, di, dm, nI)) return;  // 0 / (0 + 1e-6) == 0
     for (int c = 0; c < C; c++) {
       const float am = dm[c * nI];
       di[c * nI] = 0.f + di[c * nI];
-      dm[c * nI] = (float)((0.0 + (double)am) / ((double)(am > 0.f ? 1 : 0) + 1e-6));
+      // a zero numerator sends the fp64 division down its slow path; the quotient is the (signed) zero itself
+      dm[c * nI] = (am == 0.f) ? am : (float)((0.0 + (double)am) / ((double)(am > 0.f ? 1 : 0) + 1e-6));
     }
     return;
   }
@@ -658,7 +664,10 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k) {
     for (int c = a0; c < a1; c++) t = t + DP_ISL(c);
     const double cint = (double)t / (double)wnn;
     float* nr = blk + l.nrm + k;
-    for (int c = 0; c < C; c++) nr[c * F] = (cint > 0) ? (float)((double)DP_ISL(c) / cint) : 0.f;
+    for (int c = 0; c < C; c++) {
+      const float xv = DP_ISL(c);  // zero cells skip the fp64 division (0 / cint is the same signed zero)
+      nr[c * F] = (cint > 0) ? ((xv == 0.f) ? xv : (float)((double)xv / cint)) : 0.f;
+    }
 #undef DP_ISL
   } else {
     // legacy (scoring/utils.py:513-571): centred profile and its std for every observation
