@@ -396,6 +396,21 @@ __global__ void tbindex_keys_kernel(DevRaw raw, int ntb, uint64_t* keys, uint32_
   }
 }
 
+// sorted peak j of the time-blocked index as one 16-byte record; the 16 records behind the last peak are padding with a huge
+// m/z that is never inside a window
+__global__ void tbindex_gather_kernel(DevRaw raw, const uint64_t* keys, const uint32_t* vals, int64_t n, float4* pk, uint64_t n_segments) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n + 16) return;
+  if (j >= n || (keys[j] >> 32) >= n_segments) { pk[j] = make_float4(3.0e38f, 0.f, __uint_as_float(0xFFFFFFFFu), 0.f); return; }
+  const uint32_t i = vals[j];
+  int64_t lo = 0, hi = raw.n_spectra;  // spectrum of peak i: last s with peak_start[s] <= i and i < peak_stop[s]
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (raw.peak_stop[mid] <= (int64_t)i) lo = mid + 1; else hi = mid;
+  }
+  pk[j] = make_float4(raw.mz[i], raw.intensity[i], __uint_as_float((uint32_t)(lo / raw.cycle_len)), 0.f);
+}
+
 // tb_bucket[seg][b] = first sorted peak whose key is >= (seg, lower edge of bucket b); b == nb: end of the segment
 __global__ void tbindex_bucket_kernel(DevRaw raw, const uint64_t* keys, int64_t n, int64_t n_seg, uint32_t* table) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -793,7 +808,9 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   int64_t ws_floats = (adb_score_workspace_floats(K, c_max) + 3) & ~(int64_t)3;
   const int KS = std::max(1, std::min(K, std::min(lib->max_lib_fragments, (int)ADB_MAX_LIB_FRAGMENTS)));
   const int nIcap = (int)std::min<int64_t>(std::min<int64_t>(lib->dev.n_isotopes, cfg->top_k_isotopes), ADB_MAX_ISOTOPES);
-  const int64_t dp_batch = std::max<int64_t>(std::min<int64_t>(n, ADB_SCORE_DP_BATCH), 1);
+  int64_t dp_batch_cap = ADB_SCORE_DP_BATCH;
+  if (const char* e = getenv("ADB_DP_BATCH")) dp_batch_cap = std::max<int64_t>(std::min<int64_t>(atoll(e), ADB_SCORE_DP_BATCH), 256);  // tuning
+  const int64_t dp_batch = std::max<int64_t>(std::min<int64_t>(n, dp_batch_cap), 1);
   if (tile_path) {
     // HBM fallback scratch for candidates whose cube exceeds the shared-memory budget
     if (raw->score_ws.reserve(sizeof(float) * (size_t)ws_floats * (size_t)tiles)) return 1;
@@ -1000,11 +1017,10 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
     v.tb_width = v.bucket_width * (float)ADB_N_BUCKETS / (float)nb;
     if (!(v.tb_width > 0.f)) v.tb_width = 1.f;
     v.tb_inv_width = 1.0f / v.tb_width;
-    float *t_mz = nullptr, *t_int = nullptr; uint32_t *t_cyc = nullptr, *t_tab = nullptr;
+    float4* t_pk = nullptr; uint32_t* t_tab = nullptr;
     auto dalloc = [&](void** p, size_t bytes) { if (cudaMalloc(p, bytes) != cudaSuccess) return 1; r->allocs.push_back(*p); r->bytes += (int64_t)bytes; return 0; };
     const size_t tab_n = (size_t)n_seg * (size_t)(nb + 1);
-    if (dalloc((void**)&t_mz, 4 * (N + 64)) || dalloc((void**)&t_int, 4 * (N + 64)) || dalloc((void**)&t_cyc, 4 * (N + 64)) ||
-        dalloc((void**)&t_tab, 4 * tab_n)) { adb_rawfile_destroy(r); return fail("cudaMalloc time-blocked m/z index failed"); }
+    if (dalloc((void**)&t_pk, 16 * (N + 16)) || dalloc((void**)&t_tab, 4 * tab_n)) { adb_rawfile_destroy(r); return fail("cudaMalloc time-blocked m/z index failed"); }
     uint64_t *k_in = nullptr, *k_out = nullptr; uint32_t *v_in = nullptr, *v_out = nullptr; void* tmp = nullptr;
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)n, 0, 64, r->stream);
@@ -1016,17 +1032,14 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
       cudaMemsetAsync(v_in, 0, 4 * N, r->stream);
       tbindex_keys_kernel<<<(unsigned)((d->n_spectra * 32 + 255) / 256), 256, 0, r->stream>>>(v, ntb, k_in, v_in);
       cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)n, 0, 64, r->stream);
-      if (n > 0) mzindex_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, t_mz, t_int, t_cyc, (uint64_t)n_seg);
+      tbindex_gather_kernel<<<(unsigned)((n + 16 + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, t_pk, (uint64_t)n_seg);
       tbindex_bucket_kernel<<<(unsigned)((tab_n + 255) / 256), 256, 0, r->stream>>>(v, k_out, n, n_seg, t_tab);
-      cudaMemsetAsync(t_mz + n, 0x7f, 4 * 64, r->stream);  // padding: huge m/z, never inside a window
-      cudaMemsetAsync(t_int + n, 0, 4 * 64, r->stream);
-      cudaMemsetAsync(t_cyc + n, 0xFF, 4 * 64, r->stream);
-      r->launches += 7;
+      r->launches += 4;
       ok = cudaStreamSynchronize(r->stream) == cudaSuccess;
     }
     cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(tmp);
     if (!ok) { cudaGetLastError(); adb_rawfile_destroy(r); return fail("building the time-blocked m/z index failed (out of device memory?)"); }
-    v.tb_mz = t_mz; v.tb_int = t_int; v.tb_cyc = t_cyc; v.tb_bucket = t_tab;
+    v.tb_pk = t_pk; v.tb_bucket = t_tab;
   }
   void* st = nullptr;
   if (cudaMalloc(&st, sizeof(uint32_t)) != cudaSuccess) { adb_rawfile_destroy(r); return fail("cudaMalloc status failed"); }

@@ -59,9 +59,7 @@ struct DevRaw {
   // that block, stably sorted by m/z.  A scoring window of ~10 cycles touches 1-2 segments and finds ~1 peak of its ppm
   // window in each; tb_bucket[seg][b] is the absolute index of the first peak of the segment at or above the lower edge
   // of m/z bucket b (entry tb_nb = segment end), so a query is one table read + a search over a handful of peaks.
-  const float* tb_mz;
-  const float* tb_int;
-  const uint32_t* tb_cyc;
+  const float4* tb_pk;              // {m/z, intensity, cycle index (bit pattern), 0}: one 128-bit load per peak
   const uint32_t* tb_bucket;        // [cycle_len * tb_ntb][tb_nb + 1]
   int32_t tb_ntb, tb_nb;
   float tb_lo, tb_width, tb_inv_width;

@@ -5,6 +5,8 @@
 #include <algorithm>
 
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include "adb_score_dp.cuh"
 
@@ -31,10 +33,13 @@ __global__ void __launch_bounds__(DP_THREADS, 3) dp_template_kernel(const __grid
   if (j < P.n) dp_template(P, j);
 }
 
+// thread t <-> t-th fragment row with signal of the batch (work list)
 __global__ void __launch_bounds__(DP_THREADS, 3) dp_fragment_kernel(const __grid_constant__ DpParams P) {
   const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
-  const uint32_t j = t / (uint32_t)P.KS;
-  if (j < P.n) dp_fragment(P, j, (int)(t - j * (uint32_t)P.KS));
+  if (t >= (uint32_t)*P.n_work) return;
+  const uint32_t w = P.work[t];
+  const uint32_t j = w / (uint32_t)P.KS;
+  dp_fragment(P, j, (int)(w - j * (uint32_t)P.KS));
 }
 
 __global__ void __launch_bounds__(DP_THREADS) dp_median_kernel(const __grid_constant__ DpParams P) {
@@ -45,8 +50,10 @@ __global__ void __launch_bounds__(DP_THREADS) dp_median_kernel(const __grid_cons
 
 __global__ void __launch_bounds__(DP_THREADS) dp_corr_kernel(const __grid_constant__ DpParams P) {
   const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
-  const uint32_t j = t / (uint32_t)P.KS;
-  if (j < P.n) dp_corr(P, j, (int)(t - j * (uint32_t)P.KS));
+  if (t >= (uint32_t)*P.n_work) return;
+  const uint32_t w = P.work[t];
+  const uint32_t j = w / (uint32_t)P.KS;
+  dp_corr(P, j, (int)(w - j * (uint32_t)P.KS));
 }
 
 __global__ void __launch_bounds__(DP_THREADS) dp_aggregate_kernel(const __grid_constant__ DpParams P) {
@@ -70,9 +77,13 @@ inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 size_t adb_score_dp_plan_bytes(int64_t nb, int KS, int nIcap, size_t* scan_tmp_bytes) {
   size_t tmp = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int64_t*)nullptr, (int64_t*)nullptr, (int)(nb + 1));
+  size_t tmp2 = 0;
+  cub::DeviceSelect::Flagged(nullptr, tmp2, cub::CountingInputIterator<uint32_t>(0), (const uint8_t*)nullptr, (uint32_t*)nullptr,
+                             (int32_t*)nullptr, (int)(nb * KS));
+  tmp = std::max(tmp, tmp2);
   if (scan_tmp_bytes) *scan_tmp_bytes = tmp;
   const size_t N = (size_t)nb;
-  return align256(N) * 3 + align256(4 * N) * 2 + align256(2 * N * ADB_MAX_OBS) + align256(4 * N * (size_t)KS) +
+  return align256(N * (size_t)KS) + align256(4 * N * (size_t)KS) + 256 + align256(N) * 3 + align256(4 * N) * 2 + align256(2 * N * ADB_MAX_OBS) + align256(4 * N * (size_t)KS) +
          align256(8 * N * (size_t)nIcap * ADB_MAX_OBS) + align256(4 * N * ADB_MAX_OBS) + align256(8 * (N + 1)) * 2 + align256(tmp) + 256;
 }
 
@@ -109,6 +120,9 @@ int adb_launch_score_dp(const DevRaw& raw, const DevLib& lib, const adb_scoring_
   int64_t* off = (int64_t*)take(8 * (N + 1));
   P.off = off;
   void* scan_tmp = take(tmp);
+  P.rowflag = (uint8_t*)take(N * (size_t)KS);
+  P.work = (uint32_t*)take(4 * N * (size_t)KS);
+  P.n_work = (int32_t*)take(4);
   for (int64_t base = 0; base < cand.n; base += batch) {
     P.base = base;
     P.n = std::min<int64_t>(batch, cand.n - base);
@@ -123,13 +137,18 @@ int adb_launch_score_dp(const DevRaw& raw, const DevLib& lib, const adb_scoring_
     }
     P.cube = *cube;
     dp_extract_kernel<<<blocks_for(P.n * (P.KS + P.nIcap)), DP_THREADS, 0, stream>>>(P);
+    {
+      size_t tb = tmp;
+      cub::DeviceSelect::Flagged(scan_tmp, tb, cub::CountingInputIterator<uint32_t>(0), (const uint8_t*)P.rowflag, P.work, P.n_work,
+                                 (int)(P.n * P.KS), stream);
+    }
     dp_template_kernel<<<blocks_for(P.n), DP_THREADS, 0, stream>>>(P);
     dp_fragment_kernel<<<blocks_for(P.n * P.KS), DP_THREADS, 0, stream>>>(P);
     if (cfg.experimental_xic) dp_median_kernel<<<blocks_for(P.n * DP_MED_LANES), DP_THREADS, 0, stream>>>(P);
     dp_corr_kernel<<<blocks_for(P.n * P.KS), DP_THREADS, 0, stream>>>(P);
     dp_aggregate_kernel<<<blocks_for(P.n), DP_THREADS, 0, stream>>>(P);
     if (cfg.collect_fragments) dp_write_kernel<<<blocks_for(P.n * P.KS), DP_THREADS, 0, stream>>>(P);
-    if (n_launches) *n_launches += 7 + (cfg.experimental_xic ? 1 : 0) + (cfg.collect_fragments ? 1 : 0);
+    if (n_launches) *n_launches += 9 + (cfg.experimental_xic ? 1 : 0) + (cfg.collect_fragments ? 1 : 0);
   }
   return 0;
 }

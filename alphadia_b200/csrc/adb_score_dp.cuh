@@ -74,6 +74,9 @@ struct DpParams {
   const int64_t* off;    // [n + 1] block offset in floats (output of the scan)
   float* cube;
   uint32_t* status;
+  uint8_t* rowflag;      // [n][KS] 1: fragment row with signal (candidate.py:319-329), written by dp_extract
+  uint32_t* work;        // slot * KS + k of the fragment rows with signal, ascending (compaction of rowflag)
+  int32_t* n_work;       // their number
 };
 
 struct DpLayout {
@@ -239,45 +242,87 @@ ADB_HD void dp_setup(const DpParams& P, int64_t j) {
 // ------------------------------------------------------------------------------------------------------------------
 // All peaks of cycle position `ps` and cycles [cs, cs + C) whose m/z lies in [lo, hi] (minus the ones the previous, overlapping
 // window already consumed: the reference's search cursor only moves forward), through the time-blocked m/z index: per time
-// block one bucket-table read, a short search and a scan of the (about one) peaks inside the ppm window.  Inside a cell the
-// peaks arrive in ascending m/z = the order the reference meets them in the spectrum.  Cell recurrence: alpharaw_jit.py:300-333.
-ADB_HD bool dp_extract_row(const DevRaw& raw, int ps, float lo, float hi, float prev_hi, int cs, int C, float* di, float* dm, int stride) {
+// block one bucket-table read, a branch-free positioning over at most 8 peaks and a scan of the (about one) peaks inside the
+// ppm window, one 128-bit load per peak.  All lanes of a warp reach the scan loop at its first in-window peak, so the cell
+// updates of a warp run together.  Inside a cell the peaks arrive in ascending m/z = the order the reference meets them in
+// the spectrum.  Cell recurrence: alpharaw_jit.py:300-333.  [c_lo, c_hi] grows to the range of cells that were written.
+ADB_HD float dp_cell_mz(float num32, float den32) {
+  // (float)((double(num) + 1e-36) / (double(den) + 1e-36)): for operands in [1e-18, 1e18] the additions are absorbed and
+  // rounding the correctly rounded binary64 quotient of two binary32 numbers to binary32 equals the correctly rounded
+  // binary32 quotient (53 >= 2 * 24 + 2, no double-rounding error; quotient inside the normal range)
+  if (num32 >= 1e-18f && num32 <= 1e18f && den32 >= 1e-18f && den32 <= 1e18f) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(num32, den32);
+#else
+    return num32 / den32;
+#endif
+  }
+  return (float)(((double)num32 + 1e-36) / ((double)den32 + 1e-36));
+}
+
+ADB_HD float4 dp_ld_peak(const float4* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+ADB_HD uint32_t dp_f2u(float x) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(x);
+#else
+  union { float f; uint32_t u; } v; v.f = x; return v.u;
+#endif
+}
+
+ADB_HD void dp_extract_row(const DevRaw& raw, int ps, float lo, float hi, float prev_hi, int cs, int C, float* di, float* dm, int stride,
+                           int& c_lo, int& c_hi) {
+  // first wanted peak: m/z >= lo, or m/z > prev_hi when the previous window reaches into this one (prev_hi >= lo)
   const bool overlap = prev_hi >= lo;
-  bool any = false;
-  const int bk = adb_tb_bucket_of(raw, lo);
+  const float v = overlap ? prev_hi : lo;
+  const int bk = adb_tb_bucket_of(raw, v);
   const int tb0 = cs / ADB_TB_CYCLES, tb1 = (cs + C - 1) / ADB_TB_CYCLES;
   for (int tb = tb0; tb <= tb1; tb++) {
     const uint32_t* tab = raw.tb_bucket + (size_t)(ps * raw.tb_ntb + tb) * (size_t)(raw.tb_nb + 1);
     uint32_t a = ADB_LD(tab + bk), b = ADB_LD(tab + bk + 1);
     const uint32_t seg1 = ADB_LD(tab + raw.tb_nb);
-    while (b - a > 8u) {  // first peak of the bucket with m/z >= lo
+    while (b - a > 8u) {
       const uint32_t mid = (a + b) >> 1;
-      if (ADB_LD(raw.tb_mz + mid) < lo) a = mid + 1; else b = mid;
+      const float m = ADB_LD(&raw.tb_pk[mid].x);
+      if (overlap ? (m <= v) : (m < v)) a = mid + 1; else b = mid;
     }
-    for (uint32_t i = a; i < seg1; i++) {
-      const float nm = ADB_LD(raw.tb_mz + i);
-      if (nm < lo) continue;
+    uint32_t i = a;
+    for (uint32_t q = 0; q < 8u; q++) {  // the records behind the last peak are padding: reading past b is safe
+      const float m = ADB_LD(&raw.tb_pk[a + q].x);
+      i += (a + q < b) && (overlap ? (m <= v) : (m < v));
+    }
+    for (; i < seg1; i++) {
+      const float4 pk = dp_ld_peak(raw.tb_pk + i);
+      const float nm = pk.x;
       if (!(nm <= hi)) break;
-      if (overlap && nm <= prev_hi) continue;
-      const uint32_t c = ADB_LD(raw.tb_cyc + i) - (uint32_t)cs;
-      if (c >= (uint32_t)C) continue;
-      float ni = ADB_LD(raw.tb_int + i);
-      ni = ni * (((double)ni > 1e-26) ? 1.0f : 0.0f);
-      const float acc_i = di[c * stride], acc_m = dm[c * stride];
-      const float num32 = acc_m * acc_i + ni * nm;
-      const float den32 = acc_i + ni;
-      const double nd = ((double)num32 + 1e-36) / ((double)den32 + 1e-36);
-      di[c * stride] = den32;
-      dm[c * stride] = (float)nd;
-      any = true;
+      const uint32_t c = dp_f2u(pk.z) - (uint32_t)cs;
+      if (c < (uint32_t)C) {
+        float ni = pk.y;
+        ni = ni * (((double)ni > 1e-26) ? 1.0f : 0.0f);
+        const float acc_i = di[c * stride], acc_m = dm[c * stride];
+        const float num32 = acc_m * acc_i + ni * nm;
+        const float den32 = acc_i + ni;
+        di[c * stride] = den32;
+        dm[c * stride] = dp_cell_mz(num32, den32);
+        c_lo = min(c_lo, (int)c);
+        c_hi = max(c_hi, (int)c);
+      }
     }
   }
-  return any;
 }
 
 // r < KS: fragment row r (all observations); r >= KS: isotope row r - KS
 ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
-  if (!P.state[j]) return;
+  if (!P.state[j]) {
+    if (r < P.KS) P.rowflag[j * P.KS + r] = 0;
+    return;
+  }
   const DevRaw& raw = P.raw;
   const DevLib& lib = P.lib;
   const adb_scoring_config& cfg = P.cfg;
@@ -287,20 +332,28 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
   const DpLayout l = dp_layout(F, nobs, C, nI, cfg.experimental_xic != 0, raw.n_ms1_pos);
   if (r < P.KS) {
     const int k = r;
-    if (k >= F) return;
+    if (k >= F) { P.rowflag[j * P.KS + k] = 0; return; }
     float lo, hi, plo, prev_hi = -1.0f;
     dp_window(ADB_LD(lib.frag_mz + P.fsel[j * P.KS + k]), cfg.fragment_mz_tolerance, lo, hi);
     if (k > 0) dp_window(ADB_LD(lib.frag_mz + P.fsel[j * P.KS + k - 1]), cfg.fragment_mz_tolerance, plo, prev_hi);
+    // candidate.py:319-329 fragment mask: any signal over observations, scans and cycles.  Cells outside the written range
+    // are +0 and leave the f32 sums unchanged, so the sums run over the written range only.
+    float t_o = 0.f;
     for (int o = 0; o < nobs; o++) {
       float* di = blk + l.dfi + (o * C) * F + k;
       float* dm = blk + l.dfm + (o * C) * F + k;
       for (int c = 0; c < C; c++) { di[c * F] = 0.f; dm[c * F] = 0.f; }
-      // candidate.py:290; an untouched row stays +0 (0 * qmask is a zero of either sign: nothing downstream tells them apart)
-      if (dp_extract_row(raw, P.pos[j * ADB_MAX_OBS + o], lo, hi, prev_hi, cs, C, di, dm, F)) {
-        const float qm = P.qmask[j * ADB_MAX_OBS + o];
-        for (int c = 0; c < C; c++) di[c * F] = di[c * F] * qm;
-      }
+      int c_lo = C, c_hi = -1;
+      dp_extract_row(raw, P.pos[j * ADB_MAX_OBS + o], lo, hi, prev_hi, cs, C, di, dm, F, c_lo, c_hi);
+      // candidate.py:290; an untouched cell stays +0 (0 * qmask is a zero of either sign: nothing downstream tells them apart)
+      const float qm = P.qmask[j * ADB_MAX_OBS + o];
+      float t_c = 0.f;
+      for (int c = c_lo; c <= c_hi; c++) { const float x = di[c * F] * qm; di[c * F] = x; t_c = t_c + x; }
+      t_o = t_o + dp_twice(t_c);
     }
+    const bool fvalid = t_o > 0.f;
+    ((int*)(blk + l.fi))[FI_VALID * F + k] = fvalid ? 1 : 0;
+    P.rowflag[j * P.KS + k] = fvalid ? 1 : 0;
     return;
   }
   // candidate.py:239-269 MS1 cube with the observation collapse (sum of intensities, mean of the non-zero m/z)
@@ -316,8 +369,9 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
   float* dm = blk + l.dpm + i;
   if (raw.n_ms1_pos == 1) {
     for (int c = 0; c < C; c++) { di[c * nI] = 0.f; dm[c * nI] = 0.f; }
-    if (!dp_extract_row(raw, raw.ms1_pos[0], lo, hi, prev_hi, cs, C, di, dm, nI)) return;  // 0 / (0 + 1e-6) == 0
-    for (int c = 0; c < C; c++) {
+    int c_lo = C, c_hi = -1;
+    dp_extract_row(raw, raw.ms1_pos[0], lo, hi, prev_hi, cs, C, di, dm, nI, c_lo, c_hi);
+    for (int c = c_lo; c <= c_hi; c++) {  // unwritten cells: 0 / (0 + 1e-6) == 0
       const float am = dm[c * nI];
       di[c * nI] = 0.f + di[c * nI];
       // a zero numerator sends the fp64 division down its slow path; the quotient is the (signed) zero itself
@@ -332,7 +386,8 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
   for (int c = 0; c < C; c++) { di[c * nI] = 0.f; smz[c] = 0.0; cnt[c] = 0; }
   for (int q = 0; q < raw.n_ms1_pos; q++) {
     for (int c = 0; c < C; c++) { ta[c] = 0.f; tm[c] = 0.f; }
-    dp_extract_row(raw, raw.ms1_pos[q], lo, hi, prev_hi, cs, C, ta, tm, 1);
+    int c_lo = C, c_hi = -1;
+    dp_extract_row(raw, raw.ms1_pos[q], lo, hi, prev_hi, cs, C, ta, tm, 1, c_lo, c_hi);
     for (int c = 0; c < C; c++) {
       di[c * nI] = di[c * nI] + ta[c];
       smz[c] = smz[c] + (double)tm[c];
@@ -540,18 +595,13 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k) {
   const int64_t ci = dp_candidate_of(P, j);
   const int64_t frame_start = P.cand.frame_start[ci], frame_stop = P.cand.frame_stop[ci];
 
-  // candidate.py:319-329 fragment mask: any signal over observations, scans and cycles
-  float tcs[ADB_MAX_OBS];
-  float t_o = 0.f;
+  if (!fi[FI_VALID * F + k]) return;  // candidate.py:319-329 fragment mask, set by dp_extract
+  float tcs[ADB_MAX_OBS];  // per-observation intensity sums over the cycles
   for (int o = 0; o < nobs; o++) {
     float t_c = 0.f;
     for (int c = 0; c < C; c++) t_c = t_c + d[(o * C + c) * F];
     tcs[o] = t_c;
-    t_o = t_o + dp_twice(t_c);
   }
-  const bool fvalid = t_o > 0.f;
-  fi[FI_VALID * F + k] = fvalid ? 1 : 0;
-  if (!fvalid) return;
 
   const int best_obs = dp_best_obs(sc, nobs);
   const bool quant_all = cfg.quant_all != 0;

@@ -69,12 +69,13 @@ extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_
     }
     tab[nb] = (uint32_t)idx.size();
   }
-  std::vector<float> s_mz(idx.size() + 1), s_int(idx.size() + 1);
-  std::vector<uint32_t> s_cyc(idx.size() + 1);
-  for (size_t t = 0; t < idx.size(); t++) {
-    s_mz[t] = d->mz_values[idx[t]]; s_int[t] = d->intensity_values[idx[t]]; s_cyc[t] = (uint32_t)(spec_of[t] / L);
+  std::vector<float4> s_pk(idx.size() + 16);
+  for (size_t t = 0; t < s_pk.size(); t++) {
+    union { uint32_t u; float f; } cyc;
+    cyc.u = t < idx.size() ? (uint32_t)(spec_of[t] / L) : 0xFFFFFFFFu;
+    s_pk[t] = t < idx.size() ? make_float4(d->mz_values[idx[t]], d->intensity_values[idx[t]], cyc.f, 0.f) : make_float4(3.0e38f, 0.f, cyc.f, 0.f);
   }
-  raw.tb_mz = s_mz.data(); raw.tb_int = s_int.data(); raw.tb_cyc = s_cyc.data(); raw.tb_bucket = table.data();
+  raw.tb_pk = s_pk.data(); raw.tb_bucket = table.data();
 
   DevLib lib{};
   lib.n_precursors = ld->n_precursors; lib.precursor_idx = ld->precursor_idx; lib.frag_start_idx = ld->frag_start_idx;
@@ -103,6 +104,10 @@ extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_
   std::vector<double> qtf(N * (size_t)P.nIcap * ADB_MAX_OBS);
   std::vector<float> qmask(N * ADB_MAX_OBS);
   std::vector<int64_t> need(N + 1), off(N + 1);
+  std::vector<uint8_t> rowflag(N * (size_t)KS);
+  std::vector<uint32_t> work(N * (size_t)KS);
+  int32_t n_work = 0;
+  P.rowflag = rowflag.data(); P.work = work.data(); P.n_work = &n_work;
   P.state = state.data(); P.F = F.data(); P.nobs = nobs.data(); P.C = C.data(); P.cs = cs.data(); P.pos = pos.data();
   P.fsel = fsel.data(); P.qtf = qtf.data(); P.qmask = qmask.data(); P.need = need.data(); P.off = off.data();
   std::vector<float> cube;
@@ -118,9 +123,11 @@ extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_
     const int rows = P.KS + P.nIcap;
     for (int64_t t = 0; t < P.n * rows; t++) dp_extract(P, t / rows, (int)(t % rows));
     for (int64_t j = 0; j < P.n; j++) dp_template(P, j);
-    for (int64_t t = 0; t < P.n * P.KS; t++) dp_fragment(P, t / P.KS, (int)(t % P.KS));
+    n_work = 0;  // cub::DeviceSelect::Flagged on the device
+    for (int64_t t = 0; t < P.n * P.KS; t++) if (rowflag[(size_t)t]) work[(size_t)n_work++] = (uint32_t)t;
+    for (int32_t t = 0; t < n_work; t++) dp_fragment(P, work[(size_t)t] / P.KS, (int)(work[(size_t)t] % P.KS));
     if (cfg->experimental_xic) for (int64_t t = 0; t < P.n * DP_MED_LANES; t++) dp_median(P, t / DP_MED_LANES, (int)(t % DP_MED_LANES));
-    for (int64_t t = 0; t < P.n * P.KS; t++) dp_corr(P, t / P.KS, (int)(t % P.KS));
+    for (int32_t t = 0; t < n_work; t++) dp_corr(P, work[(size_t)t] / P.KS, (int)(work[(size_t)t] % P.KS));
     for (int64_t j = 0; j < P.n; j++) dp_aggregate(P, j);
     if (cfg->collect_fragments) for (int64_t t = 0; t < P.n * P.KS; t++) dp_write(P, t / P.KS, (int)(t % P.KS));
   }
