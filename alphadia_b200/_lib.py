@@ -14,7 +14,7 @@ import numpy as np
 from alphadia_b200 import _abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libalphadia_b200.so")
+SO_PATH = os.environ.get("ADB_LIB_PATH") or os.path.join(HERE, "libalphadia_b200.so")  # ADB_LIB_PATH: tuning builds of the same library
 
 # every symbol include/alphadia_b200.h declares
 EXPORTED_SYMBOLS = [

@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SO_PATH = os.path.join(HERE, "libalphadia_b200.so")
+SO_PATH = os.environ.get("ADB_LIB_PATH") or os.path.join(HERE, "libalphadia_b200.so")
 SOURCES = ["adb_api.cu", "adb_select.cu", "adb_score.cu", "adb_score_dp.cu", "adb_misc.cu", "adb_select4d.cu", "adb_score4d.cu"]
 # per-file flags: the data-parallel scoring passes are written in plain arithmetic and must not be FMA-contracted
 EXTRA_FLAGS = {"adb_score_dp.cu": ["--fmad=false"]}
@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = nvcc_path()
     objs = []
     procs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build" + (("_" + os.path.basename(SO_PATH)) if os.environ.get("ADB_LIB_PATH") else ""))
     os.makedirs(build_dir, exist_ok=True)
     common = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

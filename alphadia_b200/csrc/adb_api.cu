@@ -14,7 +14,8 @@
 #include "adb_common.cuh"
 
 #ifndef ADB_SCORE_DP_BATCH
-#define ADB_SCORE_DP_BATCH (1 << 19)  // candidates per batch of the data-parallel scoring passes (x 72 rows < 2^32)
+#define ADB_SCORE_DP_BATCH (1 << 21)
+#define ADB_SCORE_DP_BATCH_MAX (1 << 22)  // candidates per batch of the data-parallel scoring passes (x 72 rows < 2^32)
 #endif
 #ifndef ADB_SCORE_BLOCKS
 #define ADB_SCORE_BLOCKS 4  // row blocks of a scoring call whose D2H overlaps the next block's kernel (<= 7)
@@ -809,7 +810,7 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   const int KS = std::max(1, std::min(K, std::min(lib->max_lib_fragments, (int)ADB_MAX_LIB_FRAGMENTS)));
   const int nIcap = (int)std::min<int64_t>(std::min<int64_t>(lib->dev.n_isotopes, cfg->top_k_isotopes), ADB_MAX_ISOTOPES);
   int64_t dp_batch_cap = ADB_SCORE_DP_BATCH;
-  if (const char* e = getenv("ADB_DP_BATCH")) dp_batch_cap = std::max<int64_t>(std::min<int64_t>(atoll(e), ADB_SCORE_DP_BATCH), 256);  // tuning
+  if (const char* e = getenv("ADB_DP_BATCH")) dp_batch_cap = std::max<int64_t>(std::min<int64_t>(atoll(e), ADB_SCORE_DP_BATCH_MAX), 256);  // tuning
   const int64_t dp_batch = std::max<int64_t>(std::min<int64_t>(n, dp_batch_cap), 1);
   if (tile_path) {
     // HBM fallback scratch for candidates whose cube exceeds the shared-memory budget

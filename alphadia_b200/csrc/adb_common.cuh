@@ -65,7 +65,9 @@ struct DevRaw {
   float tb_lo, tb_width, tb_inv_width;
 };
 
+#ifndef ADB_TB_CYCLES
 #define ADB_TB_CYCLES 32
+#endif
 
 // m/z edge of bucket b of the time-blocked index (the SAME float expression builds the table and routes the queries)
 #if defined(__CUDACC__)

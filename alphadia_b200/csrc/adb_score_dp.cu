@@ -13,6 +13,20 @@
 namespace {
 
 constexpr int DP_THREADS = 256;
+#ifndef DP_LB_EXTRACT
+#define DP_LB_EXTRACT 5
+#endif
+#ifndef DP_LB_TEMPLATE
+#define DP_LB_TEMPLATE 4
+#endif
+#ifndef DP_LB_FRAGMENT
+#define DP_LB_FRAGMENT 4
+#endif
+
+__global__ void dp_wtab_p_kernel(double* tab) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 2 * DP_WTAB_P_STRIDE) tab[t] = dp_wtab_p_entry(t / DP_WTAB_P_STRIDE, t % DP_WTAB_P_STRIDE);
+}
 
 __global__ void __launch_bounds__(DP_THREADS) dp_setup_kernel(const __grid_constant__ DpParams P) {
   const int64_t j = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
@@ -21,20 +35,20 @@ __global__ void __launch_bounds__(DP_THREADS) dp_setup_kernel(const __grid_const
 }
 
 // thread t <-> (slot, row): rows 0 .. KS-1 are the fragment rows, KS .. KS+nIcap-1 the isotope rows
-__global__ void __launch_bounds__(DP_THREADS, 4) dp_extract_kernel(const __grid_constant__ DpParams P) {
+__global__ void __launch_bounds__(DP_THREADS, DP_LB_EXTRACT) dp_extract_kernel(const __grid_constant__ DpParams P) {
   const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;  // a batch has < 2^32 rows: 32-bit index arithmetic
   const uint32_t rows = (uint32_t)(P.KS + P.nIcap);
   const uint32_t j = t / rows;
   if (j < P.n) dp_extract(P, j, (int)(t - j * rows));
 }
 
-__global__ void __launch_bounds__(DP_THREADS, 3) dp_template_kernel(const __grid_constant__ DpParams P) {
+__global__ void __launch_bounds__(DP_THREADS, DP_LB_TEMPLATE) dp_template_kernel(const __grid_constant__ DpParams P) {
   const int64_t j = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
   if (j < P.n) dp_template(P, j);
 }
 
 // thread t <-> t-th fragment row with signal of the batch (work list)
-__global__ void __launch_bounds__(DP_THREADS, 3) dp_fragment_kernel(const __grid_constant__ DpParams P) {
+__global__ void __launch_bounds__(DP_THREADS, DP_LB_FRAGMENT) dp_fragment_kernel(const __grid_constant__ DpParams P) {
   const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
   if (t >= (uint32_t)*P.n_work) return;
   const uint32_t w = P.work[t];
@@ -83,7 +97,7 @@ size_t adb_score_dp_plan_bytes(int64_t nb, int KS, int nIcap, size_t* scan_tmp_b
   tmp = std::max(tmp, tmp2);
   if (scan_tmp_bytes) *scan_tmp_bytes = tmp;
   const size_t N = (size_t)nb;
-  return align256(N * (size_t)KS) + align256(4 * N * (size_t)KS) + 256 + align256(N) * 3 + align256(4 * N) * 2 + align256(2 * N * ADB_MAX_OBS) + align256(4 * N * (size_t)KS) +
+  return align256(N * (size_t)KS) + align256(4 * N * (size_t)KS) + 256 + align256(16 * DP_WTAB_P_STRIDE) + align256(N) * 3 + align256(4 * N) * 2 + align256(2 * N * ADB_MAX_OBS) + align256(4 * N * (size_t)KS) +
          align256(8 * N * (size_t)nIcap * ADB_MAX_OBS) + align256(4 * N * ADB_MAX_OBS) + align256(8 * (N + 1)) * 2 + align256(tmp) + 256;
 }
 
@@ -123,6 +137,10 @@ int adb_launch_score_dp(const DevRaw& raw, const DevLib& lib, const adb_scoring_
   P.rowflag = (uint8_t*)take(N * (size_t)KS);
   P.work = (uint32_t*)take(4 * N * (size_t)KS);
   P.n_work = (int32_t*)take(4);
+  double* wtab_p = (double*)take(16 * DP_WTAB_P_STRIDE);
+  P.wtab_p = wtab_p;
+  dp_wtab_p_kernel<<<blocks_for(2 * DP_WTAB_P_STRIDE), DP_THREADS, 0, stream>>>(wtab_p);
+  if (n_launches) *n_launches += 1;
   for (int64_t base = 0; base < cand.n; base += batch) {
     P.base = base;
     P.n = std::min<int64_t>(batch, cand.n - base);

@@ -77,10 +77,11 @@ struct DpParams {
   uint8_t* rowflag;      // [n][KS] 1: fragment row with signal (candidate.py:319-329), written by dp_extract
   uint32_t* work;        // slot * KS + k of the fragment rows with signal, ascending (compaction of rowflag)
   int32_t* n_work;       // their number
+  const double* wtab_p;  // [2][DP_WTAB_P_STRIDE] dp_wtab_p_entry(s, c)
 };
 
 struct DpLayout {
-  int dfi, dfm, bp, nrm, isl, dpi, dpm, tmpl, tfp, med, wtab, wtab_p, red, ms1, fd, ff, fi, sc, total;
+  int dfi, dfm, bp, nrm, isl, dpi, dpm, tmpl, tfp, med, wtab, red, ms1, fd, ff, fi, sc, total;
 };
 
 // per-fragment scalar slots (index k < F): doubles in fd, floats in ff, ints in fi; per-candidate scalars in sc
@@ -105,7 +106,6 @@ ADB_HD DpLayout dp_layout(int F, int nobs, int C, int nI, bool experimental, int
   l.med = o; o += C;
   o += o & 1;
   l.wtab = o; o += 4 * nobs * C;                        // double [nobs][2][C]
-  l.wtab_p = o; o += 4 * C;                             // double [2][C]
   l.fd = o; o += 2 * FD_N * F;                          // double [FD_N][F]
   l.ms1 = o; o += (n_ms1_pos > 1) ? 5 * nI * C + ((nI * C) & 1) : 0;  // double smz[nI C]; float ta, tm [nI C]; int cnt[nI C]
   l.red = o; o += experimental ? 0 : F * F;
@@ -131,6 +131,13 @@ ADB_HD void dp_window(float mz, float tol, float& lo, float& hi) {
   const double d = (double)(tol * mz) / 1000000.0;
   lo = (float)((double)mz - d);
   hi = (float)((double)mz + d);
+}
+
+// distance weight of cell (scan s, cycle c) around the fixed precursor centre (2, 1), features_utils.py:9-26
+#define DP_WTAB_P_STRIDE 4096  // = the largest cycle window dp_setup accepts
+ADB_HD double dp_wtab_p_entry(int s, int c) {
+  const double ds = (double)s - 2.0, dc = (double)c - 1.0;
+  return exp(-0.1 * sqrt(ds * ds + dc * dc));
 }
 
 ADB_HD float dp_twice(float x) { return x + x; }  // sum over the two identical scan rows of a 3-D file
@@ -210,7 +217,7 @@ ADB_HD void dp_setup(const DpParams& P, int64_t j) {
       frame_center < 0 || frame_center >= raw.n_spectra || frame_start < 0)
     return;
   if ((cs + C64) * L > raw.n_spectra) return;
-  if (C64 > 4096) { dp_status_or(P.status, ADB_STATUS_SCRATCH_OVERFLOW); return; }
+  if (C64 > DP_WTAB_P_STRIDE) { dp_status_or(P.status, ADB_STATUS_SCRATCH_OVERFLOW); return; }
   const int C = (int)C64;
 
   // quadrupole.py:80-115,261-301 transfer function of every (isotope, observation); candidate.py:287-289 its isotope mean
@@ -297,27 +304,34 @@ ADB_HD void dp_extract_row(const DevRaw& raw, int ps, float lo, float hi, float 
       const float m = ADB_LD(&raw.tb_pk[a + q].x);
       i += (a + q < b) && (overlap ? (m <= v) : (m < v));
     }
-    for (; i < seg1; i++) {
-      const float4 pk = dp_ld_peak(raw.tb_pk + i);
-      const float nm = pk.x;
-      if (!(nm <= hi)) break;
-      const uint32_t c = dp_f2u(pk.z) - (uint32_t)cs;
-      if (c < (uint32_t)C) {
-        float ni = pk.y;
-        ni = ni * (((double)ni > 1e-26) ? 1.0f : 0.0f);
-        const float acc_i = di[c * stride], acc_m = dm[c * stride];
-        const float num32 = acc_m * acc_i + ni * nm;
-        const float den32 = acc_i + ni;
-        di[c * stride] = den32;
-        dm[c * stride] = dp_cell_mz(num32, den32);
-        c_lo = min(c_lo, (int)c);
-        c_hi = max(c_hi, (int)c);
+    // scan: four records per round trip (the records behind the last peak are padding), processed in order
+    bool done = false;
+    while (!done && i < seg1) {
+      float4 pk4[4];
+      for (int q = 0; q < 4; q++) pk4[q] = dp_ld_peak(raw.tb_pk + i + q);
+      for (int q = 0; q < 4; q++) {
+        const float nm = pk4[q].x;
+        if (i + (uint32_t)q >= seg1 || !(nm <= hi)) { done = true; break; }
+        const uint32_t c = dp_f2u(pk4[q].z) - (uint32_t)cs;
+        if (c < (uint32_t)C) {
+          float ni = pk4[q].y;
+          ni = ni * (((double)ni > 1e-26) ? 1.0f : 0.0f);
+          const float acc_i = di[c * stride], acc_m = dm[c * stride];
+          const float num32 = acc_m * acc_i + ni * nm;
+          const float den32 = acc_i + ni;
+          di[c * stride] = den32;
+          dm[c * stride] = dp_cell_mz(num32, den32);
+          c_lo = min(c_lo, (int)c);
+          c_hi = max(c_hi, (int)c);
+        }
       }
+      i += 4u;
     }
   }
 }
 
-// r < KS: fragment row r (all observations); r >= KS: isotope row r - KS
+// r < KS: fragment row r (all observations); r >= KS: isotope row r - KS.  Fragment rows and the isotope rows of a file
+// with one MS1 spectrum per cycle run through the same extraction code (one call site: the lanes of a warp stay together).
 ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
   if (!P.state[j]) {
     if (r < P.KS) P.rowflag[j * P.KS + r] = 0;
@@ -330,55 +344,69 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
   const int nI = min(min(lib.n_isotopes, (int)min(cfg.top_k_isotopes, 1000u)), ADB_MAX_ISOTOPES);
   float* blk = P.cube + P.off[j];
   const DpLayout l = dp_layout(F, nobs, C, nI, cfg.experimental_xic != 0, raw.n_ms1_pos);
-  if (r < P.KS) {
-    const int k = r;
-    if (k >= F) { P.rowflag[j * P.KS + k] = 0; return; }
-    float lo, hi, plo, prev_hi = -1.0f;
-    dp_window(ADB_LD(lib.frag_mz + P.fsel[j * P.KS + k]), cfg.fragment_mz_tolerance, lo, hi);
-    if (k > 0) dp_window(ADB_LD(lib.frag_mz + P.fsel[j * P.KS + k - 1]), cfg.fragment_mz_tolerance, plo, prev_hi);
+  const bool is_frag = r < P.KS;
+  const int k = is_frag ? r : r - P.KS;  // fragment or isotope index
+  if (is_frag ? (k >= F) : (k >= nI)) {
+    if (is_frag) P.rowflag[j * P.KS + k] = 0;
+    return;
+  }
+  // m/z window of the row and of its predecessor (the reference's search cursor only moves forward)
+  float mz_row, mz_prev = 0.f, tol;
+  if (is_frag) {
+    mz_row = ADB_LD(lib.frag_mz + P.fsel[j * P.KS + k]);
+    if (k > 0) mz_prev = ADB_LD(lib.frag_mz + P.fsel[j * P.KS + k - 1]);
+    tol = cfg.fragment_mz_tolerance;
+  } else {  // candidate.py:151-163 isotope m/z
+    const int64_t p = P.cand.lib_row[dp_candidate_of(P, j)];
+    const double charge = (double)lib.charge[p];
+    const float pmz = lib.mz[p];
+    mz_row = (float)((double)k * ADB_ISOTOPE_DIFF / charge) + pmz;
+    if (k > 0) mz_prev = (float)((double)(k - 1) * ADB_ISOTOPE_DIFF / charge) + pmz;
+    tol = cfg.precursor_mz_tolerance;
+  }
+  float lo, hi, plo, prev_hi = -1.0f;
+  dp_window(mz_row, tol, lo, hi);
+  if (k > 0) dp_window(mz_prev, tol, plo, prev_hi);
+
+  if (is_frag || raw.n_ms1_pos == 1) {
+    const int stride = is_frag ? F : nI;
+    const int n_rows = is_frag ? nobs : 1;
     // candidate.py:319-329 fragment mask: any signal over observations, scans and cycles.  Cells outside the written range
     // are +0 and leave the f32 sums unchanged, so the sums run over the written range only.
     float t_o = 0.f;
-    for (int o = 0; o < nobs; o++) {
-      float* di = blk + l.dfi + (o * C) * F + k;
-      float* dm = blk + l.dfm + (o * C) * F + k;
-      for (int c = 0; c < C; c++) { di[c * F] = 0.f; dm[c * F] = 0.f; }
+    for (int o = 0; o < n_rows; o++) {
+      float* di = blk + (is_frag ? l.dfi + (o * C) * F : l.dpi) + k;
+      float* dm = blk + (is_frag ? l.dfm + (o * C) * F : l.dpm) + k;
+      for (int c = 0; c < C; c++) { di[c * stride] = 0.f; dm[c * stride] = 0.f; }
       int c_lo = C, c_hi = -1;
-      dp_extract_row(raw, P.pos[j * ADB_MAX_OBS + o], lo, hi, prev_hi, cs, C, di, dm, F, c_lo, c_hi);
-      // candidate.py:290; an untouched cell stays +0 (0 * qmask is a zero of either sign: nothing downstream tells them apart)
-      const float qm = P.qmask[j * ADB_MAX_OBS + o];
-      float t_c = 0.f;
-      for (int c = c_lo; c <= c_hi; c++) { const float x = di[c * F] * qm; di[c * F] = x; t_c = t_c + x; }
-      t_o = t_o + dp_twice(t_c);
+      dp_extract_row(raw, is_frag ? (int)P.pos[j * ADB_MAX_OBS + o] : raw.ms1_pos[0], lo, hi, prev_hi, cs, C, di, dm, stride, c_lo, c_hi);
+      if (is_frag) {
+        // candidate.py:290; an untouched cell stays +0 (0 * qmask is a zero of either sign: nothing downstream tells them apart)
+        const float qm = P.qmask[j * ADB_MAX_OBS + o];
+        float t_c = 0.f;
+        for (int c = c_lo; c <= c_hi; c++) { const float x = di[c * stride] * qm; di[c * stride] = x; t_c = t_c + x; }
+        t_o = t_o + dp_twice(t_c);
+      } else {
+        // candidate.py:239-269 MS1 observation collapse with one observation; unwritten cells: 0 / (0 + 1e-6) == 0
+        for (int c = c_lo; c <= c_hi; c++) {
+          const float am = dm[c * stride];
+          di[c * stride] = 0.f + di[c * stride];
+          // a zero numerator sends the fp64 division down its slow path; the quotient is the (signed) zero itself
+          dm[c * stride] = (am == 0.f) ? am : (float)((0.0 + (double)am) / ((double)(am > 0.f ? 1 : 0) + 1e-6));
+        }
+      }
     }
-    const bool fvalid = t_o > 0.f;
-    ((int*)(blk + l.fi))[FI_VALID * F + k] = fvalid ? 1 : 0;
-    P.rowflag[j * P.KS + k] = fvalid ? 1 : 0;
+    if (is_frag) {
+      const bool fvalid = t_o > 0.f;
+      ((int*)(blk + l.fi))[FI_VALID * F + k] = fvalid ? 1 : 0;
+      P.rowflag[j * P.KS + k] = fvalid ? 1 : 0;
+    }
     return;
   }
   // candidate.py:239-269 MS1 cube with the observation collapse (sum of intensities, mean of the non-zero m/z)
-  const int i = r - P.KS;
-  if (i >= nI) return;
-  const int64_t p = P.cand.lib_row[dp_candidate_of(P, j)];
-  const double charge = (double)lib.charge[p];
-  const float pmz = lib.mz[p];
-  float lo, hi, plo, prev_hi = -1.0f;
-  dp_window((float)((double)i * ADB_ISOTOPE_DIFF / charge) + pmz, cfg.precursor_mz_tolerance, lo, hi);
-  if (i > 0) dp_window((float)((double)(i - 1) * ADB_ISOTOPE_DIFF / charge) + pmz, cfg.precursor_mz_tolerance, plo, prev_hi);
+  const int i = k;
   float* di = blk + l.dpi + i;
   float* dm = blk + l.dpm + i;
-  if (raw.n_ms1_pos == 1) {
-    for (int c = 0; c < C; c++) { di[c * nI] = 0.f; dm[c * nI] = 0.f; }
-    int c_lo = C, c_hi = -1;
-    dp_extract_row(raw, raw.ms1_pos[0], lo, hi, prev_hi, cs, C, di, dm, nI, c_lo, c_hi);
-    for (int c = c_lo; c <= c_hi; c++) {  // unwritten cells: 0 / (0 + 1e-6) == 0
-      const float am = dm[c * nI];
-      di[c * nI] = 0.f + di[c * nI];
-      // a zero numerator sends the fp64 division down its slow path; the quotient is the (signed) zero itself
-      dm[c * nI] = (am == 0.f) ? am : (float)((0.0 + (double)am) / ((double)(am > 0.f ? 1 : 0) + 1e-6));
-    }
-    return;
-  }
   double* smz = (double*)(blk + l.ms1) + i * C;
   float* ta = blk + l.ms1 + 2 * nI * C + i * C;
   float* tm = blk + l.ms1 + 3 * nI * C + i * C;
@@ -400,12 +428,12 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
 // features_utils.py:9-26 weighted_center_mean of the intensity row r and the m/z row rm (element stride `st`) of one
 // (fragment, observation) cell over the two identical scan rows, with the tabulated distance weights wt[2][C].
 // A cell that is not > 0 adds +0.0, which leaves the (non-negative) running sums bit-identical.
-ADB_HD void dp_weighted_center_mean_pair(const float* r, const float* rm, int st, const double* wt, int C, double& h, double& mz) {
+ADB_HD void dp_weighted_center_mean_pair(const float* r, const float* rm, int st, const double* wt, int wst, int C, double& h, double& mz) {
   double v1 = 0, w1 = 0, v2 = 0, w2 = 0;
   bool any1 = false, any2 = false;
   for (int s = 0; s < 2; s++)
     for (int c = 0; c < C; c++) {
-      const double wgt = wt[s * C + c];
+      const double wgt = wt[s * wst + c];
       const float a = r[c * st], b = rm[c * st];
       const bool pa = a > 0.f, pb = b > 0.f;
       any1 |= pa; any2 |= pb;
@@ -439,7 +467,6 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
   float* tmpl = blk + l.tmpl;
   float* tfp = blk + l.tfp;
   double* wtab = (double*)(blk + l.wtab);
-  double* wtab_p = (double*)(blk + l.wtab_p);
   float* sc = blk + l.sc;
   float iso_int[ADB_MAX_ISOTOPES], iso_mz[ADB_MAX_ISOTOPES];
   const double charge = (double)lib.charge[p];
@@ -483,12 +510,8 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
     sc[SC_YM + o] = ym;
     sc[SC_YSTD + o] = sqrtf(yss / (float)C);
   }
-  // distance-weight tables for weighted_center_mean (features_utils.py:9-26); precursor "centres" = (n_scans, n_observations) = (2, 1)
-  for (int t = 0; t < 2 * C; t++) {
-    const int s = t / C, c = t % C;
-    const double ds = (double)s - 2.0, dc = (double)c - 1.0;
-    wtab_p[t] = exp(-0.1 * sqrt(ds * ds + dc * dc));
-  }
+  // distance-weight tables for weighted_center_mean (features_utils.py:9-26); the precursor "centres" are the constants
+  // (n_scans, n_observations) = (2, 1): that table is the same for every candidate (P.wtab_p, dp_wtab_p_entry)
   for (int o = 0; o < nobs; o++) {  // fragment_features.py:20-49 centre of mass of the template
     const float* r = tmpl + o * C;
     double isum = 0, ssum = 0, fsum = 0;
@@ -527,7 +550,7 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
     float wsp = 0.f;
     for (int o = 0; o < nobs; o++) wsp = wsp + spi[i] * sc[SC_OI + o];
     wspi[i] = wsp;
-    dp_weighted_center_mean_pair(dpi + i, dpm + i, nI, wtab_p, C, H[i], MZo[i]);
+    dp_weighted_center_mean_pair(dpi + i, dpm + i, nI, P.wtab_p, DP_WTAB_P_STRIDE, C, H[i], MZo[i]);
   }
   int amax = 0;
   for (int i = 1; i < nI; i++) if (iso_int[i] > iso_int[amax]) amax = i;
@@ -685,7 +708,7 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k) {
       const double wv = (double)(((obs_mask >> o) & 1u) ? sc[SC_OI + o] : 0.0f) / ((double)wsum + 1e-20);
       if (wv > 0) {
         double h_o, mz_o;
-        dp_weighted_center_mean_pair(d + (o * C) * F, dmz + (o * C) * F, F, wtab + o * 2 * C, C, h_o, mz_o);
+        dp_weighted_center_mean_pair(d + (o * C) * F, dmz + (o * C) * F, F, wtab + o * 2 * C, C, C, h_o, mz_o);
         const double lw = wv / wtot;
         a = a + mz_o * lw;
         bsum = bsum + h_o * lw;

@@ -110,6 +110,9 @@ extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_
   P.rowflag = rowflag.data(); P.work = work.data(); P.n_work = &n_work;
   P.state = state.data(); P.F = F.data(); P.nobs = nobs.data(); P.C = C.data(); P.cs = cs.data(); P.pos = pos.data();
   P.fsel = fsel.data(); P.qtf = qtf.data(); P.qmask = qmask.data(); P.need = need.data(); P.off = off.data();
+  std::vector<double> wtab_p(2 * DP_WTAB_P_STRIDE);
+  for (int t = 0; t < 2 * DP_WTAB_P_STRIDE; t++) wtab_p[(size_t)t] = dp_wtab_p_entry(t / DP_WTAB_P_STRIDE, t % DP_WTAB_P_STRIDE);
+  P.wtab_p = wtab_p.data();
   std::vector<float> cube;
   for (int64_t base = 0; base < cand->n; base += batch) {
     P.base = base;
