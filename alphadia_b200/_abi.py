@@ -153,6 +153,19 @@ class ScoresOut(C.Structure):
     ]
 
 
+class ScoresRagged(C.Structure):
+    """adb_scores_ragged (include/alphadia_b200.h): valid rows + their kept fragment slots, flattened."""
+    _fields_ = [
+        ("row_capacity", C.c_int64), ("frag_capacity", C.c_int64), ("n_rows", C.c_int64), ("n_fragments", C.c_int64),
+        ("row_index", c_i64p), ("features", c_f32p), ("frag_offset", c_i64p),
+        ("fragment_mz_library", c_f32p), ("fragment_mz", c_f32p), ("fragment_mz_observed", c_f32p),
+        ("fragment_height", c_f32p), ("fragment_intensity", c_f32p), ("fragment_mass_error", c_f32p),
+        ("fragment_correlation", c_f32p),
+        ("fragment_position", c_u8p), ("fragment_number", c_u8p), ("fragment_type", c_u8p),
+        ("fragment_charge", c_u8p), ("fragment_loss_type", c_u8p),
+    ]
+
+
 _PTR = {
     np.dtype(np.float32): c_f32p, np.dtype(np.float64): c_f64p, np.dtype(np.int64): c_i64p,
     np.dtype(np.uint32): c_u32p, np.dtype(np.uint8): c_u8p, np.dtype(np.bool_): c_u8p,
@@ -264,6 +277,26 @@ def alloc_scores_out(n: int, top_k: int):
     for k, v in arrs.items():
         setattr(d, k, ptr(v))
     return d, arrs
+
+
+def alloc_scores_ragged(row_capacity: int, frag_capacity: int, alloc=np.empty):
+    """Host buffers of a ragged scoring result; ``alloc(shape, dtype)`` may hand out pinned memory."""
+    rc, fc = max(int(row_capacity), 1), max(int(frag_capacity), 1)
+    arrs = dict(row_index=alloc(rc, np.int64), features=alloc((rc, NUM_FEATURES), np.float32), frag_offset=alloc(rc + 1, np.int64))
+    for k in FRAG_F32:
+        arrs[k] = alloc(fc, np.float32)
+    for k in FRAG_U8:
+        arrs[k] = alloc(fc, np.uint8)
+    return scores_ragged_struct(arrs), arrs
+
+
+def scores_ragged_struct(arrs: dict) -> "ScoresRagged":
+    d = ScoresRagged()
+    d.row_capacity = int(arrs["row_index"].shape[0])
+    d.frag_capacity = int(arrs[FRAG_F32[0]].shape[0])
+    for k, v in arrs.items():
+        setattr(d, k, ptr(v))
+    return d
 
 
 def make_candidates_in(lib_row, rank, scan_start, scan_stop, scan_center, frame_start, frame_stop, frame_center):

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "adb_last_error", "adb_version", "adb_device_count",
     "adb_rawfile3d_create", "adb_rawfile4d_create", "adb_rawfile_destroy", "adb_rawfile_device_bytes", "adb_rawfile_stream",
     "adb_library_create", "adb_library_destroy",
-    "adb_select_candidates", "adb_score_candidates", "adb_fragment_competition", "adb_transpose_csr",
+    "adb_select_candidates", "adb_score_candidates", "adb_score_candidates_ragged", "adb_fragment_competition", "adb_transpose_csr",
     "adb_q_values", "adb_keep_best",
     "adb_select_candidates_resident", "adb_score_candidates_resident",
     "adb_fetch_candidates", "adb_fetch_candidate_table", "adb_fetch_scores", "adb_resident_score_table",
@@ -189,6 +189,28 @@ def score_candidates(dev_raw: DeviceRawFile, dev_lib: DeviceLibrary, cfg_struct,
     check(lib.adb_score_candidates(dev_raw.handle, dev_lib.handle, C.byref(cfg_struct), C.byref(cand_in_struct), C.byref(od)),
           "adb_score_candidates")
     return arrs
+
+
+def score_candidates_ragged(dev_raw: DeviceRawFile, dev_lib: DeviceLibrary, cfg_struct, cand_in_struct, bufs: dict | None = None,
+                            max_fragments: int | None = None) -> dict:
+    """Scoring with the ragged result of ``adb_score_candidates_ragged``: the feature rows of the valid candidates and their
+    kept fragment slots, flattened in candidate order.  Returns views of length ``n_rows`` / ``n_fragments`` into ``bufs``
+    (allocated on demand: ``n`` rows, ``n * min(top_k_fragments, max_fragments)`` fragment entries)."""
+    lib = load()
+    n = int(cand_in_struct.n)
+    if bufs is None:
+        per = int(cfg_struct.top_k_fragments) if max_fragments is None else min(int(cfg_struct.top_k_fragments), int(max_fragments))
+        rd, bufs = _abi.alloc_scores_ragged(n, n * max(per, 1))
+    else:
+        rd = _abi.scores_ragged_struct(bufs)
+    check(lib.adb_score_candidates_ragged(dev_raw.handle, dev_lib.handle, C.byref(cfg_struct), C.byref(cand_in_struct), C.byref(rd)),
+          "adb_score_candidates_ragged")
+    nr, nf = int(rd.n_rows), int(rd.n_fragments)
+    out = dict(n_rows=nr, n_fragments=nf, row_index=bufs["row_index"][:nr], features=bufs["features"][:nr],
+               frag_offset=bufs["frag_offset"][:nr + 1])
+    for k in _abi.FRAG_F32 + _abi.FRAG_U8:
+        out[k] = bufs[k][:nf]
+    return out
 
 
 def select_candidates_resident(dev_raw, dev_lib, cfg_struct, kernel) -> int:

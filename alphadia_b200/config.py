@@ -139,11 +139,6 @@ class CandidateScoringConfig(_Config):
 
     def to_struct(self, quad_sigma=(0.2, 0.2), quad_delta_mu=(0.0, 0.0)) -> _abi.ScoringConfig:
         self.validate()
-        if self.top_k_fragments > _abi.MAX_FRAGMENTS:
-            raise NotImplementedError(
-                f"top_k_fragments={self.top_k_fragments} exceeds the device limit {_abi.MAX_FRAGMENTS} "
-                "(transfer-library requantification, SURVEY.md §8f rank 4, is not built yet)"
-            )
         s = _abi.ScoringConfig()
         s.collect_fragments = int(bool(self.collect_fragments))
         s.exclude_shared_ions = int(bool(self.exclude_shared_ions))

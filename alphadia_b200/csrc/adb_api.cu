@@ -20,6 +20,9 @@
 #ifndef ADB_SCORE_BLOCKS
 #define ADB_SCORE_BLOCKS 4  // row blocks of a scoring call whose D2H overlaps the next block's kernel (<= 7)
 #endif
+#ifndef ADB_RAGGED_BLOCKS
+#define ADB_RAGGED_BLOCKS 6  // same for ragged results: a block's copy starts one block late (<= 7)
+#endif
 
 namespace {
 
@@ -138,6 +141,10 @@ struct adb_rawfile {
   DevScoresOut d_scores{};
   int64_t scores_n = 0;
   int scores_k = 0;
+  // ragged results (adb_score_candidates_ragged): device-compacted tables + per-block running totals
+  DeviceBuffer rag_rows, rag_frags, rag_scan, rag_scan_tmp, rag_tot;
+  int64_t* rag_host_tot = nullptr;  // pinned [2 * (ADB_RAGGED_MAX_BLOCKS + 1)]
+  cudaEvent_t rag_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -760,6 +767,166 @@ bool use_tile_scoring() {  // ADB_SCORE_TILE=1: the r1 tile-per-candidate kernel
   return e && e[0] == '1';
 }
 
+// ---- ragged results: device-side compaction to what collect_candidates / collect_fragments keep ------------------------
+// (scoring/output.py:72-97): rows with valid != 0 and, of those, the fragment slots with mz_library > 0
+struct RaggedDev {
+  int64_t* row_index;   // [n]
+  int64_t* frag_offset; // [n + 1]
+  float* features;      // [n, 46]
+  float* f32[7];        // [n * K] each, order of adb_scores_ragged
+  uint8_t* u8[5];
+};
+
+size_t ragged_rows_bytes(int64_t n) { return (size_t)n * (8 + 4 * ADB_NUM_FEATURES) + ((size_t)n + 1) * 8 + 3 * 256; }
+size_t ragged_frags_bytes(int64_t n, int k) { return ((size_t)n * (size_t)k * 4 + 256) * 7 + ((size_t)n * (size_t)k + 256) * 5; }
+
+RaggedDev carve_ragged(void* rows, void* frags, int64_t n, int k) {
+  RaggedDev r{};
+  const size_t N = (size_t)n, NK = (size_t)n * (size_t)k;
+  char* p = (char*)rows;
+  auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) & ~(size_t)255; return q; };
+  r.row_index = (int64_t*)take(8 * N);
+  r.frag_offset = (int64_t*)take(8 * (N + 1));
+  r.features = (float*)take(4 * N * ADB_NUM_FEATURES);
+  p = (char*)frags;
+  for (int i = 0; i < 7; i++) r.f32[i] = (float*)take(4 * NK);
+  for (int i = 0; i < 5; i++) r.u8[i] = (uint8_t*)take(NK);
+  return r;
+}
+
+// per row of the block: (valid, kept fragment slots) packed as (1 << 32) | n_slots
+__global__ void ragged_count_kernel(DevScoresOut s, int k, int64_t r0, int64_t r1, unsigned long long* packed) {
+  const int64_t i = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= r1) return;
+  unsigned long long v = 0;
+  if (s.valid[i]) {
+    unsigned c = 0;
+    const float* m = s.fragment_mz_library + (size_t)i * (size_t)k;
+    for (int q = 0; q < k; q++) c += m[q] > 0.f;
+    v = (1ull << 32) | c;
+  }
+  packed[i - r0] = v;
+}
+
+// one warp per row: position = running totals of the earlier blocks + exclusive prefix inside the block
+__global__ void ragged_scatter_kernel(DevScoresOut s, int k, int64_t r0, int64_t r1, const unsigned long long* packed,
+                                      const unsigned long long* prefix, const int64_t* tot, RaggedDev out) {
+  const int64_t i = r0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= r1) return;
+  if (!(packed[i - r0] >> 32)) return;
+  const unsigned long long pre = prefix[i - r0];
+  const int64_t p = tot[0] + (int64_t)(pre >> 32);
+  int64_t q = tot[1] + (int64_t)(pre & 0xFFFFFFFFull);
+  if (lane == 0) { out.row_index[p] = i; out.frag_offset[p] = q; }
+  for (int t = lane; t < ADB_NUM_FEATURES; t += 32) out.features[(size_t)p * ADB_NUM_FEATURES + t] = s.features[(size_t)i * ADB_NUM_FEATURES + t];
+  const float* const src_f[7] = {s.fragment_mz_library, s.fragment_mz, s.fragment_mz_observed, s.fragment_height,
+                                 s.fragment_intensity, s.fragment_mass_error, s.fragment_correlation};
+  const uint8_t* const src_u[5] = {s.fragment_position, s.fragment_number, s.fragment_type, s.fragment_charge, s.fragment_loss_type};
+  for (int base = 0; base < k; base += 32) {
+    const int slot = base + lane;
+    const size_t a = (size_t)i * (size_t)k + (size_t)slot;
+    const bool keep = slot < k && s.fragment_mz_library[a] > 0.f;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+    if (keep) {
+      const int64_t d = q + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+      for (int c = 0; c < 7; c++) out.f32[c][d] = src_f[c][a];
+#pragma unroll
+      for (int c = 0; c < 5; c++) out.u8[c][d] = src_u[c][a];
+    }
+    q += __popc(m);
+  }
+}
+
+// tot += totals of the block; snap[0..1] = tot after the block
+__global__ void ragged_advance_kernel(const unsigned long long* packed, const unsigned long long* prefix, int64_t nb, int64_t* tot, int64_t* snap) {
+  if (nb > 0) {
+    const unsigned long long t = prefix[nb - 1] + packed[nb - 1];
+    tot[0] += (int64_t)(t >> 32);
+    tot[1] += (int64_t)(t & 0xFFFFFFFFull);
+  }
+  snap[0] = tot[0];
+  snap[1] = tot[1];
+}
+
+struct RaggedRun {  // host state of one adb_score_candidates_ragged call
+  adb_scores_ragged* out = nullptr;
+  RaggedDev dev{};
+  int k = 0;
+  int n_blocks = 0, copied = 0;
+  bool overflow = false;
+};
+
+int ragged_begin(adb_rawfile* raw, RaggedRun& R, int64_t n, int k) {
+  R.k = k;
+  R.n_blocks = 0;
+  R.copied = 0;
+  const int64_t N = std::max<int64_t>(n, 1);
+  if (raw->rag_rows.reserve(ragged_rows_bytes(N)) || raw->rag_frags.reserve(ragged_frags_bytes(N, k)) ||
+      raw->rag_scan.reserve(16 * (size_t)N + 512) || raw->rag_tot.reserve(256))
+    return 1;
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)N);
+  if (raw->rag_scan_tmp.reserve(tmp + 256)) return 1;
+  if (!raw->rag_host_tot) {
+    CUDA_TRY(cudaHostAlloc((void**)&raw->rag_host_tot, sizeof(int64_t) * 2 * 9, cudaHostAllocDefault));
+    for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreateWithFlags(&raw->rag_ev[i], cudaEventDisableTiming));
+  }
+  R.dev = carve_ragged(raw->rag_rows.ptr, raw->rag_frags.ptr, N, k);
+  CUDA_TRY(cudaMemsetAsync(raw->rag_tot.ptr, 0, 256, raw->stream));
+  raw->rag_host_tot[0] = raw->rag_host_tot[1] = 0;
+  return 0;
+}
+
+// on `st` (after the rows [r0, r1) are scored): compaction of the block + its running totals to the host
+int ragged_compact_block(adb_rawfile* raw, RaggedRun& R, int64_t r0, int64_t r1, cudaStream_t st) {
+  const int b = R.n_blocks++;
+  const int64_t nb = r1 - r0;
+  unsigned long long* packed = raw->rag_scan.as<unsigned long long>() + r0;
+  unsigned long long* prefix = packed + std::max<int64_t>(raw->scores_n, 1);
+  int64_t* tot = raw->rag_tot.as<int64_t>();
+  if (nb > 0) {
+    ragged_count_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(raw->d_scores, R.k, r0, r1, packed);
+    size_t tmp = raw->rag_scan_tmp.bytes;
+    cub::DeviceScan::ExclusiveSum(raw->rag_scan_tmp.ptr, tmp, packed, prefix, (int)nb, st);
+    ragged_scatter_kernel<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, st>>>(raw->d_scores, R.k, r0, r1, packed, prefix, tot, R.dev);
+    raw->launches += 4;
+  }
+  ragged_advance_kernel<<<1, 1, 0, st>>>(packed, prefix, nb, tot, tot + 2 + 2 * b);
+  raw->launches++;
+  CUDA_TRY(cudaMemcpyAsync(raw->rag_host_tot + 2 * (b + 1), tot + 2 + 2 * b, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(raw->rag_ev[b], st));
+  return 0;
+}
+
+// D2H of the compacted blocks [R.copied, upto) whose totals have arrived (blocks wait for their event)
+int ragged_copy_blocks(adb_rawfile* raw, RaggedRun& R, int upto, cudaStream_t st) {
+  adb_scores_ragged* o = R.out;
+  for (; R.copied < upto; R.copied++) {
+    const int b = R.copied;
+    CUDA_TRY(cudaEventSynchronize(raw->rag_ev[b]));
+    const int64_t p0 = raw->rag_host_tot[2 * b], p1 = raw->rag_host_tot[2 * b + 2];
+    const int64_t q0 = raw->rag_host_tot[2 * b + 1], q1 = raw->rag_host_tot[2 * b + 3];
+    if (p1 > o->row_capacity || q1 > o->frag_capacity) { R.overflow = true; continue; }
+    if (p1 > p0) {
+      const size_t a = (size_t)p0, N = (size_t)(p1 - p0);
+      CUDA_TRY(cudaMemcpyAsync(o->row_index + a, R.dev.row_index + a, 8 * N, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(o->frag_offset + a, R.dev.frag_offset + a, 8 * N, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(o->features + a * ADB_NUM_FEATURES, R.dev.features + a * ADB_NUM_FEATURES, 4 * N * ADB_NUM_FEATURES, cudaMemcpyDeviceToHost, st));
+    }
+    if (q1 > q0) {
+      const size_t a = (size_t)q0, N = (size_t)(q1 - q0);
+      float* hf[7] = {o->fragment_mz_library, o->fragment_mz, o->fragment_mz_observed, o->fragment_height,
+                      o->fragment_intensity, o->fragment_mass_error, o->fragment_correlation};
+      uint8_t* hu[5] = {o->fragment_position, o->fragment_number, o->fragment_type, o->fragment_charge, o->fragment_loss_type};
+      for (int c = 0; c < 7; c++) CUDA_TRY(cudaMemcpyAsync(hf[c] + a, R.dev.f32[c] + a, 4 * N, cudaMemcpyDeviceToHost, st));
+      for (int c = 0; c < 5; c++) CUDA_TRY(cudaMemcpyAsync(hu[c] + a, R.dev.u8[c] + a, N, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  return 0;
+}
+
 // D2H of rows [r0, r1) of the resident score tables into the caller's (row-major) host tables
 int copy_score_rows(adb_rawfile* raw, adb_scores_out* out, int64_t r0, int64_t r1, cudaStream_t st) {
   if (r1 <= r0) return 0;
@@ -780,17 +947,34 @@ int copy_score_rows(adb_rawfile* raw, adb_scores_out* out, int64_t r0, int64_t r
 
 // host_out != nullptr: the candidates are scored in up to 4 row blocks and every finished block is copied to the host on a
 // second stream while the next block is being scored
-int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cfg, int64_t c_max_hint, int64_t s_max_hint = 0,
-                adb_scores_out* host_out = nullptr) {
+int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cfg_in, int64_t c_max_hint, int64_t s_max_hint = 0,
+                adb_scores_out* host_out = nullptr, RaggedRun* rag = nullptr) {
   if (raw->device != lib->device) return fail("raw file and library live on different devices");
-  if (cfg->top_k_fragments < 1 || cfg->top_k_fragments > ADB_MAX_FRAGMENTS)
-    return fail("top_k_fragments must be in [1, " + std::to_string(ADB_MAX_FRAGMENTS) + "]");
-  if (cfg->top_k_isotopes < 1) return fail("top_k_isotopes must be >= 1");
+  if (cfg_in->top_k_fragments < 1) return fail("top_k_fragments must be >= 1");
+  if (cfg_in->top_k_isotopes < 1) return fail("top_k_isotopes must be >= 1");
+  adb_scoring_config cfg_eff = *cfg_in;
+  const adb_scoring_config* cfg = &cfg_eff;
+  const bool tile_path = use_tile_scoring();
+  if (rag) {
+    // a candidate keeps at most the fragments its precursor has: the device tables are as wide as the widest precursor
+    cfg_eff.top_k_fragments = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(cfg_in->top_k_fragments, lib->max_lib_fragments));
+    const int cap = (raw->is4d || tile_path) ? ADB_MAX_FRAGMENTS : ADB_MAX_LIB_FRAGMENTS;
+    if ((int)cfg_eff.top_k_fragments > cap)
+      return fail("the library's widest precursor has more than " + std::to_string(cap) + " fragments: not supported on this path");
+  } else if (cfg->top_k_fragments > ADB_MAX_FRAGMENTS) {
+    return fail("top_k_fragments must be in [1, " + std::to_string(ADB_MAX_FRAGMENTS) + "] for dense score tables (use adb_score_candidates_ragged)");
+  }
   if (raw->is4d) {
     if (run_scoring4d(raw, lib, cfg, s_max_hint, c_max_hint /* frames */)) return 1;
     if (host_out) {
       CUDA_TRY(cudaEventRecord(raw->ev[2], raw->stream));
       if (copy_score_rows(raw, host_out, 0, raw->scores_n, raw->stream)) return 1;
+    }
+    if (rag) {
+      CUDA_TRY(cudaEventRecord(raw->ev[2], raw->stream));
+      if (ragged_begin(raw, *rag, raw->scores_n, raw->scores_k)) return 1;
+      if (ragged_compact_block(raw, *rag, 0, raw->scores_n, raw->stream)) return 1;
+      if (ragged_copy_blocks(raw, *rag, rag->n_blocks, raw->stream)) return 1;
     }
     return 0;
   }
@@ -803,7 +987,7 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   raw->scores_k = K;
   // OutputPsmDF.__init__ zero-fills (scoring/output.py:42-70)
   CUDA_TRY(cudaMemsetAsync(raw->scores.ptr, 0, scores_bytes(std::max<int64_t>(n, 1), K), st));
-  const bool tile_path = use_tile_scoring();
+  if (rag && ragged_begin(raw, *rag, n, K)) return 1;
   int tiles = adb_score_resident_tiles(raw->device, K);
   int64_t c_max = std::max<int64_t>(c_max_hint, 32);
   int64_t ws_floats = (adb_score_workspace_floats(K, c_max) + 3) & ~(int64_t)3;
@@ -834,7 +1018,7 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   // processing order: (quad window of the precursor, frame_start) so that co-resident tiles read the same
   // spectra; results do not depend on it (disjoint output rows)
   int32_t* d_order = nullptr;
-  const int n_chunks = (host_out && n >= 200000) ? ADB_SCORE_BLOCKS : 1;
+  const int n_chunks = ((host_out || rag) && n >= 200000) ? (rag ? ADB_RAGGED_BLOCKS : ADB_SCORE_BLOCKS) : 1;
   const int64_t chunk_len = std::max<int64_t>((n + n_chunks - 1) / n_chunks, 1);
   if (n > 1 && n < 2000000000LL) {
     if (raw->order_keys.reserve(sizeof(uint64_t) * 2 * (size_t)n)) return 1;
@@ -862,6 +1046,11 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
       CUDA_TRY(cudaEventRecord(raw->ev[2], st));
       if (copy_score_rows(raw, host_out, 0, n, st)) return 1;
     }
+    if (rag) {
+      CUDA_TRY(cudaEventRecord(raw->ev[2], st));
+      if (ragged_compact_block(raw, *rag, 0, n, st)) return 1;
+      if (ragged_copy_blocks(raw, *rag, rag->n_blocks, st)) return 1;
+    }
   } else {
     for (int k = 0; k < n_chunks; k++) {
       const int64_t c0 = std::min<int64_t>(k * chunk_len, n), c1 = std::min<int64_t>(c0 + chunk_len, n);
@@ -870,15 +1059,42 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
       part.n = c1 - c0;  // the kernel visits order[c0 .. c1): the (window, time)-sorted rows of block k
       if (launch(part, d_order + c0)) return 1;
       CUDA_TRY(cudaEventRecord(raw->chunk_ev[k], st));
+      // ragged: a block is compacted on the copy stream; its D2H is issued once its totals are on the host, i.e. after
+      // the next block has been launched (launching blocks the host on the batch sizes anyway)
+      if (rag && ragged_copy_blocks(raw, *rag, rag->n_blocks, raw->copy_stream)) return 1;
       CUDA_TRY(cudaStreamWaitEvent(raw->copy_stream, raw->chunk_ev[k], 0));
-      if (copy_score_rows(raw, host_out, c0, c1, raw->copy_stream)) return 1;
+      if (host_out && copy_score_rows(raw, host_out, c0, c1, raw->copy_stream)) return 1;
+      if (rag && ragged_compact_block(raw, *rag, c0, c1, raw->copy_stream)) return 1;
     }
+    if (rag && ragged_copy_blocks(raw, *rag, rag->n_blocks, raw->copy_stream)) return 1;
     CUDA_TRY(cudaEventRecord(raw->ev[5], st));
     CUDA_TRY(cudaEventRecord(raw->ev[2], st));
     CUDA_TRY(cudaEventRecord(raw->chunk_ev[7], raw->copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, raw->chunk_ev[7], 0));  // the handle's stream is done when the copies are
   }
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// H2D of a caller's candidate table into the handle (becomes the resident candidate set)
+int upload_candidates(adb_rawfile* raw, const adb_candidates_in* cand) {
+  cudaStream_t st = raw->stream;
+  const int64_t n = cand->n;
+  if (raw->cand_in.reserve(cand_in_bytes(std::max<int64_t>(n, 1)))) return 1;
+  CandInPtrs c = carve_cand_in(raw->cand_in.ptr, std::max<int64_t>(n, 1));
+  if (n > 0) {
+    const size_t N = (size_t)n;
+    CUDA_TRY(cudaMemcpyAsync(c.lib_row, cand->lib_row, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.rank, cand->rank, N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.scan_start, cand->scan_start, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.scan_stop, cand->scan_stop, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.scan_center, cand->scan_center, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.frame_start, cand->frame_start, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.frame_stop, cand->frame_stop, 8 * N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c.frame_center, cand->frame_center, 8 * N, cudaMemcpyHostToDevice, st));
+  }
+  raw->d_cand = DevCandidatesIn{n, c.lib_row, c.rank, c.scan_start, c.scan_stop, c.scan_center, c.frame_start, c.frame_stop, c.frame_center};
+  raw->n_cand = n;
   return 0;
 }
 
@@ -1307,24 +1523,8 @@ int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scori
   if (!raw || !lib || !cfg || !cand || !out) return fail("null argument");
   if (set_device(raw->device)) return 1;
   cudaStream_t st = raw->stream;
-  const int64_t n = cand->n;
   CUDA_TRY(cudaEventRecord(raw->ev[0], st));
-  // H2D of the candidate table
-  if (raw->cand_in.reserve(cand_in_bytes(std::max<int64_t>(n, 1)))) return 1;
-  CandInPtrs c = carve_cand_in(raw->cand_in.ptr, std::max<int64_t>(n, 1));
-  if (n > 0) {
-    const size_t N = (size_t)n;
-    CUDA_TRY(cudaMemcpyAsync(c.lib_row, cand->lib_row, 8 * N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.rank, cand->rank, N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.scan_start, cand->scan_start, 8 * N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.scan_stop, cand->scan_stop, 8 * N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.scan_center, cand->scan_center, 8 * N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.frame_start, cand->frame_start, 8 * N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.frame_stop, cand->frame_stop, 8 * N, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c.frame_center, cand->frame_center, 8 * N, cudaMemcpyHostToDevice, st));
-  }
-  raw->d_cand = DevCandidatesIn{n, c.lib_row, c.rank, c.scan_start, c.scan_stop, c.scan_center, c.frame_start, c.frame_stop, c.frame_center};
-  raw->n_cand = n;
+  if (upload_candidates(raw, cand)) return 1;
   // validation and the scratch extents (longest candidate in frames / scans) are computed on the device
   int64_t s_max = 0, f_max = 0, bad_row = 0;
   if (resident_extents(raw, &s_max, &f_max, lib->dev.n_precursors, &bad_row)) return 1;
@@ -1336,6 +1536,36 @@ int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scori
   CUDA_TRY(cudaEventRecord(raw->ev[3], st));
   if (check_status(raw, "adb_score_candidates")) return 1;
   finish_timing(raw);
+  return 0;
+}
+
+int adb_score_candidates_ragged(adb_rawfile_t* raw, adb_library_t* lib, const adb_scoring_config* cfg,
+                                const adb_candidates_in* cand, adb_scores_ragged* out) {
+  if (!raw || !lib || !cfg || !cand || !out) return fail("null argument");
+  if (set_device(raw->device)) return 1;
+  cudaStream_t st = raw->stream;
+  CUDA_TRY(cudaEventRecord(raw->ev[0], st));
+  if (upload_candidates(raw, cand)) return 1;
+  int64_t s_max = 0, f_max = 0, bad_row = 0;
+  if (resident_extents(raw, &s_max, &f_max, lib->dev.n_precursors, &bad_row)) return 1;
+  if (bad_row) return fail("a candidate refers to a precursor outside the library");
+  const int64_t c_max = raw->is4d ? f_max : f_max / raw->dev.cycle_len + 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[1], st));
+  if (!raw->is4d && c_max > 4096) return fail("a candidate spans more than 4096 cycles");
+  RaggedRun R;
+  R.out = out;
+  out->n_rows = out->n_fragments = 0;
+  if (run_scoring(raw, lib, cfg, c_max, s_max, nullptr, &R)) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[3], st));
+  if (check_status(raw, "adb_score_candidates_ragged")) return 1;
+  CUDA_TRY(cudaStreamSynchronize(raw->copy_stream));
+  finish_timing(raw);
+  out->n_rows = raw->rag_host_tot[2 * R.n_blocks];
+  out->n_fragments = raw->rag_host_tot[2 * R.n_blocks + 1];
+  if (R.overflow || out->n_rows > out->row_capacity || out->n_fragments > out->frag_capacity)
+    return fail("adb_score_candidates_ragged: output capacity too small (needs " + std::to_string(out->n_rows) + " rows, " +
+                std::to_string(out->n_fragments) + " fragment entries)");
+  out->frag_offset[out->n_rows] = out->n_fragments;
   return 0;
 }
 

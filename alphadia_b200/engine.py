@@ -32,6 +32,7 @@ class HotPath:
         self.dev_lib = _lib.DeviceLibrary(lib_arrays, device=self.dev_raw.device)
         self.n_precursors = self.dev_lib.n_precursors
         self.top_k = int(self.score_struct.top_k_fragments)
+        self.max_lib_fragments = int(np.max(lib_arrays["frag_stop_idx"].astype(np.int64) - lib_arrays["frag_start_idx"].astype(np.int64))) if len(lib_arrays["frag_start_idx"]) else 1
         self.n_candidates = 0
         self._host_bufs = None
 
@@ -56,10 +57,12 @@ class HotPath:
         return dict(features=f.value, valid=v.value, lib_row=r.value, rank=k.value, n=int(n.value))
 
     # ---- host buffers (the operator path) -----------------------------------------------------------
-    def host_step(self, alloc=np.zeros) -> dict:
+    def host_step(self, alloc=np.zeros, ragged: bool = True) -> dict:
         """What the reference-facing operators do, with caller-provided (pinned) host memory:
         library batch H2D -> selection -> compacted candidate table D2H (CandidateSelection's DataFrame columns)
         -> candidate table H2D -> scoring -> score + fragment tables D2H (row blocks overlap the scoring kernel).
+        ``ragged`` (default): the result is the device-compacted form of ``adb_score_candidates_ragged`` (valid feature
+        rows + kept fragment slots); otherwise the dense ``[n, top_k]`` tables of ``adb_score_candidates``.
         ``alloc(shape, dtype) -> ndarray`` lets the caller provide pinned host memory."""
         import time
 
@@ -95,22 +98,37 @@ class HotPath:
             lap("candidate_table_d2h")
             cin = _abi.candidates_in_from_table(table, n)
             h2d += n * (7 * 8 + 1)
-            if self._host_bufs["scores"] is None or self._host_bufs["scores_n"] < n:
-                cap = int(n * 1.05) + 16
-                sc = dict(features=alloc((cap, _abi.NUM_FEATURES), np.float32), valid=alloc(cap, np.uint8))
-                for k in _abi.FRAG_F32:
-                    sc[k] = alloc((cap, self.top_k), np.float32)
-                for k in _abi.FRAG_U8:
-                    sc[k] = alloc((cap, self.top_k), np.uint8)
-                self._host_bufs["scores"], self._host_bufs["scores_n"] = sc, cap
-            sc = self._host_bufs["scores"]
-            so = _abi.ScoresOut()
-            for k, v in sc.items():
-                setattr(so, k, _abi.ptr(v))
-            lap("host_glue")
-            _lib.check(lib.adb_score_candidates(self.dev_raw.handle, dev_lib.handle, C.byref(self.score_struct),
-                                                C.byref(cin), C.byref(so)), "adb_score_candidates")
-            d2h += n * (_abi.NUM_FEATURES * 4 + 1 + self.top_k * (7 * 4 + 5))
+            if ragged:
+                # what collect_candidates / collect_fragments keep: feature rows of the valid candidates + their fragment
+                # slots with mz_library > 0, compacted on the device (adb_score_candidates_ragged)
+                per = max(1, min(self.top_k, self.max_lib_fragments))
+                if self._host_bufs["scores"] is None or self._host_bufs["scores_n"] < n or not self._host_bufs.get("ragged"):
+                    cap = int(n * 1.05) + 16
+                    _, sc = _abi.alloc_scores_ragged(cap, cap * per, alloc)
+                    self._host_bufs["scores"], self._host_bufs["scores_n"], self._host_bufs["ragged"] = sc, cap, True
+                sc = self._host_bufs["scores"]
+                lap("host_glue")
+                res = _lib.score_candidates_ragged(self.dev_raw, dev_lib, self.score_struct, cin, bufs=sc)
+                n_valid, n_frag = res["n_rows"], res["n_fragments"]
+                d2h += n_valid * (_abi.NUM_FEATURES * 4 + 16) + 8 + n_frag * (7 * 4 + 5)
+            else:
+                if self._host_bufs["scores"] is None or self._host_bufs["scores_n"] < n or self._host_bufs.get("ragged"):
+                    cap = int(n * 1.05) + 16
+                    sc = dict(features=alloc((cap, _abi.NUM_FEATURES), np.float32), valid=alloc(cap, np.uint8))
+                    for k in _abi.FRAG_F32:
+                        sc[k] = alloc((cap, self.top_k), np.float32)
+                    for k in _abi.FRAG_U8:
+                        sc[k] = alloc((cap, self.top_k), np.uint8)
+                    self._host_bufs["scores"], self._host_bufs["scores_n"], self._host_bufs["ragged"] = sc, cap, False
+                sc = self._host_bufs["scores"]
+                so = _abi.ScoresOut()
+                for k, v in sc.items():
+                    setattr(so, k, _abi.ptr(v))
+                lap("host_glue")
+                _lib.check(lib.adb_score_candidates(self.dev_raw.handle, dev_lib.handle, C.byref(self.score_struct),
+                                                    C.byref(cin), C.byref(so)), "adb_score_candidates")
+                d2h += n * (_abi.NUM_FEATURES * 4 + 1 + self.top_k * (7 * 4 + 5))
+                n_valid, n_frag = int(np.count_nonzero(sc["valid"][:n])), None
             lap("score_call")
             t_phase["score_call_device"] = dict(self.dev_raw.last_timing())
         finally:
@@ -118,8 +136,7 @@ class HotPath:
         self.n_candidates = n
         lap("library_free")
         t_phase["total"] = (time.perf_counter() - t_enter) * 1e3
-        return dict(n_candidates=n, h2d_bytes=h2d, d2h_bytes=d2h, valid=int(np.count_nonzero(sc["valid"][:n])),
-                    phases_ms=t_phase)
+        return dict(n_candidates=n, h2d_bytes=h2d, d2h_bytes=d2h, valid=n_valid, n_fragments=n_frag, phases_ms=t_phase)
 
     def close(self):
         self.dev_lib.close()

@@ -34,20 +34,51 @@ def _integer_columns(df: pd.DataFrame, columns) -> list | None:
     return cols
 
 
+def _dense_codes(v: np.ndarray) -> np.ndarray:
+    """Order-preserving dense codes 0 .. n_distinct-1 of one column (any sortable dtype; NaN / None sort last, as pandas
+    ``sort_values`` places them)."""
+    if v.dtype.kind in "OUS":
+        s = pd.Series(v)
+        codes = s.rank(method="dense", na_option="bottom").to_numpy()
+        return (codes - 1).astype(np.uint64)
+    if v.dtype.kind == "f":
+        nan = np.isnan(v)
+        uniq, inv = np.unique(v[~nan], return_inverse=True)
+        codes = np.full(len(v), len(uniq), dtype=np.uint64)
+        codes[~nan] = inv.astype(np.uint64)
+        return codes
+    _, inv = np.unique(v, return_inverse=True)
+    return inv.astype(np.uint64)
+
+
 def _pack_order_preserving(df: pd.DataFrame, columns) -> np.ndarray:
-    """uint64 key (< 2^63) whose order is the lexicographic order of the given non-negative integer columns."""
+    """uint64 key (< 2^63) whose order is the lexicographic order of the given columns.  Non-negative integer columns are
+    packed as they are; any other column (strings such as the protein group of outputtransform/protein_fdr.py:72, negative
+    or float values) or a key that would not fit is first mapped to order-preserving dense codes on the host; if even the
+    codes need more than 63 bits the rows are ranked by one host lexsort.  Key packing only: the sort that produces the
+    q-values stays on the device."""
     if len(columns) == 0:
         return np.zeros(len(df), dtype=np.uint64)
-    cols = _integer_columns(df, columns)
-    if cols is None:
-        raise NotImplementedError(f"sort columns {list(columns)} must be integer columns")
-    widths = []
-    for v in cols:
-        if len(v) and int(v.min()) < 0:
-            raise NotImplementedError(f"sort columns {list(columns)} must be non-negative")
-        widths.append(max(int(v.max()).bit_length() if len(v) else 1, 1))
+    cols = []
+    for c in columns:
+        v = df[c].to_numpy()
+        if v.dtype.kind == "b":
+            v = v.astype(np.uint8)
+        if v.dtype.kind not in "iu" or (len(v) and int(v.min()) < 0):
+            v = _dense_codes(v)
+        cols.append(v)
+    widths = [max(int(v.max()).bit_length() if len(v) else 1, 1) for v in cols]
     if sum(widths) > 63:
-        raise NotImplementedError(f"sort columns {list(columns)} need {sum(widths)} key bits, 63 are available")
+        cols = [_dense_codes(v) for v in cols]
+        widths = [max(int(v.max()).bit_length() if len(v) else 1, 1) for v in cols]
+    if sum(widths) > 63:  # rank of the row's key tuple among the distinct tuples
+        order = np.lexsort(tuple(reversed(cols)))
+        stacked = np.stack([v[order] for v in cols], axis=1)
+        new_group = np.ones(len(order), dtype=bool)
+        new_group[1:] = (stacked[1:] != stacked[:-1]).any(axis=1)
+        key = np.empty(len(order), dtype=np.uint64)
+        key[order] = (np.cumsum(new_group) - 1).astype(np.uint64)
+        return key
     key = np.zeros(len(df), dtype=np.uint64)
     for v, w in zip(cols, widths):
         key = (key << np.uint64(w)) | v.astype(np.uint64)

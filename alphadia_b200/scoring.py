@@ -505,6 +505,8 @@ class CandidateScoring:
             precursor_df_columns = DEFAULT_PRECURSOR_COLUMNS.copy()
         if hasattr(psm, "to_precursor_df"):  # an OutputPsmDF-like object (output.py:92-97), as the reference passes
             precursor_idx, rank, features = psm.to_precursor_df()
+        elif psm.get("ragged"):  # adb_score_candidates_ragged: the valid rows only, already compacted
+            precursor_idx, rank, features = psm["precursor_idx"], psm["rank"], psm["features"]
         else:  # the arrays adb_score_candidates filled
             valid = psm["valid"].astype(bool)
             if valid.all():
@@ -548,10 +550,22 @@ class CandidateScoring:
         are expanded with per-candidate slot counts, and ``elution_group_idx`` / ``decoy`` are looked up once per
         candidate instead of once per fragment row."""
         lib_mz = psm["fragment_mz_library"]
-        n, top_k = lib_mz.shape
-        mask = lib_mz.reshape(-1) > 0
-        n_rows = int(np.count_nonzero(mask))
-        if n_rows == mask.size:  # every slot filled: the flat arrays are the columns
+        if psm.get("ragged"):  # already flattened on the device: slot arrays are the columns, one count per valid candidate
+            counts = psm["fragment_counts"]
+            n, n_rows, top_k, mask = len(counts), int(lib_mz.shape[0]), 0, None
+
+            def slots(a):
+                return a
+
+            def per_candidate(a):
+                return np.repeat(a, counts)
+        else:
+            n, top_k = lib_mz.shape
+            mask = lib_mz.reshape(-1) > 0
+            n_rows = int(np.count_nonzero(mask))
+        if mask is None:
+            pass
+        elif n_rows == mask.size:  # every slot filled: the flat arrays are the columns
             def slots(a):
                 return a.reshape(-1)
 
@@ -608,22 +622,25 @@ class CandidateScoring:
         cfg_struct = self.config.to_struct(quad_sigma=quad.sigma, quad_delta_mu=quad.delta_mu)
         dev_raw = _lib.device_rawfile_for(self._dia_data, self._raw)
         dev_lib = _lib.DeviceLibrary(lib_arrays, device=dev_raw.device)
+        max_frag = 1
+        if len(lib_arrays["frag_start_idx"]):
+            max_frag = max(1, int(np.max(lib_arrays["frag_stop_idx"].astype(np.int64) - lib_arrays["frag_start_idx"].astype(np.int64))))
         try:
-            dev_out = _lib.score_candidates(dev_raw, dev_lib, cfg_struct, cin)
+            # ragged result: the feature rows of the valid candidates and their fragment slots with mz_library > 0, compacted
+            # on the device = exactly what OutputPsmDF.to_precursor_df / to_fragment_df hand to the collectors below
+            # (output.py:72-97).  top_k_fragments is not capped: 9999 (transfer-library requantification) keeps every fragment.
+            dev_out = _lib.score_candidates_ragged(dev_raw, dev_lib, cfg_struct, cin, max_fragments=max_frag)
         finally:
             dev_lib.close()
         self.last_timing = dev_raw.last_timing()
 
-        # scatter back to the OutputPsmDF layout over ALL candidates (skipped rows stay zero / invalid)
-        top_k = int(self.config.top_k_fragments)
-        if len(sel) == n_total:
-            psm = dev_out
-        else:
-            _, psm = _abi.alloc_scores_out(n_total, top_k)
-            for k, v in dev_out.items():
-                psm[k][sel] = v
-        psm["precursor_idx"] = sorted_df["precursor_idx"].values.astype(np.uint32)
-        psm["rank"] = sorted_df["rank"].values.astype(np.uint8)
+        rows = sel[dev_out["row_index"]] if len(sel) != n_total else dev_out["row_index"]
+        psm = {k: dev_out[k] for k in dev_out if k.startswith("fragment_")}
+        psm["ragged"] = True
+        psm["features"] = dev_out["features"]
+        psm["fragment_counts"] = np.diff(dev_out["frag_offset"])
+        psm["precursor_idx"] = sorted_df["precursor_idx"].values.astype(np.uint32)[rows]
+        psm["rank"] = sorted_df["rank"].values.astype(np.uint8)[rows]
 
         logger.info("Finished candidate processing")
         logger.info("Collecting candidate features")

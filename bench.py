@@ -346,7 +346,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("ADB_BENCH_WORKLOAD", "config3"))
     ap.add_argument("--precursors", type=int, default=None, help="override the library size (debugging)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-dense", action="store_true", help="e2e with the dense [n, top_k] result tables of adb_score_candidates (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check of the timed results")
     ap.add_argument("--parity-precursors", type=int, default=800)
@@ -444,10 +445,10 @@ def main():
 
     # ---- e2e through the C ABI with pinned host buffers ------------------------------------------
     alloc = pinned_alloc_factory()
-    hp.host_step(alloc)  # warm-up: allocates the pinned buffers
+    hp.host_step(alloc, ragged=not args.e2e_dense)  # warm-up: allocates the pinned buffers
     barrier()
     t0 = time.perf_counter()
-    e2e_stats = [hp.host_step(alloc) for _ in range(args.e2e_steps)]
+    e2e_stats = [hp.host_step(alloc, ragged=not args.e2e_dense) for _ in range(args.e2e_steps)]
     barrier()
     t_e2e = time.perf_counter() - t0
     t_e = torch.tensor([t_e2e, float(e2e_stats[-1]["n_candidates"])], dtype=torch.float64, device="cuda")
@@ -527,7 +528,13 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_stats[-1]["h2d_bytes"],
                     "d2h_bytes_per_step": e2e_stats[-1]["d2h_bytes"], "steps": args.e2e_steps,
-                    "path": "adb_library_create (H2D) + adb_select_candidates_resident + adb_fetch_candidate_table (D2H) + adb_score_candidates (candidate table H2D, score/fragment tables D2H in 4 row blocks overlapped with the kernel), pinned host buffers"},
+                    "valid_rows": e2e_stats[-1]["valid"], "fragment_rows": e2e_stats[-1]["n_fragments"],
+                    "path": ("adb_library_create (H2D) + adb_select_candidates_resident + adb_fetch_candidate_table (D2H) + "
+                             + ("adb_score_candidates (candidate table H2D, dense score/fragment tables D2H in 4 row blocks overlapped with the kernel)"
+                                if args.e2e_dense else
+                                "adb_score_candidates_ragged (candidate table H2D; feature rows of the valid candidates + their kept fragment slots, "
+                                "compacted on the device per row block and copied while the next block is scored)")
+                             + ", pinned host buffers")},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }

@@ -195,6 +195,37 @@ typedef struct {
   uint8_t* fragment_loss_type;
 } adb_scores_out;
 
+/* Ragged result of candidate scoring: exactly the rows OutputPsmDF.to_precursor_df / to_fragment_df keep
+ * (alphadia/search/scoring/output.py:72-97, consumed by collect_candidates / collect_fragments,
+ * alphadia/search/scoring/scoring.py:394-580): the feature rows of the valid candidates, in candidate order, and - flattened
+ * in the same order - their fragment slots with mz_library > 0.  Only these bytes cross the bus (the dense [n, top_k]
+ * tables are mostly empty slots), and top_k_fragments is not capped by ADB_MAX_FRAGMENTS here: the transfer-library
+ * requantification calls with top_k_fragments = 9999
+ * (alphadia/workflow/peptidecentric/transfer_library_requantification_handler.py:102-124); a candidate keeps at most
+ * the fragments its precursor has.  All buffers are caller-owned host memory (pinned memory makes the copies overlap the
+ * scoring kernels). */
+typedef struct {
+  int64_t row_capacity;  /* in: rows the row-wise buffers hold; adb_candidates_in.n always suffices */
+  int64_t frag_capacity; /* in: entries the fragment buffers hold; n * min(top_k_fragments, widest precursor) always suffices */
+  int64_t n_rows;        /* out: valid candidates */
+  int64_t n_fragments;   /* out: fragment entries */
+  int64_t* row_index;    /* [row_capacity] row of the candidate in adb_candidates_in */
+  float* features;       /* [row_capacity, 46] */
+  int64_t* frag_offset;  /* [row_capacity + 1] fragments of valid row r: [frag_offset[r], frag_offset[r + 1]) */
+  float* fragment_mz_library; /* [frag_capacity] each */
+  float* fragment_mz;
+  float* fragment_mz_observed;
+  float* fragment_height;
+  float* fragment_intensity;
+  float* fragment_mass_error;
+  float* fragment_correlation;
+  uint8_t* fragment_position;
+  uint8_t* fragment_number;
+  uint8_t* fragment_type;
+  uint8_t* fragment_charge;
+  uint8_t* fragment_loss_type;
+} adb_scores_ragged;
+
 /* ---- entry points ------------------------------------------------------------------------- */
 const char* adb_last_error(void);
 const char* adb_version(void);
@@ -217,6 +248,11 @@ int adb_select_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_sele
 
 int adb_score_candidates(adb_rawfile_t* raw, adb_library_t* lib, const adb_scoring_config* cfg,
                          const adb_candidates_in* cand, adb_scores_out* out);
+
+/* same scoring, ragged result (see adb_scores_ragged); fails with the needed sizes in n_rows / n_fragments when a
+ * capacity is too small */
+int adb_score_candidates_ragged(adb_rawfile_t* raw, adb_library_t* lib, const adb_scoring_config* cfg,
+                                const adb_candidates_in* cand, adb_scores_ragged* out);
 
 /* dtype flags (the reference computes in the array dtypes): is_f64 bit 0 = rt is f64 (else f32),
  * bit 1 = fragment_mz is f64 (else f32).

@@ -521,6 +521,42 @@ def run_transpose():
     print(f"[transpose] wrote {path} ({os.path.getsize(path) / 1e3:.1f} kB)", flush=True)
 
 
+def run_k9999(threads: int):
+    """Transfer-library requantification scoring (transfer_library_requantification_handler.py:102-124): every library
+    fragment is quantified, top_k_fragments = 9999, on the 20-fragment library of parity_f20 and the candidates the
+    reference selected there (tests/golden/parity_f20.npz) -> tests/golden/k9999.npz."""
+    import pandas as pd
+
+    name = "parity_f20"
+    raw, precursor_df, fragment_df, p = make_config_3d(name)
+    dia = refshim.RefDiaData(raw)
+    g = np.load(os.path.join(HERE, f"{name}.npz"), allow_pickle=False)
+    assert str(g["input_checksum"]) == input_checksum(raw, precursor_df, fragment_df)
+    cand = pd.DataFrame({k[len("cand_"):]: g[k] for k in g.files if k.startswith("cand_")})
+    sc_mod = refshim.ref("alphadia.search.scoring.scoring")
+    sccfg_mod = refshim.ref("alphadia.search.scoring.config")
+    sc_cfg = sccfg_mod.CandidateScoringConfig()
+    sc_cfg.update({**SCORING_BASE, "precursor_mz_tolerance": 5, "fragment_mz_tolerance": 10, "top_k_fragments": 9999})
+    scorer = sc_mod.CandidateScoring(
+        dia_data=dia, precursors_flat=precursor_df.copy(), fragments_flat=fragment_df.copy(),
+        config=sc_cfg, rt_column="rt_library", mobility_column="mobility_library",
+        precursor_mz_column="mz_library", fragment_mz_column="mz_library",
+    )
+    t0 = time.perf_counter()
+    feat, frag = scorer(cand.copy(), thread_count=threads, include_decoy_fragment_features=True)
+    print(f"[k9999] scoring: {time.perf_counter() - t0:.1f}s -> {len(feat)} rows, {len(frag)} fragment rows", flush=True)
+    out = {"input_checksum": g["input_checksum"]}
+    fcols = sc_mod.DEFAULT_FEATURE_COLUMNS
+    out["feat_matrix"] = feat[fcols].values.astype(np.float32)
+    out["feat_precursor_idx"] = feat["precursor_idx"].values
+    out["feat_rank"] = feat["rank"].values
+    for c in frag.columns:
+        out[f"frag_{c}"] = frag[c].values
+    path = os.path.join(HERE, "k9999.npz")
+    np.savez_compressed(path, **out)
+    print(f"[k9999] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 if __name__ == "__main__":
     names = sys.argv[1:] or ["config1", "parity_small"]
     threads = int(os.environ.get("ADB_THREADS", os.cpu_count() or 1))
@@ -545,5 +581,7 @@ if __name__ == "__main__":
             run_variants2(threads)
         elif n == "iso2":
             run_iso2(threads)
+        elif n == "k9999":
+            run_k9999(threads)
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap", "parity_f20", "parity_4d_f20")))

@@ -131,6 +131,33 @@ def candidates_in_from_arrays(lib, cand: dict):
     return d, keep
 
 
+def ragged_from_dense(dense: dict) -> dict:
+    """The result dict of ``_lib.score_candidates_ragged`` from dense ``[n, top_k]`` score tables (test stubs: the oracle only
+    produces dense tables): rows with ``valid``, slots with ``mz_library > 0`` (output.py:72-97)."""
+    v = dense["valid"].astype(bool)
+    m = (dense["fragment_mz_library"] > 0) & v[:, None]
+    out = dict(n_rows=int(v.sum()), n_fragments=int(m.sum()), row_index=np.nonzero(v)[0].astype(np.int64),
+               features=dense["features"][v], frag_offset=np.concatenate([[0], np.cumsum(m.sum(axis=1)[v])]).astype(np.int64))
+    for k in dense:
+        if k.startswith("fragment_"):
+            out[k] = dense[k][m]
+    return out
+
+
+def ragged_scoring_stub(score):
+    """``_lib.score_candidates_ragged`` replacement for CPU tests: ``score(raw_arrays, lib_arrays, cfg, cin)`` is an oracle
+    scoring function; top_k_fragments is capped at the library's widest precursor (a candidate cannot keep more)."""
+    import copy
+
+    def stub(dev_raw, dev_lib, cfg, cin, bufs=None, max_fragments=None):
+        cfg2 = copy.copy(cfg)
+        if max_fragments is not None:
+            cfg2.top_k_fragments = max(1, min(int(cfg.top_k_fragments), int(max_fragments)))
+        return ragged_from_dense(score(dev_raw.arrays, dev_lib.arrays, cfg2, cin))
+
+    return stub
+
+
 def rel_err(a, b, floor=1e-6):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
@@ -359,3 +386,4 @@ def patch_device_with_oracle(monkeypatch, oracle_lib, is4d: bool = False):
     monkeypatch.setattr(_lib, "select_candidates_resident", select_resident)
     monkeypatch.setattr(_lib, "fetch_candidate_table", fetch_table)
     monkeypatch.setattr(_lib, "score_candidates", lambda dev_raw, dev_lib, cfg, cin: score(dev_raw.arrays, dev_lib.arrays, cfg, cin))
+    monkeypatch.setattr(_lib, "score_candidates_ragged", ragged_scoring_stub(score))

@@ -1019,3 +1019,96 @@ def test_extra_two_isotope_library(engine, oracle_lib):
     scfg = H.scoring_config().to_struct()
     assert_scores_close(engine.score_candidates(draw, dlib, scfg, cin), oracle_lib.score_candidates(raw, lib, scfg, cin), what="iso2")
     dlib.close(); draw.close()
+
+
+def _assert_ragged_equals_dense(rag, dense, K):
+    """adb_score_candidates_ragged == the rows / slots OutputPsmDF.to_precursor_df / to_fragment_df keep of the dense tables."""
+    v = dense["valid"].astype(bool)
+    assert rag["n_rows"] == int(v.sum())
+    assert np.array_equal(rag["row_index"], np.nonzero(v)[0])
+    assert np.array_equal(rag["features"], dense["features"][v], equal_nan=True)
+    m = (dense["fragment_mz_library"] > 0) & v[:, None]
+    assert rag["n_fragments"] == int(m.sum())
+    counts = m.sum(axis=1)[v]
+    assert np.array_equal(rag["frag_offset"], np.concatenate([[0], np.cumsum(counts)]))
+    for k in FRAG_F32 + FRAG_U8:
+        assert np.array_equal(rag[k], dense[k][m], equal_nan=True), k
+
+
+@pytest.mark.parametrize("name", ["parity_small", "parity_4d", "parity_f20"])
+def test_ragged_scores_equal_dense_tables(engine, oracle_lib, name):
+    raw, lib, p, draw, dlib = _device_objects(engine, name)
+    is4d = draw.is_4d
+    cfg = _sel_cfg_4d(p) if is4d else H.selection_config(p["rt_tolerance"]).to_struct()
+    sel = engine.select_candidates(draw, dlib, cfg, H.default_kernel(raw))
+    m = sel["score"] > 0
+    cin, keep = H.candidates_in_from_arrays(lib, {c: sel[c][m] for c in INT_COLS})
+    for variant in ("default", "k6"):
+        scfg = H.scoring_config(**SCORING_VARIANTS[variant]).to_struct()
+        dense = engine.score_candidates(draw, dlib, scfg, cin)
+        rag = engine.score_candidates_ragged(draw, dlib, scfg, cin)
+        assert 0 < rag["n_rows"] < int(cin.n)
+        _assert_ragged_equals_dense(rag, dense, int(scfg.top_k_fragments))
+    # capacity too small: loud failure that names the needed sizes
+    from alphadia_b200 import _abi
+    rd, bufs = _abi.alloc_scores_ragged(int(cin.n), 8)
+    with pytest.raises(RuntimeError, match="capacity"):
+        engine.score_candidates_ragged(draw, dlib, scfg, cin, bufs=bufs)
+    dlib.close(); draw.close()
+
+
+def test_ragged_scores_chunked(engine):
+    """>= 200k candidates: row blocks are compacted and copied while the next block is scored; same result as the dense call."""
+    raw, lib, p, draw, dlib = _device_objects(engine, "parity_small")
+    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    n = engine.select_candidates_resident(draw, dlib, cfg, H.default_kernel(raw))
+    table = engine.fetch_candidate_table(draw, n)
+    reps = 200000 // n + 1
+    big = {k: np.ascontiguousarray(np.tile(v[:n], reps)) for k, v in table.items()}
+    from alphadia_b200 import _abi
+    N = n * reps
+    scfg = H.scoring_config().to_struct()
+    cin = _abi.candidates_in_from_table(big, N)
+    dense = engine.score_candidates(draw, dlib, scfg, cin)
+    rag = engine.score_candidates_ragged(draw, dlib, scfg, cin)
+    _assert_ragged_equals_dense(rag, dense, int(scfg.top_k_fragments))
+    dlib.close(); draw.close()
+
+
+def test_top_k_fragments_9999_transfer_requantification(engine, oracle_lib):
+    """top_k_fragments = 9999 (transfer_library_requantification_handler.py:102-124): every library fragment is quantified.
+    Ragged device result vs the oracle's dense tables at the library's width (20) and vs the live reference's tables."""
+    name = "parity_f20"
+    raw, lib, p, draw, dlib = _device_objects(engine, name)
+    g = H.load_golden(name)
+    cin, keep = H.candidates_in_from_arrays(lib, {c: g["cand_" + c] for c in INT_COLS})
+    wide = int(np.max(lib["frag_stop_idx"] - lib["frag_start_idx"]))
+    assert wide == 20
+    ref = oracle_lib.score_candidates(raw, lib, H.scoring_config(top_k_fragments=wide).to_struct(), cin)
+    rag = engine.score_candidates_ragged(draw, dlib, H.scoring_config(top_k_fragments=9999).to_struct(), cin, max_fragments=wide)
+    v = ref["valid"].astype(bool)
+    assert np.array_equal(rag["row_index"], np.nonzero(v)[0])
+    F, G = rag["features"], ref["features"][v]
+    floor = feature_scale_floor(G)
+    err = np.abs(F - G) / np.maximum(np.maximum(np.abs(F), np.abs(G)), floor[None, :])
+    assert np.where(np.isnan(F) & np.isnan(G), 0.0, err).max() < RTOL
+    m = (ref["fragment_mz_library"] > 0) & v[:, None]
+    assert rag["n_fragments"] == int(m.sum()) and m.sum(axis=1).max() > 12
+    for k in FRAG_U8:
+        assert np.array_equal(rag[k], ref[k][m]), k
+    for k in FRAG_F32:
+        assert H.rel_err(rag[k], ref[k][m]).max() < RTOL, k
+    g9 = H.load_golden("k9999")
+    if g9 is not None and str(g9["input_checksum"]) == str(g["input_checksum"]):
+        assert np.array_equal(keep["precursor_idx"][rag["row_index"]], g9["feat_precursor_idx"])
+        assert np.array_equal(keep["rank"][rag["row_index"]], g9["feat_rank"])
+        G = g9["feat_matrix"]
+        err = np.abs(F - G) / np.maximum(np.maximum(np.abs(F), np.abs(G)), feature_scale_floor(G)[None, :])
+        assert np.where(np.isnan(F) & np.isnan(G), 0.0, err).max() < RTOL
+        assert np.array_equal(rag["fragment_mz_library"], g9["frag_mz_library"])
+        assert np.array_equal(rag["fragment_number"], g9["frag_number"])
+        assert H.rel_err(rag["fragment_intensity"], g9["frag_intensity"]).max() < RTOL
+    # the dense tables cannot hold 9999 slots per candidate: loud refusal
+    with pytest.raises(RuntimeError, match="ragged"):
+        engine.score_candidates(draw, dlib, H.scoring_config(top_k_fragments=64).to_struct(), cin)
+    dlib.close(); draw.close()

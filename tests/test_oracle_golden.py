@@ -81,6 +81,36 @@ def test_scoring_vs_reference(name, tag, oracle_lib):
             assert np.array_equal(a, b), k
 
 
+def test_scoring_top_k_9999_vs_reference(oracle_lib):
+    """Transfer-library requantification (transfer_library_requantification_handler.py:102-124, top_k_fragments = 9999): the
+    live reference quantifies every library fragment (20 per precursor here).  A candidate keeps at most the fragments its
+    precursor has, so the oracle at the library's width must reproduce the reference's tables (tests/golden/k9999.npz)."""
+    g, raw, lib, p = _golden("parity_f20")
+    g9 = H.load_golden("k9999")
+    assert g9 is not None and str(g9["input_checksum"]) == str(g["input_checksum"])
+    cin, keep = H.candidates_in_from_arrays(lib, {c: g["cand_" + c] for c in INT_COLS})
+    wide = int(np.max(lib["frag_stop_idx"] - lib["frag_start_idx"]))
+    arrs = oracle_lib.score_candidates(raw, lib, H.scoring_config(top_k_fragments=wide).to_struct(), cin)
+    v = arrs["valid"].astype(bool)
+    assert np.array_equal(keep["precursor_idx"][v], g9["feat_precursor_idx"])
+    assert np.array_equal(keep["rank"][v], g9["feat_rank"])
+    F, G = arrs["features"][v], g9["feat_matrix"]
+    for j in range(46):
+        same = (F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))
+        if j in BLAS_FEATURES:
+            assert H.rel_err(F[:, j], G[:, j]).max() < 1e-4, j
+        else:
+            assert same.all(), f"feature {j} not bit-exact"
+    m = arrs["fragment_mz_library"] > 0
+    assert m.sum() == len(g9["frag_mz_library"]) and m.sum(axis=1).max() == wide
+    for k, v2 in FRAG_MAP.items():
+        a, b = arrs[v2][m], g9[f"frag_{k}"]
+        if k == "correlation":
+            assert H.rel_err(a, b).max() < 1e-4
+        else:
+            assert np.array_equal(a, b), k
+
+
 @pytest.mark.parametrize("name", ["config1", "parity_small", "parity_f20"])
 def test_fragcomp_vs_reference(name, oracle_lib):
     """FragmentCompetition on the golden feature table with the golden pseudo-proba."""
@@ -286,8 +316,7 @@ def test_multiplexed_scoring_vs_reference(tag, cfg_kw, oracle_lib, monkeypatch):
 
     monkeypatch.setattr(_lib, "device_rawfile_for", lambda dia_data, adapted: HostRaw(adapted))
     monkeypatch.setattr(_lib, "DeviceLibrary", HostLibrary)
-    monkeypatch.setattr(_lib, "score_candidates",
-                        lambda dev_raw, dev_lib, cfg, cin: oracle_lib.score_candidates(dev_raw.arrays, dev_lib.arrays, cfg, cin))
+    monkeypatch.setattr(_lib, "score_candidates_ragged", H.ragged_scoring_stub(oracle_lib.score_candidates))
     scorer = CandidateScoring(dia_data=raw, precursors_flat=mpdf.copy(), fragments_flat=fdf.copy(), config=H.scoring_config(**cfg_kw),
                               rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
                               fragment_mz_column="mz_library")
@@ -596,7 +625,7 @@ def test_candidate_scoring_tables_vs_reference(name, tag, oracle_lib, monkeypatc
 
     monkeypatch.setattr(_lib, "device_rawfile_for", lambda dia_data, adapted: HostRaw(adapted))
     monkeypatch.setattr(_lib, "DeviceLibrary", HostLibrary)
-    monkeypatch.setattr(_lib, "score_candidates", lambda dev_raw, dev_lib, cfg, cin: score(dev_raw.arrays, dev_lib.arrays, cfg, cin))
+    monkeypatch.setattr(_lib, "score_candidates_ragged", H.ragged_scoring_stub(score))
     cand_df = pd.DataFrame({c: g["cand_" + c] for c in INT_COLS + ["score", "elution_group_idx", "decoy"]})
     scorer = CandidateScoring(dia_data=raw, precursors_flat=pdf.copy(), fragments_flat=fdf.copy(), config=H.scoring_config(**VARIANTS[tag]),
                               rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
@@ -626,6 +655,62 @@ def test_candidate_scoring_tables_vs_reference(name, tag, oracle_lib, monkeypatc
             assert H.rel_err(frag[c].values, g[f"frag{tag}_{c}"]).max() < 1e-4
         else:
             assert np.array_equal(frag[c].values, g[f"frag{tag}_{c}"]), c
+
+
+def test_candidate_scoring_top_k_9999_tables_vs_reference(oracle_lib, monkeypatch):
+    """CandidateScoring with top_k_fragments = 9999, the configuration quantify_candidates uses for the transfer library
+    (extraction_handler.py:488-508, transfer_library_requantification_handler.py:102-124): the fragment table holds every
+    library fragment of every valid candidate, equal to the live reference's table (tests/golden/k9999.npz).  Device call
+    replaced by the oracle in this CPU test; tests/test_gpu_parity.py runs the real one."""
+    import pandas as pd
+
+    from alphadia_b200 import _lib
+    from alphadia_b200.scoring import DEFAULT_FEATURE_COLUMNS, FRAGMENT_COLUMNS, CandidateScoring
+
+    g, raw, lib, p = _golden("parity_f20")
+    g9 = H.load_golden("k9999")
+    assert g9 is not None and str(g9["input_checksum"]) == str(g["input_checksum"])
+    _, pdf, fdf, _, _ = H.workload("parity_f20")
+
+    class HostRaw:
+        device = 0
+
+        def __init__(self, arrays):
+            self.arrays = arrays
+
+        def last_timing(self):
+            return {}
+
+    class HostLibrary:
+        def __init__(self, arrays, device=0):
+            self.arrays = arrays
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(_lib, "device_rawfile_for", lambda dia_data, adapted: HostRaw(adapted))
+    monkeypatch.setattr(_lib, "DeviceLibrary", HostLibrary)
+    monkeypatch.setattr(_lib, "score_candidates_ragged", H.ragged_scoring_stub(oracle_lib.score_candidates))
+    cand_df = pd.DataFrame({c: g["cand_" + c] for c in INT_COLS + ["score", "elution_group_idx", "decoy"]})
+    scorer = CandidateScoring(dia_data=raw, precursors_flat=pdf.copy(), fragments_flat=fdf.copy(),
+                              config=H.scoring_config(top_k_fragments=9999), rt_column="rt_library",
+                              mobility_column="mobility_library", precursor_mz_column="mz_library", fragment_mz_column="mz_library")
+    feat, frag = scorer(cand_df.copy())
+    assert np.array_equal(feat["precursor_idx"].values, g9["feat_precursor_idx"]) and np.array_equal(feat["rank"].values, g9["feat_rank"])
+    F, G = feat[DEFAULT_FEATURE_COLUMNS].values, g9["feat_matrix"]
+    for j in range(46):
+        if j in BLAS_FEATURES:
+            assert H.rel_err(F[:, j], G[:, j]).max() < 1e-4, j
+        else:
+            assert ((F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))).all(), f"feature {j} not bit-exact"
+    assert list(frag.columns) == FRAGMENT_COLUMNS + ["elution_group_idx", "decoy"]
+    assert len(frag) == len(g9["frag_mz_library"]) and frag.groupby(["precursor_idx", "rank"]).size().max() == 20
+    for c in frag.columns:
+        assert frag[c].dtype == g9[f"frag_{c}"].dtype, (c, frag[c].dtype)
+        if c == "correlation":
+            assert H.rel_err(frag[c].values, g9[f"frag_{c}"]).max() < 1e-4
+        else:
+            assert np.array_equal(frag[c].values, g9[f"frag_{c}"]), c
 
 
 # ---- FDR bookkeeping (SURVEY 8f.2): get_q_values / keep_best of the live reference ------------------------
@@ -732,12 +817,19 @@ def test_fdr_key_packing(oracle_lib, monkeypatch):
     with np.errstate(all="ignore"):
         expect = np.flip(np.minimum.accumulate(np.flip(np.cumsum(d) / np.cumsum(1 - d))))
     assert np.array_equal(got["qval"].values, expect)
-    with pytest.raises(NotImplementedError):
-        fdr.get_q_values(df.assign(a=-df["a"]), extra_sort_columns=["a"])
-    with pytest.raises(NotImplementedError):
-        fdr.get_q_values(df, extra_sort_columns=["name"])
-    with pytest.raises(NotImplementedError):
-        fdr.get_q_values(df.assign(a=df["a"].values.astype(np.int64) * 2 ** 30, b=df["b"].values * 2 ** 10), extra_sort_columns=["a", "b"])
+    # tie-break columns of any dtype (the reference sorts by the protein-group string, outputtransform/protein_fdr.py:72),
+    # negative values and keys wider than 63 bits: same rows, order and q-values as the pandas formulation
+    wide = df.assign(a=df["a"].values.astype(np.int64) * 2 ** 30, b=df["b"].values * 2 ** 10, c=df["a"].values.astype(np.int64) * 2 ** 31)
+    huge = df.assign(a=df["a"].values.astype(np.int64) * 2 ** 40 + rng.integers(0, 2 ** 40, n), b=rng.integers(0, 2 ** 62, n), c=rng.integers(0, 2 ** 62, n))
+    for frame, cols in ((df.assign(a=-df["a"]), ["a"]), (df, ["name"]), (df, ["name", "b"]), (df, ["f"]), (wide, ["a", "b", "c"]),
+                        (huge, ["a", "b", "c"])):
+        got = fdr.get_q_values(frame, extra_sort_columns=cols)
+        ref = frame.sort_values(["proba", "_decoy", *cols], kind="stable")
+        assert np.array_equal(got.index.values, ref.index.values), cols
+        d = ref["_decoy"].to_numpy()
+        with np.errstate(all="ignore"):
+            expect = np.flip(np.minimum.accumulate(np.flip(np.cumsum(d) / np.cumsum(1 - d))))
+        assert np.array_equal(got["qval"].values, expect, equal_nan=True), cols
 
 
 @pytest.mark.parametrize("n,levels", [(1, 1), (2, 1), (1000, 7), (50_000, 300), (50_000, 10 ** 9)])
