@@ -1622,8 +1622,13 @@ int adb_fragment_competition(int device, int64_t n_windows, const int64_t* windo
     if (frag_start_idx[i] < 0 || frag_stop_idx[i] > n_frag || frag_start_idx[i] > frag_stop_idx[i]) return fail("fragment range outside the fragment table");
   if (set_device(device)) return 1;
   const size_t es_rt = (is_f64 & 1) ? 8 : 4, es = (is_f64 & 2) ? 8 : 4;
-  DeviceBuffer b_ws, b_we, b_rt, b_fs, b_fe, b_mz, b_valid;
-  auto cleanup = [&]() { b_ws.release(); b_we.release(); b_rt.release(); b_fs.release(); b_fe.release(); b_mz.release(); b_valid.release(); };
+  // grow-only device copies of the arguments, kept per device between calls (the call is a few ms in total)
+  static std::mutex fc_mutex;
+  static DeviceBuffer fc_bufs[64][7];
+  std::lock_guard<std::mutex> fc_lock(fc_mutex);
+  DeviceBuffer* fb = fc_bufs[device & 63];
+  DeviceBuffer &b_ws = fb[0], &b_we = fb[1], &b_rt = fb[2], &b_fs = fb[3], &b_fe = fb[4], &b_mz = fb[5], &b_valid = fb[6];
+  auto cleanup = [&]() {};
   if (b_ws.reserve(8 * (size_t)n_windows) || b_we.reserve(8 * (size_t)n_windows) || b_rt.reserve(es_rt * (size_t)n_psm) ||
       b_fs.reserve(8 * (size_t)n_psm) || b_fe.reserve(8 * (size_t)n_psm) || b_mz.reserve(es * (size_t)std::max<int64_t>(n_frag, 1)) ||
       b_valid.reserve((size_t)n_psm)) { cleanup(); return 1; }
@@ -1634,8 +1639,20 @@ int adb_fragment_competition(int device, int64_t n_windows, const int64_t* windo
   cp(b_mz.ptr, fragment_mz, es * (size_t)n_frag); cp(b_valid.ptr, valid, (size_t)n_psm);
   if (e != cudaSuccess) { cleanup(); return fail(std::string("fragcomp H2D failed: ") + cudaGetErrorString(e)); }
   int launches = 0;
-  adb_launch_fragcomp(n_windows, b_ws.as<int64_t>(), b_we.as<int64_t>(), b_rt.ptr, b_fs.as<int64_t>(), b_fe.as<int64_t>(),
-                      b_mz.ptr, is_f64, rt_tol_seconds, mass_tol_ppm, b_valid.as<uint8_t>(), nullptr, &launches);
+  // conflict graph over the RT-sorted windows; the window-serial kernel only when the pair list would not fit (or for A/B
+  // measurements with ADB_FRAGCOMP_SERIAL=1)
+  const char* serial = getenv("ADB_FRAGCOMP_SERIAL");
+  int rc = 2;
+  if (!(serial && serial[0] == '1')) {
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    rc = adb_run_fragcomp_graph(n_windows, b_ws.as<int64_t>(), b_we.as<int64_t>(), n_psm, b_rt.ptr, b_fs.as<int64_t>(), b_fe.as<int64_t>(),
+                                b_mz.ptr, is_f64, rt_tol_seconds, mass_tol_ppm, b_valid.as<uint8_t>(), free_b / 16, nullptr, &launches);
+    if (rc == 1) { cleanup(); return fail(std::string("fragcomp kernels failed: ") + cudaGetErrorString(cudaGetLastError())); }
+  }
+  if (rc == 2)
+    adb_launch_fragcomp(n_windows, b_ws.as<int64_t>(), b_we.as<int64_t>(), b_rt.ptr, b_fs.as<int64_t>(), b_fe.as<int64_t>(),
+                        b_mz.ptr, is_f64, rt_tol_seconds, mass_tol_ppm, b_valid.as<uint8_t>(), nullptr, &launches);
   e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpy(valid, b_valid.ptr, (size_t)n_psm, cudaMemcpyDeviceToHost);
   cleanup();

@@ -196,6 +196,9 @@ int adb_launch_score_dp(const DevRaw& raw, const DevLib& lib, const adb_scoring_
                         int* n_launches);
 int64_t adb_score_workspace_floats(int top_k, int64_t c_max);
 
+int adb_run_fragcomp_graph(int64_t n_windows, const int64_t* d_ws, const int64_t* d_we, int64_t n_psm, const void* d_rt,
+                           const int64_t* d_fs, const int64_t* d_fe, const void* d_mz, int is_f64, double rt_tol, double ppm_tol,
+                           uint8_t* d_valid, size_t pair_cap, cudaStream_t stream, int* n_launches);
 void adb_launch_fragcomp(int64_t n_windows, const int64_t* d_ws, const int64_t* d_we, const void* d_rt,
                          const int64_t* d_fs, const int64_t* d_fe, const void* d_mz, int is_f64, double rt_tol,
                          double ppm_tol, uint8_t* d_valid, cudaStream_t stream, int* n_launches);

@@ -290,6 +290,66 @@ def cpu_baseline(raw, lib, sel, sc, kernel, target_seconds=15.0):
                 precursors_per_s=size / t_sel, scoring_candidates_per_s=n / t_sc)
 
 
+def fragcomp_workload(n_psm=200_000, n_frag=12, n_windows=75, seed=11):
+    """SURVEY.md's fragment-competition probe shape: 200 000 PSMs x 12 fragments in 75 DIA windows, sorted by
+    (window, proba) as FragmentCompetition.plan leaves them (fragcomp.py:254-273).  A tenth of the PSMs are shadows of a better
+    PSM of the same window: same retention time (+- 2 s) and 4-8 of its fragment m/z (+- 5 ppm), so the veto has work to do."""
+    rng = np.random.default_rng(seed)
+    window = np.sort(rng.integers(0, n_windows, n_psm))
+    proba = rng.random(n_psm)
+    order = np.lexsort((proba, window))
+    window, proba = window[order], proba[order]
+    rt = rng.uniform(0.0, 2400.0, n_psm).astype(np.float32)
+    mz = np.sort(rng.uniform(200.0, 1800.0, (n_psm, n_frag)), axis=1).astype(np.float32)
+    ws = np.searchsorted(window, np.arange(n_windows), side="left").astype(np.int64)
+    we = np.searchsorted(window, np.arange(n_windows), side="right").astype(np.int64)
+    shadows = rng.choice(n_psm, n_psm // 10, replace=False)
+    for i in shadows:
+        w = window[i]
+        if i <= ws[w]:
+            continue
+        j = rng.integers(ws[w], i)  # a better PSM (lower proba) of the same window
+        rt[i] = rt[j] + np.float32(rng.uniform(-2.0, 2.0))
+        k = rng.integers(4, 9)
+        cols = rng.choice(n_frag, k, replace=False)
+        mz[i, cols] = mz[j, cols] * (1.0 + rng.uniform(-5e-6, 5e-6, k)).astype(np.float32)
+    fs = (np.arange(n_psm, dtype=np.int64) * n_frag)
+    return dict(window_start=ws, window_stop=we, rt=rt, frag_start=fs, frag_stop=fs + n_frag, fragment_mz=mz.reshape(-1))
+
+
+def bench_fragcomp(repeats=5):
+    """Fragment competition host-to-host through adb_fragment_competition (H2D + kernels + D2H) next to the C port on all
+    host threads, same arrays; the surviving rows must be identical."""
+    from alphadia_b200 import _lib
+
+    w = fragcomp_workload()
+    args = (w["window_start"], w["window_stop"], w["rt"], w["frag_start"], w["frag_stop"], w["fragment_mz"], 3.0, 15.0)
+    valid = _lib.fragment_competition(*args)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        valid = _lib.fragment_competition(*args)
+    t_gpu = (time.perf_counter() - t0) / repeats
+    os.environ["ADB_FRAGCOMP_SERIAL"] = "1"
+    try:
+        t0 = time.perf_counter()
+        valid_serial = _lib.fragment_competition(*args)
+        t_serial = time.perf_counter() - t0
+    finally:
+        del os.environ["ADB_FRAGCOMP_SERIAL"]
+    import oracle
+
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    ref = oracle.fragment_competition(*args, n_threads=threads).astype(bool)
+    t_cpu = time.perf_counter() - t0
+    n = len(w["rt"])
+    return {"n_psm": n, "fragments_per_psm": 12, "windows": 75, "removed": int(n - valid.sum()),
+            "psm_per_s": n / t_gpu, "ms": 1e3 * t_gpu, "window_serial_kernel_ms": 1e3 * t_serial,
+            "cpu_port_psm_per_s": n / t_cpu, "cpu_cores": threads, "identical_to_cpu_port": bool(np.array_equal(valid, ref)),
+            "identical_to_window_serial_kernel": bool(np.array_equal(valid, valid_serial)),
+            "path": "adb_fragment_competition, host arrays in and out (conflict graph over RT-sorted windows + greedy pass)"}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
@@ -349,6 +409,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-dense", action="store_true", help="e2e with the dense [n, top_k] result tables of adb_score_candidates (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fragcomp", action="store_true", help="skip the fragment-competition side benchmark")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check of the timed results")
     ap.add_argument("--parity-precursors", type=int, default=800)
     args = ap.parse_args()
@@ -544,6 +605,10 @@ def main():
             line["gather_check"] = gather_check
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_fragcomp:
+            fc = bench_fragcomp()
+            log(f"fragment competition: {json.dumps(fc)}")
+            line["fragcomp"] = fc
         print(json.dumps(line), flush=True)
     hp.close()
     if world > 1:
