@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "adb_rawfile3d_create", "adb_rawfile4d_create", "adb_rawfile_destroy", "adb_rawfile_device_bytes", "adb_rawfile_stream",
     "adb_library_create", "adb_library_destroy",
     "adb_select_candidates", "adb_score_candidates", "adb_score_candidates_ragged", "adb_fragment_competition", "adb_transpose_csr",
-    "adb_q_values", "adb_keep_best",
+    "adb_q_values", "adb_keep_best", "adb_classifier_predict_proba",
     "adb_select_candidates_resident", "adb_score_candidates_resident",
     "adb_fetch_candidates", "adb_fetch_candidate_table", "adb_fetch_scores", "adb_resident_score_table",
     "adb_last_timing", "adb_kernel_launches", "adb_last_main_kernel_ms",

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.environ.get("ADB_LIB_PATH") or os.path.join(HERE, "libalphadia_b200.so")
-SOURCES = ["adb_api.cu", "adb_select.cu", "adb_score.cu", "adb_score_dp.cu", "adb_misc.cu", "adb_select4d.cu", "adb_score4d.cu"]
+SOURCES = ["adb_api.cu", "adb_select.cu", "adb_score.cu", "adb_score_dp.cu", "adb_misc.cu", "adb_select4d.cu", "adb_score4d.cu", "adb_classifier.cu"]
 # per-file flags: the data-parallel scoring passes are written in plain arithmetic and must not be FMA-contracted
 EXTRA_FLAGS = {"adb_score_dp.cu": ["--fmad=false"]}
 HEADERS = [os.path.join(CSRC, "adb_common.cuh"), os.path.join(CSRC, "adb_score_dp.cuh"), os.path.join(os.path.dirname(HERE), "include", "alphadia_b200.h")]

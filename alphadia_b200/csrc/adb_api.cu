@@ -33,6 +33,10 @@ int fail(const std::string& msg) {
   return 1;
 }
 
+}  // namespace
+int adb_set_error(const std::string& msg) { return fail(msg); }  // for the other translation units of the library
+namespace {
+
 #define CUDA_TRY(expr)                                                                        \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \

@@ -290,6 +290,46 @@ def cpu_baseline(raw, lib, sel, sc, kernel, target_seconds=15.0):
                 precursors_per_s=size / t_sel, scoring_candidates_per_s=n / t_sc)
 
 
+def bench_operator(raw, pdf, fdf, sel_cfg, sc_cfg, steps=2):
+    """The reference-facing operator path (what ClassicExtractionHandler runs, extraction_handler.py:411-486): DataFrames in,
+    DataFrames out - CandidateSelection(...)() -> CandidateScoring(...)(candidates_df), constructors included, on the same
+    workload.  Host pandas / numpy glue, schema validation, library marshalling and every copy are inside the timed region."""
+    from alphadia_b200 import CandidateScoring, CandidateSelection
+
+    pdf = pdf.copy()
+    if "sequence" not in pdf.columns:  # string columns of a real library (a pool of distinct peptides; cheap to generate)
+        rng = np.random.default_rng(5)
+        aa = np.array(list("ACDEFGHIKLMNPQRSTVWY"))
+        pool = np.array(["".join(r) for r in aa[rng.integers(0, 20, size=(4096, 9))]], dtype=object)
+        pdf["sequence"] = pool[rng.integers(0, 4096, size=len(pdf))]
+        for col in ("mods", "mod_sites"):
+            pdf[col] = np.full(len(pdf), "", dtype=object)
+    cols = dict(rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+                fragment_mz_column="mz_library")
+    phases = []
+    n_cand = n_feat = n_frag = 0
+    for step in range(steps + 1):  # step 0 is the warm-up (second device copy of the raw file, first allocations)
+        t0 = time.perf_counter()
+        selector = CandidateSelection(raw, pdf, fdf, sel_cfg, fwhm_rt=5.0, fwhm_mobility=0.01, **cols)
+        t1 = time.perf_counter()
+        cand_df = selector(thread_count=1)
+        t2 = time.perf_counter()
+        scorer = CandidateScoring(dia_data=raw, precursors_flat=pdf, fragments_flat=fdf, config=sc_cfg, **cols)
+        t3 = time.perf_counter()
+        feat_df, frag_df = scorer(cand_df, thread_count=1)
+        t4 = time.perf_counter()
+        n_cand, n_feat, n_frag = len(cand_df), len(feat_df), len(frag_df)
+        if step:
+            phases.append({"selection_ctor": 1e3 * (t1 - t0), "selection_call": 1e3 * (t2 - t1), "scoring_ctor": 1e3 * (t3 - t2),
+                           "scoring_call": 1e3 * (t4 - t3), "total": 1e3 * (t4 - t0)})
+        del selector, scorer, cand_df, feat_df, frag_df
+    total_s = sum(p["total"] for p in phases) / 1e3 / len(phases)
+    return {"value": n_cand / total_s, "unit": UNIT, "steps": steps, "candidates": n_cand, "feature_rows": n_feat,
+            "fragment_rows": n_frag, "ms_per_step": 1e3 * total_s,
+            "phases_ms": {k: float(np.mean([p[k] for p in phases])) for k in phases[0]},
+            "path": "CandidateSelection(...)(): candidates DataFrame -> CandidateScoring(...)(candidates_df): feature + fragment DataFrames"}
+
+
 def fragcomp_workload(n_psm=200_000, n_frag=12, n_windows=75, seed=11):
     """SURVEY.md's fragment-competition probe shape: 200 000 PSMs x 12 fragments in 75 DIA windows, sorted by
     (window, proba) as FragmentCompetition.plan leaves them (fragcomp.py:254-273).  A tenth of the PSMs are shadows of a better
@@ -409,6 +449,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-dense", action="store_true", help="e2e with the dense [n, top_k] result tables of adb_score_candidates (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-operator", action="store_true", help="skip the DataFrame-level operator measurement")
+    ap.add_argument("--operator-steps", type=int, default=2)
     ap.add_argument("--no-fragcomp", action="store_true", help="skip the fragment-competition side benchmark")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check of the timed results")
     ap.add_argument("--parity-precursors", type=int, default=800)
@@ -605,6 +647,10 @@ def main():
             line["gather_check"] = gather_check
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_operator:
+            op = bench_operator(raw, pdf, fdf, sel, sc, steps=args.operator_steps)
+            log(f"operator path: {json.dumps(op)}")
+            line["e2e_operator"] = op
         if world == 1 and not args.no_fragcomp:
             fc = bench_fragcomp()
             log(f"fragment competition: {json.dumps(fc)}")

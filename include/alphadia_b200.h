@@ -285,6 +285,24 @@ int adb_q_values(int device, int64_t n, const double* score, const uint8_t* deco
  * (df[keep].reset_index(drop=True) is the reference's result). */
 int adb_keep_best(int device, int64_t n, const double* score, const uint64_t* group_key, uint8_t* keep_out);
 
+/* FDR classifier inference: BinaryClassifierLegacyNewBatching.predict_proba (alphadia/fdr/classifiers.py:441-470)
+ * = FeedForwardNN.forward in eval mode (classifiers.py:473-532): BatchNorm1d(running statistics) -> [Linear -> ReLU] per hidden
+ * layer -> Linear -> softmax, float32.  Weights in torch's layout (Linear.weight is [out, in]); x is [n, input_dim] and
+ * proba_out [n, layer_dims[n_layers - 1]], both host memory. */
+typedef struct {
+  int32_t input_dim;
+  int32_t n_layers;             /* linear layers, the output layer included (<= 8, widths <= 128) */
+  const int32_t* layer_dims;    /* [n_layers] output width of each linear layer */
+  const float* bn_weight;       /* [input_dim], NULL = 1 */
+  const float* bn_bias;         /* [input_dim], NULL = 0 */
+  const float* bn_mean;         /* running_mean */
+  const float* bn_var;          /* running_var */
+  float bn_eps;
+  const float* const* weights;  /* [n_layers] pointers, each [out, in] row-major */
+  const float* const* biases;   /* [n_layers] pointers, each [out] */
+} adb_classifier_desc;
+int adb_classifier_predict_proba(int device, const adb_classifier_desc* net, int64_t n, const float* x, float* proba_out);
+
 /* ---- resident variants (bench.py `value`, the sharded driver) -------------------------------
  * Same kernels; the raw file and library are already in HBM, results stay in HBM inside the raw
  * handle's workspace until fetched.  (Not needed by a reference-side binding.) */

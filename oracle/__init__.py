@@ -199,3 +199,22 @@ def fdr_to_q_values(fdr_values):
     L.adbo_fdr_to_q_values.restype = None
     L.adbo_fdr_to_q_values(_abi.ptr(f), C.c_int64(len(f)), _abi.ptr(q))
     return q
+
+
+def classifier_predict_proba(network_state: dict, x: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """TEST ORACLE: FeedForwardNN.forward in eval mode (alphadia/fdr/classifiers.py:473-532) restated in numpy float32:
+    BatchNorm1d with running statistics (module 0), [Linear, ReLU, Dropout = identity] per hidden layer (modules 1, 4, 7, ...),
+    Linear, softmax over axis 1.  Pinned against the live reference's predict_proba in tests/golden/classifier_small.npz."""
+    f32 = np.float32
+    g = {k: np.asarray(v) for k, v in network_state.items()}
+    a = np.asarray(x, dtype=f32)
+    a = (a - g["fc_layers.0.running_mean"].astype(f32)) / np.sqrt(g["fc_layers.0.running_var"].astype(f32) + f32(eps))
+    a = a * g["fc_layers.0.weight"].astype(f32) + g["fc_layers.0.bias"].astype(f32)
+    idx = sorted(int(k.split(".")[1]) for k in g if k.endswith(".weight") and not k.startswith("fc_layers.0."))
+    for n, i in enumerate(idx):
+        a = a @ g[f"fc_layers.{i}.weight"].astype(f32).T + g[f"fc_layers.{i}.bias"].astype(f32)
+        if n < len(idx) - 1:
+            a = np.maximum(a, f32(0))
+    a = a - a.max(axis=1, keepdims=True)
+    e = np.exp(a)
+    return (e / e.sum(axis=1, keepdims=True)).astype(f32)

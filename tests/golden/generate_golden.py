@@ -521,6 +521,27 @@ def run_transpose():
     print(f"[transpose] wrote {path} ({os.path.getsize(path) / 1e3:.1f} kB)", flush=True)
 
 
+def run_classifier():
+    """BinaryClassifierLegacyNewBatching of the unmodified reference (alphadia/fdr/classifiers.py:145-532), trained here on
+    the CPU for three epochs: its state dict, inputs and predict_proba output -> tests/golden/classifier_small.npz."""
+    from tests.helpers import classifier_inputs
+
+    cl = refshim.ref("alphadia.fdr.classifiers")
+    x, y = classifier_inputs()
+    clf = cl.BinaryClassifierLegacyNewBatching(test_size=0.001, batch_size=500, learning_rate=0.001, epochs=3, random_state=3)
+    clf.fit(x, y)
+    proba = clf.predict_proba(x)
+    sd = clf.to_state_dict()
+    out = {"input_checksum": np.array(hashlib.sha256(x.tobytes() + y.tobytes()).hexdigest()), "proba": proba.astype(np.float32),
+           "predict": clf.predict(x), "layers": np.array(sd["layers"]), "input_dim": np.array(sd["input_dim"])}
+    for k, v in sd["network_state_dict"].items():
+        out["w__" + k] = v.detach().cpu().numpy()
+    acc = float(np.mean(np.argmax(proba, axis=1) == y))
+    path = os.path.join(HERE, "classifier_small.npz")
+    np.savez_compressed(path, **out)
+    print(f"[classifier] accuracy {acc:.3f}, keys {[k for k in out if k.startswith('w__')]}; wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def run_k9999(threads: int):
     """Transfer-library requantification scoring (transfer_library_requantification_handler.py:102-124): every library
     fragment is quantified, top_k_fragments = 9999, on the 20-fragment library of parity_f20 and the candidates the
@@ -583,5 +604,7 @@ if __name__ == "__main__":
             run_iso2(threads)
         elif n == "k9999":
             run_k9999(threads)
+        elif n == "classifier":
+            run_classifier()
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap", "parity_f20", "parity_4d_f20")))

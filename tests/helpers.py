@@ -387,3 +387,16 @@ def patch_device_with_oracle(monkeypatch, oracle_lib, is4d: bool = False):
     monkeypatch.setattr(_lib, "fetch_candidate_table", fetch_table)
     monkeypatch.setattr(_lib, "score_candidates", lambda dev_raw, dev_lib, cfg, cin: score(dev_raw.arrays, dev_lib.arrays, cfg, cin))
     monkeypatch.setattr(_lib, "score_candidates_ragged", ragged_scoring_stub(score))
+
+
+def classifier_inputs(seed: int = 21, n: int = 12000, n_features: int = 47):
+    """Feature matrix and target / decoy labels for the FDR classifier tests (tests/golden/classifier_small.npz): two
+    overlapping populations with feature scales spanning six orders of magnitude, as the 46 scoring features do."""
+    rng = np.random.default_rng(seed)
+    y = (rng.random(n) < 0.5).astype(np.float64)
+    scale = 10.0 ** rng.uniform(-2, 4, n_features)
+    shift = rng.normal(0, 1, n_features) * (rng.random(n_features) < 0.6)
+    x = (rng.normal(0, 1, (n, n_features)) + y[:, None] * shift[None, :]) * scale[None, :]
+    x[:, 3] = np.round(x[:, 3])            # an integer-valued feature
+    x[:, 5] = 0.0                          # a constant feature (zero variance in the batch norm)
+    return x.astype(np.float32), y

@@ -1135,3 +1135,43 @@ def test_fragcomp_conflict_graph_equals_window_serial_kernel_and_oracle(engine, 
     serial = engine.fragment_competition(*args)
     assert 1000 < (~ref).sum() < 10000
     assert np.array_equal(got, ref) and np.array_equal(serial, ref)
+
+
+def test_classifier_predict_proba_matches_reference(engine):
+    """adb_classifier_predict_proba with the weights the live reference trained (tests/golden/classifier_small.npz): within 1e-4
+    of the reference's predict_proba and of the numpy oracle, same classes; then fit on the device and check it learns."""
+    import hashlib
+
+    import oracle
+    from alphadia_b200.classifier import BinaryClassifierLegacyNewBatching
+
+    g = H.load_golden("classifier_small")
+    x, y = H.classifier_inputs()
+    if g is None or str(g["input_checksum"]) != hashlib.sha256(x.tobytes() + y.tobytes()).hexdigest():
+        pytest.skip("golden not applicable")
+    state = {k[3:]: g[k] for k in g.files if k.startswith("w__")}
+    clf = BinaryClassifierLegacyNewBatching()
+    clf.from_state_dict({"input_dim": int(g["input_dim"]), "output_dim": 2, "layers": [int(v) for v in g["layers"]], "dropout": 0.001,
+                         "network_state_dict": state})
+    p = clf.predict_proba(x)
+    assert p.shape == g["proba"].shape and p.dtype == np.float32
+    assert np.abs(p - g["proba"]).max() < 1e-5 and H.rel_err(p[:, 1], g["proba"][:, 1], floor=1e-3).max() < RTOL
+    assert np.abs(p - oracle.classifier_predict_proba(state, x)).max() < 1e-5
+    assert np.array_equal(clf.predict(x), g["predict"])
+    assert clf.predict_proba(x[:0]).shape == (0, 2)
+    # a wide input and odd layer widths (padding of the 4-output groups)
+    rng = np.random.default_rng(0)
+    dims = [128, 37, 6, 3]
+    st = {"fc_layers.0.weight": rng.random(dims[0]).astype(np.float32) + 0.5, "fc_layers.0.bias": rng.normal(size=dims[0]).astype(np.float32),
+          "fc_layers.0.running_mean": rng.normal(size=dims[0]).astype(np.float32), "fc_layers.0.running_var": rng.random(dims[0]).astype(np.float32) + 0.1}
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+        st[f"fc_layers.{1 + 3 * i}.weight"] = (rng.normal(size=(b, a)) / np.sqrt(a)).astype(np.float32)
+        st[f"fc_layers.{1 + 3 * i}.bias"] = rng.normal(size=b).astype(np.float32)
+    xx = rng.normal(size=(1000, dims[0])).astype(np.float32)
+    from alphadia_b200.classifier import network_forward_device
+    assert np.abs(network_forward_device(st, xx) - oracle.classifier_predict_proba(st, xx)).max() < 1e-5
+    # training on the device: the same recipe learns the planted separation
+    fit = BinaryClassifierLegacyNewBatching(test_size=0.001, batch_size=500, learning_rate=0.001, epochs=3, random_state=3)
+    fit.fit(x, y)
+    assert fit.fitted and np.mean(fit.predict(x) == y) > 0.97
+    assert len(fit.metrics["train_loss"]) >= 1

@@ -852,3 +852,48 @@ def test_fdr_oracle_equals_pandas_formulation(n, levels, oracle_lib):
     keep = oracle_lib.keep_best(score, group)
     best = pd.DataFrame({"s": score, "g": group}).sort_values(["s", "g"]).groupby("g").head(1).sort_index()
     assert np.array_equal(np.flatnonzero(keep), best.index.values)
+
+
+# ---- FDR classifier: BinaryClassifierLegacyNewBatching of the live reference ----------------------------
+def _classifier_golden():
+    import hashlib
+
+    g = H.load_golden("classifier_small")
+    if g is None:
+        pytest.skip("golden classifier_small.npz missing")
+    x, y = H.classifier_inputs()
+    if str(g["input_checksum"]) != hashlib.sha256(x.tobytes() + y.tobytes()).hexdigest():
+        pytest.skip("classifier_inputs differs from the one the golden file was made with (numpy version?)")
+    state = {k[3:]: g[k] for k in g.files if k.startswith("w__")}
+    return g, x, y, state
+
+
+def test_classifier_oracle_vs_reference():
+    """The numpy restatement of FeedForwardNN.forward (eval mode) against predict_proba / predict of the reference classifier
+    trained in this container (torch CPU): probabilities within 1e-5 absolute, identical classes."""
+    import oracle
+
+    g, x, y, state = _classifier_golden()
+    p = oracle.classifier_predict_proba(state, x)
+    assert p.shape == g["proba"].shape and p.dtype == np.float32
+    assert np.abs(p - g["proba"]).max() < 1e-5
+    assert H.rel_err(p[:, 1], g["proba"][:, 1], floor=1e-3).max() < 1e-4
+    assert np.array_equal(np.argmax(p, axis=1), g["predict"])
+
+
+def test_classifier_state_dict_round_trip():
+    """from_state_dict accepts the reference's dictionary (classifiers.py:258-309) and to_state_dict hands it back."""
+    from alphadia_b200.classifier import BinaryClassifierLegacyNewBatching
+
+    g, x, y, state = _classifier_golden()
+    clf = BinaryClassifierLegacyNewBatching()
+    assert not clf.fitted
+    with pytest.raises(ValueError):
+        clf.predict_proba(x)
+    clf.from_state_dict({"_fitted": True, "input_dim": int(g["input_dim"]), "output_dim": 2, "layers": [int(v) for v in g["layers"]],
+                         "dropout": 0.001, "epochs": 3, "network_state_dict": state}, load_hyperparameters=True)
+    assert clf.fitted and clf.input_dim == x.shape[1] and clf.layers == [100, 50, 20, 5] and clf.epochs == 3
+    sd = clf.to_state_dict()
+    assert set(sd["network_state_dict"]) == set(state)
+    for k, v in state.items():
+        assert np.array_equal(sd["network_state_dict"][k], v), k
