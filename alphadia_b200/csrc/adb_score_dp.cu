@@ -47,13 +47,95 @@ __global__ void __launch_bounds__(DP_THREADS, DP_LB_TEMPLATE) dp_template_kernel
   if (j < P.n) dp_template(P, j);
 }
 
-// thread t <-> t-th fragment row with signal of the batch (work list)
-__global__ void __launch_bounds__(DP_THREADS, DP_LB_FRAGMENT) dp_fragment_kernel(const __grid_constant__ DpParams P) {
-  const uint32_t t = blockIdx.x * DP_THREADS + threadIdx.x;
-  if (t >= (uint32_t)*P.n_work) return;
-  const uint32_t w = P.work[t];
+// ---- dp_fragment: work list + bulk-asynchronous staging of the fragment cubes ------------------------------------------
+// thread t <-> t-th fragment row with signal of the batch (work list, ascending slot).  The rows of one CTA belong to a run
+// of consecutive slots; the first row of every slot ("head") fetches that candidate's fragment cube [dfi | dfm] - one
+// contiguous, 16-byte aligned piece of the batch workspace whose address is known before any arithmetic - into the CTA's
+// shared-memory arena with ONE cp.async.bulk (TMA engine, completion counted on an mbarrier); the pass then reads its
+// intensity / m/z rows at shared-memory latency.  Cubes that do not fit the arena are read in place.
+// Measured on config 3 (r2, gpurun_out/w_*.json): staging ON with 128 threads x 36 KB x 6 CTAs/SM: scoring 58.6 ms, 128 x 26 KB
+// x 8: 57.9 ms; staging OFF with 256 threads x 4 CTAs/SM: 53.2 ms.  The pass still chases its other arrays (best profile,
+// template, weight tables) through L1/L2, the arena costs a quarter of the resident threads, and the cube rows are re-read
+// from L1 anyway - so the default build reads in place; -DDPF_STAGE=1 -DDPF_THREADS_N=128 -DDPF_ARENA_KB=36 -DDPF_MIN_BLOCKS=6
+// compiles the staged variant (SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64).
+#ifndef DPF_STAGE
+#define DPF_STAGE 0
+#endif
+#ifndef DPF_THREADS_N
+#define DPF_THREADS_N 256
+#endif
+#ifndef DPF_ARENA_KB
+#define DPF_ARENA_KB 0
+#endif
+#ifndef DPF_MIN_BLOCKS
+#define DPF_MIN_BLOCKS 4
+#endif
+constexpr int DPF_THREADS = DPF_THREADS_N;
+constexpr int DPF_ARENA_BYTES = DPF_ARENA_KB * 1024;
+
+__device__ __forceinline__ uint32_t dp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(DPF_THREADS, DPF_MIN_BLOCKS) dp_fragment_kernel(const __grid_constant__ DpParams P) {
+  extern __shared__ __align__(128) unsigned char dpf_arena[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ int s_off[DPF_THREADS];  // arena byte offset of the i-th slot run of this CTA, -1: read in place
+  __shared__ int s_warp_bytes[DPF_THREADS / 32], s_warp_heads[DPF_THREADS / 32];
+  const uint32_t t = blockIdx.x * DPF_THREADS + threadIdx.x;
+  const uint32_t n_work = (uint32_t)*P.n_work;
+  if (blockIdx.x * DPF_THREADS >= n_work) return;  // whole CTA idle
+  const bool active = t < n_work;
+  const uint32_t w = active ? P.work[t] : 0u;
   const uint32_t j = w / (uint32_t)P.KS;
-  dp_fragment(P, j, (int)(w - j * (uint32_t)P.KS));
+  const int k = (int)(w - j * (uint32_t)P.KS);
+  const bool head = active && (threadIdx.x == 0 || P.work[t - 1] / (uint32_t)P.KS != j);
+  int bytes = 0;
+  if (head) bytes = (2 * (int)P.F[j] * (int)P.nobs[j] * P.C[j] * 4 + 15) & ~15;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dp_smem_u32(&mbar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // CTA-wide exclusive scans of (bytes, head flags): warp shuffles + one pass over the warp totals
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc_b = bytes, inc_h = head ? 1 : 0;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int ub = __shfl_up_sync(0xFFFFFFFFu, inc_b, d), uh = __shfl_up_sync(0xFFFFFFFFu, inc_h, d);
+    if (lane >= d) { inc_b += ub; inc_h += uh; }
+  }
+  if (lane == 31) { s_warp_bytes[wid] = inc_b; s_warp_heads[wid] = inc_h; }
+  __syncthreads();
+  int base_b = 0, base_h = 0;
+  for (int q = 0; q < wid; q++) { base_b += s_warp_bytes[q]; base_h += s_warp_heads[q]; }
+  const int off = base_b + inc_b - bytes;        // exclusive
+  const int run = base_h + inc_h - 1;            // ordinal of this thread's slot run inside the CTA
+  const bool fits = DPF_STAGE && head && off + bytes <= DPF_ARENA_BYTES && bytes > 0;
+  if (head) s_off[run] = fits ? off : -1;
+  // total bytes in flight = those of the fitting heads (a prefix of the runs: offsets only grow)
+  int staged_bytes = fits ? bytes : 0;
+  for (int d = 16; d > 0; d >>= 1) staged_bytes += __shfl_xor_sync(0xFFFFFFFFu, staged_bytes, d);
+  if (lane == 0) s_warp_bytes[wid] = staged_bytes;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int q = 0; q < DPF_THREADS / 32; q++) total += s_warp_bytes[q];
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dp_smem_u32(&mbar)), "r"(total) : "memory");
+  }
+  if (fits) {
+    const float* src = P.cube + P.off[j];  // the block starts with [dfi | dfm]
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dp_smem_u32(dpf_arena + off)),
+                 "l"(src), "r"(bytes), "r"(dp_smem_u32(&mbar))
+                 : "memory");
+  }
+  {  // every thread waits for phase 0 of the barrier: all staged cubes have landed
+    const uint32_t bar = dp_smem_u32(&mbar);
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(0) : "memory");
+    }
+  }
+  if (!active) return;
+  const int so = s_off[run];
+  dp_fragment(P, j, k, so >= 0 ? (const float*)(dpf_arena + so) : nullptr);
 }
 
 __global__ void __launch_bounds__(DP_THREADS) dp_median_kernel(const __grid_constant__ DpParams P) {
@@ -161,7 +243,7 @@ int adb_launch_score_dp(const DevRaw& raw, const DevLib& lib, const adb_scoring_
                                  (int)(P.n * P.KS), stream);
     }
     dp_template_kernel<<<blocks_for(P.n), DP_THREADS, 0, stream>>>(P);
-    dp_fragment_kernel<<<blocks_for(P.n * P.KS), DP_THREADS, 0, stream>>>(P);
+    dp_fragment_kernel<<<(unsigned)((P.n * P.KS + DPF_THREADS - 1) / DPF_THREADS), DPF_THREADS, DPF_ARENA_BYTES, stream>>>(P);
     if (cfg.experimental_xic) dp_median_kernel<<<blocks_for(P.n * DP_MED_LANES), DP_THREADS, 0, stream>>>(P);
     dp_corr_kernel<<<blocks_for(P.n * P.KS), DP_THREADS, 0, stream>>>(P);
     dp_aggregate_kernel<<<blocks_for(P.n), DP_THREADS, 0, stream>>>(P);

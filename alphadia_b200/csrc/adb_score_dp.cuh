@@ -595,7 +595,9 @@ ADB_HD int dp_best_obs(const float* sc, int nobs) {
 // ------------------------------------------------------------------------------------------------------------------
 // dp_fragment: candidate.py:319-329 mask, fragment_features.py:198-336, profile_features.py (per-fragment parts)
 // ------------------------------------------------------------------------------------------------------------------
-ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k) {
+// `staged`: optional copy of the candidate's fragment cube [dfi | dfm] (2 * F * nobs * C floats) in shared memory - the
+// kernel stages it with one bulk asynchronous copy per candidate; every other array of the block is used in place.
+ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k, const float* staged = nullptr) {
   if (!P.state[j]) return;
   const DevRaw& raw = P.raw;
   const DevLib& lib = P.lib;
@@ -607,8 +609,8 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k) {
   float* blk = P.cube + P.off[j];
   const bool experimental = cfg.experimental_xic != 0;
   const DpLayout l = dp_layout(F, nobs, C, nI, experimental, raw.n_ms1_pos);
-  const float* d = blk + l.dfi + k;   // d[(o * C + c) * F]
-  const float* dmz = blk + l.dfm + k;
+  const float* d = (staged ? staged : blk + l.dfi) + k;   // d[(o * C + c) * F]
+  const float* dmz = (staged ? staged + (l.dfm - l.dfi) : blk + l.dfm) + k;
   float* b = blk + l.bp + k;          // b[c * F]
   const float* sc = blk + l.sc;
   int* fi = (int*)(blk + l.fi);

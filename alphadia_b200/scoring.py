@@ -163,12 +163,31 @@ def _merge_by_sorted_key(left_df, right_df, on, columns):
     return pd.concat([out, pd.DataFrame(new_cols, index=out.index, copy=False)], axis=1)
 
 
+def _count_residues_arrow(sequences, res):
+    """pyarrow's vectorised ``count_substring`` when the column is Arrow-backed (the ``str`` dtype of pandas >= 3): no
+    conversion of the strings to Python objects.  None when not applicable (other dtypes, missing values)."""
+    pa_array = getattr(sequences, "_pa_array", None)
+    if pa_array is None:
+        return None
+    try:
+        import pyarrow.compute as pc
+
+        if pa_array.null_count:
+            return None
+        return [np.asarray(pc.count_substring(pa_array, r)).astype(np.int64, copy=False) for r in res]
+    except Exception:  # an older pyarrow without the kernel: the numpy path below gives the same counts
+        return None
+
+
 def count_residues(sequences, residues) -> list:
     """``Series.str.count(r)`` for single-character patterns (scoring.py:461-463 n_K / n_R / n_P) without a Python call
     per row: the distinct sequences are counted once as fixed-width code points and the counts are gathered.
     Returns one int64 array per residue (a single array when ``residues`` is a single character)."""
     single = isinstance(residues, str) and len(residues) == 1
     res = [residues] if single else list(residues)
+    pa_counts = _count_residues_arrow(sequences, res)
+    if pa_counts is not None:
+        return pa_counts[0] if single else pa_counts
     values = np.asarray(sequences, dtype=object)
     if len(values) == 0:
         out = [np.zeros(0, dtype=np.int64) for _ in res]
@@ -522,7 +541,7 @@ class CandidateScoring:
             self.precursor_mz_column, precursor_df_columns,
         )
         candidates_psm_df["delta_rt"] = candidates_psm_df["rt_observed"] - candidates_psm_df[self.rt_column]
-        n_k, n_r, n_p = count_residues(candidates_psm_df["sequence"].values, ["K", "R", "P"])
+        n_k, n_r, n_p = count_residues(candidates_psm_df["sequence"].array, ["K", "R", "P"])
         candidates_psm_df["n_K"], candidates_psm_df["n_R"], candidates_psm_df["n_P"] = n_k, n_r, n_p
         return candidates_psm_df
 

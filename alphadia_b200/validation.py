@@ -7,6 +7,7 @@ column -> ValueError) and alphadia/validation/schemas.py:11-120 (column sets and
 from __future__ import annotations
 
 import logging
+import os
 
 import numpy as np
 import pandas as pd
@@ -57,8 +58,9 @@ class Schema:
     @staticmethod
     def _warn_on_critical_values(df: pd.DataFrame) -> None:
         """validation/base.py:120-152 (NaN / Inf counts per float column).  ``sum`` is finite only if every element is,
-        so the common all-finite case costs one read and no temporary; columns that are strided views into one shared
-        2-D array (a feature matrix wrapped in a DataFrame) are cleared by a single pass over that array."""
+        so the common all-finite case costs one read and no temporary.  Columns that are strided views into one shared
+        2-D array (a feature matrix wrapped in a DataFrame) are cleared together: one row-major pass over that array
+        (row blocks on a few threads) yields every column sum; only the columns whose sum is not finite are counted."""
         floats = []
         for col in df.columns:
             dtype = df[col].dtype
@@ -67,16 +69,20 @@ class Schema:
         shared: dict = {}
         for _, v in floats:
             base = v.base
-            if isinstance(base, np.ndarray) and base.dtype == v.dtype and not v.flags.c_contiguous:
-                entry = shared.setdefault(id(base), [base, 0])
-                entry[1] += 1
-        finite_bases = set()
+            if (isinstance(base, np.ndarray) and base.ndim == 2 and base.dtype == v.dtype and base.flags.c_contiguous
+                    and v.ndim == 1 and v.strides[0] == base.strides[0] and len(v) == base.shape[0]):
+                shared.setdefault(id(base), base)
+        column_finite: dict = {}
         with np.errstate(over="ignore", invalid="ignore"):
-            for key, (base, n_cols) in shared.items():
-                if base.size <= 2 * n_cols * max(len(df), 1) and np.isfinite(base.sum()):
-                    finite_bases.add(key)
+            for key, base in shared.items():
+                column_finite[key] = np.isfinite(_column_sums(base))
             for col, v in floats:
-                if id(v.base) in finite_bases or np.isfinite(v.sum()):
+                key = id(v.base)
+                if key in column_finite:
+                    j = (v.__array_interface__["data"][0] - shared[key].__array_interface__["data"][0]) // v.itemsize
+                    if 0 <= j < shared[key].shape[1] and column_finite[key][j]:
+                        continue
+                elif np.isfinite(v.sum()):
                     continue
                 n_nan = int(np.isnan(v).sum())
                 n_inf = int(np.isinf(v).sum())
@@ -84,6 +90,21 @@ class Schema:
                     logger.warning(f"{col} has {n_nan} NaNs ( {n_nan / len(df) * 100:.2f} % out of {len(df)})")
                 if n_inf:
                     logger.warning(f"{col} has {n_inf} Infs ( {n_inf / len(df) * 100:.2f} % out of {len(df)})")
+
+
+def _column_sums(a: np.ndarray) -> np.ndarray:
+    """Column sums of a C-contiguous 2-D array; large arrays are summed in row blocks on a few threads (numpy releases the
+    GIL inside the reduction)."""
+    n = a.shape[0]
+    if a.size < (1 << 22):
+        return a.sum(axis=0)
+    from concurrent.futures import ThreadPoolExecutor
+
+    workers = min(8, os.cpu_count() or 1)
+    bounds = np.linspace(0, n, 4 * workers + 1).astype(np.int64)
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        parts = list(pool.map(lambda i: a[bounds[i]:bounds[i + 1]].sum(axis=0), range(len(bounds) - 1)))
+    return np.sum(parts, axis=0)
 
 
 _ISO = [Optional(f"i_{i}", np.float32) for i in range(10)]

@@ -392,3 +392,30 @@ def test_adapt_dia_data_variants():
     bad = SimpleNamespace(**{**vars(c), "dia_precursor_cycle": c.dia_precursor_cycle[:-1]})
     with pytest.raises(ValueError):
         _abi.make_rawfile4d_desc(bad)
+
+
+def test_count_residues_arrow_backed_strings_and_nan_columns_in_validation(caplog):
+    """The Arrow-backed ``str`` columns of pandas >= 3 are counted without a trip through Python objects; the per-column
+    NaN / Inf warnings of Schema.validate come out of one pass over a shared feature matrix."""
+    import logging
+
+    import pandas as pd
+
+    from alphadia_b200.scoring import count_residues
+    from alphadia_b200.validation import Schema
+
+    rng = np.random.default_rng(2)
+    alphabet = np.array(list("ACDEFGHIKLMNPQRSTVWY"))
+    seqs = pd.Series(["".join(rng.choice(alphabet, size=rng.integers(0, 30))) for _ in range(5000)], dtype="str")
+    for got, r in zip(count_residues(seqs.array, ["K", "R", "P"]), "KRP"):
+        assert got.dtype == np.int64 and np.array_equal(got, seqs.str.count(r).values)
+    block = rng.random((300_000, 16)).astype(np.float32)  # > 2^22 elements: the threaded column sums
+    block[::7, 3] = np.nan
+    block[5, 9] = np.inf
+    df = pd.DataFrame(block, columns=[f"f{j}" for j in range(16)], copy=False)
+    df["extra"] = np.float32(1.0)
+    with caplog.at_level(logging.WARNING):
+        Schema("t", [])._warn_on_critical_values(df)
+    msgs = [r.getMessage() for r in caplog.records]
+    assert any(m.startswith("f3 has 42858 NaNs") for m in msgs) and any(m.startswith("f9 has 1 Infs") for m in msgs)
+    assert len(msgs) == 2
