@@ -76,14 +76,28 @@ class Schema:
         with np.errstate(over="ignore", invalid="ignore"):
             for key, base in shared.items():
                 column_finite[key] = np.isfinite(_column_sums(base))
+            suspects = []
+            singles = []
             for col, v in floats:
                 key = id(v.base)
                 if key in column_finite:
                     j = (v.__array_interface__["data"][0] - shared[key].__array_interface__["data"][0]) // v.itemsize
-                    if 0 <= j < shared[key].shape[1] and column_finite[key][j]:
+                    if 0 <= j < shared[key].shape[1]:
+                        if not column_finite[key][j]:
+                            suspects.append((col, v))
                         continue
-                elif np.isfinite(v.sum()):
-                    continue
+                singles.append((col, v))
+            # stand-alone columns: one sum each, on a few threads when the table is large (numpy releases the GIL)
+            if len(singles) > 1 and len(df) >= (1 << 20):
+                from concurrent.futures import ThreadPoolExecutor
+
+                with ThreadPoolExecutor(max_workers=min(8, len(singles), os.cpu_count() or 1)) as pool:
+                    finite = list(pool.map(lambda cv: bool(np.isfinite(cv[1].sum())), singles))
+            else:
+                finite = [bool(np.isfinite(v.sum())) for _, v in singles]
+            suspects += [cv for cv, ok in zip(singles, finite) if not ok]
+            order = {col: i for i, (col, _) in enumerate(floats)}
+            for col, v in sorted(suspects, key=lambda cv: order[cv[0]]):
                 n_nan = int(np.isnan(v).sum())
                 n_inf = int(np.isinf(v).sum())
                 if n_nan:
