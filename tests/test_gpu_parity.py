@@ -1175,3 +1175,26 @@ def test_classifier_predict_proba_matches_reference(engine):
     fit.fit(x, y)
     assert fit.fitted and np.mean(fit.predict(x) == y) > 0.97
     assert len(fit.metrics["train_loss"]) >= 1
+
+
+@pytest.mark.parametrize("workload,n_prec", [("config3", 700), ("config4", 600)])
+def test_full_size_benchmark_workloads_vs_oracle(engine, oracle_lib, workload, n_prec):
+    """The two benchmarked workloads at their FULL size (config 3: 2 M precursors, 3-D; config 4: 200 k precursors, timsTOF,
+    80 scans x 112 cycles per search window): one resident step on the device, then the oracle selects and scores a random
+    subsample of the library against the same raw file (>= 1 500 candidate rows) - candidate container rows bit for bit, valid
+    mask, 46 features and the fragment tables within 1e-4 (the check bench.py attaches to its timed results)."""
+    import bench
+    from alphadia_b200.engine import HotPath
+
+    raw, pdf, fdf, lib, p, sel, sc, kernel = bench.build_workload(workload, 0, None)
+    hp = HotPath(raw, lib, sel, sc, kernel, device=0)
+    try:
+        stats = hp.resident_step()
+        assert stats["n_candidates"] > 0.9 * hp.n_precursors * sel.candidate_count
+        cont = engine.fetch_candidates(hp.dev_raw, int(hp.n_precursors * sel.candidate_count))
+        r = bench.parity_spot_check(hp, raw, lib, sel, sc, kernel, cont, n_prec=n_prec)
+    finally:
+        hp.close()
+    assert r["n"] >= 1500 and r["valid"] > 0.5 * r["n"], r
+    assert r["int_exact"] and r["selection_score_bit_exact"] and r["valid_exact"], r
+    assert r["max_rel"] < RTOL and r["fragment_table_max_rel"] < 3 * RTOL, r
