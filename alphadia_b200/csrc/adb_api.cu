@@ -168,6 +168,7 @@ int check_status(adb_rawfile* raw, const char* where) {
   if (st & ADB_STATUS_TOO_MANY_OBS) msg += " a precursor overlaps more than " + std::to_string(ADB_MAX_OBS) + " quadrupole windows;";
   if (st & ADB_STATUS_TOO_MANY_LIB_FRAGMENTS) msg += " a precursor has more than " + std::to_string(ADB_MAX_LIB_FRAGMENTS) + " library fragments;";
   if (st & ADB_STATUS_SCRATCH_OVERFLOW) msg += " a candidate/precursor window exceeds the device scratch;";
+  if (st & ADB_STATUS_TOO_MANY_PEAKS) msg += " a spectrum segment exceeds the index limits;";
   CUDA_TRY(cudaMemsetAsync(raw->d_status, 0, sizeof(uint32_t), raw->stream));
   return fail(msg);
 }
@@ -1579,11 +1580,18 @@ int adb_score_candidates_resident(adb_rawfile_t* raw, adb_library_t* lib, const 
   cudaStream_t st = raw->stream;
   CUDA_TRY(cudaEventRecord(raw->ev[0], st));
   CUDA_TRY(cudaEventRecord(raw->ev[1], st));
+  // extents of the resident candidate table (join_close_candidates and a user-set max_size_rt make windows of any length)
+  // and the library-row bounds check, as adb_score_candidates does for a caller's table
+  int64_t s_max = 0, f_max = 0, bad_row = 0;
+  if (resident_extents(raw, &s_max, &f_max, lib->dev.n_precursors, &bad_row)) return 1;
+  if (bad_row) return fail("a resident candidate refers to a precursor outside the library");
   if (raw->is4d) {
-    int64_t s_max = 0, f_max = 0;
-    if (resident_extents(raw, &s_max, &f_max)) return 1;
     if (run_scoring(raw, lib, cfg, f_max, s_max)) return 1;
-  } else if (run_scoring(raw, lib, cfg, 64)) return 1;  // selection emits at most 2 * max_size_rt - 1 cycles
+  } else {
+    const int64_t c_max = f_max / raw->dev.cycle_len + 1;
+    if (c_max > 4096) return fail("a candidate spans more than 4096 cycles");
+    if (run_scoring(raw, lib, cfg, c_max)) return 1;
+  }
   CUDA_TRY(cudaEventRecord(raw->ev[2], st));
   if (check_status(raw, "adb_score_candidates_resident")) return 1;
   CUDA_TRY(cudaEventRecord(raw->ev[3], st));

@@ -106,7 +106,11 @@ def get_q_values(
     qval_column: str = "qval",
     extra_sort_columns: list[str] | None = None,
 ) -> pd.DataFrame:
-    """fdr.py:226-297: rows sorted by ``[score, decoy, *extra_sort_columns]`` with the q-value column added."""
+    """fdr.py:226-297: rows sorted by ``[score, decoy, *extra_sort_columns]`` with the q-value column added.
+
+    Restriction (documented divergence): a NaN in ``score_column`` or a decoy value other than 0 / 1 raises instead of being
+    sorted last as pandas would; ``perform_fdr`` drops rows with missing features before the classifier runs (fdr.py:84-98),
+    so its probabilities are finite."""
     if extra_sort_columns is None:
         extra_sort_columns = ["precursor_idx"]
     decoy = df[decoy_column].to_numpy()
@@ -123,7 +127,10 @@ def get_q_values(
 
 
 def keep_best(df: pd.DataFrame, score_column: str = "proba", group_columns: list[str] | None = None) -> pd.DataFrame:
-    """fdr.py:195-224: the best-scoring (lowest ``score_column``) row of every group, in the original row order."""
+    """fdr.py:195-224: the best-scoring (lowest ``score_column``) row of every group, in the original row order.
+
+    Restriction (documented divergence): NaN scores raise; rows whose group key is NaN form their own group here, while
+    ``groupby(...).head(1)`` of the reference drops them (integer group columns, the only ones the workflow uses, have no NaN)."""
     if group_columns is None:
         group_columns = ["channel", "precursor_idx"]
     df = df.reset_index(drop=True)
