@@ -21,7 +21,10 @@
 #define ADB_SCORE_BLOCKS 4  // row blocks of a scoring call whose D2H overlaps the next block's kernel (<= 7)
 #endif
 #ifndef ADB_RAGGED_BLOCKS
-#define ADB_RAGGED_BLOCKS 6  // same for ragged results: a block's copy starts one block late (<= 7)
+#define ADB_RAGGED_BLOCKS 7  // same for ragged results: a block's copy starts one block late (<= 7)
+#endif
+#ifndef ADB_RAGGED_BLOCK_RATIO
+#define ADB_RAGGED_BLOCK_RATIO 0.6  // size of block k + 1 relative to block k
 #endif
 
 namespace {
@@ -294,7 +297,9 @@ __global__ void order_key_kernel(DevRaw raw, DevLib lib, uint64_t* keys, int32_t
 // processing order of the candidates: (output row block, quad window, time bucket of 32 cycles, cost class).  Candidates
 // that are resident together read the same spectra (L2 reuse) and the candidates of one CTA round cost about the same
 // (the scoring kernel runs its tiles in lock step).  Results do not depend on the order (disjoint output rows).
-__global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn cand, int64_t chunk_len, int n_iso,
+struct RowBlocks { int n; int64_t start[9]; };  // row blocks [start[k], start[k + 1]) of a scoring call
+
+__global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn cand, RowBlocks blocks, int n_iso,
                                        uint64_t* keys, int32_t* vals) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cand.n) return;
@@ -315,7 +320,9 @@ __global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn c
   // cost class = (observations, cycles): the two candidates that share a warp and the tiles of a lock-step round then
   // run loops of identical trip counts (less divergence than sorting by the product)
   const uint64_t cost = ((uint64_t)min(max(nobs, 1), 3) << 6) | (uint64_t)min(cyc, 63LL);
-  keys[i] = ((uint64_t)(i / chunk_len) << 48) | ((uint64_t)win << 32) | (bucket << 8) | cost;
+  uint64_t blk = 0;
+  for (int k = 1; k < blocks.n; k++) blk += i >= blocks.start[k];
+  keys[i] = (blk << 48) | ((uint64_t)win << 32) | (bucket << 8) | cost;
   vals[i] = (int32_t)i;
 }
 
@@ -1024,7 +1031,20 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   // spectra; results do not depend on it (disjoint output rows)
   int32_t* d_order = nullptr;
   const int n_chunks = ((host_out || rag) && n >= 200000) ? (rag ? ADB_RAGGED_BLOCKS : ADB_SCORE_BLOCKS) : 1;
-  const int64_t chunk_len = std::max<int64_t>((n + n_chunks - 1) / n_chunks, 1);
+  // row blocks: equal for the dense tables; geometric (ratio 0.6 = copy time / scoring time of a block) for the ragged
+  // result, whose copy starts one block late - every copy then hides behind the next, smaller block and the un-overlapped
+  // tail is the copy of the last two (smallest) blocks
+  RowBlocks blocks{};
+  blocks.n = n_chunks;
+  {
+    double w[8], tot = 0;
+    for (int k = 0; k < n_chunks; k++) { w[k] = rag ? pow(ADB_RAGGED_BLOCK_RATIO, k) : 1.0; tot += w[k]; }
+    double acc = 0;
+    for (int k = 0; k < n_chunks; k++) { blocks.start[k] = std::min<int64_t>((int64_t)(acc / tot * (double)n), n); acc += w[k]; }
+    blocks.start[0] = 0;
+    blocks.start[n_chunks] = n;
+    for (int k = n_chunks + 1; k < 9; k++) blocks.start[k] = n;
+  }
   if (n > 1 && n < 2000000000LL) {
     if (raw->order_keys.reserve(sizeof(uint64_t) * 2 * (size_t)n)) return 1;
     if (raw->order_vals.reserve(sizeof(int32_t) * 2 * (size_t)n)) return 1;
@@ -1032,7 +1052,7 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
     uint64_t* k_out = k_in + n;
     int32_t* v_in = raw->order_vals.as<int32_t>();
     int32_t* v_out = v_in + n;
-    score_order_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->dev, lib->dev, raw->d_cand, chunk_len,
+    score_order_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw->dev, lib->dev, raw->d_cand, blocks,
                                                                       (int)std::min<int64_t>(std::min<int64_t>(lib->dev.n_isotopes, cfg->top_k_isotopes), ADB_MAX_ISOTOPES), k_in, v_in);
     raw->launches++;
     const int end_bit = n_chunks > 1 ? 52 : 48;
@@ -1058,7 +1078,7 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
     }
   } else {
     for (int k = 0; k < n_chunks; k++) {
-      const int64_t c0 = std::min<int64_t>(k * chunk_len, n), c1 = std::min<int64_t>(c0 + chunk_len, n);
+      const int64_t c0 = blocks.start[k], c1 = blocks.start[k + 1];
       if (c1 <= c0) continue;
       DevCandidatesIn part = raw->d_cand;
       part.n = c1 - c0;  // the kernel visits order[c0 .. c1): the (window, time)-sorted rows of block k
