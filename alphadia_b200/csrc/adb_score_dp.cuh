@@ -29,6 +29,7 @@
 // fragment index fastest: the F threads of a candidate touch F adjacent floats for the same (observation, cycle).
 #pragma once
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "adb_common.cuh"
@@ -44,6 +45,48 @@
 #else
 #define ADB_LD(p) (*(p))
 #endif
+
+// Workspace tiles: the blocks of DP_W consecutive slots are interleaved - element x of slot j lives at
+// tile_base + x * DP_W + (j % DP_W) - so that the lanes of a warp (consecutive slots, same loop index) read and write
+// consecutive addresses.  The pass bodies index their block through the small pointer wrappers below and are written as if
+// the block were contiguous (DP_W = 1 is exactly that layout).
+#ifndef DP_W
+#define DP_W 8   // measured on config 3: 1 (contiguous blocks) 54.1 ms, 4 / 8 / 16: 46.7 ms, 32: 48.2 ms (padding to the largest block of a tile)
+#endif
+
+template <typename T>
+struct DpPtr {  // T = float or int
+  T* p;
+  ADB_HD T& operator[](int i) const { return p[(ptrdiff_t)i * DP_W]; }
+  ADB_HD DpPtr operator+(int o) const { return DpPtr{p + (ptrdiff_t)o * DP_W}; }
+};
+typedef DpPtr<float> FPtr;
+typedef DpPtr<int> IPtr;
+ADB_HD IPtr dp_as_int(FPtr f) { return IPtr{(int*)f.p}; }
+
+struct DpDRef {  // a double kept as its two 32-bit halves in neighbouring elements
+  float* lo;
+  ADB_HD operator double() const {
+    union { double d; uint32_t u[2]; } v;
+    v.u[0] = ((const uint32_t*)lo)[0];
+    v.u[1] = ((const uint32_t*)lo)[DP_W];
+    return v.d;
+  }
+  ADB_HD const DpDRef& operator=(double x) const {
+    union { double d; uint32_t u[2]; } v;
+    v.d = x;
+    ((uint32_t*)lo)[0] = v.u[0];
+    ((uint32_t*)lo)[DP_W] = v.u[1];
+    return *this;
+  }
+  ADB_HD const DpDRef& operator=(const DpDRef& o) const { return *this = (double)o; }
+};
+struct DPtr {
+  float* p;
+  ADB_HD DpDRef operator[](int i) const { return DpDRef{p + (ptrdiff_t)(2 * i) * DP_W}; }
+  ADB_HD DPtr operator+(int o) const { return DPtr{p + (ptrdiff_t)(2 * o) * DP_W}; }
+};
+ADB_HD DPtr dp_as_double(FPtr f) { return DPtr{f.p}; }
 
 #define DP_MAXF ADB_MAX_LIB_FRAGMENTS  // fragments one candidate may keep (top_k_fragments is clamped to the library's widest precursor)
 #define DP_MED_LANES 16                // threads per candidate in dp_median
@@ -70,8 +113,9 @@ struct DpParams {
   uint32_t* fsel;        // [n][KS] library fragment index of the selected fragments, m/z order
   double* qtf;           // [n][nIcap * ADB_MAX_OBS]
   float* qmask;          // [n][ADB_MAX_OBS]
-  int64_t* need;         // [n + 1] block size in floats (input of the scan)
-  const int64_t* off;    // [n + 1] block offset in floats (output of the scan)
+  int64_t* need;         // [n] block size of a slot in floats
+  int64_t* tile_need;    // [n_tiles + 1] DP_W * the largest block of the tile (input of the scan)
+  const int64_t* off;    // [n_tiles + 1] tile offset in floats (output of the scan)
   float* cube;
   uint32_t* status;
   uint8_t* rowflag;      // [n][KS] 1: fragment row with signal (candidate.py:319-329), written by dp_extract
@@ -123,6 +167,18 @@ ADB_HD void dp_status_or(uint32_t* status, uint32_t bit) {
   *status |= bit;
 #endif
 }
+
+ADB_HD FPtr dp_block(const DpParams& P, int64_t j) { return FPtr{P.cube + P.off[j / DP_W] + (j % DP_W)}; }
+
+// thread index <-> (slot, row) for passes with `per` rows per slot: inside a tile the slot index runs fastest, so the lanes
+// of a warp hold the same row of consecutive slots
+ADB_HD void dp_decode(uint32_t t, uint32_t per, uint32_t& j, uint32_t& r) {
+  const uint32_t tile = t / (DP_W * per), rem = t - tile * (DP_W * per);
+  r = rem / DP_W;
+  j = tile * DP_W + (rem - r * DP_W);
+}
+ADB_HD uint32_t dp_encode(uint32_t j, uint32_t r, uint32_t per) { return (j / DP_W) * (DP_W * per) + r * DP_W + (j % DP_W); }
+ADB_HD int64_t dp_padded_slots(int64_t n) { return (n + DP_W - 1) / DP_W * DP_W; }
 
 ADB_HD int64_t dp_candidate_of(const DpParams& P, int64_t j) { return P.order ? (int64_t)P.order[P.base + j] : P.base + j; }
 
@@ -283,7 +339,7 @@ ADB_HD uint32_t dp_f2u(float x) {
 #endif
 }
 
-ADB_HD void dp_extract_row(const DevRaw& raw, int ps, float lo, float hi, float prev_hi, int cs, int C, float* di, float* dm, int stride,
+ADB_HD void dp_extract_row(const DevRaw& raw, int ps, float lo, float hi, float prev_hi, int cs, int C, FPtr di, FPtr dm, int stride,
                            int& c_lo, int& c_hi) {
   // first wanted peak: m/z >= lo, or m/z > prev_hi when the previous window reaches into this one (prev_hi >= lo)
   const bool overlap = prev_hi >= lo;
@@ -334,7 +390,7 @@ ADB_HD void dp_extract_row(const DevRaw& raw, int ps, float lo, float hi, float 
 // with one MS1 spectrum per cycle run through the same extraction code (one call site: the lanes of a warp stay together).
 ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
   if (!P.state[j]) {
-    if (r < P.KS) P.rowflag[j * P.KS + r] = 0;
+    if (r < P.KS) P.rowflag[dp_encode((uint32_t)j, (uint32_t)r, (uint32_t)P.KS)] = 0;
     return;
   }
   const DevRaw& raw = P.raw;
@@ -342,12 +398,12 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
   const adb_scoring_config& cfg = P.cfg;
   const int F = P.F[j], nobs = P.nobs[j], C = P.C[j], cs = P.cs[j];
   const int nI = min(min(lib.n_isotopes, (int)min(cfg.top_k_isotopes, 1000u)), ADB_MAX_ISOTOPES);
-  float* blk = P.cube + P.off[j];
+  const FPtr blk = dp_block(P, j);
   const DpLayout l = dp_layout(F, nobs, C, nI, cfg.experimental_xic != 0, raw.n_ms1_pos);
   const bool is_frag = r < P.KS;
   const int k = is_frag ? r : r - P.KS;  // fragment or isotope index
   if (is_frag ? (k >= F) : (k >= nI)) {
-    if (is_frag) P.rowflag[j * P.KS + k] = 0;
+    if (is_frag) P.rowflag[dp_encode((uint32_t)j, (uint32_t)k, (uint32_t)P.KS)] = 0;
     return;
   }
   // m/z window of the row and of its predecessor (the reference's search cursor only moves forward)
@@ -375,8 +431,8 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
     // are +0 and leave the f32 sums unchanged, so the sums run over the written range only.
     float t_o = 0.f;
     for (int o = 0; o < n_rows; o++) {
-      float* di = blk + (is_frag ? l.dfi + (o * C) * F : l.dpi) + k;
-      float* dm = blk + (is_frag ? l.dfm + (o * C) * F : l.dpm) + k;
+      const FPtr di = blk + ((is_frag ? l.dfi + (o * C) * F : l.dpi) + k);
+      const FPtr dm = blk + ((is_frag ? l.dfm + (o * C) * F : l.dpm) + k);
       for (int c = 0; c < C; c++) { di[c * stride] = 0.f; dm[c * stride] = 0.f; }
       int c_lo = C, c_hi = -1;
       dp_extract_row(raw, is_frag ? (int)P.pos[j * ADB_MAX_OBS + o] : raw.ms1_pos[0], lo, hi, prev_hi, cs, C, di, dm, stride, c_lo, c_hi);
@@ -398,19 +454,19 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
     }
     if (is_frag) {
       const bool fvalid = t_o > 0.f;
-      ((int*)(blk + l.fi))[FI_VALID * F + k] = fvalid ? 1 : 0;
-      P.rowflag[j * P.KS + k] = fvalid ? 1 : 0;
+      dp_as_int(blk + l.fi)[FI_VALID * F + k] = fvalid ? 1 : 0;
+      P.rowflag[dp_encode((uint32_t)j, (uint32_t)k, (uint32_t)P.KS)] = fvalid ? 1 : 0;
     }
     return;
   }
   // candidate.py:239-269 MS1 cube with the observation collapse (sum of intensities, mean of the non-zero m/z)
   const int i = k;
-  float* di = blk + l.dpi + i;
-  float* dm = blk + l.dpm + i;
-  double* smz = (double*)(blk + l.ms1) + i * C;
-  float* ta = blk + l.ms1 + 2 * nI * C + i * C;
-  float* tm = blk + l.ms1 + 3 * nI * C + i * C;
-  int* cnt = (int*)(blk + l.ms1 + 4 * nI * C) + i * C;
+  const FPtr di = blk + (l.dpi + i);
+  const FPtr dm = blk + (l.dpm + i);
+  const DPtr smz = dp_as_double(blk + l.ms1) + i * C;
+  const FPtr ta = blk + (l.ms1 + 2 * nI * C + i * C);
+  const FPtr tm = blk + (l.ms1 + 3 * nI * C + i * C);
+  const IPtr cnt = dp_as_int(blk + (l.ms1 + 4 * nI * C)) + i * C;
   for (int c = 0; c < C; c++) { di[c * nI] = 0.f; smz[c] = 0.0; cnt[c] = 0; }
   for (int q = 0; q < raw.n_ms1_pos; q++) {
     for (int c = 0; c < C; c++) { ta[c] = 0.f; tm[c] = 0.f; }
@@ -428,7 +484,8 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
 // features_utils.py:9-26 weighted_center_mean of the intensity row r and the m/z row rm (element stride `st`) of one
 // (fragment, observation) cell over the two identical scan rows, with the tabulated distance weights wt[2][C].
 // A cell that is not > 0 adds +0.0, which leaves the (non-negative) running sums bit-identical.
-ADB_HD void dp_weighted_center_mean_pair(const float* r, const float* rm, int st, const double* wt, int wst, int C, double& h, double& mz) {
+template <typename WT>  // weights: DPtr (table inside the block) or const double* (the shared precursor table)
+ADB_HD void dp_weighted_center_mean_pair(FPtr r, FPtr rm, int st, WT wt, int wst, int C, double& h, double& mz) {
   double v1 = 0, w1 = 0, v2 = 0, w2 = 0;
   bool any1 = false, any2 = false;
   for (int s = 0; s < 2; s++)
@@ -455,19 +512,19 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
   const adb_scoring_config& cfg = P.cfg;
   const int F = P.F[j], nobs = P.nobs[j], C = P.C[j];
   const int nI = min(min(lib.n_isotopes, (int)min(cfg.top_k_isotopes, 1000u)), ADB_MAX_ISOTOPES);
-  float* blk = P.cube + P.off[j];
+  const FPtr blk = dp_block(P, j);
   const DpLayout l = dp_layout(F, nobs, C, nI, cfg.experimental_xic != 0, raw.n_ms1_pos);
   const int64_t ci = dp_candidate_of(P, j);
   const int64_t p = P.cand.lib_row[ci];
   const int64_t frame_start = P.cand.frame_start[ci], frame_stop = P.cand.frame_stop[ci], frame_center = P.cand.frame_center[ci];
   const int64_t scan_start = P.cand.scan_start[ci], scan_stop = P.cand.scan_stop[ci], scan_center = P.cand.scan_center[ci];
   const double* qtf = P.qtf + j * (int64_t)(P.nIcap * ADB_MAX_OBS);
-  const float* dpi = blk + l.dpi;
-  const float* dpm = blk + l.dpm;
-  float* tmpl = blk + l.tmpl;
-  float* tfp = blk + l.tfp;
-  double* wtab = (double*)(blk + l.wtab);
-  float* sc = blk + l.sc;
+  const FPtr dpi = blk + l.dpi;
+  const FPtr dpm = blk + l.dpm;
+  const FPtr tmpl = blk + l.tmpl;
+  const FPtr tfp = blk + l.tfp;
+  const DPtr wtab = dp_as_double(blk + l.wtab);
+  const FPtr sc = blk + l.sc;
   float iso_int[ADB_MAX_ISOTOPES], iso_mz[ADB_MAX_ISOTOPES];
   const double charge = (double)lib.charge[p];
   const float pmz = lib.mz[p];
@@ -513,7 +570,7 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
   // distance-weight tables for weighted_center_mean (features_utils.py:9-26); the precursor "centres" are the constants
   // (n_scans, n_observations) = (2, 1): that table is the same for every candidate (P.wtab_p, dp_wtab_p_entry)
   for (int o = 0; o < nobs; o++) {  // fragment_features.py:20-49 centre of mass of the template
-    const float* r = tmpl + o * C;
+    const FPtr r = tmpl + o * C;
     double isum = 0, ssum = 0, fsum = 0;
     bool any = false;
     for (int s = 0; s < 2; s++)
@@ -532,7 +589,7 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
       wtab[o * 2 * C + t] = exp(-0.1 * sqrt(ds * ds + dc * dc));
     }
   }
-  float* fa = sc + SC_FEAT;
+  const FPtr fa = sc + SC_FEAT;
   for (int t = 0; t < ADB_NUM_FEATURES; t++) fa[t] = 0.f;
   // features/location_features.py:9-33
   fa[0] = raw.mobility_values[scan_start] - raw.mobility_values[scan_stop - 1];
@@ -586,7 +643,7 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
   fa[16] = (float)(num2 / (sqrt(sxx * shh) + 1e-12));
 }
 
-ADB_HD int dp_best_obs(const float* sc, int nobs) {
+ADB_HD int dp_best_obs(FPtr sc, int nobs) {
   int best = 0;
   for (int o = 1; o < nobs; o++) if (sc[SC_OI + o] > sc[SC_OI + best]) best = o;
   return best;
@@ -595,9 +652,7 @@ ADB_HD int dp_best_obs(const float* sc, int nobs) {
 // ------------------------------------------------------------------------------------------------------------------
 // dp_fragment: candidate.py:319-329 mask, fragment_features.py:198-336, profile_features.py (per-fragment parts)
 // ------------------------------------------------------------------------------------------------------------------
-// `staged`: optional copy of the candidate's fragment cube [dfi | dfm] (2 * F * nobs * C floats) in shared memory - the
-// kernel stages it with one bulk asynchronous copy per candidate; every other array of the block is used in place.
-ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k, const float* staged = nullptr) {
+ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k) {
   if (!P.state[j]) return;
   const DevRaw& raw = P.raw;
   const DevLib& lib = P.lib;
@@ -606,16 +661,16 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k, const float* staged
   if (k >= F) return;
   const int nobs = P.nobs[j], C = P.C[j];
   const int nI = min(min(lib.n_isotopes, (int)min(cfg.top_k_isotopes, 1000u)), ADB_MAX_ISOTOPES);
-  float* blk = P.cube + P.off[j];
+  const FPtr blk = dp_block(P, j);
   const bool experimental = cfg.experimental_xic != 0;
   const DpLayout l = dp_layout(F, nobs, C, nI, experimental, raw.n_ms1_pos);
-  const float* d = (staged ? staged : blk + l.dfi) + k;   // d[(o * C + c) * F]
-  const float* dmz = (staged ? staged + (l.dfm - l.dfi) : blk + l.dfm) + k;
-  float* b = blk + l.bp + k;          // b[c * F]
-  const float* sc = blk + l.sc;
-  int* fi = (int*)(blk + l.fi);
-  float* ff = blk + l.ff;
-  double* fd = (double*)(blk + l.fd);
+  const FPtr d = blk + (l.dfi + k);   // d[(o * C + c) * F]
+  const FPtr dmz = blk + (l.dfm + k);
+  const FPtr b = blk + (l.bp + k);    // b[c * F]
+  const FPtr sc = blk + l.sc;
+  const IPtr fi = dp_as_int(blk + l.fi);
+  const FPtr ff = blk + l.ff;
+  const DPtr fd = dp_as_double(blk + l.fd);
   const int64_t L = raw.cycle_len;
   const int64_t ci = dp_candidate_of(P, j);
   const int64_t frame_start = P.cand.frame_start[ci], frame_stop = P.cand.frame_stop[ci];
@@ -705,7 +760,7 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k, const float* staged
   }
   double a = 0, bsum = 0;
   if (cnt > 0) {
-    const double* wtab = (const double*)(blk + l.wtab);
+    const DPtr wtab = dp_as_double(blk + l.wtab);
     for (int o = 0; o < nobs; o++) {
       const double wv = (double)(((obs_mask >> o) & 1u) ? sc[SC_OI + o] : 0.0f) / ((double)wsum + 1e-20);
       if (wv > 0) {
@@ -727,7 +782,7 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k, const float* staged
 #define DP_FFP(o, c) ((!quant_all && (o) == best_obs) ? b[(c) * F] : dp_twice(d[((o) * C + (c)) * F]))
   if (experimental) {
     // fragments_frame_profile.sum(axis=1)
-    float* islr = blk + l.isl + k;
+    const FPtr islr = blk + (l.isl + k);
     if (nobs > 1)
       for (int c = 0; c < C; c++) { float t = 0.f; for (int o = 0; o < nobs; o++) t = t + DP_FFP(o, c); islr[c * F] = t; }
 #define DP_ISL(c) (nobs == 1 ? (quant_all ? dp_twice(d[(c) * F]) : b[(c) * F]) : islr[(c) * F])
@@ -738,7 +793,7 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k, const float* staged
     float t = 0.f;
     for (int c = a0; c < a1; c++) t = t + DP_ISL(c);
     const double cint = (double)t / (double)wnn;
-    float* nr = blk + l.nrm + k;
+    const FPtr nr = blk + (l.nrm + k);
     for (int c = 0; c < C; c++) {
       const float xv = DP_ISL(c);  // zero cells skip the fp64 division (0 / cint is the same signed zero)
       nr[c * F] = (cint > 0) ? ((xv == 0.f) ? xv : (float)((double)xv / cint)) : 0.f;
@@ -746,7 +801,7 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k, const float* staged
 #undef DP_ISL
   } else {
     // legacy (scoring/utils.py:513-571): centred profile and its std for every observation
-    float* cen = blk + l.nrm + k;  // cen[(o * C + c) * F]
+    const FPtr cen = blk + (l.nrm + k);  // cen[(o * C + c) * F]
     for (int o = 0; o < nobs; o++) {
       float s = 0.f;
       for (int c = 0; c < C; c++) s = s + DP_FFP(o, c);
@@ -757,11 +812,11 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k, const float* staged
     }
   }
   // template correlation (profile_features.py:82-85), cycle fwhm (:142-144), frame peak (:193-204)
-  const float* tfp = blk + l.tfp;
+  const FPtr tfp = blk + l.tfp;
   const float rt_width = raw.rt_values[frame_stop - 1] - raw.rt_values[frame_start];
   float tcorr = 0.f, fwhm = 0.f;
   for (int o = 0; o < nobs; o++) {
-    const float* y = tfp + o * C;
+    const FPtr y = tfp + o * C;
     const float ym = sc[SC_YM + o], ystd = sc[SC_YSTD + o];
     float xs = 0.f, mxv = 0.f;
     int am = 0;
@@ -795,7 +850,7 @@ ADB_HD void dp_fragment(const DpParams& P, int64_t j, int k, const float* staged
 }
 
 // masked fragment list of a slot: fmap[w] = k of the w-th fragment with signal; returns Fv
-ADB_HD int dp_fragment_mask(const int* fi, int F, uint8_t* fmap) {
+ADB_HD int dp_fragment_mask(IPtr fi, int F, uint8_t* fmap) {
   int Fv = 0;
   for (int k = 0; k < F; k++) if (fi[FI_VALID * F + k]) fmap[Fv++] = (uint8_t)k;
   return Fv;
@@ -808,13 +863,13 @@ ADB_HD void dp_median(const DpParams& P, int64_t j, int lane) {
   if (!P.state[j] || !P.cfg.experimental_xic) return;
   const int F = P.F[j], nobs = P.nobs[j], C = P.C[j];
   const int nI = min(min(P.lib.n_isotopes, (int)min(P.cfg.top_k_isotopes, 1000u)), ADB_MAX_ISOTOPES);
-  float* blk = P.cube + P.off[j];
+  const FPtr blk = dp_block(P, j);
   const DpLayout l = dp_layout(F, nobs, C, nI, true, P.raw.n_ms1_pos);
   uint8_t fmap[DP_MAXF];
-  const int Fv = dp_fragment_mask((const int*)(blk + l.fi), F, fmap);
+  const int Fv = dp_fragment_mask(dp_as_int(blk + l.fi), F, fmap);
   if (Fv < 2) return;
-  const float* nrm = blk + l.nrm;
-  float* med = blk + l.med;
+  const FPtr nrm = blk + l.nrm;
+  const FPtr med = blk + l.med;
   for (int c = lane; c < C; c += DP_MED_LANES) {
     float vlo = 0.f, vhi = 0.f;
     for (int w = 0; w < Fv; w++) {
@@ -846,19 +901,19 @@ ADB_HD void dp_corr(const DpParams& P, int64_t j, int k) {
   if (k >= F) return;
   const int nobs = P.nobs[j], C = P.C[j];
   const int nI = min(min(P.lib.n_isotopes, (int)min(cfg.top_k_isotopes, 1000u)), ADB_MAX_ISOTOPES);
-  float* blk = P.cube + P.off[j];
+  const FPtr blk = dp_block(P, j);
   const bool experimental = cfg.experimental_xic != 0;
   const DpLayout l = dp_layout(F, nobs, C, nI, experimental, P.raw.n_ms1_pos);
-  const int* fi = (const int*)(blk + l.fi);
+  const IPtr fi = dp_as_int(blk + l.fi);
   if (!fi[FI_VALID * F + k]) return;
-  float* ff = blk + l.ff;
-  const float* sc = blk + l.sc;
+  const FPtr ff = blk + l.ff;
+  const FPtr sc = blk + l.sc;
   if (experimental) {
-    const float* med = blk + l.med;
+    const FPtr med = blk + l.med;
     const bool quant_all = cfg.quant_all != 0;
-    const float* d = blk + l.dfi + k;
-    const float* b = blk + l.bp + k;
-    const float* islr = blk + l.isl + k;
+    const FPtr d = blk + (l.dfi + k);
+    const FPtr b = blk + (l.bp + k);
+    const FPtr islr = blk + (l.isl + k);
 #define DP_ISL(c) (nobs == 1 ? (quant_all ? dp_twice(d[(c) * F]) : b[(c) * F]) : islr[(c) * F])
     float sx = 0.f;
     for (int c = 0; c < C; c++) sx = sx + med[c];
@@ -887,8 +942,8 @@ ADB_HD void dp_corr(const DpParams& P, int64_t j, int k) {
   const int Fv = dp_fragment_mask(fi, F, fmap);
   if (Fv < 2) return;
   dp_masked_intensity(P, j, fmap, Fv, fint);
-  const float* cen = blk + l.nrm;
-  float* red = blk + l.red + k * F;  // row of fragment k, columns by fragment index
+  const FPtr cen = blk + l.nrm;
+  const FPtr red = blk + (l.red + k * F);  // row of fragment k, columns by fragment index
   for (int w = 0; w < Fv; w++) red[fmap[w]] = 0.f;
   for (int o = 0; o < nobs; o++) {
     const float rfa = ff[(FF_N + o) * F + k];
@@ -931,13 +986,13 @@ ADB_HD void dp_aggregate(const DpParams& P, int64_t j) {
   const adb_scoring_config& cfg = P.cfg;
   const int F = P.F[j], nobs = P.nobs[j], C = P.C[j];
   const int nI = min(min(lib.n_isotopes, (int)min(cfg.top_k_isotopes, 1000u)), ADB_MAX_ISOTOPES);
-  float* blk = P.cube + P.off[j];
+  const FPtr blk = dp_block(P, j);
   const bool experimental = cfg.experimental_xic != 0;
   const DpLayout l = dp_layout(F, nobs, C, nI, experimental, P.raw.n_ms1_pos);
-  int* fi = (int*)(blk + l.fi);
-  const float* ff = blk + l.ff;
-  const double* fd = (const double*)(blk + l.fd);
-  float* sc = blk + l.sc;
+  const IPtr fi = dp_as_int(blk + l.fi);
+  const FPtr ff = blk + l.ff;
+  const DPtr fd = dp_as_double(blk + l.fd);
+  const FPtr sc = blk + l.sc;
   uint8_t fmap[DP_MAXF], sorted_idx[DP_MAXF];
   float fint[DP_MAXF], fin[DP_MAXF];
   const int Fv = dp_fragment_mask(fi, F, fmap);
@@ -969,7 +1024,7 @@ ADB_HD void dp_aggregate(const DpParams& P, int64_t j) {
     ftype[w] = ADB_LD(lib.frag_type + g);
     fpos[w] = ADB_LD(lib.frag_position + g);
   }
-  float* fa = sc + SC_FEAT;
+  const FPtr fa = sc + SC_FEAT;
   fa[28] = (float)((double)Fv / (double)F);  // candidate.py:362
   bool anyh = false;  // a weighted-centre height > 0 exists: some (fragment, observation) row has signal; true for every masked fragment
   anyh = Fv > 0;
@@ -1019,7 +1074,7 @@ ADB_HD void dp_aggregate(const DpParams& P, int64_t j) {
     for (int r = 0; r < n3; r++) t = t + corr_list[sorted_idx[r]];
     fa[32] = (float)((double)t / (double)n3);
   } else {
-    const float* red = blk + l.red;
+    const FPtr red = blk + l.red;
     float t = 0.f;
     for (int a = 0; a < n3; a++)
       for (int b = 0; b < n3; b++) t = t + red[fmap[sorted_idx[a]] * F + fmap[sorted_idx[b]]];
@@ -1078,13 +1133,13 @@ ADB_HD void dp_write(const DpParams& P, int64_t j, int w) {
   const DevLib& lib = P.lib;
   const int F = P.F[j], nobs = P.nobs[j], C = P.C[j];
   const int nI = min(min(lib.n_isotopes, (int)min(P.cfg.top_k_isotopes, 1000u)), ADB_MAX_ISOTOPES);
-  const float* blk = P.cube + P.off[j];
+  const FPtr blk = dp_block(P, j);
   const DpLayout l = dp_layout(F, nobs, C, nI, P.cfg.experimental_xic != 0, P.raw.n_ms1_pos);
   const int Fv = (int)blk[l.sc + SC_FV];
   if (w >= Fv || w >= P.out_k) return;
-  const int* fi = (const int*)(blk + l.fi);
-  const float* ff = blk + l.ff;
-  const double* fd = (const double*)(blk + l.fd);
+  const IPtr fi = dp_as_int(blk + l.fi);
+  const FPtr ff = blk + l.ff;
+  const DPtr fd = dp_as_double(blk + l.fd);
   const int k = fi[FI_FMAP * F + w];
   const uint32_t g = P.fsel[j * P.KS + k];
   const size_t o = (size_t)dp_candidate_of(P, j) * (size_t)P.out_k + (size_t)w;

@@ -96,20 +96,20 @@ extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_
   P.nIcap = (int)std::min<int64_t>(std::min<int64_t>(lib.n_isotopes, cfg->top_k_isotopes), ADB_MAX_ISOTOPES);
   uint32_t status = 0;
   P.status = &status;
-  const size_t N = (size_t)std::max<int64_t>(batch, 1);
+  const size_t N = (size_t)dp_padded_slots(std::max<int64_t>(batch, 1));
   std::vector<uint8_t> state(N), F(N), nobs(N);
   std::vector<int32_t> C(N), cs(N);
   std::vector<uint16_t> pos(N * ADB_MAX_OBS);
   std::vector<uint32_t> fsel(N * (size_t)KS);
   std::vector<double> qtf(N * (size_t)P.nIcap * ADB_MAX_OBS);
   std::vector<float> qmask(N * ADB_MAX_OBS);
-  std::vector<int64_t> need(N + 1), off(N + 1);
+  std::vector<int64_t> need(N + 1), tile_need(N + 1), off(N + 1);
   std::vector<uint8_t> rowflag(N * (size_t)KS);
   std::vector<uint32_t> work(N * (size_t)KS);
   int32_t n_work = 0;
   P.rowflag = rowflag.data(); P.work = work.data(); P.n_work = &n_work;
   P.state = state.data(); P.F = F.data(); P.nobs = nobs.data(); P.C = C.data(); P.cs = cs.data(); P.pos = pos.data();
-  P.fsel = fsel.data(); P.qtf = qtf.data(); P.qmask = qmask.data(); P.need = need.data(); P.off = off.data();
+  P.fsel = fsel.data(); P.qtf = qtf.data(); P.qmask = qmask.data(); P.need = need.data(); P.tile_need = tile_need.data(); P.off = off.data();
   std::vector<double> wtab_p(2 * DP_WTAB_P_STRIDE);
   for (int t = 0; t < 2 * DP_WTAB_P_STRIDE; t++) wtab_p[(size_t)t] = dp_wtab_p_entry(t / DP_WTAB_P_STRIDE, t % DP_WTAB_P_STRIDE);
   P.wtab_p = wtab_p.data();
@@ -118,21 +118,33 @@ extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_
     P.base = base;
     P.n = std::min<int64_t>(batch, cand->n - base);
     for (int64_t j = 0; j < P.n; j++) dp_setup(P, j);
-    need[(size_t)P.n] = 0;
-    int64_t run = 0;
-    for (int64_t j = 0; j <= P.n; j++) { off[(size_t)j] = run; run += need[(size_t)j]; }
+    const int64_t n_tiles = (P.n + DP_W - 1) / DP_W, n_pad = n_tiles * DP_W;
+    int64_t run = 0;  // dp_tile_need_kernel + the exclusive scan
+    for (int64_t t = 0; t <= n_tiles; t++) {
+      int64_t m = 0;
+      for (int64_t j = t * DP_W; t < n_tiles && j < std::min<int64_t>((t + 1) * (int64_t)DP_W, P.n); j++) m = std::max(m, need[(size_t)j]);
+      off[(size_t)t] = run;
+      run += m * DP_W;
+    }
     cube.assign((size_t)run + 4, -12345.0f);  // poison: a pass that reads what no pass wrote shows up as a mismatch
     P.cube = cube.data();
-    const int rows = P.KS + P.nIcap;
-    for (int64_t t = 0; t < P.n * rows; t++) dp_extract(P, t / rows, (int)(t % rows));
-    for (int64_t j = 0; j < P.n; j++) dp_template(P, j);
+    const uint32_t rows = (uint32_t)(P.KS + P.nIcap), KS32 = (uint32_t)P.KS;
+    uint32_t j, r;
+    for (uint32_t t = 0; t < (uint32_t)(n_pad * rows); t++) {
+      dp_decode(t, rows, j, r);
+      if (j < P.n) dp_extract(P, j, (int)r);
+      else if (r < KS32) rowflag[dp_encode(j, r, KS32)] = 0;
+    }
+    for (int64_t jj = 0; jj < P.n; jj++) dp_template(P, jj);
     n_work = 0;  // cub::DeviceSelect::Flagged on the device
-    for (int64_t t = 0; t < P.n * P.KS; t++) if (rowflag[(size_t)t]) work[(size_t)n_work++] = (uint32_t)t;
-    for (int32_t t = 0; t < n_work; t++) dp_fragment(P, work[(size_t)t] / P.KS, (int)(work[(size_t)t] % P.KS));
-    if (cfg->experimental_xic) for (int64_t t = 0; t < P.n * DP_MED_LANES; t++) dp_median(P, t / DP_MED_LANES, (int)(t % DP_MED_LANES));
-    for (int32_t t = 0; t < n_work; t++) dp_corr(P, work[(size_t)t] / P.KS, (int)(work[(size_t)t] % P.KS));
-    for (int64_t j = 0; j < P.n; j++) dp_aggregate(P, j);
-    if (cfg->collect_fragments) for (int64_t t = 0; t < P.n * P.KS; t++) dp_write(P, t / P.KS, (int)(t % P.KS));
+    for (int64_t t = 0; t < n_pad * P.KS; t++) if (rowflag[(size_t)t]) work[(size_t)n_work++] = (uint32_t)t;
+    for (int32_t t = 0; t < n_work; t++) { dp_decode(work[(size_t)t], KS32, j, r); dp_fragment(P, j, (int)r); }
+    if (cfg->experimental_xic)
+      for (uint32_t t = 0; t < (uint32_t)(n_pad * DP_MED_LANES); t++) { dp_decode(t, DP_MED_LANES, j, r); if (j < P.n) dp_median(P, j, (int)r); }
+    for (int32_t t = 0; t < n_work; t++) { dp_decode(work[(size_t)t], KS32, j, r); dp_corr(P, j, (int)r); }
+    for (int64_t jj = 0; jj < P.n; jj++) dp_aggregate(P, jj);
+    if (cfg->collect_fragments)
+      for (uint32_t t = 0; t < (uint32_t)(n_pad * P.KS); t++) { dp_decode(t, KS32, j, r); if (j < P.n) dp_write(P, j, (int)r); }
   }
   if (status_out) *status_out = status;
   return 0;
