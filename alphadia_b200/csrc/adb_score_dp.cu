@@ -84,9 +84,29 @@ __global__ void __launch_bounds__(DP_THREADS) dp_corr_kernel(const __grid_consta
   dp_corr(P, j, (int)k);
 }
 
-__global__ void __launch_bounds__(DP_THREADS) dp_aggregate_kernel(const __grid_constant__ DpParams P) {
-  const int64_t j = (int64_t)blockIdx.x * DP_THREADS + threadIdx.x;
-  if (j < P.n) dp_aggregate(P, j);
+// thread <-> slot; the finished feature rows of a warp are staged in shared memory and written row by row with the 32 lanes
+// on consecutive floats (46 scattered 4-byte stores per thread were a quarter of this kernel's stall samples)
+constexpr int DPA_THREADS = 128;
+__global__ void __launch_bounds__(DPA_THREADS) dp_aggregate_kernel(const __grid_constant__ DpParams P) {
+  __shared__ float rows[DPA_THREADS / 32][32][ADB_NUM_FEATURES + 1];
+  const int64_t j = (int64_t)blockIdx.x * DPA_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool scored = false;
+  if (j < P.n) {
+    dp_aggregate(P, j, rows[warp][lane]);
+    scored = P.state[j] == 2;
+  }
+  const long long ci = scored ? (long long)dp_candidate_of(P, j) : -1;
+  __syncwarp();  // the staged rows are visible to the whole warp
+  unsigned m = __ballot_sync(0xFFFFFFFFu, scored);
+  while (m) {
+    const int r = __ffs(m) - 1;
+    m &= m - 1;
+    const long long row = __shfl_sync(0xFFFFFFFFu, ci, r);
+    float* dst = P.out.features + (size_t)row * ADB_NUM_FEATURES;
+    dst[lane] = rows[warp][r][lane];
+    if (lane + 32 < ADB_NUM_FEATURES) dst[lane + 32] = rows[warp][r][lane + 32];
+  }
 }
 
 __global__ void __launch_bounds__(DP_THREADS) dp_write_kernel(const __grid_constant__ DpParams P) {
@@ -182,7 +202,7 @@ int adb_launch_score_dp(const DevRaw& raw, const DevLib& lib, const adb_scoring_
     dp_fragment_kernel<<<blocks_for(n_pad * P.KS), DP_THREADS, 0, stream>>>(P);
     if (cfg.experimental_xic) dp_median_kernel<<<blocks_for(n_pad * DP_MED_LANES), DP_THREADS, 0, stream>>>(P);
     dp_corr_kernel<<<blocks_for(n_pad * P.KS), DP_THREADS, 0, stream>>>(P);
-    dp_aggregate_kernel<<<blocks_for(P.n), DP_THREADS, 0, stream>>>(P);
+    dp_aggregate_kernel<<<(unsigned)((P.n + DPA_THREADS - 1) / DPA_THREADS), DPA_THREADS, 0, stream>>>(P);
     if (cfg.collect_fragments) dp_write_kernel<<<blocks_for(n_pad * P.KS), DP_THREADS, 0, stream>>>(P);
     if (n_launches) *n_launches += 10 + (cfg.experimental_xic ? 1 : 0) + (cfg.collect_fragments ? 1 : 0);
   }

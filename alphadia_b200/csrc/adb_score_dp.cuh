@@ -980,7 +980,9 @@ ADB_HD double dp_corrcoef01(const double* x, const float* yf, int n) {
 // ------------------------------------------------------------------------------------------------------------------
 // dp_aggregate: fragment_features.py:337-427, profile_features.py aggregates, candidate.py:362,475-481
 // ------------------------------------------------------------------------------------------------------------------
-ADB_HD void dp_aggregate(const DpParams& P, int64_t j) {
+// `stage`: when given, the finished feature row goes there instead of straight into the output table (the kernel then
+// writes the rows of a warp cooperatively, full sectors instead of 46 scattered 4-byte stores per thread)
+ADB_HD void dp_aggregate(const DpParams& P, int64_t j, float* stage = nullptr) {
   if (!P.state[j]) return;
   const DevLib& lib = P.lib;
   const adb_scoring_config& cfg = P.cfg;
@@ -1118,7 +1120,11 @@ ADB_HD void dp_aggregate(const DpParams& P, int64_t j) {
   }
   // candidate.py:475-481
   const int64_t ci = dp_candidate_of(P, j);
-  for (int t = 0; t < ADB_NUM_FEATURES; t++) P.out.features[(size_t)ci * ADB_NUM_FEATURES + t] = fa[t];
+  if (stage) {
+    for (int t = 0; t < ADB_NUM_FEATURES; t++) stage[t] = fa[t];
+  } else {
+    for (int t = 0; t < ADB_NUM_FEATURES; t++) P.out.features[(size_t)ci * ADB_NUM_FEATURES + t] = fa[t];
+  }
   P.out.valid[ci] = 1;
   for (int w = 0; w < Fv; w++) fi[FI_FMAP * F + w] = fmap[w];
   sc[SC_FV] = (float)Fv;
