@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "adb_library_create", "adb_library_destroy",
     "adb_select_candidates", "adb_score_candidates", "adb_score_candidates_ragged", "adb_fragment_competition", "adb_transpose_csr",
     "adb_q_values", "adb_keep_best", "adb_classifier_predict_proba",
-    "adb_select_candidates_resident", "adb_score_candidates_resident",
+    "adb_select_candidates_resident", "adb_score_candidates_resident", "adb_select_score_candidates_ragged",
     "adb_fetch_candidates", "adb_fetch_candidate_table", "adb_fetch_scores", "adb_resident_score_table",
     "adb_last_timing", "adb_kernel_launches", "adb_last_main_kernel_ms",
 ]
@@ -207,6 +207,28 @@ def score_candidates_ragged(dev_raw: DeviceRawFile, dev_lib: DeviceLibrary, cfg_
           "adb_score_candidates_ragged")
     nr, nf = int(rd.n_rows), int(rd.n_fragments)
     out = dict(n_rows=nr, n_fragments=nf, row_index=bufs["row_index"][:nr], features=bufs["features"][:nr],
+               frag_offset=bufs["frag_offset"][:nr + 1])
+    for k in _abi.FRAG_F32 + _abi.FRAG_U8:
+        out[k] = bufs[k][:nf]
+    return out
+
+
+def select_score_candidates_ragged(dev_raw, dev_lib, sel_struct, kernel, score_struct, table: dict, bufs: dict,
+                                   score_cutoff: float = float("-inf")) -> dict:
+    """Selection + score cutoff + scoring in one call (``adb_select_score_candidates_ragged``): fills the candidate table
+    ``table`` (``_abi.alloc_candidate_table(capacity)``) and the ragged result buffers ``bufs``; returns the views of
+    ``score_candidates_ragged`` plus ``n_candidates``."""
+    lib = load()
+    kernel = np.ascontiguousarray(kernel, dtype=np.float32)
+    cap = int(table["lib_row"].shape[0])
+    t = _abi.candidate_table_struct(table, cap)
+    rd = _abi.scores_ragged_struct(bufs)
+    check(lib.adb_select_score_candidates_ragged(dev_raw.handle, dev_lib.handle, C.byref(sel_struct), _abi.ptr(kernel),
+                                                 C.c_int32(kernel.shape[0]), C.c_int32(kernel.shape[1]), C.c_float(score_cutoff),
+                                                 C.byref(score_struct), C.byref(t), C.byref(rd)),
+          "adb_select_score_candidates_ragged")
+    nr, nf = int(rd.n_rows), int(rd.n_fragments)
+    out = dict(n_candidates=int(t.n), n_rows=nr, n_fragments=nf, row_index=bufs["row_index"][:nr], features=bufs["features"][:nr],
                frag_offset=bufs["frag_offset"][:nr + 1])
     for k in _abi.FRAG_F32 + _abi.FRAG_U8:
         out[k] = bufs[k][:nf]

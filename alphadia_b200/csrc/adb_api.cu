@@ -18,13 +18,16 @@
 #define ADB_SCORE_DP_BATCH_MAX (1 << 22)  // candidates per batch of the data-parallel scoring passes (x 72 rows < 2^32)
 #endif
 #ifndef ADB_SCORE_BLOCKS
-#define ADB_SCORE_BLOCKS 4  // row blocks of a scoring call whose D2H overlaps the next block's kernel (<= 7)
+#define ADB_SCORE_BLOCKS 4  // row blocks of a scoring call whose D2H overlaps the next block's kernel (<= ADB_MAX_BLOCKS)
 #endif
 #ifndef ADB_RAGGED_BLOCKS
-#define ADB_RAGGED_BLOCKS 7  // same for ragged results: a block's copy starts one block late (<= 7)
+#define ADB_RAGGED_BLOCKS 5  // same for ragged results: a block's copy starts one block late (<= ADB_MAX_BLOCKS)
 #endif
 #ifndef ADB_RAGGED_BLOCK_RATIO
-#define ADB_RAGGED_BLOCK_RATIO 0.6  // size of block k + 1 relative to block k
+#define ADB_RAGGED_BLOCK_RATIO 0.7  // size of block k + 1 relative to block k
+#endif
+#ifndef ADB_MAX_BLOCKS
+#define ADB_MAX_BLOCKS 15  // 4 key bits
 #endif
 
 namespace {
@@ -144,14 +147,14 @@ struct adb_rawfile {
   const uint32_t* d_cand_pidx = nullptr;  // compacted precursor_idx / score of the resident candidates
   const float* d_cand_score = nullptr;
   cudaStream_t copy_stream = nullptr;     // D2H of finished scoring chunks overlaps the next chunk's kernel
-  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t chunk_ev[ADB_MAX_BLOCKS + 1] = {};  // [ADB_MAX_BLOCKS]: end-of-copies marker
   DevScoresOut d_scores{};
   int64_t scores_n = 0;
   int scores_k = 0;
   // ragged results (adb_score_candidates_ragged): device-compacted tables + per-block running totals
   DeviceBuffer rag_rows, rag_frags, rag_scan, rag_scan_tmp, rag_tot;
   int64_t* rag_host_tot = nullptr;  // pinned [2 * (ADB_RAGGED_MAX_BLOCKS + 1)]
-  cudaEvent_t rag_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t rag_ev[ADB_MAX_BLOCKS + 1] = {};
 };
 
 namespace {
@@ -297,7 +300,7 @@ __global__ void order_key_kernel(DevRaw raw, DevLib lib, uint64_t* keys, int32_t
 // processing order of the candidates: (output row block, quad window, time bucket of 32 cycles, cost class).  Candidates
 // that are resident together read the same spectra (L2 reuse) and the candidates of one CTA round cost about the same
 // (the scoring kernel runs its tiles in lock step).  Results do not depend on the order (disjoint output rows).
-struct RowBlocks { int n; int64_t start[9]; };  // row blocks [start[k], start[k + 1]) of a scoring call
+struct RowBlocks { int n; int64_t start[ADB_MAX_BLOCKS + 2]; };  // row blocks [start[k], start[k + 1]) of a scoring call
 
 __global__ void score_order_key_kernel(DevRaw raw, DevLib lib, DevCandidatesIn cand, RowBlocks blocks, int n_iso,
                                        uint64_t* keys, int32_t* vals) {
@@ -740,7 +743,7 @@ int run_selection(adb_rawfile* raw, adb_library* lib, const adb_selection_config
   return 0;
 }
 
-int run_compaction(adb_rawfile* raw) {
+int run_compaction(adb_rawfile* raw, float score_cutoff = -INFINITY) {
   cudaStream_t st = raw->stream;
   const int64_t rows = raw->cont_rows;
   if (raw->flags.reserve(sizeof(int) * (size_t)std::max<int64_t>(rows, 1))) return 1;
@@ -753,7 +756,7 @@ int run_compaction(adb_rawfile* raw) {
   CUDA_TRY(cudaMemsetAsync(raw->count.ptr, 0, sizeof(int64_t), st));
   adb_launch_compact_ex(raw->d_cont, raw->cont_count, raw->flags.as<int>(), raw->offs.as<int>(), raw->scan_tmp.ptr, tmp,
                         c.lib_row, c.rank, c.scan_start, c.scan_stop, c.scan_center, c.frame_start, c.frame_stop,
-                        c.frame_center, c.precursor_idx, c.score, raw->count.as<int64_t>(), st, &raw->launches);
+                        c.frame_center, c.precursor_idx, c.score, raw->count.as<int64_t>(), st, &raw->launches, score_cutoff);
   raw->d_cand_pidx = c.precursor_idx;
   raw->d_cand_score = c.score;
   CUDA_TRY(cudaGetLastError());
@@ -882,8 +885,8 @@ int ragged_begin(adb_rawfile* raw, RaggedRun& R, int64_t n, int k) {
   cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)N);
   if (raw->rag_scan_tmp.reserve(tmp + 256)) return 1;
   if (!raw->rag_host_tot) {
-    CUDA_TRY(cudaHostAlloc((void**)&raw->rag_host_tot, sizeof(int64_t) * 2 * 9, cudaHostAllocDefault));
-    for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreateWithFlags(&raw->rag_ev[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaHostAlloc((void**)&raw->rag_host_tot, sizeof(int64_t) * 2 * (ADB_MAX_BLOCKS + 2), cudaHostAllocDefault));
+    for (int i = 0; i <= ADB_MAX_BLOCKS; i++) CUDA_TRY(cudaEventCreateWithFlags(&raw->rag_ev[i], cudaEventDisableTiming));
   }
   R.dev = carve_ragged(raw->rag_rows.ptr, raw->rag_frags.ptr, N, k);
   CUDA_TRY(cudaMemsetAsync(raw->rag_tot.ptr, 0, 256, raw->stream));
@@ -1030,20 +1033,26 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
   // processing order: (quad window of the precursor, frame_start) so that co-resident tiles read the same
   // spectra; results do not depend on it (disjoint output rows)
   int32_t* d_order = nullptr;
-  const int n_chunks = ((host_out || rag) && n >= 200000) ? (rag ? ADB_RAGGED_BLOCKS : ADB_SCORE_BLOCKS) : 1;
-  // row blocks: equal for the dense tables; geometric (ratio 0.6 = copy time / scoring time of a block) for the ragged
-  // result, whose copy starts one block late - every copy then hides behind the next, smaller block and the un-overlapped
-  // tail is the copy of the last two (smallest) blocks
+  int n_chunks = ((host_out || rag) && n >= 200000) ? (rag ? ADB_RAGGED_BLOCKS : ADB_SCORE_BLOCKS) : 1;
+  double block_ratio = ADB_RAGGED_BLOCK_RATIO;
+  if (rag && n_chunks > 1) {  // tuning knobs
+    if (const char* e = getenv("ADB_RAGGED_BLOCKS_N")) n_chunks = std::max(1, std::min(atoi(e), (int)ADB_MAX_BLOCKS));
+    if (const char* e = getenv("ADB_RAGGED_RATIO")) block_ratio = std::max(0.1, std::min(atof(e), 2.0));
+  }
+  // row blocks: equal for the dense tables; geometrically shrinking for the ragged result, whose copy starts one block
+  // late - every copy hides behind the next block and the un-overlapped tail is the copy of the last, smallest blocks.
+  // Measured on config 3 (fused call, ms per e2e step): 3 blocks / ratio 0.6: 160.8, 4 / 0.7: 158.2, 5 / 0.7: 157.4, 6 / 0.7: 157.2,
+  // 6 / 0.8: 159.7, 7 / 0.6: 162.6, 8 / 0.9: 162.1, 12 / 0.95: 165.5, 15 / 1.0: 168.5 - every block costs about a millisecond
   RowBlocks blocks{};
   blocks.n = n_chunks;
   {
-    double w[8], tot = 0;
-    for (int k = 0; k < n_chunks; k++) { w[k] = rag ? pow(ADB_RAGGED_BLOCK_RATIO, k) : 1.0; tot += w[k]; }
+    double w[ADB_MAX_BLOCKS + 1], tot = 0;
+    for (int k = 0; k < n_chunks; k++) { w[k] = rag ? pow(block_ratio, k) : 1.0; tot += w[k]; }
     double acc = 0;
     for (int k = 0; k < n_chunks; k++) { blocks.start[k] = std::min<int64_t>((int64_t)(acc / tot * (double)n), n); acc += w[k]; }
     blocks.start[0] = 0;
     blocks.start[n_chunks] = n;
-    for (int k = n_chunks + 1; k < 9; k++) blocks.start[k] = n;
+    for (int k = n_chunks + 1; k < ADB_MAX_BLOCKS + 2; k++) blocks.start[k] = n;
   }
   if (n > 1 && n < 2000000000LL) {
     if (raw->order_keys.reserve(sizeof(uint64_t) * 2 * (size_t)n)) return 1;
@@ -1094,8 +1103,8 @@ int run_scoring(adb_rawfile* raw, adb_library* lib, const adb_scoring_config* cf
     if (rag && ragged_copy_blocks(raw, *rag, rag->n_blocks, raw->copy_stream)) return 1;
     CUDA_TRY(cudaEventRecord(raw->ev[5], st));
     CUDA_TRY(cudaEventRecord(raw->ev[2], st));
-    CUDA_TRY(cudaEventRecord(raw->chunk_ev[7], raw->copy_stream));
-    CUDA_TRY(cudaStreamWaitEvent(st, raw->chunk_ev[7], 0));  // the handle's stream is done when the copies are
+    CUDA_TRY(cudaEventRecord(raw->chunk_ev[ADB_MAX_BLOCKS], raw->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, raw->chunk_ev[ADB_MAX_BLOCKS], 0));  // the handle's stream is done when the copies are
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1155,7 +1164,7 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
   CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&r->ev[i]));
   CUDA_TRY(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreateWithFlags(&r->chunk_ev[i], cudaEventDisableTiming));
+  for (int i = 0; i <= ADB_MAX_BLOCKS; i++) CUDA_TRY(cudaEventCreateWithFlags(&r->chunk_ev[i], cudaEventDisableTiming));
   cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, device);
   DevRaw& v = r->dev;
   double* cyc; float *rt, *mob, *mz, *it; int64_t *ps, *pe;
@@ -1322,7 +1331,7 @@ int adb_rawfile4d_create(const adb_rawfile4d_desc* d, int device, adb_rawfile_t*
   CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
   for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&r->ev[i]));
   CUDA_TRY(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreateWithFlags(&r->chunk_ev[i], cudaEventDisableTiming));
+  for (int i = 0; i <= ADB_MAX_BLOCKS; i++) CUDA_TRY(cudaEventCreateWithFlags(&r->chunk_ev[i], cudaEventDisableTiming));
   cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, device);
   DevRaw4& v = r->dev4;
   double *cyc, *rt, *mob, *mz; int64_t *dpc, *ip; uint32_t* push; uint16_t* it;
@@ -1364,7 +1373,7 @@ void adb_rawfile_destroy(adb_rawfile_t* r) {
                           &r->flags, &r->offs, &r->scan_tmp, &r->count, &r->scores, &r->score_ws, &r->dp_plan, &r->staging, &r->extent};
   for (DeviceBuffer* b : bufs) b->release();
   for (int i = 0; i < 6; i++) if (r->ev[i]) cudaEventDestroy(r->ev[i]);
-  for (int i = 0; i < 8; i++) if (r->chunk_ev[i]) cudaEventDestroy(r->chunk_ev[i]);
+  for (int i = 0; i <= ADB_MAX_BLOCKS; i++) if (r->chunk_ev[i]) cudaEventDestroy(r->chunk_ev[i]);
   if (r->copy_stream) { cudaStreamSynchronize(r->copy_stream); cudaStreamDestroy(r->copy_stream); }
   if (r->stream) cudaStreamDestroy(r->stream);
   delete r;
@@ -1469,12 +1478,10 @@ int adb_fetch_candidates(adb_rawfile_t* raw, adb_candidates_out* out) {
   return 0;
 }
 
-int adb_fetch_candidate_table(adb_rawfile_t* raw, adb_candidate_table* out) {
-  if (!raw || !out) return fail("null argument");
-  if (out->n != raw->n_cand) return fail("candidate table size mismatch (expected the count returned by adb_select_candidates_resident)");
-  if (!raw->d_cand_pidx) return fail("no resident candidate table (call adb_select_candidates_resident first)");
-  if (set_device(raw->device)) return 1;
-  cudaStream_t st = raw->stream;
+}  // extern "C"
+namespace {
+// asynchronous D2H of the resident candidate table on `st`
+int copy_candidate_table(adb_rawfile* raw, adb_candidate_table* out, cudaStream_t st) {
   const size_t N = (size_t)raw->n_cand;
   const DevCandidatesIn& c = raw->d_cand;
   if (N > 0) {
@@ -1489,7 +1496,18 @@ int adb_fetch_candidate_table(adb_rawfile_t* raw, adb_candidate_table* out) {
     CUDA_TRY(cudaMemcpyAsync(out->precursor_idx, raw->d_cand_pidx, 4 * N, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(out->score, raw->d_cand_score, 4 * N, cudaMemcpyDeviceToHost, st));
   }
-  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+}  // namespace
+extern "C" {
+
+int adb_fetch_candidate_table(adb_rawfile_t* raw, adb_candidate_table* out) {
+  if (!raw || !out) return fail("null argument");
+  if (out->n != raw->n_cand) return fail("candidate table size mismatch (expected the count returned by adb_select_candidates_resident)");
+  if (!raw->d_cand_pidx) return fail("no resident candidate table (call adb_select_candidates_resident first)");
+  if (set_device(raw->device)) return 1;
+  if (copy_candidate_table(raw, out, raw->stream)) return 1;
+  CUDA_TRY(cudaStreamSynchronize(raw->stream));
   return 0;
 }
 
@@ -1589,6 +1607,46 @@ int adb_score_candidates_ragged(adb_rawfile_t* raw, adb_library_t* lib, const ad
   out->n_fragments = raw->rag_host_tot[2 * R.n_blocks + 1];
   if (R.overflow || out->n_rows > out->row_capacity || out->n_fragments > out->frag_capacity)
     return fail("adb_score_candidates_ragged: output capacity too small (needs " + std::to_string(out->n_rows) + " rows, " +
+                std::to_string(out->n_fragments) + " fragment entries)");
+  out->frag_offset[out->n_rows] = out->n_fragments;
+  return 0;
+}
+
+int adb_select_score_candidates_ragged(adb_rawfile_t* raw, adb_library_t* lib, const adb_selection_config* sel_cfg, const float* kernel,
+                                       int32_t kh, int32_t kw, float score_cutoff, const adb_scoring_config* cfg,
+                                       adb_candidate_table* table, adb_scores_ragged* out) {
+  if (!raw || !lib || !sel_cfg || !kernel || !cfg || !out) return fail("null argument");
+  if (run_selection(raw, lib, sel_cfg, kernel, kh, kw)) return 1;
+  if (run_compaction(raw, score_cutoff)) return 1;
+  if (check_status(raw, "adb_select_score_candidates_ragged (selection)")) return 1;
+  cudaStream_t st = raw->stream;
+  if (table) {
+    if (table->n < raw->n_cand) {
+      const int64_t need = raw->n_cand;
+      table->n = need;
+      return fail("adb_select_score_candidates_ragged: candidate table capacity too small (needs " + std::to_string(need) + " rows)");
+    }
+    table->n = raw->n_cand;
+    // the table travels on the copy stream while the first scoring block runs
+    CUDA_TRY(cudaEventRecord(raw->chunk_ev[ADB_MAX_BLOCKS], st));
+    CUDA_TRY(cudaStreamWaitEvent(raw->copy_stream, raw->chunk_ev[ADB_MAX_BLOCKS], 0));
+    if (copy_candidate_table(raw, table, raw->copy_stream)) return 1;
+  }
+  int64_t s_max = 0, f_max = 0;
+  if (resident_extents(raw, &s_max, &f_max)) return 1;
+  const int64_t c_max = raw->is4d ? f_max : f_max / raw->dev.cycle_len + 1;
+  if (!raw->is4d && c_max > 4096) return fail("a candidate spans more than 4096 cycles");
+  RaggedRun R;
+  R.out = out;
+  out->n_rows = out->n_fragments = 0;
+  if (run_scoring(raw, lib, cfg, c_max, s_max, nullptr, &R)) return 1;
+  CUDA_TRY(cudaEventRecord(raw->ev[3], st));
+  if (check_status(raw, "adb_select_score_candidates_ragged")) return 1;
+  CUDA_TRY(cudaStreamSynchronize(raw->copy_stream));
+  out->n_rows = raw->rag_host_tot[2 * R.n_blocks];
+  out->n_fragments = raw->rag_host_tot[2 * R.n_blocks + 1];
+  if (R.overflow || out->n_rows > out->row_capacity || out->n_fragments > out->frag_capacity)
+    return fail("adb_select_score_candidates_ragged: output capacity too small (needs " + std::to_string(out->n_rows) + " rows, " +
                 std::to_string(out->n_fragments) + " fragment entries)");
   out->frag_offset[out->n_rows] = out->n_fragments;
   return 0;

@@ -222,7 +222,7 @@ void adb_launch_compact_ex(DevCandidatesOut cont, int64_t candidate_count, int* 
                            size_t tmp_bytes, int64_t* d_lib_row, uint8_t* d_rank, int64_t* d_scan_start,
                            int64_t* d_scan_stop, int64_t* d_scan_center, int64_t* d_frame_start, int64_t* d_frame_stop,
                            int64_t* d_frame_center, uint32_t* d_precursor_idx, float* d_score, int64_t* d_count,
-                           cudaStream_t stream, int* n_launches);
+                           cudaStream_t stream, int* n_launches, float score_cutoff = -INFINITY);
 
 // ---- small device helpers ------------------------------------------------------------------
 __device__ __forceinline__ int64_t adb_lower_bound(const float* __restrict__ a, int64_t lo, int64_t hi, float v) {

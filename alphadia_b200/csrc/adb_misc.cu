@@ -195,9 +195,11 @@ __global__ void fc_resolve_kernel(int64_t n_windows, const int64_t* __restrict__
   }
 }
 
-__global__ void adb_flag_kernel(const float* __restrict__ score, int64_t n, int* __restrict__ flags) {
+__global__ void adb_flag_kernel(const float* __restrict__ score, int64_t n, float cutoff, int* __restrict__ flags) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) flags[t] = score[t] > 0.f;  // CandidateContainer.get_candidate_df_data, config_df.py:270-284
+  // CandidateContainer.get_candidate_df_data, config_df.py:270-284 (score > 0), optionally followed by the handler's score
+  // cutoff (extraction_handler.py:177-202, score > cutoff on the float32 column)
+  if (t < n) flags[t] = score[t] > 0.f && score[t] > cutoff;
 }
 
 __global__ void adb_scatter_kernel(DevCandidatesOut c, int64_t candidate_count, const int* __restrict__ flags,
@@ -333,10 +335,10 @@ void adb_launch_compact_ex(DevCandidatesOut cont, int64_t candidate_count, int* 
                            size_t tmp_bytes, int64_t* d_lib_row, uint8_t* d_rank, int64_t* d_scan_start,
                            int64_t* d_scan_stop, int64_t* d_scan_center, int64_t* d_frame_start, int64_t* d_frame_stop,
                            int64_t* d_frame_center, uint32_t* d_precursor_idx, float* d_score, int64_t* d_count,
-                           cudaStream_t stream, int* n_launches) {
+                           cudaStream_t stream, int* n_launches, float score_cutoff) {
   if (cont.n_rows <= 0) return;
   unsigned blocks = (unsigned)((cont.n_rows + 255) / 256);
-  adb_flag_kernel<<<blocks, 256, 0, stream>>>(cont.score, cont.n_rows, d_flags);
+  adb_flag_kernel<<<blocks, 256, 0, stream>>>(cont.score, cont.n_rows, score_cutoff, d_flags);
   cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_flags, d_offs, (int)cont.n_rows, stream);
   adb_scatter_kernel<<<blocks, 256, 0, stream>>>(cont, candidate_count, d_flags, d_offs, d_lib_row, d_rank, d_scan_start,
                                                  d_scan_stop, d_scan_center, d_frame_start, d_frame_stop, d_frame_center,

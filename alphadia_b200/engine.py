@@ -57,12 +57,15 @@ class HotPath:
         return dict(features=f.value, valid=v.value, lib_row=r.value, rank=k.value, n=int(n.value))
 
     # ---- host buffers (the operator path) -----------------------------------------------------------
-    def host_step(self, alloc=np.zeros, ragged: bool = True) -> dict:
+    def host_step(self, alloc=np.zeros, ragged: bool = True, fused: bool = False) -> dict:
         """What the reference-facing operators do, with caller-provided (pinned) host memory:
         library batch H2D -> selection -> compacted candidate table D2H (CandidateSelection's DataFrame columns)
         -> candidate table H2D -> scoring -> score + fragment tables D2H (row blocks overlap the scoring kernel).
         ``ragged`` (default): the result is the device-compacted form of ``adb_score_candidates_ragged`` (valid feature
         rows + kept fragment slots); otherwise the dense ``[n, top_k]`` tables of ``adb_score_candidates``.
+        ``fused``: selection and scoring in ONE C-ABI call (``adb_select_score_candidates_ragged``, the workflow's
+        select_candidates -> score_and_quantify_candidates pair): the candidate table is copied to the host while the first
+        scoring block runs and is not uploaded again.
         ``alloc(shape, dtype) -> ndarray`` lets the caller provide pinned host memory."""
         import time
 
@@ -89,6 +92,26 @@ class HotPath:
         dev_lib = _lib.DeviceLibrary(self._host_bufs["lib"], device=self.dev_raw.device)
         h2d = sum(int(v.nbytes) for v in self.lib_arrays.values())
         lap("library_upload")
+        if fused:
+            try:
+                per = max(1, min(self.top_k, self.max_lib_fragments))
+                if self._host_bufs["scores"] is None or self._host_bufs["scores_n"] < n_rows or not self._host_bufs.get("ragged"):
+                    _, sc = _abi.alloc_scores_ragged(n_rows, n_rows * per, alloc)
+                    self._host_bufs["scores"], self._host_bufs["scores_n"], self._host_bufs["ragged"] = sc, n_rows, True
+                sc = self._host_bufs["scores"]
+                lap("host_glue")
+                res = _lib.select_score_candidates_ragged(self.dev_raw, dev_lib, self.sel_struct, self.kernel, self.score_struct,
+                                                          table, sc)
+                lap("select_score_call")
+            finally:
+                dev_lib.close()
+            n = res["n_candidates"]
+            self.n_candidates = n
+            lap("library_free")
+            t_phase["total"] = (time.perf_counter() - t_enter) * 1e3
+            d2h = n * (7 * 8 + 1 + 4 + 4) + res["n_rows"] * (_abi.NUM_FEATURES * 4 + 16) + 8 + res["n_fragments"] * (7 * 4 + 5)
+            return dict(n_candidates=n, h2d_bytes=h2d, d2h_bytes=d2h, valid=res["n_rows"], n_fragments=res["n_fragments"],
+                        phases_ms=t_phase)
         try:
             n = _lib.select_candidates_resident(self.dev_raw, dev_lib, self.sel_struct, self.kernel)
             t_phase["select_call_device"] = dict(self.dev_raw.last_timing())

@@ -447,6 +447,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("ADB_BENCH_WORKLOAD", "config3"))
     ap.add_argument("--precursors", type=int, default=None, help="override the library size (debugging)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-two-calls", action="store_true", help="e2e with separate selection and scoring calls: the candidate table goes to the host and is uploaded again (A/B)")
     ap.add_argument("--e2e-dense", action="store_true", help="e2e with the dense [n, top_k] result tables of adb_score_candidates (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-operator", action="store_true", help="skip the DataFrame-level operator measurement")
@@ -548,10 +549,11 @@ def main():
 
     # ---- e2e through the C ABI with pinned host buffers ------------------------------------------
     alloc = pinned_alloc_factory()
-    hp.host_step(alloc, ragged=not args.e2e_dense)  # warm-up: allocates the pinned buffers
+    fused = not (args.e2e_dense or args.e2e_two_calls)
+    hp.host_step(alloc, ragged=not args.e2e_dense, fused=fused)  # warm-up: allocates the pinned buffers
     barrier()
     t0 = time.perf_counter()
-    e2e_stats = [hp.host_step(alloc, ragged=not args.e2e_dense) for _ in range(args.e2e_steps)]
+    e2e_stats = [hp.host_step(alloc, ragged=not args.e2e_dense, fused=fused) for _ in range(args.e2e_steps)]
     barrier()
     t_e2e = time.perf_counter() - t0
     t_e = torch.tensor([t_e2e, float(e2e_stats[-1]["n_candidates"])], dtype=torch.float64, device="cuda")
@@ -638,12 +640,16 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_stats[-1]["h2d_bytes"],
                     "d2h_bytes_per_step": e2e_stats[-1]["d2h_bytes"], "steps": args.e2e_steps,
                     "valid_rows": e2e_stats[-1]["valid"], "fragment_rows": e2e_stats[-1]["n_fragments"],
-                    "path": ("adb_library_create (H2D) + adb_select_candidates_resident + adb_fetch_candidate_table (D2H) + "
-                             + ("adb_score_candidates (candidate table H2D, dense score/fragment tables D2H in 4 row blocks overlapped with the kernel)"
-                                if args.e2e_dense else
-                                "adb_score_candidates_ragged (candidate table H2D; feature rows of the valid candidates + their kept fragment slots, "
-                                "compacted on the device per row block and copied while the next block is scored)")
-                             + ", pinned host buffers")},
+                    "path": (("adb_library_create (H2D) + adb_select_score_candidates_ragged (selection, candidate table D2H while the first "
+                              "scoring block runs, scoring from the resident table; feature rows of the valid candidates + their kept "
+                              "fragment slots compacted on the device per row block and copied while the next block is scored)")
+                             if fused else
+                             ("adb_library_create (H2D) + adb_select_candidates_resident + adb_fetch_candidate_table (D2H) + "
+                              + ("adb_score_candidates (candidate table H2D, dense score/fragment tables D2H in 4 row blocks overlapped with the kernel)"
+                                 if args.e2e_dense else
+                                 "adb_score_candidates_ragged (candidate table H2D; feature rows of the valid candidates + their kept fragment slots, "
+                                 "compacted on the device per row block and copied while the next block is scored)")))
+                            + ", pinned host buffers"},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }

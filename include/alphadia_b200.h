@@ -328,6 +328,17 @@ typedef struct {
   float* score;
 } adb_candidate_table;
 int adb_fetch_candidate_table(adb_rawfile_t* raw, adb_candidate_table* out);
+/* Selection and scoring of one library batch in ONE call - what the workflow does back to back
+ * (alphadia/workflow/peptidecentric/peptidecentric.py:196-207: extraction_handler.select_candidates(apply_cutoff=True) ->
+ * extraction_handler.score_and_quantify_candidates(candidates_df, ...)): candidate selection, the `score > 0` filter of
+ * candidate_container_to_df (config_df.py:270-298) and the handler's score cutoff (`score > score_cutoff` on the float32
+ * column, extraction_handler.py:177-202; pass -INFINITY for none), scoring of the surviving candidates from the resident
+ * table.  `table` (host, capacity in table->n, row count out) receives the candidate table while the first scoring block
+ * runs and may be NULL; `out` is the ragged result of adb_score_candidates_ragged, its row_index refers to `table`. */
+int adb_select_score_candidates_ragged(adb_rawfile_t* raw, adb_library_t* lib, const adb_selection_config* sel_cfg,
+                                       const float* kernel, int32_t kernel_h, int32_t kernel_w, float score_cutoff,
+                                       const adb_scoring_config* score_cfg, adb_candidate_table* table,
+                                       adb_scores_ragged* out);
 /* scores the resident candidates; outputs stay on the device */
 int adb_score_candidates_resident(adb_rawfile_t* raw, adb_library_t* lib, const adb_scoring_config* cfg);
 /* D2H of the resident results: the full candidate container (n_precursors * candidate_count rows) ... */

@@ -1198,3 +1198,37 @@ def test_full_size_benchmark_workloads_vs_oracle(engine, oracle_lib, workload, n
     assert r["n"] >= 1500 and r["valid"] > 0.5 * r["n"], r
     assert r["int_exact"] and r["selection_score_bit_exact"] and r["valid_exact"], r
     assert r["max_rel"] < RTOL and r["fragment_table_max_rel"] < 3 * RTOL, r
+
+
+@pytest.mark.parametrize("name", ["parity_small", "parity_4d"])
+def test_fused_select_score_equals_two_calls(engine, oracle_lib, name):
+    """adb_select_score_candidates_ragged (selection -> score cutoff -> scoring from the resident table, one call) against the
+    two-call flow select_candidates_resident / fetch_candidate_table / score_candidates_ragged, with and without a cutoff."""
+    from alphadia_b200 import _abi
+
+    raw, lib, p, draw, dlib = _device_objects(engine, name)
+    cfg = _sel_cfg_4d(p) if draw.is_4d else H.selection_config(p["rt_tolerance"]).to_struct()
+    kernel = H.default_kernel(raw)
+    scfg = H.scoring_config().to_struct()
+    n = engine.select_candidates_resident(draw, dlib, cfg, kernel)
+    table = engine.fetch_candidate_table(draw, n)
+    ref = engine.score_candidates_ragged(draw, dlib, scfg, _abi.candidates_in_from_table(table, n))
+    cap = int(len(lib["precursor_idx"]) * cfg.candidate_count)
+    for cutoff in (float("-inf"), float(np.median(table["score"][:n]))):
+        t2 = _abi.alloc_candidate_table(cap)
+        _, bufs = _abi.alloc_scores_ragged(cap, cap * 12)
+        got = engine.select_score_candidates_ragged(draw, dlib, cfg, kernel, scfg, t2, bufs, score_cutoff=cutoff)
+        keep = table["score"][:n] > np.float32(cutoff)
+        assert got["n_candidates"] == int(keep.sum()) and 0 < got["n_candidates"] <= n
+        for k, v in table.items():
+            assert np.array_equal(t2[k][:got["n_candidates"]], v[:n][keep]), k
+        # rows of the filtered table that are valid == the valid rows of the full table that pass the cutoff
+        old_rows = np.flatnonzero(keep)[got["row_index"]]
+        m = keep[ref["row_index"]]
+        assert np.array_equal(old_rows, ref["row_index"][m])
+        assert np.array_equal(got["features"], ref["features"][m], equal_nan=True)
+        counts = np.diff(ref["frag_offset"])
+        fm = np.repeat(m, counts)
+        for k in FRAG_F32 + FRAG_U8:
+            assert np.array_equal(got[k], ref[k][fm], equal_nan=True), k
+    dlib.close(); draw.close()
