@@ -1261,8 +1261,8 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
     const int64_t n_cycles = (d->n_spectra + d->cycle_len - 1) / d->cycle_len;
     const int ntb = (int)std::max<int64_t>((n_cycles + ADB_TB_CYCLES - 1) / ADB_TB_CYCLES, 1);
     const int64_t n_seg = d->cycle_len * ntb;
-    int nb = 64;  // about 8 peaks per bucket of an average segment
-    while (nb < 4096 && (int64_t)nb * 8 * n_seg < n) nb *= 2;
+    int nb = 64;  // about 4 peaks per bucket of an average segment
+    while (nb < ADB_TB_MAX_BUCKETS && (int64_t)nb * 4 * n_seg < n) nb *= 2;
     v.tb_ntb = ntb; v.tb_nb = nb;
     v.tb_lo = v.bucket_lo;
     v.tb_width = v.bucket_width * (float)ADB_N_BUCKETS / (float)nb;

@@ -65,6 +65,9 @@ struct DevRaw {
   float tb_lo, tb_width, tb_inv_width;
 };
 
+#ifndef ADB_TB_MAX_BUCKETS
+#define ADB_TB_MAX_BUCKETS 16384  // m/z buckets per segment of the time-blocked index (about 4 peaks per bucket)
+#endif
 #ifndef ADB_TB_CYCLES
 #define ADB_TB_CYCLES 32
 #endif

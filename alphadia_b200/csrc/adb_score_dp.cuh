@@ -422,7 +422,9 @@ ADB_HD void dp_extract(const DpParams& P, int64_t j, int r) {
   }
   float lo, hi, plo, prev_hi = -1.0f;
   dp_window(mz_row, tol, lo, hi);
-  if (k > 0) dp_window(mz_prev, tol, plo, prev_hi);
+  // the previous window matters only if it reaches into this one; a float pre-check with a wide margin (tolerance + 1e-5
+  // relative) skips its fp64 division for the usual well-separated neighbours (prev_hi < lo then, whatever its exact value)
+  if (k > 0 && mz_prev * (1.0f + 1e-6f * tol + 1e-5f) >= lo) dp_window(mz_prev, tol, plo, prev_hi);
 
   if (is_frag || raw.n_ms1_pos == 1) {
     const int stride = is_frag ? F : nI;

@@ -35,7 +35,7 @@ extern "C" int adb_hostsim_score(const adb_rawfile3d_desc* d, const adb_library_
     }
   if (!(mz_max > mz_min)) { mz_min = 0.f; mz_max = 1.f; }
   int nb = 64;
-  while (nb < 4096 && (int64_t)nb * 8 * n_seg < d->n_peaks) nb *= 2;
+  while (nb < ADB_TB_MAX_BUCKETS && (int64_t)nb * 4 * n_seg < d->n_peaks) nb *= 2;
   if (nb_override > 0) nb = nb_override;
   raw.tb_ntb = ntb; raw.tb_nb = nb; raw.tb_lo = mz_min;
   raw.tb_width = (mz_max - mz_min) / (float)nb * 1.0001f;
