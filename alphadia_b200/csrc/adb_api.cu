@@ -378,22 +378,6 @@ __global__ void mzindex_keys_kernel(DevRaw raw, uint64_t* keys, uint32_t* vals) 
   }
 }
 
-__global__ void mzindex_gather_kernel(DevRaw raw, const uint64_t* keys, const uint32_t* vals, int64_t n, float* s_mz, float* s_int,
-                                      uint32_t* s_cyc, uint64_t n_segments) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  if ((keys[j] >> 32) >= n_segments) { s_mz[j] = 3.0e38f; s_int[j] = 0.f; s_cyc[j] = 0xFFFFFFFFu; return; }  // not in a spectrum
-  const uint32_t i = vals[j];
-  int64_t lo = 0, hi = raw.n_spectra;  // spectrum of peak i: last s with peak_start[s] <= i and i < peak_stop[s]
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (raw.peak_stop[mid] <= (int64_t)i) lo = mid + 1; else hi = mid;
-  }
-  s_mz[j] = raw.mz[i];
-  s_int[j] = raw.intensity[i];
-  s_cyc[j] = (uint32_t)(lo / raw.cycle_len);
-}
-
 __global__ void mzindex_segments_kernel(const uint64_t* keys, int64_t n, int64_t L, int64_t* pos_start) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p > L) return;
@@ -419,11 +403,12 @@ __global__ void tbindex_keys_kernel(DevRaw raw, int ntb, uint64_t* keys, uint32_
   }
 }
 
-// sorted peak j of the time-blocked index as one 16-byte record; the 16 records behind the last peak are padding with a huge
+// sorted peak j of an m/z-sorted index as one 16-byte record; the `pad` records behind the last peak are padding with a huge
 // m/z that is never inside a window
-__global__ void tbindex_gather_kernel(DevRaw raw, const uint64_t* keys, const uint32_t* vals, int64_t n, float4* pk, uint64_t n_segments) {
+__global__ void tbindex_gather_kernel(DevRaw raw, const uint64_t* keys, const uint32_t* vals, int64_t n, float4* pk, uint64_t n_segments,
+                                      int pad) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n + 16) return;
+  if (j >= n + pad) return;
   if (j >= n || (keys[j] >> 32) >= n_segments) { pk[j] = make_float4(3.0e38f, 0.f, __uint_as_float(0xFFFFFFFFu), 0.f); return; }
   const uint32_t i = vals[j];
   int64_t lo = 0, hi = raw.n_spectra;  // spectrum of peak i: last s with peak_start[s] <= i and i < peak_stop[s]
@@ -435,16 +420,17 @@ __global__ void tbindex_gather_kernel(DevRaw raw, const uint64_t* keys, const ui
 }
 
 // tb_bucket[seg][b] = first sorted peak whose key is >= (seg, lower edge of bucket b); b == nb: end of the segment
-__global__ void tbindex_bucket_kernel(DevRaw raw, const uint64_t* keys, int64_t n, int64_t n_seg, uint32_t* table) {
+__global__ void tbindex_bucket_kernel(const uint64_t* keys, int64_t n, int64_t n_seg, int nb, float edge_lo, float edge_width,
+                                      uint32_t* table) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t per = raw.tb_nb + 1;
+  const int64_t per = nb + 1;
   if (t >= n_seg * per) return;
   const int64_t seg = t / per;
   const int b = (int)(t - seg * per);
   uint64_t v;
   if (b == 0) v = (uint64_t)seg << 32;
-  else if (b == raw.tb_nb) v = (uint64_t)(seg + 1) << 32;
-  else v = ((uint64_t)seg << 32) | ordered_bits(adb_tb_edge(raw, b));
+  else if (b == nb) v = (uint64_t)(seg + 1) << 32;
+  else v = ((uint64_t)seg << 32) | ordered_bits(adb_bucket_edge(edge_lo, edge_width, b));
   int64_t lo = 0, hi = n;
   while (lo < hi) {
     const int64_t mid = (lo + hi) >> 1;
@@ -1227,9 +1213,17 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
   {  // derived m/z-major index (see DevRaw): stable radix sort of (cycle position, m/z) over all peaks
     const int64_t n = d->n_peaks;
     const size_t N = (size_t)std::max<int64_t>(n, 1);
-    float *s_mz = nullptr, *s_int = nullptr; uint32_t* s_cyc = nullptr; int64_t* pstart = nullptr;
+    float4* s_pk = nullptr; uint32_t* s_tab = nullptr; int64_t* pstart = nullptr;
+    int nb = 64;  // about 16 peaks per bucket of an average position
+    while (nb < (1 << 18) && (int64_t)nb * 16 * d->cycle_len < n) nb *= 2;
+    v.sb_nb = nb;
+    v.sb_lo = v.bucket_lo;
+    v.sb_width = v.bucket_width * (float)ADB_N_BUCKETS / (float)nb;
+    if (!(v.sb_width > 0.f)) v.sb_width = 1.f;
+    v.sb_inv_width = 1.0f / v.sb_width;
+    const size_t tab_n = (size_t)d->cycle_len * (size_t)(nb + 1);
     auto dalloc = [&](void** p, size_t bytes) { if (cudaMalloc(p, bytes) != cudaSuccess) return 1; r->allocs.push_back(*p); r->bytes += (int64_t)bytes; return 0; };
-    if (dalloc((void**)&s_mz, 4 * (N + 64)) || dalloc((void**)&s_int, 4 * (N + 64)) || dalloc((void**)&s_cyc, 4 * (N + 64)) ||
+    if (dalloc((void**)&s_pk, 16 * (N + 64)) || dalloc((void**)&s_tab, 4 * tab_n) ||
         dalloc((void**)&pstart, 8 * (size_t)(d->cycle_len + 1))) { adb_rawfile_destroy(r); return fail("cudaMalloc m/z index failed"); }
     uint64_t *k_in = nullptr, *k_out = nullptr; uint32_t *v_in = nullptr, *v_out = nullptr; void* tmp = nullptr;
     size_t tmp_bytes = 0;
@@ -1243,17 +1237,15 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
       cudaMemsetAsync(v_in, 0, 4 * N, r->stream);
       mzindex_keys_kernel<<<(unsigned)((d->n_spectra * 32 + 255) / 256), 256, 0, r->stream>>>(v, k_in, v_in);
       cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)n, 0, end_bit, r->stream);
-      if (n > 0) mzindex_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, s_mz, s_int, s_cyc, (uint64_t)d->cycle_len);
+      tbindex_gather_kernel<<<(unsigned)((n + 64 + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, s_pk, (uint64_t)d->cycle_len, 64);
       mzindex_segments_kernel<<<(unsigned)((d->cycle_len + 1 + 255) / 256), 256, 0, r->stream>>>(k_out, n, d->cycle_len, pstart);
-      cudaMemsetAsync(s_mz + n, 0x7f, 4 * 64, r->stream);  // padding: huge m/z, never inside a window
-      cudaMemsetAsync(s_int + n, 0, 4 * 64, r->stream);
-      cudaMemsetAsync(s_cyc + n, 0xFF, 4 * 64, r->stream);
-      r->launches += 7;
+      tbindex_bucket_kernel<<<(unsigned)((tab_n + 255) / 256), 256, 0, r->stream>>>(k_out, n, d->cycle_len, nb, v.sb_lo, v.sb_width, s_tab);
+      r->launches += 5;
       ok = cudaStreamSynchronize(r->stream) == cudaSuccess;
     }
     cudaFree(k_in); cudaFree(k_out); cudaFree(v_in); cudaFree(v_out); cudaFree(tmp);
     if (!ok) { cudaGetLastError(); adb_rawfile_destroy(r); return fail("building the m/z-major index failed (out of device memory?)"); }
-    v.s_mz = s_mz; v.s_int = s_int; v.s_cyc = s_cyc; v.pos_start = pstart;
+    v.s_pk = s_pk; v.s_bucket = s_tab; v.pos_start = pstart;
   }
   {  // derived time-blocked m/z index (see DevRaw): stable radix sort of (cycle position, time block, m/z) over all peaks
     const int64_t n = d->n_peaks;
@@ -1283,8 +1275,8 @@ int adb_rawfile3d_create(const adb_rawfile3d_desc* d, int device, adb_rawfile_t*
       cudaMemsetAsync(v_in, 0, 4 * N, r->stream);
       tbindex_keys_kernel<<<(unsigned)((d->n_spectra * 32 + 255) / 256), 256, 0, r->stream>>>(v, ntb, k_in, v_in);
       cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)n, 0, 64, r->stream);
-      tbindex_gather_kernel<<<(unsigned)((n + 16 + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, t_pk, (uint64_t)n_seg);
-      tbindex_bucket_kernel<<<(unsigned)((tab_n + 255) / 256), 256, 0, r->stream>>>(v, k_out, n, n_seg, t_tab);
+      tbindex_gather_kernel<<<(unsigned)((n + 16 + 255) / 256), 256, 0, r->stream>>>(v, k_out, v_out, n, t_pk, (uint64_t)n_seg, 16);
+      tbindex_bucket_kernel<<<(unsigned)((tab_n + 255) / 256), 256, 0, r->stream>>>(k_out, n, n_seg, nb, v.tb_lo, v.tb_width, t_tab);
       r->launches += 4;
       ok = cudaStreamSynchronize(r->stream) == cudaSuccess;
     }

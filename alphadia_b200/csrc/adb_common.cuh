@@ -47,13 +47,16 @@ struct DevRaw {
   const uint2* bucket_pair;         // [n_spectra][ADB_N_BUCKETS]
   float bucket_lo, bucket_width, bucket_inv_width;
   // derived m/z-major index (built once per file on the device): for every cycle position p the peaks of ALL its
-  // spectra, stably sorted by m/z: segment [pos_start[p], pos_start[p + 1]) of (s_mz, s_int, s_cyc = cycle index).
+  // spectra, stably sorted by m/z: segment [pos_start[p], pos_start[p + 1]) of s_pk records.
   // One search answers "which peaks of this quad window fall into this m/z window, in any cycle" — candidate selection
   // extracts a whole XIC row (hundreds of cycles) with it instead of one binary search per spectrum.
-  const float* s_mz;
-  const float* s_int;
-  const uint32_t* s_cyc;
+  const float4* s_pk;               // {m/z, intensity, cycle index (bit pattern), 0}: one 128-bit load per peak
   const int64_t* pos_start;         // [cycle_len + 1]
+  // s_bucket[p][b]: first peak of position p at or above the lower edge of m/z bucket b (entry sb_nb = segment end),
+  // about 16 peaks per bucket: the row search of candidate selection is one table read + one 32-wide probe
+  const uint32_t* s_bucket;         // [cycle_len][sb_nb + 1]
+  int32_t sb_nb;
+  float sb_lo, sb_width, sb_inv_width;
   // derived time-blocked m/z index (built once per file on the device), used by candidate scoring: segment
   // (cycle position p, time block t = cycle / ADB_TB_CYCLES) holds the peaks of the <= ADB_TB_CYCLES spectra of position p in
   // that block, stably sorted by m/z.  A scoring window of ~10 cycles touches 1-2 segments and finds ~1 peak of its ppm
@@ -72,22 +75,32 @@ struct DevRaw {
 #define ADB_TB_CYCLES 32
 #endif
 
-// m/z edge of bucket b of the time-blocked index (the SAME float expression builds the table and routes the queries)
+// m/z edge of bucket b of a bucket table (the SAME float expression builds the table and routes the queries)
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline float adb_tb_edge(const DevRaw& raw, int b) { return fmaf((float)b, raw.tb_width, raw.tb_lo); }
+inline float adb_bucket_edge(float lo, float width, int b) { return fmaf((float)b, width, lo); }
 
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline int adb_tb_bucket_of(const DevRaw& raw, float v) {
-  int b = (int)((v - raw.tb_lo) * raw.tb_inv_width);
-  b = b < 0 ? 0 : (b > raw.tb_nb - 1 ? raw.tb_nb - 1 : b);
-  while (b > 0 && adb_tb_edge(raw, b) > v) b--;
-  while (b < raw.tb_nb - 1 && adb_tb_edge(raw, b + 1) <= v) b++;
+inline int adb_bucket_of(float lo, float width, float inv_width, int nb, float v) {
+  int b = (int)((v - lo) * inv_width);
+  b = b < 0 ? 0 : (b > nb - 1 ? nb - 1 : b);
+  while (b > 0 && adb_bucket_edge(lo, width, b) > v) b--;
+  while (b < nb - 1 && adb_bucket_edge(lo, width, b + 1) <= v) b++;
   return b;
 }
+
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline float adb_tb_edge(const DevRaw& raw, int b) { return adb_bucket_edge(raw.tb_lo, raw.tb_width, b); }
+
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int adb_tb_bucket_of(const DevRaw& raw, float v) { return adb_bucket_of(raw.tb_lo, raw.tb_width, raw.tb_inv_width, raw.tb_nb, v); }
 
 // timsTOF (4-D) raw file resident in HBM: the TimsTOFTransposeJIT arrays the hot path reads
 // (alphadia/search/jitclasses/bruker_jit.py:20-137), CSR by tof index.

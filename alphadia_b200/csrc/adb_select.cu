@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(SEL_PLAN_THREADS) adb_select_plan_kernel(const
 // ---------------------------------------------------------------------------------------------------------
 // XIC extraction (alpharaw_jit.py:398-423) through the m/z-major index: ONE WARP PER XIC ROW (precursor, layer).
 // The reference walks every spectrum of the cycle window and binary-searches each m/z window in it; here the peaks of
-// one cycle position are stored sorted by m/z across all cycles (DevRaw::s_mz/s_int/s_cyc), so a row needs one
+// one cycle position are stored sorted by m/z across all cycles (DevRaw::s_pk records + the s_bucket table), so a row needs one
 // warp-cooperative 32-ary search per observation and a scan over the few dozen peaks inside the m/z window; peaks whose
 // cycle lies outside [cs, cs + C) are skipped.  Bit-exactness: a cell sums its peaks in ascending m/z order and its
 // observations in ascending cycle-position order, exactly like the reference — the index is a STABLE sort, observations
@@ -323,13 +323,13 @@ __global__ void __launch_bounds__(SEL_PLAN_THREADS) adb_select_plan_kernel(const
 // not seen again) becomes the extra lower bound mz > hi[k - 1].
 #define SEL_ROWS_PER_CTA (SEL_EXTRACT_THREADS / 32)
 
-__device__ __forceinline__ int64_t warp_lower_bound_window(const float* __restrict__ mz, int64_t lo, int64_t hi, float v_lo, float prev_hi,
+__device__ __forceinline__ int64_t warp_lower_bound_window(const float4* __restrict__ pk, int64_t lo, int64_t hi, float v_lo, float prev_hi,
                                                            int lane) {
-  // first index in [lo, hi) whose m/z is >= v_lo and > prev_hi ("before" = mz < v_lo || mz <= prev_hi, monotone)
+  // first index in [lo, hi] whose m/z is >= v_lo and > prev_hi ("before" = mz < v_lo || mz <= prev_hi, monotone)
   while (hi - lo > 32) {
     const int64_t n = hi - lo, step = (n + 31) >> 5;
     const int64_t last = lo + min((int64_t)(lane + 1) * step, n) - 1;  // last element of sub-block `lane`
-    const float m = __ldg(mz + last);
+    const float m = __ldg(&pk[last].x);
     const unsigned b = __ballot_sync(FULL, (m < v_lo) || (m <= prev_hi));
     const int c = __popc(b);  // leading sub-blocks that lie completely before the window
     const int64_t nlo = lo + min((int64_t)c * step, n);
@@ -338,7 +338,7 @@ __device__ __forceinline__ int64_t warp_lower_bound_window(const float* __restri
   }
   const int64_t i = lo + lane;
   float m = 3.0e38f;
-  if (i < hi) m = __ldg(mz + i);
+  if (i < hi) m = __ldg(&pk[i].x);
   const unsigned b = __ballot_sync(FULL, i < hi && ((m < v_lo) || (m <= prev_hi)));
   return lo + __popc(b);
 }
@@ -355,17 +355,22 @@ __device__ __forceinline__ void extract_row(const SelectParams& P, const PrecPla
   const uint32_t cs = (uint32_t)pl.cs;
   for (int o = 0; o < n_o; o++) {
     const int p = ms1 ? raw.ms1_pos[o] : (int)pl.pos[o];
-    const int64_t seg1 = __ldg(raw.pos_start + p + 1);
-    int64_t idx = warp_lower_bound_window(raw.s_mz, __ldg(raw.pos_start + p), seg1, lo, prev_hi, lane);
+    // bucket of the first wanted m/z (the previous window's upper edge when that window reaches into this one): the
+    // first wanted peak lies inside the bucket or is the first peak of the next one
+    const uint32_t* tab = raw.s_bucket + (size_t)p * (size_t)(raw.sb_nb + 1);
+    const int bk = adb_bucket_of(raw.sb_lo, raw.sb_width, raw.sb_inv_width, raw.sb_nb, prev_hi >= lo ? prev_hi : lo);
+    const int64_t seg1 = (int64_t)__ldg(tab + raw.sb_nb);
+    int64_t idx = warp_lower_bound_window(raw.s_pk, (int64_t)__ldg(tab + bk), (int64_t)__ldg(tab + bk + 1), lo, prev_hi, lane);
     while (idx < seg1) {  // chunks of 32 peaks in ascending m/z
       const int64_t i = idx + lane;
-      const float m = __ldg(raw.s_mz + i);  // padded behind the last segment
+      const float4 pk = __ldg(raw.s_pk + i);  // padded behind the last segment
+      const float m = pk.x;
       const bool inw = i < seg1 && m <= hi;
-      const uint32_t c = __ldg(raw.s_cyc + i) - cs;
+      const uint32_t c = __float_as_uint(pk.z) - cs;
       const bool take = inw && c < (uint32_t)C;
       const unsigned tb = __ballot_sync(FULL, take);
       if (tb) {
-        const float v = __ldg(raw.s_int + i);
+        const float v = pk.y;
         const unsigned grp = __match_any_sync(FULL, take ? c : 0xFFFFFF00u + (uint32_t)lane);
         const int rank = __popc(grp & ((1u << lane) - 1u));
         const unsigned multi = __ballot_sync(FULL, take && rank > 0);
