@@ -610,8 +610,10 @@ __global__ void __launch_bounds__(SEL_FUSED_THREADS) adb_select_fused_kernel(con
       for (int t = lane; t < stride + 1; t += 32) ext[t] = 0.f;
       __syncwarp();
       extract_row(P, pl, it, k, ext + off, lane);
-      for (int t = lane; t < stride; t += 32)  // circular halo (C >= kw is guaranteed by the plan)
-        if (t < off) ext[t] = ext[t + C]; else if (t >= off + C) ext[t] = ext[t - C];
+      for (int h = lane; h < kw - 1; h += 32) {  // circular halo: kw - 1 cells (C >= kw is guaranteed by the plan)
+        const int t = h < off ? h : h + C;
+        ext[t] = h < off ? ext[t + C] : ext[t - C];
+      }
       __syncwarp();
       unsigned any_nz = 0;
       for (int w = 0; w <= n_words; w++) {
