@@ -7,9 +7,16 @@
 
 One "step" = candidate selection + candidate scoring of the whole library batch against one raw file
 (SURVEY.md §8d).  `value` is measured with raw file and library resident in HBM (results stay in HBM);
-`e2e` is measured through the C-ABI calls the reference-facing operators make, with pinned HOST buffers
-(library batch H2D, compacted candidate table D2H, candidate table H2D, score + fragment tables D2H every step;
-the raw file is uploaded once per file, as `dia_data.to_jitclass()` is built once per file in the reference).
+`e2e` is measured through the C ABI with pinned HOST buffers: library batch H2D, then ONE call
+adb_select_score_candidates_ragged (selection, candidate table D2H, scoring, ragged score + fragment tables D2H) every
+step (`--e2e-two-calls` / `--e2e-dense`: the separate-call and dense-table variants); the raw file is uploaded once per
+file, as `dia_data.to_jitclass()` is built once per file in the reference.  `e2e_operator` is the DataFrame-level operator
+path, `fragcomp` the fragment competition host to host, `parity` an oracle spot check of the timed results.
+
+Baselines: `cpu_baseline` and `--impl reference` run the C/OpenMP PORT of the reference algorithm (oracle/adb_oracle.c,
+`kind: "port"`), not the numba code (it cannot travel to the GPU box; BASELINE.md has the numba calibration).  Everywhere
+in this repository "the reference" means alphaDIA with its float32 rocket-fft convolution replaced by the direct fp64
+circular convolution (rocket-fft is not installed) - on the oracle, the golden vectors and the device alike.
 """
 
 from __future__ import annotations
