@@ -66,7 +66,21 @@ def main():
         def last_timing(self):
             return {}
 
+    def fake_score_ragged(dev_raw, dev_lib, cfg, cin, bufs=None, max_fragments=None):
+        """Stand-in for adb_score_candidates_ragged: valid rows with `valid_frac`, 4 kept fragment slots each."""
+        n = int(cin.n)
+        valid = np.flatnonzero(np.random.default_rng(1).random(n) < valid_frac).astype(np.int64)
+        nr, per = len(valid), 4
+        out = dict(n_rows=nr, n_fragments=nr * per, row_index=valid, features=np.ones((nr, _abi.NUM_FEATURES), np.float32),
+                   frag_offset=np.arange(nr + 1, dtype=np.int64) * per)
+        for k in _abi.FRAG_F32:
+            out[k] = np.full(nr * per, 500.0, np.float32)
+        for k in _abi.FRAG_U8:
+            out[k] = np.ones(nr * per, np.uint8)
+        return out
+
     _lib.score_candidates = fake_score
+    _lib.score_candidates_ragged = fake_score_ragged
     _lib.DeviceLibrary = FakeLib
     _lib.device_rawfile_for = lambda dia, raw: FakeDevRaw()
     scoring.adapt_dia_data = lambda d: d

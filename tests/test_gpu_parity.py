@@ -1232,3 +1232,22 @@ def test_fused_select_score_equals_two_calls(engine, oracle_lib, name):
         for k in FRAG_F32 + FRAG_U8:
             assert np.array_equal(got[k], ref[k][fm], equal_nan=True), k
     dlib.close(); draw.close()
+
+
+def test_ragged_scores_empty_and_all_invalid(engine):
+    """Zero candidates, and candidates that are all rejected (windows of one cycle): the ragged result is empty and well-formed."""
+    raw, lib, p, draw, dlib = _device_objects(engine, "parity_small")
+    scfg = H.scoring_config().to_struct()
+    empty = {c: np.zeros(0, np.int64) for c in INT_COLS}
+    cin, keep = H.candidates_in_from_arrays(lib, empty)
+    rag = engine.score_candidates_ragged(draw, dlib, scfg, cin)
+    assert rag["n_rows"] == 0 and rag["n_fragments"] == 0 and list(rag["frag_offset"]) == [0]
+    L = raw.cycle.shape[1]
+    one = dict(precursor_idx=lib["precursor_idx"][:50].astype(np.int64), rank=np.zeros(50, np.int64), scan_center=np.zeros(50, np.int64),
+               scan_start=np.zeros(50, np.int64), scan_stop=np.ones(50, np.int64), frame_center=np.full(50, 10 * L, np.int64),
+               frame_start=np.full(50, 10 * L, np.int64), frame_stop=np.full(50, 10 * L, np.int64))  # zero cycles wide
+    cin, keep = H.candidates_in_from_arrays(lib, one)
+    rag = engine.score_candidates_ragged(draw, dlib, scfg, cin)
+    dense = engine.score_candidates(draw, dlib, scfg, cin)
+    assert not dense["valid"].any() and rag["n_rows"] == 0 and rag["n_fragments"] == 0
+    dlib.close(); draw.close()
