@@ -7,26 +7,28 @@
 //
 // One pass = one kernel = one function below; a "thread" owns one candidate, one (candidate, fragment) row or one
 // (candidate, cycle) column and runs the reference's loops for it sequentially, in the reference's order (sequential f32 /
-// f64 accumulation; this file is compiled with --fmad=false, so nothing is contracted).  No pass uses warp-level
+// f64 accumulation; this file is compiled with --fmad=false, so nothing is contracted).  No pass BODY uses warp-level
 // cooperation, which has two consequences: every lane of a warp does useful work (the r1 tile-per-candidate kernel kept 13.9
 // of 32 lanes busy), and the very same source runs thread by thread on a CPU (tests/hostsim/) where it is compared with
 // the oracle without a GPU.
 //
 //   dp_setup      per candidate           fragment selection / m/z sort, isotope windows, quad-window hits, cycle window,
 //                                         quadrupole transfer function; size of the candidate's workspace block
-//   (exclusive scan of the block sizes -> block offsets)
+//   (largest block of every tile of DP_W slots, exclusive scan -> tile offsets)
 //   dp_extract    per (candidate, row)    one XIC row (fragment x observation, or isotope) through the time-blocked m/z index:
-//                                         per 32-cycle block one bucket read + a scan of the ~1 peaks inside the ppm window
+//                                         per 32-cycle block one bucket read + a scan of the ~1 peaks inside the ppm window;
+//                                         fragment mask (rows with signal -> work list of dp_fragment / dp_corr)
 //   dp_template   per candidate           template, observation importance, distance-weight tables, precursor features
-//   dp_fragment   per (candidate, frag)   fragment mask, best profile + envelope, area, weighted centres, mass error, cosine,
+//   dp_fragment   per row with signal     best profile + envelope, area, weighted centres, mass error, cosine,
 //                                         normalised profile, template correlation, FWHM, frame peak
 //   dp_median     per (candidate, cycle)  median profile over the fragments (experimental_xic)
 //   dp_corr       per (candidate, frag)   correlation with the median profile / legacy F x F correlation rows
 //   dp_aggregate  per candidate           the remaining aggregate features, feature row + valid flag
 //   dp_write      per (candidate, frag)   the per-fragment output table
 //
-// Workspace block of one candidate (float offsets from DpLayout), cube layout [observation][cycle][fragment] with the
-// fragment index fastest: the F threads of a candidate touch F adjacent floats for the same (observation, cycle).
+// Workspace block of one candidate (float offsets from DpLayout), cube layout [observation][cycle][fragment]; the blocks of
+// DP_W neighbouring slots are interleaved element by element (see DpPtr below), and every pass maps its threads with the
+// slot index fastest, so the lanes of a warp touch consecutive addresses.
 #pragma once
 #include <math.h>
 #include <stddef.h>
