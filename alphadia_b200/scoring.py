@@ -179,6 +179,30 @@ def _count_residues_arrow(sequences, res):
         return None
 
 
+def gather_missing_columns(left_df, right_df, right_columns, pos):
+    """``merge_missing_columns(left_df, right_df, right_columns, on=key, how="left")`` when row ``i`` of ``left_df`` is known
+    to match row ``pos[i]`` of ``right_df`` (unique right keys, every left key present): the columns missing on the left are
+    gathered by position, in the order of ``right_columns`` - no key search."""
+    seen = set()
+    missing = [c for c in right_columns if c not in left_df.columns and not (c in seen or seen.add(c))]
+    if not missing:
+        return left_df
+    absent = [c for c in missing if c not in right_df.columns]
+    if absent:
+        raise ValueError(f"Columns {absent} must be present in right_df")
+    out = left_df.reset_index(drop=True)
+    numeric = [c for c in missing if isinstance(right_df[c].dtype, np.dtype) and right_df[c].dtype != object]
+    gathered = _run_column_tasks({c: ((lambda a: a[pos]), right_df[c].values) for c in numeric}, len(out))  # numpy releases the GIL
+    new_cols = {}
+    for c in missing:
+        if c in gathered:
+            new_cols[c] = gathered[c]
+        else:  # object / extension columns: keep the dtype (pandas would re-infer `str` from an object array)
+            src = right_df[c]
+            new_cols[c] = pd.Series(src.values[pos], index=out.index, dtype=src.dtype)
+    return pd.concat([out, pd.DataFrame(new_cols, index=out.index, copy=False)], axis=1)
+
+
 def count_residues(sequences, residues) -> list:
     """``Series.str.count(r)`` for single-character patterns (scoring.py:461-463 n_K / n_R / n_P) without a Python call
     per row: the distinct sequences are counted once as fixed-width code points and the counts are gathered.
@@ -535,11 +559,24 @@ class CandidateScoring:
         candidates_psm_df = pd.DataFrame(features, columns=feature_columns, copy=False)  # one block, no second copy
         candidates_psm_df["precursor_idx"] = precursor_idx
         candidates_psm_df["rank"] = rank
-        candidates_psm_df = self.merge_candidate_data(candidates_psm_df, candidates_df, candidate_columns)
-        candidates_psm_df = self.merge_precursor_data(
-            candidates_psm_df, self.precursors_flat_df, self.rt_column, self.mobility_column,
-            self.precursor_mz_column, precursor_df_columns,
-        )
+        positions = psm.get("positions") if isinstance(psm, dict) else None
+        if positions is not None:
+            # the ragged result knows which candidate row and which precursor row every feature row belongs to: the two left
+            # merges (scoring.py:436-459) are gathers by position ((precursor_idx, rank) is unique after the score-group check,
+            # precursor_idx is unique in precursors_flat)
+            cols = candidate_columns + (["score"] if "score" in candidates_df.columns else [])
+            candidates_psm_df = gather_missing_columns(candidates_psm_df, positions["candidates_df"], cols, positions["candidate_rows"])
+            pcols = precursor_df_columns + _get_isotope_column_names(self.precursors_flat_df.columns)
+            for col in [self.rt_column, self.mobility_column, self.precursor_mz_column]:
+                if col not in pcols:
+                    pcols.append(col)
+            candidates_psm_df = gather_missing_columns(candidates_psm_df, self.precursors_flat_df, pcols, positions["precursor_rows"])
+        else:
+            candidates_psm_df = self.merge_candidate_data(candidates_psm_df, candidates_df, candidate_columns)
+            candidates_psm_df = self.merge_precursor_data(
+                candidates_psm_df, self.precursors_flat_df, self.rt_column, self.mobility_column,
+                self.precursor_mz_column, precursor_df_columns,
+            )
         candidates_psm_df["delta_rt"] = candidates_psm_df["rt_observed"] - candidates_psm_df[self.rt_column]
         n_k, n_r, n_p = count_residues(candidates_psm_df["sequence"].array, ["K", "R", "P"])
         candidates_psm_df["n_K"], candidates_psm_df["n_R"], candidates_psm_df["n_P"] = n_k, n_r, n_p
@@ -660,6 +697,9 @@ class CandidateScoring:
         psm["fragment_counts"] = np.diff(dev_out["frag_offset"])
         psm["precursor_idx"] = sorted_df["precursor_idx"].values.astype(np.uint32)[rows]
         psm["rank"] = sorted_df["rank"].values.astype(np.uint8)[rows]
+        lib_pidx = lib_arrays["precursor_idx"]
+        if len(lib_pidx) < 2 or bool(np.all(lib_pidx[1:] > lib_pidx[:-1])):  # unique keys: merges become gathers
+            psm["positions"] = dict(candidates_df=sorted_df, candidate_rows=rows, precursor_rows=keep["lib_row"][dev_out["row_index"]])
 
         logger.info("Finished candidate processing")
         logger.info("Collecting candidate features")

@@ -92,7 +92,15 @@ class CandidateSelection:
         candidate_df = pd.DataFrame(
             {c: table[c][:n].astype(container_dtypes.get(c, np.uint32), copy=False) for c in CANDIDATE_COLUMNS}
         )
-        # selection.py:670-676
+        # selection.py:670-676: left merge with the precursor table on precursor_idx.  Every candidate row carries the
+        # library row it came from, so with unique precursor_idx values the merge is a gather of two columns (row order,
+        # columns and dtypes of DataFrame.merge(how="left")); duplicated precursor_idx values take the real merge.
+        pidx = precursors["precursor_idx"].values
+        if len(pidx) < 2 or bool(np.all(pidx[1:] > pidx[:-1])):
+            rows = table["lib_row"][:n]
+            candidate_df["elution_group_idx"] = precursors["elution_group_idx"].values[rows]
+            candidate_df["decoy"] = precursors["decoy"].values[rows]
+            return candidate_df
         return candidate_df.merge(
             self.precursors_flat[["precursor_idx", "elution_group_idx", "decoy"]],
             on="precursor_idx",

@@ -372,6 +372,8 @@ def patch_device_with_oracle(monkeypatch, oracle_lib, is4d: bool = False):
         arrs = select(dev_raw.arrays, dev_lib.arrays, cfg, kernel)
         keep = arrs["score"] > 0  # adb_fetch_candidate_table: rows with score > 0 in container order
         state["table"] = {c: arrs[c][keep] for c in int_cols + ["score"]}
+        # library row of every container row (the container holds candidate_count rows per precursor, in library order)
+        state["table"]["lib_row"] = (np.flatnonzero(keep) // int(cfg.candidate_count)).astype(np.int64)
         return int(keep.sum())
 
     def fetch_table(dev_raw, n, arrs=None):

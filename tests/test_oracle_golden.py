@@ -566,6 +566,8 @@ def test_candidate_selection_table_vs_reference(name, oracle_lib, monkeypatch):
         arrs = select(dev_raw.arrays, dev_lib.arrays, cfg, kernel)
         keep = arrs["score"] > 0  # adb_fetch_candidate_table: rows with score > 0 in container order
         state["table"] = {c: arrs[c][keep] for c in INT_COLS + ["score"]}
+        # library row of every container row (the container holds candidate_count rows per precursor, in library order)
+        state["table"]["lib_row"] = (np.flatnonzero(keep) // int(cfg.candidate_count)).astype(np.int64)
         return int(keep.sum())
 
     def fetch_table(dev_raw, n, arrs=None):
