@@ -1396,7 +1396,9 @@ int adb_library_create(const adb_library_desc* d, int device, adb_library_t** ou
   const size_t Pn = (size_t)std::max<int64_t>(P, 0), Fn = (size_t)std::max<int64_t>(NF, 0);
   add(0, d->precursor_idx, 4 * Pn); add(1, d->frag_start_idx, 4 * Pn); add(2, d->frag_stop_idx, 4 * Pn); add(3, d->charge, Pn);
   add(4, d->rt, 4 * Pn); add(5, d->mobility, 4 * Pn); add(6, d->mz, 4 * Pn); add(7, d->isotopes, 4 * Pn * (size_t)d->n_isotopes);
-  add(8, d->frag_mz_library, 4 * Fn); add(9, d->frag_mz, 4 * Fn); add(10, d->frag_intensity, 4 * Fn); add(11, d->frag_type, Fn);
+  // uncalibrated searches pass the SAME host column as library m/z and search m/z: it is uploaded once and shared
+  const bool mz_alias = d->frag_mz == d->frag_mz_library;
+  add(8, d->frag_mz_library, 4 * Fn); add(9, d->frag_mz, mz_alias ? 0 : 4 * Fn); add(10, d->frag_intensity, 4 * Fn); add(11, d->frag_type, Fn);
   add(12, d->frag_loss_type, Fn); add(13, d->frag_charge, Fn); add(14, d->frag_number, Fn); add(15, d->frag_position, Fn);
   add(16, d->frag_cardinality, Fn);
   void* pool = nullptr;
@@ -1426,7 +1428,7 @@ int adb_library_create(const adb_library_desc* d, int device, adb_library_t** ou
   v.frag_stop_idx = (const uint32_t*)(b + items[2].off); v.charge = (const uint8_t*)(b + items[3].off);
   v.rt = (const float*)(b + items[4].off); v.mobility = (const float*)(b + items[5].off); v.mz = (const float*)(b + items[6].off);
   v.isotopes = (const float*)(b + items[7].off); v.frag_mz_library = (const float*)(b + items[8].off);
-  v.frag_mz = (const float*)(b + items[9].off); v.frag_intensity = (const float*)(b + items[10].off);
+  v.frag_mz = (const float*)(b + items[mz_alias ? 8 : 9].off); v.frag_intensity = (const float*)(b + items[10].off);
   v.frag_type = (const uint8_t*)(b + items[11].off); v.frag_loss_type = (const uint8_t*)(b + items[12].off);
   v.frag_charge = (const uint8_t*)(b + items[13].off); v.frag_number = (const uint8_t*)(b + items[14].off);
   v.frag_position = (const uint8_t*)(b + items[15].off); v.frag_cardinality = (const uint8_t*)(b + items[16].off);

@@ -82,15 +82,21 @@ class HotPath:
         n_rows = int(self.n_precursors * self.sel_struct.candidate_count)
         if self._host_bufs is None or self._host_bufs["n_rows"] != n_rows:
             lib_host = {}
+            by_address = {}
             for k, v in self.lib_arrays.items():  # the library batch as the caller would hold it: (pinned) host arrays
+                key = (v.__array_interface__["data"][0], v.shape, v.dtype.str)
+                if key in by_address:  # two fields that are views of one column (library m/z == search m/z) stay one buffer
+                    lib_host[k] = lib_host[by_address[key]]
+                    continue
                 buf = alloc(v.shape, v.dtype)
                 np.copyto(buf, v)
                 lib_host[k] = buf
+                by_address[key] = k
             self._host_bufs = dict(n_rows=n_rows, table=_abi.alloc_candidate_table(n_rows, alloc), lib=lib_host,
                                    scores=None, scores_n=0)
         table = self._host_bufs["table"]
         dev_lib = _lib.DeviceLibrary(self._host_bufs["lib"], device=self.dev_raw.device)
-        h2d = sum(int(v.nbytes) for v in self.lib_arrays.values())
+        h2d = sum(int(v.nbytes) for v in {id(v): v for v in self._host_bufs["lib"].values()}.values())
         lap("library_upload")
         if fused:
             try:
