@@ -14,7 +14,7 @@
 #include "adb_common.cuh"
 
 #ifndef ADB_SCORE_DP_BATCH
-#define ADB_SCORE_DP_BATCH (1 << 21)
+#define ADB_SCORE_DP_BATCH (3 << 20)
 #define ADB_SCORE_DP_BATCH_MAX (1 << 22)  // candidates per batch of the data-parallel scoring passes (x 72 rows < 2^32)
 #endif
 #ifndef ADB_SCORE_BLOCKS
