@@ -6,7 +6,7 @@
 #include "../../include/alphadia_b200.h"
 
 #define ADB_MAX_OBS 8            // quad windows one candidate may hit
-#define ADB_MAX_LIB_FRAGMENTS 64 // fragments per precursor in the flat library (before top-k)
+#define ADB_MAX_LIB_FRAGMENTS 128 // fragments per precursor in the flat library (before top-k)
 #define ADB_MAX_MS1_POS 8        // MS1 spectra per DIA cycle
 #define ADB_MAX_KERNEL_W 64
 #define ADB_ISOTOPE_DIFF 1.0033548350700006

@@ -56,15 +56,21 @@ struct SelectParams {
   float* dense;                    // [chunk_n][layer_cap][c_cap]
 };
 
-// per-warp staging for the plan kernel / per-CTA state for the smoothing kernel
-struct SlotMeta {
+// what the peak picking / write-out needs of a precursor (per warp in the fused kernel, per CTA in the smoothing kernel)
+struct SlotFinish {
+  int C;
+  long long frame_lo, row;
+  double* score;   // [C]
+};
+// per-warp staging of the plan kernel (the only user of the per-fragment arrays: the fused kernel keeps 8 of these small
+// SlotFinish records in shared memory instead, which leaves room for 5 CTAs per SM whatever ADB_MAX_LIB_FRAGMENTS is)
+struct SlotMeta : SlotFinish {
   float lo[SEL_MAX_LAYERS], hi[SEL_MAX_LAYERS];
   float tmp_mz[ADB_MAX_LIB_FRAGMENTS];
   float iso_mz[ADB_MAX_ISOTOPES];
   int pos[ADB_MAX_OBS];
-  int nF, nI, nobs, C, ok;
-  long long frame_lo, cs, row;
-  double* score;   // [C]
+  int nF, nI, nobs, ok;
+  long long cs;
 };
 
 __device__ __forceinline__ double limits_value(const double* a, int idx, int nrows) {
@@ -173,7 +179,7 @@ __device__ void slot_setup(const SelectParams& P, SlotMeta& sl, int64_t i, int l
 }
 
 // phase 3 for one slot, executed by one warp
-__device__ void slot_finish(const SelectParams& P, SlotMeta& sl, int lane) {
+__device__ void slot_finish(const SelectParams& P, SlotFinish& sl, int lane) {
   const DevRaw& raw = P.raw;
   const adb_selection_config& cfg = P.cfg;
   const int64_t L = raw.cycle_len;
@@ -582,7 +588,7 @@ __host__ __device__ inline FusedLayout fused_layout(int c_cap, int kw) {
 
 __global__ void __launch_bounds__(SEL_FUSED_THREADS) adb_select_fused_kernel(const __grid_constant__ SelectParams P) {
   extern __shared__ __align__(16) unsigned char dyn_f[];
-  __shared__ SlotMeta slots[SEL_FUSED_WARPS];
+  __shared__ SlotFinish slots[SEL_FUSED_WARPS];
   const adb_selection_config& cfg = P.cfg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kw = P.kw, off = kw - 1 - kw / 2;
@@ -594,7 +600,7 @@ __global__ void __launch_bounds__(SEL_FUSED_THREADS) adb_select_fused_kernel(con
   float* lp = (float*)(wb + fl.lp_off);
   float* ext = (float*)(wb + fl.ext_off);
   uint32_t* mask = (uint32_t*)(wb + fl.mask_off);
-  SlotMeta& sl = slots[warp];
+  SlotFinish& sl = slots[warp];
   for (int t = tid; t < 2 * kw; t += SEL_FUSED_THREADS) skern[t] = P.kern[t];
   __syncthreads();
   const uint32_t kw_mask = (kw >= 32) ? 0xFFFFFFFFu : ((1u << kw) - 1u);
@@ -681,7 +687,7 @@ void launch_smooth(const SelectParams& P, int threads, long long grid, size_t dy
 // the fused kernel needs its rows in shared memory and a kernel width that fits one 32-bit tap mask
 bool adb_select_fused(int c_cap, int max_layers, int kw) {
   if (getenv("ADB_SELECT_LEGACY")) return false;  // test hook: force the extract + dense-smoothing pair
-  return kw <= 32 && c_cap <= SEL_FUSED_MAX_C && fused_layout(c_cap, kw).bytes + SEL_FUSED_WARPS * sizeof(SlotMeta) + 1024 <= 200 * 1024;
+  return kw <= 32 && c_cap <= SEL_FUSED_MAX_C && fused_layout(c_cap, kw).bytes + SEL_FUSED_WARPS * sizeof(SlotFinish) + 1024 <= 200 * 1024;
 }
 
 size_t adb_select_bytes_per_precursor(int c_cap, int max_layers, int kw) {

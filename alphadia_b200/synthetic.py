@@ -291,6 +291,18 @@ CONFIGS_3D = {
         cycle_seconds=1.0, n_noise_ms2=400, n_noise_ms1=800, rt_tolerance=25.0,
         planted_fraction=0.6, max_planted=None, n_fragments=20,
     ),
+    # 48 library fragments per precursor (transfer-library scale: top_k_fragments = 9999 keeps all of them)
+    "parity_f48": dict(
+        seed=37, n_precursors=200, n_cycles=120, n_windows=12, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=1.0, n_noise_ms2=400, n_noise_ms1=800, rt_tolerance=25.0,
+        planted_fraction=0.6, max_planted=None, n_fragments=48,
+    ),
+    # 96 library fragments per precursor: beyond every dense table, close to the device limit of 128 per precursor
+    "parity_f96": dict(
+        seed=41, n_precursors=120, n_cycles=120, n_windows=12, quad_lo=400.0, quad_hi=1000.0,
+        cycle_seconds=1.0, n_noise_ms2=400, n_noise_ms1=800, rt_tolerance=25.0,
+        planted_fraction=0.6, max_planted=None, n_fragments=96,
+    ),
     # config 2: 50k precursors, Thermo shape (91 200 spectra, ~1.4e8 peaks)
     "config2": dict(
         seed=2, n_precursors=50_000, n_cycles=1200, n_windows=75, quad_lo=400.0, quad_hi=1000.0,

@@ -29,6 +29,11 @@
 
 #ifdef _OPENMP
 #include <omp.h>
+
+/* fragments one candidate may keep in the oracle (the device's dense tables stop at ADB_MAX_FRAGMENTS = 32, its ragged
+ * results at 64; the oracle covers both) */
+#define ORACLE_MAX_FRAGMENTS 128
+
 #endif
 
 #define ISOTOPE_DIFF 1.0033548350700006
@@ -529,9 +534,9 @@ int adbo_select_candidates(const adb_rawfile3d_desc* raw, const adb_library_desc
 
 typedef struct { /* FragmentContainer subset, fragment_container.py:12-45 */
   int n;
-  float mz_library[ADB_MAX_FRAGMENTS], mz[ADB_MAX_FRAGMENTS], intensity[ADB_MAX_FRAGMENTS];
-  uint8_t type[ADB_MAX_FRAGMENTS], loss_type[ADB_MAX_FRAGMENTS], charge[ADB_MAX_FRAGMENTS],
-      number[ADB_MAX_FRAGMENTS], position[ADB_MAX_FRAGMENTS];
+  float mz_library[ORACLE_MAX_FRAGMENTS], mz[ORACLE_MAX_FRAGMENTS], intensity[ORACLE_MAX_FRAGMENTS];
+  uint8_t type[ORACLE_MAX_FRAGMENTS], loss_type[ORACLE_MAX_FRAGMENTS], charge[ORACLE_MAX_FRAGMENTS],
+      number[ORACLE_MAX_FRAGMENTS], position[ORACLE_MAX_FRAGMENTS];
 } frag_set;
 
 /* features/features_utils.py:9-26 weighted_center_mean on x[S][C] (row-major nonzero order) */
@@ -715,8 +720,8 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
     int* ord = (int*)malloc(sizeof(int) * (size_t)(m + 1));
     argsort_f32(inten, m, ord);
     int k = m < K ? m : K;
-    if (k > ADB_MAX_FRAGMENTS) k = ADB_MAX_FRAGMENTS;
-    int64_t sel[ADB_MAX_FRAGMENTS]; float selmz[ADB_MAX_FRAGMENTS]; int ord2[ADB_MAX_FRAGMENTS];
+    if (k > ORACLE_MAX_FRAGMENTS) k = ORACLE_MAX_FRAGMENTS;
+    int64_t sel[ORACLE_MAX_FRAGMENTS]; float selmz[ORACLE_MAX_FRAGMENTS]; int ord2[ORACLE_MAX_FRAGMENTS];
     for (int r = 0; r < k; r++) { sel[r] = src[ord[m - 1 - r]]; selmz[r] = lib->frag_mz[sel[r]]; }
     argsort_f32(selmz, k, ord2);
     fr.n = k;
@@ -743,7 +748,7 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
   float q0 = (float)((double)mn - 0.5), q1 = (float)((double)mx + 0.5);
 
   /* candidate.py:216-246 dense cubes, always carried as [..][S][C] from here on */
-  float lo[ADB_MAX_FRAGMENTS], hi[ADB_MAX_FRAGMENTS];
+  float lo[ORACLE_MAX_FRAGMENTS], hi[ORACLE_MAX_FRAGMENTS];
   int F = fr.n;
   int64_t C = 0;
   int nobs = 0;
@@ -881,7 +886,7 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
   }
 
   /* candidate.py:319-329 fragment mask */
-  uint8_t fmask[ADB_MAX_FRAGMENTS];
+  uint8_t fmask[ORACLE_MAX_FRAGMENTS];
   int Fv = 0;
   for (int f = 0; f < F; f++) {
     float t_o = 0;
@@ -993,8 +998,8 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
   }
 
   /* ---------------- features/fragment_features.py:198-427 ---------------- */
-  double ofmm[ADB_MAX_FRAGMENTS], mass_error[ADB_MAX_FRAGMENTS], ofh_mean[ADB_MAX_FRAGMENTS], area_norm[ADB_MAX_FRAGMENTS];
-  float fin[ADB_MAX_FRAGMENTS];
+  double ofmm[ORACLE_MAX_FRAGMENTS], mass_error[ORACLE_MAX_FRAGMENTS], ofh_mean[ORACLE_MAX_FRAGMENTS], area_norm[ORACLE_MAX_FRAGMENTS];
+  float fin[ORACLE_MAX_FRAGMENTS];
   {
     fa[17] = (float)nobs;
     { float t = 0; for (int f = 0; f < F; f++) t = t + fr.intensity[f]; for (int f = 0; f < F; f++) fin[f] = fr.intensity[f] / t; }
@@ -1024,7 +1029,7 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
     if (w1 > C) w1 = C;
     if (w0 < 0) w0 = 0;
     int64_t wn = w1 - w0; if (wn < 0) wn = 0;
-    float ofi[ADB_MAX_FRAGMENTS];
+    float ofi[ORACLE_MAX_FRAGMENTS];
     for (int f = 0; f < F; f++) {
       double area = 0;
       for (int64_t t = 0; t + 1 < wn; t++) {
@@ -1090,7 +1095,7 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
       sum_ofh_mean += b;
       free(wrow);
     }
-    double find[ADB_MAX_FRAGMENTS];
+    double find[ORACLE_MAX_FRAGMENTS];
     for (int f = 0; f < F; f++) find[f] = (double)fin[f];
     if (any_height > 0) fa[18] = (float)corrcoef01(area_norm, find, F);
     if (sum_ofh_mean > 0.0) fa[19] = (float)corrcoef01(ofh_mean, find, F);
@@ -1123,7 +1128,7 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
     }
     /* fragment_features.py:387-396 */
     for (int f = 0; f < F; f++) mass_error[f] = (ofmm[f] - (double)fr.mz[f]) / (double)fr.mz[f] * 1e6;
-    int ord[ADB_MAX_FRAGMENTS];
+    int ord[ORACLE_MAX_FRAGMENTS];
     argsort_f32(fr.intensity, F, ord);
     { int n3 = F < 3 ? F : 3; double t = 0; for (int r = 0; r < n3; r++) t += mass_error[ord[F - 1 - r]]; fa[41] = (float)(t / (double)n3); }
     { double t = 0; for (int f = 0; f < F; f++) t += mass_error[f]; fa[42] = (float)(t / (double)F); }
@@ -1145,18 +1150,18 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
 
   /* ---------------- features/fragment_features.py:430-480 fragment_mobility_correlation (has_mobility) ------- */
   if (raw4) {
-    int idx[ADB_MAX_FRAGMENTS], nz = 0;
+    int idx[ORACLE_MAX_FRAGMENTS], nz = 0;
     for (int f = 0; f < F; f++) {
       float t_o = 0;
       for (int o = 0; o < nobs; o++) { float t_s = 0; for (int sc = 0; sc < S; sc++) t_s = t_s + fsp[((size_t)f * nobs + o) * S + sc]; t_o = t_o + t_s; }
       if (t_o > 0) idx[nz++] = f;
     }
     if (nz >= 3) {
-      float norm[ADB_MAX_FRAGMENTS];
+      float norm[ORACLE_MAX_FRAGMENTS];
       { float t = 0; for (int a = 0; a < nz; a++) t = t + fr.intensity[idx[a]]; for (int a = 0; a < nz; a++) norm[a] = fr.intensity[idx[a]] / t; }
       float* red = (float*)calloc((size_t)nz * nz, sizeof(float));
       float* cen = (float*)malloc(sizeof(float) * (size_t)nz * S);
-      float stdv[ADB_MAX_FRAGMENTS];
+      float stdv[ORACLE_MAX_FRAGMENTS];
       for (int o = 0; o < nobs; o++) { /* scoring/utils.py:513-571 fragment_correlation on the scan profiles */
         for (int a = 0; a < nz; a++) {
           const float* r = fsp + ((size_t)idx[a] * nobs + o) * S;
@@ -1193,11 +1198,11 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
   }
 
   /* ---------------- features/profile_features.py:18-206 ---------------- */
-  float corr_list[ADB_MAX_FRAGMENTS];
+  float corr_list[ORACLE_MAX_FRAGMENTS];
   {
-    int ord[ADB_MAX_FRAGMENTS];
+    int ord[ORACLE_MAX_FRAGMENTS];
     argsort_f32(fr.intensity, F, ord);
-    int sorted_idx[ADB_MAX_FRAGMENTS];
+    int sorted_idx[ORACLE_MAX_FRAGMENTS];
     for (int r = 0; r < F; r++) sorted_idx[r] = ord[F - 1 - r];
     int n3 = F < 3 ? F : 3;
     float top3 = 0;
@@ -1218,7 +1223,7 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
         if (ci_ > 0) for (int64_t c = 0; c < C; c++) nrm[(size_t)f * C + c] = (float)((double)isl[(size_t)f * C + c] / ci_);
       }
       float* med = (float*)malloc(sizeof(float) * (size_t)C);
-      float tmpv[ADB_MAX_FRAGMENTS];
+      float tmpv[ORACLE_MAX_FRAGMENTS];
       for (int64_t c = 0; c < C; c++) { for (int f = 0; f < F; f++) tmpv[f] = nrm[(size_t)f * C + c]; med[c] = median_f32(tmpv, F); }
       /* correlation_coefficient(median_profile, intensity_slice) */
       float sx = 0; for (int64_t c = 0; c < C; c++) sx = sx + med[c];
@@ -1246,7 +1251,7 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
       /* scoring/utils.py:513-571 fragment_correlation, float32 throughout */
       float* red = (float*)calloc((size_t)F * F, sizeof(float));
       float* cen = (float*)malloc(sizeof(float) * (size_t)F * C);
-      float stdv[ADB_MAX_FRAGMENTS];
+      float stdv[ORACLE_MAX_FRAGMENTS];
       for (int o = 0; o < nobs; o++) {
         for (int f = 0; f < F; f++) {
           const float* r = ffp + ((size_t)f * nobs + o) * C;
@@ -1334,7 +1339,7 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
     /* profile_features.py:190-204 delta_frame_peak */
     {
       double acc = 0;
-      double tmpd[ADB_MAX_FRAGMENTS];
+      double tmpd[ORACLE_MAX_FRAGMENTS];
       for (int o = 0; o < nobs; o++) {
         for (int f = 0; f < F; f++) {
           const float* r = ffp + ((size_t)f * nobs + o) * C;
@@ -1389,7 +1394,7 @@ static void zero_scores(const adb_scoring_config* cfg, int64_t n, adb_scores_out
 /* scoring.py:114-137 over all candidates */
 int adbo_score_candidates(const adb_rawfile3d_desc* raw, const adb_library_desc* lib, const adb_scoring_config* cfg,
                           const adb_candidates_in* cand, adb_scores_out* out, int32_t n_threads, adbo_scoring_tap* tap) {
-  if (cfg->top_k_fragments > ADB_MAX_FRAGMENTS) return 1;
+  if (cfg->top_k_fragments > ORACLE_MAX_FRAGMENTS) return 1;
   zero_scores(cfg, cand->n, out);
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
@@ -1605,7 +1610,7 @@ static int extract_cubes_4d(const adb_rawfile4d_desc* raw, int64_t frame_start, 
   size_t tot = (size_t)n_q * nobs * S * C;
   float* di = (float*)calloc(tot, sizeof(float));
   float* dm = (float*)calloc(tot, sizeof(float));
-  float lo[ADB_MAX_FRAGMENTS > ADB_MAX_ISOTOPES ? ADB_MAX_FRAGMENTS : ADB_MAX_ISOTOPES], hi[ADB_MAX_FRAGMENTS > ADB_MAX_ISOTOPES ? ADB_MAX_FRAGMENTS : ADB_MAX_ISOTOPES];
+  float lo[ORACLE_MAX_FRAGMENTS > ADB_MAX_ISOTOPES ? ORACLE_MAX_FRAGMENTS : ADB_MAX_ISOTOPES], hi[ORACLE_MAX_FRAGMENTS > ADB_MAX_ISOTOPES ? ORACLE_MAX_FRAGMENTS : ADB_MAX_ISOTOPES];
   mass_range_f32tol(mz, n_q, tol, lo, hi);
   for (int j = 0; j < n_q; j++) {
     int64_t t0, t1;
@@ -1842,7 +1847,7 @@ int adbo_select_candidates_4d(const adb_rawfile4d_desc* raw, const adb_library_d
 
 int adbo_score_candidates_4d(const adb_rawfile4d_desc* raw, const adb_library_desc* lib, const adb_scoring_config* cfg,
                              const adb_candidates_in* cand, adb_scores_out* out, int32_t n_threads) {
-  if (cfg->top_k_fragments > ADB_MAX_FRAGMENTS) return 1;
+  if (cfg->top_k_fragments > ORACLE_MAX_FRAGMENTS) return 1;
   zero_scores(cfg, cand->n, out);
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);

@@ -521,6 +521,45 @@ def run_transpose():
     print(f"[transpose] wrote {path} ({os.path.getsize(path) / 1e3:.1f} kB)", flush=True)
 
 
+def run_k9999_f48(threads: int):
+    """The same requantification scoring (top_k_fragments = 9999) on the 48-fragment library `parity_f48` - more fragments per
+    candidate than the dense device tables hold (32) - with the candidates the reference itself selects
+    -> tests/golden/k9999_f48.npz (candidate table, feature matrix, fragment table)."""
+    name = "parity_f48"
+    raw, precursor_df, fragment_df, p = make_config_3d(name)
+    dia = refshim.RefDiaData(raw)
+    sel_mod = refshim.ref("alphadia.search.selection.selection")
+    cfg_mod = refshim.ref("alphadia.search.selection.config_df")
+    sc_mod = refshim.ref("alphadia.search.scoring.scoring")
+    sccfg_mod = refshim.ref("alphadia.search.scoring.config")
+    sel_cfg = cfg_mod.CandidateSelectionConfig()
+    sel_cfg.update({**SELECTION_BASE, "rt_tolerance": float(p["rt_tolerance"]), "mobility_tolerance": 0.1, "candidate_count": 3,
+                    "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0})
+    sel = sel_mod.CandidateSelection(dia, precursor_df.copy(), fragment_df.copy(), sel_cfg, rt_column="rt_library",
+                                     mobility_column="mobility_library", precursor_mz_column="mz_library",
+                                     fragment_mz_column="mz_library", fwhm_rt=5.0, fwhm_mobility=0.01)
+    cand = sel(thread_count=threads)
+    print(f"[k9999_f48] selection -> {len(cand)} candidates", flush=True)
+    sc_cfg = sccfg_mod.CandidateScoringConfig()
+    sc_cfg.update({**SCORING_BASE, "precursor_mz_tolerance": 5, "fragment_mz_tolerance": 10, "top_k_fragments": 9999})
+    scorer = sc_mod.CandidateScoring(dia_data=dia, precursors_flat=precursor_df.copy(), fragments_flat=fragment_df.copy(), config=sc_cfg,
+                                     rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+                                     fragment_mz_column="mz_library")
+    feat, frag = scorer(cand.copy(), thread_count=threads, include_decoy_fragment_features=True)
+    print(f"[k9999_f48] scoring -> {len(feat)} rows, {len(frag)} fragment rows", flush=True)
+    out = {"input_checksum": np.array(input_checksum(raw, precursor_df, fragment_df))}
+    for c in cand.columns:
+        out[f"cand_{c}"] = cand[c].values
+    out["feat_matrix"] = feat[sc_mod.DEFAULT_FEATURE_COLUMNS].values.astype(np.float32)
+    out["feat_precursor_idx"] = feat["precursor_idx"].values
+    out["feat_rank"] = feat["rank"].values
+    for c in frag.columns:
+        out[f"frag_{c}"] = frag[c].values
+    path = os.path.join(HERE, "k9999_f48.npz")
+    np.savez_compressed(path, **out)
+    print(f"[k9999_f48] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def run_classifier():
     """BinaryClassifierLegacyNewBatching of the unmodified reference (alphadia/fdr/classifiers.py:145-532), trained here on
     the CPU for three epochs: its state dict, inputs and predict_proba output -> tests/golden/classifier_small.npz."""
@@ -606,5 +645,7 @@ if __name__ == "__main__":
             run_k9999(threads)
         elif n == "classifier":
             run_classifier()
+        elif n == "k9999_f48":
+            run_k9999_f48(threads)
         else:
             run(n, threads, variants=(n in ("parity_small", "parity_4d", "parity_4d_overlap", "parity_f20", "parity_4d_f20")))

@@ -1251,3 +1251,40 @@ def test_ragged_scores_empty_and_all_invalid(engine):
     dense = engine.score_candidates(draw, dlib, scfg, cin)
     assert not dense["valid"].any() and rag["n_rows"] == 0 and rag["n_fragments"] == 0
     dlib.close(); draw.close()
+
+
+@pytest.mark.parametrize("name", ["parity_f48", "parity_f96"])
+def test_wide_fragment_library_ragged(engine, oracle_lib, name):
+    """48 / 96 library fragments per precursor: selection (plan over all of them, top 12 layers) bit-exact, ragged scoring with
+    top_k_fragments = 9999 (every fragment kept, more than the dense tables' 32 slots) against the oracle at the same width
+    and, for 48, the live reference's tables (tests/golden/k9999_f48.npz)."""
+    wide = int(name[len("parity_f"):])
+    raw, lib, p, draw, dlib = _device_objects(engine, name)
+    cfg = H.selection_config(p["rt_tolerance"]).to_struct()
+    kernel = H.default_kernel(raw)
+    got = engine.select_candidates(draw, dlib, cfg, kernel)
+    ref = oracle_lib.select_candidates(raw, lib, cfg, kernel)
+    assert_candidates_equal(got, ref)
+    m = got["score"] > 0
+    cin, keep = H.candidates_in_from_arrays(lib, {c: got[c][m] for c in INT_COLS})
+    for kw in (dict(), dict(quant_all=False, experimental_xic=False)):
+        o = oracle_lib.score_candidates(raw, lib, H.scoring_config(top_k_fragments=wide, **kw).to_struct(), cin)
+        rag = engine.score_candidates_ragged(draw, dlib, H.scoring_config(top_k_fragments=9999, **kw).to_struct(), cin, max_fragments=wide)
+        v = o["valid"].astype(bool)
+        assert np.array_equal(rag["row_index"], np.nonzero(v)[0])
+        F, G = rag["features"], o["features"][v]
+        err = np.abs(F - G) / np.maximum(np.maximum(np.abs(F), np.abs(G)), feature_scale_floor(G)[None, :])
+        assert np.where(np.isnan(F) & np.isnan(G), 0.0, err).max() < RTOL
+        fm = (o["fragment_mz_library"] > 0) & v[:, None]
+        assert rag["n_fragments"] == int(fm.sum()) and fm.sum(axis=1).max() == wide
+        for k in FRAG_U8:
+            assert np.array_equal(rag[k], o[k][fm]), k
+        for k in FRAG_F32:
+            assert H.rel_err(rag[k], o[k][fm]).max() < RTOL, k
+    g = H.load_golden("k9999_f48") if wide == 48 else None
+    if g is not None and str(g["input_checksum"]) == H.input_checksum(*H.workload("parity_f48")[:3]):
+        rag = engine.score_candidates_ragged(draw, dlib, H.scoring_config(top_k_fragments=9999).to_struct(), cin, max_fragments=48)
+        assert np.array_equal(keep["precursor_idx"][rag["row_index"]], g["feat_precursor_idx"])
+        assert np.array_equal(rag["fragment_mz_library"], g["frag_mz_library"]) and np.array_equal(rag["fragment_number"], g["frag_number"])
+        assert H.rel_err(rag["fragment_intensity"], g["frag_intensity"]).max() < RTOL
+    dlib.close(); draw.close()

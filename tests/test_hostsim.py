@@ -97,3 +97,23 @@ def test_hostsim_ragged_library_and_edge_windows(oracle_lib):
         ref = oracle_lib.score_candidates(raw, lib, cfg, cin)
         assert 0 < ref["valid"].sum() < int(cin.n)
         assert_scores_close(hostsim.score_candidates(raw, lib, cfg, cin), ref, what=f"edge/{variant}")
+
+
+@pytest.mark.parametrize("name,kw", [("parity_f48", dict(top_k_fragments=9999)),
+                                     ("parity_f48", dict(top_k_fragments=40, quant_all=False, experimental_xic=False)),
+                                     ("parity_f96", dict(top_k_fragments=9999))])
+def test_hostsim_wide_fragment_libraries(oracle_lib, name, kw):
+    """48 and 96 library fragments per precursor (more than the 32 slots of the dense device tables; the ragged entry keeps up to
+    128): the scoring passes with top_k_fragments = 9999 / 40 against the oracle at the same width."""
+    raw, pdf, fdf, lib, p = H.workload(name)
+    sel = oracle_lib.select_candidates(raw, lib, H.selection_config(p["rt_tolerance"]).to_struct(), H.default_kernel(raw))
+    m = sel["score"] > 0
+    cin, keep = H.candidates_in_from_arrays(lib, {c: sel[c][m] for c in INT_COLS})
+    wide = int(np.max(lib["frag_stop_idx"] - lib["frag_start_idx"]))
+    assert wide == int(name[len("parity_f"):])
+    k_eff = min(int(kw["top_k_fragments"]), wide)
+    ref = oracle_lib.score_candidates(raw, lib, H.scoring_config(**{**kw, "top_k_fragments": k_eff}).to_struct(), cin)
+    assert ref["valid"].sum() > 100 and (ref["fragment_mz_library"] > 0).sum(axis=1).max() == k_eff
+    cfg = H.scoring_config(**{**kw, "top_k_fragments": k_eff}).to_struct()
+    got = hostsim.score_candidates(raw, lib, cfg, cin, batch=97, ks=k_eff)
+    assert_scores_close(got, ref, what=f"{name}/{kw}")

@@ -81,13 +81,16 @@ def test_scoring_vs_reference(name, tag, oracle_lib):
             assert np.array_equal(a, b), k
 
 
-def test_scoring_top_k_9999_vs_reference(oracle_lib):
+@pytest.mark.parametrize("name,golden", [("parity_f20", "k9999"), ("parity_f48", "k9999_f48")])
+def test_scoring_top_k_9999_vs_reference(oracle_lib, name, golden):
     """Transfer-library requantification (transfer_library_requantification_handler.py:102-124, top_k_fragments = 9999): the
-    live reference quantifies every library fragment (20 per precursor here).  A candidate keeps at most the fragments its
-    precursor has, so the oracle at the library's width must reproduce the reference's tables (tests/golden/k9999.npz)."""
-    g, raw, lib, p = _golden("parity_f20")
-    g9 = H.load_golden("k9999")
-    assert g9 is not None and str(g9["input_checksum"]) == str(g["input_checksum"])
+    live reference quantifies every library fragment (20 / 48 per precursor here - 48 is more than the dense device tables
+    hold).  A candidate keeps at most the fragments its precursor has, so the oracle at the library's width must reproduce the
+    reference's tables (tests/golden/k9999.npz, k9999_f48.npz)."""
+    g9 = H.load_golden(golden)
+    raw, pdf, fdf, lib, p = H.workload(name)
+    assert g9 is not None and str(g9["input_checksum"]) == H.input_checksum(raw, pdf, fdf)
+    g = g9 if "cand_precursor_idx" in g9.files else H.load_golden(name)
     cin, keep = H.candidates_in_from_arrays(lib, {c: g["cand_" + c] for c in INT_COLS})
     wide = int(np.max(lib["frag_stop_idx"] - lib["frag_start_idx"]))
     arrs = oracle_lib.score_candidates(raw, lib, H.scoring_config(top_k_fragments=wide).to_struct(), cin)
