@@ -571,7 +571,7 @@ def test_unsupported_inputs_fail_loudly(engine):
     raw, pdf, fdf, lib0, p = H.workload("parity_small")
     draw = engine.DeviceRawFile(raw, device=0)
     lib = {k: v.copy() for k, v in lib0.items()}
-    lib["frag_stop_idx"][0] = lib["frag_start_idx"][0] + 100  # > 64 library fragments for one precursor
+    lib["frag_stop_idx"][0] = lib["frag_start_idx"][0] + 200  # > 128 library fragments for one precursor
     dlib = engine.DeviceLibrary(lib, device=0)
     with pytest.raises(RuntimeError, match="library fragments"):
         engine.select_candidates(draw, dlib, H.selection_config(p["rt_tolerance"]).to_struct(), H.default_kernel(raw))
