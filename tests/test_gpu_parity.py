@@ -1280,7 +1280,9 @@ def test_wide_fragment_library_ragged(engine, oracle_lib, name):
         for k in FRAG_U8:
             assert np.array_equal(rag[k], o[k][fm]), k
         for k in FRAG_F32:
-            assert H.rel_err(rag[k], o[k][fm]).max() < RTOL, k
+            # the mass error (ppm) is a difference of two nearly equal m/z values: relative to 0.01 ppm at least
+            floor = 1e-2 if k == "fragment_mass_error" else 1e-6
+            assert H.rel_err(rag[k], o[k][fm], floor=floor).max() < RTOL, k
     g = H.load_golden("k9999_f48") if wide == 48 else None
     if g is not None and str(g["input_checksum"]) == H.input_checksum(*H.workload("parity_f48")[:3]):
         rag = engine.score_candidates_ragged(draw, dlib, H.scoring_config(top_k_fragments=9999).to_struct(), cin, max_fragments=48)
