@@ -1061,8 +1061,10 @@ __device__ void score_one_4d(const Score4Params& P, int64_t ci, Small4& sm, floa
   if (lane == 0) P.out.valid[ci] = 1;
 }
 
+// 4 resident CTAs (16 warps) per SM: 126 registers per thread without spills; left to itself ptxas takes 178 registers and
+// only 2 CTAs fit, which costs this latency-bound kernel a third of its speed (config 4: 117 -> 86 ms; 5 and 6 CTAs: same)
 #ifndef SC4_MIN_CTAS
-#define SC4_MIN_CTAS 1
+#define SC4_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(SC4_THREADS, SC4_MIN_CTAS) adb_score4d_kernel(const __grid_constant__ Score4Params P) {
   __shared__ Small4 small[SC4_WARPS];
