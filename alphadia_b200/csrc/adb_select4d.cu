@@ -30,7 +30,9 @@
 #include "adb_common.cuh"
 
 #define FULL 0xffffffffu
+#ifndef S4_THREADS
 #define S4_THREADS 256
+#endif
 #define S4_WARPS (S4_THREADS / 32)
 #define S4_MAX_LAYERS (ADB_MAX_LIB_FRAGMENTS + ADB_MAX_ISOTOPES)
 #define S4_MAX_CAND 16
