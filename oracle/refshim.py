@@ -15,6 +15,10 @@ Shims — all outside the arithmetic except the FFT:
      replaced by the arithmetic definition the oracle uses — direct circular same-size
      convolution, fp64 FMA accumulation over kernel rows then columns ascending, one rounding
      to f32 — see oracle/adb_oracle.c:conv_circular.
+     With ``ADB_REFSHIM_FFT=pocketfft`` in the environment the module instead follows fft.py:141-212 step by step
+     (rfft2 of the zero-padded kernel, product, irfft2, the four-block roll) on scipy.fft's single-precision pocketfft —
+     the library rocket-fft binds.  Only ``tests/golden/measure_fft_disagreement.py`` uses that mode: it measures how far
+     the candidate tables move between the two convolutions; no golden vector comes from it.
 """
 
 from __future__ import annotations
@@ -120,6 +124,68 @@ def _make_pjit():
     return pjit, set_threads
 
 
+def _make_pocketfft_module():
+    """fft.py:141-212 on scipy.fft (pocketfft, complex64): the measurement mode, see the module docstring."""
+    import numba as nb
+    import scipy.fft as sf
+    from numba.extending import overload
+
+    class NumbaContextOnly(Exception):
+        pass
+
+    def convolve_fourier(dense, kernel):
+        raise NumbaContextOnly("numba context only")
+
+    def _layer(x, fourier_filter, k0, k1, out):
+        delta0, delta1 = -k0 // 2, -k1 // 2
+        layer = sf.irfft2(sf.rfft2(x) * fourier_filter, s=x.shape).astype(np.float32, copy=False)
+        out[delta0:, delta1:] = layer[:-delta0, :-delta1]
+        out[:delta0, delta1:] = layer[-delta0:, :-delta1]
+        out[delta0:, :delta1] = layer[:-delta0, -delta1:]
+        out[:delta0, :delta1] = layer[-delta0:, -delta1:]
+
+    def _py_conv(dense, kernel):
+        dense = np.ascontiguousarray(dense, dtype=np.float32)
+        kernel = np.ascontiguousarray(kernel, dtype=np.float32)
+        k0, k1 = kernel.shape
+        ff = sf.rfft2(kernel, s=dense.shape[-2:])
+        assert ff.dtype == np.complex64
+        out = np.zeros_like(dense)
+        flat_in = dense.reshape((-1,) + dense.shape[-2:])
+        flat_out = out.reshape((-1,) + dense.shape[-2:])
+        for i in range(flat_in.shape[0]):
+            _layer(flat_in[i], ff, k0, k1, flat_out[i])
+        return out
+
+    @overload(convolve_fourier)
+    def _ov(dense, kernel):
+        if dense.ndim == 2:
+            def impl(dense, kernel):
+                with nb.objmode(out="float32[:,::1]"):
+                    out = _py_conv(dense, kernel)
+                return out
+            return impl
+        if dense.ndim == 3:
+            def impl(dense, kernel):
+                with nb.objmode(out="float32[:,:,::1]"):
+                    out = _py_conv(dense, kernel)
+                return out
+            return impl
+        if dense.ndim == 4:
+            def impl(dense, kernel):
+                with nb.objmode(out="float32[:,:,:,::1]"):
+                    out = _py_conv(dense, kernel)
+                return out
+            return impl
+        return None
+
+    m = types.ModuleType("alphadia.search.selection.fft")
+    m.NumbaContextOnly = NumbaContextOnly
+    m.convolve_fourier = convolve_fourier
+    m._py_conv = _py_conv
+    return m
+
+
 def _make_fft_module():
     import numba as nb
     from numba.extending import overload
@@ -223,7 +289,10 @@ def install() -> None:
 
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    sys.modules["alphadia.search.selection.fft"] = _make_fft_module()
+    import os
+
+    pocket = os.environ.get("ADB_REFSHIM_FFT", "") == "pocketfft"
+    sys.modules["alphadia.search.selection.fft"] = _make_pocketfft_module() if pocket else _make_fft_module()
     _installed = True
 
 
