@@ -53,7 +53,16 @@
 // consecutive addresses.  The pass bodies index their block through the small pointer wrappers below and are written as if
 // the block were contiguous (DP_W = 1 is exactly that layout).
 #ifndef DP_W
-#define DP_W 8   // measured on config 3: 1 (contiguous blocks) 54.1 ms, 4 / 8 / 16: 46.7 ms, 32: 48.2 ms (padding to the largest block of a tile)
+#define DP_W 8
+// dp_template keeps its loops rolled: unrolled by the compiler the kernel is 9 600 instructions (154 KB) and stalls on instruction
+// fetch (7 of 15 stall cycles per issue); rolled it is 5 400 and config 3 scoring goes 45.5 -> 44.2 ms.  The same limit on
+// dp_fragment / dp_aggregate costs memory-level parallelism and measured slower (45.0 / 45.1 ms).
+#ifndef DP_TPL_UNROLL_N
+#define DP_TPL_UNROLL_N 1
+#endif
+#define DP_PRAGMA_(x) _Pragma(#x)
+#define DP_PRAGMA(x) DP_PRAGMA_(x)
+#define DP_TPL_UNROLL DP_PRAGMA(unroll DP_TPL_UNROLL_N)   // measured on config 3: 1 (contiguous blocks) 54.1 ms, 4 / 8 / 16: 46.7 ms, 32: 48.2 ms (padding to the largest block of a tile)
 #endif
 
 template <typename T>
@@ -537,7 +546,9 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
     iso_mz[i] = (float)((double)i * ADB_ISOTOPE_DIFF / charge) + pmz;
   }
   // quadrupole.py:304-324 template
+DP_TPL_UNROLL
   for (int o = 0; o < nobs; o++)
+DP_TPL_UNROLL
     for (int c = 0; c < C; c++) {
       double acc = 0;
       for (int i = 0; i < nI; i++) acc = acc + (double)(dpi[c * nI + i] * iso_int[i]) * qtf[i * nobs + o];
@@ -545,16 +556,21 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
     }
   // quadrupole.py:327-335 observation importance
   float tot = 0.f;
+DP_TPL_UNROLL
   for (int o = 0; o < nobs; o++) {
     float s = 0.f;
+DP_TPL_UNROLL
     for (int c = 0; c < C; c++) s = s + tmpl[o * C + c];
     sc[SC_STI + o] = dp_twice(s);  // sum_template_intensity, also used by the cosine score
     tot = tot + sc[SC_STI + o];
   }
+DP_TPL_UNROLL
   for (int o = 0; o < nobs; o++) sc[SC_OI + o] = (tot == 0.f) ? 1.0f / (float)nobs : sc[SC_STI + o] / tot;
   // candidate.py:341 template frame profile with or_envelope (scoring/utils.py:46-53) and its statistics
+DP_TPL_UNROLL
   for (int o = 0; o < nobs; o++) {
     float ys = 0.f;
+DP_TPL_UNROLL
     for (int c = 0; c < C; c++) {
       const float x = dp_twice(tmpl[o * C + c]);
       float res = x;
@@ -567,26 +583,33 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
     }
     const float ym = ys / (float)C;
     float yss = 0.f;
+DP_TPL_UNROLL
     for (int c = 0; c < C; c++) { const float yc = tfp[o * C + c] - ym; yss = yss + yc * yc; }
     sc[SC_YM + o] = ym;
     sc[SC_YSTD + o] = sqrtf(yss / (float)C);
   }
   // distance-weight tables for weighted_center_mean (features_utils.py:9-26); the precursor "centres" are the constants
   // (n_scans, n_observations) = (2, 1): that table is the same for every candidate (P.wtab_p, dp_wtab_p_entry)
+DP_TPL_UNROLL
   for (int o = 0; o < nobs; o++) {  // fragment_features.py:20-49 centre of mass of the template
     const FPtr r = tmpl + o * C;
     double isum = 0, ssum = 0, fsum = 0;
     bool any = false;
+DP_TPL_UNROLL
     for (int s = 0; s < 2; s++)
+DP_TPL_UNROLL
       for (int c = 0; c < C; c++) { const float v = r[c]; if (v > 0.f) { any = true; isum = isum + (double)v; } }
     if (any)
+DP_TPL_UNROLL
       for (int s = 0; s < 2; s++)
+DP_TPL_UNROLL
         for (int c = 0; c < C; c++) {
           const float v = r[c];
           if (v > 0.f) { ssum = ssum + (double)s * (double)v; fsum = fsum + (double)c * (double)v; }
         }
     const double esc = (any && isum > 0) ? ssum / isum : 0.0;
     const double efc = (any && isum > 0) ? fsum / isum : 0.0;
+DP_TPL_UNROLL
     for (int t = 0; t < 2 * C; t++) {
       const int s = t / C, c = t % C;
       const double ds = (double)s - esc, dc = (double)c - efc;
@@ -594,6 +617,7 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
     }
   }
   const FPtr fa = sc + SC_FEAT;
+DP_TPL_UNROLL
   for (int t = 0; t < ADB_NUM_FEATURES; t++) fa[t] = 0.f;
   // features/location_features.py:9-33
   fa[0] = raw.mobility_values[scan_start] - raw.mobility_values[scan_stop - 1];
@@ -606,9 +630,11 @@ ADB_HD void dp_template(const DpParams& P, int64_t j) {
   double H[ADB_MAX_ISOTOPES], MZo[ADB_MAX_ISOTOPES];
   for (int i = 0; i < nI; i++) {
     float tc = 0.f;
+DP_TPL_UNROLL
     for (int c = 0; c < C; c++) tc = tc + dpi[c * nI + i];
     spi[i] = dp_twice(tc);
     float wsp = 0.f;
+DP_TPL_UNROLL
     for (int o = 0; o < nobs; o++) wsp = wsp + spi[i] * sc[SC_OI + o];
     wspi[i] = wsp;
     dp_weighted_center_mean_pair(dpi + i, dpm + i, nI, P.wtab_p, DP_WTAB_P_STRIDE, C, H[i], MZo[i]);
