@@ -578,7 +578,14 @@ class CandidateScoring:
                 self.precursor_mz_column, precursor_df_columns,
             )
         candidates_psm_df["delta_rt"] = candidates_psm_df["rt_observed"] - candidates_psm_df[self.rt_column]
-        n_k, n_r, n_p = count_residues(candidates_psm_df["sequence"].array, ["K", "R", "P"])
+        flat = self.precursors_flat_df
+        if (positions is not None and "sequence" in flat.columns and "sequence" not in cols and "sequence" not in feature_columns
+                and len(flat) <= len(candidates_psm_df)):
+            # the sequences were gathered from precursors_flat by row: count once per precursor and gather the counts
+            prow = positions["precursor_rows"]
+            n_k, n_r, n_p = (c[prow] for c in count_residues(flat["sequence"].array, ["K", "R", "P"]))
+        else:
+            n_k, n_r, n_p = count_residues(candidates_psm_df["sequence"].array, ["K", "R", "P"])
         candidates_psm_df["n_K"], candidates_psm_df["n_R"], candidates_psm_df["n_P"] = n_k, n_r, n_p
         return candidates_psm_df
 
@@ -640,12 +647,18 @@ class CandidateScoring:
         for col in FRAGMENT_COLUMNS[2:]:
             tasks[col] = (slots, psm["fragment_" + col])
         right_columns = ["elution_group_idx", "decoy"]
-        per_cand_df = merge_missing_columns(pd.DataFrame({"precursor_idx": psm["precursor_idx"]}), self.precursors_flat_df,
-                                            right_columns, on=["precursor_idx"], how="left")
-        lookup_per_candidate = len(per_cand_df) == n  # False only if precursors_flat repeats a precursor_idx
-        if lookup_per_candidate:
+        positions = psm.get("positions")
+        if positions is not None and len(positions["precursor_rows"]) == n:  # row mapping known: gather, no key search
+            lookup_per_candidate = True
             for col in right_columns:
-                tasks[col] = (per_candidate, per_cand_df[col].values)
+                tasks[col] = (per_candidate, self.precursors_flat_df[col].values[positions["precursor_rows"]])
+        else:
+            per_cand_df = merge_missing_columns(pd.DataFrame({"precursor_idx": psm["precursor_idx"]}), self.precursors_flat_df,
+                                                right_columns, on=["precursor_idx"], how="left")
+            lookup_per_candidate = len(per_cand_df) == n  # False only if precursors_flat repeats a precursor_idx
+            if lookup_per_candidate:
+                for col in right_columns:
+                    tasks[col] = (per_candidate, per_cand_df[col].values)
         df = pd.DataFrame(_run_column_tasks(tasks, n_rows), copy=False)  # fresh arrays: no consolidation copy
         if lookup_per_candidate:
             return df
