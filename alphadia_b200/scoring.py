@@ -191,15 +191,16 @@ def gather_missing_columns(left_df, right_df, right_columns, pos):
     if absent:
         raise ValueError(f"Columns {absent} must be present in right_df")
     out = left_df.reset_index(drop=True)
-    numeric = [c for c in missing if isinstance(right_df[c].dtype, np.dtype) and right_df[c].dtype != object]
-    gathered = _run_column_tasks({c: ((lambda a: a[pos]), right_df[c].values) for c in numeric}, len(out))  # numpy releases the GIL
+    numeric = {c for c in missing if isinstance(right_df[c].dtype, np.dtype) and right_df[c].dtype != object}
+    # numpy and pyarrow release the GIL inside the gathers: numeric and Arrow-backed string columns are taken side by side
+    gathered = _run_column_tasks({c: ((lambda a: a[pos]), right_df[c].values if c in numeric else right_df[c].array)
+                                  for c in missing}, len(out))
     new_cols = {}
     for c in missing:
-        if c in gathered:
+        if c in numeric:
             new_cols[c] = gathered[c]
         else:  # object / extension columns: keep the dtype (pandas would re-infer `str` from an object array)
-            src = right_df[c]
-            new_cols[c] = pd.Series(src.values[pos], index=out.index, dtype=src.dtype)
+            new_cols[c] = pd.Series(gathered[c], index=out.index, dtype=right_df[c].dtype)
     return pd.concat([out, pd.DataFrame(new_cols, index=out.index, copy=False)], axis=1)
 
 
