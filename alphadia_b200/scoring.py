@@ -158,7 +158,7 @@ def _merge_by_sorted_key(left_df, right_df, on, columns):
         if isinstance(src.dtype, np.dtype) and src.dtype != object:
             new_cols[c] = src.values[pos]
         else:  # object / extension columns: keep the dtype (pandas would re-infer `str` from an object array)
-            new_cols[c] = pd.Series(src.values[pos], index=out.index, dtype=src.dtype)
+            new_cols[c] = _series_like(_gather_source(src)[pos], src.dtype, out.index)
     # one concat instead of one block-manager insert per column
     return pd.concat([out, pd.DataFrame(new_cols, index=out.index, copy=False)], axis=1)
 
@@ -179,6 +179,20 @@ def _count_residues_arrow(sequences, res):
         return None
 
 
+def _gather_source(series: pd.Series):
+    """What to index when rows of a column are gathered: the numpy array of a numpy-typed column (object columns too - wrapped
+    as an extension array they would be scanned for missing values on every Series construction), else the extension array."""
+    return series.values if isinstance(series.dtype, np.dtype) else series.array
+
+
+def _series_like(values, dtype, index) -> pd.Series:
+    """A Series of ``dtype`` from gathered values.  An extension array that already has the dtype (``str`` columns) is wrapped
+    as it is: passing ``dtype=`` again makes pandas re-validate every element (a missing-value scan per column)."""
+    if not isinstance(dtype, np.dtype) and not isinstance(values, np.ndarray) and getattr(values, "dtype", None) == dtype:
+        return pd.Series(values, index=index, copy=False)
+    return pd.Series(values, index=index, dtype=dtype)
+
+
 def gather_missing_columns(left_df, right_df, right_columns, pos):
     """``merge_missing_columns(left_df, right_df, right_columns, on=key, how="left")`` when row ``i`` of ``left_df`` is known
     to match row ``pos[i]`` of ``right_df`` (unique right keys, every left key present): the columns missing on the left are
@@ -193,14 +207,13 @@ def gather_missing_columns(left_df, right_df, right_columns, pos):
     out = left_df.reset_index(drop=True)
     numeric = {c for c in missing if isinstance(right_df[c].dtype, np.dtype) and right_df[c].dtype != object}
     # numpy and pyarrow release the GIL inside the gathers: numeric and Arrow-backed string columns are taken side by side
-    gathered = _run_column_tasks({c: ((lambda a: a[pos]), right_df[c].values if c in numeric else right_df[c].array)
-                                  for c in missing}, len(out))
+    gathered = _run_column_tasks({c: ((lambda a: a[pos]), _gather_source(right_df[c])) for c in missing}, len(out))
     new_cols = {}
     for c in missing:
         if c in numeric:
             new_cols[c] = gathered[c]
         else:  # object / extension columns: keep the dtype (pandas would re-infer `str` from an object array)
-            new_cols[c] = pd.Series(gathered[c], index=out.index, dtype=right_df[c].dtype)
+            new_cols[c] = _series_like(gathered[c], right_df[c].dtype, out.index)
     return pd.concat([out, pd.DataFrame(new_cols, index=out.index, copy=False)], axis=1)
 
 
