@@ -108,19 +108,32 @@ def get_q_values(
 ) -> pd.DataFrame:
     """fdr.py:226-297: rows sorted by ``[score, decoy, *extra_sort_columns]`` with the q-value column added.
 
-    Restriction (documented divergence): a NaN in ``score_column`` or a decoy value other than 0 / 1 raises instead of being
-    sorted last as pandas would; ``perform_fdr`` drops rows with missing features before the classifier runs (fdr.py:84-98),
-    so its probabilities are finite."""
+    NaN scores sort last, as ``sort_values`` places them: the device ranks the rows with a score; the NaN rows follow in
+    ``[decoy, *extra_sort_columns]`` order, their FDR values continue the two running counts, and the running minimum from the
+    back (fdr.py:227-246) carries the smallest FDR of that tail into the q-values in front of it.  A decoy value other than
+    0 / 1 raises."""
     if extra_sort_columns is None:
         extra_sort_columns = ["precursor_idx"]
     decoy = df[decoy_column].to_numpy()
     if len(decoy) and not np.isin(decoy, (0, 1)).all():
         raise ValueError(f"{decoy_column} must hold 0 (target) or 1 (decoy)")
-    order, qval = _lib.q_values(
-        df[score_column].to_numpy().astype(np.float64, copy=False),
-        decoy.astype(np.uint8),
-        _pack_order_preserving(df, extra_sort_columns),
-    )
+    score = df[score_column].to_numpy().astype(np.float64, copy=False)
+    decoy8 = decoy.astype(np.uint8)
+    key = _pack_order_preserving(df, extra_sort_columns)
+    missing = np.isnan(score)
+    if not missing.any():
+        order, qval = _lib.q_values(score, decoy8, key)
+    else:
+        have = np.flatnonzero(~missing)
+        order_f, q_f = _lib.q_values(score[have], decoy8[have], key[have])
+        tail = np.flatnonzero(missing)
+        tail = tail[np.lexsort((key[tail], decoy8[tail]))]  # stable: decoy, then the tie-break key, then the row order
+        d_tail = decoy8[tail].astype(np.int64)
+        with np.errstate(all="ignore"):
+            fdr_tail = (int(decoy8[have].sum()) + np.cumsum(d_tail)) / (int((1 - decoy8[have].astype(np.int64)).sum()) + np.cumsum(1 - d_tail))
+        q_tail = np.flip(np.minimum.accumulate(np.flip(fdr_tail)))
+        order = np.concatenate([have[order_f], tail])
+        qval = np.concatenate([np.minimum(q_f, q_tail[0]), q_tail])
     out = df.iloc[order].copy()
     out[qval_column] = qval
     return out
@@ -129,13 +142,31 @@ def get_q_values(
 def keep_best(df: pd.DataFrame, score_column: str = "proba", group_columns: list[str] | None = None) -> pd.DataFrame:
     """fdr.py:195-224: the best-scoring (lowest ``score_column``) row of every group, in the original row order.
 
-    Restriction (documented divergence): NaN scores raise; rows whose group key is NaN form their own group here, while
-    ``groupby(...).head(1)`` of the reference drops them (integer group columns, the only ones the workflow uses, have no NaN)."""
+    Missing values as pandas treats them: rows whose group key holds a NaN / None belong to no group and are dropped
+    (``groupby`` default ``dropna=True``); a NaN score sorts after every number, so a group keeps a NaN row - its first -
+    only if none of its rows has a score."""
     if group_columns is None:
         group_columns = ["channel", "precursor_idx"]
     df = df.reset_index(drop=True)
-    keep = _lib.keep_best(df[score_column].to_numpy().astype(np.float64, copy=False), _pack_groups(df, group_columns))
-    return df[keep.astype(bool)].reset_index(drop=True)
+    in_group = ~df[list(group_columns)].isna().any(axis=1).to_numpy() if len(group_columns) else np.ones(len(df), dtype=bool)
+    if not in_group.all():
+        df_in = df[in_group]
+    else:
+        df_in = df
+    score = df_in[score_column].to_numpy().astype(np.float64, copy=False)
+    groups = _pack_groups(df_in, group_columns)
+    missing = np.isnan(score)
+    if not missing.any():
+        keep = _lib.keep_best(score, groups).astype(bool)
+    else:
+        keep = np.zeros(len(df_in), dtype=bool)
+        have = np.flatnonzero(~missing)
+        keep[have] = _lib.keep_best(score[have], groups[have]).astype(bool)
+        rest = np.flatnonzero(missing)
+        rest = rest[~np.isin(groups[rest], groups[have])]  # groups without any score: their first row
+        _, first = np.unique(groups[rest], return_index=True)
+        keep[rest[first]] = True
+    return df_in[keep].reset_index(drop=True)
 
 
 def _drop_incomplete(df: pd.DataFrame, columns, label: str) -> None:

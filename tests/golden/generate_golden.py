@@ -250,6 +250,27 @@ def run_fdr():
     print(f"[fdr] {len(df)} rows -> q-values {len(q)}, final {len(final)}; wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def run_fdr_nan():
+    """get_q_values / keep_best of the unmodified reference on a table with NaN scores and NaN group keys -> fdr_nan.npz."""
+    from tests.helpers import fdr_inputs_nan
+
+    fdr = refshim.ref("alphadia.fdr.fdr")
+    df = fdr_inputs_nan()
+    out = {"input_checksum": np.array(hashlib.sha256(df.to_numpy().tobytes() + df.index.to_numpy().tobytes()).hexdigest())}
+    with np.errstate(all="ignore"):
+        q = fdr.get_q_values(df.copy(), "proba", "_decoy")
+        q2 = fdr.get_q_values(df.copy(), "proba", "_decoy", extra_sort_columns=["rank", "gnan"])
+    out["q_row"], out["q_index"], out["q_qval"] = q["row"].values, q.index.values, q["qval"].values
+    out["q2_row"], out["q2_qval"] = q2["row"].values, q2["qval"].values
+    for tag, cols in {"precursor": ["precursor_idx"], "gnan": ["gnan"], "gnan_channel": ["gnan", "channel"]}.items():
+        kept = fdr.keep_best(df.copy(), group_columns=cols)
+        out[f"keep_{tag}_row"] = kept["row"].values
+    path = os.path.join(HERE, "fdr_nan.npz")
+    np.savez_compressed(path, **out)
+    print(f"[fdr_nan] {len(df)} rows, {int(df['proba'].isna().sum())} NaN scores, {int(df['gnan'].isna().sum())} NaN group keys; "
+          f"kept {[len(out[k]) for k in out if k.startswith('keep_')]}; wrote {path}", flush=True)
+
+
 def run_perform_fdr():
     """perform_fdr of the unmodified reference (alphadia/fdr/fdr.py:25-192) with a deterministic stand-in classifier on the
     scoring golden of parity_small -> tests/golden/perform_fdr_small.npz."""
@@ -627,6 +648,8 @@ if __name__ == "__main__":
             run_variants(threads)
         elif n == "fdr":
             run_fdr()
+        elif n == "fdr_nan":
+            run_fdr_nan()
         elif n == "perform_fdr":
             run_perform_fdr()
         elif n == "ragged":

@@ -191,6 +191,27 @@ def fdr_inputs(seed: int = 11, n: int = 6000):
     return df
 
 
+def fdr_inputs_nan(seed: int = 12, n: int = 3000):
+    """``fdr_inputs`` with missing values (tests/golden/fdr_nan.npz): NaN probabilities scattered over the table, every row
+    of a few precursors NaN (a group without any finite score), +inf next to NaN inside one group, and a float group
+    column ``gnan`` with missing keys (pandas drops such rows from a groupby)."""
+    df = fdr_inputs(seed, n)
+    rng = np.random.default_rng(seed + 1)
+    proba = df["proba"].to_numpy().copy()
+    pidx = df["precursor_idx"].to_numpy()
+    proba[rng.random(n) < 0.08] = np.nan
+    for p in np.unique(pidx)[:5]:  # groups that hold NaN only
+        proba[pidx == p] = np.nan
+    rows = np.flatnonzero(pidx == np.unique(pidx)[7])
+    if len(rows) >= 2:  # NaN first, +inf later in the same group: the +inf row wins (NaN sorts after every number)
+        proba[rows[0]], proba[rows[1:]] = np.nan, np.inf
+    df["proba"] = proba
+    g = (pidx % 50).astype(np.float64)
+    g[rng.random(n) < 0.1] = np.nan
+    df["gnan"] = g
+    return df
+
+
 class PseudoClassifier:
     """Deterministic stand-in for the FDR classifier (fit is a no-op): probability of being a decoy from two correlation
     features, rounded to two decimals so that ties occur.  Used identically by the golden generator (reference

@@ -887,6 +887,20 @@ def test_fdr_bookkeeping(engine, oracle_lib):
         fdr.get_q_values(pd.DataFrame({"precursor_idx": [0], "proba": [0.5], "_decoy": [2]}))
 
 
+def test_fdr_missing_values_device_vs_reference(engine):
+    """NaN scores / NaN group keys through the device calls against the live reference's tables (tests/golden/fdr_nan.npz)."""
+    from alphadia_b200 import fdr
+
+    g = H.load_golden("fdr_nan")
+    df = H.fdr_inputs_nan()
+    q = fdr.get_q_values(df.copy(), "proba", "_decoy")
+    assert np.array_equal(q["row"].values, g["q_row"]) and np.array_equal(q["qval"].values, g["q_qval"], equal_nan=True)
+    q2 = fdr.get_q_values(df.copy(), "proba", "_decoy", extra_sort_columns=["rank", "gnan"])
+    assert np.array_equal(q2["row"].values, g["q2_row"]) and np.array_equal(q2["qval"].values, g["q2_qval"], equal_nan=True)
+    for tag, cols in {"precursor": ["precursor_idx"], "gnan": ["gnan"], "gnan_channel": ["gnan", "channel"]}.items():
+        assert np.array_equal(fdr.keep_best(df.copy(), group_columns=cols)["row"].values, g[f"keep_{tag}_row"]), tag
+
+
 def test_perform_fdr_matches_reference_golden(engine):
     """The perform_fdr sequence (q-values -> fragment competition -> best per group -> q-values) on the device against the
     reference's perform_fdr run with the same stand-in classifier (tests/golden/perform_fdr_small.npz)."""

@@ -902,3 +902,29 @@ def test_classifier_state_dict_round_trip():
     assert set(sd["network_state_dict"]) == set(state)
     for k, v in state.items():
         assert np.array_equal(sd["network_state_dict"][k], v), k
+
+
+def test_fdr_missing_values_vs_reference(oracle_lib, monkeypatch):
+    """NaN scores and NaN group keys (tests/golden/fdr_nan.npz from the live reference): same rows, order and q-values."""
+    g = H.load_golden("fdr_nan")
+    if g is None:
+        pytest.skip("golden fdr_nan.npz missing")
+    import hashlib
+
+    df = H.fdr_inputs_nan()
+    assert str(g["input_checksum"]) == hashlib.sha256(df.to_numpy().tobytes() + df.index.to_numpy().tobytes()).hexdigest()
+    fdr = host_fdr_with_oracle(monkeypatch, oracle_lib)
+    q = fdr.get_q_values(df.copy(), "proba", "_decoy")
+    assert np.array_equal(q["row"].values, g["q_row"]) and np.array_equal(q.index.values, g["q_index"])
+    assert np.array_equal(q["qval"].values, g["q_qval"], equal_nan=True)
+    q2 = fdr.get_q_values(df.copy(), "proba", "_decoy", extra_sort_columns=["rank", "gnan"])
+    assert np.array_equal(q2["row"].values, g["q2_row"]) and np.array_equal(q2["qval"].values, g["q2_qval"], equal_nan=True)
+    for tag, cols in {"precursor": ["precursor_idx"], "gnan": ["gnan"], "gnan_channel": ["gnan", "channel"]}.items():
+        kept = fdr.keep_best(df.copy(), group_columns=cols)
+        assert np.array_equal(kept["row"].values, g[f"keep_{tag}_row"]), tag
+        assert np.array_equal(kept.index.values, np.arange(len(kept)))
+    # the NaN-only groups keep exactly one row each, the group with NaN first and +inf later keeps an +inf row
+    kept = fdr.keep_best(df.copy(), group_columns=["precursor_idx"])
+    pidx = np.unique(df["precursor_idx"].values)
+    assert kept[kept["precursor_idx"].isin(pidx[:5])]["proba"].isna().all() and len(kept[kept["precursor_idx"].isin(pidx[:5])]) == 5
+    assert np.isposinf(kept[kept["precursor_idx"] == pidx[7]]["proba"].values).all()
