@@ -6,7 +6,8 @@
 1. ``CandidateSelection(dia_data, precursors_flat, fragments_flat, config, ...)()``  -> candidates DataFrame
 2. ``CandidateScoring(dia_data=..., ...)(candidates_df)``                            -> (features_df, fragments_df)
 3. ``FragmentCompetition()(psm_df, fragments_df, dia_data.cycle)``                    -> surviving PSMs
-4. ``keep_best`` / ``get_q_values`` (alphadia_b200.fdr)                                -> best row per group with q-values
+4. ``perform_fdr(BinaryClassifierLegacyNewBatching(...), ...)`` (alphadia_b200.fdr)     -> best row per group with q-values
+   (classifier inference, q-values, fragment competition and best-row-per-group on the device)
 
 `dia_data` is whatever the reference passes around (an AlphaRaw / TimsTOFTranspose wrapper or its jitclass); here it is a
 synthetic run from ``alphadia_b200.synthetic`` so that the script has no external inputs.  The classes, their arguments and
@@ -52,15 +53,24 @@ t2 = time.perf_counter()
 print(f"scoring: {len(features_df)} scored candidates x {features_df.shape[1]} columns, {len(fragments_df)} fragment rows in {t2 - t1:.2f} s")
 print(features_df[["precursor_idx", "rank", "rt_observed", "intensity_correlation", "mean_observation_score", "delta_rt"]].head(3).to_string())
 
-if not getattr(raw, "has_mobility", False):  # the reference runs fragment competition for non-mobility data only (fdr/fdr.py:157)
-    psm_df = features_df.copy()
-    psm_df["proba"] = np.random.default_rng(0).uniform(0, 1, len(psm_df))  # stands in for the FDR classifier's output
-    kept = FragmentCompetition(rt_tol_seconds=3, mass_tol_ppm=15)(psm_df, fragments_df.copy(), raw.cycle)
-    print(f"fragment competition: {len(kept)} of {len(psm_df)} PSMs keep their fragments ({time.perf_counter() - t2:.2f} s)")
-    # the bookkeeping perform_fdr runs around it (alphadia/fdr/fdr.py:157-186): best row per elution group, then q-values
-    from alphadia_b200.fdr import get_q_values, keep_best
+# the FDR step between scoring and the final table (alphadia/fdr/fdr.py:25-192): the reference's feed-forward classifier is
+# trained on the 46 features + the candidate columns (torch on the device), its inference runs in adb_classifier_predict_proba,
+# and q-values, fragment competition (data without ion mobility only, fdr.py:157) and best-row-per-group on the device
+from alphadia_b200.classifier import BinaryClassifierLegacyNewBatching  # noqa: E402
+from alphadia_b200.fdr import perform_fdr  # noqa: E402
+from alphadia_b200.scoring import DEFAULT_FEATURE_COLUMNS  # noqa: E402
 
-    kept = kept.assign(_decoy=kept["decoy"].values, channel=0)
-    q_df = get_q_values(keep_best(kept, group_columns=["elution_group_idx", "channel"]), "proba", "_decoy")
-    print(f"q-values: {len(q_df)} best-per-group PSMs, {int((q_df['qval'] <= 0.01).sum())} at q <= 0.01 "
-          "(with the random stand-in probabilities this only reflects the target / decoy ratio of the scored rows)")
+available = [c for c in DEFAULT_FEATURE_COLUMNS if features_df[c].notna().all() and features_df[c].std() > 0]
+psm_df = features_df.assign(channel=0)
+classifier = BinaryClassifierLegacyNewBatching(input_dim=len(available), epochs=40, batch_size=64, learning_rate=0.005, random_state=0)
+result = perform_fdr(classifier, available, psm_df[psm_df["decoy"] == 0].copy(), psm_df[psm_df["decoy"] == 1].copy(),
+                     competitive=True, df_fragments=fragments_df.copy(), dia_cycle=raw.cycle, random_state=0)
+t3 = time.perf_counter()
+targets = result[result["_decoy"] == 0]
+print(f"perform_fdr: {len(available)} features, {len(psm_df)} PSMs -> {len(result)} best-per-elution-group rows, "
+      f"{int((targets['qval'] <= 0.01).sum())} targets at q <= 0.01 in {t3 - t2:.2f} s")
+print(result[["precursor_idx", "rank", "decoy", "proba", "qval"]].head(5).to_string())
+
+if not getattr(raw, "has_mobility", False):  # the pieces perform_fdr calls, on their own
+    kept = FragmentCompetition(rt_tol_seconds=3, mass_tol_ppm=15)(result.copy(), fragments_df.copy(), raw.cycle)
+    print(f"fragment competition on its own: {len(kept)} of {len(result)} PSMs keep their fragments")
