@@ -11,7 +11,9 @@ One "step" = candidate selection + candidate scoring of the whole library batch 
 adb_select_score_candidates_ragged (selection, candidate table D2H, scoring, ragged score + fragment tables D2H) every
 step (`--e2e-two-calls` / `--e2e-dense`: the separate-call and dense-table variants); the raw file is uploaded once per
 file, as `dia_data.to_jitclass()` is built once per file in the reference.  `e2e_operator` is the DataFrame-level operator
-path, `fragcomp` the fragment competition host to host, `parity` an oracle spot check of the timed results.
+path, `fragcomp` the fragment competition host to host, `parity` an oracle spot check of the timed results, and
+`other_workloads` (default N = 1 run only) condensed lines of BASELINE.json's config 2 and config 4, each from a short child run
+of this script after the main measurement (`--no-other-workloads` skips them).
 
 Baselines: `cpu_baseline` and `--impl reference` run the C/OpenMP PORT of the reference algorithm (oracle/adb_oracle.c,
 `kind: "port"`), not the numba code (it cannot travel to the GPU box; BASELINE.md has the numba calibration).  Everywhere
@@ -431,6 +433,35 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def other_workload_lines(names, timeout_s=300):
+    """BASELINE.json's other single-GPU configurations, each measured by a short run of this script in a child process after
+    the main measurement (same code path: resident value, C-ABI e2e, oracle spot check of the timed results); the child's
+    JSON line is condensed to the figures below.  A failure is recorded, it never breaks the main line."""
+    import subprocess
+
+    out = {}
+    for name in names:
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", "3", "--warmup", "3", "--e2e-steps", "3",
+               "--no-cpu-baseline", "--no-operator", "--no-fragcomp", "--no-other-workloads"]
+        t0 = time.time()
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            par = d.get("parity") or {}
+            out[name] = {
+                "workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"], "e2e": d["e2e"]["value"],
+                "ms_per_step": d["ms_per_step"], "stage_ms": d["config"]["stage_ms"], "candidates_per_step": d["config"]["candidates_per_step"],
+                "steps": d["steps"], "warmup": d["warmup"], "gpu_launches": d.get("gpu_launches"),
+                "roofline_frac": d["roofline"]["frac"], "roofline_kernel": d["roofline"]["kernel"],
+                "parity": {k: par.get(k) for k in ("n", "int_exact", "selection_score_bit_exact", "valid_exact", "max_rel", "tolerance")},
+                "wall_s": round(time.time() - t0, 1),
+            }
+        except Exception as e:  # noqa: BLE001 - reported, not raised
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300], "wall_s": round(time.time() - t0, 1)}
+        log(f"other workload {name}: {json.dumps(out[name])}")
+    return out
+
+
 def workload_description(name, P):
     from alphadia_b200.synthetic import CONFIGS_3D, CONFIGS_4D
 
@@ -461,6 +492,8 @@ def main():
     ap.add_argument("--operator-steps", type=int, default=2)
     ap.add_argument("--no-fragcomp", action="store_true", help="skip the fragment-competition side benchmark")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check of the timed results")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="skip the short runs of BASELINE.json's other single-GPU configurations (config 2, config 4) that the default N = 1 run adds to its line")
     ap.add_argument("--parity-precursors", type=int, default=800)
     args = ap.parse_args()
 
@@ -674,6 +707,8 @@ def main():
             fc = bench_fragcomp()
             log(f"fragment competition: {json.dumps(fc)}")
             line["fragcomp"] = fc
+        if world == 1 and args.workload == "config3" and args.precursors is None and not args.no_other_workloads:
+            line["other_workloads"] = other_workload_lines(("config2", "config4"))
         print(json.dumps(line), flush=True)
     hp.close()
     if world > 1:
