@@ -419,3 +419,36 @@ def test_count_residues_arrow_backed_strings_and_nan_columns_in_validation(caplo
     msgs = [r.getMessage() for r in caplog.records]
     assert any(m.startswith("f3 has 42858 NaNs") for m in msgs) and any(m.startswith("f9 has 1 Infs") for m in msgs)
     assert len(msgs) == 2
+
+
+def test_bench_other_workload_lines_never_break_the_main_line(monkeypatch):
+    """bench.py condenses the child runs of config 2 / config 4 into the main line; a failing or hanging child is recorded."""
+    import json
+    import subprocess
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    child = {"metric": "m", "value": 2.0, "unit": "candidates/s", "steps": 3, "warmup": 3, "ms_per_step": 1.5, "gpu_launches": 7,
+             "config": {"workload": "w", "stage_ms": {"selection": 1.0, "scoring": 0.5}, "candidates_per_step": 3.0},
+             "e2e": {"value": 1.0}, "roofline": {"frac": 0.1, "kernel": "k"},
+             "parity": {"n": 5, "int_exact": True, "selection_score_bit_exact": True, "valid_exact": True, "max_rel": 0.0, "tolerance": 1e-4,
+                        "checked": "long text that is not copied"}}
+    calls = []
+
+    def fake_run(cmd, **kw):
+        calls.append(cmd)
+        name = cmd[cmd.index("--workload") + 1]
+        if name == "config4":
+            raise subprocess.TimeoutExpired(cmd, kw.get("timeout"))
+        return subprocess.CompletedProcess(cmd, 0, stdout="noise\n" + json.dumps(child) + "\n", stderr="")
+
+    monkeypatch.setattr(subprocess, "run", fake_run)
+    out = bench.other_workload_lines(("config2", "config4", "config9"))
+    assert out["config2"]["value"] == 2.0 and out["config2"]["e2e"] == 1.0 and out["config2"]["parity"]["int_exact"] is True
+    assert "checked" not in out["config2"]["parity"] and out["config2"]["stage_ms"] == {"selection": 1.0, "scoring": 0.5}
+    assert "TimeoutExpired" in out["config4"]["error"]
+    assert all("--no-other-workloads" in c and "--no-cpu-baseline" in c for c in calls)  # children never recurse
+    monkeypatch.setattr(subprocess, "run", lambda cmd, **kw: subprocess.CompletedProcess(cmd, 1, stdout="", stderr="boom"))
+    assert "error" in bench.other_workload_lines(("config2",))["config2"]
