@@ -1,10 +1,9 @@
 """``FragmentCompetition`` — drop-in for alphadia/fragcomp/fragcomp.py:146-299 on the B200 engine.
 
-The pandas preparation (candidate hash, fragment start/stop indices, DIA-window assignment, the
-``[window_idx, proba, precursor_idx]`` sort) follows the reference line by line, including its
-in-place side effects on ``psm_df`` / ``frag_df``; the greedy veto itself
-(``_compete_for_fragments``, fragcomp.py:51-143) runs as one CUDA launch (one CTA per DIA window)
-behind ``adb_fragment_competition``.
+The table preparation keeps the reference's helper names, results and in-place side effects on ``psm_df`` / ``frag_df``
+(candidate hash, fragment start/stop indices, DIA-window assignment, the ``[window_idx, proba, precursor_idx]`` sort) but is
+written on run boundaries and sorted look-ups instead of group-by / merge; the greedy veto itself (``_compete_for_fragments``,
+fragcomp.py:51-143) runs on the device behind ``adb_fragment_competition`` (conflict graph over RT-sorted windows).
 """
 
 from __future__ import annotations
@@ -25,18 +24,45 @@ def candidate_hash(precursor_idx: np.ndarray, rank: np.ndarray) -> np.ndarray:
     return (precursor_idx.astype(np.int64) + (rank.astype(np.int64) << 32)).astype(np.uint64)
 
 
+def _key_extents(keys: np.ndarray):
+    """``(distinct keys ascending, first row, last row + 1)`` of every key of a column - what ``groupby(key).agg(min, max)`` of
+    the row number gives.  Rows of one key are normally one contiguous run; a key that comes back later spans from its first
+    run to its last (the rows in between included, as with the reference's min / max)."""
+    n = len(keys)
+    if n == 0:
+        return keys[:0], np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    cut = np.flatnonzero(keys[1:] != keys[:-1]) + 1
+    run_start = np.concatenate(([0], cut)).astype(np.int64)
+    run_stop = np.concatenate((cut, [n])).astype(np.int64)
+    order = np.argsort(keys[run_start], kind="stable")
+    run_key, run_start, run_stop = keys[run_start][order], run_start[order], run_stop[order]
+    head = np.ones(len(run_key), dtype=bool)
+    head[1:] = run_key[1:] != run_key[:-1]
+    if head.all():
+        return run_key, run_start, run_stop
+    at = np.flatnonzero(head)
+    return run_key[at], np.minimum.reduceat(run_start, at), np.maximum.reduceat(run_stop, at)
+
+
 def add_frag_start_stop_idx(psm_df: pd.DataFrame, frag_df: pd.DataFrame) -> pd.DataFrame:
-    """alphadia/fragcomp/utils.py:10-45."""
+    """alphadia/fragcomp/utils.py:10-45: ``_frag_start_idx`` / ``_frag_stop_idx`` of every PSM = the extent of its
+    ``_candidate_idx`` in ``frag_df`` (which gains a ``frag_idx`` column, as in the reference); PSMs without fragments are
+    dropped (inner join) and the result has a fresh index."""
     if "_frag_start_idx" in psm_df.columns and "_frag_stop_idx" in psm_df.columns:
         logger.warning("Fragment start and stop indices already present in PSM dataframe. Skipping.")
         return psm_df
     frag_df["frag_idx"] = np.arange(len(frag_df))
-    index_df = frag_df.groupby("_candidate_idx", as_index=False).agg(
-        _frag_start_idx=pd.NamedAgg("frag_idx", "min"),
-        _frag_stop_idx=pd.NamedAgg("frag_idx", "max"),
-    )
-    index_df["_frag_stop_idx"] += 1
-    return psm_df.merge(index_df, "inner", on="_candidate_idx")
+    key, first, last = _key_extents(frag_df["_candidate_idx"].values)
+    wanted = psm_df["_candidate_idx"].values
+    if len(key):
+        pos = np.minimum(np.searchsorted(key, wanted), len(key) - 1)
+        found = key[pos] == wanted
+    else:
+        pos, found = np.zeros(len(wanted), dtype=np.int64), np.zeros(len(wanted), dtype=bool)
+    out = psm_df[found].reset_index(drop=True)
+    out["_frag_start_idx"] = first[pos[found]]
+    out["_frag_stop_idx"] = last[pos[found]]
+    return out
 
 
 @dataclass
@@ -60,28 +86,26 @@ class FragmentCompetition:
 
     @staticmethod
     def _add_window_idx(psm_df: pd.DataFrame, cycle: np.ndarray) -> pd.DataFrame:
-        """fragcomp.py:170-202."""
+        """fragcomp.py:170-202: the first cycle position whose quadrupole range [min lower, max upper) over the scans holds
+        ``mz_observed``; position 0 when none does.  One pass per position instead of an n x positions matrix."""
         if "window_idx" in psm_df.columns:
             logger.warning("Window index already present in PSM dataframe. Skipping.")
             return psm_df
-        lower_limit = np.min(cycle[0, :, :, 0], axis=1, keepdims=True).T
-        upper_limit = np.max(cycle[0, :, :, 1], axis=1, keepdims=True).T
-        mz = np.expand_dims(psm_df["mz_observed"].values, axis=-1)
-        idx = (mz >= lower_limit) & (mz < upper_limit)
-        psm_df["window_idx"] = np.argmax(idx, axis=1)
+        lower = cycle[0, :, :, 0].min(axis=1)
+        upper = cycle[0, :, :, 1].max(axis=1)
+        mz = psm_df["mz_observed"].values
+        window = np.zeros(len(mz), dtype=np.int64)
+        for position in range(len(lower) - 1, -1, -1):  # earlier positions overwrite later ones: the first match wins
+            window[(mz >= lower[position]) & (mz < upper[position])] = position
+        psm_df["window_idx"] = window
         return psm_df
 
     @staticmethod
     def _get_thread_plan_df(psm_df: pd.DataFrame) -> pd.DataFrame:
-        """fragcomp.py:204-229."""
-        psm_df["_thread_idx"] = np.arange(len(psm_df))
-        index_df = psm_df.groupby("window_idx", as_index=False).agg(
-            start_idx=pd.NamedAgg("_thread_idx", "min"),
-            stop_idx=pd.NamedAgg("_thread_idx", "max"),
-        )
-        index_df["stop_idx"] += 1
-        psm_df.drop(columns=["_thread_idx"], inplace=True)
-        return index_df
+        """fragcomp.py:204-229: one row per DIA window with the extent ``[start_idx, stop_idx)`` of its PSMs in the (sorted)
+        table."""
+        window, start, stop = _key_extents(psm_df["window_idx"].values)
+        return pd.DataFrame({"window_idx": window, "start_idx": start, "stop_idx": stop})
 
     def plan(self, psm_df: pd.DataFrame, frag_df: pd.DataFrame, cycle: np.ndarray) -> FragcompPlan:
         """Everything of ``__call__`` up to the kernel launch (fragcomp.py:254-273)."""
