@@ -440,3 +440,60 @@ def _known_q_values(fdr):
 
 
 FDR_KNOWN_ANSWERS = [_known_keep_best, _known_keep_best_2, _known_q_values]
+
+
+def _plan_with_pandas(psm_df, frag_df, cycle):
+    """The preparation of fragcomp.py:254-273 / fragcomp/utils.py:10-45 spelled out with group-by, merge and the n x positions
+    window matrix - the specification the run-boundary implementation is held to."""
+    psm_df["_candidate_idx"] = candidate_hash(psm_df["precursor_idx"].values, psm_df["rank"].values)
+    frag_df["_candidate_idx"] = candidate_hash(frag_df["precursor_idx"].values, frag_df["rank"].values)
+    frag_df["frag_idx"] = np.arange(len(frag_df))
+    ext = frag_df.groupby("_candidate_idx", as_index=False).agg(_frag_start_idx=("frag_idx", "min"), _frag_stop_idx=("frag_idx", "max"))
+    ext["_frag_stop_idx"] += 1
+    psm_df = psm_df.merge(ext, "inner", on="_candidate_idx")
+    lower = np.min(cycle[0, :, :, 0], axis=1, keepdims=True).T
+    upper = np.max(cycle[0, :, :, 1], axis=1, keepdims=True).T
+    mz = psm_df["mz_observed"].values[:, None]
+    psm_df["window_idx"] = np.argmax((mz >= lower) & (mz < upper), axis=1)
+    psm_df = psm_df.sort_values(by=["window_idx", "proba", "precursor_idx"])
+    pos = pd.DataFrame({"window_idx": psm_df["window_idx"].values, "row": np.arange(len(psm_df))})
+    win = pos.groupby("window_idx", as_index=False).agg(start=("row", "min"), stop=("row", "max"))
+    return psm_df, win["start"].values, win["stop"].values + 1
+
+
+def test_fragment_competition_preparation_vs_pandas_formulation():
+    """Random adversarial tables: duplicate candidates, PSMs without fragments, fragments of one candidate in several runs,
+    m/z outside every window or NaN, overlapping and empty (-1, -1) cycle positions, shuffled indices, empty inputs."""
+    rng = np.random.default_rng(0)
+    for it in range(120):
+        n, n_pos, n_scan = int(rng.integers(0, 60)), int(rng.integers(1, 8)), int(rng.integers(1, 4))
+        psm = pd.DataFrame({"precursor_idx": rng.integers(0, 25, n), "rank": rng.integers(0, 3, n).astype(np.uint8),
+                            "rt_observed": rng.random(n) * 50, "proba": np.round(rng.random(n), 1),
+                            "mz_observed": np.where(rng.random(n) < 0.1, np.nan, rng.uniform(50, 450, n))})
+        if rng.random() < 0.5:
+            psm = psm.drop_duplicates(["precursor_idx", "rank"])
+        psm.index = rng.permutation(len(psm)) + 7
+        m = int(rng.integers(0, 200))
+        frag = pd.DataFrame({"precursor_idx": rng.integers(0, 28, m), "rank": rng.integers(0, 3, m).astype(np.uint8),
+                             "mz_observed": rng.uniform(100, 1000, m)})
+        mode = int(rng.integers(0, 3))
+        if mode == 0:
+            frag = frag.sort_values(["precursor_idx", "rank"]).reset_index(drop=True)
+        elif mode == 1:
+            frag = frag.sort_values(["rank", "precursor_idx"], kind="stable").reset_index(drop=True)
+        cycle = np.zeros((1, n_pos, n_scan, 2))
+        lo = np.sort(rng.uniform(0, 400, n_pos))
+        for pos in range(n_pos):
+            for s in range(n_scan):
+                a = lo[pos] + rng.uniform(-20, 20)
+                cycle[0, pos, s] = (a, a + rng.uniform(10, 150))
+        if rng.random() < 0.5:
+            cycle[0, 0] = -1
+        psm_a, frag_a, psm_b, frag_b = psm.copy(), frag.copy(), psm.copy(), frag.copy()
+        plan = FragmentCompetition().plan(psm_a, frag_a, cycle)
+        want, start, stop = _plan_with_pandas(psm_b, frag_b, cycle)
+        pd.testing.assert_frame_equal(plan.psm_df, want)
+        pd.testing.assert_frame_equal(psm_a, psm_b)  # side effects on the caller's frames
+        pd.testing.assert_frame_equal(frag_a, frag_b)
+        assert np.array_equal(plan.window_start, start) and np.array_equal(plan.window_stop, stop), it
+        assert np.array_equal(plan.frag_start, want["_frag_start_idx"].values) and np.array_equal(plan.frag_stop, want["_frag_stop_idx"].values)
