@@ -124,8 +124,9 @@ def _make_pjit():
     return pjit, set_threads
 
 
-def _make_pocketfft_module():
-    """fft.py:141-212 on scipy.fft (pocketfft, complex64): the measurement mode, see the module docstring."""
+def _make_pocketfft_module(_MODE="pocketfft"):
+    """fft.py:141-212 on scipy.fft (pocketfft, complex64): the measurement mode, see the module docstring.  ``_MODE ==
+    "separable"``: the same circular convolution as two 1-D passes (what a separable GPU kernel would compute)."""
     import numba as nb
     import scipy.fft as sf
     from numba.extending import overload
@@ -144,10 +145,33 @@ def _make_pocketfft_module():
         out[delta0:, :delta1] = layer[:-delta0, -delta1:]
         out[:delta0, :delta1] = layer[-delta0:, -delta1:]
 
+    def _separable_layer(x, kernel):
+        """Rank-1 reading of the Gaussian: K ~ outer(u, v) with u = the centre column, v = the centre row / the centre value;
+        circular convolution along the cycles with v, then along the scans with u, both in fp64, one rounding to f32."""
+        k0, k1 = kernel.shape
+        s0, s1 = k0 // 2, k1 // 2
+        u = kernel[:, s1].astype(np.float64)
+        v = kernel[s0, :].astype(np.float64) / np.float64(kernel[s0, s1])
+        xd = x.astype(np.float64)
+        tmp = np.zeros_like(xd)
+        for b in range(k1):
+            tmp += v[b] * np.roll(xd, b - s1, axis=1)
+        out = np.zeros_like(xd)
+        for a in range(k0):
+            out += u[a] * np.roll(tmp, a - s0, axis=0)
+        return out.astype(np.float32)
+
     def _py_conv(dense, kernel):
         dense = np.ascontiguousarray(dense, dtype=np.float32)
         kernel = np.ascontiguousarray(kernel, dtype=np.float32)
         k0, k1 = kernel.shape
+        if _MODE == "separable":
+            out = np.zeros_like(dense)
+            flat_in = dense.reshape((-1,) + dense.shape[-2:])
+            flat_out = out.reshape((-1,) + dense.shape[-2:])
+            for i in range(flat_in.shape[0]):
+                flat_out[i] = _separable_layer(flat_in[i], kernel)
+            return out
         ff = sf.rfft2(kernel, s=dense.shape[-2:])
         assert ff.dtype == np.complex64
         out = np.zeros_like(dense)
@@ -291,8 +315,8 @@ def install() -> None:
         sys.path.insert(0, REFERENCE_ROOT)
     import os
 
-    pocket = os.environ.get("ADB_REFSHIM_FFT", "") == "pocketfft"
-    sys.modules["alphadia.search.selection.fft"] = _make_pocketfft_module() if pocket else _make_fft_module()
+    mode = os.environ.get("ADB_REFSHIM_FFT", "")
+    sys.modules["alphadia.search.selection.fft"] = _make_pocketfft_module(mode) if mode in ("pocketfft", "separable") else _make_fft_module()
     _installed = True
 
 

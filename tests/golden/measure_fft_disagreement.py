@@ -13,7 +13,7 @@ import os
 import sys
 import time
 
-os.environ["ADB_REFSHIM_FFT"] = "pocketfft"
+os.environ.setdefault("ADB_REFSHIM_FFT", "pocketfft")  # or "separable": two 1-D fp64 passes instead of the 2-D sum
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
 
@@ -81,6 +81,6 @@ if __name__ == "__main__":
     threads = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     names = [a for a in sys.argv[2:]] or ["parity_small", "parity_4d"]
     out = [run(n, threads) for n in names]
-    print(json.dumps({"what": "reference selection with a single-precision pocketfft convolution (scipy.fft) vs the committed "
+    print(json.dumps({"mode": os.environ["ADB_REFSHIM_FFT"], "what": "reference selection with a single-precision pocketfft convolution (scipy.fft; mode separable: two 1-D fp64 passes) vs the committed "
                               "golden candidate tables (direct fp64 circular convolution); a candidate = (precursor_idx, "
                               "scan/frame centre, start, stop)", "results": out}, indent=1))
