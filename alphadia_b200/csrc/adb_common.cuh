@@ -345,3 +345,58 @@ __device__ __forceinline__ int64_t adb_wrap0(int64_t v, int64_t limit) {
   if (v < 0) return 0;
   return v < limit ? v : limit;
 }
+
+// np.argsort as numba compiles it (numba/misc/quicksort.py, argsort variant): ranges of more than 15 elements are partitioned
+// around a median-of-three pivot (NOT stable: the order of exact ties follows the algorithm), ranges of up to 15 elements are
+// insertion-sorted (stable).  The fragment orders of the reference (top-k by intensity, m/z order, intensity order of the masked
+// fragments) come from it, so for more than 15 elements it is followed step by step; up to 15 the callers keep their stable
+// rank counting, which gives the same order.
+#if defined(__CUDACC__)
+#define ADB_HOSTDEV __host__ __device__ inline
+#else
+#define ADB_HOSTDEV inline
+#endif
+#define ADB_NUMBA_SMALL_SORT 15
+ADB_HOSTDEV void adb_argsort_numba(const float* v, int n, uint8_t* R) {
+  for (int i = 0; i < n; i++) R[i] = (uint8_t)i;
+  if (n < 2) return;
+  uint8_t lo_stack[16], hi_stack[16];  // the larger side of every split is pushed: depth <= log2(n) + 1
+  int sp = 1;
+  lo_stack[0] = 0; hi_stack[0] = (uint8_t)(n - 1);
+  while (sp > 0) {
+    sp--;
+    int low = lo_stack[sp], high = hi_stack[sp];
+    while (high - low >= ADB_NUMBA_SMALL_SORT) {
+      const int mid = (low + high) >> 1;
+      uint8_t t;
+      if (v[R[mid]] < v[R[low]]) { t = R[low]; R[low] = R[mid]; R[mid] = t; }
+      if (v[R[high]] < v[R[mid]]) { t = R[high]; R[high] = R[mid]; R[mid] = t; }
+      if (v[R[mid]] < v[R[low]]) { t = R[low]; R[low] = R[mid]; R[mid] = t; }
+      const float pivot = v[R[mid]];
+      t = R[high]; R[high] = R[mid]; R[mid] = t;
+      int i = low, k = high - 1;
+      for (;;) {
+        while (i < high && v[R[i]] < pivot) i++;
+        while (k >= low && pivot < v[R[k]]) k--;
+        if (i >= k) break;
+        t = R[i]; R[i] = R[k]; R[k] = t;
+        i++; k--;
+      }
+      t = R[i]; R[i] = R[high]; R[high] = t;
+      if (high - i > i - low) {
+        if (high > i && sp < 16) { lo_stack[sp] = (uint8_t)(i + 1); hi_stack[sp] = (uint8_t)high; sp++; }
+        high = i - 1;
+      } else {
+        if (i > low && sp < 16) { lo_stack[sp] = (uint8_t)low; hi_stack[sp] = (uint8_t)(i - 1); sp++; }
+        low = i + 1;
+      }
+    }
+    for (int i = low + 1; i <= high; i++) {
+      const uint8_t key = R[i];
+      const float x = v[key];
+      int k = i;
+      while (k > low && x < v[R[k - 1]]) { R[k] = R[k - 1]; k--; }
+      R[k] = key;
+    }
+  }
+}

@@ -250,23 +250,45 @@ __device__ void score_one_4d(const Score4Params& P, int64_t ci, Small4& sm, floa
   }
   __syncwarp();
   const int F = min(min(m, K), SC4_F);
+  if (m > ADB_NUMBA_SMALL_SORT) {  // more than 15 elements: numba's quicksort order among ties (adb_argsort_numba), one lane
+    if (lane == 0) {
+      uint8_t ord[ADB_MAX_LIB_FRAGMENTS];
+      adb_argsort_numba(sm.t_int, m, ord);
+      for (int r = 0; r < F; r++) sm.t_sel[r] = ord[m - 1 - r];
+    }
+  } else {
 #pragma unroll 1
-  for (int u = lane; u < m; u += 32) {  // descending-intensity position (stable argsort reversed)
-    const float v = sm.t_int[u];
-    int rank_asc = 0;
+    for (int u = lane; u < m; u += 32) {  // descending-intensity position (stable argsort reversed)
+      const float v = sm.t_int[u];
+      int rank_asc = 0;
 #pragma unroll 1
-    for (int q = 0; q < m; q++) rank_asc += (sm.t_int[q] < v) || (sm.t_int[q] == v && q < u);
-    const int r = m - 1 - rank_asc;
-    if (r < F) sm.t_sel[r] = u;
+      for (int q = 0; q < m; q++) rank_asc += (sm.t_int[q] < v) || (sm.t_int[q] == v && q < u);
+      const int r = m - 1 - rank_asc;
+      if (r < F) sm.t_sel[r] = u;
+    }
   }
   __syncwarp();
+  if (F > ADB_NUMBA_SMALL_SORT) {  // m/z order of the selected fragments, same rule; sorted_idx is free until the fragment features
+    if (lane == 0) {
+      float sel_mz[SC4_F];
+      uint8_t ord[SC4_F];
+      for (int r = 0; r < F; r++) sel_mz[r] = sm.t_mz[sm.t_sel[r]];
+      adb_argsort_numba(sel_mz, F, ord);
+      for (int k = 0; k < F; k++) sm.sorted_idx[ord[k]] = k;
+    }
+    __syncwarp();
+  }
 #pragma unroll 1
   for (int r = lane; r < F; r += 32) {  // stable m/z order among the selected
     const int u = sm.t_sel[r];
     const float v = sm.t_mz[u];
     int rank2 = 0;
+    if (F > ADB_NUMBA_SMALL_SORT) {
+      rank2 = sm.sorted_idx[r];
+    } else {
 #pragma unroll 1
-    for (int q = 0; q < F; q++) { const float vq = sm.t_mz[sm.t_sel[q]]; rank2 += (vq < v) || (vq == v && q < r); }
+      for (int q = 0; q < F; q++) { const float vq = sm.t_mz[sm.t_sel[q]]; rank2 += (vq < v) || (vq == v && q < r); }
+    }
     const int64_t g = fs + sm.t_src[u];
     sm.mz_library[rank2] = lib.frag_mz_library[g];
     sm.mz[rank2] = v;
@@ -693,6 +715,14 @@ __device__ void score_one_4d(const Score4Params& P, int64_t ci, Small4& sm, floa
   }
   const unsigned anyh_b = __ballot_sync(FULL, anyh);
   __syncwarp();
+  if (Fv > ADB_NUMBA_SMALL_SORT) {  // more than 15 masked fragments: numba's quicksort order among ties
+    if (lane == 0) {
+      uint8_t ord[SC4_F];
+      adb_argsort_numba(sm.fint, Fv, ord);
+      for (int r = 0; r < Fv; r++) sm.sorted_idx[r] = ord[Fv - 1 - r];
+    }
+    __syncwarp();
+  }
   // fragment-level outputs, candidate.py:403-442
   const size_t obase = (size_t)ci * (size_t)K;
   if (act && cfg.collect_fragments && lane < K) {

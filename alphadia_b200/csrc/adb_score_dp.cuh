@@ -248,6 +248,11 @@ ADB_HD void dp_setup(const DpParams& P, int64_t j) {
     }
   }
   const int F = min(m, (int)min(cfg.top_k_fragments, (uint32_t)P.KS));
+  if (m > ADB_NUMBA_SMALL_SORT) {  // np.argsort(intensity)[::-1][:top_k], numba's quicksort order among ties
+    uint8_t ord[DP_MAXF];
+    adb_argsort_numba(t_int, m, ord);
+    for (int r = 0; r < F; r++) t_sel[r] = ord[m - 1 - r];
+  } else
   for (int u = 0; u < m; u++) {  // descending-intensity position (stable argsort, reversed)
     const float v = t_int[u];
     int rank_asc = 0;
@@ -256,6 +261,13 @@ ADB_HD void dp_setup(const DpParams& P, int64_t j) {
     if (r < F) t_sel[r] = (uint8_t)u;
   }
   if (F <= 3) return;
+  if (F > ADB_NUMBA_SMALL_SORT) {  // np.argsort(mz) of the selected fragments, numba's quicksort order among ties
+    float sel_mz[DP_MAXF];
+    uint8_t ord[DP_MAXF];
+    for (int r = 0; r < F; r++) sel_mz[r] = t_mz[t_sel[r]];
+    adb_argsort_numba(sel_mz, F, ord);
+    for (int r = 0; r < F; r++) P.fsel[j * P.KS + r] = (uint32_t)(fs + t_src[t_sel[ord[r]]]);
+  } else
   for (int r = 0; r < F; r++) {  // stable m/z order among the selected
     const int u = t_sel[r];
     const float v = t_mz[u];
@@ -1035,6 +1047,11 @@ ADB_HD void dp_aggregate(const DpParams& P, int64_t j, float* stage = nullptr) {
     for (int w = 0; w < Fv; w++) t = t + fint[w];
     for (int w = 0; w < Fv; w++) fin[w] = fint[w] / t;
   }
+  if (Fv > ADB_NUMBA_SMALL_SORT) {  // np.argsort(fragments.intensity)[::-1], numba's quicksort order among ties
+    uint8_t ord[DP_MAXF];
+    adb_argsort_numba(fint, Fv, ord);
+    for (int r = 0; r < Fv; r++) sorted_idx[r] = ord[Fv - 1 - r];
+  } else
   for (int w = 0; w < Fv; w++) {  // np.argsort(fragments.intensity)[::-1]
     const float v = fint[w];
     int rank_asc = 0;

@@ -51,8 +51,8 @@ static inline float log1p_feature(float x) { return (float)log((double)x + 1.0);
  * ---------------------------------------------------------------------------------------- */
 
 /* numba quicksort falls back to insertion sort for <= 15 elements (numba/misc/quicksort.py,
- * SMALL_QUICKSORT = 15) => stable ascending argsort.  For larger inputs any order among exact
- * ties is "correct"; we stay stable. */
+ * SMALL_QUICKSORT = 15) => stable ascending argsort.  Used where ties cannot change the result (selection: layers
+ * with equal m/z are identical rows; peak values); the fragment orders of the scoring path use argsort_numba_f32. */
 static void argsort_f32(const float* v, int n, int* idx) {
   for (int i = 0; i < n; i++) idx[i] = i;
   for (int i = 1; i < n; i++) {
@@ -64,6 +64,58 @@ static void argsort_f32(const float* v, int n, int* idx) {
       j--;
     }
     idx[j] = k;
+  }
+}
+/* np.argsort as numba compiles it (numba/misc/quicksort.py, is_argsort): ranges of more than 15 elements are partitioned
+ * around a median-of-three pivot - NOT stable, so the order of exact ties depends on the algorithm - and ranges of up to 15
+ * are insertion-sorted.  Restated step by step so that libraries with more than 15 fragments per precursor and tied m/z or
+ * intensity values give the reference's fragment order (found by tests/golden/sweep_reference_vs_oracle.py). */
+static void numba_insertion_f32(const float* v, int* R, int low, int high) {
+  for (int i = low + 1; i <= high; i++) {
+    int k = R[i];
+    float x = v[k];
+    int j = i;
+    while (j > low && x < v[R[j - 1]]) { R[j] = R[j - 1]; j--; }
+    R[j] = k;
+  }
+}
+static int numba_partition_f32(const float* v, int* R, int low, int high) {
+  int mid = (low + high) >> 1, t;
+  if (v[R[mid]] < v[R[low]]) { t = R[low]; R[low] = R[mid]; R[mid] = t; }
+  if (v[R[high]] < v[R[mid]]) { t = R[high]; R[high] = R[mid]; R[mid] = t; }
+  if (v[R[mid]] < v[R[low]]) { t = R[low]; R[low] = R[mid]; R[mid] = t; }
+  float pivot = v[R[mid]];
+  t = R[high]; R[high] = R[mid]; R[mid] = t;
+  int i = low, j = high - 1;
+  for (;;) {
+    while (i < high && v[R[i]] < pivot) i++;
+    while (j >= low && pivot < v[R[j]]) j--;
+    if (i >= j) break;
+    t = R[i]; R[i] = R[j]; R[j] = t;
+    i++; j--;
+  }
+  t = R[i]; R[i] = R[high]; R[high] = t;
+  return i;
+}
+static void argsort_numba_f32(const float* v, int n, int* R) {
+  for (int i = 0; i < n; i++) R[i] = i;
+  if (n < 2) return;
+  int lo_stack[64], hi_stack[64], sp = 0;
+  lo_stack[0] = 0; hi_stack[0] = n - 1; sp = 1;
+  while (sp > 0) {
+    sp--;
+    int low = lo_stack[sp], high = hi_stack[sp];
+    while (high - low >= 15) {
+      int i = numba_partition_f32(v, R, low, high);
+      if (high - i > i - low) {
+        if (high > i) { lo_stack[sp] = i + 1; hi_stack[sp] = high; sp++; }
+        high = i - 1;
+      } else {
+        if (i > low) { lo_stack[sp] = low; hi_stack[sp] = i - 1; sp++; }
+        low = i + 1;
+      }
+    }
+    numba_insertion_f32(v, R, low, high);
   }
 }
 static void argsort_f64(const double* v, int n, int* idx) {
@@ -718,12 +770,12 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
     for (int64_t j = fs; j < fe; j++)
       if (!cfg->exclude_shared_ions || lib->frag_cardinality[j] <= 1) { src[m] = j; inten[m] = lib->frag_intensity[j]; m++; }
     int* ord = (int*)malloc(sizeof(int) * (size_t)(m + 1));
-    argsort_f32(inten, m, ord);
+    argsort_numba_f32(inten, m, ord);
     int k = m < K ? m : K;
     if (k > ORACLE_MAX_FRAGMENTS) k = ORACLE_MAX_FRAGMENTS;
     int64_t sel[ORACLE_MAX_FRAGMENTS]; float selmz[ORACLE_MAX_FRAGMENTS]; int ord2[ORACLE_MAX_FRAGMENTS];
     for (int r = 0; r < k; r++) { sel[r] = src[ord[m - 1 - r]]; selmz[r] = lib->frag_mz[sel[r]]; }
-    argsort_f32(selmz, k, ord2);
+    argsort_numba_f32(selmz, k, ord2);
     fr.n = k;
     for (int r = 0; r < k; r++) {
       int64_t j = sel[ord2[r]];
@@ -1129,7 +1181,7 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
     /* fragment_features.py:387-396 */
     for (int f = 0; f < F; f++) mass_error[f] = (ofmm[f] - (double)fr.mz[f]) / (double)fr.mz[f] * 1e6;
     int ord[ORACLE_MAX_FRAGMENTS];
-    argsort_f32(fr.intensity, F, ord);
+    argsort_numba_f32(fr.intensity, F, ord);
     { int n3 = F < 3 ? F : 3; double t = 0; for (int r = 0; r < n3; r++) t += mass_error[ord[F - 1 - r]]; fa[41] = (float)(t / (double)n3); }
     { double t = 0; for (int f = 0; f < F; f++) t += mass_error[f]; fa[42] = (float)(t / (double)F); }
     /* fragment_features.py:400-420 */
@@ -1201,7 +1253,7 @@ static void score_one(const rawview* rv, const adb_library_desc* lib, const adb_
   float corr_list[ORACLE_MAX_FRAGMENTS];
   {
     int ord[ORACLE_MAX_FRAGMENTS];
-    argsort_f32(fr.intensity, F, ord);
+    argsort_numba_f32(fr.intensity, F, ord);
     int sorted_idx[ORACLE_MAX_FRAGMENTS];
     for (int r = 0; r < F; r++) sorted_idx[r] = ord[F - 1 - r];
     int n3 = F < 3 ? F : 3;
