@@ -5,7 +5,7 @@ The committed golden vectors pin ``oracle/adb_oracle.c`` at fixed seeds and conf
 libraries (some ragged), selection and scoring configurations and quadrupole parameters, runs the unmodified numba path through
 ``oracle/refshim.py`` and the oracle on the same inputs, and holds the oracle to the bar of tests/test_oracle_golden.py:
 candidate table bit-exact (integer columns and f32 score), valid rows equal, features bit-exact except the BLAS-summed ones
-(1e-4), per-fragment columns bit-exact except the correlation (1e-4).
+(1e-4 relative + 1e-6 absolute), per-fragment columns bit-exact except the correlation (same tolerance).
 
     python tests/golden/sweep_reference_vs_oracle.py [n_cases] [seed] > tests/golden/sweep_reference_vs_oracle.json
 """
@@ -25,6 +25,16 @@ from alphadia_b200.synthetic import make_config_3d, make_config_4d  # noqa: E402
 from oracle import refshim  # noqa: E402
 from tests import helpers as H  # noqa: E402
 from tests.test_oracle_golden import BLAS_FEATURES, FRAG_MAP, INT_COLS  # noqa: E402
+
+
+def _excess(a, b):
+    """Largest |a - b| in units of the tolerance of BASELINE.json's north star for the BLAS-summed quantities (correlations, whose
+    summation order numpy / BLAS leave open): 1e-4 relative plus an absolute 1e-6 (they live in [-1, 1]; a value of 1e-8 cannot be
+    held to 1e-4 relative)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    d = np.where(both_nan, 0.0, np.abs(a - b))
+    return float(np.max(d / (1e-4 * np.maximum(np.abs(a), np.abs(b)) + 1e-6))) if d.size else 0.0
 
 
 def draw_case(rng, it):
@@ -111,13 +121,13 @@ def one_case(rng, it, threads, drawn=None, debug=None):
             for j in range(46):
                 same = (F[:, j] == G[:, j]) | (np.isnan(F[:, j]) & np.isnan(G[:, j]))
                 if j in BLAS_FEATURES:
-                    e = float(H.rel_err(F[:, j], G[:, j]).max()) if len(F) else 0.0
+                    e = float(_excess(F[:, j], G[:, j])) if len(F) else 0.0
                     worst = max(worst, e)
-                    if e >= 1e-4:
-                        problems.append(f"feature {j} rel {e:.2e}")
+                    if e > 1.0:
+                        problems.append(f"feature {j}: {e:.2f} x the tolerance")
                 elif not same.all():
                     problems.append(f"feature {j} not bit-exact ({int((~same).sum())} rows)")
-            info["max_rel_blas_features"] = worst
+            info["max_blas_feature_error_in_tolerances"] = worst
             mm = res["fragment_mz_library"] > 0
             if mm.sum() != len(frag):
                 problems.append(f"fragment rows {int(mm.sum())} vs {len(frag)}")
@@ -125,7 +135,7 @@ def one_case(rng, it, threads, drawn=None, debug=None):
                 for k, v2 in FRAG_MAP.items():
                     a, b = res[v2][mm], frag[k].values
                     if k == "correlation":
-                        if len(a) and float(H.rel_err(a, b).max()) >= 1e-4:
+                        if len(a) and float(_excess(a, b)) > 1.0:
                             problems.append("fragment correlation")
                     elif not np.array_equal(a, b):
                         problems.append(f"fragment column {k}")
