@@ -581,6 +581,45 @@ def run_k9999_f48(threads: int):
     print(f"[k9999_f48] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
 
 
+def run_ties_f20(threads: int):
+    """Scoring of the tie-heavy 20-fragment library (tests/helpers.py tied_fragment_library) with top_k_fragments = 20 and 16 by
+    the unmodified reference -> tests/golden/ties_f20.npz.  Pins the order numba's (unstable) argsort gives tied fragments."""
+    from tests.helpers import tied_fragment_library
+
+    raw, precursor_df, fragment_df, p = tied_fragment_library()
+    dia = refshim.RefDiaData(raw)
+    sel_mod = refshim.ref("alphadia.search.selection.selection")
+    cfg_mod = refshim.ref("alphadia.search.selection.config_df")
+    sc_mod = refshim.ref("alphadia.search.scoring.scoring")
+    sccfg_mod = refshim.ref("alphadia.search.scoring.config")
+    sel_cfg = cfg_mod.CandidateSelectionConfig()
+    sel_cfg.update({**SELECTION_BASE, "rt_tolerance": float(p["rt_tolerance"]), "mobility_tolerance": 0.1, "candidate_count": 3,
+                    "precursor_mz_tolerance": 5.0, "fragment_mz_tolerance": 10.0})
+    sel = sel_mod.CandidateSelection(dia, precursor_df.copy(), fragment_df.copy(), sel_cfg, rt_column="rt_library",
+                                     mobility_column="mobility_library", precursor_mz_column="mz_library",
+                                     fragment_mz_column="mz_library", fwhm_rt=5.0, fwhm_mobility=0.01)
+    cand = sel(thread_count=threads)
+    out = {"input_checksum": np.array(input_checksum(raw, precursor_df, fragment_df))}
+    for c in cand.columns:
+        out[f"cand_{c}"] = cand[c].values
+    for k in (20, 16):
+        sc_cfg = sccfg_mod.CandidateScoringConfig()
+        sc_cfg.update({**SCORING_BASE, "precursor_mz_tolerance": 5, "fragment_mz_tolerance": 10, "top_k_fragments": k})
+        scorer = sc_mod.CandidateScoring(dia_data=dia, precursors_flat=precursor_df.copy(), fragments_flat=fragment_df.copy(), config=sc_cfg,
+                                         rt_column="rt_library", mobility_column="mobility_library", precursor_mz_column="mz_library",
+                                         fragment_mz_column="mz_library")
+        feat, frag = scorer(cand.copy(), thread_count=threads, include_decoy_fragment_features=True)
+        print(f"[ties_f20] top_k_fragments={k}: {len(cand)} candidates -> {len(feat)} rows, {len(frag)} fragment rows", flush=True)
+        out[f"feat_k{k}_matrix"] = feat[sc_mod.DEFAULT_FEATURE_COLUMNS].values.astype(np.float32)
+        out[f"feat_k{k}_precursor_idx"] = feat["precursor_idx"].values
+        out[f"feat_k{k}_rank"] = feat["rank"].values
+        for c in frag.columns:
+            out[f"frag_k{k}_{c}"] = frag[c].values
+    path = os.path.join(HERE, "ties_f20.npz")
+    np.savez_compressed(path, **out)
+    print(f"[ties_f20] wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)", flush=True)
+
+
 def run_classifier():
     """BinaryClassifierLegacyNewBatching of the unmodified reference (alphadia/fdr/classifiers.py:145-532), trained here on
     the CPU for three epochs: its state dict, inputs and predict_proba output -> tests/golden/classifier_small.npz."""
@@ -650,6 +689,8 @@ if __name__ == "__main__":
             run_fdr()
         elif n == "fdr_nan":
             run_fdr_nan()
+        elif n == "ties_f20":
+            run_ties_f20(threads)
         elif n == "perform_fdr":
             run_perform_fdr()
         elif n == "ragged":

@@ -191,6 +191,26 @@ def fdr_inputs(seed: int = 11, n: int = 6000):
     return df
 
 
+def tied_fragment_library(name: str = "parity_f20", seed: int = 31):
+    """``name``'s library with exact ties inside every precursor's fragment list (tests/golden/ties_f20.npz): three pairs of
+    fragments share their m/z (different type / position / number), and the library intensities are rounded to one decimal, so
+    that top-k by intensity has ties at its boundary.  With more than 15 fragments numba's argsort is a quicksort that is not
+    stable - the order of the tied fragments follows its partition steps."""
+    raw, pdf, fdf, lib, p = workload(name)
+    rng = np.random.default_rng(seed)
+    fdf = fdf.copy()
+    mz = fdf["mz_library"].to_numpy().copy()
+    inten = np.round(fdf["intensity"].to_numpy().astype(np.float64), 1).astype(np.float32)
+    inten[inten == 0] = 0.1
+    for s, e in zip(pdf["flat_frag_start_idx"].to_numpy(), pdf["flat_frag_stop_idx"].to_numpy()):
+        idx = rng.permutation(np.arange(int(s), int(e)))
+        for a, b in zip(idx[0:6:2], idx[1:6:2]):
+            mz[b] = mz[a]
+    fdf["mz_library"] = mz
+    fdf["intensity"] = inten
+    return raw, pdf.copy(), fdf, p
+
+
 def fdr_inputs_nan(seed: int = 12, n: int = 3000):
     """``fdr_inputs`` with missing values (tests/golden/fdr_nan.npz): NaN probabilities scattered over the table, every row
     of a few precursors NaN (a group without any finite score), +inf next to NaN inside one group, and a float group

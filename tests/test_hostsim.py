@@ -157,3 +157,20 @@ def test_hostsim_randomized_sweep(oracle_lib, seed):
         assert err == 0.0, f"seed {seed} case {it}: features differ (max rel {err:.3e})"
         compared += 1
     assert compared >= 4
+
+
+@pytest.mark.parametrize("k", [20, 16])
+def test_hostsim_tied_fragments(oracle_lib, k):
+    """The tie-heavy 20-fragment library of tests/golden/ties_f20.npz: the passes follow numba's quicksort order among tied
+    fragment m/z and intensities exactly as the oracle (which the golden pins against the live reference)."""
+    from alphadia_b200.library import assemble_library_arrays
+
+    raw, pdf, fdf, p = H.tied_fragment_library()
+    lib = assemble_library_arrays(pdf, fdf, "rt_library", "mobility_library", "mz_library", "mz_library")
+    g = H.load_golden("ties_f20")
+    cin, keep = H.candidates_in_from_arrays(lib, {c: g["cand_" + c] for c in INT_COLS})
+    cfg = H.scoring_config(top_k_fragments=k).to_struct()
+    ref = oracle_lib.score_candidates(raw, lib, cfg, cin)
+    got = hostsim.score_candidates(raw, lib, cfg, cin, batch=101, ks=k)
+    err, _ = assert_scores_close(got, ref, what=f"ties k={k}")
+    assert err == 0.0
